@@ -1,0 +1,625 @@
+// ORACLE (test infrastructure, NOT product code): CPU restatement of the MPEG Layer III synthesis
+// stage of pdeljanov/Symphonia @ ee35874.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference leg may build, load or call this file.
+//
+// PARITY PINNING: the Rust reference cannot be compiled here (no rustc/cargo, no network).  This
+// restatement is pinned against every known-answer vector the reference's own tests hold for
+// this path (tests/test_oracle_kat.py): dct32 (synthesis.rs:866-882), imdct36
+// (hybrid_synthesis.rs:802-822) and imdct12_win (hybrid_synthesis.rs:510-556), at the reference's
+// own 1e-5 tolerance against f64 analytical transforms.  Those pins are tolerance-level, not
+// bit-level: bit-level agreement with the Rust binary is by construction (same operations, same
+// order, one IEEE-754 rounding per operation, no FMA contraction: build with -ffp-contract=off).
+//
+// Every function cites the reference lines it restates.  Arithmetic order is preserved exactly;
+// control structure (recursion instead of hand-flattening, index tables instead of iterator
+// chains) is our own.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../include/symgpu.h"
+#include "mp3_iso_data.h"
+#include "oracle.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Tables (host libm, f64 then cast unless stated) -- §8a row T of SURVEY.md.
+// ------------------------------------------------------------------------------------------
+struct Mp3Tables {
+    float synth_d[512];       // synthesis.rs:13-142 (9-decimal literals -> f32)
+    float imdct_win[4][36];   // hybrid_synthesis.rs:53-92
+    float half_cos12[6][6];   // hybrid_synthesis.rs:105-119
+    float cs[8], ca[8];       // hybrid_synthesis.rs:136-149
+    float is_mpeg1[7][2];     // stereo.rs:105-121
+    float is_mpeg2[2][32][2]; // stereo.rs:59-81
+    float dct_iv_scale[18];   // hybrid_synthesis.rs:611-630   2cos(pi(2m+1)/72)
+    float sdct18_scale[9];    // hybrid_synthesis.rs:668-678   2cos(pi(2m+1)/36)
+    float sdct9_d[7];         // hybrid_synthesis.rs:722-730
+    float lee16[16], lee8[8], lee4[4], lee2[2], lee1; // synthesis.rs:354-396
+    Mp3Tables() {
+        const double PI = 3.14159265358979323846264338327950288;
+        for (int i = 0; i < 512; ++i) {
+            char txt[32];
+            std::snprintf(txt, sizeof txt, "%.9f", (double)kSynthWindowNum[i] / 65536.0);
+            synth_d[i] = std::strtof(txt, nullptr);
+        }
+        std::memset(imdct_win, 0, sizeof imdct_win);
+        const double pi36 = PI / 36.0, pi12 = PI / 12.0;
+        for (int i = 0; i < 36; ++i) imdct_win[0][i] = (float)std::sin(pi36 * ((double)i + 0.5));
+        for (int i = 0; i < 18; ++i) imdct_win[1][i] = (float)std::sin(pi36 * ((double)i + 0.5));
+        for (int i = 18; i < 24; ++i) imdct_win[1][i] = 1.0f;
+        for (int i = 24; i < 30; ++i) imdct_win[1][i] = (float)std::sin(pi12 * ((double)(i - 18) + 0.5));
+        for (int i = 0; i < 12; ++i) imdct_win[2][i] = (float)std::sin(pi12 * ((double)i + 0.5));
+        for (int i = 6; i < 12; ++i) imdct_win[3][i] = (float)std::sin(pi12 * ((double)(i - 6) + 0.5));
+        for (int i = 12; i < 18; ++i) imdct_win[3][i] = 1.0f;
+        for (int i = 18; i < 36; ++i) imdct_win[3][i] = (float)std::sin(pi36 * ((double)i + 0.5));
+        const double pi24 = PI / 24.0;
+        for (int i = 0; i < 6; ++i)
+            for (int k = 0; k < 6; ++k) {
+                const int n = (2 * (i + 3) + (12 / 2) + 1) * (2 * k + 1);
+                half_cos12[i][k] = (float)std::cos(pi24 * (double)n);
+            }
+        const double c[8] = {-0.6, -0.535, -0.33, -0.185, -0.095, -0.041, -0.0142, -0.0037};
+        for (int i = 0; i < 8; ++i) {
+            const double sq = std::sqrt(1.0 + c[i] * c[i]);
+            cs[i] = (float)(1.0 / sq);
+            ca[i] = (float)(c[i] / sq);
+        }
+        for (int p = 0; p < 7; ++p) {
+            const double r = std::tan(pi12 * (double)p);
+            is_mpeg1[p][0] = (float)(r / (1.0 + r));
+            is_mpeg1[p][1] = (float)(1.0 / (1.0 + r));
+        }
+        is_mpeg1[6][0] = 1.0f;
+        is_mpeg1[6][1] = 0.0f;
+        const double SQRT2 = 1.41421356237309504880168872420969808;
+        const double is_scale[2] = {1.0 / std::sqrt(SQRT2), 0.707106781186547524400844362104849039};
+        for (int p = 0; p < 32; ++p)
+            for (int s = 0; s < 2; ++s) {
+                if (p & 1) {
+                    is_mpeg2[s][p][0] = (float)std::pow(is_scale[s], (double)(p + 1) / 2.0);
+                    is_mpeg2[s][p][1] = 1.0f;
+                } else {
+                    is_mpeg2[s][p][0] = 1.0f;
+                    is_mpeg2[s][p][1] = (float)std::pow(is_scale[s], (double)p / 2.0);
+                }
+            }
+        for (int m = 0; m < 18; ++m) dct_iv_scale[m] = (float)(2.0 * std::cos(PI * (2 * m + 1) / 72.0));
+        for (int m = 0; m < 9; ++m) sdct18_scale[m] = (float)(2.0 * std::cos(PI * (2 * m + 1) / 36.0));
+        sdct18_scale[4] = 1.41421356237309504880168872420969808f; // f32::consts::SQRT_2
+        sdct9_d[0] = (float)(-std::sqrt(3.0));
+        sdct9_d[1] = (float)(-2.0 * std::cos(8.0 * PI / 9.0));
+        sdct9_d[2] = (float)(-2.0 * std::cos(4.0 * PI / 9.0));
+        sdct9_d[3] = (float)(-2.0 * std::cos(2.0 * PI / 9.0));
+        sdct9_d[4] = (float)(-2.0 * std::sin(8.0 * PI / 9.0));
+        sdct9_d[5] = (float)(-2.0 * std::sin(4.0 * PI / 9.0));
+        sdct9_d[6] = (float)(-2.0 * std::sin(2.0 * PI / 9.0));
+        // c[i] = 1 / (2 cos(pi (2i+1) / (2N))), N = 32,16,8,4,2 (synthesis.rs:349-353).
+        for (int i = 0; i < 16; ++i) lee16[i] = (float)(1.0 / (2.0 * std::cos(PI * (2 * i + 1) / 64.0)));
+        for (int i = 0; i < 8; ++i) lee8[i] = (float)(1.0 / (2.0 * std::cos(PI * (2 * i + 1) / 32.0)));
+        for (int i = 0; i < 4; ++i) lee4[i] = (float)(1.0 / (2.0 * std::cos(PI * (2 * i + 1) / 16.0)));
+        for (int i = 0; i < 2; ++i) lee2[i] = (float)(1.0 / (2.0 * std::cos(PI * (2 * i + 1) / 8.0)));
+        lee1 = 0.707106781186547524400844362104849039f;
+    }
+};
+
+const Mp3Tables& T() {
+    static const Mp3Tables t;
+    return t;
+}
+
+const float kFrac1Sqrt2 = 0.707106781186547524400844362104849039f; // f32::consts::FRAC_1_SQRT_2
+
+// ------------------------------------------------------------------------------------------
+// R1 requantize (layer3/requantize.rs:239-381)
+// ------------------------------------------------------------------------------------------
+struct Edges {
+    const uint16_t* e;
+    int n; // number of edges
+};
+
+void requant_long(const symgpu_mp3_gc& gc, Edges bands, float* buf) {
+    // requantize.rs:240-291.  Note the iteration pairs bands[i], bands[i+1] over the slice given.
+    const int a = (int)gc.global_gain - 210;
+    const int shift = (gc.flags & SYMGPU_MP3_F_SCALEFAC_SCALE) ? 2 : 1;
+    for (int i = 0; i + 1 < bands.n; ++i) {
+        const int start = bands.e[i], end = bands.e[i + 1];
+        if (start >= (int)gc.rzero) break;
+        const uint8_t pre = (gc.flags & SYMGPU_MP3_F_PREFLAG) ? kPreEmphasis[i] : 0;
+        const int b = (int)(uint8_t)((uint8_t)(gc.scalefacs[i] + pre) << shift);
+        const float pow2ab = (float)std::pow(2.0, 0.25 * (double)(a - b));
+        const int band_end = std::min(end, (int)gc.rzero);
+        for (int k = start; k < band_end; ++k) buf[k] *= pow2ab;
+    }
+}
+
+void requant_short(const symgpu_mp3_gc& gc, Edges bands, int sw, float* buf) {
+    // requantize.rs:294-355
+    const int gain = (int)gc.global_gain - 210;
+    const int a[3] = {gain - 8 * (int)gc.subblock_gain[0], gain - 8 * (int)gc.subblock_gain[1],
+                      gain - 8 * (int)gc.subblock_gain[2]};
+    const int shift = (gc.flags & SYMGPU_MP3_F_SCALEFAC_SCALE) ? 2 : 1;
+    for (int i = 0; i + 1 < bands.n; ++i) {
+        const int start = bands.e[i], end = bands.e[i + 1];
+        if (start >= (int)gc.rzero) break;
+        const int b = (int)(uint8_t)(gc.scalefacs[sw + i] << shift);
+        const float pow2ab = (float)std::pow(2.0, 0.25 * (double)(a[i % 3] - b));
+        const int win_end = std::min(end, (int)gc.rzero);
+        for (int k = start; k < win_end; ++k) buf[k] *= pow2ab;
+    }
+}
+
+bool is_short(const symgpu_mp3_gc& gc) { return gc.block_type == SYMGPU_MP3_SHORT; }
+bool is_mixed(const symgpu_mp3_gc& gc) { return is_short(gc) && (gc.flags & SYMGPU_MP3_F_MIXED); }
+
+void requantize(const symgpu_mp3_gc& gc, float* buf) {
+    // requantize.rs:358-381
+    const int sr = gc.sample_rate_idx;
+    if (is_short(gc) && !is_mixed(gc)) {
+        requant_short(gc, Edges{kShortEdges[sr], 40}, 0, buf);
+    } else if (is_mixed(gc)) {
+        const int sw = kMixedSwitch[sr];
+        requant_long(gc, Edges{kMixedEdges[sr], sw}, buf);
+        requant_short(gc, Edges{kMixedEdges[sr] + sw, kMixedCount[sr] - sw}, sw, buf);
+    } else {
+        requant_long(gc, Edges{kLongEdges[sr], 23}, buf);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// R2 joint stereo (layer3/stereo.rs)
+// ------------------------------------------------------------------------------------------
+void mid_side(float* m, float* s, int n) { // stereo.rs:143-152
+    for (int i = 0; i < n; ++i) {
+        const float l = (m[i] + s[i]) * kFrac1Sqrt2;
+        const float r = (m[i] - s[i]) * kFrac1Sqrt2;
+        m[i] = l;
+        s[i] = r;
+    }
+}
+
+struct IsTable {
+    const float (*ratio)[2];
+    uint8_t inv_pos;
+};
+
+void intensity(uint8_t pos, IsTable t, bool ms, float* ch0, float* ch1, int n) { // stereo.rs:168-188
+    if (pos < t.inv_pos) {
+        const float rl = t.ratio[pos][0], rr = t.ratio[pos][1];
+        for (int i = 0; i < n; ++i) {
+            const float is = ch0[i];
+            ch0[i] = rl * is;
+            ch1[i] = rr * is;
+        }
+    } else if (ms) {
+        mid_side(ch0, ch1, n);
+    }
+}
+
+bool zero_band(const float* b, int n) { // stereo.rs:191-194
+    for (int i = 0; i < n; ++i)
+        if (b[i] != 0.0f) return false;
+    return true;
+}
+
+IsTable pick_is_table(const symgpu_mp3_gc& gc1) { // stereo.rs:216-222, :342-348
+    if (gc1.flags & SYMGPU_MP3_F_MPEG1) return IsTable{T().is_mpeg1, 7};
+    const int s = (gc1.flags & SYMGPU_MP3_F_SFC_LSB) ? 1 : 0;
+    return IsTable{T().is_mpeg2[s], 31};
+}
+
+int intensity_long(const symgpu_mp3_gc& gc1, bool ms, int max_bound, float* ch0, float* ch1) {
+    // stereo.rs:198-261
+    const int rzero = gc1.rzero;
+    const IsTable t = pick_is_table(gc1);
+    const uint16_t* bands = kLongEdges[gc1.sample_rate_idx];
+    uint8_t pos[22];
+    std::memcpy(pos, gc1.scalefacs, 22);
+    pos[21] = pos[20];
+    int bound = max_bound;
+    for (int b = 21; b >= 0; --b) {
+        const int start = bands[b], end = bands[b + 1];
+        const bool z = start >= rzero || zero_band(ch1 + start, end - start);
+        if (!z) break;
+        intensity(pos[b], t, ms, ch0 + start, ch1 + start, end - start);
+        bound = start;
+    }
+    return bound;
+}
+
+int intensity_short(const symgpu_mp3_gc& gc1, bool mixed, bool ms, int max_bound, float* ch0, float* ch1) {
+    // stereo.rs:265-482
+    const int sr = gc1.sample_rate_idx;
+    const uint16_t* sb;  // short band edges
+    int n_sb;            // number of short edges
+    const uint16_t* lb = nullptr;
+    int n_lb = 0;
+    int sfi;
+    if (mixed) {
+        const int sw = kMixedSwitch[sr];
+        sb = kMixedEdges[sr] + sw;
+        n_sb = kMixedCount[sr] - sw;
+        lb = kMixedEdges[sr];
+        n_lb = sw + 1;
+        sfi = kMixedCount[sr] - 1;
+    } else {
+        sb = kShortEdges[sr];
+        n_sb = 40;
+        sfi = 39;
+    }
+    const IsTable t = pick_is_table(gc1);
+    uint8_t pos[39];
+    std::memcpy(pos, gc1.scalefacs, 36);
+    std::memcpy(pos + 36, gc1.scalefacs + 33, 3);
+
+    bool wz[3] = {true, true, true};
+    int bound = max_bound;
+    bool found = false;
+    // zip of 4 shifted iterators, step_by(3), reversed: quads start at 0,3,6,... while q+3 < n_sb.
+    const int n_quads = (n_sb - 3 + 2) / 3;
+    for (int q = n_quads - 1; q >= 0; --q) {
+        const int s0 = sb[3 * q], s1 = sb[3 * q + 1], s2 = sb[3 * q + 2], s3 = sb[3 * q + 3];
+        const int lo[3] = {s0, s1, s2}, hi[3] = {s1, s2, s3};
+        for (int w = 2; w >= 0; --w) {
+            wz[w] = wz[w] && zero_band(ch1 + lo[w], hi[w] - lo[w]);
+            if (wz[w])
+                intensity(pos[sfi - 1], t, ms, ch0 + lo[w], ch1 + lo[w], hi[w] - lo[w]);
+            else if (ms)
+                mid_side(ch0 + lo[w], ch1 + lo[w], hi[w] - lo[w]);
+            sfi -= 1;
+        }
+        bound = s0;
+        found = !wz[0] && !wz[1] && !wz[2];
+        if (found) break;
+    }
+    if (!found && lb) {
+        for (int b = n_lb - 2; b >= 0; --b) {
+            const int start = lb[b], end = lb[b + 1];
+            if (!zero_band(ch1 + start, end - start)) break;
+            intensity(pos[sfi - 1], t, ms, ch0 + start, ch1 + start, end - start);
+            sfi -= 1;
+            bound = start;
+        }
+    }
+    return bound;
+}
+
+// Returns false on the reference's "block_type mismatch" decode error (stereo.rs:503-505).
+bool stereo(symgpu_mp3_gc& g0, symgpu_mp3_gc& g1, float* ch0, float* ch1) {
+    // stereo.rs:485-556.  Frame flags are replicated in every unit; read them from channel 0.
+    const bool ms = g0.flags & SYMGPU_MP3_F_MID_SIDE;
+    const bool is = g0.flags & SYMGPU_MP3_F_INTENSITY;
+    if (!ms && !is) return true;
+    if (g0.block_type != g1.block_type || (is_short(g0) && is_mixed(g0) != is_mixed(g1))) return false;
+    const int end = std::max((int)g0.rzero, (int)g1.rzero);
+    int bound = end;
+    if (is) {
+        bound = is_short(g1) ? intensity_short(g1, is_mixed(g1), ms, end, ch0, ch1)
+                             : intensity_long(g1, ms, end, ch0, ch1);
+    }
+    if (ms && bound > 0) mid_side(ch0, ch1, bound);
+    g0.rzero = (uint16_t)end;
+    g1.rzero = (uint16_t)end;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// H1 reorder, H2 antialias (layer3/hybrid_synthesis.rs:153-277)
+// ------------------------------------------------------------------------------------------
+void reorder(symgpu_mp3_gc& gc, float* buf) { // :153-215
+    if (!is_short(gc)) return;
+    const int sr = gc.sample_rate_idx;
+    const uint16_t* bands;
+    int n;
+    if (is_mixed(gc)) {
+        const int sw = kMixedSwitch[sr];
+        bands = kMixedEdges[sr] + sw;
+        n = kMixedCount[sr] - sw;
+    } else {
+        bands = kShortEdges[sr];
+        n = 40;
+    }
+    float tmp[576] = {0};
+    const int start = bands[0];
+    int i = start;
+    for (int q = 0; q + 3 < n; q += 3) {
+        const int s0 = bands[q], s1 = bands[q + 1], s2 = bands[q + 2], s3 = bands[q + 3];
+        if (s0 >= (int)gc.rzero) break;
+        // zip() stops at the shortest window; the three windows have equal length in every table
+        // except the reference's 8 kHz mixed guess, so take the minimum explicitly.
+        const int len = std::min(std::min(s1 - s0, s2 - s1), s3 - s2);
+        for (int k = 0; k < len; ++k) {
+            tmp[i + 0] = buf[s0 + k];
+            tmp[i + 1] = buf[s1 + k];
+            tmp[i + 2] = buf[s2 + k];
+            i += 3;
+        }
+    }
+    std::memcpy(buf + start, tmp + start, sizeof(float) * (size_t)(i - start));
+    gc.rzero = (uint16_t)std::max((int)gc.rzero, i);
+}
+
+void antialias(symgpu_mp3_gc& gc, float* s) { // :218-277
+    int sb_limit;
+    if (is_short(gc))
+        if (is_mixed(gc)) sb_limit = 2; else return;
+    else
+        sb_limit = 32;
+    const float* cs = T().cs;
+    const float* ca = T().ca;
+    const int sb_rzero = gc.rzero / 18;
+    gc.rzero = (uint16_t)(18 * std::min(std::min(sb_limit, sb_rzero + 2), 32));
+    for (int sb = 18; sb < (int)gc.rzero; sb += 18)
+        for (int i = 0; i < 8; ++i) {
+            const int li = sb - 1 - i, ui = sb + i;
+            const float lower = s[li], upper = s[ui];
+            s[li] = lower * cs[i] - upper * ca[i];
+            s[ui] = upper * cs[i] + lower * ca[i];
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// H3 hybrid synthesis: IMDCT-36 (Szu-Wei Lee) / IMDCT-12 x3 (hybrid_synthesis.rs:280-455, :559-779)
+// ------------------------------------------------------------------------------------------
+void sdct_ii_9(const float* x, float* y /* stride 2 */) { // :721-779
+    const float* D = T().sdct9_d;
+    const float a01 = x[3] + x[5], a02 = x[3] - x[5], a03 = x[6] + x[2], a04 = x[6] - x[2];
+    const float a05 = x[1] + x[7], a06 = x[1] - x[7], a07 = x[8] + x[0], a08 = x[8] - x[0];
+    const float a09 = x[4] + a05, a10 = a01 + a03, a11 = a10 + a07, a12 = a03 - a07;
+    const float a13 = a01 - a07, a14 = a01 - a03, a15 = a02 - a04, a16 = a15 + a08;
+    const float a17 = a04 + a08, a18 = a02 - a08, a19 = a02 + a04, a20 = 2.0f * x[4] - a05;
+    const float m1 = D[0] * a06, m2 = D[1] * a12, m3 = D[2] * a13, m4 = D[3] * a14;
+    const float m5 = D[0] * a16, m6 = D[4] * a17, m7 = D[5] * a18, m8 = D[6] * a19;
+    const float a21 = a20 + m2, a22 = a20 - m2, a23 = a20 + m3, a24 = m1 + m6, a25 = m1 - m6, a26 = m1 + m7;
+    y[0] = a09 + a11;
+    y[2] = m8 - a26;
+    y[4] = m4 - a21;
+    y[6] = m5;
+    y[8] = a22 - m3;
+    y[10] = a25 - m7;
+    y[12] = a11 - 2.0f * a09;
+    y[14] = a24 + m8;
+    y[16] = a23 + m4;
+}
+
+void sdct_ii_18(const float* x, float* y) { // :665-716
+    const float* S = T().sdct18_scale;
+    float even[9], odd[9];
+    for (int i = 0; i < 9; ++i) even[i] = x[i] + x[17 - i];
+    sdct_ii_9(even, y);
+    for (int i = 0; i < 9; ++i) odd[i] = S[i] * (x[i] - x[17 - i]);
+    sdct_ii_9(odd, y + 1);
+    for (int i = 3; i <= 17; i += 2) y[i] -= y[i - 2];
+}
+
+void dct_iv_18(const float* x, float* y) { // :608-660
+    const float* S = T().dct_iv_scale;
+    float s[18];
+    for (int i = 0; i < 18; ++i) s[i] = S[i] * x[i];
+    sdct_ii_18(s, y);
+    y[0] /= 2.0f;
+    for (int i = 1; i < 18; ++i) y[i] = (y[i] / 2.0f) - y[i - 1];
+}
+
+void imdct36(float* x, const float* window, float* overlap) { // :571-603
+    float dct[18];
+    dct_iv_18(x, dct);
+    for (int i = 0; i < 9; ++i) x[i] = overlap[i] + dct[9 + i] * window[i];
+    for (int i = 9; i < 18; ++i) x[i] = overlap[i] - dct[27 - i - 1] * window[i];
+    for (int i = 18; i < 27; ++i) overlap[i - 18] = -dct[27 - i - 1] * window[i];
+    for (int i = 27; i < 36; ++i) overlap[i - 18] = -dct[i - 27] * window[i];
+}
+
+void imdct12_win(float* x, const float* window, float* overlap) { // :363-455
+    const float(*c)[6] = T().half_cos12;
+    float tmp[36] = {0};
+    for (int w = 0; w < 3; ++w)
+        for (int i = 0; i < 3; ++i) {
+            const float yl = (x[w] * c[i][0]) + (x[3 + w] * c[i][1]) + (x[6 + w] * c[i][2]) +
+                             (x[9 + w] * c[i][3]) + (x[12 + w] * c[i][4]) + (x[15 + w] * c[i][5]);
+            const float yr = (x[w] * c[i + 3][0]) + (x[3 + w] * c[i + 3][1]) + (x[6 + w] * c[i + 3][2]) +
+                             (x[9 + w] * c[i + 3][3]) + (x[12 + w] * c[i + 3][4]) + (x[15 + w] * c[i + 3][5]);
+            tmp[6 + 6 * w + 3 - i - 1] += -yl * window[3 - i - 1];
+            tmp[6 + 6 * w + i + 3] += yl * window[i + 3];
+            tmp[6 + 6 * w + i + 6] += yr * window[i + 6];
+            tmp[6 + 6 * w + 12 - i - 1] += yr * window[12 - i - 1];
+        }
+    for (int i = 0; i < 18; ++i) {
+        x[i] = tmp[i] + overlap[i];
+        overlap[i] = tmp[i + 18];
+    }
+}
+
+void hybrid_synthesis(const symgpu_mp3_gc& gc, float (*overlap)[18], float* s) { // :280-359
+    const int sb_limit = ((int)gc.rzero + 17) / 18;
+    const int sb_split = is_short(gc) ? (is_mixed(gc) ? 2 : 0) : 32;
+    if (sb_split > 0) {
+        const float* win = gc.block_type == SYMGPU_MP3_START ? T().imdct_win[1]
+                         : gc.block_type == SYMGPU_MP3_END   ? T().imdct_win[3]
+                                                             : T().imdct_win[0];
+        const int end = std::min(sb_split, sb_limit);
+        for (int sb = 0; sb < end; ++sb) imdct36(s + 18 * sb, win, overlap[sb]);
+    }
+    if (sb_split < 32) {
+        const int begin = std::min(sb_split, sb_limit);
+        for (int sb = begin; sb < sb_limit; ++sb) imdct12_win(s + 18 * sb, T().imdct_win[2], overlap[sb]);
+    }
+    for (int sb = sb_limit; sb < 32; ++sb) {
+        std::memcpy(s + 18 * sb, overlap[sb], sizeof(float) * 18);
+        for (int i = 0; i < 18; ++i) overlap[sb][i] = 0.0f;
+    }
+}
+
+void frequency_inversion(float* s) { // :458-485
+    for (int sb = 1; sb < 32; sb += 2)
+        for (int t = 1; t < 18; t += 2) s[18 * sb + t] = -s[18 * sb + t];
+}
+
+// ------------------------------------------------------------------------------------------
+// P1 dct32 (Lee, synthesis.rs:348-844) as the recursion the reference hand-flattens.
+// ------------------------------------------------------------------------------------------
+const float* lee_coef(int half) {
+    switch (half) {
+        case 16: return T().lee16;
+        case 8: return T().lee8;
+        case 4: return T().lee4;
+        case 2: return T().lee2;
+        default: return &T().lee1;
+    }
+}
+
+void lee_dct(const float* x, float* y, int n) {
+    if (n == 2) { // synthesis.rs:479
+        y[0] = x[0] + x[1];
+        y[1] = (x[0] - x[1]) * T().lee1;
+        return;
+    }
+    const int h = n / 2;
+    const float* c = lee_coef(h);
+    float lo[16], hi[16], lo_t[16], hi_t[16];
+    for (int i = 0; i < h; ++i) {
+        lo[i] = x[i] + x[n - 1 - i];
+        hi[i] = (x[i] - x[n - 1 - i]) * c[i];
+    }
+    lee_dct(lo, lo_t, h);
+    lee_dct(hi, hi_t, h);
+    for (int i = 0; i < h - 1; ++i) {
+        y[2 * i] = lo_t[i];
+        y[2 * i + 1] = hi_t[i] + hi_t[i + 1];
+    }
+    y[n - 2] = lo_t[h - 1];
+    y[n - 1] = hi_t[h - 1];
+}
+
+// ------------------------------------------------------------------------------------------
+// P2 polyphase synthesis (synthesis.rs:158-336), with the reference's literal v_vec FIFO.
+// ------------------------------------------------------------------------------------------
+void polyphase(oracle_mp3_state* st, int ch, int n_slots, const float* in, float* out) {
+    const float* D = T().synth_d;
+    for (int b = 0; b < n_slots; ++b) {
+        float s[32], d[32];
+        for (int i = 0; i < 32; ++i) s[i] = in[n_slots * i + b];
+        float* v = st->v_vec[ch][st->v_front[ch]];
+        lee_dct(s, d, 32);
+        for (int k = 1; k < 16; ++k) { // :247-258
+            v[48 - k] = -d[k];
+            v[48 + k] = -d[k];
+            v[32 - k] = -d[16 + k];
+            v[k] = d[16 + k];
+        }
+        v[0] = d[16];
+        v[32] = -d[16];
+        v[48] = -d[0];
+        v[16] = 0.0f;
+        float o[32];
+        for (int i = 0; i < 32; ++i) o[i] = 0.0f;
+        for (int j = 0; j < 8; ++j) { // :311-323
+            const int v_start = st->v_front[ch] + (j << 1);
+            const float* v0 = st->v_vec[ch][(v_start + 0) & 0xf];
+            const float* v1 = st->v_vec[ch][(v_start + 1) & 0xf] + 32;
+            const int k = j << 6;
+            for (int i = 0; i < 32; ++i) {
+                o[i] += v0[i] * D[k + i];
+                o[i] += v1[i] * D[k + i + 32];
+            }
+        }
+        std::memcpy(out + (b << 5), o, sizeof o);
+        st->v_front[ch] = (st->v_front[ch] + 15) & 0xf;
+    }
+}
+
+} // namespace
+
+// ==========================================================================================
+// extern "C" surface used by tests / bench (see oracle.h)
+// ==========================================================================================
+extern "C" {
+
+void oracle_mp3_state_reset(oracle_mp3_state* st) { std::memset(st, 0, sizeof *st); }
+
+// O1: Layer3::decode granule loop (layer3/mod.rs:421-477) for one frame.
+//   units   [2][2]       (modified in place exactly as the reference mutates rzero)
+//   spectra [2][2][576]  (in: read_huffman_samples output; out: scratch)
+//   pcm     [2][1152]
+// returns 0, or 1 for the reference's decode_error (stereo block_type mismatch).
+int oracle_mp3_frame(oracle_mp3_state* st, symgpu_mp3_gc* units, float* spectra, float* pcm) {
+    const int n_gr = (units[0].flags & SYMGPU_MP3_F_MPEG1) ? 2 : 1;
+    const int n_ch = (units[1].flags & SYMGPU_MP3_F_MUTE) ? 1 : 2;
+    for (int gr = 0; gr < n_gr; ++gr) {
+        symgpu_mp3_gc* g = units + 2 * gr;
+        float* s0 = spectra + (2 * gr + 0) * 576;
+        float* s1 = spectra + (2 * gr + 1) * 576;
+        requantize(g[0], s0);
+        if (n_ch == 2) {
+            requantize(g[1], s1);
+            if (!stereo(g[0], g[1], s0, s1)) return 1;
+        }
+        for (int ch = 0; ch < n_ch; ++ch) {
+            float* s = ch ? s1 : s0;
+            reorder(g[ch], s);
+            antialias(g[ch], s);
+            hybrid_synthesis(g[ch], st->overlap[ch], s);
+            frequency_inversion(s);
+            polyphase(st, ch, 18, s, pcm + ch * 1152 + gr * 576);
+        }
+    }
+    return 0;
+}
+
+// A whole batch: the same contract as symgpu_mp3_synth_host (include/symgpu.h).
+int oracle_mp3_batch(oracle_mp3_state* states, const symgpu_mp3_gc* units, const float* spectra,
+                     const symgpu_mp3_run* runs, uint32_t n_runs, float* pcm) {
+    int rc = 0;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        oracle_mp3_state* st = states + runs[r].stream;
+        for (uint32_t f = runs[r].first_frame; f < runs[r].first_frame + runs[r].n_frames; ++f) {
+            symgpu_mp3_gc u[4];
+            float s[SYMGPU_MP3_FRAME_FLOATS];
+            std::memcpy(u, units + 4 * (size_t)f, sizeof u);
+            std::memcpy(s, spectra + (size_t)f * SYMGPU_MP3_FRAME_FLOATS, sizeof s);
+            rc |= oracle_mp3_frame(st, u, s, pcm + (size_t)f * SYMGPU_MP3_FRAME_FLOATS);
+        }
+    }
+    return rc;
+}
+
+// Building blocks exposed for the known-answer tests.
+void oracle_mp3_dct32(const float* x, float* y) { lee_dct(x, y, 32); }
+void oracle_mp3_imdct36(float* x, const float* window, float* overlap) { imdct36(x, window, overlap); }
+void oracle_mp3_imdct12_win(float* x, const float* window, float* overlap) { imdct12_win(x, window, overlap); }
+void oracle_mp3_polyphase(oracle_mp3_state* st, int ch, int n_slots, const float* in, float* out) {
+    polyphase(st, ch, n_slots, in, out);
+}
+const float* oracle_mp3_imdct_window(int which) { return T().imdct_win[which]; }
+float oracle_mp3_pow43(int i) { return std::pow((float)i, 4.0f / 3.0f); } // requantize.rs:29 (f32 powf)
+
+// Flat copy of the constant tables in the product's blob order (see symphonia_b200/csrc/tables.h).
+size_t oracle_mp3_tables(float* out, size_t cap_floats) {
+    const Mp3Tables& t = T();
+    float buf[2048];
+    size_t n = 0;
+    auto put = [&](const float* p, size_t k) { std::memcpy(buf + n, p, k * sizeof(float)); n += k; };
+    put(t.synth_d, 512);
+    put(&t.imdct_win[0][0], 144);
+    put(&t.half_cos12[0][0], 36);
+    put(t.cs, 8);
+    put(t.ca, 8);
+    put(&t.is_mpeg1[0][0], 14);
+    put(&t.is_mpeg2[0][0][0], 128);
+    put(t.dct_iv_scale, 18);
+    put(t.sdct18_scale, 9);
+    put(t.sdct9_d, 7);
+    put(t.lee16, 16);
+    put(t.lee8, 8);
+    put(t.lee4, 4);
+    put(t.lee2, 2);
+    put(&t.lee1, 1);
+    if (out && cap_floats >= n) std::memcpy(out, buf, n * sizeof(float));
+    return n;
+}
+
+} // extern "C"

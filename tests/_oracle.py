@@ -1,0 +1,65 @@
+"""Loader for liboracle.so (ORACLE = test infrastructure; never imported by the product).
+
+Builds it with oracle/Makefile when the prebuilt file is missing (gcc is present both in the build
+container and on the GPU box).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+class Mp3State(ctypes.Structure):
+    _fields_ = [("overlap", ctypes.c_float * (2 * 32 * 18)),
+                ("v_vec", ctypes.c_float * (2 * 16 * 64)),
+                ("v_front", ctypes.c_int32 * 2)]
+
+
+def build(arch=None, out=None):
+    cmd = ["make", "-C", ODIR, "-s"]
+    if arch:
+        cmd.append("ARCH=" + arch)
+    if out:
+        cmd.append("OUT=" + out)
+    subprocess.check_call(cmd)
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def load(path=None):
+    path = path or os.path.join(ODIR, "_build", "liboracle.so")
+    if not os.path.exists(path):
+        build()
+    lib = ctypes.CDLL(path)
+    lib.oracle_mp3_tables.restype = ctypes.c_size_t
+    lib.oracle_mp3_tables.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    lib.oracle_mp3_pow43.restype = ctypes.c_float
+    lib.oracle_mp3_imdct_window.restype = c_f32p
+    lib.oracle_mp3_batch.restype = ctypes.c_int
+    lib.oracle_mp3_batch.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_void_p]
+    lib.oracle_mp3_frame.restype = ctypes.c_int
+    lib.oracle_mp3_frame.argtypes = [ctypes.c_void_p] * 4
+    lib.oracle_mp3_polyphase.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_void_p]
+    return lib
+
+
+def mp3_batch(lib, units, spectra, runs, n_streams):
+    """Runs the oracle over a batch laid out as symgpu_mp3_synth_host expects; fresh stream state."""
+    n_frames = spectra.shape[0]
+    states = (Mp3State * n_streams)()
+    pcm = np.zeros((n_frames, 2, 1152), dtype=np.float32)
+    units = np.ascontiguousarray(units)
+    spectra = np.ascontiguousarray(spectra, dtype=np.float32)
+    runs = np.ascontiguousarray(runs)
+    rc = lib.oracle_mp3_batch(ctypes.byref(states), ptr(units), ptr(spectra), ptr(runs),
+                              ctypes.c_uint32(len(runs)), ptr(pcm))
+    return rc, pcm, states
