@@ -116,11 +116,18 @@ typedef struct symgpu_mp3_run {
     uint32_t stream;
     uint32_t first_frame;
     uint32_t n_frames;
-    uint32_t reserved;
+    uint8_t granules_per_frame; /* 2 = MPEG-1, 1 = MPEG-2 / 2.5 (header.n_granules()); 0 means 2 */
+    uint8_t channels;           /* 1 or 2 (header.n_channels()); 0 means 2                      */
+    uint16_t reserved;          /* must be zero                                                  */
 } symgpu_mp3_run;
 
 #define SYMGPU_MP3_LINES 576
 #define SYMGPU_MP3_FRAME_FLOATS (2 * 2 * 576) /* spectra [gr][ch][576]; pcm [ch][gr*576 + i]  */
+
+/* POW43[x] = f32 powf(x, 4/3) for x in 0..8206 (requantize.rs:23-32): the magnitude the CPU
+ * Huffman stage writes for quantised value x (requantize.rs:128, :144).  Host libm, no GPU
+ * needed.  Returns the table length (8207); copies min(cap, 8207) floats when `out` != NULL. */
+size_t symgpu_mp3_pow43(float* out, size_t cap);
 
 /* Allocates / zeroes device state for `n_streams` MP3 streams (Layer3::new, mod.rs:262-269). */
 symgpu_status symgpu_mp3_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams);
@@ -130,7 +137,7 @@ symgpu_status symgpu_mp3_stream_reset(symgpu_ctx* ctx, uint32_t stream);
 /* Synthesises a batch of `n_frames` frames.
  *   units   [n_frames][2][2]      symgpu_mp3_gc
  *   spectra [n_frames][2][2][576] f32, values as left by read_huffman_samples
- *   runs    [n_runs]              frames of one stream are consecutive and in decode order; runs
+ *   runs    [n_runs]  (host)      frames of one stream are consecutive and in decode order; runs
  *                                 must tile [0, n_frames) without overlap and no stream may
  *                                 appear in two runs of the same call
  *   pcm     [n_frames][2][1152]   f32 planar per frame: plane(ch)[gr*576 .. gr*576+576]
@@ -138,7 +145,9 @@ symgpu_status symgpu_mp3_stream_reset(symgpu_ctx* ctx, uint32_t stream);
 symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
                                     const float* spectra, const symgpu_mp3_run* runs,
                                     uint32_t n_runs, uint32_t n_frames, float* pcm);
-/* Device variant: all four pointers are device memory; asynchronous on the context stream. */
+/* Device variant: `units`, `spectra` and `pcm` are device memory already resident in HBM; `runs`
+ * is HOST memory (control plane: the library cuts runs into per-CTA tiles on the host).
+ * Asynchronous on the context stream; call symgpu_sync() before reading `pcm`. */
 symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
                                    const float* spectra, const symgpu_mp3_run* runs,
                                    uint32_t n_runs, uint32_t n_frames, float* pcm);

@@ -546,9 +546,7 @@ void oracle_mp3_state_reset(oracle_mp3_state* st) { std::memset(st, 0, sizeof *s
 //   spectra [2][2][576]  (in: read_huffman_samples output; out: scratch)
 //   pcm     [2][1152]
 // returns 0, or 1 for the reference's decode_error (stereo block_type mismatch).
-int oracle_mp3_frame(oracle_mp3_state* st, symgpu_mp3_gc* units, float* spectra, float* pcm) {
-    const int n_gr = (units[0].flags & SYMGPU_MP3_F_MPEG1) ? 2 : 1;
-    const int n_ch = (units[1].flags & SYMGPU_MP3_F_MUTE) ? 1 : 2;
+int oracle_mp3_frame(oracle_mp3_state* st, symgpu_mp3_gc* units, float* spectra, float* pcm, int n_gr, int n_ch) {
     for (int gr = 0; gr < n_gr; ++gr) {
         symgpu_mp3_gc* g = units + 2 * gr;
         float* s0 = spectra + (2 * gr + 0) * 576;
@@ -581,7 +579,9 @@ int oracle_mp3_batch(oracle_mp3_state* states, const symgpu_mp3_gc* units, const
             float s[SYMGPU_MP3_FRAME_FLOATS];
             std::memcpy(u, units + 4 * (size_t)f, sizeof u);
             std::memcpy(s, spectra + (size_t)f * SYMGPU_MP3_FRAME_FLOATS, sizeof s);
-            rc |= oracle_mp3_frame(st, u, s, pcm + (size_t)f * SYMGPU_MP3_FRAME_FLOATS);
+            rc |= oracle_mp3_frame(st, u, s, pcm + (size_t)f * SYMGPU_MP3_FRAME_FLOATS,
+                                   runs[r].granules_per_frame ? runs[r].granules_per_frame : 2,
+                                   runs[r].channels ? runs[r].channels : 2);
         }
     }
     return rc;

@@ -1,0 +1,86 @@
+"""ctypes binding of libsymgpu.so (the in-tree build; never a site-packages copy)."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsymgpu.so")
+
+
+# numpy mirror of `symgpu_mp3_gc` (include/symgpu.h), 64 bytes
+MP3_GC_DTYPE = np.dtype([
+    ("rzero", "<u2"), ("global_gain", "u1"), ("block_type", "u1"), ("flags", "u1"),
+    ("sample_rate_idx", "u1"), ("subblock_gain", "u1", (3,)), ("scalefacs", "u1", (39,)),
+    ("reserved", "u1", (16,)),
+])
+assert MP3_GC_DTYPE.itemsize == 64
+# `symgpu_mp3_run`, 16 bytes
+MP3_RUN_DTYPE = np.dtype([
+    ("stream", "<u4"), ("first_frame", "<u4"), ("n_frames", "<u4"),
+    ("granules_per_frame", "u1"), ("channels", "u1"), ("reserved", "<u2"),
+])
+assert MP3_RUN_DTYPE.itemsize == 16
+
+MP3_LONG, MP3_START, MP3_SHORT, MP3_END = 0, 1, 2, 3
+F_MIXED, F_SCALEFAC_SCALE, F_PREFLAG, F_SFC_LSB = 1, 2, 4, 8
+F_MID_SIDE, F_INTENSITY, F_MPEG1, F_MUTE = 16, 32, 64, 128
+
+
+def lib():
+    """Loads the library; raises NativeLibraryMissing (never falls back to anything)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise NativeLibraryMissing(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C symphonia_b200/csrc`). There is no CPU fallback.")
+    L = ctypes.CDLL(path)
+    vp, u32, sz = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_size_t
+    L.symgpu_abi_version.restype = ctypes.c_int
+    L.symgpu_strerror.restype = ctypes.c_char_p
+    L.symgpu_strerror.argtypes = [ctypes.c_int]
+    L.symgpu_last_cuda_error.restype = ctypes.c_char_p
+    L.symgpu_last_cuda_error.argtypes = [vp]
+    L.symgpu_ctx_create.restype = ctypes.c_int
+    L.symgpu_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.symgpu_ctx_destroy.restype = None
+    L.symgpu_ctx_destroy.argtypes = [vp]
+    L.symgpu_tables_host_blob.restype = sz
+    L.symgpu_tables_host_blob.argtypes = [vp, sz]
+    L.symgpu_tables_upload.restype = ctypes.c_int
+    L.symgpu_tables_upload.argtypes = [vp, vp, sz]
+    L.symgpu_sync.restype = ctypes.c_int
+    L.symgpu_sync.argtypes = [vp]
+    L.symgpu_cuda_stream.restype = vp
+    L.symgpu_cuda_stream.argtypes = [vp]
+    L.symgpu_launch_count.restype = ctypes.c_uint64
+    L.symgpu_launch_count.argtypes = [vp]
+    L.symgpu_mp3_pow43.restype = sz
+    L.symgpu_mp3_pow43.argtypes = [vp, sz]
+    L.symgpu_mp3_streams_alloc.restype = ctypes.c_int
+    L.symgpu_mp3_streams_alloc.argtypes = [vp, u32]
+    L.symgpu_mp3_stream_reset.restype = ctypes.c_int
+    L.symgpu_mp3_stream_reset.argtypes = [vp, u32]
+    for name in ("symgpu_mp3_synth_host", "symgpu_mp3_synth_dev"):
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [vp, vp, vp, vp, u32, u32, vp]
+    _LIB = L
+    return L
+
+
+def mp3_pow43():
+    out = np.zeros(8207, dtype=np.float32)
+    lib().symgpu_mp3_pow43(out.ctypes.data_as(ctypes.c_void_p), 8207)
+    return out

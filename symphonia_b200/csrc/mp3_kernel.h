@@ -1,0 +1,56 @@
+// Host <-> kernel interface of the fused MP3 synthesis kernel (mp3_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/symgpu.h"
+#include "tables.h"
+
+namespace symgpu {
+
+// Granules per tile and warps per CTA.  15 granules = 270 time slots; with the 15-slot history the
+// DCT phase has 285 slot-jobs for 288 threads, and the 17 granule jobs (15 + 2 halo) take two
+// rounds of 9 warps.  Shared memory: 17 regions x 4752 B + scratch = 88 KB -> 2 CTAs / SM.
+constexpr int kMp3TileGranules = 15;
+constexpr int kMp3Warps = 9;
+
+enum : uint8_t { kTileLoadState = 1, kTileStoreState = 2 };
+
+// One CTA's work: `n_granules` consecutive granules of one stream.  Built on the host from the
+// caller's runs (symgpu.cpp: build_tiles).
+struct Mp3Tile {
+    uint32_t first_frame; // batch frame index holding the tile's first granule
+    uint32_t stream;      // per-stream state slot
+    uint16_t first_gr;    // granule-in-frame of the tile's first granule
+    uint16_t n_granules;  // 1..kMp3TileGranules
+    uint8_t gpf;          // granules per frame: 2 (MPEG-1) or 1 (MPEG-2 / 2.5)
+    uint8_t n_ch;         // 1 or 2
+    uint8_t flags;        // kTileLoadState | kTileStoreState
+    uint8_t pad;
+};
+static_assert(sizeof(Mp3Tile) == 16, "Mp3Tile is 16 bytes");
+
+// Persistent per-stream state in HBM: what Layer3.overlap and Layer3.synthesis hold in the
+// reference (layer3/mod.rs:254-259, synthesis.rs:145-154), in feed-forward form: instead of the
+// 16x64 v_vec FIFO we keep the last 15 DCT-32 output vectors (both channels interleaved), from
+// which every FIFO entry the next 15 slots can read is a copy or a negation.
+struct Mp3StreamState {
+    float overlap[2][32][18];
+    float2 dhist[15][32];
+};
+
+struct Mp3Args {
+    const symgpu_mp3_gc* units;
+    const float* spectra;
+    float* pcm;
+    const Mp3Tile* tiles;
+    Mp3StreamState* states;
+    const Mp3Tables* tab;
+};
+
+cudaError_t mp3_upload_const(const Mp3Tables& t, cudaStream_t stream);
+cudaError_t mp3_launch(const Mp3Args& a, int n_tiles, cudaStream_t stream);
+int mp3_tile_granules();
+
+} // namespace symgpu

@@ -1,0 +1,303 @@
+// libsymgpu.so -- implementation of the C ABI in include/symgpu.h.
+//
+// There is deliberately no CPU implementation of the synthesis path in this library: every entry
+// point that produces PCM launches the CUDA kernels, and context creation fails loudly when no
+// CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/symgpu.h"
+#include "mp3_kernel.h"
+#include "tables.h"
+
+using namespace symgpu;
+
+struct symgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char cuda_err[256] = {0};
+    uint64_t launches = 0;
+    // tables
+    Mp3Tables* d_mp3_tab = nullptr;
+    // MP3 streams
+    Mp3StreamState* d_mp3_states = nullptr;
+    uint32_t n_mp3_streams = 0;
+    // tile list (host staging is pinned; cached while the caller repeats the same runs)
+    Mp3Tile* d_tiles = nullptr;
+    Mp3Tile* h_tiles = nullptr;
+    size_t tiles_cap = 0;
+    std::vector<symgpu_mp3_run> cached_runs;
+    uint32_t cached_frames = 0;
+    int cached_tiles = 0;
+    // staging for the host entry point
+    void* d_stage = nullptr;
+    size_t stage_cap = 0;
+};
+
+namespace {
+
+symgpu_status cuda_fail(symgpu_ctx* ctx, cudaError_t e, const char* where) {
+    if (ctx) std::snprintf(ctx->cuda_err, sizeof ctx->cuda_err, "%s: %s", where, cudaGetErrorString(e));
+    return SYMGPU_ERR_CUDA;
+}
+
+#define CU(ctx, call)                                                   \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return cuda_fail((ctx), e_, #call);      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Cuts the caller's runs into per-CTA tiles (mp3_kernel.h).  Returns SYMGPU_OK or an argument /
+// limit error; never touches the device.
+symgpu_status build_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
+                          std::vector<Mp3Tile>& out) {
+    const int T = mp3_tile_granules();
+    uint64_t covered = 0;
+    out.clear();
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_mp3_run& run = runs[r];
+        const int gpf = run.granules_per_frame ? run.granules_per_frame : 2;
+        const int n_ch = run.channels ? run.channels : 2;
+        if (gpf < 1 || gpf > 2 || n_ch < 1 || n_ch > 2 || run.reserved != 0) return SYMGPU_ERR_ARG;
+        if (run.n_frames == 0) continue;
+        if ((uint64_t)run.first_frame + run.n_frames > n_frames) return SYMGPU_ERR_ARG;
+        if (run.stream >= ctx->n_mp3_streams) return SYMGPU_ERR_LIMIT;
+        covered += run.n_frames;
+        const uint32_t n_gran = run.n_frames * (uint32_t)gpf;
+        for (uint32_t q0 = 0; q0 < n_gran; q0 += (uint32_t)T) {
+            Mp3Tile t{};
+            t.first_frame = run.first_frame + q0 / (uint32_t)gpf;
+            t.first_gr = (uint16_t)(q0 % (uint32_t)gpf);
+            t.stream = run.stream;
+            t.n_granules = (uint16_t)((n_gran - q0 < (uint32_t)T) ? n_gran - q0 : (uint32_t)T);
+            t.gpf = (uint8_t)gpf;
+            t.n_ch = (uint8_t)n_ch;
+            t.flags = (uint8_t)((q0 == 0 ? kTileLoadState : 0) | (q0 + t.n_granules == n_gran ? kTileStoreState : 0));
+            out.push_back(t);
+        }
+    }
+    if (covered != n_frames) return SYMGPU_ERR_ARG; // runs must tile the batch exactly
+    return SYMGPU_OK;
+}
+
+symgpu_status ensure_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, int* n_tiles) {
+    if (ctx->cached_frames == n_frames && ctx->cached_runs.size() == n_runs &&
+        (n_runs == 0 || std::memcmp(ctx->cached_runs.data(), runs, n_runs * sizeof *runs) == 0)) {
+        *n_tiles = ctx->cached_tiles;
+        return SYMGPU_OK;
+    }
+    std::vector<Mp3Tile> tiles;
+    symgpu_status s = build_tiles(ctx, runs, n_runs, n_frames, tiles);
+    if (s != SYMGPU_OK) return s;
+    if (tiles.size() > ctx->tiles_cap) {
+        // the previous launch may still be reading the old list
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+        if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
+        ctx->d_tiles = nullptr;
+        ctx->h_tiles = nullptr;
+        ctx->tiles_cap = 0;
+        const size_t cap = tiles.size() + tiles.size() / 2 + 64;
+        CU(ctx, cudaMalloc(&ctx->d_tiles, cap * sizeof(Mp3Tile)));
+        CU(ctx, cudaMallocHost(&ctx->h_tiles, cap * sizeof(Mp3Tile)));
+        ctx->tiles_cap = cap;
+    } else {
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // h_tiles is about to be rewritten
+    }
+    if (!tiles.empty()) {
+        std::memcpy(ctx->h_tiles, tiles.data(), tiles.size() * sizeof(Mp3Tile));
+        CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->cached_runs.assign(runs, runs + n_runs);
+    ctx->cached_frames = n_frames;
+    ctx->cached_tiles = (int)tiles.size();
+    *n_tiles = ctx->cached_tiles;
+    return SYMGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int symgpu_abi_version(void) { return SYMGPU_ABI_VERSION; }
+
+const char* symgpu_strerror(symgpu_status status) {
+    switch (status) {
+        case SYMGPU_OK: return "ok";
+        case SYMGPU_ERR_DECODE: return "symgpu: malformed synthesis unit";
+        case SYMGPU_ERR_UNSUPPORTED: return "symgpu: unsupported stream configuration";
+        case SYMGPU_ERR_LIMIT: return "symgpu: batch or stream limit exceeded";
+        case SYMGPU_ERR_RESET: return "symgpu: decoder reset required";
+        case SYMGPU_ERR_CUDA: return "symgpu: CUDA failure (see symgpu_last_cuda_error)";
+        case SYMGPU_ERR_ARG: return "symgpu: invalid argument";
+    }
+    return "symgpu: unknown status";
+}
+
+const char* symgpu_last_cuda_error(const symgpu_ctx* ctx) { return ctx ? ctx->cuda_err : ""; }
+
+size_t symgpu_tables_host_blob(void* out, size_t cap) {
+    const Mp3Tables& t = mp3_tables_host();
+    if (out && cap >= sizeof t) std::memcpy(out, &t, sizeof t);
+    return sizeof t;
+}
+
+size_t symgpu_mp3_pow43(float* out, size_t cap) {
+    const Mp3Tables& t = mp3_tables_host();
+    if (out) std::memcpy(out, t.pow43, sizeof(float) * (cap < 8207 ? cap : 8207));
+    return 8207;
+}
+
+symgpu_status symgpu_tables_upload(symgpu_ctx* ctx, const void* blob, size_t bytes) {
+    if (!ctx || !blob || bytes != sizeof(Mp3Tables)) return SYMGPU_ERR_ARG;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMemcpy(ctx->d_mp3_tab, blob, bytes, cudaMemcpyHostToDevice));
+    CU(ctx, mp3_upload_const(*static_cast<const Mp3Tables*>(blob), ctx->stream));
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
+    if (!out) return SYMGPU_ERR_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || device < 0 || device >= n_dev) {
+        std::fprintf(stderr, "symgpu: no usable CUDA device %d (%s); this library has no CPU path\n", device,
+                     e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range");
+        return SYMGPU_ERR_CUDA;
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        std::fprintf(stderr, "symgpu: device %d is not sm_100-class; kernels are built for sm_100a only\n", device);
+        return SYMGPU_ERR_UNSUPPORTED;
+    }
+    symgpu_ctx* ctx = new (std::nothrow) symgpu_ctx();
+    if (!ctx) return SYMGPU_ERR_LIMIT;
+    ctx->device = device;
+    DeviceGuard guard(device);
+    auto fail = [&](cudaError_t err, const char* where) {
+        std::fprintf(stderr, "symgpu: %s failed: %s\n", where, cudaGetErrorString(err));
+        symgpu_ctx_destroy(ctx);
+        return SYMGPU_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaMalloc(&ctx->d_mp3_tab, sizeof(Mp3Tables))) != cudaSuccess) return fail(e, "cudaMalloc(tables)");
+    const Mp3Tables& t = mp3_tables_host();
+    if ((e = cudaMemcpy(ctx->d_mp3_tab, &t, sizeof t, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy(tables)");
+    if ((e = mp3_upload_const(t, ctx->stream)) != cudaSuccess) return fail(e, "cudaMemcpyToSymbol(tables)");
+    *out = ctx;
+    return SYMGPU_OK;
+}
+
+void symgpu_ctx_destroy(symgpu_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_mp3_tab) cudaFree(ctx->d_mp3_tab);
+    if (ctx->d_mp3_states) cudaFree(ctx->d_mp3_states);
+    if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+    if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+symgpu_status symgpu_sync(symgpu_ctx* ctx) {
+    if (!ctx) return SYMGPU_ERR_ARG;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SYMGPU_OK;
+}
+
+void* symgpu_cuda_stream(symgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t symgpu_launch_count(const symgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+symgpu_status symgpu_mp3_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams) {
+    if (!ctx || n_streams == 0) return SYMGPU_ERR_ARG;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_mp3_states) cudaFree(ctx->d_mp3_states);
+    ctx->d_mp3_states = nullptr;
+    ctx->n_mp3_streams = 0;
+    ctx->cached_runs.clear();
+    ctx->cached_frames = 0;
+    CU(ctx, cudaMalloc(&ctx->d_mp3_states, (size_t)n_streams * sizeof(Mp3StreamState)));
+    CU(ctx, cudaMemset(ctx->d_mp3_states, 0, (size_t)n_streams * sizeof(Mp3StreamState)));
+    ctx->n_mp3_streams = n_streams;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_mp3_stream_reset(symgpu_ctx* ctx, uint32_t stream) {
+    if (!ctx) return SYMGPU_ERR_ARG;
+    if (stream >= ctx->n_mp3_streams) return SYMGPU_ERR_LIMIT;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaMemsetAsync(ctx->d_mp3_states + stream, 0, sizeof(Mp3StreamState), ctx->stream));
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
+                                   const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, float* pcm) {
+    if (!ctx || !units || !spectra || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (n_frames == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    int n_tiles = 0;
+    symgpu_status s = ensure_tiles(ctx, runs, n_runs, n_frames, &n_tiles);
+    if (s != SYMGPU_OK) return s;
+    Mp3Args a{units, spectra, pcm, ctx->d_tiles, ctx->d_mp3_states, ctx->d_mp3_tab};
+    CU(ctx, mp3_launch(a, n_tiles, ctx->stream));
+    ctx->launches += 1;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
+                                    const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, float* pcm) {
+    if (!ctx || !units || !spectra || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (n_frames == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    const size_t unit_bytes = (size_t)n_frames * 4 * sizeof(symgpu_mp3_gc);
+    const size_t spec_bytes = (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
+    const size_t need = unit_bytes + 2 * spec_bytes;
+    if (need > ctx->stage_cap) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_stage) cudaFree(ctx->d_stage);
+        ctx->d_stage = nullptr;
+        ctx->stage_cap = 0;
+        CU(ctx, cudaMalloc(&ctx->d_stage, need));
+        ctx->stage_cap = need;
+    }
+    char* base = static_cast<char*>(ctx->d_stage);
+    float* d_spec = reinterpret_cast<float*>(base);
+    float* d_pcm = reinterpret_cast<float*>(base + spec_bytes);
+    symgpu_mp3_gc* d_units = reinterpret_cast<symgpu_mp3_gc*>(base + 2 * spec_bytes);
+    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_spec, spectra, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // Mono / MPEG-2 frames leave part of each PCM slot untouched: define it as zero.
+    bool partial = false;
+    for (uint32_t r = 0; r < n_runs; ++r) partial |= runs[r].granules_per_frame == 1 || runs[r].channels == 1;
+    if (partial) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
+    symgpu_status s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
+    if (s != SYMGPU_OK) return s;
+    CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SYMGPU_OK;
+}
+
+} // extern "C"

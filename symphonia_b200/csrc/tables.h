@@ -1,0 +1,46 @@
+// Lookup tables of the synthesis engine.  Everything is built ON THE HOST with libm (f64 then
+// cast, except where the reference itself computes in f32) and uploaded verbatim; device math
+// never regenerates a table (SURVEY.md §7 "Tables come from host libm").  The blob is one POD
+// struct so that multi-GPU ranks can broadcast it as raw bytes.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace symgpu {
+
+// Exponent range of the requantisation scale 2^(0.25*(A-B)) (layer3/requantize.rs:259-280,
+// :317-343): A = global_gain-210-8*subblock_gain in [-266, 45]; B is a u8 in [0, 255].
+constexpr int kPow2qMin = -521;
+constexpr int kPow2qLen = 568;
+
+enum Mp3Kind { kKindLong = 0, kKindShort = 1, kKindMixed = 2 };
+
+struct Mp3Tables {
+    // ---- f32 tables (first 913 floats are compared 1:1 with the oracle's tables in tests) ----
+    float synth_d[512];        // ISO 11172-3 Table B.3 as the reference's 9-decimal literals
+    float imdct_win[4][36];    // long / start / short / end
+    float half_cos12[6][6];
+    float cs[8], ca[8];
+    float is_mpeg1[7][2];
+    float is_mpeg2[2][32][2];
+    float dct_iv_scale[18];
+    float sdct18_scale[9];
+    float sdct9_d[7];
+    float lee16[16], lee8[8], lee4[4], lee2[2], lee1;
+    // ---- engine-only tables ----
+    float pow2q[kPow2qLen];    // (float)pow(2.0, 0.25 * k), k = kPow2qMin ..
+    float pow43[8208];         // f32 powf(i, 4/3), requantize.rs:23-32 (for CPU front-ends / workloads)
+    // ---- integer maps ----
+    uint16_t edges[9][3][41];       // [sample_rate_idx][kind][edge]; interval i = [edges[i], edges[i+1])
+    uint8_t n_edges[9][3];
+    uint8_t mixed_switch[9];
+    uint8_t pre_emphasis[24];
+    uint8_t iv_of_line[9][3][576];  // interval index of each spectral line
+    uint16_t reorder_src[9][2][576]; // [..][0 short | 1 mixed][dest line] -> source line
+    uint16_t reorder_start[9][2];
+};
+
+// Builds the tables (host libm).  Thread-safe, built once.
+const Mp3Tables& mp3_tables_host();
+
+} // namespace symgpu

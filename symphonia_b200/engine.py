@@ -1,0 +1,111 @@
+"""Engine: one symgpu context (one CUDA device, one stream) driven from Python.
+
+Host entry points take numpy arrays (ideally backed by pinned memory); device entry points take
+torch CUDA tensors that already live in HBM.  torch is plumbing only (allocation / pointers).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from ._native import MP3_GC_DTYPE, MP3_RUN_DTYPE
+
+
+class SymgpuError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        msg = _native.lib().symgpu_strerror(status).decode()
+        super().__init__(f"{msg} [{status}] {detail}".strip())
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _native.lib()
+        self._ctx = ctypes.c_void_p()
+        st = self._lib.symgpu_ctx_create(int(device), ctypes.byref(self._ctx))
+        if st != 0:
+            self._ctx = None
+            raise SymgpuError(st, "symgpu_ctx_create failed: a B200-class CUDA device is required; "
+                                  "there is no CPU fallback")
+        self.device = int(device)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.symgpu_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st):
+        if st != 0:
+            raise SymgpuError(st, self._lib.symgpu_last_cuda_error(self._ctx).decode())
+
+    # -- misc -------------------------------------------------------------------------------
+    def sync(self):
+        self._check(self._lib.symgpu_sync(self._ctx))
+
+    @property
+    def cuda_stream(self):
+        return self._lib.symgpu_cuda_stream(self._ctx)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.symgpu_launch_count(self._ctx))
+
+    def upload_tables(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._check(self._lib.symgpu_tables_upload(self._ctx, _np_ptr(blob), blob.nbytes))
+
+    # -- MP3 --------------------------------------------------------------------------------
+    def mp3_streams_alloc(self, n_streams):
+        self._check(self._lib.symgpu_mp3_streams_alloc(self._ctx, int(n_streams)))
+
+    def mp3_stream_reset(self, stream):
+        self._check(self._lib.symgpu_mp3_stream_reset(self._ctx, int(stream)))
+
+    @staticmethod
+    def _mp3_args(units, spectra, runs):
+        units = np.ascontiguousarray(units, dtype=MP3_GC_DTYPE)
+        runs = np.ascontiguousarray(runs, dtype=MP3_RUN_DTYPE)
+        n_frames = units.size // 4
+        if units.size != n_frames * 4:
+            raise ValueError("units must hold 4 granule-channels per frame")
+        return units, runs, n_frames
+
+    def mp3_synth_host(self, units, spectra, runs, out=None):
+        """units [F,2,2] MP3_GC_DTYPE, spectra [F,2,2,576] f32, runs [R] MP3_RUN_DTYPE -> pcm [F,2,1152]."""
+        units, runs, n_frames = self._mp3_args(units, spectra, runs)
+        spectra = np.ascontiguousarray(spectra, dtype=np.float32)
+        if spectra.size != n_frames * 2304:
+            raise ValueError("spectra must be [n_frames, 2, 2, 576]")
+        if out is None:
+            out = np.empty((n_frames, 2, 1152), dtype=np.float32)
+        self._check(self._lib.symgpu_mp3_synth_host(self._ctx, _np_ptr(units), _np_ptr(spectra), _np_ptr(runs),
+                                                    len(runs), n_frames, _np_ptr(out)))
+        return out
+
+    def mp3_synth_dev(self, units_t, spectra_t, runs, pcm_t):
+        """Device-resident variant: torch CUDA tensors (uint8 [F*256], f32 [F,2,2,576], f32 [F,2,1152])."""
+        runs = np.ascontiguousarray(runs, dtype=MP3_RUN_DTYPE)
+        n_frames = spectra_t.numel() // 2304
+        assert units_t.is_cuda and spectra_t.is_cuda and pcm_t.is_cuda
+        assert units_t.numel() * units_t.element_size() == n_frames * 256
+        assert pcm_t.numel() == n_frames * 2304 and spectra_t.is_contiguous() and pcm_t.is_contiguous()
+        self._check(self._lib.symgpu_mp3_synth_dev(self._ctx, ctypes.c_void_p(units_t.data_ptr()),
+                                                   ctypes.c_void_p(spectra_t.data_ptr()), _np_ptr(runs), len(runs),
+                                                   n_frames, ctypes.c_void_p(pcm_t.data_ptr())))

@@ -115,4 +115,6 @@ def test_pow43_table(oracle):
     # requantize.rs:23-32
     for i in (0, 1, 2, 8, 27, 1000, 8206):
         assert abs(oracle.oracle_mp3_pow43(i) - float(i) ** (4.0 / 3.0)) <= 1e-6 * max(1.0, float(i) ** (4.0 / 3.0))
-    assert oracle.oracle_mp3_pow43(8) == 16.0
+    # f32 powf with the f32 exponent 4.0/3.0 (slightly above 4/3), as the reference computes it:
+    # 8^(4/3) is 16.000002, not 16.  Pinned so nobody "fixes" it.
+    assert np.float32(oracle.oracle_mp3_pow43(8)) == np.float32(16.000002)
