@@ -226,7 +226,12 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
     const bool load_state = tile.flags & kTileLoadState;
     const bool store_state = tile.flags & kTileStoreState;
     const Mp3Tables* __restrict__ tab = a.tab;
-    Mp3StreamState* st = a.states + tile.stream;
+    // Stream state is double-buffered: a launch reads generation g and writes generation g+1, so a
+    // run-starting tile never races with the run-ending tile of the same stream (they are
+    // different CTAs of the same launch).  The last CTA to finish bumps the generations.
+    const uint32_t gen = a.gen[tile.stream];
+    const Mp3StreamState* st_in = a.states + (size_t)tile.stream * 2 + (gen & 1);
+    Mp3StreamState* st = a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
     const int gseq0 = (int)tile.first_frame * gpf + tile.first_gr; // batch granule sequence index of region 2
 
     // ------------------------------------------------------------------------------------------
@@ -546,11 +551,11 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
         for (int idx = threadIdx.x; idx < 2 * 32 * 18; idx += NW * 32) {
             const int ch = idx / 576, rem = idx - ch * 576, sb = rem / 18, t = rem - sb * 18;
             float* p = X2 + (t * kPitch + sb) * 2 + ch;
-            *p = *p + finv(st->overlap[ch][sb][t], sb, t);
+            *p = *p + finv(st_in->overlap[ch][sb][t], sb, t);
         }
         for (int idx = threadIdx.x; idx < 15 * 32; idx += NW * 32) {
             const int s = idx >> 5, col = idx & 31;
-            *reinterpret_cast<float2*>(hist + (s * kPitch + col) * 2) = st->dhist[s][col];
+            *reinterpret_cast<float2*>(hist + (s * kPitch + col) * 2) = st_in->dhist[s][col];
         }
     }
     __syncthreads();
@@ -646,6 +651,20 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
             const int s = idx >> 5, col = idx & 31;
             st->dhist[s][col] = *reinterpret_cast<const float2*>(last + (s * kPitch + col) * 2);
         }
+    }
+
+    // Launch epilogue: the last CTA to retire publishes the new state generation of every run.
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += NW * 32)
+            if (a.tiles[i].flags & kTileStoreState) a.gen[a.tiles[i].stream] += 1;
+        if (threadIdx.x == 0) *a.done = 0;
     }
 }
 

@@ -45,7 +45,9 @@ struct Mp3Args {
     const float* spectra;
     float* pcm;
     const Mp3Tile* tiles;
-    Mp3StreamState* states;
+    Mp3StreamState* states; // [n_streams][2] double-buffered, see gen
+    uint32_t* gen;          // [n_streams] state generation; buffer (gen & 1) is current
+    unsigned* done;         // retired-CTA counter (self-resetting)
     const Mp3Tables* tab;
 };
 

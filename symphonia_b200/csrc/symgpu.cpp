@@ -25,7 +25,8 @@ struct symgpu_ctx {
     // tables
     Mp3Tables* d_mp3_tab = nullptr;
     // MP3 streams
-    Mp3StreamState* d_mp3_states = nullptr;
+    Mp3StreamState* d_mp3_states = nullptr; // [n][2]
+    uint32_t* d_mp3_gen = nullptr;           // [n] + 1 word: retired-CTA counter
     uint32_t n_mp3_streams = 0;
     // tile list (host staging is pinned; cached while the caller repeats the same runs)
     Mp3Tile* d_tiles = nullptr;
@@ -213,6 +214,7 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_mp3_tab) cudaFree(ctx->d_mp3_tab);
     if (ctx->d_mp3_states) cudaFree(ctx->d_mp3_states);
+    if (ctx->d_mp3_gen) cudaFree(ctx->d_mp3_gen);
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
     if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
@@ -235,12 +237,16 @@ symgpu_status symgpu_mp3_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams) {
     DeviceGuard guard(ctx->device);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->d_mp3_states) cudaFree(ctx->d_mp3_states);
+    if (ctx->d_mp3_gen) cudaFree(ctx->d_mp3_gen);
     ctx->d_mp3_states = nullptr;
+    ctx->d_mp3_gen = nullptr;
     ctx->n_mp3_streams = 0;
     ctx->cached_runs.clear();
     ctx->cached_frames = 0;
-    CU(ctx, cudaMalloc(&ctx->d_mp3_states, (size_t)n_streams * sizeof(Mp3StreamState)));
-    CU(ctx, cudaMemset(ctx->d_mp3_states, 0, (size_t)n_streams * sizeof(Mp3StreamState)));
+    CU(ctx, cudaMalloc(&ctx->d_mp3_states, (size_t)n_streams * 2 * sizeof(Mp3StreamState)));
+    CU(ctx, cudaMemset(ctx->d_mp3_states, 0, (size_t)n_streams * 2 * sizeof(Mp3StreamState)));
+    CU(ctx, cudaMalloc(&ctx->d_mp3_gen, ((size_t)n_streams + 1) * sizeof(uint32_t)));
+    CU(ctx, cudaMemset(ctx->d_mp3_gen, 0, ((size_t)n_streams + 1) * sizeof(uint32_t)));
     ctx->n_mp3_streams = n_streams;
     return SYMGPU_OK;
 }
@@ -249,7 +255,7 @@ symgpu_status symgpu_mp3_stream_reset(symgpu_ctx* ctx, uint32_t stream) {
     if (!ctx) return SYMGPU_ERR_ARG;
     if (stream >= ctx->n_mp3_streams) return SYMGPU_ERR_LIMIT;
     DeviceGuard guard(ctx->device);
-    CU(ctx, cudaMemsetAsync(ctx->d_mp3_states + stream, 0, sizeof(Mp3StreamState), ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_mp3_states + (size_t)stream * 2, 0, 2 * sizeof(Mp3StreamState), ctx->stream));
     return SYMGPU_OK;
 }
 
@@ -261,7 +267,8 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
     int n_tiles = 0;
     symgpu_status s = ensure_tiles(ctx, runs, n_runs, n_frames, &n_tiles);
     if (s != SYMGPU_OK) return s;
-    Mp3Args a{units, spectra, pcm, ctx->d_tiles, ctx->d_mp3_states, ctx->d_mp3_tab};
+    Mp3Args a{units, spectra, pcm, ctx->d_tiles, ctx->d_mp3_states, ctx->d_mp3_gen,
+              ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
     CU(ctx, mp3_launch(a, n_tiles, ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;

@@ -15,8 +15,8 @@ constexpr int kPow2qLen = 568;
 
 enum Mp3Kind { kKindLong = 0, kKindShort = 1, kKindMixed = 2 };
 
-struct Mp3Tables {
-    // ---- f32 tables (first 913 floats are compared 1:1 with the oracle's tables in tests) ----
+struct alignas(16) Mp3Tables {
+    // ---- f32 tables (first 915 floats are compared 1:1 with the oracle's tables in tests) ----
     float synth_d[512];        // ISO 11172-3 Table B.3 as the reference's 9-decimal literals
     float imdct_win[4][36];    // long / start / short / end
     float half_cos12[6][6];
@@ -31,12 +31,12 @@ struct Mp3Tables {
     float pow2q[kPow2qLen];    // (float)pow(2.0, 0.25 * k), k = kPow2qMin ..
     float pow43[8208];         // f32 powf(i, 4/3), requantize.rs:23-32 (for CPU front-ends / workloads)
     // ---- integer maps ----
-    uint16_t edges[9][3][41];       // [sample_rate_idx][kind][edge]; interval i = [edges[i], edges[i+1])
+    alignas(16) uint16_t edges[9][3][41];       // [sample_rate_idx][kind][edge]; interval i = [edges[i], edges[i+1])
     uint8_t n_edges[9][3];
     uint8_t mixed_switch[9];
     uint8_t pre_emphasis[24];
-    uint8_t iv_of_line[9][3][576];  // interval index of each spectral line
-    uint16_t reorder_src[9][2][576]; // [..][0 short | 1 mixed][dest line] -> source line
+    alignas(16) uint8_t iv_of_line[9][3][576];  // interval index of each spectral line (read as uchar4)
+    alignas(16) uint16_t reorder_src[9][2][576]; // [..][0 short | 1 mixed][dest line] -> source line
     uint16_t reorder_start[9][2];
 };
 
