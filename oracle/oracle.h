@@ -22,6 +22,8 @@ void oracle_mp3_state_reset(oracle_mp3_state* st);
 int oracle_mp3_frame(oracle_mp3_state* st, symgpu_mp3_gc* units, float* spectra, float* pcm, int n_gr, int n_ch);
 int oracle_mp3_batch(oracle_mp3_state* states, const symgpu_mp3_gc* units, const float* spectra,
                      const symgpu_mp3_run* runs, uint32_t n_runs, float* pcm);
+int oracle_mp3_batch_mt(oracle_mp3_state* states, const symgpu_mp3_gc* units, const float* spectra,
+                        const symgpu_mp3_run* runs, uint32_t n_runs, float* pcm, int n_threads);
 void oracle_mp3_dct32(const float* x, float* y);
 void oracle_mp3_imdct36(float* x, const float* window, float* overlap);
 void oracle_mp3_imdct12_win(float* x, const float* window, float* overlap);

@@ -19,6 +19,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../include/symgpu.h"
 #include "mp3_iso_data.h"
@@ -583,6 +585,28 @@ int oracle_mp3_batch(oracle_mp3_state* states, const symgpu_mp3_gc* units, const
                                    runs[r].granules_per_frame ? runs[r].granules_per_frame : 2,
                                    runs[r].channels ? runs[r].channels : 2);
         }
+    }
+    return rc;
+}
+
+// Same, with the runs sharded over `n_threads` std::threads (one stream shard per thread: the
+// reference's decoders are single-threaded per stream, BENCHMARKS.md:140; an application scales
+// by running one decoder per thread).  Used only as the timed CPU baseline.
+int oracle_mp3_batch_mt(oracle_mp3_state* states, const symgpu_mp3_gc* units, const float* spectra,
+                        const symgpu_mp3_run* runs, uint32_t n_runs, float* pcm, int n_threads) {
+    if (n_threads <= 1) return oracle_mp3_batch(states, units, spectra, runs, n_runs, pcm);
+    std::vector<std::thread> pool;
+    std::vector<int> rcs((size_t)n_threads, 0);
+    for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&, t] {
+            const uint32_t lo = (uint32_t)((uint64_t)n_runs * t / n_threads);
+            const uint32_t hi = (uint32_t)((uint64_t)n_runs * (t + 1) / n_threads);
+            if (hi > lo) rcs[t] = oracle_mp3_batch(states, units, spectra, runs + lo, hi - lo, pcm);
+        });
+    int rc = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        pool[t].join();
+        rc |= rcs[t];
     }
     return rc;
 }

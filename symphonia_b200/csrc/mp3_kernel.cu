@@ -312,12 +312,12 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                 if (ch < n_ch) {
                     v = __ldg(spec4 + q);
                     const uchar4 iv = __ldg((ch ? ivm1 : ivm0) + l4);
-                    const int rz = ch ? rz1 : rz0;
-                    const int l = l4 * 4;
-                    if (l + 0 < rz) v.x *= ws.scale[ch][iv.x];
-                    if (l + 1 < rz) v.y *= ws.scale[ch][iv.y];
-                    if (l + 2 < rz) v.z *= ws.scale[ch][iv.z];
-                    if (l + 3 < rz) v.w *= ws.scale[ch][iv.w];
+                    // Lines at or beyond rzero are +0.0 by contract (requantize.rs:234), and +0 * scale is
+                    // +0, so the reference's "stop at rzero" (requantize.rs:267,:284) needs no predicate.
+                    v.x *= ws.scale[ch][iv.x];
+                    v.y *= ws.scale[ch][iv.y];
+                    v.z *= ws.scale[ch][iv.z];
+                    v.w *= ws.scale[ch][iv.w];
                     if (ch && is) {
                         if (v.x != 0.0f) ws.nz[iv.x] = 1;
                         if (v.y != 0.0f) ws.nz[iv.y] = 1;
@@ -333,61 +333,104 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
             if (ms || is) {
                 const int end = max(rz0, rz1);
                 int bound = end;
-                if (is && lane == 0) {
+                if (is) {
+                    // Warp-parallel restatement of the two top-down scans (stereo.rs:198-261, :265-482).
+                    // Every lane derives the same facts from one 40-bit "interval of channel 1 is
+                    // non-zero" mask; lane iv then labels interval iv (and iv + 32).
                     const bool mpeg1 = g1.flags & SYMGPU_MP3_F_MPEG1;
                     const int inv_pos = mpeg1 ? 7 : 31;
                     const float(*rt)[2] = mpeg1 ? c_mp3.is_mpeg1 : c_mp3.is_mpeg2[(g1.flags & SYMGPU_MP3_F_SFC_LSB) ? 1 : 0];
                     const uint16_t* e = tab->edges[sr][kind1];
+                    const int n_e = c_mp3.n_edges[sr][kind1];
+                    const int n_iv = n_e - 1;
                     const uint8_t mode_hi = ms ? 1 : 0;
-                    auto set_is = [&](int iv, int pos) { // process_intensity, stereo.rs:168-188
-                        if (pos < inv_pos) {
-                            ws.smode[iv] = 2;
-                            ws.sratio[iv] = make_float2(rt[pos][0], rt[pos][1]);
-                        } else {
-                            ws.smode[iv] = mode_hi;
-                        }
-                    };
-                    if (kind1 == kKindLong) { // stereo.rs:198-261
-                        for (int b = 21; b >= 0; --b) {
-                            const int start = e[b];
-                            if (!(start >= rz1 || !ws.nz[b])) break;
-                            set_is(b, g1.scalefacs[b == 21 ? 20 : b]);
-                            bound = start;
-                        }
-                    } else { // stereo.rs:265-482
+                    bool nza = false, nzb = false;
+                    if (lane < n_iv) nza = ws.nz[lane] && (kind1 != kKindLong || (int)e[lane] < rz1);
+                    if (lane + 32 < n_iv) nzb = ws.nz[lane + 32] && (kind1 != kKindLong || (int)e[lane + 32] < rz1);
+                    const unsigned long long nzmask = (unsigned long long)__ballot_sync(0xffffffffu, nza) |
+                                                      ((unsigned long long)__ballot_sync(0xffffffffu, nzb) << 32);
+                    // is_lo: first interval labelled by the scan; iv_is[w]: first interval of window w that is
+                    // intensity coded (every labelled interval of that window at or above it is).
+                    int is_lo, first_is0, first_is1, first_is2;
+                    if (kind1 == kKindLong) {
+                        const int hb = nzmask ? 63 - __clzll((long long)nzmask) : -1; // highest non-zero band
+                        is_lo = hb + 1;
+                        first_is0 = first_is1 = first_is2 = hb + 1;
+                        if (hb < 21) bound = e[hb + 1];
+                    } else {
                         const int sw = (kind1 == kKindMixed) ? c_mp3.mixed_switch[sr] : 0;
-                        const int n_e = c_mp3.n_edges[sr][kind1];
                         const int n_quads = (n_e - sw - 1) / 3;
-                        int sfi = (kind1 == kKindMixed) ? n_e - 1 : 39;
-                        bool wz0 = true, wz1 = true, wz2 = true, found = false;
-                        auto pos_of = [&](int k) { return (int)g1.scalefacs[k < 36 ? k : k - 3]; };
-                        for (int q = n_quads - 1; q >= 0; --q) {
-                            const int iv0 = sw + 3 * q;
-                            wz2 = wz2 && !ws.nz[iv0 + 2];
-                            if (wz2) set_is(iv0 + 2, pos_of(sfi - 1)); else ws.smode[iv0 + 2] = mode_hi;
-                            sfi -= 1;
-                            wz1 = wz1 && !ws.nz[iv0 + 1];
-                            if (wz1) set_is(iv0 + 1, pos_of(sfi - 1)); else ws.smode[iv0 + 1] = mode_hi;
-                            sfi -= 1;
-                            wz0 = wz0 && !ws.nz[iv0];
-                            if (wz0) set_is(iv0, pos_of(sfi - 1)); else ws.smode[iv0] = mode_hi;
-                            sfi -= 1;
-                            bound = e[iv0];
-                            found = !wz0 && !wz1 && !wz2;
-                            if (found) break;
+                        int hq0 = -1, hq1 = -1, hq2 = -1; // highest quad whose window w is non-zero
+                        for (int q = 0; q < n_quads; ++q) {
+                            const unsigned bits = (unsigned)(nzmask >> (sw + 3 * q)) & 7u;
+                            if (bits & 1u) hq0 = q;
+                            if (bits & 2u) hq1 = q;
+                            if (bits & 4u) hq2 = q;
                         }
-                        if (!found && kind1 == kKindMixed) {
-                            for (int b = sw - 1; b >= 0; --b) {
-                                if (ws.nz[b]) break;
-                                set_is(b, pos_of(sfi - 1));
-                                sfi -= 1;
-                                bound = e[b];
+                        const int qstop = min(hq0, min(hq1, hq2)); // quad where all three windows are done, or -1
+                        const int qlo = max(qstop, 0);
+                        is_lo = sw + 3 * qlo;
+                        first_is0 = sw + 3 * (hq0 + 1);
+                        first_is1 = sw + 3 * (hq1 + 1) + 1;
+                        first_is2 = sw + 3 * (hq2 + 1) + 2;
+                        bound = e[is_lo];
+                        if (qstop < 0 && kind1 == kKindMixed) { // continue into the long bands of a mixed block
+                            const unsigned long long lmask = nzmask & ((1ull << sw) - 1ull);
+                            const int hb = lmask ? 63 - __clzll((long long)lmask) : -1;
+                            if (hb < sw - 1) {
+                                is_lo = hb + 1;
+                                bound = e[hb + 1];
                             }
                         }
                     }
+                    for (int iv = lane; iv < n_iv; iv += 32) {
+                        if (iv < is_lo) continue;
+                        bool coded;
+                        if (kind1 == kKindLong) {
+                            coded = true;
+                        } else {
+                            const int sw = (kind1 == kKindMixed) ? c_mp3.mixed_switch[sr] : 0;
+                            if (iv < sw) coded = true; // mixed long band reached by the scan: always zero
+                            else {
+                                const int w = (iv - sw) % 3;
+                                coded = iv >= (w == 0 ? first_is0 : w == 1 ? first_is1 : first_is2);
+                            }
+                        }
+                        uint8_t mode = mode_hi;
+                        if (coded) {
+                            // is_pos: long: scalefacs[b], band 21 copies band 20 (stereo.rs:228-230);
+                            // short: scalefacs[k], the last three copy [33..36) (stereo.rs:352-354).
+                            const int k = (kind1 == kKindLong) ? (iv == 21 ? 20 : iv) : (iv < 36 ? iv : iv - 3);
+                            const int pos = g1.scalefacs[k];
+                            if (pos < inv_pos) { // process_intensity, stereo.rs:168-188
+                                mode = 2;
+                                ws.sratio[iv] = make_float2(rt[pos][0], rt[pos][1]);
+                            }
+                        }
+                        ws.smode[iv] = mode;
+                    }
                 }
-                bound = __shfl_sync(0xffffffffu, bound, 0);
                 __syncwarp();
+                if (!is) {
+                    // mid/side only: every line below max(rzero) (stereo.rs:536-544)
+                    for (int l4 = lane; l4 * 4 < bound; l4 += 32) {
+                        float4 m = reinterpret_cast<float4*>(S)[l4];
+                        float4 d = reinterpret_cast<float4*>(S + 576)[l4];
+                        const int l = l4 * 4;
+                        float4 L, R;
+                        L.x = (m.x + d.x) * kFrac1Sqrt2; R.x = (m.x - d.x) * kFrac1Sqrt2;
+                        L.y = (m.y + d.y) * kFrac1Sqrt2; R.y = (m.y - d.y) * kFrac1Sqrt2;
+                        L.z = (m.z + d.z) * kFrac1Sqrt2; R.z = (m.z - d.z) * kFrac1Sqrt2;
+                        L.w = (m.w + d.w) * kFrac1Sqrt2; R.w = (m.w - d.w) * kFrac1Sqrt2;
+                        if (l + 3 >= bound) { // rzero is not always a multiple of 4: keep the tail untouched
+                            if (l + 1 >= bound) { L.y = m.y; R.y = d.y; }
+                            if (l + 2 >= bound) { L.z = m.z; R.z = d.z; }
+                            L.w = m.w; R.w = d.w;
+                        }
+                        reinterpret_cast<float4*>(S)[l4] = L;
+                        reinterpret_cast<float4*>(S + 576)[l4] = R;
+                    }
+                } else {
                 for (int l4 = lane; l4 < 144; l4 += 32) {
                     float4 m = reinterpret_cast<float4*>(S)[l4];
                     float4 s = reinterpret_cast<float4*>(S + 576)[l4];
@@ -414,6 +457,7 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                     apply(m.w, s.w, l + 3, iv.w);
                     reinterpret_cast<float4*>(S)[l4] = m;
                     reinterpret_cast<float4*>(S + 576)[l4] = s;
+                }
                 }
                 rz0 = end;
                 rz1 = end;
@@ -614,6 +658,14 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                 wl[(m + 1) & 15] = *reinterpret_cast<const float2*>(row + 2 * col_lo);
                 wh[(m + 1) & 15] = *reinterpret_cast<const float2*>(row + 2 * col_hi);
             }
+            // Output pointer of slot s_begin; consecutive slots of a frame are contiguous in a PCM plane
+            // (plane[gr*576 + t*32 + i]), frames are SYMGPU_MP3_FRAME_FLOATS apart.
+            const int slots_per_frame = 18 * gpf;
+            const int q0 = (gseq0 * 18) + (s_begin - 36); // slot sequence index within the batch
+            int sif = q0 % slots_per_frame;                // slot in frame
+            float* out = a.pcm + (size_t)(q0 / slots_per_frame) * SYMGPU_MP3_FRAME_FLOATS + sif * 32 + lane;
+            const int frame_jump = SYMGPU_MP3_FRAME_FLOATS - slots_per_frame * 32;
+            const bool stereo_out = n_ch == 2;
             for (int base = s_begin; base < s_end; base += 16) {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
@@ -632,12 +684,13 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                             o0 += v1.x * dhi[j];
                             o1 += v1.y * dhi[j];
                         }
-                        const int reg = s / 18, t = s - reg * 18;
-                        const int gseq = gseq0 + (reg - 2);
-                        const int frame = gseq / gpf, gr = gseq - frame * gpf;
-                        float* out = a.pcm + (size_t)frame * SYMGPU_MP3_FRAME_FLOATS + gr * 576 + t * 32 + lane;
                         out[0] = o0;
-                        if (n_ch == 2) out[1152] = o1;
+                        if (stereo_out) out[1152] = o1;
+                        out += 32;
+                        if (++sif == slots_per_frame) {
+                            sif = 0;
+                            out += frame_jump;
+                        }
                     }
                 }
             }

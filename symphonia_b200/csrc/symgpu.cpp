@@ -82,16 +82,21 @@ symgpu_status build_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t 
         if (run.stream >= ctx->n_mp3_streams) return SYMGPU_ERR_LIMIT;
         covered += run.n_frames;
         const uint32_t n_gran = run.n_frames * (uint32_t)gpf;
-        for (uint32_t q0 = 0; q0 < n_gran; q0 += (uint32_t)T) {
+        // Equal-sized tiles (a 1-granule tail tile would still pay the 2-granule halo).
+        const uint32_t n_t = (n_gran + (uint32_t)T - 1) / (uint32_t)T;
+        uint32_t q0 = 0;
+        for (uint32_t k = 0; k < n_t; ++k) {
+            const uint32_t q1 = (uint32_t)(((uint64_t)n_gran * (k + 1)) / n_t);
             Mp3Tile t{};
             t.first_frame = run.first_frame + q0 / (uint32_t)gpf;
             t.first_gr = (uint16_t)(q0 % (uint32_t)gpf);
             t.stream = run.stream;
-            t.n_granules = (uint16_t)((n_gran - q0 < (uint32_t)T) ? n_gran - q0 : (uint32_t)T);
+            t.n_granules = (uint16_t)(q1 - q0);
             t.gpf = (uint8_t)gpf;
             t.n_ch = (uint8_t)n_ch;
-            t.flags = (uint8_t)((q0 == 0 ? kTileLoadState : 0) | (q0 + t.n_granules == n_gran ? kTileStoreState : 0));
+            t.flags = (uint8_t)((k == 0 ? kTileLoadState : 0) | (k + 1 == n_t ? kTileStoreState : 0));
             out.push_back(t);
+            q0 = q1;
         }
     }
     if (covered != n_frames) return SYMGPU_ERR_ARG; // runs must tile the batch exactly

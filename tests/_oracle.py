@@ -45,6 +45,8 @@ def load(path=None):
     lib.oracle_mp3_imdct_window.restype = c_f32p
     lib.oracle_mp3_batch.restype = ctypes.c_int
     lib.oracle_mp3_batch.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_void_p]
+    lib.oracle_mp3_batch_mt.restype = ctypes.c_int
+    lib.oracle_mp3_batch_mt.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
     lib.oracle_mp3_frame.restype = ctypes.c_int
     lib.oracle_mp3_frame.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int]
     lib.oracle_mp3_polyphase.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
