@@ -152,6 +152,111 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
                                    const float* spectra, const symgpu_mp3_run* runs,
                                    uint32_t n_runs, uint32_t n_frames, float* pcm);
 
+/* ---- AAC-LC filterbank --------------------------------------------------------------------- */
+
+/* Window sequences, symphonia-codec-aac/src/aac/common.rs:17-20. */
+enum { SYMGPU_AAC_ONLY_LONG = 0, SYMGPU_AAC_LONG_START = 1, SYMGPU_AAC_EIGHT_SHORT = 2, SYMGPU_AAC_LONG_STOP = 3 };
+
+/* One channel of one frame: the arguments of Dsp::synth (aac/dsp.rs:57-65) that are not sample
+ * data, plus a reference to the channel's TNS filters.  16 bytes, 2 per frame. */
+typedef struct symgpu_aac_unit {
+    uint8_t window_sequence;   /* IcsInfo::window_sequence                                      */
+    uint8_t window_shape;      /* 0 sine, 1 KBD (IcsInfo::window_shape)                         */
+    uint8_t prev_window_shape; /* IcsInfo::prev_window_shape (ics/mod.rs:119, :172-177)         */
+    uint8_t n_tns;             /* number of TNS filters with order > 0 to run on this channel   */
+    uint32_t tns_first;        /* index of the first of them in the `tns` array                 */
+    uint32_t reserved[2];      /* must be zero                                                  */
+} symgpu_aac_unit;
+
+/* One TNS all-pole filter, already resolved to a line range by the parser
+ * (Tns::synth, aac/ics/tns.rs:149-199: start/end = w*128 + bands[min(.., tns_max_bands)]).
+ * direction 0 filters upward from `start`, 1 downward from `end - 1`. */
+typedef struct symgpu_aac_tns {
+    uint16_t start, end;       /* [start, end) within the channel's 1024 lines                  */
+    uint8_t order;             /* 1..20 (AAC-LC: <= 12)                                         */
+    uint8_t direction;
+    uint16_t reserved;
+    float lpc[20];             /* TnsCoeffs::coef                                               */
+} symgpu_aac_tns;
+
+typedef struct symgpu_aac_run {
+    uint32_t stream;           /* per-stream state slot: Ics.delay of both channels             */
+    uint32_t first_frame;
+    uint32_t n_frames;
+    uint8_t channels;          /* 1 or 2; 0 means 2                                             */
+    uint8_t reserved[3];
+} symgpu_aac_run;
+
+symgpu_status symgpu_aac_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams);
+symgpu_status symgpu_aac_stream_reset(symgpu_ctx* ctx, uint32_t stream); /* Ics::reset, ics/mod.rs:229-232 */
+
+/* Synthesises `n_frames` AAC-LC frames (Pulse::synth, <= 4 lines, stays with the parser):
+ *   units  [n_frames][2], tns [n_tns], coeffs [n_frames][2][1024] -> pcm [n_frames][2][1024]
+ * (plane(ch) of frame f at pcm[f][ch]).  Same host/dev split as the MP3 entry points; `runs` is
+ * host memory in both. */
+symgpu_status symgpu_aac_synth_host(symgpu_ctx* ctx, const symgpu_aac_unit* units, const symgpu_aac_tns* tns,
+                                    uint32_t n_tns, const float* coeffs, const symgpu_aac_run* runs,
+                                    uint32_t n_runs, uint32_t n_frames, float* pcm);
+symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units, const symgpu_aac_tns* tns,
+                                   uint32_t n_tns, const float* coeffs, const symgpu_aac_run* runs,
+                                   uint32_t n_runs, uint32_t n_frames, float* pcm);
+
+/* ---- Vorbis synthesis ---------------------------------------------------------------------- */
+
+/* What floor-1 curve synthesis needs from Floor1Setup (codec-vorbis/src/floor.rs:546-560):
+ * the X list, the precomputed neighbours (find_neighbors, :748-773) and the sort order. */
+typedef struct symgpu_vorbis_floor1 {
+    uint8_t multiplier;        /* floor1_multiplier, 1..4                                       */
+    uint8_t n_posts;           /* floor1_x_list.len(), 2..65                                    */
+    uint16_t x_list[65];
+    uint8_t low[65], high[65]; /* floor1_x_list_neighbors                                       */
+    uint8_t sort_order[65];    /* floor1_x_list_sort_order                                      */
+    uint8_t reserved[5];
+} symgpu_vorbis_floor1;        /* 332 bytes */
+
+/* Identification-header facts of a stream (lib.rs:404-406).  Up to two channels with at most one
+ * coupling step (magnitude = channel 0, angle = channel 1) are supported in this version. */
+typedef struct symgpu_vorbis_stream {
+    uint8_t bs0_exp, bs1_exp;  /* blocksize exponents, 6..13                                    */
+    uint8_t channels;          /* 1 or 2                                                        */
+    uint8_t coupled;           /* 1: inverse coupling of (ch0 magnitude, ch1 angle)             */
+} symgpu_vorbis_stream;
+
+/* One audio packet after entropy decode (lib.rs:248 | :250).  16 bytes. */
+typedef struct symgpu_vorbis_unit {
+    uint8_t block_flag;        /* mode.block_flag: 1 = long block                               */
+    uint8_t prev_block_flag;   /* dsp.prev_block_flag.unwrap_or(block_flag)  (lib.rs:298)       */
+    uint8_t do_not_decode[2];  /* per channel, after non-zero vector propagate (lib.rs:215-225) */
+    uint16_t floor[2];         /* per channel: index of its floor-1 setup in `floors`, or 0xffff
+                                  when the floor is unused (zero curve, floor.rs is_unused)     */
+    uint8_t reserved[8];
+} symgpu_vorbis_unit;
+
+typedef struct symgpu_vorbis_run {
+    uint32_t stream;           /* index into `streams` and of the per-stream overlap state      */
+    uint32_t first_packet;
+    uint32_t n_packets;
+    uint32_t reserved;
+} symgpu_vorbis_run;
+
+/* Registers stream configurations (and zeroes their overlap state) / floor setups with a context. */
+symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_stream* streams, uint32_t n_streams);
+symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floor1* floors, uint32_t n_floors);
+symgpu_status symgpu_vorbis_stream_reset(symgpu_ctx* ctx, uint32_t stream); /* dsp.rs:26-32, :128-131 */
+
+/* Synthesises `n_packets` packets.  Every per-packet array uses fixed slots of `slot` floats per
+ * channel, slot >= the largest blocksize_1 / 2 in the batch:
+ *   units [n_packets], floor_y [n_packets][2][65] (Floor1.floor_y), residue [n_packets][2][slot]
+ *   -> pcm [n_packets][2][slot], of which the first (prev_n + n) / 4 samples are the packet's output.
+ * Floor curves are rendered on the device (floor1 synthesis step 1 + 2), then inverse coupling,
+ * floor * residue, IMDCT, window, overlap-add. */
+symgpu_status symgpu_vorbis_synth_host(symgpu_ctx* ctx, const symgpu_vorbis_unit* units, const uint16_t* floor_y,
+                                       const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
+                                       uint32_t n_packets, uint32_t slot, float* pcm);
+symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit* units, const uint16_t* floor_y,
+                                      const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
+                                      uint32_t n_packets, uint32_t slot, float* pcm);
+
 #ifdef __cplusplus
 }
 #endif

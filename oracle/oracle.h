@@ -32,6 +32,46 @@ const float* oracle_mp3_imdct_window(int which);
 float oracle_mp3_pow43(int i);
 size_t oracle_mp3_tables(float* out, size_t cap_floats);
 
+
+// ---- shared IMDCT / FFT (oracle_mdct.cpp) ----
+void oracle_fft_inplace(float* x, int n);
+void oracle_imdct(const float* spec, float* out, int n, double scale);
+void oracle_fft_twiddle(int size, int k, float* re_im);
+
+// ---- AAC-LC filterbank (oracle_aac.cpp) ----
+// Per-channel state: Ics.delay (aac/ics/mod.rs:207).
+typedef struct oracle_aac_state {
+    float delay[1024];
+} oracle_aac_state;
+void oracle_aac_tns(float* coeffs, const symgpu_aac_tns* filters, uint32_t n_filters);
+void oracle_aac_synth(const float* coeffs, float* delay, int seq, int window_shape, int prev_window_shape, float* dst);
+int oracle_aac_batch(oracle_aac_state* states, const symgpu_aac_unit* units, const symgpu_aac_tns* tns,
+                     const float* coeffs, const symgpu_aac_run* runs, uint32_t n_runs, float* pcm, int n_threads);
+const float* oracle_aac_window(int kbd, int is_short);
+
+// ---- Vorbis synthesis (oracle_vorbis.cpp) ----
+typedef struct oracle_vorbis_state {
+    float overlap[2][4096]; // DspChannel.overlap, bs1/2 <= 4096
+} oracle_vorbis_state;
+void oracle_vorbis_floor1(const symgpu_vorbis_floor1* setup, const uint16_t* floor_y, uint32_t n, float* floor);
+int oracle_vorbis_batch(oracle_vorbis_state* states, const symgpu_vorbis_stream* streams,
+                        const symgpu_vorbis_floor1* floors, const symgpu_vorbis_unit* units, const uint16_t* floor_y,
+                        const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs, uint32_t slot, float* pcm,
+                        int n_threads);
+const float* oracle_vorbis_window(int bs);
+float oracle_vorbis_inverse_db(int i);
+
 #ifdef __cplusplus
 }
+
+#include <vector>
+namespace oracle {
+struct Imdct {
+    int n;
+    std::vector<float> tw_re, tw_im;
+    Imdct(int n, double scale);
+    void run(const float* spec, float* out) const; // spec[n] -> out[2n]
+};
+const Imdct& imdct_for(int n, double scale);
+} // namespace oracle
 #endif

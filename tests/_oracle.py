@@ -21,6 +21,14 @@ class Mp3State(ctypes.Structure):
                 ("v_front", ctypes.c_int32 * 2)]
 
 
+class AacState(ctypes.Structure):
+    _fields_ = [("delay", ctypes.c_float * 1024)]
+
+
+class VorbisState(ctypes.Structure):
+    _fields_ = [("overlap", ctypes.c_float * (2 * 4096))]
+
+
 def build(arch=None, out=None):
     cmd = ["make", "-C", ODIR, "-s"]
     if arch:
@@ -51,6 +59,18 @@ def load(path=None):
     lib.oracle_mp3_frame.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int]
     lib.oracle_mp3_polyphase.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_void_p]
+    lib.oracle_imdct.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+    lib.oracle_fft_inplace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.oracle_aac_synth.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p]
+    lib.oracle_aac_tns.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    lib.oracle_aac_batch.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
+    lib.oracle_aac_window.restype = c_f32p
+    lib.oracle_vorbis_floor1.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+    lib.oracle_vorbis_batch.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                                                ctypes.c_int]
+    lib.oracle_vorbis_window.restype = c_f32p
+    lib.oracle_vorbis_inverse_db.restype = ctypes.c_float
     return lib
 
 
