@@ -30,6 +30,24 @@ MP3_RUN_DTYPE = np.dtype([
 ])
 assert MP3_RUN_DTYPE.itemsize == 16
 
+# AAC / Vorbis structs (include/symgpu.h)
+AAC_UNIT_DTYPE = np.dtype([("window_sequence", "u1"), ("window_shape", "u1"), ("prev_window_shape", "u1"),
+                           ("n_tns", "u1"), ("tns_first", "<u4"), ("reserved", "<u4", (2,))])
+AAC_TNS_DTYPE = np.dtype([("start", "<u2"), ("end", "<u2"), ("order", "u1"), ("direction", "u1"), ("reserved", "<u2"),
+                          ("lpc", "<f4", (20,))])
+AAC_RUN_DTYPE = np.dtype([("stream", "<u4"), ("first_frame", "<u4"), ("n_frames", "<u4"), ("channels", "u1"),
+                          ("reserved", "u1", (3,))])
+VORBIS_FLOOR1_DTYPE = np.dtype([("multiplier", "u1"), ("n_posts", "u1"), ("x_list", "<u2", (65,)), ("low", "u1", (65,)),
+                                ("high", "u1", (65,)), ("sort_order", "u1", (65,)), ("reserved", "u1", (5,))])
+VORBIS_STREAM_DTYPE = np.dtype([("bs0_exp", "u1"), ("bs1_exp", "u1"), ("channels", "u1"), ("coupled", "u1")])
+VORBIS_UNIT_DTYPE = np.dtype([("block_flag", "u1"), ("prev_block_flag", "u1"), ("do_not_decode", "u1", (2,)),
+                              ("floor", "<u2", (2,)), ("reserved", "u1", (8,))])
+VORBIS_RUN_DTYPE = np.dtype([("stream", "<u4"), ("first_packet", "<u4"), ("n_packets", "<u4"), ("reserved", "<u4")])
+assert AAC_UNIT_DTYPE.itemsize == 16 and AAC_TNS_DTYPE.itemsize == 88 and AAC_RUN_DTYPE.itemsize == 16
+assert VORBIS_FLOOR1_DTYPE.itemsize == 332 and VORBIS_STREAM_DTYPE.itemsize == 4
+assert VORBIS_UNIT_DTYPE.itemsize == 16 and VORBIS_RUN_DTYPE.itemsize == 16
+AAC_ONLY_LONG, AAC_LONG_START, AAC_EIGHT_SHORT, AAC_LONG_STOP = 0, 1, 2, 3
+
 MP3_LONG, MP3_START, MP3_SHORT, MP3_END = 0, 1, 2, 3
 F_MIXED, F_SCALEFAC_SCALE, F_PREFLAG, F_SFC_LSB = 1, 2, 4, 8
 F_MID_SIDE, F_INTENSITY, F_MPEG1, F_MUTE = 16, 32, 64, 128
@@ -76,6 +94,24 @@ def lib():
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, vp, vp, vp, u32, u32, vp]
+    L.symgpu_aac_streams_alloc.restype = ctypes.c_int
+    L.symgpu_aac_streams_alloc.argtypes = [vp, u32]
+    L.symgpu_aac_stream_reset.restype = ctypes.c_int
+    L.symgpu_aac_stream_reset.argtypes = [vp, u32]
+    for name in ("symgpu_aac_synth_host", "symgpu_aac_synth_dev"):
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, vp]
+    L.symgpu_vorbis_streams_set.restype = ctypes.c_int
+    L.symgpu_vorbis_streams_set.argtypes = [vp, vp, u32]
+    L.symgpu_vorbis_floors_set.restype = ctypes.c_int
+    L.symgpu_vorbis_floors_set.argtypes = [vp, vp, u32]
+    L.symgpu_vorbis_stream_reset.restype = ctypes.c_int
+    L.symgpu_vorbis_stream_reset.argtypes = [vp, u32]
+    for name in ("symgpu_vorbis_synth_host", "symgpu_vorbis_synth_dev"):
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, vp]
     _LIB = L
     return L
 

@@ -1,0 +1,62 @@
+// Host <-> kernel interface of the AAC and Vorbis synthesis kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/symgpu.h"
+#include "tables.h"
+
+namespace symgpu {
+
+enum : uint8_t { kChunkLoadState = 1, kChunkStoreState = 2 };
+
+// One CTA's work: `count` consecutive frames / packets of one stream (AAC: of one channel).
+struct CodecChunk {
+    uint32_t first;   // batch index of the first frame / packet
+    uint32_t stream;  // state slot
+    uint16_t count;
+    uint8_t channel;  // AAC only
+    uint8_t flags;    // kChunkLoadState: starts its run (take state from HBM) | kChunkStoreState: ends it
+    uint32_t pad;
+};
+static_assert(sizeof(CodecChunk) == 16, "CodecChunk is 16 bytes");
+
+constexpr int kAacChunkFrames = 8;
+constexpr int kVorbisChunkPackets = 8;
+constexpr int kVorbisStateFloats = 2 * 4096; // overlap of both channels, blocksize_1 <= 8192
+
+struct AacArgs {
+    const symgpu_aac_unit* units;
+    const symgpu_aac_tns* tns;
+    const float* coeffs;
+    const float* tns_scratch;   // same buffer as tns_scratch_rw, read side
+    float* tns_scratch_rw;
+    float* pcm;
+    const CodecChunk* chunks;
+    float* states;              // [n_streams][2 generations][2 channels][1024]
+    uint32_t* gen;
+    unsigned* done;
+    const CodecTables* tab;
+};
+
+struct VorbisArgs {
+    const symgpu_vorbis_unit* units;
+    const uint16_t* floor_y;
+    const float* residue;
+    float* pcm;
+    const CodecChunk* chunks;
+    const symgpu_vorbis_stream* streams;
+    const symgpu_vorbis_floor1* floors;
+    uint32_t n_floors;
+    uint32_t slot;              // floats per channel slot in residue / pcm
+    float* states;              // [n_streams][2 generations][kVorbisStateFloats]
+    uint32_t* gen;
+    unsigned* done;
+    const CodecTables* tab;
+};
+
+cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, cudaStream_t stream);
+cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream);
+
+} // namespace symgpu

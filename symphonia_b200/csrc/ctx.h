@@ -1,0 +1,94 @@
+// Internal context definition shared by symgpu.cpp (MP3 + context) and symgpu_codecs.cpp (AAC, Vorbis).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/symgpu.h"
+#include "codec_kernels.h"
+#include "mp3_kernel.h"
+#include "tables.h"
+
+struct symgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char cuda_err[256] = {0};
+    uint64_t launches = 0;
+    // tables
+    symgpu::Mp3Tables* d_mp3_tab = nullptr;
+    // MP3 streams
+    symgpu::Mp3StreamState* d_mp3_states = nullptr; // [n][2]
+    uint32_t* d_mp3_gen = nullptr;           // [n] + 1 word: retired-CTA counter
+    uint32_t n_mp3_streams = 0;
+    // tile list (host staging is pinned; cached while the caller repeats the same runs)
+    symgpu::Mp3Tile* d_tiles = nullptr;
+    symgpu::Mp3Tile* h_tiles = nullptr;
+    size_t tiles_cap = 0;
+    std::vector<symgpu_mp3_run> cached_runs;
+    uint32_t cached_frames = 0;
+    int cached_tiles = 0;
+    // staging for the host entry points
+    void* d_stage = nullptr;
+    size_t stage_cap = 0;
+    // ---- AAC / Vorbis ----
+    symgpu::CodecTables* d_codec_tab = nullptr;
+    symgpu::CodecChunk* d_chunks = nullptr;
+    symgpu::CodecChunk* h_chunks = nullptr;
+    size_t chunks_cap = 0;
+    float* d_aac_states = nullptr;   // [n][2 gen][2 ch][1024]
+    uint32_t* d_aac_gen = nullptr;   // [n] + retired-CTA counter
+    uint32_t n_aac_streams = 0;
+    float* d_aac_scratch = nullptr;  // TNS output, same shape as the batch spectra
+    size_t aac_scratch_cap = 0;
+    symgpu_vorbis_stream* d_vorbis_streams = nullptr;
+    std::vector<symgpu_vorbis_stream> h_vorbis_streams;
+    symgpu_vorbis_floor1* d_vorbis_floors = nullptr;
+    uint32_t n_vorbis_floors = 0;
+    float* d_vorbis_states = nullptr; // [n][2 gen][kVorbisStateFloats]
+    uint32_t* d_vorbis_gen = nullptr;
+    uint32_t n_vorbis_streams = 0;
+};
+
+namespace symgpu_detail {
+
+inline symgpu_status cuda_fail(symgpu_ctx* ctx, cudaError_t e, const char* where) {
+    if (ctx) std::snprintf(ctx->cuda_err, sizeof ctx->cuda_err, "%s: %s", where, cudaGetErrorString(e));
+    return SYMGPU_ERR_CUDA;
+}
+
+#define CU(ctx, call)                                                   \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return cuda_fail((ctx), e_, #call);      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+
+// Grows the scratch/staging buffer of a context (synchronises the stream first).
+inline symgpu_status ensure_stage(symgpu_ctx* ctx, size_t need) {
+    if (need <= ctx->stage_cap) return SYMGPU_OK;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_cap = 0;
+    e = cudaMalloc(&ctx->d_stage, need);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(stage)");
+    ctx->stage_cap = need;
+    return SYMGPU_OK;
+}
+
+} // namespace symgpu_detail

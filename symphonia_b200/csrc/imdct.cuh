@@ -1,0 +1,194 @@
+// Power-of-two IMDCT shared by the AAC and Vorbis kernels: the GPU form of symphonia-core's
+// `Imdct::imdct` (dsp/mdct.rs:67-146) over its in-tree radix-2 FFT (dsp/fft/no_simd.rs).
+//
+// The reference runs, per block: pre-twiddle -> bit reversal -> fft2/4/8/16/32 base cases ->
+// breadth-first merges -> post-twiddle.  Here a group of threads owns one block (or a batch of equal
+// blocks) in shared memory and executes the SAME butterfly network, three levels per pass with the
+// eight points of a thread held in registers between levels.  Every butterfly performs exactly the
+// reference's operations on the reference's operands:
+//   level size <= 32: k = 0 -> q = o; k = N/4 -> q = (o.im, -o.re); k = N/8, 3N/8 -> the 1/sqrt(2)
+//     forms of no_simd.rs:302-305/312/320; any other k -> literal * o  (num-complex Mul);
+//   level size >= 64: q = o * W[k] from the f64-built tables (no_simd.rs:16-36, merge :222-238).
+// Lanes that need different rules compute the candidate forms and SELECT (no divergent branches);
+// the selected value is bit-identical to what the reference's specialised code computes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace symgpu {
+
+constexpr float kFrac1Sqrt2F = 0.707106781186547524400844362104849039f;
+
+// Device-side tables (global memory, built on the host in tables.cpp).
+struct FftTables {
+    float2 lit16[8];       // (cos(pi k/8), -sin(pi k/8)), k = 0..7   -- level-16 literals
+    float2 lit32[16];      // (cos(pi k/16), -sin(pi k/16)), k = 0..15 -- level-32 literals
+    float2 merge[2048 - 32]; // level size s >= 64: W_s[k] at merge[s/2 - 32 + k], s = 64 .. 4096
+};
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// num-complex: (a+bi)(c+di) = (ac - bd) + (ad + bc)i
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// Shared-memory index of logical complex element p: one pad element per 8 keeps the stride-8
+// accesses of the first pass on distinct banks.
+__device__ __forceinline__ int zpad(int p) { return p + (p >> 3); }
+__host__ __device__ constexpr int zpad_len(int n) { return n + (n >> 3) + 1; }
+
+// q = o "times" the level-`size` twiddle k, with the reference's rules.  `size` is a compile-time
+// constant at every call site; k is per-thread.
+template <int SIZE>
+__device__ __forceinline__ float2 twiddled(float2 o, int k, const FftTables* __restrict__ ft) {
+    if constexpr (SIZE == 2) {
+        return o;
+    } else if constexpr (SIZE == 4) {
+        return k == 0 ? o : make_float2(o.y, -o.x);
+    } else if constexpr (SIZE <= 32) {
+        constexpr int half = SIZE / 2;
+        const float a = kFrac1Sqrt2F * o.x, b = kFrac1Sqrt2F * o.y;      // k = N/8
+        const float na = -kFrac1Sqrt2F * o.x, nb = -kFrac1Sqrt2F * o.y;  // k = 3N/8
+        float2 q;
+        if constexpr (SIZE == 8) {
+            q = o; // every k of an 8-point level is special; placeholder for k = 0
+        } else {
+            const float2 w = SIZE == 16 ? ft->lit16[k] : ft->lit32[k];
+            q = cmul(w, o); // literal on the left (no_simd.rs:309 ...)
+        }
+        if (k == 0) q = o;
+        if (4 * k == half) q = make_float2(a + b, b - a);
+        if (2 * k == half) q = make_float2(o.y, -o.x);
+        if (4 * k == 3 * half) q = make_float2(na - nb, na + nb);
+        return q;
+    } else {
+        return cmul(o, ft->merge[SIZE / 2 - 32 + k]); // merge(): o * w
+    }
+}
+
+// NL butterfly levels on the R = 2^NL register points of one thread.  The points are logical
+// elements base + j * stride (stride = 2^(L0-1) = half of the first level's size).
+template <int L0, int NL>
+__device__ __forceinline__ void levels_in_registers(float2 (&v)[1 << NL], int t_in_stride, const FftTables* __restrict__ ft) {
+    constexpr int R = 1 << NL;
+    constexpr int stride = 1 << (L0 - 1);
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int span = 1 << l; // register distance of the butterfly partners
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if ((j & span) == 0) {
+                // twiddle index within the half: (position of element j) mod (stride * span)
+                const int k = t_in_stride + stride * (j & (span - 1));
+                float2 q;
+                // level size = 2 * stride * span
+                if (l == 0) q = twiddled<2 * stride>(v[j + span], k, ft);
+                else if (l == 1) q = twiddled<4 * stride>(v[j + span], k, ft);
+                else q = twiddled<8 * stride>(v[j + span], k, ft);
+                const float2 p = v[j];
+                v[j] = cadd(p, q);
+                v[j + span] = csub(p, q);
+            }
+        }
+    }
+}
+
+// One pass over `n_pts` logical points (possibly several independent blocks laid end to end, each a
+// multiple of 2^(L0+NL-1) long): levels L0 .. L0+NL-1.
+template <int L0, int NL>
+__device__ __forceinline__ void fft_pass(float2* z, int n_pts, int tid, int n_threads, const FftTables* __restrict__ ft) {
+    constexpr int R = 1 << NL;
+    constexpr int stride = 1 << (L0 - 1);
+    for (int t = tid; t < n_pts / R; t += n_threads) {
+        const int t_in = t & (stride - 1);
+        const int base = (t >> (L0 - 1)) * (stride * R) + t_in;
+        float2 v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = z[zpad(base + j * stride)];
+        levels_in_registers<L0, NL>(v, t_in, ft);
+#pragma unroll
+        for (int j = 0; j < R; ++j) z[zpad(base + j * stride)] = v[j];
+    }
+}
+
+// Forward FFT of `batch` independent blocks of 2^LOG2 complex points stored consecutively in z
+// (already in bit-reversed order).  The whole CTA takes part (barriers are __syncthreads).
+template <int LOG2>
+__device__ __forceinline__ void fft_levels(float2* z, int batch, int tid, int n_threads, const FftTables* __restrict__ ft) {
+    const int n_pts = batch << LOG2;
+    static_assert(LOG2 >= 4 && LOG2 <= 11, "FFT sizes 16..2048");
+    fft_pass<1, 3>(z, n_pts, tid, n_threads, ft);
+    __syncthreads();
+    if constexpr (LOG2 == 4) {
+        fft_pass<4, 1>(z, n_pts, tid, n_threads, ft);
+    } else if constexpr (LOG2 == 5) {
+        fft_pass<4, 2>(z, n_pts, tid, n_threads, ft);
+    } else {
+        fft_pass<4, 3>(z, n_pts, tid, n_threads, ft);
+        if constexpr (LOG2 > 6) {
+            __syncthreads();
+            if constexpr (LOG2 == 7) fft_pass<7, 1>(z, n_pts, tid, n_threads, ft);
+            else if constexpr (LOG2 == 8) fft_pass<7, 2>(z, n_pts, tid, n_threads, ft);
+            else {
+                fft_pass<7, 3>(z, n_pts, tid, n_threads, ft);
+                if constexpr (LOG2 > 9) {
+                    __syncthreads();
+                    if constexpr (LOG2 == 10) fft_pass<10, 1>(z, n_pts, tid, n_threads, ft);
+                    else fft_pass<10, 2>(z, n_pts, tid, n_threads, ft);
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// IMDCT of `batch` blocks: spec [batch][N] (shared) -> out [batch][2N] (shared), N = 2^(LOG2+1)
+// spectral lines per block, FFT size n2 = 2^LOG2.  tw = Imdct.twiddle (n2 complex).  z is scratch of
+// zpad_len(batch * n2) complex.  All `n_threads` threads of the group must call this.
+template <int LOG2>
+__device__ __forceinline__ void imdct_blocks(const float* spec, float* out, float2* z, int batch,
+                                             const float2* __restrict__ tw, const FftTables* __restrict__ ft, int tid,
+                                             int n_threads) {
+    constexpr int n2 = 1 << LOG2, n = 2 * n2, n4 = n2 / 2;
+    // Pre-twiddle (mdct.rs:81-88) fused with the bit-reversal permutation (no_simd.rs:101-107).
+    for (int e = tid; e < batch * n2; e += n_threads) {
+        const int b = e >> LOG2, i = e & (n2 - 1);
+        const float* s = spec + b * n;
+        const float even = s[2 * i];
+        const float odd = -s[n - 1 - 2 * i];
+        const float2 w = __ldg(tw + i);
+        const float re = odd * w.y - even * w.x;
+        const float im = odd * w.x + even * w.y;
+        const int r = (int)(__brev((unsigned)i) >> (32 - LOG2));
+        z[zpad((b << LOG2) + r)] = make_float2(re, im);
+    }
+    __syncthreads();
+    fft_levels<LOG2>(z, batch, tid, n_threads, ft);
+    // Post-twiddle (mdct.rs:100-137): val = w * conj(x), scattered into the four quarters.
+    for (int e = tid; e < batch * n2; e += n_threads) {
+        const int b = e >> LOG2, k = e & (n2 - 1);
+        const float2 x = z[zpad(e)];
+        const float2 w = __ldg(tw + k);
+        const float2 val = cmul(w, make_float2(x.x, -x.y));
+        float* o = out + b * 2 * n;
+        if (k < n4) {
+            const int fi = 2 * k, ri = n2 - 1 - 2 * k;
+            o[ri] = -val.y;
+            o[n2 + fi] = val.y;
+            o[2 * n2 + ri] = val.x;
+            o[3 * n2 + fi] = val.x;
+        } else {
+            const int i = k - n4;
+            const int fi = 2 * i, ri = n2 - 1 - 2 * i;
+            o[fi] = -val.x;
+            o[n2 + ri] = val.x;
+            o[2 * n2 + fi] = val.y;
+            o[3 * n2 + ri] = val.y;
+        }
+    }
+    __syncthreads();
+}
+
+} // namespace symgpu

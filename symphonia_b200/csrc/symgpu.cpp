@@ -11,59 +11,13 @@
 #include <new>
 #include <vector>
 
-#include "../../include/symgpu.h"
-#include "mp3_kernel.h"
-#include "tables.h"
+#include "ctx.h"
+
 
 using namespace symgpu;
-
-struct symgpu_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    char cuda_err[256] = {0};
-    uint64_t launches = 0;
-    // tables
-    Mp3Tables* d_mp3_tab = nullptr;
-    // MP3 streams
-    Mp3StreamState* d_mp3_states = nullptr; // [n][2]
-    uint32_t* d_mp3_gen = nullptr;           // [n] + 1 word: retired-CTA counter
-    uint32_t n_mp3_streams = 0;
-    // tile list (host staging is pinned; cached while the caller repeats the same runs)
-    Mp3Tile* d_tiles = nullptr;
-    Mp3Tile* h_tiles = nullptr;
-    size_t tiles_cap = 0;
-    std::vector<symgpu_mp3_run> cached_runs;
-    uint32_t cached_frames = 0;
-    int cached_tiles = 0;
-    // staging for the host entry point
-    void* d_stage = nullptr;
-    size_t stage_cap = 0;
-};
+using namespace symgpu_detail;
 
 namespace {
-
-symgpu_status cuda_fail(symgpu_ctx* ctx, cudaError_t e, const char* where) {
-    if (ctx) std::snprintf(ctx->cuda_err, sizeof ctx->cuda_err, "%s: %s", where, cudaGetErrorString(e));
-    return SYMGPU_ERR_CUDA;
-}
-
-#define CU(ctx, call)                                                   \
-    do {                                                                \
-        cudaError_t e_ = (call);                                        \
-        if (e_ != cudaSuccess) return cuda_fail((ctx), e_, #call);      \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 
 // Cuts the caller's runs into per-CTA tiles (mp3_kernel.h).  Returns SYMGPU_OK or an argument /
 // limit error; never touches the device.
@@ -223,6 +177,16 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
     if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->d_codec_tab) cudaFree(ctx->d_codec_tab);
+    if (ctx->d_chunks) cudaFree(ctx->d_chunks);
+    if (ctx->h_chunks) cudaFreeHost(ctx->h_chunks);
+    if (ctx->d_aac_states) cudaFree(ctx->d_aac_states);
+    if (ctx->d_aac_gen) cudaFree(ctx->d_aac_gen);
+    if (ctx->d_aac_scratch) cudaFree(ctx->d_aac_scratch);
+    if (ctx->d_vorbis_streams) cudaFree(ctx->d_vorbis_streams);
+    if (ctx->d_vorbis_floors) cudaFree(ctx->d_vorbis_floors);
+    if (ctx->d_vorbis_states) cudaFree(ctx->d_vorbis_states);
+    if (ctx->d_vorbis_gen) cudaFree(ctx->d_vorbis_gen);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -1,0 +1,293 @@
+// AAC-LC and Vorbis entry points of the C ABI (include/symgpu.h).  Like the MP3 ones they only
+// stage buffers, cut runs into per-CTA chunks and launch CUDA kernels: there is no CPU path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "ctx.h"
+
+using namespace symgpu;
+using namespace symgpu_detail;
+
+namespace {
+
+symgpu_status upload_chunks(symgpu_ctx* ctx, const std::vector<CodecChunk>& chunks) {
+    // Chunk lists are small; rewriting them needs the previous launch to have consumed the old list.
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (chunks.size() > ctx->chunks_cap) {
+        if (ctx->d_chunks) cudaFree(ctx->d_chunks);
+        if (ctx->h_chunks) cudaFreeHost(ctx->h_chunks);
+        ctx->d_chunks = nullptr;
+        ctx->h_chunks = nullptr;
+        ctx->chunks_cap = 0;
+        const size_t cap = chunks.size() * 2 + 64;
+        CU(ctx, cudaMalloc(&ctx->d_chunks, cap * sizeof(CodecChunk)));
+        CU(ctx, cudaMallocHost(&ctx->h_chunks, cap * sizeof(CodecChunk)));
+        ctx->chunks_cap = cap;
+    }
+    std::memcpy(ctx->h_chunks, chunks.data(), chunks.size() * sizeof(CodecChunk));
+    CU(ctx, cudaMemcpyAsync(ctx->d_chunks, ctx->h_chunks, chunks.size() * sizeof(CodecChunk), cudaMemcpyHostToDevice, ctx->stream));
+    return SYMGPU_OK;
+}
+
+// Splits [0, n) into ceil(n / per) near-equal pieces.
+template <typename F>
+void split_even(uint32_t n, uint32_t per, F&& f) {
+    const uint32_t pieces = (n + per - 1) / per;
+    uint32_t lo = 0;
+    for (uint32_t k = 0; k < pieces; ++k) {
+        const uint32_t hi = (uint32_t)(((uint64_t)n * (k + 1)) / pieces);
+        f(lo, hi, k == 0, k + 1 == pieces);
+        lo = hi;
+    }
+}
+
+symgpu_status ensure_codec_tables(symgpu_ctx* ctx) {
+    if (ctx->d_codec_tab) return SYMGPU_OK;
+    const CodecTables& t = codec_tables_host();
+    CU(ctx, cudaMalloc(&ctx->d_codec_tab, sizeof t));
+    CU(ctx, cudaMemcpy(ctx->d_codec_tab, &t, sizeof t, cudaMemcpyHostToDevice));
+    return SYMGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+// ---- AAC ---------------------------------------------------------------------------------------
+
+symgpu_status symgpu_aac_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams) {
+    if (!ctx || n_streams == 0) return SYMGPU_ERR_ARG;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    symgpu_status s = ensure_codec_tables(ctx);
+    if (s != SYMGPU_OK) return s;
+    if (ctx->d_aac_states) cudaFree(ctx->d_aac_states);
+    if (ctx->d_aac_gen) cudaFree(ctx->d_aac_gen);
+    ctx->d_aac_states = nullptr;
+    ctx->d_aac_gen = nullptr;
+    ctx->n_aac_streams = 0;
+    const size_t bytes = (size_t)n_streams * 2 * 2 * 1024 * sizeof(float);
+    CU(ctx, cudaMalloc(&ctx->d_aac_states, bytes));
+    CU(ctx, cudaMemset(ctx->d_aac_states, 0, bytes));
+    CU(ctx, cudaMalloc(&ctx->d_aac_gen, ((size_t)n_streams + 1) * sizeof(uint32_t)));
+    CU(ctx, cudaMemset(ctx->d_aac_gen, 0, ((size_t)n_streams + 1) * sizeof(uint32_t)));
+    ctx->n_aac_streams = n_streams;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_aac_stream_reset(symgpu_ctx* ctx, uint32_t stream) {
+    if (!ctx) return SYMGPU_ERR_ARG;
+    if (stream >= ctx->n_aac_streams) return SYMGPU_ERR_LIMIT;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaMemsetAsync(ctx->d_aac_states + (size_t)stream * 4096, 0, 4096 * sizeof(float), ctx->stream));
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units, const symgpu_aac_tns* tns,
+                                   uint32_t n_tns, const float* coeffs, const symgpu_aac_run* runs, uint32_t n_runs,
+                                   uint32_t n_frames, float* pcm) {
+    if (!ctx || !units || !coeffs || !runs || !pcm || (n_tns && !tns)) return SYMGPU_ERR_ARG;
+    if (n_frames == 0) return SYMGPU_OK;
+    if (!ctx->d_aac_states) return SYMGPU_ERR_LIMIT;
+    DeviceGuard guard(ctx->device);
+    std::vector<CodecChunk> chunks;
+    uint64_t covered = 0;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_aac_run& run = runs[r];
+        const int n_ch = run.channels ? run.channels : 2;
+        if (n_ch < 1 || n_ch > 2) return SYMGPU_ERR_ARG;
+        if (run.n_frames == 0) continue;
+        if ((uint64_t)run.first_frame + run.n_frames > n_frames) return SYMGPU_ERR_ARG;
+        if (run.stream >= ctx->n_aac_streams) return SYMGPU_ERR_LIMIT;
+        covered += run.n_frames;
+        for (int ch = 0; ch < n_ch; ++ch)
+            split_even(run.n_frames, kAacChunkFrames, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
+                CodecChunk c{};
+                c.first = run.first_frame + lo;
+                c.stream = run.stream;
+                c.count = (uint16_t)(hi - lo);
+                c.channel = (uint8_t)ch;
+                c.flags = (uint8_t)((first ? kChunkLoadState : 0) | (last ? kChunkStoreState : 0));
+                chunks.push_back(c);
+            });
+    }
+    if (covered != n_frames) return SYMGPU_ERR_ARG;
+    symgpu_status s = upload_chunks(ctx, chunks);
+    if (s != SYMGPU_OK) return s;
+    const size_t spec_bytes = (size_t)n_frames * 2 * 1024 * sizeof(float);
+    if (n_tns && spec_bytes > ctx->aac_scratch_cap) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_aac_scratch) cudaFree(ctx->d_aac_scratch);
+        ctx->d_aac_scratch = nullptr;
+        ctx->aac_scratch_cap = 0;
+        CU(ctx, cudaMalloc(&ctx->d_aac_scratch, spec_bytes));
+        ctx->aac_scratch_cap = spec_bytes;
+    }
+    AacArgs a{units, tns, coeffs, ctx->d_aac_scratch, ctx->d_aac_scratch, pcm, ctx->d_chunks, ctx->d_aac_states,
+              ctx->d_aac_gen, ctx->d_aac_gen + ctx->n_aac_streams, ctx->d_codec_tab};
+    CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, (int)chunks.size(), ctx->stream));
+    ctx->launches += n_tns ? 2 : 1;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_aac_synth_host(symgpu_ctx* ctx, const symgpu_aac_unit* units, const symgpu_aac_tns* tns,
+                                    uint32_t n_tns, const float* coeffs, const symgpu_aac_run* runs, uint32_t n_runs,
+                                    uint32_t n_frames, float* pcm) {
+    if (!ctx || !units || !coeffs || !runs || !pcm || (n_tns && !tns)) return SYMGPU_ERR_ARG;
+    if (n_frames == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    const size_t unit_bytes = (size_t)n_frames * 2 * sizeof(symgpu_aac_unit);
+    const size_t spec_bytes = (size_t)n_frames * 2 * 1024 * sizeof(float);
+    const size_t tns_bytes = ((size_t)n_tns * sizeof(symgpu_aac_tns) + 15) & ~(size_t)15;
+    symgpu_status s = ensure_stage(ctx, 2 * spec_bytes + unit_bytes + tns_bytes);
+    if (s != SYMGPU_OK) return s;
+    char* base = static_cast<char*>(ctx->d_stage);
+    float* d_spec = reinterpret_cast<float*>(base);
+    float* d_pcm = reinterpret_cast<float*>(base + spec_bytes);
+    symgpu_aac_unit* d_units = reinterpret_cast<symgpu_aac_unit*>(base + 2 * spec_bytes);
+    symgpu_aac_tns* d_tns = reinterpret_cast<symgpu_aac_tns*>(base + 2 * spec_bytes + unit_bytes);
+    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_tns) CU(ctx, cudaMemcpyAsync(d_tns, tns, (size_t)n_tns * sizeof(symgpu_aac_tns), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_spec, coeffs, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    bool mono = false;
+    for (uint32_t r = 0; r < n_runs; ++r) mono |= runs[r].channels == 1;
+    if (mono) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
+    s = symgpu_aac_synth_dev(ctx, d_units, d_tns, n_tns, d_spec, runs, n_runs, n_frames, d_pcm);
+    if (s != SYMGPU_OK) return s;
+    CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SYMGPU_OK;
+}
+
+// ---- Vorbis ------------------------------------------------------------------------------------
+
+symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_stream* streams, uint32_t n_streams) {
+    if (!ctx || !streams || n_streams == 0) return SYMGPU_ERR_ARG;
+    for (uint32_t i = 0; i < n_streams; ++i) {
+        const symgpu_vorbis_stream& s = streams[i];
+        if (s.bs0_exp < 6 || s.bs1_exp > 13 || s.bs0_exp > s.bs1_exp) return SYMGPU_ERR_ARG; // lib.rs:404-417
+        if (s.channels < 1 || s.channels > 2) return SYMGPU_ERR_UNSUPPORTED;
+        if (s.coupled && s.channels != 2) return SYMGPU_ERR_ARG;
+    }
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    symgpu_status st = ensure_codec_tables(ctx);
+    if (st != SYMGPU_OK) return st;
+    if (ctx->d_vorbis_streams) cudaFree(ctx->d_vorbis_streams);
+    if (ctx->d_vorbis_states) cudaFree(ctx->d_vorbis_states);
+    if (ctx->d_vorbis_gen) cudaFree(ctx->d_vorbis_gen);
+    ctx->d_vorbis_streams = nullptr;
+    ctx->d_vorbis_states = nullptr;
+    ctx->d_vorbis_gen = nullptr;
+    ctx->n_vorbis_streams = 0;
+    CU(ctx, cudaMalloc(&ctx->d_vorbis_streams, (size_t)n_streams * sizeof *streams));
+    CU(ctx, cudaMemcpy(ctx->d_vorbis_streams, streams, (size_t)n_streams * sizeof *streams, cudaMemcpyHostToDevice));
+    const size_t bytes = (size_t)n_streams * 2 * kVorbisStateFloats * sizeof(float);
+    CU(ctx, cudaMalloc(&ctx->d_vorbis_states, bytes));
+    CU(ctx, cudaMemset(ctx->d_vorbis_states, 0, bytes));
+    CU(ctx, cudaMalloc(&ctx->d_vorbis_gen, ((size_t)n_streams + 1) * sizeof(uint32_t)));
+    CU(ctx, cudaMemset(ctx->d_vorbis_gen, 0, ((size_t)n_streams + 1) * sizeof(uint32_t)));
+    ctx->h_vorbis_streams.assign(streams, streams + n_streams);
+    ctx->n_vorbis_streams = n_streams;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
+    if (!ctx || !floors || n_floors == 0) return SYMGPU_ERR_ARG;
+    for (uint32_t i = 0; i < n_floors; ++i) {
+        const symgpu_vorbis_floor1& f = floors[i];
+        if (f.multiplier < 1 || f.multiplier > 4 || f.n_posts < 2 || f.n_posts > 65) return SYMGPU_ERR_ARG;
+        for (int k = 0; k < f.n_posts; ++k)
+            if (f.low[k] >= f.n_posts || f.high[k] >= f.n_posts || f.sort_order[k] >= f.n_posts) return SYMGPU_ERR_ARG;
+    }
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_vorbis_floors) cudaFree(ctx->d_vorbis_floors);
+    ctx->d_vorbis_floors = nullptr;
+    ctx->n_vorbis_floors = 0;
+    CU(ctx, cudaMalloc(&ctx->d_vorbis_floors, (size_t)n_floors * sizeof *floors));
+    CU(ctx, cudaMemcpy(ctx->d_vorbis_floors, floors, (size_t)n_floors * sizeof *floors, cudaMemcpyHostToDevice));
+    ctx->n_vorbis_floors = n_floors;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_stream_reset(symgpu_ctx* ctx, uint32_t stream) {
+    if (!ctx) return SYMGPU_ERR_ARG;
+    if (stream >= ctx->n_vorbis_streams) return SYMGPU_ERR_LIMIT;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, cudaMemsetAsync(ctx->d_vorbis_states + (size_t)stream * 2 * kVorbisStateFloats, 0,
+                            2 * kVorbisStateFloats * sizeof(float), ctx->stream));
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit* units, const uint16_t* floor_y,
+                                      const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
+                                      uint32_t n_packets, uint32_t slot, float* pcm) {
+    if (!ctx || !units || !floor_y || !residue || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (n_packets == 0) return SYMGPU_OK;
+    if (!ctx->d_vorbis_states || !ctx->d_vorbis_floors) return SYMGPU_ERR_LIMIT;
+    DeviceGuard guard(ctx->device);
+    std::vector<CodecChunk> chunks;
+    uint64_t covered = 0;
+    int max_bs1 = 6;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_vorbis_run& run = runs[r];
+        if (run.n_packets == 0) continue;
+        if ((uint64_t)run.first_packet + run.n_packets > n_packets || run.reserved) return SYMGPU_ERR_ARG;
+        if (run.stream >= ctx->n_vorbis_streams) return SYMGPU_ERR_LIMIT;
+        const symgpu_vorbis_stream& cfg = ctx->h_vorbis_streams[run.stream];
+        if ((1u << (cfg.bs1_exp - 1)) > slot) return SYMGPU_ERR_ARG; // slot too small for this stream
+        max_bs1 = std::max(max_bs1, (int)cfg.bs1_exp);
+        covered += run.n_packets;
+        split_even(run.n_packets, kVorbisChunkPackets, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
+            CodecChunk c{};
+            c.first = run.first_packet + lo;
+            c.stream = run.stream;
+            c.count = (uint16_t)(hi - lo);
+            c.flags = (uint8_t)((first ? kChunkLoadState : 0) | (last ? kChunkStoreState : 0));
+            chunks.push_back(c);
+        });
+    }
+    if (covered != n_packets) return SYMGPU_ERR_ARG;
+    symgpu_status s = upload_chunks(ctx, chunks);
+    if (s != SYMGPU_OK) return s;
+    VorbisArgs a{units, floor_y, residue, pcm, ctx->d_chunks, ctx->d_vorbis_streams, ctx->d_vorbis_floors,
+                 ctx->n_vorbis_floors, slot, ctx->d_vorbis_states, ctx->d_vorbis_gen,
+                 ctx->d_vorbis_gen + ctx->n_vorbis_streams, ctx->d_codec_tab};
+    CU(ctx, vorbis_launch(a, (int)chunks.size(), max_bs1, ctx->stream));
+    ctx->launches += 1;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_synth_host(symgpu_ctx* ctx, const symgpu_vorbis_unit* units, const uint16_t* floor_y,
+                                       const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
+                                       uint32_t n_packets, uint32_t slot, float* pcm) {
+    if (!ctx || !units || !floor_y || !residue || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (n_packets == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    const size_t unit_bytes = (size_t)n_packets * sizeof(symgpu_vorbis_unit);
+    const size_t fy_bytes = ((size_t)n_packets * 2 * 65 * sizeof(uint16_t) + 15) & ~(size_t)15;
+    const size_t spec_bytes = (size_t)n_packets * 2 * slot * sizeof(float);
+    symgpu_status s = ensure_stage(ctx, 2 * spec_bytes + unit_bytes + fy_bytes);
+    if (s != SYMGPU_OK) return s;
+    char* base = static_cast<char*>(ctx->d_stage);
+    float* d_res = reinterpret_cast<float*>(base);
+    float* d_pcm = reinterpret_cast<float*>(base + spec_bytes);
+    symgpu_vorbis_unit* d_units = reinterpret_cast<symgpu_vorbis_unit*>(base + 2 * spec_bytes);
+    uint16_t* d_fy = reinterpret_cast<uint16_t*>(base + 2 * spec_bytes + unit_bytes);
+    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_fy, floor_y, (size_t)n_packets * 2 * 65 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_res, residue, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream)); // packets fill only (prev_n + n) / 4 of their slot
+    s = symgpu_vorbis_synth_dev(ctx, d_units, d_fy, d_res, runs, n_runs, n_packets, slot, d_pcm);
+    if (s != SYMGPU_OK) return s;
+    CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SYMGPU_OK;
+}
+
+} // extern "C"

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace symgpu {
 namespace {
@@ -191,6 +192,139 @@ const Mp3Tables& mp3_tables_host() {
         build_edges(*tab);
         build_line_maps(*tab);
         build_float_tables(*tab);
+    });
+    return *tab;
+}
+
+} // namespace symgpu
+
+// =============================================================================================
+// IMDCT codecs (AAC-LC, Vorbis)
+// =============================================================================================
+namespace symgpu {
+namespace {
+
+// floor1_inverse_dB_table of the Vorbis I specification as f32 bit patterns (the values the
+// reference's 8-digit literals parse to, floor.rs:21-86).
+const uint32_t kInverseDbBits[256] = {
+    0x33e4b43e, 0x33f39109, 0x3401b28b, 0x340a203c, 0x34131a23, 0x341ca960, 0x3426d7a7, 0x3431af4b,
+    0x343d3b50, 0x34498770, 0x3456a023, 0x346492b8, 0x34736d55, 0x34819f88, 0x348a0bfc, 0x34930493,
+    0x349c9269, 0x34a6bf32, 0x34b1953f, 0x34bd1f93, 0x34c969e4, 0x34d680ad, 0x34e47136, 0x34f349a6,
+    0x35018c88, 0x3509f7c0, 0x3512ef06, 0x351c7b76, 0x3526a6c0, 0x35317b37, 0x353d03da, 0x35494c5e,
+    0x3556613b, 0x35644fb9, 0x357325fc, 0x3581798a, 0x3589e386, 0x3592d97c, 0x359c6485, 0x35a68e52,
+    0x35b16133, 0x35bce825, 0x35c92edc, 0x35d641ce, 0x35e42e41, 0x35f30257, 0x3601668f, 0x3609cf4f,
+    0x3612c3f5, 0x361c4d98, 0x362675e8, 0x36314732, 0x363ccc74, 0x3649115e, 0x36562265, 0x36640cce,
+    0x3672deb8, 0x36815397, 0x3689bb1c, 0x3692ae72, 0x369c36af, 0x36a65d81, 0x36b12d35, 0x36bcb0c7,
+    0x36c8f3e4, 0x36d60301, 0x36e3eb60, 0x36f2bb1e, 0x370140a2, 0x3709a6eb, 0x371298f1, 0x371c1fc9,
+    0x3726451e, 0x3731133d, 0x373c951e, 0x3748d66f, 0x3755e3a2, 0x3763c9f7, 0x37729789, 0x37812daf,
+    0x378992be, 0x37928374, 0x379c08e6, 0x37a62cbe, 0x37b0f947, 0x37bc7979, 0x37c8b8fe, 0x37d5c447,
+    0x37e3a892, 0x37f273f8, 0x38011ac0, 0x38097e93, 0x38126df9, 0x381bf206, 0x38261462, 0x3830df56,
+    0x383c5dd8, 0x38489b92, 0x3855a4f2, 0x38638733, 0x3872506e, 0x388107d3, 0x38896a6b, 0x38925882,
+    0x389bdb2a, 0x38a5fc09, 0x38b0c568, 0x38bc423b, 0x38c87e29, 0x38d585a0, 0x38e365d9, 0x38f22ce8,
+    0x3900f4e9, 0x39095646, 0x3912430e, 0x391bc451, 0x3925e3b5, 0x3930ab7f, 0x393c26a2, 0x394860c5,
+    0x39556653, 0x39634483, 0x39720968, 0x3980e201, 0x39894224, 0x39922d9d, 0x399bad7b, 0x39a5cb63,
+    0x39b09199, 0x39bc0b0d, 0x39c84366, 0x39d5470b, 0x39e32332, 0x39f1e5ed, 0x3a00cf1d, 0x3a092e05,
+    0x3a121830, 0x3a1b96a9, 0x3a25b315, 0x3a3077b7, 0x3a3bef7c, 0x3a48260a, 0x3a5527c7, 0x3a6301e6,
+    0x3a71c278, 0x3a80bc3b, 0x3a8919e9, 0x3a9202c6, 0x3a9b7fdb, 0x3aa59acb, 0x3ab05dd8, 0x3abbd3ef,
+    0x3ac808b3, 0x3ad50888, 0x3ae2e09f, 0x3af19f07, 0x3b00a95c, 0x3b0905d0, 0x3b11ed5e, 0x3b1b690f,
+    0x3b258284, 0x3b3043fd, 0x3b3bb867, 0x3b47eb61, 0x3b54e94d, 0x3b62bf5d, 0x3b717b9c, 0x3b80967f,
+    0x3b88f1ba, 0x3b91d7f9, 0x3b9b5247, 0x3ba56a41, 0x3bb02a27, 0x3bbb9ce2, 0x3bc7ce12, 0x3bd4ca17,
+    0x3be29e20, 0x3bf15835, 0x3c0083a6, 0x3c08dda7, 0x3c11c298, 0x3c1b3b82, 0x3c255201, 0x3c301054,
+    0x3c3b8161, 0x3c47b0c8, 0x3c54aae5, 0x3c627ce8, 0x3c7134d4, 0x3c8070cf, 0x3c88c996, 0x3c91ad3a,
+    0x3c9b24c0, 0x3ca539c5, 0x3caff685, 0x3cbb65e5, 0x3cc79382, 0x3cd48bb9, 0x3ce25bb4, 0x3cf11179,
+    0x3d005dfb, 0x3d08b589, 0x3d1197df, 0x3d1b0e02, 0x3d25218d, 0x3d2fdcb9, 0x3d3b4a6d, 0x3d477640,
+    0x3d546c91, 0x3d623a85, 0x3d70ee22, 0x3d804b2a, 0x3d88a17f, 0x3d918288, 0x3d9af748, 0x3da50958,
+    0x3dafc2f2, 0x3dbb2ef8, 0x3dc75903, 0x3dd44d6d, 0x3de2195c, 0x3df0cad1, 0x3e00385b, 0x3e088d77,
+    0x3e116d33, 0x3e1ae090, 0x3e24f127, 0x3e2fa92e, 0x3e3b1387, 0x3e473bca, 0x3e542e4d, 0x3e61f837,
+    0x3e70a784, 0x3e80258f, 0x3e887973, 0x3e9157e2, 0x3e9ac9dc, 0x3ea4d8f9, 0x3eaf8f6d, 0x3ebaf81b,
+    0x3ec71e95, 0x3ed40f33, 0x3ee1d717, 0x3ef0843d, 0x3f0012c6, 0x3f086572, 0x3f114293, 0x3f1ab32b,
+    0x3f24c0ce, 0x3f2f75b1, 0x3f3adcb2, 0x3f470165, 0x3f53f01d, 0x3f61b5fb, 0x3f7060fb, 0x3f800000
+};
+
+void imdct_twiddles(Cplx* out, int n, double scale) { // mdct.rs:42-54
+    const double PI = 3.14159265358979323846264338327950288;
+    const int n2 = n / 2;
+    const double alpha = 1.0 / 8.0 + (std::signbit(scale) ? (double)n2 : 0.0);
+    const double pi_n = PI / (double)n;
+    const double root = std::sqrt(std::fabs(scale));
+    for (int k = 0; k < n2; ++k) {
+        const double theta = pi_n * (alpha + (double)k);
+        out[k].re = (float)(root * std::cos(theta));
+        out[k].im = (float)(root * std::sin(theta));
+    }
+}
+
+void fft_twiddles(Cplx* out, int size) { // no_simd.rs:16-36: (cos(pi k / half), -sin(pi k / half))
+    const double PI = 3.14159265358979323846264338327950288;
+    const int half = size / 2;
+    const double theta = PI / (double)half;
+    for (int k = 0; k < half; ++k) {
+        const double angle = theta * (double)k;
+        out[k].re = (float)std::cos(angle);
+        out[k].im = (float)(-std::sin(angle));
+    }
+}
+
+double bessel_i0(double x) { // aac/window.rs:56-63
+    double val = 1.0;
+    for (int n = 63; n >= 1; --n) {
+        val *= x / (double)(n * n);
+        val += 1.0;
+    }
+    return val;
+}
+
+void aac_sine_window(float* dst, int size) { // aac/window.rs:29-36: f32 arithmetic and f32 sin
+    const float pi = 3.14159265358979323846264338327950288f;
+    const float param = pi / (float)(2 * size);
+    for (int n = 0; n < size; ++n) dst[n] = std::sin(((float)n + 0.5f) * param) * 1.0f;
+}
+
+void aac_kbd_window(float* dst, int size, float alpha) { // aac/window.rs:37-52
+    const float pi = 3.14159265358979323846264338327950288f;
+    const float dlen = (float)size;
+    const float a = alpha * pi / dlen;
+    const double alpha2 = (double)(a * a);
+    std::vector<double> kb((size_t)size);
+    double sum = 0.0;
+    for (int n = 0; n < size; ++n) {
+        sum += bessel_i0((double)(n * (size - n)) * alpha2);
+        kb[(size_t)n] = sum;
+    }
+    sum += 1.0;
+    for (int n = 0; n < size; ++n) dst[n] = (float)std::sqrt(kb[(size_t)n] / sum);
+}
+
+void vorbis_window(float* dst, int bs) { // codec-vorbis/src/window.rs:11-24
+    const double half_pi = 1.57079632679489661923132169163975144;
+    const int len = bs / 2;
+    for (int i = 0; i < len; ++i) {
+        const double frac = half_pi * (((double)i + 0.5) / (double)len);
+        const double s = std::sin(frac);
+        dst[i] = (float)std::sin(half_pi * (s * s));
+    }
+}
+
+} // namespace
+
+const CodecTables& codec_tables_host() {
+    static CodecTables* tab = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        tab = new CodecTables();
+        std::memset(tab, 0, sizeof *tab);
+        fft_twiddles(tab->fft_lit16, 16);
+        fft_twiddles(tab->fft_lit32, 32);
+        for (int size = 64; size <= 4096; size <<= 1) fft_twiddles(tab->fft_merge + (size / 2 - 32), size);
+        imdct_twiddles(tab->aac_tw_long, 1024, 1.0 / 2048.0);
+        imdct_twiddles(tab->aac_tw_short, 128, 1.0 / 256.0);
+        for (int n2 = 16; n2 <= 2048; n2 <<= 1) imdct_twiddles(tab->vorbis_tw + (n2 - 16), 2 * n2, 1.0);
+        aac_sine_window(tab->aac_sine_long, 1024);
+        aac_sine_window(tab->aac_sine_short, 128);
+        aac_kbd_window(tab->aac_kbd_long, 1024, 4.0f);
+        aac_kbd_window(tab->aac_kbd_short, 128, 6.0f);
+        for (int bs = 64; bs <= 8192; bs <<= 1) vorbis_window(tab->vorbis_win + (bs / 2 - 32), bs);
+        std::memcpy(tab->vorbis_inverse_db, kInverseDbBits, sizeof kInverseDbBits);
     });
     return *tab;
 }

@@ -43,4 +43,29 @@ struct alignas(16) Mp3Tables {
 // Builds the tables (host libm).  Thread-safe, built once.
 const Mp3Tables& mp3_tables_host();
 
+// ---- tables of the power-of-two IMDCT codecs (AAC-LC, Vorbis) --------------------------------
+struct Cplx {
+    float re, im;
+};
+
+struct alignas(16) CodecTables {
+    // FFT (symphonia-core/src/dsp/fft/no_simd.rs): level-16 / level-32 literal twiddles and the
+    // f64-built merge tables of sizes 64..4096, size s at offset s/2 - 32.
+    Cplx fft_lit16[8];
+    Cplx fft_lit32[16];
+    Cplx fft_merge[2048 - 32];
+    // Imdct::new_scaled twiddles (symphonia-core/src/dsp/mdct.rs:35-60).
+    Cplx aac_tw_long[512];   // n = 1024, scale 1/2048   (aac/dsp.rs:49)
+    Cplx aac_tw_short[64];   // n = 128,  scale 1/256    (aac/dsp.rs:50)
+    Cplx vorbis_tw[4096 - 16]; // unscaled, n2 = 16..2048 complex at offset n2 - 16  (lib.rs:123-124)
+    // AAC windows (aac/window.rs:28-63), first halves.
+    float aac_sine_long[1024], aac_sine_short[128], aac_kbd_long[1024], aac_kbd_short[128];
+    // Vorbis power-sine window left halves (window.rs:11-24): blocksize bs at offset bs/2 - 32.
+    float vorbis_win[8192 - 32];
+    // floor1_inverse_dB_table (floor.rs:21-86).
+    float vorbis_inverse_db[256];
+};
+
+const CodecTables& codec_tables_host();
+
 } // namespace symgpu

@@ -1,0 +1,269 @@
+// Vorbis synthesis for sm_100a (codec-vorbis/src/lib.rs:250-315):
+//   floor-1 curve (floor.rs:568-653, :776-825)  ->  inverse coupling (lib.rs:252-278)
+//   -> floor * residue (lib.rs:282-292) -> IMDCT -> power-sine window + overlap-add (dsp.rs:68-145)
+//
+// One 64-thread CTA walks a chunk of consecutive packets of one stream (both channels, because the
+// coupling step mixes them) with the overlap line in shared memory.  A chunk that does not start its
+// run first recomputes the previous packet's IMDCT tail (one halo packet, output suppressed): the
+// overlap is overwritten by every packet, never accumulated (dsp.rs:125).
+//
+// Floor step 1 is an integer recurrence over <= 65 posts (one lane per channel); step 2 is evaluated
+// per spectral line in closed form: after d steps of render_line's error accumulator,
+//   y(d) = y0 + d*base + sign(dy) * floor(d*ady / adx)
+// which is the same integer the reference's loop reaches, so the table lookup is identical.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/symgpu.h"
+#include "codec_kernels.h"
+#include "imdct.cuh"
+#include "tables.h"
+
+namespace symgpu {
+namespace {
+
+constexpr int kVorbisThreads = 64;
+
+struct FloorPoints { // active posts in X order, built by step 1/2 of one channel
+    int x[68];
+    int16_t y[68];
+    int n;
+};
+
+__device__ __forceinline__ int render_point(int x0, int y0, int x1, int y1, int x) { // floor.rs:776-782
+    const int dy = y1 - y0;
+    const unsigned adx = (unsigned)(x1 - x0);
+    const unsigned err = (unsigned)abs(dy) * (unsigned)(x - x0);
+    const unsigned off = err / adx;
+    return dy < 0 ? y0 - (int)off : y0 + (int)off;
+}
+
+// Step 1 (floor.rs:568-625) + the sort-order walk of step 2 (floor.rs:627-653): one thread.
+__device__ void floor1_points(const symgpu_vorbis_floor1& s, const uint16_t* __restrict__ fy, int n_half, FloorPoints& out) {
+    int final_y[65];
+    unsigned long long flag = 3ull; // floor_step2_flag[0] = [1] = true
+    const int count = s.n_posts;
+    const int mult = s.multiplier;
+    const int range = mult == 1 ? 256 : mult == 2 ? 128 : mult == 3 ? 86 : 64;
+    final_y[0] = fy[0];
+    final_y[1] = fy[1];
+    for (int i = 2; i < count; ++i) {
+        const int lo = s.low[i], hi = s.high[i];
+        const int predicted = render_point(s.x_list[lo], final_y[lo], s.x_list[hi], final_y[hi], s.x_list[i]);
+        const int val = fy[i];
+        const int highroom = range - predicted, lowroom = predicted;
+        if (val != 0) {
+            const int room = 2 * (highroom < lowroom ? highroom : lowroom);
+            flag |= (1ull << lo) | (1ull << hi) | (1ull << i);
+            int fin;
+            if (val >= room) fin = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
+            else fin = (val & 1) ? predicted - ((val + 1) / 2) : predicted + (val / 2);
+            final_y[i] = fin;
+        } else {
+            flag &= ~(1ull << i);
+            final_y[i] = predicted;
+        }
+    }
+    // NOTE: final_y is indexed dynamically; it lives in local memory (65 ints) -- acceptable for a
+    // once-per-channel-packet integer recurrence.
+    int n = 0;
+    int hx = 0, hy = 0;
+    out.x[0] = 0;
+    out.y[0] = (int16_t)min(max(final_y[s.sort_order[0]] * mult, 0), 255);
+    n = 1;
+    for (int k = 1; k < count; ++k) {
+        const int i = s.sort_order[k];
+        if ((flag >> i) & 1ull) {
+            hy = min(max(final_y[i] * mult, 0), 255);
+            hx = s.x_list[i];
+            out.x[n] = hx;
+            out.y[n] = (int16_t)hy;
+            ++n;
+        }
+    }
+    if (hx < n_half) { // render_line(hx, hy, n, hy): a flat tail
+        out.x[n] = n_half;
+        out.y[n] = (int16_t)hy;
+        ++n;
+    }
+    out.n = n;
+}
+
+// Value of the rendered curve at line x (0 <= x < n_half): segment lookup + closed-form Bresenham.
+__device__ __forceinline__ float floor1_at(const FloorPoints& p, int x, const float* __restrict__ inv_db) {
+    int lo = 0, hi = p.n - 1; // find the last point with p.x[s] <= x
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)p.x[mid] <= x) lo = mid; else hi = mid;
+    }
+    if ((int)p.x[hi] <= x) lo = hi;
+    const int x0 = p.x[lo], y0 = p.y[lo];
+    if (lo + 1 >= p.n) return __ldg(inv_db + y0);
+    const int x1 = p.x[lo + 1], y1 = p.y[lo + 1];
+    const int dy = y1 - y0, adx = x1 - x0;
+    const int base = dy / adx;
+    const int ady = abs(dy) - abs(base) * adx;
+    const int d = x - x0;
+    const int carries = (d * ady) / adx;
+    const int y = y0 + d * base + (dy < 0 ? -carries : carries);
+    return __ldg(inv_db + y);
+}
+
+template <int LOG2>
+__device__ __forceinline__ void imdct_one(const float* spec, float* out, float2* z, const CodecTables* tab, int tid) {
+    const FftTables* ft = reinterpret_cast<const FftTables*>(tab->fft_lit16);
+    const float2* tw = reinterpret_cast<const float2*>(tab->vorbis_tw) + ((1 << LOG2) - 16);
+    imdct_blocks<LOG2>(spec, out, z, 1, tw, ft, tid, kVorbisThreads);
+}
+
+__device__ void imdct_dispatch(int log2_n2, const float* spec, float* out, float2* z, const CodecTables* tab, int tid) {
+    switch (log2_n2) { // FFT size = blocksize / 4
+        case 4: imdct_one<4>(spec, out, z, tab, tid); break;
+        case 5: imdct_one<5>(spec, out, z, tab, tid); break;
+        case 6: imdct_one<6>(spec, out, z, tab, tid); break;
+        case 7: imdct_one<7>(spec, out, z, tab, tid); break;
+        case 8: imdct_one<8>(spec, out, z, tab, tid); break;
+        case 9: imdct_one<9>(spec, out, z, tab, tid); break;
+        case 10: imdct_one<10>(spec, out, z, tab, tid); break;
+        default: imdct_one<11>(spec, out, z, tab, tid); break;
+    }
+}
+
+__global__ void __launch_bounds__(kVorbisThreads) vorbis_synth_kernel(VorbisArgs a, int slot_smem) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    // layout: spec[2][slot_smem] | out[2*slot_smem] | overlap[2][slot_smem] | z | points[2]
+    float* spec = reinterpret_cast<float*>(raw);
+    float* out = spec + 2 * slot_smem;
+    float* overlap = out + 2 * slot_smem;
+    float2* z = reinterpret_cast<float2*>(overlap + 2 * slot_smem);
+    FloorPoints* pts = reinterpret_cast<FloorPoints*>(z + zpad_len(slot_smem / 2));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const CodecChunk ck = a.chunks[blockIdx.x];
+    const symgpu_vorbis_stream cfg = a.streams[ck.stream];
+    const CodecTables* __restrict__ tab = a.tab;
+    const int bs0 = 1 << cfg.bs0_exp, bs1 = 1 << cfg.bs1_exp;
+    const int n_ch = cfg.channels;
+    const uint32_t gen = a.gen[ck.stream];
+    const float* st_in = a.states + ((size_t)ck.stream * 2 + (gen & 1)) * kVorbisStateFloats;
+    float* st_out = a.states + ((size_t)ck.stream * 2 + ((gen + 1) & 1)) * kVorbisStateFloats;
+    const bool load_state = ck.flags & kChunkLoadState;
+    const int half1 = bs1 >> 1;
+
+    if (load_state)
+        for (int i = tid; i < 2 * half1; i += kVorbisThreads) overlap[(i / half1) * slot_smem + (i % half1)] = st_in[i];
+    __syncthreads();
+
+    const int p_begin = (int)ck.first - (load_state ? 0 : 1);
+    const int p_end = (int)ck.first + ck.count;
+    for (int p = p_begin; p < p_end; ++p) {
+        const bool emit = p >= (int)ck.first;
+        const symgpu_vorbis_unit u = a.units[p];
+        const bool block_flag = u.block_flag != 0, prev_flag = u.prev_block_flag != 0;
+        const int bs = block_flag ? bs1 : bs0;
+        const int n2 = bs >> 1;
+
+        // (1) floor curves: warp = channel
+        if (warp < n_ch) {
+            const int ch = warp;
+            const bool used = u.floor[ch] != 0xffff && u.floor[ch] < a.n_floors;
+            if (used) {
+                if (lane == 0) floor1_points(a.floors[u.floor[ch]], a.floor_y + ((size_t)p * 2 + ch) * 65, n2, pts[ch]);
+                __syncwarp();
+                for (int x = lane; x < n2; x += 32) spec[ch * slot_smem + x] = floor1_at(pts[ch], x, tab->vorbis_inverse_db);
+            } else {
+                for (int x = lane; x < n2; x += 32) spec[ch * slot_smem + x] = 0.0f; // ch.floor[..n2].fill(0.0)
+            }
+        }
+        __syncthreads();
+
+        // (2) inverse coupling + dot product
+        const float* r0 = a.residue + ((size_t)p * 2 + 0) * a.slot;
+        const float* r1 = a.residue + ((size_t)p * 2 + 1) * a.slot;
+        for (int i = tid; i < n2; i += kVorbisThreads) {
+            float m = __ldg(r0 + i);
+            float ang = n_ch == 2 ? __ldg(r1 + i) : 0.0f;
+            if (cfg.coupled && n_ch == 2) { // lib.rs:267-277: comparisons are "> 0.0"
+                float nm, na;
+                if (m > 0.0f) {
+                    if (ang > 0.0f) { nm = m; na = m - ang; } else { nm = m + ang; na = m; }
+                } else {
+                    if (ang > 0.0f) { nm = m; na = m + ang; } else { nm = m - ang; na = m; }
+                }
+                m = nm;
+                ang = na;
+            }
+            if (!u.do_not_decode[0]) spec[i] = spec[i] * m;
+            if (n_ch == 2 && !u.do_not_decode[1]) spec[slot_smem + i] = spec[slot_smem + i] * ang;
+        }
+        __syncthreads();
+
+        // (3) per channel: IMDCT, window + overlap-add, save the tail (dsp.rs:68-126)
+        const int out_len = ((prev_flag ? bs1 : bs0) + bs) >> 2;
+        for (int ch = 0; ch < n_ch; ++ch) {
+            imdct_dispatch(31 - __clz(bs >> 2), spec + ch * slot_smem, out, z, tab, tid);
+            float* ov = overlap + ch * slot_smem;
+            float* dst = a.pcm + ((size_t)p * 2 + ch) * a.slot;
+            const float* win = tab->vorbis_win + (((block_flag && prev_flag) ? bs1 : bs0) / 2 - 32);
+            if (emit) {
+                if (prev_flag == block_flag) {
+                    const int len = bs / 2;
+                    for (int k = tid; k < len; k += kVorbisThreads)
+                        dst[k] = ov[k] * __ldg(win + len - 1 - k) + out[k] * __ldg(win + k);
+                } else if (prev_flag && !block_flag) {
+                    const int start = (bs1 - bs0) / 4, len = bs0 / 2;
+                    for (int k = tid; k < out_len; k += kVorbisThreads) {
+                        if (k < start) dst[k] = ov[k];
+                        else {
+                            const int j = k - start;
+                            dst[k] = ov[k] * __ldg(win + len - 1 - j) + out[j] * __ldg(win + j);
+                        }
+                    }
+                } else {
+                    const int start = (bs1 - bs0) / 4, len = bs0 / 2, end = start + len;
+                    for (int k = tid; k < out_len; k += kVorbisThreads) {
+                        if (k < len) dst[k] = ov[k] * __ldg(win + len - 1 - k) + out[start + k] * __ldg(win + k);
+                        else dst[k] = out[end + (k - len)];
+                    }
+                }
+            }
+            __syncthreads(); // every thread has read the old overlap
+            for (int k = tid; k < bs / 2; k += kVorbisThreads) ov[k] = out[bs / 2 + k];
+            __syncthreads();
+        }
+    }
+
+    if (ck.flags & kChunkStoreState)
+        for (int i = tid; i < 2 * half1; i += kVorbisThreads) st_out[i] = overlap[(i / half1) * slot_smem + (i % half1)];
+
+    __shared__ bool is_last;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        for (unsigned i = tid; i < gridDim.x; i += kVorbisThreads)
+            if (a.chunks[i].flags & kChunkStoreState) a.gen[a.chunks[i].stream] += 1;
+        if (tid == 0) *a.done = 0;
+    }
+}
+
+} // namespace
+
+cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream) {
+    const int slot_smem = 1 << (max_bs1_exp - 1);
+    const size_t smem = sizeof(float) * 6 * (size_t)slot_smem + sizeof(float2) * zpad_len(slot_smem / 2) + 2 * sizeof(FloorPoints) + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(vorbis_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    vorbis_synth_kernel<<<n_chunks, kVorbisThreads, smem, stream>>>(a, slot_smem);
+    return cudaGetLastError();
+}
+
+} // namespace symgpu

@@ -8,7 +8,8 @@ import ctypes
 import numpy as np
 
 from . import _native
-from ._native import MP3_GC_DTYPE, MP3_RUN_DTYPE
+from ._native import (AAC_RUN_DTYPE, AAC_TNS_DTYPE, AAC_UNIT_DTYPE, MP3_GC_DTYPE, MP3_RUN_DTYPE, VORBIS_FLOOR1_DTYPE,
+                      VORBIS_RUN_DTYPE, VORBIS_STREAM_DTYPE, VORBIS_UNIT_DTYPE)
 
 
 class SymgpuError(RuntimeError):
@@ -109,3 +110,66 @@ class Engine:
         self._check(self._lib.symgpu_mp3_synth_dev(self._ctx, ctypes.c_void_p(units_t.data_ptr()),
                                                    ctypes.c_void_p(spectra_t.data_ptr()), _np_ptr(runs), len(runs),
                                                    n_frames, ctypes.c_void_p(pcm_t.data_ptr())))
+
+    # -- AAC --------------------------------------------------------------------------------
+    def aac_streams_alloc(self, n_streams):
+        self._check(self._lib.symgpu_aac_streams_alloc(self._ctx, int(n_streams)))
+
+    def aac_stream_reset(self, stream):
+        self._check(self._lib.symgpu_aac_stream_reset(self._ctx, int(stream)))
+
+    def aac_synth_host(self, units, tns, coeffs, runs, out=None):
+        """units [F,2] AAC_UNIT_DTYPE, tns [T] AAC_TNS_DTYPE, coeffs [F,2,1024] f32 -> pcm [F,2,1024]."""
+        units = np.ascontiguousarray(units, dtype=AAC_UNIT_DTYPE)
+        tns = np.ascontiguousarray(tns, dtype=AAC_TNS_DTYPE)
+        runs = np.ascontiguousarray(runs, dtype=AAC_RUN_DTYPE)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float32)
+        n_frames = units.size // 2
+        if coeffs.size != n_frames * 2048:
+            raise ValueError("coeffs must be [n_frames, 2, 1024]")
+        if out is None:
+            out = np.empty((n_frames, 2, 1024), dtype=np.float32)
+        self._check(self._lib.symgpu_aac_synth_host(self._ctx, _np_ptr(units), _np_ptr(tns) if len(tns) else None, len(tns),
+                                                    _np_ptr(coeffs), _np_ptr(runs), len(runs), n_frames, _np_ptr(out)))
+        return out
+
+    def aac_synth_dev(self, units_t, tns_t, n_tns, coeffs_t, runs, pcm_t):
+        runs = np.ascontiguousarray(runs, dtype=AAC_RUN_DTYPE)
+        n_frames = coeffs_t.numel() // 2048
+        self._check(self._lib.symgpu_aac_synth_dev(
+            self._ctx, ctypes.c_void_p(units_t.data_ptr()), ctypes.c_void_p(tns_t.data_ptr()) if n_tns else None, int(n_tns),
+            ctypes.c_void_p(coeffs_t.data_ptr()), _np_ptr(runs), len(runs), n_frames, ctypes.c_void_p(pcm_t.data_ptr())))
+
+    # -- Vorbis -----------------------------------------------------------------------------
+    def vorbis_streams_set(self, streams):
+        streams = np.ascontiguousarray(streams, dtype=VORBIS_STREAM_DTYPE)
+        self._check(self._lib.symgpu_vorbis_streams_set(self._ctx, _np_ptr(streams), len(streams)))
+
+    def vorbis_floors_set(self, floors):
+        floors = np.ascontiguousarray(floors, dtype=VORBIS_FLOOR1_DTYPE)
+        self._check(self._lib.symgpu_vorbis_floors_set(self._ctx, _np_ptr(floors), len(floors)))
+
+    def vorbis_stream_reset(self, stream):
+        self._check(self._lib.symgpu_vorbis_stream_reset(self._ctx, int(stream)))
+
+    def vorbis_synth_host(self, units, floor_y, residue, runs, slot, out=None):
+        """units [P] VORBIS_UNIT_DTYPE, floor_y [P,2,65] u16, residue [P,2,slot] f32 -> pcm [P,2,slot]."""
+        units = np.ascontiguousarray(units, dtype=VORBIS_UNIT_DTYPE)
+        floor_y = np.ascontiguousarray(floor_y, dtype=np.uint16)
+        residue = np.ascontiguousarray(residue, dtype=np.float32)
+        runs = np.ascontiguousarray(runs, dtype=VORBIS_RUN_DTYPE)
+        n = len(units)
+        if residue.size != n * 2 * slot or floor_y.size != n * 130:
+            raise ValueError("residue must be [n, 2, slot] and floor_y [n, 2, 65]")
+        if out is None:
+            out = np.empty((n, 2, slot), dtype=np.float32)
+        self._check(self._lib.symgpu_vorbis_synth_host(self._ctx, _np_ptr(units), _np_ptr(floor_y), _np_ptr(residue),
+                                                       _np_ptr(runs), len(runs), n, int(slot), _np_ptr(out)))
+        return out
+
+    def vorbis_synth_dev(self, units_t, floor_y_t, residue_t, runs, slot, pcm_t):
+        runs = np.ascontiguousarray(runs, dtype=VORBIS_RUN_DTYPE)
+        n = units_t.numel() * units_t.element_size() // 16
+        self._check(self._lib.symgpu_vorbis_synth_dev(
+            self._ctx, ctypes.c_void_p(units_t.data_ptr()), ctypes.c_void_p(floor_y_t.data_ptr()),
+            ctypes.c_void_p(residue_t.data_ptr()), _np_ptr(runs), len(runs), n, int(slot), ctypes.c_void_p(pcm_t.data_ptr())))

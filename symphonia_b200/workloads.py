@@ -110,3 +110,195 @@ def mp3_audio_seconds(n_frames, sample_rate_idx=0):
 
 
 MP3_ALGO_BYTES_PER_FRAME = 9216 + 256 + 9216  # spectra + descriptors + PCM
+
+
+# =================================================================================================
+# AAC-LC
+# =================================================================================================
+from ._native import (AAC_EIGHT_SHORT, AAC_LONG_START, AAC_LONG_STOP, AAC_ONLY_LONG, AAC_RUN_DTYPE, AAC_TNS_DTYPE,  # noqa: E402
+                      AAC_UNIT_DTYPE, VORBIS_FLOOR1_DTYPE, VORBIS_RUN_DTYPE, VORBIS_STREAM_DTYPE, VORBIS_UNIT_DTYPE)
+
+
+def _tns_lpc(rng, order, coef_res=True):
+    """TNS LPC coefficients by the quantised-sine construction of aac/ics/tns.rs:66-101."""
+    bits = 4 if coef_res else 3
+    fac_base = 8.0 if coef_res else 4.0
+    iqfac = np.float32((fac_base - 0.5) / (np.pi / 2))
+    iqfac_m = np.float32((fac_base + 0.5) / (np.pi / 2))
+    c = rng.integers(-(1 << (bits - 1)), 1 << (bits - 1), size=order).astype(np.float32)
+    tmp = np.sin(np.where(c >= 0, c / iqfac, c / iqfac_m).astype(np.float32)).astype(np.float32)
+    coef = np.zeros(21, dtype=np.float32)
+    b = np.zeros(21, dtype=np.float32)
+    for m in range(1, order + 1):
+        for i in range(1, m):
+            b[i] = coef[i - 1] + tmp[m - 1] * coef[m - i - 1]
+        coef[: m - 1] = b[1:m]
+        coef[m - 1] = tmp[m - 1]
+    return coef[:20]
+
+
+def aac_batch(n_streams=64, frames_per_stream=128, seed=SEED_BASE + 2, channels=2, tns_prob=0.2, block_switching=True):
+    """AAC-LC batch: (units [S*F,2], tns [T], coeffs [S*F,2,1024], runs [S])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    S, F = int(n_streams), int(frames_per_stream)
+    n = S * F
+    units = np.zeros((S, F, 2), dtype=AAC_UNIT_DTYPE)
+    k = np.arange(1024)
+    env = (2.0 ** (-k / 128.0) * 2000.0) * (k < 672)
+    coeffs = (rng.standard_normal((S, F, 2, 1024)) * env).astype(np.float32)
+    coeffs[..., 672:] = 0.0
+    tns = []
+    for s in range(S):
+        for ch in range(2):
+            seq, prev_shape = AAC_ONLY_LONG, 0
+            for f in range(F):
+                if block_switching:
+                    u = rng.random()
+                    if seq == AAC_ONLY_LONG:
+                        nxt = AAC_LONG_START if u < 0.1 else AAC_ONLY_LONG
+                    elif seq == AAC_LONG_START:
+                        nxt = AAC_EIGHT_SHORT
+                    elif seq == AAC_EIGHT_SHORT:
+                        nxt = AAC_EIGHT_SHORT if u < 0.5 else AAC_LONG_STOP
+                    else:
+                        nxt = AAC_ONLY_LONG
+                    if f:
+                        seq = nxt
+                shape = int(rng.random() < 0.5)
+                uu = units[s, f, ch]
+                uu["window_sequence"], uu["window_shape"], uu["prev_window_shape"] = seq, shape, prev_shape
+                prev_shape = shape
+                if ch < channels and rng.random() < tns_prob:
+                    first = len(tns)
+                    if seq == AAC_EIGHT_SHORT:
+                        for w in range(8):
+                            if rng.random() < 0.5:
+                                lo = int(rng.integers(0, 60))
+                                hi = int(rng.integers(lo + 4, 112))
+                                order = int(rng.integers(1, 8))
+                                tns.append((w * 128 + lo, w * 128 + hi, order, int(rng.random() < 0.5), _tns_lpc(rng, order, False)))
+                    else:
+                        top = int(rng.integers(300, 672))
+                        for _ in range(int(rng.integers(1, 4))):
+                            bottom = max(0, top - int(rng.integers(40, 300)))
+                            order = int(rng.integers(1, 13))
+                            if top > bottom:
+                                tns.append((bottom, top, order, int(rng.random() < 0.5), _tns_lpc(rng, order)))
+                            top = bottom
+                    uu["n_tns"], uu["tns_first"] = len(tns) - first, first
+    if channels == 1:
+        coeffs[:, :, 1] = 0.0
+    tns_arr = np.zeros(len(tns), dtype=AAC_TNS_DTYPE)
+    for i, (a, b, o, d, lpc) in enumerate(tns):
+        tns_arr[i]["start"], tns_arr[i]["end"], tns_arr[i]["order"], tns_arr[i]["direction"] = a, b, o, d
+        tns_arr[i]["lpc"] = lpc
+    runs = np.zeros(S, dtype=AAC_RUN_DTYPE)
+    runs["stream"] = np.arange(S)
+    runs["first_frame"] = np.arange(S) * F
+    runs["n_frames"] = F
+    runs["channels"] = channels
+    return units.reshape(n, 2), tns_arr, coeffs.reshape(n, 2, 1024), runs
+
+
+AAC_ALGO_BYTES_PER_FRAME = 8192 + 32 + 8192  # SURVEY.md §8d (two 16-byte units)
+
+
+# =================================================================================================
+# Vorbis
+# =================================================================================================
+def find_neighbors(x_list, i):
+    """low_neighbor / high_neighbor of the Vorbis I spec 9.2.4-9.2.5 (floor.rs:748-773)."""
+    bound = x_list[i]
+    low, high = 0, 0xFFFFFFFF
+    res = [0, 0]
+    for k in range(i):
+        xv = x_list[k]
+        if low < xv < bound:
+            low, res[0] = xv, k
+        if bound < xv < high:
+            high, res[1] = xv, k
+    return res
+
+
+def make_floor1_setup(x_list, multiplier):
+    """What Floor1::read_setup precomputes (floor.rs:546-560) for a given X list."""
+    s = np.zeros((), dtype=VORBIS_FLOOR1_DTYPE)
+    n = len(x_list)
+    s["multiplier"] = multiplier
+    s["n_posts"] = n
+    s["x_list"][:n] = x_list
+    for i in range(n):
+        lo, hi = find_neighbors(list(x_list), i)
+        s["low"][i], s["high"][i] = lo, hi
+    s["sort_order"][:n] = sorted(range(n), key=lambda k: x_list[k])
+    return s
+
+
+def vorbis_batch(n_streams=64, packets_per_stream=128, seed=SEED_BASE + 3, bs_exp=(8, 11), channels=2, coupled=True,
+                 unused_prob=0.05):
+    """Vorbis batch with a long/short block mix.
+
+    Returns dict(streams, floors, units [P], floor_y [P,2,65], residue [P,2,slot], runs, slot, out_len [P])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    S, F = int(n_streams), int(packets_per_stream)
+    bs0, bs1 = 1 << bs_exp[0], 1 << bs_exp[1]
+    slot = bs1 // 2
+    streams = np.zeros(S, dtype=VORBIS_STREAM_DTYPE)
+    streams["bs0_exp"], streams["bs1_exp"], streams["channels"] = bs_exp[0], bs_exp[1], channels
+    streams["coupled"] = 1 if (coupled and channels == 2) else 0
+    # four floor configurations per block size: 20-40 posts, multiplier 1..4 (2 most common)
+    floors, by_size = [], {0: [], 1: []}
+    for flag, n2 in ((0, bs0 // 2), (1, bs1 // 2)):
+        for _ in range(4):
+            n_posts = int(min(rng.integers(20, 41), n2 // 2))
+            inner = rng.choice(np.arange(1, n2), size=n_posts - 2, replace=False).tolist()
+            rng.shuffle(inner)
+            mult = int(rng.choice([1, 2, 2, 2, 3, 4]))
+            by_size[flag].append(len(floors))
+            floors.append(make_floor1_setup([0, n2] + inner, mult))
+    floors = np.array(floors, dtype=VORBIS_FLOOR1_DTYPE)
+    P = S * F
+    units = np.zeros((S, F), dtype=VORBIS_UNIT_DTYPE)
+    floor_y = np.zeros((S, F, 2, 65), dtype=np.uint16)
+    residue = np.zeros((S, F, 2, slot), dtype=np.float32)
+    out_len = np.zeros((S, F), dtype=np.int32)
+    flag = (rng.random(S) < 0.8).astype(np.uint8)
+    for f in range(F):
+        if f:
+            u = rng.random(S)
+            flag = np.where(flag == 1, (u < 0.92).astype(np.uint8), (u >= 0.75).astype(np.uint8))
+        prev = units["block_flag"][:, f - 1] if f else flag
+        units["block_flag"][:, f] = flag
+        units["prev_block_flag"][:, f] = prev
+        out_len[:, f] = (np.where(prev == 1, bs1, bs0) + np.where(flag == 1, bs1, bs0)) // 4
+        for s in range(S):
+            n2 = (bs1 if flag[s] else bs0) // 2
+            unused = [False, False]
+            for ch in range(channels):
+                fi = by_size[int(flag[s])][int(rng.integers(0, 4))]
+                setup = floors[fi]
+                npost = int(setup["n_posts"])
+                rng_ = {1: 256, 2: 128, 3: 86, 4: 64}[int(setup["multiplier"])]
+                y = rng.integers(0, 24, size=npost)
+                y[rng.random(npost) < 0.3] = 0
+                y[0], y[1] = rng.integers(0, rng_, size=2)
+                floor_y[s, f, ch, :npost] = y
+                unused[ch] = rng.random() < unused_prob
+                units[s, f]["floor"][ch] = 0xFFFF if unused[ch] else fi
+                r = rng.standard_normal(n2).astype(np.float32) * 4.0
+                r[int(0.8 * n2):] = 0.0
+                residue[s, f, ch, :n2] = r
+            if channels == 1:
+                units[s, f]["floor"][1] = 0xFFFF
+                units[s, f]["do_not_decode"] = [int(unused[0]), 1]
+            else:
+                dnd = list(unused)
+                if streams["coupled"][s] and dnd[0] != dnd[1]:  # non-zero vector propagate, lib.rs:215-225
+                    dnd = [False, False]
+                units[s, f]["do_not_decode"] = [int(dnd[0]), int(dnd[1])]
+    runs = np.zeros(S, dtype=VORBIS_RUN_DTYPE)
+    runs["stream"] = np.arange(S)
+    runs["first_packet"] = np.arange(S) * F
+    runs["n_packets"] = F
+    return dict(streams=streams, floors=floors, units=units.reshape(P), floor_y=floor_y.reshape(P, 2, 65),
+                residue=residue.reshape(P, 2, slot), runs=runs, slot=slot, out_len=out_len.reshape(P))

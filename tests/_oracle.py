@@ -85,3 +85,26 @@ def mp3_batch(lib, units, spectra, runs, n_streams):
     rc = lib.oracle_mp3_batch(ctypes.byref(states), ptr(units), ptr(spectra), ptr(runs),
                               ctypes.c_uint32(len(runs)), ptr(pcm))
     return rc, pcm, states
+
+
+def aac_batch(lib, units, tns, coeffs, runs, n_streams, n_threads=1):
+    n_frames = coeffs.shape[0]
+    states = (AacState * (2 * n_streams))()
+    pcm = np.zeros((n_frames, 2, 1024), dtype=np.float32)
+    units, tns, runs = np.ascontiguousarray(units), np.ascontiguousarray(tns), np.ascontiguousarray(runs)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float32)
+    rc = lib.oracle_aac_batch(ctypes.byref(states), ptr(units), ptr(tns) if len(tns) else None, ptr(coeffs), ptr(runs),
+                              ctypes.c_uint32(len(runs)), ptr(pcm), n_threads)
+    return rc, pcm
+
+
+def vorbis_batch(lib, wl, n_threads=1):
+    """wl: the dict returned by symphonia_b200.workloads.vorbis_batch."""
+    n_streams = len(wl["streams"])
+    states = (VorbisState * n_streams)()
+    pcm = np.zeros((len(wl["units"]), 2, wl["slot"]), dtype=np.float32)
+    arrs = {k: np.ascontiguousarray(wl[k]) for k in ("streams", "floors", "units", "floor_y", "residue", "runs")}
+    rc = lib.oracle_vorbis_batch(ctypes.byref(states), ptr(arrs["streams"]), ptr(arrs["floors"]), ptr(arrs["units"]),
+                                 ptr(arrs["floor_y"]), ptr(arrs["residue"]), ptr(arrs["runs"]),
+                                 ctypes.c_uint32(len(arrs["runs"])), ctypes.c_uint32(wl["slot"]), ptr(pcm), n_threads)
+    return rc, pcm

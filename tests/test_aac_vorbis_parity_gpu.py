@@ -1,0 +1,171 @@
+"""GPU parity for the AAC-LC and Vorbis kernels (through the C ABI) vs the oracle: bit-exact PCM."""
+import numpy as np
+import pytest
+
+from tests import _oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import symphonia_b200 as sb
+    eng = sb.Engine(0)
+    yield eng
+    eng.close()
+
+
+def _cmp(got, want, what):
+    g = np.ascontiguousarray(got, dtype=np.float32).view(np.uint32)
+    w = np.ascontiguousarray(want, dtype=np.float32).view(np.uint32)
+    bad = g != w
+    if bad.any():
+        idx = tuple(int(x[0]) for x in np.nonzero(bad))
+        raise AssertionError(f"{what}: {int(bad.sum())} of {g.size} PCM words differ; first at {idx}: gpu {got[idx]!r} "
+                             f"oracle {want[idx]!r}")
+    assert np.abs(want).max() > 1e-6
+
+
+# ---- AAC -------------------------------------------------------------------------------------------
+
+def _aac_case(engine, oracle, S, F, **kw):
+    from symphonia_b200 import workloads
+    units, tns, coeffs, runs = workloads.aac_batch(S, F, **kw)
+    rc, want = _oracle.aac_batch(oracle, units, tns, coeffs, runs, S)
+    engine.aac_streams_alloc(S)
+    got = engine.aac_synth_host(units, tns, coeffs, runs)
+    ch = kw.get("channels", 2)
+    _cmp(got[:, :ch], want[:, :ch], f"aac S={S} F={F} {kw}")
+    return units, tns, coeffs, runs, want
+
+
+def test_aac_mixed(engine, oracle):
+    _aac_case(engine, oracle, 6, 40, seed=101)
+
+
+def test_aac_long_only_no_tns(engine, oracle):
+    _aac_case(engine, oracle, 3, 12, seed=102, tns_prob=0.0, block_switching=False)
+
+
+def test_aac_heavy_tns(engine, oracle):
+    _aac_case(engine, oracle, 3, 20, seed=103, tns_prob=0.9)
+
+
+def test_aac_chunk_boundaries_and_single_frames(engine, oracle):
+    for F in (1, 7, 8, 9, 17):
+        _aac_case(engine, oracle, 5, F, seed=110 + F)
+
+
+def test_aac_mono(engine, oracle):
+    _aac_case(engine, oracle, 3, 10, seed=104, channels=1)
+
+
+def test_aac_state_carry_and_reset(engine, oracle):
+    from symphonia_b200 import workloads
+    S, F = 4, 21
+    units, tns, coeffs, runs = workloads.aac_batch(S, F, seed=105)
+    rc, want = _oracle.aac_batch(oracle, units, tns, coeffs, runs, S)
+    engine.aac_streams_alloc(S)
+    u3, c3 = units.reshape(S, F, 2), coeffs.reshape(S, F, 2, 1024)
+    got = np.zeros((S, F, 2, 1024), dtype=np.float32)
+    lo = 0
+    for part in (5, 1, 15):
+        hi = lo + part
+        r = runs.copy()
+        r["first_frame"] = np.arange(S) * part
+        r["n_frames"] = part
+        out = engine.aac_synth_host(np.ascontiguousarray(u3[:, lo:hi]).reshape(-1, 2), tns,
+                                    np.ascontiguousarray(c3[:, lo:hi]).reshape(-1, 2, 1024), r)
+        got[:, lo:hi] = out.reshape(S, part, 2, 1024)
+        lo = hi
+    _cmp(got.reshape(S * F, 2, 1024), want, "aac state carry")
+    for s in range(S):
+        engine.aac_stream_reset(s)
+    again = engine.aac_synth_host(units, tns, coeffs, runs)
+    _cmp(again, want, "aac after reset")
+
+
+def test_aac_device_entry_point(engine, oracle):
+    import torch
+    from symphonia_b200 import workloads
+    S, F = 3, 10
+    units, tns, coeffs, runs = workloads.aac_batch(S, F, seed=106)
+    rc, want = _oracle.aac_batch(oracle, units, tns, coeffs, runs, S)
+    engine.aac_streams_alloc(S)
+    dev = torch.device("cuda", 0)
+    u_t = torch.from_numpy(units.view(np.uint8).reshape(-1).copy()).to(dev)
+    t_t = torch.from_numpy(tns.view(np.uint8).reshape(-1).copy()).to(dev)
+    c_t = torch.from_numpy(coeffs).to(dev)
+    p_t = torch.zeros((S * F, 2, 1024), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    engine.aac_synth_dev(u_t, t_t, len(tns), c_t, runs, p_t)
+    engine.sync()
+    _cmp(p_t.cpu().numpy(), want, "aac device entry point")
+
+
+# ---- Vorbis ----------------------------------------------------------------------------------------
+
+def _vorbis_case(engine, oracle, S, F, **kw):
+    from symphonia_b200 import workloads
+    wl = workloads.vorbis_batch(S, F, **kw)
+    rc, want = _oracle.vorbis_batch(oracle, wl)
+    engine.vorbis_streams_set(wl["streams"])
+    engine.vorbis_floors_set(wl["floors"])
+    got = engine.vorbis_synth_host(wl["units"], wl["floor_y"], wl["residue"], wl["runs"], wl["slot"])
+    ch = kw.get("channels", 2)
+    mask = np.arange(wl["slot"])[None, None, :] < wl["out_len"][:, None, None]
+    mask = np.broadcast_to(mask, got.shape).copy()
+    mask[:, ch:, :] = False
+    _cmp(np.where(mask, got, 0), np.where(mask, want, 0), f"vorbis S={S} F={F} {kw}")
+    return wl, want
+
+
+def test_vorbis_mixed(engine, oracle):
+    _vorbis_case(engine, oracle, 6, 40, seed=201)
+
+
+@pytest.mark.parametrize("bs", [(6, 6), (6, 9), (7, 10), (8, 11), (9, 12), (8, 13), (11, 11)])
+def test_vorbis_block_sizes(engine, oracle, bs):
+    _vorbis_case(engine, oracle, 2, 12, seed=210 + bs[0] + 16 * bs[1], bs_exp=bs)
+
+
+def test_vorbis_uncoupled_and_mono(engine, oracle):
+    _vorbis_case(engine, oracle, 3, 14, seed=202, coupled=False)
+    _vorbis_case(engine, oracle, 3, 14, seed=203, channels=1)
+
+
+def test_vorbis_many_unused_floors(engine, oracle):
+    _vorbis_case(engine, oracle, 3, 20, seed=204, unused_prob=0.5)
+
+
+def test_vorbis_chunk_boundaries(engine, oracle):
+    for F in (1, 7, 8, 9, 17):
+        _vorbis_case(engine, oracle, 4, F, seed=220 + F)
+
+
+def test_vorbis_state_carry(engine, oracle):
+    from symphonia_b200 import workloads
+    S, F = 4, 19
+    wl = workloads.vorbis_batch(S, F, seed=205)
+    rc, want = _oracle.vorbis_batch(oracle, wl)
+    engine.vorbis_streams_set(wl["streams"])
+    engine.vorbis_floors_set(wl["floors"])
+    slot = wl["slot"]
+    u2 = wl["units"].reshape(S, F)
+    fy = wl["floor_y"].reshape(S, F, 2, 65)
+    rs = wl["residue"].reshape(S, F, 2, slot)
+    got = np.zeros((S, F, 2, slot), dtype=np.float32)
+    lo = 0
+    for part in (6, 1, 12):
+        hi = lo + part
+        r = wl["runs"].copy()
+        r["first_packet"] = np.arange(S) * part
+        r["n_packets"] = part
+        out = engine.vorbis_synth_host(np.ascontiguousarray(u2[:, lo:hi]).reshape(-1),
+                                       np.ascontiguousarray(fy[:, lo:hi]).reshape(-1, 2, 65),
+                                       np.ascontiguousarray(rs[:, lo:hi]).reshape(-1, 2, slot), r, slot)
+        got[:, lo:hi] = out.reshape(S, part, 2, slot)
+        lo = hi
+    mask = np.arange(slot)[None, None, :] < wl["out_len"][:, None, None]
+    got = got.reshape(S * F, 2, slot)
+    _cmp(np.where(mask, got, 0), np.where(mask, want, 0), "vorbis state carry")
