@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Secondary measurements: BASELINE configs[2] (AAC-LC 48 kHz stereo, 8192 frames) and configs[3]
+(Vorbis 44.1 kHz stereo long/short mix, 8192 packets) on one B200, device-resident inputs.
+Prints one JSON line per codec with the same roofline arithmetic as bench.py (the headline metric
+and the driver contract live in bench.py; this script feeds profiles/ and DESIGN.md)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _time_steps(eng, fn, steps, warmup):
+    import torch
+    ext = torch.cuda.ExternalStream(eng.cuda_stream)
+    for i in range(warmup):
+        fn(i)
+    eng.sync()
+    with torch.cuda.stream(ext):
+        evs = []
+        for i in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(warmup + i)
+            b.record()
+            evs.append((a, b))
+    eng.sync()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--codec", default="both", choices=["aac", "vorbis", "both"])
+    ap.add_argument("--tns", type=float, default=0.2)
+    args = ap.parse_args()
+    import torch
+    import symphonia_b200 as sb
+    from symphonia_b200 import workloads
+    dev = torch.device("cuda", 0)
+    eng = sb.Engine(0)
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    S, F, SETS = 64, 128, 4
+    if args.codec in ("aac", "both"):
+        units, tns, coeffs, runs = workloads.aac_batch(S, F, tns_prob=args.tns)
+        eng.aac_streams_alloc(S)
+        sets = []
+        for _ in range(SETS):
+            sets.append((torch.from_numpy(units.view(np.uint8).reshape(-1).copy()).to(dev),
+                         torch.from_numpy(tns.view(np.uint8).reshape(-1).copy()).to(dev) if len(tns) else torch.zeros(8, device=dev),
+                         torch.from_numpy(coeffs).to(dev), torch.empty((S * F, 2, 1024), dtype=torch.float32, device=dev)))
+        ms = _time_steps(eng, lambda i: eng.aac_synth_dev(sets[i % SETS][0], sets[i % SETS][1], len(tns), sets[i % SETS][2],
+                                                          runs, sets[i % SETS][3]), args.steps, args.warmup)
+        algo = S * F * workloads.AAC_ALGO_BYTES_PER_FRAME
+        audio = S * F * 1024 / 48000.0
+        ach = algo / (ms * 1e-3) / 1e9
+        print(json.dumps({"codec": "aac-lc", "workload": "AAC-LC 48kHz stereo, 8192 frames, TNS in %.0f%% of channel-frames" % (100 * args.tns),
+                          "value": audio / (ms * 1e-3), "unit": "audio-s/s", "kernel_ms": ms, "n_tns_filters": int(len(tns)),
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                       "algorithmic_bytes_per_launch": algo}}), flush=True)
+    if args.codec in ("vorbis", "both"):
+        wl = workloads.vorbis_batch(S, F)
+        eng.vorbis_streams_set(wl["streams"])
+        eng.vorbis_floors_set(wl["floors"])
+        slot = wl["slot"]
+        sets = []
+        for _ in range(SETS):
+            sets.append((torch.from_numpy(wl["units"].view(np.uint8).reshape(-1).copy()).to(dev),
+                         torch.from_numpy(wl["floor_y"].view(np.int16).copy()).to(dev), torch.from_numpy(wl["residue"]).to(dev),
+                         torch.zeros((S * F, 2, slot), dtype=torch.float32, device=dev)))
+        ms = _time_steps(eng, lambda i: eng.vorbis_synth_dev(sets[i % SETS][0], sets[i % SETS][1], sets[i % SETS][2],
+                                                             wl["runs"], slot, sets[i % SETS][3]), args.steps, args.warmup)
+        n2 = np.where(wl["units"]["block_flag"] == 1, 1024, 128)
+        algo = int((n2 * 4 * 2 + 2 * 65 * 2 + 16 + wl["out_len"] * 4 * 2).sum())
+        audio = float(wl["out_len"].sum()) / 44100.0
+        ach = algo / (ms * 1e-3) / 1e9
+        print(json.dumps({"codec": "vorbis", "workload": "Vorbis 44.1kHz stereo coupled, blocksizes 256/2048, 8192 packets "
+                          "(%.0f%% long)" % (100 * float((n2 == 1024).mean())),
+                          "value": audio / (ms * 1e-3), "unit": "audio-s/s", "kernel_ms": ms,
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                       "algorithmic_bytes_per_launch": algo}}), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
