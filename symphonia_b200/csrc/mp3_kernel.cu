@@ -4,11 +4,14 @@
 // in ONE launch, PCM written straight to HBM.  No intermediate ever leaves the SM.
 //
 // Parallelisation: every piece of cross-granule state on this path is overwritten,
-// never accumulated (hybrid overlap, polyphase FIFO), so a stream is cut into TILES of T
-// consecutive granules; one CTA owns one tile.  A tile that starts a run loads the stream state
-// from HBM; any other tile recomputes a 2-granule halo (the overlap of granule g-1 needs IMDCT of
-// g-1; the 15 polyphase history slots need the time samples of g-1, which need the overlap of
-// g-2).
+// never accumulated (hybrid overlap, polyphase FIFO), so a stream is cut into TILES of <= T consecutive
+// granules.  A tile that starts a run takes overlap + polyphase history from the stream state in
+// HBM; any other tile recomputes a 2-granule halo (the overlap of granule g-1 needs IMDCT of g-1;
+// the 15 history slots need the time samples of g-1, which need the overlap of g-2).  The grid is
+// PERSISTENT: one CTA of NW warps per SM walks tiles blockIdx, blockIdx+grid, ... with all its
+// warps in the same phase (several phases live on one SM thrash the instruction cache: measured
+// +30% time with 2 CTAs/SM).  The spectra of the next tile are fetched by TMA bulk copies
+// (cp.async.bulk -> mbarrier) while the current tile is in its DCT / window phases.
 //
 // Bit-exactness rules: compiled with -fmad=false; every expression keeps the reference's operand
 // order; tables come from the host (tables.cpp).  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2
@@ -35,6 +38,7 @@ struct Mp3Const {
     float lee16[16], lee8[8], lee4[4], lee2[2], lee1;
     float is_mpeg1[7][2];
     float is_mpeg2[2][32][2];
+    float cs[8], ca[8];
     uint8_t pre_emphasis[24];
     uint8_t mixed_switch[12];
     uint8_t n_edges[9][3];
@@ -55,6 +59,8 @@ cudaError_t mp3_upload_const(const Mp3Tables& t, cudaStream_t stream) {
     h.lee1 = t.lee1;
     memcpy(h.is_mpeg1, t.is_mpeg1, sizeof h.is_mpeg1);
     memcpy(h.is_mpeg2, t.is_mpeg2, sizeof h.is_mpeg2);
+    memcpy(h.cs, t.cs, sizeof h.cs);
+    memcpy(h.ca, t.ca, sizeof h.ca);
     memcpy(h.pre_emphasis, t.pre_emphasis, sizeof h.pre_emphasis);
     memset(h.mixed_switch, 0, sizeof h.mixed_switch);
     memcpy(h.mixed_switch, t.mixed_switch, 9);
@@ -211,56 +217,190 @@ __device__ __forceinline__ float finv(float v, int sb, int t) { return ((sb & t)
 } // namespace
 
 // =============================================================================================
+namespace {
+
+// ---- mbarrier / TMA bulk-copy wrappers (PTX ISA 8.6, sm_90+) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+// Polyphase window of `total` consecutive time slots whose DCT vectors sit in XT rows row0 ..
+// (with the 15 rows before row0 holding the history).  lane = PCM sample index i; each warp walks a
+// contiguous range of slots with a 16-deep register window of (V_lo[i], V_hi[i]) for both channels:
+//   V_lo[i] =  d[16+i] (i<16) | 0 (i=16, the constant column 32) | -d[48-i] (i>16)
+//   V_hi[i] = -d[16-i] (i<=16) | -d[i-16] (i>16)                         (synthesis.rs:247-263)
+//   o[i] = sum_j  V_lo(t-2j)[i] * D[64j+i]  then  + V_hi(t-2j-1)[i] * D[64j+32+i]   (:309-323)
+// The signs are folded into the per-lane coefficients ((-d)*D == d*(-D) exactly).  `slot_seq0` is the
+// batch-wide sequence number of the first slot: slots of a frame are contiguous in a PCM plane
+// (plane[gr*576 + t*32 + i]) and frames are SYMGPU_MP3_FRAME_FLOATS apart.
+template <int NW>
+__device__ __forceinline__ void window_phase(const float* xt, int row0, int total, int warp, int lane,
+                                             const float* __restrict__ synth_d, float* __restrict__ pcm, int slot_seq0,
+                                             int slots_per_frame, bool stereo) {
+    const int col_lo = lane < 16 ? 16 + lane : (lane == 16 ? 32 : 48 - lane);
+    const int col_hi = lane <= 16 ? 16 - lane : lane - 16;
+    float dlo[8], dhi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float a0 = __ldg(synth_d + 64 * j + lane);
+        dlo[j] = lane > 16 ? -a0 : a0;
+        dhi[j] = -__ldg(synth_d + 64 * j + 32 + lane);
+    }
+    const int per = (total + NW - 1) / NW;
+    const int begin = warp * per;                  // slot index relative to row0
+    const int end = min(total, begin + per);
+    if (begin >= end) return;
+    constexpr uint32_t kRowBytes = kPitch * 8;
+    uint32_t a_lo = smem_u32(xt) + (uint32_t)((row0 + begin - 15) * kPitch + col_lo) * 8u;
+    uint32_t a_hi = smem_u32(xt) + (uint32_t)((row0 + begin - 15) * kPitch + col_hi) * 8u;
+    float2 wl[16], wh[16];
+#pragma unroll
+    for (int m = 0; m < 15; ++m) { // the 15 slots before `begin` -> window index (m+1)&15
+        wl[(m + 1) & 15] = lds64(a_lo + m * kRowBytes);
+        wh[(m + 1) & 15] = lds64(a_hi + m * kRowBytes);
+    }
+    a_lo += 15 * kRowBytes;
+    a_hi += 15 * kRowBytes;
+    const int off1 = stereo ? 1152 : 0; // mono: the channel-1 store lands on the channel-0 word and is overwritten
+    const int frame_jump = SYMGPU_MP3_FRAME_FLOATS - slots_per_frame * 32;
+    for (int base = begin; base < end; base += 16) {
+        const int seq = slot_seq0 + base;
+        const int frame = seq / slots_per_frame, sif = seq - frame * slots_per_frame;
+        float* out0 = pcm + (size_t)frame * SYMGPU_MP3_FRAME_FLOATS + sif * 32 + lane;
+        float* out1 = out0 + frame_jump;        // valid once the block has crossed into the next frame
+        const int kj = slots_per_frame - sif;   // steps until the frame boundary (a frame has >= 18 slots)
+        const int cnt = end - base;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (u < cnt) {
+                wl[u] = lds64(a_lo + u * kRowBytes);
+                wh[u] = lds64(a_hi + u * kRowBytes);
+                float o0 = 0.0f, o1 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 v0 = wl[(u - 2 * j) & 15];
+                    const float2 v1 = wh[(u - 2 * j - 1) & 15];
+                    o0 += v0.x * dlo[j];
+                    o1 += v0.y * dlo[j];
+                    o0 += v1.x * dhi[j];
+                    o1 += v1.y * dhi[j];
+                }
+                float* o = (u < kj ? out0 : out1) + u * 32;
+                o[off1] = o1;
+                o[0] = o0;
+            }
+        }
+        a_lo += 16 * kRowBytes;
+        a_hi += 16 * kRowBytes;
+    }
+}
+
 template <int T, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
+struct Mp3Smem {
+    static constexpr int kRows = 18 * (T + 1);            // region 0 = granule g0-1 (history), then the tile
+    float xt[kRows * kPitch * 2];                         // [row][33][2 channels]
+    alignas(16) float spec[T + 2][2 * 576];               // TMA destination: spectra of the 2 halo + T granules
+    alignas(16) symgpu_mp3_gc units[T + 2][2];            // TMA destination: their descriptors
+    WarpScratch ws[NW];
+    alignas(8) uint64_t bar;
+    bool is_last;
+};
+
+} // namespace
+
+template <int T, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
+    static_assert(NW >= T + 2, "one warp per granule job (tile + 2 halo granules)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* xt = reinterpret_cast<float*>(smem_raw);                       // [(T+2)*18][kPitch][2]
-    WarpScratch* wscr = reinterpret_cast<WarpScratch*>(smem_raw + (size_t)(T + 2) * 18 * kPitch * 8);
+    using Smem = Mp3Smem<T, NW>;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    float* xt = sm.xt;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const Mp3Tile tile = a.tiles[blockIdx.x];
-    const int n = tile.n_granules;
-    const int n_ch = tile.n_ch;
-    const int gpf = tile.gpf;
-    const bool load_state = tile.flags & kTileLoadState;
-    const bool store_state = tile.flags & kTileStoreState;
     const Mp3Tables* __restrict__ tab = a.tab;
-    // Stream state is double-buffered: a launch reads generation g and writes generation g+1, so a
-    // run-starting tile never races with the run-ending tile of the same stream (they are
-    // different CTAs of the same launch).  The last CTA to finish bumps the generations.
-    const uint32_t gen = a.gen[tile.stream];
-    const Mp3StreamState* st_in = a.states + (size_t)tile.stream * 2 + (gen & 1);
-    Mp3StreamState* st = a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
-    const int gseq0 = (int)tile.first_frame * gpf + tile.first_gr; // batch granule sequence index of region 2
+    const int n_tiles = a.n_tiles;
 
-    // ------------------------------------------------------------------------------------------
-    // Phase A+B: one warp per granule ("job"), regions processed in descending rounds so that the
-    // overlap hand-off into region r+1 always targets a region whose own samples are complete.
-    // ------------------------------------------------------------------------------------------
-    const int r_lo = load_state ? 2 : 0;
-    const int n_regions = n + 2;
-    WarpScratch& ws = wscr[warp];
-    const float cs_l = tab->cs[lane & 7], ca_l = tab->ca[lane & 7];
+    auto issue_prefetch = [&](int ti) { // one thread: TMA descriptors + spectra of tile ti into the stage
+        const Mp3Tile t = a.tiles[ti];
+        const int j0 = (t.flags & kTileLoadState) ? 2 : 0;
+        const int shift = t.gpf == 2 ? 1 : 0;
+        const int gseq0 = ((int)t.first_frame << shift) + t.first_gr;
+        mbar_expect_tx(&sm.bar, (uint32_t)(t.n_granules + 2 - j0) * (4608u + 128u));
+        for (int j = j0; j < t.n_granules + 2; ++j) {
+            const int gseq = gseq0 - 2 + j;
+            const size_t slot = ((size_t)(gseq >> shift) * 2 + (gseq & (t.gpf - 1))); // [frame][gr]
+            tma_bulk_g2s(sm.spec[j], a.spectra + slot * 1152, 4608u, &sm.bar);
+            tma_bulk_g2s(sm.units[j], a.units + slot * 2, 128u, &sm.bar);
+        }
+    };
 
-    for (int r_hi = n_regions; r_hi > r_lo; r_hi -= NW) {
-        const int r = r_hi - 1 - warp; // region of this warp's job in this round
-        const bool active = r >= r_lo;
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue_prefetch(blockIdx.x);
+
+    WarpScratch& ws = sm.ws[warp];
+    int it = 0;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++it) {
+        const Mp3Tile tile = a.tiles[ti];
+        const int n = tile.n_granules;
+        const int n_ch = tile.n_ch;
+        const int gpf_shift = tile.gpf == 2 ? 1 : 0;
+        const bool load_state = tile.flags & kTileLoadState;
+        const bool store_state = tile.flags & kTileStoreState;
+        // Stream state is double-buffered: a launch reads generation g and writes generation g+1, so a
+        // run-starting tile never races with the run-ending tile of the same stream.
+        const uint32_t gen = a.gen[tile.stream];
+        const Mp3StreamState* st_in = a.states + (size_t)tile.stream * 2 + (gen & 1);
+        Mp3StreamState* st_out = a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
+        const int gseq0 = ((int)tile.first_frame << gpf_shift) + tile.first_gr; // first granule of the tile
+        mbar_wait(&sm.bar, (uint32_t)(it & 1));
+
+        // --------------------------------------------------------------------------------------
+        // Phase A+B: one warp per granule job j (j = 0, 1: halo granules g0-2, g0-1; j >= 2: the tile),
+        // lane = sub-band, everything in registers.  Job j >= 1 owns XT region j-1 (rows 18(j-1)..).
+        // --------------------------------------------------------------------------------------
+        const int g = warp; // job index
+        const bool active = g < n + 2 && (g >= 2 || !load_state);
         float sec[2][18];
-        float* S = xt + (size_t)r * 18 * kPitch * 2; // region memory doubles as the job's [2][576] scratch
         if (active) {
-            const int gseq = gseq0 + (r - 2);
-            const int frame = gseq / gpf, gr = gseq - frame * gpf;
-            const symgpu_mp3_gc* u = a.units + ((size_t)frame * 2 + gr) * 2;
-            const float4* spec4 = reinterpret_cast<const float4*>(a.spectra + ((size_t)frame * 2 + gr) * 2 * 576);
-
-            // A0: descriptors -> shared (two 64-byte units)
-            if (lane < 8) reinterpret_cast<uint4*>(ws.gc)[lane] = __ldg(reinterpret_cast<const uint4*>(u) + lane);
+            const symgpu_mp3_gc& g0 = sm.units[g][0];
+            const symgpu_mp3_gc& g1 = sm.units[g][1];
+            const float* S = sm.spec[g];
             if (lane < 10) reinterpret_cast<uint32_t*>(ws.smode)[lane] = 0;
             if (lane >= 16 && lane < 26) reinterpret_cast<uint32_t*>(ws.nz)[lane - 16] = 0;
-            __syncwarp();
-            const symgpu_mp3_gc& g0 = ws.gc[0];
-            const symgpu_mp3_gc& g1 = ws.gc[1];
             const int sr = g0.sample_rate_idx;
             const int kind0 = kind_of(g0), kind1 = (n_ch == 2) ? kind_of(g1) : kind0;
             const bool ms = (n_ch == 2) && (g0.flags & SYMGPU_MP3_F_MID_SIDE);
@@ -269,11 +409,11 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
 
             // A1: per-interval requantisation scale (requantize.rs:240-355)
             for (int ch = 0; ch < n_ch; ++ch) {
-                const symgpu_mp3_gc& g = ws.gc[ch];
+                const symgpu_mp3_gc& gg = sm.units[g][ch];
                 const int kind = ch ? kind1 : kind0;
                 const int n_iv = c_mp3.n_edges[sr][kind] - 1;
-                const int gain = (int)g.global_gain - 210;
-                const int shift = (g.flags & SYMGPU_MP3_F_SCALEFAC_SCALE) ? 2 : 1;
+                const int gain = (int)gg.global_gain - 210;
+                const int shift = (gg.flags & SYMGPU_MP3_F_SCALEFAC_SCALE) ? 2 : 1;
                 const int sw = c_mp3.mixed_switch[sr];
                 for (int idx = lane; idx < 40; idx += 32) {
                     float s = 1.0f;
@@ -282,16 +422,15 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                         bool scaled = true;
                         const bool long_part = (kind == kKindLong) || (kind == kKindMixed && idx < sw - 1);
                         if (long_part) {
-                            const int pre = (g.flags & SYMGPU_MP3_F_PREFLAG) ? c_mp3.pre_emphasis[idx] : 0;
-                            const int b = ((g.scalefacs[idx] + pre) << shift) & 0xff;
+                            const int pre = (gg.flags & SYMGPU_MP3_F_PREFLAG) ? c_mp3.pre_emphasis[idx] : 0;
+                            const int b = ((gg.scalefacs[idx] + pre) << shift) & 0xff;
                             e = gain - b;
                         } else if (kind == kKindMixed && idx == sw - 1) {
                             scaled = false; // lines between the last long band and the first short band
                         } else {
-                            const int j = (kind == kKindMixed) ? idx - sw : idx;
-                            const int sfi = (kind == kKindMixed) ? idx : idx; // scalefacs[switch + j]
-                            const int b = (g.scalefacs[sfi] << shift) & 0xff;
-                            e = gain - 8 * (int)g.subblock_gain[j % 3] - b;
+                            const int j = (kind == kKindMixed) ? idx - sw : idx; // scalefacs[switch + j] == scalefacs[idx]
+                            const int b = (gg.scalefacs[idx] << shift) & 0xff;
+                            e = gain - 8 * (int)gg.subblock_gain[j % 3] - b;
                         }
                         if (scaled) s = __ldg(&tab->pow2q[e - kPow2qMin]);
                     }
@@ -300,43 +439,70 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
             }
             __syncwarp();
 
-            // A2: load spectra, requantise, record channel-1 non-zero intervals
-            const uchar4* ivm0 = reinterpret_cast<const uchar4*>(tab->iv_of_line[sr][kind0]);
-            const uchar4* ivm1 = reinterpret_cast<const uchar4*>(tab->iv_of_line[sr][kind1]);
-#pragma unroll 3
-            for (int it = 0; it < 9; ++it) {
-                const int q = it * 32 + lane; // float4 index in [2][144]
-                const int ch = q >= 144;
-                const int l4 = q - ch * 144;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch < n_ch) {
-                    v = __ldg(spec4 + q);
-                    const uchar4 iv = __ldg((ch ? ivm1 : ivm0) + l4);
-                    // Lines at or beyond rzero are +0.0 by contract (requantize.rs:234), and +0 * scale is
-                    // +0, so the reference's "stop at rzero" (requantize.rs:267,:284) needs no predicate.
-                    v.x *= ws.scale[ch][iv.x];
-                    v.y *= ws.scale[ch][iv.y];
-                    v.z *= ws.scale[ch][iv.z];
-                    v.w *= ws.scale[ch][iv.w];
-                    if (ch && is) {
-                        if (v.x != 0.0f) ws.nz[iv.x] = 1;
-                        if (v.y != 0.0f) ws.nz[iv.y] = 1;
-                        if (v.z != 0.0f) ws.nz[iv.z] = 1;
-                        if (v.w != 0.0f) ws.nz[iv.w] = 1;
+            // A2: my 18 lines of each channel, requantised.  The short-block reorder
+            // (hybrid_synthesis.rs:153-215) is a permutation applied AFTER the element-wise requantise
+            // and stereo steps, so it is folded into the load: line d of the sub-band comes from source
+            // line s, and every per-line decision below is taken on s.
+            float x[2][18];
+            // stereo.rs:550-553 sets both rzero to max(rzero) before reorder / antialias / hybrid see them
+            const int rz_joint = max(rz0, rz1);
+            const int rze[2] = {(ms || is) ? rz_joint : rz0, (ms || is) ? rz_joint : rz1};
+            int rzr[2] = {rze[0], rze[1]}; // rzero after the reorder step
+            int ro_start = 0, ro_end = 0;  // reordered line range of channel 1's block kind (joint stereo)
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                if (ch >= n_ch) {
+#pragma unroll
+                    for (int i = 0; i < 18; ++i) x[ch][i] = 0.0f;
+                    continue;
+                }
+                const int kind = ch ? kind1 : kind0;
+                const uint8_t* ivm = tab->iv_of_line[sr][kind];
+                const float* Sc = S + ch * 576;
+                if (kind == kKindLong) {
+                    const uint16_t* iv2 = reinterpret_cast<const uint16_t*>(ivm + 18 * lane);
+#pragma unroll
+                    for (int i = 0; i < 18; i += 2) {
+                        const float2 v = *reinterpret_cast<const float2*>(Sc + 18 * lane + i);
+                        const unsigned ivp = __ldg(iv2 + (i >> 1));
+                        // lines at or beyond rzero are +0.0 by contract (requantize.rs:234): 0 * scale = 0
+                        x[ch][i] = v.x * ws.scale[ch][ivp & 0xff];
+                        x[ch][i + 1] = v.y * ws.scale[ch][ivp >> 8];
+                        if (ch && is) {
+                            if (x[ch][i] != 0.0f) ws.nz[ivp & 0xff] = 1;
+                            if (x[ch][i + 1] != 0.0f) ws.nz[ivp >> 8] = 1;
+                        }
+                    }
+                } else {
+                    const int m = (kind == kKindMixed) ? 1 : 0;
+                    const int sw = m ? c_mp3.mixed_switch[sr] : 0;
+                    const uint16_t* e = tab->edges[sr][kind] + sw;
+                    const int n_quads = (c_mp3.n_edges[sr][kind] - sw - 1) / 3;
+                    const int rz = rze[ch];
+                    const bool below = (lane < n_quads) && ((int)e[3 * lane] < rz);
+                    const int n_done = __popc(__ballot_sync(0xffffffffu, below)); // reordered quads form a prefix
+                    const int start = e[0], i_end = e[3 * n_done];
+                    rzr[ch] = max(rz, i_end); // hybrid_synthesis.rs:213
+                    if (ch == n_ch - 1) { ro_start = start; ro_end = i_end; }
+                    const uint16_t* src = tab->reorder_src[sr][m];
+#pragma unroll
+                    for (int i = 0; i < 18; ++i) {
+                        const int d = 18 * lane + i;
+                        const int s = (d >= start && d < i_end) ? (int)__ldg(src + d) : d;
+                        const int iv = __ldg(ivm + s);
+                        x[ch][i] = Sc[s] * ws.scale[ch][iv];
+                        if (ch && is && x[ch][i] != 0.0f) ws.nz[iv] = 1;
                     }
                 }
-                reinterpret_cast<float4*>(S)[q] = v;
             }
             __syncwarp();
 
-            // A3/A4: joint stereo (stereo.rs:485-556)
+            // A3/A4: joint stereo (stereo.rs:485-556), decided per SOURCE line
             if (ms || is) {
                 const int end = max(rz0, rz1);
                 int bound = end;
                 if (is) {
                     // Warp-parallel restatement of the two top-down scans (stereo.rs:198-261, :265-482).
-                    // Every lane derives the same facts from one 40-bit "interval of channel 1 is
-                    // non-zero" mask; lane iv then labels interval iv (and iv + 32).
                     const bool mpeg1 = g1.flags & SYMGPU_MP3_F_MPEG1;
                     const int inv_pos = mpeg1 ? 7 : 31;
                     const float(*rt)[2] = mpeg1 ? c_mp3.is_mpeg1 : c_mp3.is_mpeg2[(g1.flags & SYMGPU_MP3_F_SFC_LSB) ? 1 : 0];
@@ -349,8 +515,6 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                     if (lane + 32 < n_iv) nzb = ws.nz[lane + 32] && (kind1 != kKindLong || (int)e[lane + 32] < rz1);
                     const unsigned long long nzmask = (unsigned long long)__ballot_sync(0xffffffffu, nza) |
                                                       ((unsigned long long)__ballot_sync(0xffffffffu, nzb) << 32);
-                    // is_lo: first interval labelled by the scan; iv_is[w]: first interval of window w that is
-                    // intensity coded (every labelled interval of that window at or above it is).
                     int is_lo, first_is0, first_is1, first_is2;
                     if (kind1 == kKindLong) {
                         const int hb = nzmask ? 63 - __clzll((long long)nzmask) : -1; // highest non-zero band
@@ -390,7 +554,7 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                             coded = true;
                         } else {
                             const int sw = (kind1 == kKindMixed) ? c_mp3.mixed_switch[sr] : 0;
-                            if (iv < sw) coded = true; // mixed long band reached by the scan: always zero
+                            if (iv < sw) coded = true;
                             else {
                                 const int w = (iv - sw) % 3;
                                 coded = iv >= (w == 0 ? first_is0 : w == 1 ? first_is1 : first_is2);
@@ -398,8 +562,6 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                         }
                         uint8_t mode = mode_hi;
                         if (coded) {
-                            // is_pos: long: scalefacs[b], band 21 copies band 20 (stereo.rs:228-230);
-                            // short: scalefacs[k], the last three copy [33..36) (stereo.rs:352-354).
                             const int k = (kind1 == kKindLong) ? (iv == 21 ? 20 : iv) : (iv < 36 ? iv : iv - 3);
                             const int pos = g1.scalefacs[k];
                             if (pos < inv_pos) { // process_intensity, stereo.rs:168-188
@@ -409,146 +571,89 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                         }
                         ws.smode[iv] = mode;
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (!is) {
-                    // mid/side only: every line below max(rzero) (stereo.rs:536-544)
-                    for (int l4 = lane; l4 * 4 < bound; l4 += 32) {
-                        float4 m = reinterpret_cast<float4*>(S)[l4];
-                        float4 d = reinterpret_cast<float4*>(S + 576)[l4];
-                        const int l = l4 * 4;
-                        float4 L, R;
-                        L.x = (m.x + d.x) * kFrac1Sqrt2; R.x = (m.x - d.x) * kFrac1Sqrt2;
-                        L.y = (m.y + d.y) * kFrac1Sqrt2; R.y = (m.y - d.y) * kFrac1Sqrt2;
-                        L.z = (m.z + d.z) * kFrac1Sqrt2; R.z = (m.z - d.z) * kFrac1Sqrt2;
-                        L.w = (m.w + d.w) * kFrac1Sqrt2; R.w = (m.w - d.w) * kFrac1Sqrt2;
-                        if (l + 3 >= bound) { // rzero is not always a multiple of 4: keep the tail untouched
-                            if (l + 1 >= bound) { L.y = m.y; R.y = d.y; }
-                            if (l + 2 >= bound) { L.z = m.z; R.z = d.z; }
-                            L.w = m.w; R.w = d.w;
+                // Source line of my i-th value: with joint stereo both channels share the block kind and the
+                // post-stereo rzero, hence the reorder map computed in A2.
+                const bool shortk = kind1 != kKindLong;
+                const int start = ro_start, i_end = ro_end;
+                const uint16_t* src = tab->reorder_src[sr][kind1 == kKindMixed ? 1 : 0];
+                const uint8_t* ivm1 = tab->iv_of_line[sr][kind1];
+#pragma unroll
+                for (int i = 0; i < 18; ++i) {
+                    const int d = 18 * lane + i;
+                    int mode;
+                    if (!is) {
+                        // MS only: decided on the source line, but "below bound" is the same set before and
+                        // after the permutation only if we test the source line
+                        int s = d;
+                        if (shortk && d >= start && d < i_end) s = (int)__ldg(src + d);
+                        mode = (s < bound) ? 1 : 0;
+                    } else {
+                        int s = d;
+                        if (shortk && d >= start && d < i_end) s = (int)__ldg(src + d);
+                        mode = (s < bound) ? (ms ? 1 : 0) : (int)ws.smode[__ldg(ivm1 + s)];
+                        if (mode == 2) {
+                            const float2 r = ws.sratio[__ldg(ivm1 + s)];
+                            const float isv = x[0][i];
+                            x[0][i] = r.x * isv;
+                            x[1][i] = r.y * isv;
                         }
-                        reinterpret_cast<float4*>(S)[l4] = L;
-                        reinterpret_cast<float4*>(S + 576)[l4] = R;
                     }
-                } else {
-                for (int l4 = lane; l4 < 144; l4 += 32) {
-                    float4 m = reinterpret_cast<float4*>(S)[l4];
-                    float4 s = reinterpret_cast<float4*>(S + 576)[l4];
-                    const uchar4 iv = __ldg(ivm1 + l4);
-                    const int l = l4 * 4;
-                    auto apply = [&](float& x, float& y, int line, int ivx) {
-                        int mode;
-                        if (line < bound) mode = ms ? 1 : 0; else mode = ws.smode[ivx];
-                        if (mode == 1) { // process_mid_side, stereo.rs:143-152
-                            const float left = (x + y) * kFrac1Sqrt2;
-                            const float right = (x - y) * kFrac1Sqrt2;
-                            x = left;
-                            y = right;
-                        } else if (mode == 2) {
-                            const float2 rt = ws.sratio[ivx];
-                            const float isv = x;
-                            x = rt.x * isv;
-                            y = rt.y * isv;
-                        }
-                    };
-                    apply(m.x, s.x, l + 0, iv.x);
-                    apply(m.y, s.y, l + 1, iv.y);
-                    apply(m.z, s.z, l + 2, iv.z);
-                    apply(m.w, s.w, l + 3, iv.w);
-                    reinterpret_cast<float4*>(S)[l4] = m;
-                    reinterpret_cast<float4*>(S + 576)[l4] = s;
+                    if (mode == 1) { // process_mid_side, stereo.rs:143-152
+                        const float left = (x[0][i] + x[1][i]) * kFrac1Sqrt2;
+                        const float right = (x[0][i] - x[1][i]) * kFrac1Sqrt2;
+                        x[0][i] = left;
+                        x[1][i] = right;
+                    }
                 }
-                }
-                rz0 = end;
-                rz1 = end;
-                __syncwarp();
             }
 
-            // A5: reorder short blocks (hybrid_synthesis.rs:153-215)
-            for (int ch = 0; ch < n_ch; ++ch) {
-                const int kind = ch ? kind1 : kind0;
-                if (kind == kKindLong) continue;
-                const int m = (kind == kKindMixed) ? 1 : 0;
-                const int sw = m ? c_mp3.mixed_switch[sr] : 0;
-                const uint16_t* e = tab->edges[sr][kind] + sw;
-                const int n_quads = (c_mp3.n_edges[sr][kind] - sw - 1) / 3;
-                int rz = ch ? rz1 : rz0;
-                const bool below = (lane < n_quads) && ((int)e[3 * lane] < rz);
-                const int n_done = __popc(__ballot_sync(0xffffffffu, below)); // quads form a prefix
-                const int start = e[0];
-                const int i_end = e[3 * n_done];
-                const uint16_t* src = tab->reorder_src[sr][m];
-                float* Sc = S + ch * 576;
-                float tmp[18];
+            // A6: antialias (hybrid_synthesis.rs:218-277) across neighbouring lanes
+            int rzh[2]; // rzero seen by hybrid_synthesis
 #pragma unroll
-                for (int k = 0; k < 18; ++k) {
-                    const int d = k * 32 + lane;
-                    tmp[k] = (d >= start && d < i_end) ? Sc[__ldg(src + d)] : 0.0f;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < 18; ++k) {
-                    const int d = k * 32 + lane;
-                    if (d >= start && d < i_end) Sc[d] = tmp[k];
-                }
-                rz = max(rz, i_end);
-                if (ch) rz1 = rz; else rz0 = rz;
-                __syncwarp();
-            }
-
-            // A6: antialias (hybrid_synthesis.rs:218-277)
-            for (int ch = 0; ch < n_ch; ++ch) {
+            for (int ch = 0; ch < 2; ++ch) {
                 const int kind = ch ? kind1 : kind0;
-                if (kind == kKindShort) continue;
+                rzh[ch] = rzr[ch];
+                if (ch >= n_ch || kind == kKindShort) continue; // (warp-uniform)
                 const int sb_limit = (kind == kKindMixed) ? 2 : 32;
-                int rz = ch ? rz1 : rz0;
-                rz = 18 * min(min(sb_limit, rz / 18 + 2), 32);
-                float* Sc = S + ch * 576;
+                const int rz = 18 * min(min(sb_limit, rzr[ch] / 18 + 2), 32);
+                rzh[ch] = rz;
+                float nb_lo[8], nb_up[8];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int p = it * 32 + lane; // (boundary-1)*8 + i
-                    const int sbb = 18 * ((p >> 3) + 1);
-                    if (sbb < rz) { // p < 248 always holds when sbb <= 558
-                        const int i = p & 7;
-                        const int li = sbb - 1 - i, ui = sbb + i;
-                        const float lower = Sc[li], upper = Sc[ui];
-                        Sc[li] = lower * cs_l - upper * ca_l;
-                        Sc[ui] = upper * cs_l + lower * ca_l;
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    nb_lo[i] = __shfl_up_sync(0xffffffffu, x[ch][17 - i], 1);   // lower[li] of the boundary below me
+                    nb_up[i] = __shfl_down_sync(0xffffffffu, x[ch][i], 1);      // upper[ui] of the boundary above me
                 }
-                if (ch) rz1 = rz; else rz0 = rz;
+                const bool do_bottom = lane >= 1 && 18 * lane < rz;
+                const bool do_top = lane < 31 && 18 * (lane + 1) < rz;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float up = x[ch][i], lo = x[ch][17 - i];
+                    if (do_bottom) x[ch][i] = up * c_mp3.cs[i] + nb_lo[i] * c_mp3.ca[i];       // samples[ui]
+                    if (do_top) x[ch][17 - i] = lo * c_mp3.cs[i] - nb_up[i] * c_mp3.ca[i];     // samples[li]
+                }
             }
-            __syncwarp();
 
-            // B: hybrid synthesis, lane = sub-band (hybrid_synthesis.rs:280-359)
-            float xin[2][18];
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-                for (int i = 0; i < 18; i += 2) {
-                    const float2 v = *reinterpret_cast<const float2*>(S + ch * 576 + 18 * lane + i);
-                    xin[ch][i] = v.x;
-                    xin[ch][i + 1] = v.y;
-                }
-            __syncwarp(); // every lane holds its inputs; the scratch may now be overwritten
-            float* X = xt + (size_t)r * 18 * kPitch * 2;
+            // B: hybrid synthesis (hybrid_synthesis.rs:280-359)
+            float* X = xt + (size_t)(18 * (g - 1)) * kPitch * 2; // unused by job 0 (it only hands its overlap on)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 float first[18];
                 if (ch < n_ch) {
-                    const symgpu_mp3_gc& g = ws.gc[ch];
+                    const symgpu_mp3_gc& gg = sm.units[g][ch];
                     const int kind = ch ? kind1 : kind0;
-                    const int rz = ch ? rz1 : rz0;
+                    const int rz = rzh[ch];
                     const int sb_limit = (rz + 17) / 18;
                     const int sb_split = (kind == kKindShort) ? 0 : (kind == kKindMixed) ? 2 : 32;
                     const int long_end = min(sb_split, sb_limit);
                     if (lane < long_end) {
-                        const int wsel = g.block_type == SYMGPU_MP3_START ? 1 : g.block_type == SYMGPU_MP3_END ? 3 : 0;
-                        imdct36(xin[ch], c_mp3.imdct_win[wsel], first, sec[ch]);
+                        const int wsel = gg.block_type == SYMGPU_MP3_START ? 1 : gg.block_type == SYMGPU_MP3_END ? 3 : 0;
+                        imdct36(x[ch], c_mp3.imdct_win[wsel], first, sec[ch]);
                     } else if (lane < sb_limit) {
-                        imdct12x3(xin[ch], first, sec[ch]);
+                        imdct12x3(x[ch], first, sec[ch]);
                     } else {
-                        // samples = overlap; overlap = 0  (:351-358).  overlap + (-0.0) == overlap bit for bit.
+                        // samples = overlap; overlap = 0 (:351-358).  overlap + (-0.0) == overlap bit for bit.
 #pragma unroll
                         for (int i = 0; i < 18; ++i) {
                             first[i] = -0.0f;
@@ -562,15 +667,26 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
                         sec[ch][i] = 0.0f;
                     }
                 }
+                if (g == 2 && load_state) { // a run's first granule takes the overlap of the stream state
 #pragma unroll
-                for (int t = 0; t < 18; ++t) X[(t * kPitch + lane) * 2 + ch] = finv(first[t], lane, t);
+                    for (int t = 0; t < 18; ++t) first[t] = first[t] + st_in->overlap[ch][lane][t];
+                }
+                if (g >= 1) {
+#pragma unroll
+                    for (int t = 0; t < 18; ++t) X[(t * kPitch + lane) * 2 + ch] = finv(first[t], lane, t);
+                }
             }
         }
         __syncthreads();
-        // overlap hand-off: region r+1 += second(r)   (x = overlap + imdct_first, commutative)
+        // The stage is free: fetch this CTA's next tile while the current one is in its DCT / window phases.
+        if (threadIdx.x == NW * 32 - 32 && ti + (int)gridDim.x < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_prefetch(ti + gridDim.x);
+        }
+        // overlap hand-off: region of job g+1 += second(g); the run's last granule feeds the stream state
         if (active) {
-            if (r + 1 < n_regions) {
-                float* Xn = xt + (size_t)(r + 1) * 18 * kPitch * 2;
+            if (g + 1 < n + 2) {
+                float* Xn = xt + (size_t)(18 * g) * kPitch * 2;
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
@@ -582,167 +698,93 @@ __global__ void __launch_bounds__(NW * 32, 2) mp3_synth_kernel(Mp3Args a) {
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-                    for (int t = 0; t < 18; ++t) st->overlap[ch][lane][t] = sec[ch][t];
+                    for (int t = 0; t < 18; ++t) st_out->overlap[ch][lane][t] = sec[ch][t];
+            }
+        }
+        if (load_state) { // polyphase history (rows 3..17 of region 0) from the stream state
+            for (int idx = threadIdx.x; idx < 15 * kPitch; idx += NW * 32) {
+                const int s = idx / kPitch, col = idx - s * kPitch;
+                float2 v = make_float2(0.0f, 0.0f);
+                if (col < 32) v = st_in->dhist[s][col];
+                *reinterpret_cast<float2*>(xt + (size_t)((3 + s) * kPitch + col) * 2) = v;
             }
         }
         __syncthreads();
-    }
 
-    // A run-starting tile takes the overlap and the 15-slot polyphase history from the stream state.
-    float* hist = xt + (size_t)(18 + 3) * kPitch * 2; // region 1, slot 3
-    if (load_state) {
-        float* X2 = xt + (size_t)2 * 18 * kPitch * 2;
-        for (int idx = threadIdx.x; idx < 2 * 32 * 18; idx += NW * 32) {
-            const int ch = idx / 576, rem = idx - ch * 576, sb = rem / 18, t = rem - sb * 18;
-            float* p = X2 + (t * kPitch + sb) * 2 + ch;
-            *p = *p + finv(st_in->overlap[ch][sb][t], sb, t);
-        }
-        for (int idx = threadIdx.x; idx < 15 * 32; idx += NW * 32) {
-            const int s = idx >> 5, col = idx & 31;
-            *reinterpret_cast<float2*>(hist + (s * kPitch + col) * 2) = st_in->dhist[s][col];
-        }
-    }
-    __syncthreads();
-
-    // ------------------------------------------------------------------------------------------
-    // Phase C: DCT-32 of every time slot, in place.  Half-warp = 16 slots of one channel, so the
-    // 32-bit shared accesses of a warp hit 32 distinct banks (row pitch 66 words).
-    // ------------------------------------------------------------------------------------------
-    {
-        const int s_first = load_state ? 36 : 18 + 3;
-        const int s_last = n_regions * 18;
-        const int ch = lane >> 4;
-        for (int base = s_first + warp * 16; base < s_last; base += NW * 16) {
-            const int s = base + (lane & 15);
-            if (s < s_last) {
-                float* row = xt + (size_t)s * kPitch * 2 + ch;
-                float x[32], y[32];
+        // --------------------------------------------------------------------------------------
+        // Phase C: DCT-32 of every time slot of the tile, in place.  Half-warp = 16 slots of one
+        // channel: the 32-bit accesses of a warp hit 32 distinct banks (row pitch 66 words).
+        // --------------------------------------------------------------------------------------
+        {
+            const int row_begin = load_state ? 18 : 3;
+            const int row_end = 18 * (n + 1);
+            const int chn = lane >> 4;
+            for (int base = row_begin + warp * 16; base < row_end; base += NW * 16) {
+                const int s = base + (lane & 15);
+                if (s < row_end) {
+                    float* row = xt + (size_t)s * kPitch * 2 + chn;
+                    float v[32], y[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = row[2 * i];
-                lee_dct<32>(x, y);
+                    for (int i = 0; i < 32; ++i) v[i] = row[2 * i];
+                    lee_dct<32>(v, y);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) row[2 * i] = y[i];
-                row[64] = 0.0f; // column 32: V[16] = 0.0 (synthesis.rs:263)
-            }
-        }
-        if (load_state) {
-            for (int idx = threadIdx.x; idx < 30; idx += NW * 32) hist[((idx >> 1) * kPitch + 32) * 2 + (idx & 1)] = 0.0f;
-        }
-    }
-    __syncthreads();
-
-    // ------------------------------------------------------------------------------------------
-    // Phase D: polyphase window (synthesis.rs:247-263, :309-327).  lane = PCM sample index i; each
-    // warp walks a contiguous range of slots with a 16-deep register window of (V_lo[i], V_hi[i]).
-    //   V_lo[i] =  d[16+i] (i<16) | 0 (i=16) | -d[48-i] (i>16);   V_hi[i] = -d[16-i] (i<=16) | -d[i-16]
-    // ------------------------------------------------------------------------------------------
-    {
-        const int col_lo = lane < 16 ? 16 + lane : (lane == 16 ? 32 : 48 - lane);
-        const int col_hi = lane <= 16 ? 16 - lane : lane - 16;
-        float dlo[8], dhi[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float a0 = __ldg(&tab->synth_d[64 * j + lane]);
-            dlo[j] = lane > 16 ? -a0 : a0;
-            dhi[j] = -__ldg(&tab->synth_d[64 * j + 32 + lane]);
-        }
-        const int total = n * 18;
-        const int per = (total + NW - 1) / NW;
-        const int s_begin = 36 + warp * per;
-        const int s_end = min(36 + total, s_begin + per);
-        if (s_begin < s_end) {
-            float2 wl[16], wh[16];
-#pragma unroll
-            for (int m = 0; m < 15; ++m) { // slots s_begin-15 .. s_begin-1 -> index (m+1)&15
-                const float* row = xt + (size_t)(s_begin - 15 + m) * kPitch * 2;
-                wl[(m + 1) & 15] = *reinterpret_cast<const float2*>(row + 2 * col_lo);
-                wh[(m + 1) & 15] = *reinterpret_cast<const float2*>(row + 2 * col_hi);
-            }
-            // Output pointer of slot s_begin; consecutive slots of a frame are contiguous in a PCM plane
-            // (plane[gr*576 + t*32 + i]), frames are SYMGPU_MP3_FRAME_FLOATS apart.
-            const int slots_per_frame = 18 * gpf;
-            const int q0 = (gseq0 * 18) + (s_begin - 36); // slot sequence index within the batch
-            int sif = q0 % slots_per_frame;                // slot in frame
-            float* out = a.pcm + (size_t)(q0 / slots_per_frame) * SYMGPU_MP3_FRAME_FLOATS + sif * 32 + lane;
-            const int frame_jump = SYMGPU_MP3_FRAME_FLOATS - slots_per_frame * 32;
-            const bool stereo_out = n_ch == 2;
-            for (int base = s_begin; base < s_end; base += 16) {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int s = base + u;
-                    if (s < s_end) {
-                        const float* row = xt + (size_t)s * kPitch * 2;
-                        wl[u] = *reinterpret_cast<const float2*>(row + 2 * col_lo);
-                        wh[u] = *reinterpret_cast<const float2*>(row + 2 * col_hi);
-                        float o0 = 0.0f, o1 = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float2 v0 = wl[(u - 2 * j) & 15];
-                            const float2 v1 = wh[(u - 2 * j - 1) & 15];
-                            o0 += v0.x * dlo[j];
-                            o1 += v0.y * dlo[j];
-                            o0 += v1.x * dhi[j];
-                            o1 += v1.y * dhi[j];
-                        }
-                        out[0] = o0;
-                        if (stereo_out) out[1152] = o1;
-                        out += 32;
-                        if (++sif == slots_per_frame) {
-                            sif = 0;
-                            out += frame_jump;
-                        }
-                    }
+                    for (int i = 0; i < 32; ++i) row[2 * i] = y[i];
+                    row[64] = 0.0f; // column 32: V[16] = 0.0 (synthesis.rs:263)
                 }
             }
         }
-    }
+        __syncthreads();
 
-    // The run's last tile publishes the polyphase history (last 15 DCT vectors) for the next batch.
-    if (store_state) {
-        const float* last = xt + (size_t)(n_regions * 18 - 15) * kPitch * 2;
-        for (int idx = threadIdx.x; idx < 15 * 32; idx += NW * 32) {
-            const int s = idx >> 5, col = idx & 31;
-            st->dhist[s][col] = *reinterpret_cast<const float2*>(last + (s * kPitch + col) * 2);
+        // Phase D: polyphase window (synthesis.rs:247-263, :309-327), see window_phase().
+        window_phase<NW>(xt, 18, n * 18, warp, lane, tab->synth_d, a.pcm, gseq0 * 18, 18 << gpf_shift, n_ch == 2);
+        __syncthreads();
+        // The run's last tile publishes the polyphase history (last 15 DCT vectors) for the next batch.
+        if (store_state) {
+            const float* last = xt + (size_t)(18 * (n + 1) - 15) * kPitch * 2;
+            for (int idx = threadIdx.x; idx < 15 * 32; idx += NW * 32) {
+                const int s = idx >> 5, col = idx & 31;
+                st_out->dhist[s][col] = *reinterpret_cast<const float2*>(last + (size_t)(s * kPitch + col) * 2);
+            }
         }
+        __syncthreads(); // XT and the stage descriptors are reused by the next tile
     }
 
     // Launch epilogue: the last CTA to retire publishes the new state generation of every run.
-    __shared__ bool is_last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+        sm.is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last) {
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += NW * 32)
+    if (sm.is_last) {
+        for (int i = threadIdx.x; i < n_tiles; i += NW * 32)
             if (a.tiles[i].flags & kTileStoreState) a.gen[a.tiles[i].stream] += 1;
         if (threadIdx.x == 0) *a.done = 0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-namespace {
-template <int T, int NW>
-cudaError_t launch(const Mp3Args& a, int n_tiles, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)(T + 2) * 18 * kPitch * 8 + NW * sizeof(WarpScratch);
-    static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(mp3_synth_kernel<T, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[dev & 63] = true;
-    }
-    mp3_synth_kernel<T, NW><<<n_tiles, NW * 32, smem, stream>>>(a);
-    return cudaGetLastError();
-}
-} // namespace
-
 int mp3_tile_granules() { return kMp3TileGranules; }
 
-cudaError_t mp3_launch(const Mp3Args& a, int n_tiles, cudaStream_t stream) {
-    return launch<kMp3TileGranules, kMp3Warps>(a, n_tiles, stream);
+cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream) {
+    constexpr size_t smem = sizeof(Mp3Smem<kMp3TileGranules, kMp3Warps>);
+    static int grid_for_device[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!grid_for_device[dev & 63]) {
+        e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int n_sm = 0, per_sm = 0;
+        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, kMp3Warps * 32, smem);
+        if (e != cudaSuccess) return e;
+        grid_for_device[dev & 63] = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    const int grid = a.n_tiles < grid_for_device[dev & 63] ? a.n_tiles : grid_for_device[dev & 63];
+    mp3_synth_kernel<kMp3TileGranules, kMp3Warps><<<grid, kMp3Warps * 32, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 } // namespace symgpu

@@ -9,11 +9,17 @@
 
 namespace symgpu {
 
-// Granules per tile and warps per CTA.  15 granules = 270 time slots; with the 15-slot history the
-// DCT phase has 285 slot-jobs for 288 threads, and the 17 granule jobs (15 + 2 halo) take two
-// rounds of 9 warps.  Shared memory: 17 regions x 4752 B + scratch = 88 KB -> 2 CTAs / SM.
-constexpr int kMp3TileGranules = 15;
-constexpr int kMp3Warps = 9;
+// Granules per tile and warps per CTA.  One persistent CTA of 16 warps per SM (4 per scheduler: 5
+// would cap the kernel at 96 registers because registers are partitioned per scheduler): 13 + 2 halo
+// granule jobs in the hybrid phase; (15 + 234) time slots x 2 channels = 498 DCT jobs for 512
+// threads; 234 slots = 15 per warp in the window phase.  Shared memory: 252 XT rows (66.5 KB) + the
+// TMA stage of 15 granules (71 KB) + scratch.
+#ifndef SYMGPU_MP3_T
+#define SYMGPU_MP3_T 13
+#define SYMGPU_MP3_NW 16
+#endif
+constexpr int kMp3TileGranules = SYMGPU_MP3_T;
+constexpr int kMp3Warps = SYMGPU_MP3_NW;
 
 enum : uint8_t { kTileLoadState = 1, kTileStoreState = 2 };
 
@@ -45,6 +51,7 @@ struct Mp3Args {
     const float* spectra;
     float* pcm;
     const Mp3Tile* tiles;
+    int n_tiles;
     Mp3StreamState* states; // [n_streams][2] double-buffered, see gen
     uint32_t* gen;          // [n_streams] state generation; buffer (gen & 1) is current
     unsigned* done;         // retired-CTA counter (self-resetting)
@@ -52,7 +59,7 @@ struct Mp3Args {
 };
 
 cudaError_t mp3_upload_const(const Mp3Tables& t, cudaStream_t stream);
-cudaError_t mp3_launch(const Mp3Args& a, int n_tiles, cudaStream_t stream);
+cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream);
 int mp3_tile_granules();
 
 } // namespace symgpu

@@ -236,9 +236,9 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
     int n_tiles = 0;
     symgpu_status s = ensure_tiles(ctx, runs, n_runs, n_frames, &n_tiles);
     if (s != SYMGPU_OK) return s;
-    Mp3Args a{units, spectra, pcm, ctx->d_tiles, ctx->d_mp3_states, ctx->d_mp3_gen,
+    Mp3Args a{units, spectra, pcm, ctx->d_tiles, n_tiles, ctx->d_mp3_states, ctx->d_mp3_gen,
               ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
-    CU(ctx, mp3_launch(a, n_tiles, ctx->stream));
+    CU(ctx, mp3_launch(a, ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;
 }
