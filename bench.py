@@ -149,15 +149,9 @@ def run_ours(args):
 
     # The one collective of this path: broadcast the host-built table blob from rank 0 so that every
     # GPU decodes with byte-identical tables even if host libm builds differ between nodes.
-    lib = sb.lib()
-    nbytes = lib.symgpu_tables_host_blob(None, 0)
-    blob = np.zeros(nbytes, dtype=np.uint8)
-    lib.symgpu_tables_host_blob(blob.ctypes.data_as(ctypes.c_void_p), nbytes)
     if world > 1:
-        t = torch.from_numpy(blob).to(dev)
-        dist.broadcast(t, src=0)
-        blob = t.cpu().numpy()
-        eng.upload_tables(blob)
+        from symphonia_b200 import sharding
+        eng.upload_tables(sharding.broadcast_tables(dist, dev, src=0))
 
     # Per-rank batch (weak scaling): distinct seed per rank, same shape.
     units, spectra, runs = workloads.mp3_batch(N_STREAMS, FRAMES_PER_STREAM, seed=workloads.SEED_BASE + 1 + 1000 * rank)

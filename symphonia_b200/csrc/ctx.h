@@ -32,6 +32,10 @@ struct symgpu_ctx {
     // staging for the host entry points
     void* d_stage = nullptr;
     size_t stage_cap = 0;
+    // copy pipeline of the host entry points: H2D on copy_in, kernels on `stream`, D2H on copy_out
+    static constexpr int kMaxSlices = 8;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
     // ---- AAC / Vorbis ----
     symgpu::CodecTables* d_codec_tab = nullptr;
     symgpu::CodecChunk* d_chunks = nullptr;

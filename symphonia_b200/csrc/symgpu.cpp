@@ -5,6 +5,7 @@
 // CUDA device is usable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -22,7 +23,7 @@ namespace {
 // Cuts the caller's runs into per-CTA tiles (mp3_kernel.h).  Returns SYMGPU_OK or an argument /
 // limit error; never touches the device.
 symgpu_status build_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
-                          std::vector<Mp3Tile>& out) {
+                          std::vector<Mp3Tile>& out, bool whole_batch = true) {
     const int T = mp3_tile_granules();
     uint64_t covered = 0;
     out.clear();
@@ -53,7 +54,7 @@ symgpu_status build_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t 
             q0 = q1;
         }
     }
-    if (covered != n_frames) return SYMGPU_ERR_ARG; // runs must tile the batch exactly
+    if (whole_batch && covered != n_frames) return SYMGPU_ERR_ARG; // runs must tile the batch exactly
     return SYMGPU_OK;
 }
 
@@ -187,6 +188,12 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (ctx->d_vorbis_floors) cudaFree(ctx->d_vorbis_floors);
     if (ctx->d_vorbis_states) cudaFree(ctx->d_vorbis_states);
     if (ctx->d_vorbis_gen) cudaFree(ctx->d_vorbis_gen);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (int i = 0; i < symgpu_ctx::kMaxSlices; ++i) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -250,28 +257,101 @@ symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
     DeviceGuard guard(ctx->device);
     const size_t unit_bytes = (size_t)n_frames * 4 * sizeof(symgpu_mp3_gc);
     const size_t spec_bytes = (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
-    const size_t need = unit_bytes + 2 * spec_bytes;
-    if (need > ctx->stage_cap) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_stage) cudaFree(ctx->d_stage);
-        ctx->d_stage = nullptr;
-        ctx->stage_cap = 0;
-        CU(ctx, cudaMalloc(&ctx->d_stage, need));
-        ctx->stage_cap = need;
-    }
+    symgpu_status s = ensure_stage(ctx, unit_bytes + 2 * spec_bytes);
+    if (s != SYMGPU_OK) return s;
     char* base = static_cast<char*>(ctx->d_stage);
     float* d_spec = reinterpret_cast<float*>(base);
     float* d_pcm = reinterpret_cast<float*>(base + spec_bytes);
     symgpu_mp3_gc* d_units = reinterpret_cast<symgpu_mp3_gc*>(base + 2 * spec_bytes);
-    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(d_spec, spectra, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
     // Mono / MPEG-2 frames leave part of each PCM slot untouched: define it as zero.
-    bool partial = false;
-    for (uint32_t r = 0; r < n_runs; ++r) partial |= runs[r].granules_per_frame == 1 || runs[r].channels == 1;
+    bool partial = false, sorted = true;
+    uint64_t next = 0;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        partial |= runs[r].granules_per_frame == 1 || runs[r].channels == 1;
+        sorted &= runs[r].first_frame == next;
+        next += runs[r].n_frames;
+    }
+    sorted &= next == n_frames;
     if (partial) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
-    symgpu_status s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
-    if (s != SYMGPU_OK) return s;
-    CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+
+    if (!sorted || n_frames < 512 || n_runs < 2) {
+        // small or unsorted batch: one copy in, one launch, one copy out
+        CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d_spec, spectra, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
+        if (s != SYMGPU_OK) return s;
+        CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return SYMGPU_OK;
+    }
+
+    // Copy pipeline: the batch is cut into slices of whole runs; the H2D copy of slice i+1 (copy_in),
+    // the kernel of slice i (ctx->stream) and the D2H copy of slice i-1 (copy_out) overlap, so both
+    // PCIe directions stay busy.
+    if (!ctx->copy_in) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < symgpu_ctx::kMaxSlices; ++i) {
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+        }
+    }
+    const int n_slices = (int)std::min<uint32_t>(symgpu_ctx::kMaxSlices, n_runs);
+    struct Slice { uint32_t r0, r1, f0, f1; int t0, t1; };
+    std::vector<Slice> slices;
+    std::vector<Mp3Tile> all_tiles, tiles;
+    uint32_t r = 0;
+    for (int i = 0; i < n_slices; ++i) {
+        const uint32_t target = (uint32_t)(((uint64_t)n_frames * (i + 1)) / n_slices);
+        Slice sl{r, r, runs[r].first_frame, 0, (int)all_tiles.size(), 0};
+        while (r < n_runs && (runs[r].first_frame + runs[r].n_frames <= target || sl.r1 == sl.r0)) {
+            ++r;
+            sl.r1 = r;
+        }
+        if (i + 1 == n_slices) { r = n_runs; sl.r1 = n_runs; }
+        sl.f1 = sl.r1 < n_runs ? runs[sl.r1].first_frame : n_frames;
+        s = build_tiles(ctx, runs + sl.r0, sl.r1 - sl.r0, n_frames, tiles, false);
+        if (s != SYMGPU_OK) return s;
+        all_tiles.insert(all_tiles.end(), tiles.begin(), tiles.end());
+        sl.t1 = (int)all_tiles.size();
+        if (sl.r1 > sl.r0) slices.push_back(sl);
+        if (r >= n_runs) break;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->cached_runs.clear(); // the cached tile list of the device entry point is about to be replaced
+    ctx->cached_frames = 0;
+    if (all_tiles.size() > ctx->tiles_cap) {
+        if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+        if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
+        ctx->d_tiles = nullptr;
+        ctx->h_tiles = nullptr;
+        ctx->tiles_cap = 0;
+        const size_t cap = all_tiles.size() * 2 + 64;
+        CU(ctx, cudaMalloc(&ctx->d_tiles, cap * sizeof(Mp3Tile)));
+        CU(ctx, cudaMallocHost(&ctx->h_tiles, cap * sizeof(Mp3Tile)));
+        ctx->tiles_cap = cap;
+    }
+    std::memcpy(ctx->h_tiles, all_tiles.data(), all_tiles.size() * sizeof(Mp3Tile));
+    CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, all_tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t i = 0; i < slices.size(); ++i) {
+        const Slice& sl = slices[i];
+        const size_t nf = sl.f1 - sl.f0;
+        CU(ctx, cudaMemcpyAsync(d_units + (size_t)sl.f0 * 4, units + (size_t)sl.f0 * 4, nf * 4 * sizeof(symgpu_mp3_gc),
+                                cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(ctx, cudaMemcpyAsync(d_spec + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS, spectra + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS,
+                                nf * SYMGPU_MP3_FRAME_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+        Mp3Args a{d_units, d_spec, d_pcm, ctx->d_tiles + sl.t0, sl.t1 - sl.t0, ctx->d_mp3_states, ctx->d_mp3_gen,
+                  ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
+        CU(ctx, mp3_launch(a, ctx->stream));
+        ctx->launches += 1;
+        CU(ctx, cudaEventRecord(ctx->ev_k[i], ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
+        CU(ctx, cudaMemcpyAsync(pcm + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS, d_pcm + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS,
+                                nf * SYMGPU_MP3_FRAME_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->copy_out));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SYMGPU_OK;
 }
