@@ -1,0 +1,234 @@
+// C++ host-side mirror of the reference's decoder plug-in interface, on top of the C ABI (symgpu.h).
+//
+// The reference is Rust; its toolchain is not available in this environment (see INTEGRATION.md for
+// the Rust adapter a maintainer would add).  This header restates the SAME interface in C++17 with
+// the same names, argument meaning and error behaviour, so a C++ host can drop the GPU synthesis
+// path in behind a registry exactly as a Rust host would:
+//
+//   AudioDecoder            symphonia-core/src/codecs/audio.rs:251-298   (reset / codec_params / decode /
+//                                                                          finalize / last_decoded)
+//   AudioDecoderOptions     symphonia-core/src/codecs/audio.rs:210-227   (gapless = true, verify = false)
+//   CodecRegistry, Tier     symphonia-core/src/codecs/registry.rs:176-341, symphonia-core/src/common.rs:54-62
+//                           (lookup order preferred -> standard -> fallback)
+//   Error                   symphonia-core/src/errors.rs:43-57
+//   Packet                  symphonia-core/src/packet.rs:146-170 (PacketRef)
+//
+// Until the CPU entropy front-ends exist in C++, a packet handed to the GPU decoders
+// carries the *parsed* frame -- the state the reference has at layer3/mod.rs:421 -- as bytes:
+//   MP3: symgpu_mp3_gc[2][2] (256 B) followed by f32 spectra [2][2][576].
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../symgpu.h"
+
+namespace symgpu_host {
+
+enum class ErrorKind { None, IoError, DecodeError, SeekError, Unsupported, LimitError, ResetRequired };
+struct Error {
+    ErrorKind kind = ErrorKind::None;
+    const char* message = ""; // static storage, like the reference's &'static str
+    explicit operator bool() const { return kind != ErrorKind::None; }
+};
+template <typename T>
+struct Result {
+    T value{};
+    Error error{};
+    bool ok() const { return !error; }
+};
+
+inline Error map_status(symgpu_status st) {
+    switch (st) {
+        case SYMGPU_OK: return {};
+        case SYMGPU_ERR_DECODE: return {ErrorKind::DecodeError, symgpu_strerror(st)};
+        case SYMGPU_ERR_UNSUPPORTED: return {ErrorKind::Unsupported, symgpu_strerror(st)};
+        case SYMGPU_ERR_LIMIT: return {ErrorKind::LimitError, symgpu_strerror(st)};
+        case SYMGPU_ERR_RESET: return {ErrorKind::ResetRequired, symgpu_strerror(st)};
+        default: return {ErrorKind::IoError, symgpu_strerror(st)};
+    }
+}
+
+// Codec ids, symphonia-core/src/codecs/audio.rs:404-418.
+constexpr uint32_t CODEC_ID_VORBIS = 0x1000, CODEC_ID_MP3 = 0x1006, CODEC_ID_AAC = 0x1007;
+
+struct AudioCodecParameters {
+    uint32_t codec = 0;
+    uint32_t sample_rate = 0;
+    uint32_t channels = 0;
+    std::vector<uint8_t> extra_data;
+};
+struct AudioDecoderOptions {
+    bool gapless = true;
+    bool verify = false;
+};
+struct FinalizeResult {
+    bool has_verify = false, verify_ok = false;
+};
+struct Packet { // PacketRef
+    uint32_t track_id = 0;
+    uint64_t pts = 0, dur = 0;
+    uint32_t trim_start = 0, trim_end = 0;
+    const uint8_t* data = nullptr;
+    size_t len = 0;
+};
+// Borrow of the decoder-owned planar f32 buffer, valid until the next call on the decoder
+// (GenericAudioBufferRef over AudioBuffer<f32>, symphonia-core/src/audio/buf.rs:68-73).
+struct AudioBufferRef {
+    const float* planes[2] = {nullptr, nullptr};
+    size_t n_planes = 0;
+    size_t frames = 0;
+};
+
+class AudioDecoder {
+  public:
+    virtual ~AudioDecoder() = default;
+    virtual void reset() = 0;
+    virtual const AudioCodecParameters& codec_params() const = 0;
+    virtual Result<AudioBufferRef> decode(const Packet& packet) = 0;
+    virtual FinalizeResult finalize() { return {}; }
+    virtual AudioBufferRef last_decoded() const = 0;
+};
+
+enum class Tier { Preferred, Standard, Fallback };
+using AudioDecoderFactory =
+    std::function<Result<std::unique_ptr<AudioDecoder>>(const AudioCodecParameters&, const AudioDecoderOptions&)>;
+
+class CodecRegistry {
+  public:
+    void register_audio_decoder_at_tier(Tier tier, uint32_t codec, AudioDecoderFactory factory) {
+        slots_[codec][(int)tier] = std::move(factory);
+    }
+    // registry.rs:330-341: preferred, then standard, then fallback.
+    Result<std::unique_ptr<AudioDecoder>> make_audio_decoder(const AudioCodecParameters& p, const AudioDecoderOptions& o) const {
+        auto it = slots_.find(p.codec);
+        if (it != slots_.end())
+            for (int t = 0; t < 3; ++t)
+                if (it->second[t]) return it->second[t](p, o);
+        return {nullptr, {ErrorKind::Unsupported, "core (codec): unsupported codec"}};
+    }
+
+  private:
+    std::map<uint32_t, AudioDecoderFactory[3]> slots_;
+};
+
+// A context shared by the GPU decoders of one thread (one CUDA stream, codecs/audio.rs "Send + Sync":
+// one call at a time per context).  Stream-state slots are handed out from a free list.
+class GpuContext {
+  public:
+    static Result<std::shared_ptr<GpuContext>> create(int device, uint32_t max_streams) {
+        symgpu_ctx* c = nullptr;
+        symgpu_status st = symgpu_ctx_create(device, &c);
+        if (st != SYMGPU_OK) return {nullptr, map_status(st)};
+        std::shared_ptr<GpuContext> g(new GpuContext(c, max_streams));
+        st = symgpu_mp3_streams_alloc(c, max_streams);
+        if (st != SYMGPU_OK) return {nullptr, map_status(st)};
+        return {g, {}};
+    }
+    ~GpuContext() { symgpu_ctx_destroy(ctx_); }
+    symgpu_ctx* raw() const { return ctx_; }
+    int acquire_stream() {
+        if (free_.empty()) return -1;
+        const int s = free_.back();
+        free_.pop_back();
+        return s;
+    }
+    void release_stream(int s) { free_.push_back(s); }
+
+  private:
+    GpuContext(symgpu_ctx* c, uint32_t n) : ctx_(c) {
+        for (int i = (int)n - 1; i >= 0; --i) free_.push_back(i);
+    }
+    symgpu_ctx* ctx_;
+    std::vector<int> free_;
+};
+
+// MPEG Layer III decoder whose synthesis stage runs on the GPU (mirrors MpaDecoder,
+// symphonia-bundle-mp3/src/decoder.rs:138-197).  See the packet format note at the top of this file.
+class GpuMpaDecoder final : public AudioDecoder {
+  public:
+    static constexpr size_t kPacketBytes = 4 * sizeof(symgpu_mp3_gc) + SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
+
+    static Result<std::unique_ptr<AudioDecoder>> try_new(std::shared_ptr<GpuContext> gpu, const AudioCodecParameters& p,
+                                                         const AudioDecoderOptions& o) {
+        if (p.codec != CODEC_ID_MP3) return {nullptr, {ErrorKind::Unsupported, "mpa: invalid codec type"}};
+        const int slot = gpu->acquire_stream();
+        if (slot < 0) return {nullptr, {ErrorKind::LimitError, "symgpu: no free stream slot"}};
+        return {std::unique_ptr<AudioDecoder>(new GpuMpaDecoder(std::move(gpu), p, o, (uint32_t)slot)), {}};
+    }
+    ~GpuMpaDecoder() override {
+        symgpu_mp3_stream_reset(gpu_->raw(), stream_);
+        gpu_->release_stream((int)stream_);
+    }
+    void reset() override { // decoder.rs:152-155
+        symgpu_mp3_stream_reset(gpu_->raw(), stream_);
+        frames_ = 0;
+    }
+    const AudioCodecParameters& codec_params() const override { return params_; }
+    Result<AudioBufferRef> decode(const Packet& packet) override {
+        frames_ = 0; // buf.clear(): on any error the buffer stays empty (codecs/audio.rs:278)
+        if (packet.len != kPacketBytes) return {{}, {ErrorKind::DecodeError, "mpa: invalid packet length"}};
+        symgpu_mp3_gc units[4];
+        std::memcpy(units, packet.data, sizeof units);
+        const float* spectra = reinterpret_cast<const float*>(packet.data + sizeof units);
+        const bool mpeg1 = units[0].flags & SYMGPU_MP3_F_MPEG1;
+        const bool mono = units[1].flags & SYMGPU_MP3_F_MUTE;
+        const bool joint = units[0].flags & (SYMGPU_MP3_F_MID_SIDE | SYMGPU_MP3_F_INTENSITY);
+        // stereo.rs:503-505: a parse-level validity check that stays on the host side of the ABI
+        for (int gr = 0; gr < (mpeg1 ? 2 : 1) && joint && !mono; ++gr)
+            if (units[2 * gr].block_type != units[2 * gr + 1].block_type ||
+                ((units[2 * gr].flags ^ units[2 * gr + 1].flags) & SYMGPU_MP3_F_MIXED))
+                return {{}, {ErrorKind::DecodeError, "mpa: stereo channel pair block_type mismatch"}};
+        symgpu_mp3_run run{};
+        run.stream = stream_;
+        run.first_frame = 0;
+        run.n_frames = 1;
+        run.granules_per_frame = mpeg1 ? 2 : 1;
+        run.channels = mono ? 1 : 2;
+        const symgpu_status st = symgpu_mp3_synth_host(gpu_->raw(), units, spectra, &run, 1, 1, pcm_.data());
+        if (st != SYMGPU_OK) return {{}, map_status(st)};
+        frames_ = mpeg1 ? 1152 : 576;
+        // gapless trimming (decoder.rs:130-132)
+        size_t begin = 0, end = frames_;
+        if (opts_.gapless) {
+            begin = std::min<size_t>(packet.trim_start, frames_);
+            end = frames_ - std::min<size_t>(packet.trim_end, frames_ - begin);
+        }
+        first_ = begin;
+        frames_ = end - begin;
+        return {last_decoded(), {}};
+    }
+    AudioBufferRef last_decoded() const override {
+        AudioBufferRef r;
+        r.n_planes = params_.channels ? params_.channels : 2;
+        r.frames = frames_;
+        r.planes[0] = pcm_.data() + first_;
+        r.planes[1] = pcm_.data() + 1152 + first_;
+        return r;
+    }
+
+  private:
+    GpuMpaDecoder(std::shared_ptr<GpuContext> gpu, AudioCodecParameters p, AudioDecoderOptions o, uint32_t stream)
+        : gpu_(std::move(gpu)), params_(std::move(p)), opts_(o), stream_(stream), pcm_(SYMGPU_MP3_FRAME_FLOATS, 0.0f) {}
+    std::shared_ptr<GpuContext> gpu_;
+    AudioCodecParameters params_;
+    AudioDecoderOptions opts_;
+    uint32_t stream_;
+    std::vector<float> pcm_;
+    size_t frames_ = 0, first_ = 0;
+};
+
+// What an application does next to symphonia::default::register_enabled_codecs (symphonia/src/lib.rs:234-255).
+inline void register_gpu_decoders(CodecRegistry& registry, std::shared_ptr<GpuContext> gpu) {
+    registry.register_audio_decoder_at_tier(Tier::Preferred, CODEC_ID_MP3,
+                                            [gpu](const AudioCodecParameters& p, const AudioDecoderOptions& o) {
+                                                return GpuMpaDecoder::try_new(gpu, p, o);
+                                            });
+}
+
+} // namespace symgpu_host

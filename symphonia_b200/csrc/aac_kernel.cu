@@ -81,16 +81,50 @@ __global__ void __launch_bounds__(256) aac_tns_kernel(const symgpu_aac_unit* __r
 }
 
 // ---- filterbank --------------------------------------------------------------------------------
-struct AacSmem {
-    float spec[1024];
-    float out[2048];
-    float delay[1024];
+// One CTA = one chunk of <= K consecutive frames of one channel, plus one slot for the frame before
+// the chunk (its delay line).  Each frame has its own group of 64 threads and its own named barrier,
+// so the K+1 IMDCTs proceed independently; the window / overlap step then reads the IMDCT output of
+// frame f and of frame f-1 (the `delay` of the reference is a pure function of frame f-1's output).
+constexpr int kAacK = kAacChunkFrames;
+struct alignas(16) AacFrameSmem {
+    float out[2048];          // spectrum (first 1024 floats) until the pre-twiddle has consumed it, then pcm_long
     float2 z[zpad_len(512)];
 };
 
-__global__ void __launch_bounds__(kAacThreads) aac_synth_kernel(AacArgs a) {
-    __shared__ AacSmem sm;
+// delay[i] after a frame with IMDCT output `out` (aac/dsp.rs:131-157) -- what the NEXT frame overlaps with.
+__device__ __forceinline__ float aac_new_delay(int seq, const float* out, const float* __restrict__ lw,
+                                               const float* __restrict__ sw, const float* __restrict__ psw, int i);
+
+// pcm_short[x] of aac/dsp.rs:86-101, rebuilt per sample with the reference's operation order: the
+// second half of window w-1 is written first (assignment for w-1 = 0, "0.0 +=" otherwise), then the
+// first half of window w is added.
+__device__ __forceinline__ float aac_pcm_short(const float* out, const float* __restrict__ sw,
+                                               const float* __restrict__ psw, int x) {
+    const int w = x >> 7, i = x & 127;
+    if (w == 0) return out[i] * __ldg(psw + i);
+    const float t2 = out[256 * (w - 1) + 128 + i] * __ldg(sw + 127 - i);
+    const float prev = (w == 1) ? t2 : 0.0f + t2;
+    if (w == 8) return prev;
+    return prev + out[256 * w + i] * __ldg(sw + i);
+}
+
+__device__ __forceinline__ float aac_new_delay(int seq, const float* out, const float* __restrict__ lw,
+                                               const float* __restrict__ sw, const float* __restrict__ psw, int i) {
+    switch (seq) {
+        case SYMGPU_AAC_ONLY_LONG:
+        case SYMGPU_AAC_LONG_STOP: return out[i + 1024] * __ldg(lw + 1023 - i);
+        case SYMGPU_AAC_EIGHT_SHORT: return i < P1 ? aac_pcm_short(out, sw, psw, i + 512 + 64) : 0.0f;
+        default: // LONG_START
+            return i < P0 ? out[i + 1024] : i < P1 ? out[i + 1024] * __ldg(sw + 127 - (i - P0)) : 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs a) {
+    extern __shared__ __align__(16) unsigned char aac_raw[];
+    AacFrameSmem* fs = reinterpret_cast<AacFrameSmem*>(aac_raw);
+    __shared__ bool is_last;
     const int tid = threadIdx.x;
+    const int grp = tid >> 6, gt = tid & 63; // frame slot of this thread, thread within the slot's group
     const CodecChunk ck = a.chunks[blockIdx.x];
     const int ch = ck.channel;
     const CodecTables* __restrict__ tab = a.tab;
@@ -99,78 +133,65 @@ __global__ void __launch_bounds__(kAacThreads) aac_synth_kernel(AacArgs a) {
     const float* st_in = a.states + (((size_t)ck.stream * 2 + (gen & 1)) * 2 + ch) * 1024;
     float* st_out = a.states + (((size_t)ck.stream * 2 + ((gen + 1) & 1)) * 2 + ch) * 1024;
     const bool load_state = ck.flags & kChunkLoadState;
+    const int count = ck.count;
 
-    if (load_state)
-        for (int i = tid; i < 1024; i += kAacThreads) sm.delay[i] = st_in[i];
+    // slot 0 = the frame before the chunk (or the stream state), slot k = chunk frame k-1
+    const int f = (int)ck.first - 1 + grp;
+    const bool have_frame = grp <= count && (grp > 0 || !load_state);
+    symgpu_aac_unit u = {};
+    if (have_frame) {
+        const size_t unit_idx = 2 * (size_t)f + ch;
+        u = a.units[unit_idx];
+        AacFrameSmem& me = fs[grp];
+        const float* src = (u.n_tns ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
+        for (int i = gt; i < 256; i += 64) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        NamedSync sync{1 + grp, 64};
+        sync();
+        // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
+        if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
+            imdct_blocks<9>(me.out, me.out, me.z, 1, reinterpret_cast<const float2*>(tab->aac_tw_long), ft, gt, 64, sync);
+        else
+            imdct_blocks<6>(me.out, me.out, me.z, 8, reinterpret_cast<const float2*>(tab->aac_tw_short), ft, gt, 64, sync);
+    } else if (grp == 0) {
+        // run start: slot 0 holds the delay line itself (stored in out[1024..2048))
+        for (int i = gt; i < 1024; i += 64) fs[0].out[1024 + i] = st_in[i];
+    }
     __syncthreads();
 
-    const int f_begin = (int)ck.first - (load_state ? 0 : 1);
-    const int f_end = (int)ck.first + ck.count;
-    for (int f = f_begin; f < f_end; ++f) {
-        const bool emit = f >= (int)ck.first;
-        const size_t unit_idx = 2 * (size_t)f + ch;
-        const symgpu_aac_unit u = a.units[unit_idx];
-        const float* src = (u.n_tns ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
-        for (int i = tid; i < 256; i += kAacThreads)
-            reinterpret_cast<float4*>(sm.spec)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        __syncthreads();
-        const int seq = u.window_sequence;
-        if (seq != SYMGPU_AAC_EIGHT_SHORT)
-            imdct_blocks<9>(sm.spec, sm.out, sm.z, 1, reinterpret_cast<const float2*>(tab->aac_tw_long), ft, tid, kAacThreads);
-        else
-            imdct_blocks<6>(sm.spec, sm.out, sm.z, 8, reinterpret_cast<const float2*>(tab->aac_tw_short), ft, tid, kAacThreads);
-
-        const float* lw = u.window_shape ? tab->aac_kbd_long : tab->aac_sine_long;
+    // window + overlap-add (aac/dsp.rs:103-129): thread = (frame slot, sample)
+    if (grp >= 1 && grp <= count) {
+        const float* out = fs[grp].out;
+        const float* pout = fs[grp - 1].out;
+        const symgpu_aac_unit pu = (grp > 1 || !load_state) ? a.units[2 * (size_t)(f - 1) + ch] : symgpu_aac_unit{};
+        const bool prev_is_state = grp == 1 && load_state;
+        const int seq = u.window_sequence, pseq = pu.window_sequence;
         const float* sw = u.window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
         const float* plw = u.prev_window_shape ? tab->aac_kbd_long : tab->aac_sine_long;
         const float* psw = u.prev_window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
-        float* dst = a.pcm + unit_idx * 1024;
-
-        // pcm_short[x] of aac/dsp.rs:86-101, rebuilt per sample with the reference's operation order:
-        // the second half of window w-1 is written first (assignment for w-1 = 0, "0.0 +=" otherwise),
-        // then the first half of window w is added.
-        auto pcm_short = [&](int x) -> float {
-            const int w = x >> 7, i = x & 127;
-            if (w == 0) return sm.out[i] * __ldg(psw + i);
-            const float t2 = sm.out[256 * (w - 1) + 128 + i] * __ldg(sw + 127 - i);
-            const float prev = (w == 1) ? t2 : 0.0f + t2;
-            if (w == 8) return prev;
-            return prev + sm.out[256 * w + i] * __ldg(sw + i);
-        };
-
+        // windows of the PREVIOUS frame, for its delay line
+        const float* q_lw = pu.window_shape ? tab->aac_kbd_long : tab->aac_sine_long;
+        const float* q_sw = pu.window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
+        const float* q_psw = pu.prev_window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
+        float* dst = a.pcm + (2 * (size_t)f + ch) * 1024;
 #pragma unroll 4
-        for (int i = tid; i < 1024; i += kAacThreads) {
-            const float d = sm.delay[i];
-            float y, nd;
+        for (int i = gt; i < 1024; i += 64) {
+            const float d = prev_is_state ? pout[1024 + i] : aac_new_delay(pseq, pout, q_lw, q_sw, q_psw, i);
+            float y;
             switch (seq) {
                 case SYMGPU_AAC_ONLY_LONG:
-                    y = d + (sm.out[i] * __ldg(plw + i));
-                    nd = sm.out[i + 1024] * __ldg(lw + 1023 - i);
-                    break;
-                case SYMGPU_AAC_LONG_START:
-                    y = d + (sm.out[i] * __ldg(plw + i));
-                    nd = i < P0 ? sm.out[i + 1024] : i < P1 ? sm.out[i + 1024] * __ldg(sw + 127 - (i - P0)) : 0.0f;
-                    break;
-                case SYMGPU_AAC_EIGHT_SHORT:
-                    y = i < P0 ? d : d + pcm_short(i - P0);
-                    nd = i < P1 ? pcm_short(i + 512 + 64) : 0.0f;
-                    break;
-                default: // LONG_STOP
-                    y = i < P0 ? d : i < P1 ? d + sm.out[i] * __ldg(psw + i - P0) : d + sm.out[i];
-                    nd = sm.out[i + 1024] * __ldg(lw + 1023 - i);
-                    break;
+                case SYMGPU_AAC_LONG_START: y = d + (out[i] * __ldg(plw + i)); break;
+                case SYMGPU_AAC_EIGHT_SHORT: y = i < P0 ? d : d + aac_pcm_short(out, sw, psw, i - P0); break;
+                default: y = i < P0 ? d : i < P1 ? d + out[i] * __ldg(psw + i - P0) : d + out[i]; break; // LONG_STOP
             }
-            if (emit) dst[i] = y;
-            sm.delay[i] = nd;
+            dst[i] = y;
         }
-        __syncthreads();
+        if (grp == count && (ck.flags & kChunkStoreState)) { // the run's last frame leaves its delay line in the state
+            const float* lw = u.window_shape ? tab->aac_kbd_long : tab->aac_sine_long;
+            for (int i = gt; i < 1024; i += 64) st_out[i] = aac_new_delay(seq, out, lw, sw, psw, i);
+        }
     }
 
-    if (ck.flags & kChunkStoreState)
-        for (int i = tid; i < 1024; i += kAacThreads) st_out[i] = sm.delay[i];
-
     // launch epilogue: the last CTA publishes the new state generation (see mp3_kernel.cu)
-    __shared__ bool is_last;
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -178,7 +199,7 @@ __global__ void __launch_bounds__(kAacThreads) aac_synth_kernel(AacArgs a) {
     }
     __syncthreads();
     if (is_last) {
-        for (unsigned i = tid; i < gridDim.x; i += kAacThreads)
+        for (unsigned i = tid; i < gridDim.x; i += blockDim.x)
             if ((a.chunks[i].flags & kChunkStoreState) && a.chunks[i].channel == 0) a.gen[a.chunks[i].stream] += 1;
         if (tid == 0) *a.done = 0;
     }
@@ -192,7 +213,14 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    aac_synth_kernel<<<n_chunks, kAacThreads, 0, stream>>>(a);
+    constexpr size_t smem = (kAacK + 1) * sizeof(AacFrameSmem);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(aac_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    aac_synth_kernel<<<n_chunks, (kAacK + 1) * 64, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

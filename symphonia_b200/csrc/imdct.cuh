@@ -113,14 +113,25 @@ __device__ __forceinline__ void fft_pass(float2* z, int n_pts, int tid, int n_th
     }
 }
 
+// Barrier policies for the thread group that owns a block: the whole CTA, or a named barrier shared by
+// `N` threads (several groups of one CTA each running their own IMDCT).
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct NamedSync {
+    int id, n;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+};
+
 // Forward FFT of `batch` independent blocks of 2^LOG2 complex points stored consecutively in z
-// (already in bit-reversed order).  The whole CTA takes part (barriers are __syncthreads).
-template <int LOG2>
-__device__ __forceinline__ void fft_levels(float2* z, int batch, int tid, int n_threads, const FftTables* __restrict__ ft) {
+// (already in bit-reversed order).  Every thread of the owning group takes part.
+template <int LOG2, typename Sync>
+__device__ __forceinline__ void fft_levels(float2* z, int batch, int tid, int n_threads, const FftTables* __restrict__ ft,
+                                           Sync sync) {
     const int n_pts = batch << LOG2;
     static_assert(LOG2 >= 4 && LOG2 <= 11, "FFT sizes 16..2048");
     fft_pass<1, 3>(z, n_pts, tid, n_threads, ft);
-    __syncthreads();
+    sync();
     if constexpr (LOG2 == 4) {
         fft_pass<4, 1>(z, n_pts, tid, n_threads, ft);
     } else if constexpr (LOG2 == 5) {
@@ -128,29 +139,29 @@ __device__ __forceinline__ void fft_levels(float2* z, int batch, int tid, int n_
     } else {
         fft_pass<4, 3>(z, n_pts, tid, n_threads, ft);
         if constexpr (LOG2 > 6) {
-            __syncthreads();
+            sync();
             if constexpr (LOG2 == 7) fft_pass<7, 1>(z, n_pts, tid, n_threads, ft);
             else if constexpr (LOG2 == 8) fft_pass<7, 2>(z, n_pts, tid, n_threads, ft);
             else {
                 fft_pass<7, 3>(z, n_pts, tid, n_threads, ft);
                 if constexpr (LOG2 > 9) {
-                    __syncthreads();
+                    sync();
                     if constexpr (LOG2 == 10) fft_pass<10, 1>(z, n_pts, tid, n_threads, ft);
                     else fft_pass<10, 2>(z, n_pts, tid, n_threads, ft);
                 }
             }
         }
     }
-    __syncthreads();
+    sync();
 }
 
 // IMDCT of `batch` blocks: spec [batch][N] (shared) -> out [batch][2N] (shared), N = 2^(LOG2+1)
 // spectral lines per block, FFT size n2 = 2^LOG2.  tw = Imdct.twiddle (n2 complex).  z is scratch of
 // zpad_len(batch * n2) complex.  All `n_threads` threads of the group must call this.
-template <int LOG2>
+template <int LOG2, typename Sync = CtaSync>
 __device__ __forceinline__ void imdct_blocks(const float* spec, float* out, float2* z, int batch,
                                              const float2* __restrict__ tw, const FftTables* __restrict__ ft, int tid,
-                                             int n_threads) {
+                                             int n_threads, Sync sync = Sync()) {
     constexpr int n2 = 1 << LOG2, n = 2 * n2, n4 = n2 / 2;
     // Pre-twiddle (mdct.rs:81-88) fused with the bit-reversal permutation (no_simd.rs:101-107).
     for (int e = tid; e < batch * n2; e += n_threads) {
@@ -164,8 +175,8 @@ __device__ __forceinline__ void imdct_blocks(const float* spec, float* out, floa
         const int r = (int)(__brev((unsigned)i) >> (32 - LOG2));
         z[zpad((b << LOG2) + r)] = make_float2(re, im);
     }
-    __syncthreads();
-    fft_levels<LOG2>(z, batch, tid, n_threads, ft);
+    sync();
+    fft_levels<LOG2>(z, batch, tid, n_threads, ft, sync);
     // Post-twiddle (mdct.rs:100-137): val = w * conj(x), scattered into the four quarters.
     for (int e = tid; e < batch * n2; e += n_threads) {
         const int b = e >> LOG2, k = e & (n2 - 1);
@@ -188,7 +199,7 @@ __device__ __forceinline__ void imdct_blocks(const float* spec, float* out, floa
             o[3 * n2 + ri] = val.y;
         }
     }
-    __syncthreads();
+    sync();
 }
 
 } // namespace symgpu

@@ -1,0 +1,115 @@
+// Host-side plug-in interface exercised from C++ (include/symgpu/decoder.hpp).
+//   decoder_host registry            CPU tier: tier ordering / Unsupported / no-GPU error behaviour
+//   decoder_host decode IN OUT       GPU tier: decode a stream of parsed MP3 packets one decode() call at a
+//                                    time (BASELINE config 0 "plumbing") and write planar PCM
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <vector>
+
+#include "../../include/symgpu/decoder.hpp"
+
+using namespace symgpu_host;
+
+struct StubDecoder final : AudioDecoder {
+    AudioCodecParameters p;
+    int tag;
+    StubDecoder(AudioCodecParameters pp, int t) : p(std::move(pp)), tag(t) {}
+    void reset() override {}
+    const AudioCodecParameters& codec_params() const override { return p; }
+    Result<AudioBufferRef> decode(const Packet&) override { return {{}, {ErrorKind::DecodeError, "stub"}}; }
+    AudioBufferRef last_decoded() const override { return {}; }
+};
+
+static int check(bool cond, const char* what) {
+    if (!cond) std::fprintf(stderr, "FAILED: %s\n", what);
+    return cond ? 0 : 1;
+}
+
+static int test_registry() {
+    int bad = 0;
+    CodecRegistry reg;
+    AudioCodecParameters mp3;
+    mp3.codec = CODEC_ID_MP3;
+    AudioCodecParameters aac;
+    aac.codec = CODEC_ID_AAC;
+    bad += check(reg.make_audio_decoder(mp3, {}).error.kind == ErrorKind::Unsupported, "empty registry -> Unsupported");
+    auto stub = [](int tag) {
+        return [tag](const AudioCodecParameters& p, const AudioDecoderOptions&) -> Result<std::unique_ptr<AudioDecoder>> {
+            return {std::unique_ptr<AudioDecoder>(new StubDecoder(p, tag)), {}};
+        };
+    };
+    reg.register_audio_decoder_at_tier(Tier::Fallback, CODEC_ID_MP3, stub(3));
+    reg.register_audio_decoder_at_tier(Tier::Standard, CODEC_ID_MP3, stub(2));
+    auto d = reg.make_audio_decoder(mp3, {});
+    bad += check(d.ok() && static_cast<StubDecoder*>(d.value.get())->tag == 2, "standard beats fallback");
+    reg.register_audio_decoder_at_tier(Tier::Preferred, CODEC_ID_MP3, stub(1));
+    d = reg.make_audio_decoder(mp3, {});
+    bad += check(d.ok() && static_cast<StubDecoder*>(d.value.get())->tag == 1, "preferred beats standard");
+    bad += check(reg.make_audio_decoder(aac, {}).error.kind == ErrorKind::Unsupported, "unknown codec -> Unsupported");
+    bad += check(map_status(SYMGPU_ERR_DECODE).kind == ErrorKind::DecodeError, "status mapping: decode");
+    bad += check(map_status(SYMGPU_ERR_RESET).kind == ErrorKind::ResetRequired, "status mapping: reset");
+    bad += check(map_status(SYMGPU_ERR_CUDA).kind == ErrorKind::IoError, "status mapping: cuda");
+    // without a GPU the context cannot be created: the error is surfaced, nothing falls back to a CPU path
+    auto gpu = GpuContext::create(0, 4);
+    if (!gpu.ok()) {
+        bad += check(gpu.error.kind == ErrorKind::IoError || gpu.error.kind == ErrorKind::Unsupported, "no GPU -> error");
+        std::printf("no usable GPU: %s\n", gpu.error.message);
+    } else {
+        CodecRegistry r2;
+        register_gpu_decoders(r2, gpu.value);
+        auto g = r2.make_audio_decoder(mp3, {});
+        bad += check(g.ok(), "GPU decoder registered at Tier::Preferred");
+        uint8_t junk[16] = {0};
+        Packet p;
+        p.data = junk;
+        p.len = sizeof junk;
+        auto res = g.value->decode(p);
+        bad += check(res.error.kind == ErrorKind::DecodeError && g.value->last_decoded().frames == 0,
+                     "malformed packet -> DecodeError and an empty buffer");
+    }
+    std::printf(bad ? "registry: FAILED\n" : "registry: ok\n");
+    return bad;
+}
+
+static int run_decode(const char* in_path, const char* out_path) {
+    std::ifstream in(in_path, std::ios::binary);
+    std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    const size_t n = bytes.size() / GpuMpaDecoder::kPacketBytes;
+    auto gpu = GpuContext::create(0, 2);
+    if (!gpu.ok()) {
+        std::fprintf(stderr, "%s\n", gpu.error.message);
+        return 2;
+    }
+    CodecRegistry reg;
+    register_gpu_decoders(reg, gpu.value);
+    AudioCodecParameters params;
+    params.codec = CODEC_ID_MP3;
+    params.channels = 2;
+    AudioDecoderOptions opts;
+    opts.gapless = false;
+    auto dec = reg.make_audio_decoder(params, opts);
+    if (!dec.ok()) return 3;
+    std::ofstream out(out_path, std::ios::binary);
+    for (size_t i = 0; i < n; ++i) {
+        Packet p;
+        p.data = bytes.data() + i * GpuMpaDecoder::kPacketBytes;
+        p.len = GpuMpaDecoder::kPacketBytes;
+        auto res = dec.value->decode(p);
+        if (!res.ok()) {
+            std::fprintf(stderr, "decode failed at packet %zu: %s\n", i, res.error.message);
+            return 4;
+        }
+        for (size_t ch = 0; ch < 2; ++ch)
+            out.write(reinterpret_cast<const char*>(res.value.planes[ch]), (std::streamsize)(res.value.frames * sizeof(float)));
+    }
+    std::printf("decoded %zu packets\n", n);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "registry") return test_registry();
+    if (argc >= 4 && std::string(argv[1]) == "decode") return run_decode(argv[2], argv[3]);
+    std::fprintf(stderr, "usage: decoder_host registry | decode IN OUT\n");
+    return 64;
+}

@@ -1,0 +1,44 @@
+"""The C++ host-side mirror of the reference's decoder plug-in interface (include/symgpu/decoder.hpp):
+CPU tier checks registry tiers / error mapping / loud failure without a GPU; the GPU tier decodes a
+stream packet by packet through AudioDecoder::decode (BASELINE config 0, "plumbing") and compares
+with the oracle bit for bit."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "decoder_host")
+
+
+def _build():
+    src = os.path.join(ROOT, "tests", "cpp", "decoder_host.cpp")
+    lib = os.path.join(ROOT, "symphonia_b200", "libsymgpu.so")
+    hdr = os.path.join(ROOT, "include", "symgpu", "decoder.hpp")
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(lib), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", EXE, src, "-L" + os.path.dirname(lib), "-lsymgpu",
+                               "-Wl,-rpath," + os.path.dirname(lib)])
+    return EXE
+
+
+def test_registry_and_errors_cpu():
+    out = subprocess.run([_build(), "registry"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "registry: ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_packet_by_packet_decode_matches_oracle(tmp_path, oracle):
+    from symphonia_b200 import workloads
+    from tests import _oracle
+    F = 24
+    units, spectra, runs = workloads.mp3_batch(1, F, seed=321)
+    rc, want, _ = _oracle.mp3_batch(oracle, units, spectra, runs, 1)
+    blob = b"".join(units[f].tobytes() + spectra[f].tobytes() for f in range(F))
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    inp.write_bytes(blob)
+    res = subprocess.run([_build(), "decode", str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    got = np.frombuffer(outp.read_bytes(), dtype=np.float32).reshape(F, 2, 1152)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
