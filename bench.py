@@ -30,6 +30,10 @@ N_STREAMS = 64
 FRAMES_PER_STREAM = 128
 N_FRAMES = N_STREAMS * FRAMES_PER_STREAM
 N_BUFFER_SETS = 4  # rotating input/output sets: 4 x 151 MB = 604 MB > 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum of one mp3_synth_kernel launch on this workload, from the
+# `ncu --set full` capture summarised in profiles/r01_mp3_ncu_summary.csv (78.3 MB + 30.4 MB; below the
+# algorithmic 153 MB because part of the PCM is still in the 126 MB L2 when the launch ends).
+NCU_DRAM_TRAFFIC_BYTES = 108_699_136
 WORKLOAD = "MP3 MPEG-1 Layer III 44.1kHz stereo, batch=8192 frames (64 streams x 128 frames), synthetic spectra"
 
 
@@ -245,10 +249,11 @@ def run_ours(args):
                        "l2": f"rotating {N_BUFFER_SETS} input/output buffer sets ({N_BUFFER_SETS * 151} MB) > 126 MB L2",
                        "fma": "disabled (bit-exact parity with the reference)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": NCU_DRAM_TRAFFIC_BYTES, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": avg_kernel_ms,
-                         "note": "FMA is off for parity, so the kernel is FP32-issue bound: the no-FMA floor for this "
-                                 "batch is ~29 us (4.1e9 lane-ops at 36e12/s measured) vs 23 us at the HBM peak"},
+                         "note": "FMA is off for parity, so the kernel is FP32-issue bound, not HBM bound: the no-FMA floor "
+                                 "for this batch is ~31 us (4.1e9 f32 lane-ops at the measured 35.9e12/s) vs 23 us at the "
+                                 "HBM peak; traffic is from the ncu capture in profiles/"},
             "e2e": {"value": world * audio_per_step * e2e_steps / e2e_s, "unit": "audio-s/s",
                     "h2d_bytes_per_step": N_FRAMES * (256 + 9216), "d2h_bytes_per_step": N_FRAMES * 9216,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "checksum": checksum},
