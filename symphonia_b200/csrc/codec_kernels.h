@@ -23,7 +23,7 @@ struct CodecChunk {
 static_assert(sizeof(CodecChunk) == 16, "CodecChunk is 16 bytes");
 
 constexpr int kAacChunkFrames = 7;
-constexpr int kVorbisChunkPackets = 8;
+
 constexpr int kVorbisStateFloats = 2 * 4096; // overlap of both channels, blocksize_1 <= 8192
 
 struct AacArgs {
@@ -58,5 +58,7 @@ struct VorbisArgs {
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, cudaStream_t stream);
 cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream);
+// Packet slots per CTA (chunk packets + 1) for a batch whose largest blocksize_1 is 2^max_bs1_exp.
+int vorbis_slots_for(int max_bs1_exp);
 
 } // namespace symgpu

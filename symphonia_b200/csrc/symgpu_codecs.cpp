@@ -234,6 +234,10 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
     std::vector<CodecChunk> chunks;
     uint64_t covered = 0;
     int max_bs1 = 6;
+    for (uint32_t r = 0; r < n_runs; ++r)
+        if (runs[r].n_packets && runs[r].stream < ctx->n_vorbis_streams)
+            max_bs1 = std::max(max_bs1, (int)ctx->h_vorbis_streams[runs[r].stream].bs1_exp);
+    const uint32_t per_chunk = (uint32_t)vorbis_slots_for(max_bs1) - 1; // one slot is the packet before the chunk
     for (uint32_t r = 0; r < n_runs; ++r) {
         const symgpu_vorbis_run& run = runs[r];
         if (run.n_packets == 0) continue;
@@ -243,7 +247,7 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
         if ((1u << (cfg.bs1_exp - 1)) > slot) return SYMGPU_ERR_ARG; // slot too small for this stream
         max_bs1 = std::max(max_bs1, (int)cfg.bs1_exp);
         covered += run.n_packets;
-        split_even(run.n_packets, kVorbisChunkPackets, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
+        split_even(run.n_packets, per_chunk, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
             CodecChunk c{};
             c.first = run.first_packet + lo;
             c.stream = run.stream;

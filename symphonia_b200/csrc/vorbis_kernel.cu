@@ -2,10 +2,14 @@
 //   floor-1 curve (floor.rs:568-653, :776-825)  ->  inverse coupling (lib.rs:252-278)
 //   -> floor * residue (lib.rs:282-292) -> IMDCT -> power-sine window + overlap-add (dsp.rs:68-145)
 //
-// One 64-thread CTA walks a chunk of consecutive packets of one stream (both channels, because the
-// coupling step mixes them) with the overlap line in shared memory.  A chunk that does not start its
-// run first recomputes the previous packet's IMDCT tail (one halo packet, output suppressed): the
-// overlap is overwritten by every packet, never accumulated (dsp.rs:125).
+// The overlap line is overwritten by every packet, never accumulated (dsp.rs:125): what a packet
+// overlaps with is the second half of the PREVIOUS packet's IMDCT output.  So a CTA takes a chunk of
+// consecutive packets of one stream plus the packet before it, gives every packet its own group of
+// 64 threads with its own named barrier (both channels in the group, because the coupling step
+// mixes them), runs all the IMDCTs independently, and after one CTA barrier windows / overlap-adds
+// every packet against its predecessor's tail.  A run's first chunk takes the tail from the
+// (double-buffered) stream state instead.  The number of packet slots adapts to the block size
+// (8 slots of 22 KB at blocksize_1 = 2048).
 //
 // Floor step 1 is an integer recurrence over <= 65 posts (one lane per channel); step 2 is evaluated
 // per spectral line in closed form: after d steps of render_line's error accumulator,
@@ -111,35 +115,43 @@ __device__ __forceinline__ float floor1_at(const FloorPoints& p, int x, const fl
 }
 
 template <int LOG2>
-__device__ __forceinline__ void imdct_one(const float* spec, float* out, float2* z, const CodecTables* tab, int tid) {
+__device__ __forceinline__ void imdct_one(const float* spec, float* out, float2* z, const CodecTables* tab, int gt, NamedSync sync) {
     const FftTables* ft = reinterpret_cast<const FftTables*>(tab->fft_lit16);
     const float2* tw = reinterpret_cast<const float2*>(tab->vorbis_tw) + ((1 << LOG2) - 16);
-    imdct_blocks<LOG2>(spec, out, z, 1, tw, ft, tid, kVorbisThreads);
+    imdct_blocks<LOG2>(spec, out, z, 1, tw, ft, gt, kVorbisThreads, sync);
 }
 
-__device__ void imdct_dispatch(int log2_n2, const float* spec, float* out, float2* z, const CodecTables* tab, int tid) {
+__device__ void imdct_dispatch(int log2_n2, const float* spec, float* out, float2* z, const CodecTables* tab, int gt,
+                               NamedSync sync) {
     switch (log2_n2) { // FFT size = blocksize / 4
-        case 4: imdct_one<4>(spec, out, z, tab, tid); break;
-        case 5: imdct_one<5>(spec, out, z, tab, tid); break;
-        case 6: imdct_one<6>(spec, out, z, tab, tid); break;
-        case 7: imdct_one<7>(spec, out, z, tab, tid); break;
-        case 8: imdct_one<8>(spec, out, z, tab, tid); break;
-        case 9: imdct_one<9>(spec, out, z, tab, tid); break;
-        case 10: imdct_one<10>(spec, out, z, tab, tid); break;
-        default: imdct_one<11>(spec, out, z, tab, tid); break;
+        case 4: imdct_one<4>(spec, out, z, tab, gt, sync); break;
+        case 5: imdct_one<5>(spec, out, z, tab, gt, sync); break;
+        case 6: imdct_one<6>(spec, out, z, tab, gt, sync); break;
+        case 7: imdct_one<7>(spec, out, z, tab, gt, sync); break;
+        case 8: imdct_one<8>(spec, out, z, tab, gt, sync); break;
+        case 9: imdct_one<9>(spec, out, z, tab, gt, sync); break;
+        case 10: imdct_one<10>(spec, out, z, tab, gt, sync); break;
+        default: imdct_one<11>(spec, out, z, tab, gt, sync); break;
     }
 }
 
-__global__ void __launch_bounds__(kVorbisThreads) vorbis_synth_kernel(VorbisArgs a, int slot_smem) {
+// Shared-memory bytes of one packet slot for blocksize_1 / 2 = slot_smem floats per channel:
+// out[2][2*slot_smem] (the spectrum of a channel lives in the first half of its `out` until the
+// pre-twiddle has consumed it) | z | floor points of both channels.
+__host__ __device__ inline size_t vorbis_slot_bytes(int slot_smem) {
+    size_t b = sizeof(float) * 4 * (size_t)slot_smem + sizeof(float2) * zpad_len(slot_smem / 2) + 2 * sizeof(FloorPoints);
+    return (b + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slot_smem) {
     extern __shared__ __align__(16) unsigned char raw[];
-    // layout: spec[2][slot_smem] | out[2*slot_smem] | overlap[2][slot_smem] | z | points[2]
-    float* spec = reinterpret_cast<float*>(raw);
-    float* out = spec + 2 * slot_smem;
-    float* overlap = out + 2 * slot_smem;
-    float2* z = reinterpret_cast<float2*>(overlap + 2 * slot_smem);
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, grp = tid >> 6, gt = tid & 63, warp_in_grp = gt >> 5, lane = tid & 31;
+    const size_t slot_bytes = vorbis_slot_bytes(slot_smem);
+    auto slot_out = [&](int k, int ch) { return reinterpret_cast<float*>(raw + k * slot_bytes) + (size_t)ch * 2 * slot_smem; };
+    float2* z = reinterpret_cast<float2*>(reinterpret_cast<float*>(raw + grp * slot_bytes) + 4 * slot_smem);
     FloorPoints* pts = reinterpret_cast<FloorPoints*>(z + zpad_len(slot_smem / 2));
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const CodecChunk ck = a.chunks[blockIdx.x];
     const symgpu_vorbis_stream cfg = a.streams[ck.stream];
     const CodecTables* __restrict__ tab = a.tab;
@@ -149,39 +161,39 @@ __global__ void __launch_bounds__(kVorbisThreads) vorbis_synth_kernel(VorbisArgs
     const float* st_in = a.states + ((size_t)ck.stream * 2 + (gen & 1)) * kVorbisStateFloats;
     float* st_out = a.states + ((size_t)ck.stream * 2 + ((gen + 1) & 1)) * kVorbisStateFloats;
     const bool load_state = ck.flags & kChunkLoadState;
+    const int count = ck.count;
     const int half1 = bs1 >> 1;
 
-    if (load_state)
-        for (int i = tid; i < 2 * half1; i += kVorbisThreads) overlap[(i / half1) * slot_smem + (i % half1)] = st_in[i];
-    __syncthreads();
-
-    const int p_begin = (int)ck.first - (load_state ? 0 : 1);
-    const int p_end = (int)ck.first + ck.count;
-    for (int p = p_begin; p < p_end; ++p) {
-        const bool emit = p >= (int)ck.first;
-        const symgpu_vorbis_unit u = a.units[p];
-        const bool block_flag = u.block_flag != 0, prev_flag = u.prev_block_flag != 0;
-        const int bs = block_flag ? bs1 : bs0;
+    // slot 0 = the packet before the chunk (or the stream state), slot k = chunk packet k-1
+    const int p = (int)ck.first - 1 + grp;
+    const bool have_packet = grp <= count && (grp > 0 || !load_state);
+    symgpu_vorbis_unit u = {};
+    int bs = bs0;
+    if (have_packet) {
+        u = a.units[p];
+        bs = u.block_flag ? bs1 : bs0;
         const int n2 = bs >> 1;
-
-        // (1) floor curves: warp = channel
-        if (warp < n_ch) {
-            const int ch = warp;
+        NamedSync sync{1 + grp, kVorbisThreads};
+        // (1) floor curves: warp = channel, rendered into the channel's spectrum area
+        if (warp_in_grp < n_ch) {
+            const int ch = warp_in_grp;
+            float* spec = slot_out(grp, ch);
             const bool used = u.floor[ch] != 0xffff && u.floor[ch] < a.n_floors;
             if (used) {
                 if (lane == 0) floor1_points(a.floors[u.floor[ch]], a.floor_y + ((size_t)p * 2 + ch) * 65, n2, pts[ch]);
                 __syncwarp();
-                for (int x = lane; x < n2; x += 32) spec[ch * slot_smem + x] = floor1_at(pts[ch], x, tab->vorbis_inverse_db);
+                for (int x = lane; x < n2; x += 32) spec[x] = floor1_at(pts[ch], x, tab->vorbis_inverse_db);
             } else {
-                for (int x = lane; x < n2; x += 32) spec[ch * slot_smem + x] = 0.0f; // ch.floor[..n2].fill(0.0)
+                for (int x = lane; x < n2; x += 32) spec[x] = 0.0f; // ch.floor[..n2].fill(0.0)
             }
         }
-        __syncthreads();
-
+        sync();
         // (2) inverse coupling + dot product
         const float* r0 = a.residue + ((size_t)p * 2 + 0) * a.slot;
         const float* r1 = a.residue + ((size_t)p * 2 + 1) * a.slot;
-        for (int i = tid; i < n2; i += kVorbisThreads) {
+        float* spec0 = slot_out(grp, 0);
+        float* spec1 = slot_out(grp, 1);
+        for (int i = gt; i < n2; i += kVorbisThreads) {
             float m = __ldg(r0 + i);
             float ang = n_ch == 2 ? __ldg(r1 + i) : 0.0f;
             if (cfg.coupled && n_ch == 2) { // lib.rs:267-277: comparisons are "> 0.0"
@@ -194,50 +206,54 @@ __global__ void __launch_bounds__(kVorbisThreads) vorbis_synth_kernel(VorbisArgs
                 m = nm;
                 ang = na;
             }
-            if (!u.do_not_decode[0]) spec[i] = spec[i] * m;
-            if (n_ch == 2 && !u.do_not_decode[1]) spec[slot_smem + i] = spec[slot_smem + i] * ang;
+            if (!u.do_not_decode[0]) spec0[i] = spec0[i] * m;
+            if (n_ch == 2 && !u.do_not_decode[1]) spec1[i] = spec1[i] * ang;
         }
-        __syncthreads();
+        sync();
+        // (3) IMDCT per channel, in place over the channel's area (the spectrum is dead after the pre-twiddle)
+        for (int ch = 0; ch < n_ch; ++ch) imdct_dispatch(31 - __clz(bs >> 2), slot_out(grp, ch), slot_out(grp, ch), z, tab, gt, sync);
+    } else if (grp == 0) {
+        // run start: slot 0 holds the overlap line itself, as the tail of a maximum-size block
+        for (int i = gt; i < 2 * half1; i += kVorbisThreads) slot_out(0, i / half1)[half1 + (i % half1)] = st_in[i];
+    }
+    __syncthreads();
 
-        // (3) per channel: IMDCT, window + overlap-add, save the tail (dsp.rs:68-126)
+    // (4) window + overlap-add against the previous packet's tail (dsp.rs:83-122)
+    if (grp >= 1 && grp <= count) {
+        const bool block_flag = u.block_flag != 0, prev_flag = u.prev_block_flag != 0;
+        const bool prev_is_state = grp == 1 && load_state;
+        const int pbs = prev_is_state ? bs1 : (a.units[p - 1].block_flag ? bs1 : bs0); // geometry of slot grp-1's tail
         const int out_len = ((prev_flag ? bs1 : bs0) + bs) >> 2;
+        const float* win = tab->vorbis_win + (((block_flag && prev_flag) ? bs1 : bs0) / 2 - 32);
         for (int ch = 0; ch < n_ch; ++ch) {
-            imdct_dispatch(31 - __clz(bs >> 2), spec + ch * slot_smem, out, z, tab, tid);
-            float* ov = overlap + ch * slot_smem;
+            const float* out = slot_out(grp, ch);
+            const float* ov = slot_out(grp - 1, ch) + pbs / 2; // overlap[..] = imdct[bs/2..bs] of the previous packet
             float* dst = a.pcm + ((size_t)p * 2 + ch) * a.slot;
-            const float* win = tab->vorbis_win + (((block_flag && prev_flag) ? bs1 : bs0) / 2 - 32);
-            if (emit) {
-                if (prev_flag == block_flag) {
-                    const int len = bs / 2;
-                    for (int k = tid; k < len; k += kVorbisThreads)
-                        dst[k] = ov[k] * __ldg(win + len - 1 - k) + out[k] * __ldg(win + k);
-                } else if (prev_flag && !block_flag) {
-                    const int start = (bs1 - bs0) / 4, len = bs0 / 2;
-                    for (int k = tid; k < out_len; k += kVorbisThreads) {
-                        if (k < start) dst[k] = ov[k];
-                        else {
-                            const int j = k - start;
-                            dst[k] = ov[k] * __ldg(win + len - 1 - j) + out[j] * __ldg(win + j);
-                        }
-                    }
-                } else {
-                    const int start = (bs1 - bs0) / 4, len = bs0 / 2, end = start + len;
-                    for (int k = tid; k < out_len; k += kVorbisThreads) {
-                        if (k < len) dst[k] = ov[k] * __ldg(win + len - 1 - k) + out[start + k] * __ldg(win + k);
-                        else dst[k] = out[end + (k - len)];
+            if (prev_flag == block_flag) {
+                const int len = bs / 2;
+                for (int k = gt; k < len; k += kVorbisThreads)
+                    dst[k] = ov[k] * __ldg(win + len - 1 - k) + out[k] * __ldg(win + k);
+            } else if (prev_flag && !block_flag) {
+                const int start = (bs1 - bs0) / 4, len = bs0 / 2;
+                for (int k = gt; k < out_len; k += kVorbisThreads) {
+                    if (k < start) dst[k] = ov[k];
+                    else {
+                        const int j = k - start;
+                        dst[k] = ov[k] * __ldg(win + len - 1 - j) + out[j] * __ldg(win + j);
                     }
                 }
+            } else {
+                const int start = (bs1 - bs0) / 4, len = bs0 / 2, end = start + len;
+                for (int k = gt; k < out_len; k += kVorbisThreads) {
+                    if (k < len) dst[k] = ov[k] * __ldg(win + len - 1 - k) + out[start + k] * __ldg(win + k);
+                    else dst[k] = out[end + (k - len)];
+                }
             }
-            __syncthreads(); // every thread has read the old overlap
-            for (int k = tid; k < bs / 2; k += kVorbisThreads) ov[k] = out[bs / 2 + k];
-            __syncthreads();
+            if (grp == count && (ck.flags & kChunkStoreState)) // the run's last packet leaves its tail in the state
+                for (int k = gt; k < bs / 2; k += kVorbisThreads) st_out[ch * half1 + k] = out[bs / 2 + k];
         }
     }
 
-    if (ck.flags & kChunkStoreState)
-        for (int i = tid; i < 2 * half1; i += kVorbisThreads) st_out[i] = overlap[(i / half1) * slot_smem + (i % half1)];
-
-    __shared__ bool is_last;
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(kVorbisThreads) vorbis_synth_kernel(VorbisArgs
     }
     __syncthreads();
     if (is_last) {
-        for (unsigned i = tid; i < gridDim.x; i += kVorbisThreads)
+        for (unsigned i = tid; i < gridDim.x; i += blockDim.x)
             if (a.chunks[i].flags & kChunkStoreState) a.gen[a.chunks[i].stream] += 1;
         if (tid == 0) *a.done = 0;
     }
@@ -253,16 +269,23 @@ __global__ void __launch_bounds__(kVorbisThreads) vorbis_synth_kernel(VorbisArgs
 
 } // namespace
 
+int vorbis_slots_for(int max_bs1_exp) {
+    const size_t per = vorbis_slot_bytes(1 << (max_bs1_exp - 1));
+    const int n = (int)((200u * 1024u) / per);
+    return n < 2 ? 2 : (n > 8 ? 8 : n);
+}
+
 cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream) {
     const int slot_smem = 1 << (max_bs1_exp - 1);
-    const size_t smem = sizeof(float) * 6 * (size_t)slot_smem + sizeof(float2) * zpad_len(slot_smem / 2) + 2 * sizeof(FloorPoints) + 16;
+    const int n_slots = vorbis_slots_for(max_bs1_exp);
+    const size_t smem = vorbis_slot_bytes(slot_smem) * n_slots;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(vorbis_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    vorbis_synth_kernel<<<n_chunks, kVorbisThreads, smem, stream>>>(a, slot_smem);
+    vorbis_synth_kernel<<<n_chunks, n_slots * kVorbisThreads, smem, stream>>>(a, slot_smem);
     return cudaGetLastError();
 }
 
