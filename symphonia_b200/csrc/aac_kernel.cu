@@ -90,6 +90,14 @@ struct alignas(16) AacFrameSmem {
     float out[2048];          // spectrum (first 1024 floats) until the pre-twiddle has consumed it, then pcm_long
     float2 z[zpad_len(512)];
 };
+// Twiddle tables staged in shared memory once per CTA: the 200 KB of frame slots leave almost no L1,
+// and the FFT passes read twiddles at lane-dependent indices (ncu: long_scoreboard 7.7 per issue with
+// the tables in global memory).
+struct alignas(16) AacTabSmem {
+    float2 fft[8 + 16 + 480]; // FftTables prefix: lit16, lit32, merge tables of sizes 64..512
+    float2 tw_long[512];
+    float2 tw_short[64];
+};
 
 // delay[i] after a frame with IMDCT output `out` (aac/dsp.rs:131-157) -- what the NEXT frame overlaps with.
 __device__ __forceinline__ float aac_new_delay(int seq, const float* out, const float* __restrict__ lw,
@@ -122,13 +130,23 @@ __device__ __forceinline__ float aac_new_delay(int seq, const float* out, const 
 __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs a) {
     extern __shared__ __align__(16) unsigned char aac_raw[];
     AacFrameSmem* fs = reinterpret_cast<AacFrameSmem*>(aac_raw);
+    AacTabSmem& ts = *reinterpret_cast<AacTabSmem*>(aac_raw + (kAacK + 1) * sizeof(AacFrameSmem));
     __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int grp = tid >> 6, gt = tid & 63; // frame slot of this thread, thread within the slot's group
     const CodecChunk ck = a.chunks[blockIdx.x];
     const int ch = ck.channel;
     const CodecTables* __restrict__ tab = a.tab;
-    const FftTables* ft = reinterpret_cast<const FftTables*>(tab->fft_lit16);
+    {
+        const float2* g_fft = reinterpret_cast<const float2*>(tab->fft_lit16);
+        const float2* g_twl = reinterpret_cast<const float2*>(tab->aac_tw_long);
+        const float2* g_tws = reinterpret_cast<const float2*>(tab->aac_tw_short);
+        for (int i = tid; i < 504; i += blockDim.x) ts.fft[i] = __ldg(g_fft + i);
+        for (int i = tid; i < 512; i += blockDim.x) ts.tw_long[i] = __ldg(g_twl + i);
+        if (tid < 64) ts.tw_short[tid] = __ldg(g_tws + tid);
+    }
+    __syncthreads();
+    const FftTables* ft = reinterpret_cast<const FftTables*>(ts.fft);
     const uint32_t gen = a.gen[ck.stream];
     const float* st_in = a.states + (((size_t)ck.stream * 2 + (gen & 1)) * 2 + ch) * 1024;
     float* st_out = a.states + (((size_t)ck.stream * 2 + ((gen + 1) & 1)) * 2 + ch) * 1024;
@@ -149,9 +167,9 @@ __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs 
         sync();
         // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
         if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-            imdct_blocks<9>(me.out, me.out, me.z, 1, reinterpret_cast<const float2*>(tab->aac_tw_long), ft, gt, 64, sync);
+            imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
         else
-            imdct_blocks<6>(me.out, me.out, me.z, 8, reinterpret_cast<const float2*>(tab->aac_tw_short), ft, gt, 64, sync);
+            imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 64, sync);
     } else if (grp == 0) {
         // run start: slot 0 holds the delay line itself (stored in out[1024..2048))
         for (int i = gt; i < 1024; i += 64) fs[0].out[1024 + i] = st_in[i];
@@ -213,7 +231,7 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    constexpr size_t smem = (kAacK + 1) * sizeof(AacFrameSmem);
+    constexpr size_t smem = (kAacK + 1) * sizeof(AacFrameSmem) + sizeof(AacTabSmem);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(aac_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

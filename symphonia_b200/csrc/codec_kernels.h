@@ -22,7 +22,7 @@ struct CodecChunk {
 };
 static_assert(sizeof(CodecChunk) == 16, "CodecChunk is 16 bytes");
 
-constexpr int kAacChunkFrames = 7;
+constexpr int kAacChunkFrames = 6;
 
 constexpr int kVorbisStateFloats = 2 * 4096; // overlap of both channels, blocksize_1 <= 8192
 

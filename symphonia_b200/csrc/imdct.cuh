@@ -169,7 +169,7 @@ __device__ __forceinline__ void imdct_blocks(const float* spec, float* out, floa
         const float* s = spec + b * n;
         const float even = s[2 * i];
         const float odd = -s[n - 1 - 2 * i];
-        const float2 w = __ldg(tw + i);
+        const float2 w = tw[i];
         const float re = odd * w.y - even * w.x;
         const float im = odd * w.x + even * w.y;
         const int r = (int)(__brev((unsigned)i) >> (32 - LOG2));
@@ -181,7 +181,7 @@ __device__ __forceinline__ void imdct_blocks(const float* spec, float* out, floa
     for (int e = tid; e < batch * n2; e += n_threads) {
         const int b = e >> LOG2, k = e & (n2 - 1);
         const float2 x = z[zpad(e)];
-        const float2 w = __ldg(tw + k);
+        const float2 w = tw[k];
         const float2 val = cmul(w, make_float2(x.x, -x.y));
         float* o = out + b * 2 * n;
         if (k < n4) {

@@ -32,54 +32,58 @@ constexpr int kVorbisThreads = 64;
 struct FloorPoints { // active posts in X order, built by step 1/2 of one channel
     int x[68];
     int16_t y[68];
+    int16_t final_y[66]; // step-1 amplitudes (kept in shared memory: indexed dynamically)
     int n;
 };
 
+// floor(a / b) for 0 <= a < 2^23, 1 <= b < 2^14, exactly: float estimate + fix-up.
+__device__ __forceinline__ int div_small(int a, int b) {
+    int q = (int)((float)a * __frcp_rn((float)b));
+    while (q * b > a) --q;
+    while ((q + 1) * b <= a) ++q;
+    return q;
+}
+
 __device__ __forceinline__ int render_point(int x0, int y0, int x1, int y1, int x) { // floor.rs:776-782
     const int dy = y1 - y0;
-    const unsigned adx = (unsigned)(x1 - x0);
-    const unsigned err = (unsigned)abs(dy) * (unsigned)(x - x0);
-    const unsigned off = err / adx;
-    return dy < 0 ? y0 - (int)off : y0 + (int)off;
+    const int adx = x1 - x0;
+    const int off = div_small(abs(dy) * (x - x0), adx);
+    return dy < 0 ? y0 - off : y0 + off;
 }
 
 // Step 1 (floor.rs:568-625) + the sort-order walk of step 2 (floor.rs:627-653): one thread.
 __device__ void floor1_points(const symgpu_vorbis_floor1& s, const uint16_t* __restrict__ fy, int n_half, FloorPoints& out) {
-    int final_y[65];
     unsigned long long flag = 3ull; // floor_step2_flag[0] = [1] = true
     const int count = s.n_posts;
     const int mult = s.multiplier;
     const int range = mult == 1 ? 256 : mult == 2 ? 128 : mult == 3 ? 86 : 64;
-    final_y[0] = fy[0];
-    final_y[1] = fy[1];
+    int16_t* final_y = out.final_y;
+    final_y[0] = (int16_t)fy[0];
+    final_y[1] = (int16_t)fy[1];
     for (int i = 2; i < count; ++i) {
         const int lo = s.low[i], hi = s.high[i];
         const int predicted = render_point(s.x_list[lo], final_y[lo], s.x_list[hi], final_y[hi], s.x_list[i]);
         const int val = fy[i];
         const int highroom = range - predicted, lowroom = predicted;
+        int fin = predicted;
         if (val != 0) {
             const int room = 2 * (highroom < lowroom ? highroom : lowroom);
             flag |= (1ull << lo) | (1ull << hi) | (1ull << i);
-            int fin;
             if (val >= room) fin = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
             else fin = (val & 1) ? predicted - ((val + 1) / 2) : predicted + (val / 2);
-            final_y[i] = fin;
         } else {
             flag &= ~(1ull << i);
-            final_y[i] = predicted;
         }
+        final_y[i] = (int16_t)fin;
     }
-    // NOTE: final_y is indexed dynamically; it lives in local memory (65 ints) -- acceptable for a
-    // once-per-channel-packet integer recurrence.
-    int n = 0;
+    int n = 1;
     int hx = 0, hy = 0;
     out.x[0] = 0;
-    out.y[0] = (int16_t)min(max(final_y[s.sort_order[0]] * mult, 0), 255);
-    n = 1;
+    out.y[0] = (int16_t)min(max((int)final_y[s.sort_order[0]] * mult, 0), 255);
     for (int k = 1; k < count; ++k) {
         const int i = s.sort_order[k];
         if ((flag >> i) & 1ull) {
-            hy = min(max(final_y[i] * mult, 0), 255);
+            hy = min(max((int)final_y[i] * mult, 0), 255);
             hx = s.x_list[i];
             out.x[n] = hx;
             out.y[n] = (int16_t)hy;
@@ -91,27 +95,35 @@ __device__ void floor1_points(const symgpu_vorbis_floor1& s, const uint16_t* __r
         out.y[n] = (int16_t)hy;
         ++n;
     }
+    out.x[n] = 0x7fffffff; // sentinel for the segment walk
     out.n = n;
 }
 
-// Value of the rendered curve at line x (0 <= x < n_half): segment lookup + closed-form Bresenham.
-__device__ __forceinline__ float floor1_at(const FloorPoints& p, int x, const float* __restrict__ inv_db) {
-    int lo = 0, hi = p.n - 1; // find the last point with p.x[s] <= x
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)p.x[mid] <= x) lo = mid; else hi = mid;
+// Renders the curve for lines x = lane, lane + 32, ... < n_half: each lane walks the segments in
+// ascending x (floor.rs:785-825 in closed form: after d steps of render_line's error accumulator,
+// y(d) = y0 + d*base + sign(dy) * floor(d*ady / adx)).
+__device__ __forceinline__ void floor1_render(const FloorPoints& p, int n_half, int lane, float* spec,
+                                              const float* __restrict__ inv_db) {
+    int seg = 0;
+    int x0 = p.x[0], y0 = p.y[0], x1 = p.x[1], y1 = p.y[1];
+    int dy = y1 - y0, adx = x1 - x0, base = dy / adx, ady = abs(dy) - abs(base) * adx;
+    for (int x = lane; x < n_half; x += 32) {
+        while (x >= x1) { // advance to the segment containing x (at most 66 advances per lane in total)
+            ++seg;
+            x0 = x1;
+            y0 = y1;
+            x1 = p.x[seg + 1];
+            y1 = p.y[seg + 1];
+            dy = y1 - y0;
+            adx = x1 - x0;
+            base = dy / adx;
+            ady = abs(dy) - abs(base) * adx;
+        }
+        const int d = x - x0;
+        const int carries = div_small(d * ady, adx);
+        const int y = y0 + d * base + (dy < 0 ? -carries : carries);
+        spec[x] = __ldg(inv_db + y);
     }
-    if ((int)p.x[hi] <= x) lo = hi;
-    const int x0 = p.x[lo], y0 = p.y[lo];
-    if (lo + 1 >= p.n) return __ldg(inv_db + y0);
-    const int x1 = p.x[lo + 1], y1 = p.y[lo + 1];
-    const int dy = y1 - y0, adx = x1 - x0;
-    const int base = dy / adx;
-    const int ady = abs(dy) - abs(base) * adx;
-    const int d = x - x0;
-    const int carries = (d * ady) / adx;
-    const int y = y0 + d * base + (dy < 0 ? -carries : carries);
-    return __ldg(inv_db + y);
 }
 
 template <int LOG2>
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
             if (used) {
                 if (lane == 0) floor1_points(a.floors[u.floor[ch]], a.floor_y + ((size_t)p * 2 + ch) * 65, n2, pts[ch]);
                 __syncwarp();
-                for (int x = lane; x < n2; x += 32) spec[x] = floor1_at(pts[ch], x, tab->vorbis_inverse_db);
+                floor1_render(pts[ch], n2, lane, spec, tab->vorbis_inverse_db);
             } else {
                 for (int x = lane; x < n2; x += 32) spec[x] = 0.0f; // ch.floor[..n2].fill(0.0)
             }
