@@ -38,7 +38,7 @@ struct FloorPoints { // active posts in X order, built by step 1/2 of one channe
 
 // floor(a / b) for 0 <= a < 2^23, 1 <= b < 2^14, exactly: float estimate + fix-up.
 __device__ __forceinline__ int div_small(int a, int b) {
-    int q = (int)((float)a * __frcp_rn((float)b));
+    int q = (int)__fdividef((float)a, (float)b); // estimate only (no FFMA sequence); made exact below
     while (q * b > a) --q;
     while ((q + 1) * b <= a) ++q;
     return q;
