@@ -66,6 +66,9 @@ int symgpu_abi_version(void);
  * (ncclBroadcast / torch.distributed.broadcast) and tests can compare it with the oracle's
  * tables without a GPU.  Returns the number of bytes; `out` may be NULL to query the size. */
 size_t symgpu_tables_host_blob(void* out, size_t cap);
+/* Same for the tables of the power-of-two IMDCT codecs (FFT / IMDCT twiddles, AAC and Vorbis windows,
+ * floor1 inverse-dB table); layout = struct CodecTables of symphonia_b200/csrc/tables.h. */
+size_t symgpu_codec_tables_host_blob(void* out, size_t cap);
 /* Replace the device tables of `ctx` with a blob received from rank 0. */
 symgpu_status symgpu_tables_upload(symgpu_ctx* ctx, const void* blob, size_t bytes);
 

@@ -177,6 +177,13 @@ void oracle_fft_inplace(float* x, int n) { oracle::fft_inplace(reinterpret_cast<
 // N-point IMDCT with scaling: spec[n] -> out[2n] (Imdct::new_scaled(n, scale).imdct).
 void oracle_imdct(const float* spec, float* out, int n, double scale) { oracle::imdct_for(n, scale).run(spec, out); }
 
+// Imdct.twiddle[k] of Imdct::new_scaled(n, scale) (mdct.rs:42-54).
+void oracle_imdct_twiddle(int n, double scale, int k, float* re_im) {
+    const oracle::Imdct& im = oracle::imdct_for(n, scale);
+    re_im[0] = im.tw_re[k];
+    re_im[1] = im.tw_im[k];
+}
+
 // Twiddle of the level-`size` butterfly, for the constant check against the reference's literals.
 void oracle_fft_twiddle(int size, int k, float* re_im) {
     const oracle::Cpx w = oracle::twiddle(size, k);

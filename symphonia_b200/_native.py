@@ -76,6 +76,8 @@ def lib():
     L.symgpu_ctx_destroy.argtypes = [vp]
     L.symgpu_tables_host_blob.restype = sz
     L.symgpu_tables_host_blob.argtypes = [vp, sz]
+    L.symgpu_codec_tables_host_blob.restype = sz
+    L.symgpu_codec_tables_host_blob.argtypes = [vp, sz]
     L.symgpu_tables_upload.restype = ctypes.c_int
     L.symgpu_tables_upload.argtypes = [vp, vp, sz]
     L.symgpu_sync.restype = ctypes.c_int

@@ -24,7 +24,7 @@ constexpr float kFrac1Sqrt2F = 0.707106781186547524400844362104849039f;
 struct FftTables {
     float2 lit16[8];       // (cos(pi k/8), -sin(pi k/8)), k = 0..7   -- level-16 literals
     float2 lit32[16];      // (cos(pi k/16), -sin(pi k/16)), k = 0..15 -- level-32 literals
-    float2 merge[2048 - 32]; // level size s >= 64: W_s[k] at merge[s/2 - 32 + k], s = 64 .. 4096
+    float2 merge[2048 - 32]; // level size s >= 64: W_s[k] at merge[s/2 - 32 + k], s = 64 .. 2048
 };
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }

@@ -120,6 +120,12 @@ size_t symgpu_tables_host_blob(void* out, size_t cap) {
     return sizeof t;
 }
 
+size_t symgpu_codec_tables_host_blob(void* out, size_t cap) {
+    const CodecTables& t = codec_tables_host();
+    if (out && cap >= sizeof t) std::memcpy(out, &t, sizeof t);
+    return sizeof t;
+}
+
 size_t symgpu_mp3_pow43(float* out, size_t cap) {
     const Mp3Tables& t = mp3_tables_host();
     if (out) std::memcpy(out, t.pow43, sizeof(float) * (cap < 8207 ? cap : 8207));

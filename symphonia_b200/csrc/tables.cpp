@@ -315,7 +315,7 @@ const CodecTables& codec_tables_host() {
         std::memset(tab, 0, sizeof *tab);
         fft_twiddles(tab->fft_lit16, 16);
         fft_twiddles(tab->fft_lit32, 32);
-        for (int size = 64; size <= 4096; size <<= 1) fft_twiddles(tab->fft_merge + (size / 2 - 32), size);
+        for (int size = 64; size <= 2048; size <<= 1) fft_twiddles(tab->fft_merge + (size / 2 - 32), size);
         imdct_twiddles(tab->aac_tw_long, 1024, 1.0 / 2048.0);
         imdct_twiddles(tab->aac_tw_short, 128, 1.0 / 256.0);
         for (int n2 = 16; n2 <= 2048; n2 <<= 1) imdct_twiddles(tab->vorbis_tw + (n2 - 16), 2 * n2, 1.0);

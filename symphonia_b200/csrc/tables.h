@@ -50,7 +50,7 @@ struct Cplx {
 
 struct alignas(16) CodecTables {
     // FFT (symphonia-core/src/dsp/fft/no_simd.rs): level-16 / level-32 literal twiddles and the
-    // f64-built merge tables of sizes 64..4096, size s at offset s/2 - 32.
+    // f64-built merge tables of sizes 64..2048, size s at offset s/2 - 32.
     Cplx fft_lit16[8];
     Cplx fft_lit32[16];
     Cplx fft_merge[2048 - 32];

@@ -80,3 +80,63 @@ def test_workload_generator_is_deterministic_and_well_formed():
     assert not np.signbit(s1[s1 == 0]).any()   # zeros are +0.0, as the reference writes them
     # joint stereo requires equal block types in both channels (stereo.rs:503-505)
     assert (u1["block_type"][:, :, 0] == u1["block_type"][:, :, 1]).all()
+
+
+def test_codec_tables_match_oracle(oracle):
+    """FFT / IMDCT twiddles, AAC windows, Vorbis windows and the inverse-dB table built by the product
+    (tables.cpp) equal the oracle's independently written ones bit for bit."""
+    import symphonia_b200 as sb
+    lib = sb.lib()
+    n = lib.symgpu_codec_tables_host_blob(None, 0)
+    blob = np.zeros(n, dtype=np.uint8)
+    lib.symgpu_codec_tables_host_blob(blob.ctypes.data_as(ctypes.c_void_p), n)
+    f = blob.view(np.float32)
+    pos = 0
+
+    def take(count):
+        nonlocal pos
+        out = f[pos:pos + count]
+        pos += count
+        return out
+
+    lit16, lit32, merge = take(16).reshape(8, 2), take(32).reshape(16, 2), take(2 * 2016).reshape(2016, 2)
+    tw_long, tw_short, vtw = take(1024).reshape(512, 2), take(128).reshape(64, 2), take(2 * 4080).reshape(4080, 2)
+    sine_long, sine_short, kbd_long, kbd_short = take(1024), take(128), take(1024), take(128)
+    vwin, inv_db = take(8160), take(256)
+    out = (ctypes.c_float * 2)()
+
+    def tw(size, k):
+        oracle.oracle_fft_twiddle(size, k, out)
+        return np.float32(out[0]), np.float32(out[1])
+
+    for k in range(8):
+        assert tuple(lit16[k]) == tw(16, k)
+    for k in range(16):
+        assert tuple(lit32[k]) == tw(32, k)
+    for size in (64, 128, 512, 2048):
+        for k in (0, 1, size // 8, size // 4, size // 2 - 1):
+            assert tuple(merge[size // 2 - 32 + k]) == tw(size, k), (size, k)
+    oracle.oracle_imdct_twiddle.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+
+    def itw(nn, scale, k):
+        oracle.oracle_imdct_twiddle(nn, scale, k, out)
+        return np.float32(out[0]), np.float32(out[1])
+
+    for k in (0, 1, 255, 511):
+        assert tuple(tw_long[k]) == itw(1024, 1.0 / 2048.0, k)
+    for k in (0, 31, 63):
+        assert tuple(tw_short[k]) == itw(128, 1.0 / 256.0, k)
+    for n2 in (16, 64, 512, 2048):
+        for k in (0, n2 // 2, n2 - 1):
+            assert tuple(vtw[n2 - 16 + k]) == itw(2 * n2, 1.0, k), (n2, k)
+    get = oracle.oracle_aac_window
+    for arr, (kbd, short, ln) in ((sine_long, (0, 0, 1024)), (sine_short, (0, 1, 128)), (kbd_long, (1, 0, 1024)),
+                                  (kbd_short, (1, 1, 128))):
+        want = np.ctypeslib.as_array(get(kbd, short), shape=(ln,))
+        assert (arr.view(np.uint32) == want.view(np.uint32)).all()
+    for bs in (64, 256, 2048, 8192):
+        want = np.ctypeslib.as_array(oracle.oracle_vorbis_window(bs), shape=(bs // 2,))
+        got = vwin[bs // 2 - 32: bs // 2 - 32 + bs // 2]
+        assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    assert all(np.float32(oracle.oracle_vorbis_inverse_db(i)) == inv_db[i] for i in range(256))
+    assert pos * 4 == n

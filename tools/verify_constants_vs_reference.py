@@ -110,5 +110,39 @@ def main():
     return 1 if bad else 0
 
 
+
+
+def verify_fft_literals():
+    """The level-16 / level-32 twiddles the oracle and the product compute as (cos, -sin) in f64 equal the
+    reference's 20-digit literals (symphonia-core/src/dsp/fft/no_simd.rs:309-323, :376-382) bit for bit,
+    and the Vorbis inverse-dB table equals the reference's 8-digit literals."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle/_build/liboracle.so"))
+    src = open(os.path.join(REF, "symphonia-core/src/dsp/fft/no_simd.rs")).read()
+    bad = 0
+    for fn, size in (("fft32", 32), ("fft16", 16)):
+        body = src[src.index(f"fn {fn}("):]
+        body = body[:body.index("\n}\n")]
+        lits = re.findall(r"complex!\((-?[0-9.]+), (-?[0-9.]+)\) \* x1\[(\d+)\]", body)
+        assert lits, fn
+        for re_s, im_s, k in lits:
+            out = (ctypes.c_float * 2)()
+            lib.oracle_fft_twiddle(size, int(k), out)
+            ok = np.float32(out[0]) == np.float32(float(re_s)) and np.float32(out[1]) == np.float32(float(im_s))
+            bad += 0 if ok else 1
+            if not ok:
+                print("  mismatch", fn, k, out[0], out[1], re_s, im_s)
+        print(f"{fn} literal twiddles          {len(lits)} checked")
+    vsrc = open(os.path.join(REF, "symphonia-codec-vorbis/src/floor.rs")).read()
+    m = re.search(r"static FLOOR1_INVERSE_DB_TABLE: \[f32; 256\] = \[(.*?)\];", vsrc, re.S)
+    vals = [np.float32(float(v.strip().replace("_", ""))) for v in re.sub(r"//.*", "", m.group(1)).replace("\n", " ").split(",") if v.strip()]
+    lib.oracle_vorbis_inverse_db.restype = ctypes.c_float
+    same = sum(np.float32(lib.oracle_vorbis_inverse_db(i)) == vals[i] for i in range(256))
+    print(f"FLOOR1_INVERSE_DB_TABLE       {same}/256 bit-identical")
+    bad += 0 if same == 256 else 1
+    return bad
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    rc |= 1 if verify_fft_literals() else 0
+    sys.exit(rc)
