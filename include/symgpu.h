@@ -260,6 +260,60 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
                                       const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
                                       uint32_t n_packets, uint32_t slot, float* pcm);
 
+/* ===================================================================================================
+ * Output stage: planar f32 PCM -> interleaved samples of the caller's format, with
+ * the decoder's gapless trim, on the device -- so that the D2H copy carries i16 instead of f32.
+ * Replaces, for the batch:
+ *   AudioBuffer::trim(start, end)            symphonia-core/src/audio/buf.rs:404-433
+ *     (called by the decoders at symphonia-bundle-mp3/src/decoder.rs:130-132 and
+ *      symphonia-codec-vorbis/src/lib.rs:318-326)
+ *   Audio::copy_to_slice_interleaved::<Sout> symphonia-core/src/audio/buf.rs:469-476
+ *   FromSample<f32> for u8/i16/i24/i32/f32    symphonia-core/src/audio/conv.rs:592-607
+ *   clamp_f32 / clamp_i24                    symphonia-core/src/util.rs:230-237, :258-266
+ * Integer results are bit-exact: clamp to [-1, 1] (NaN passes through), scale by a power of two,
+ * truncate toward zero with Rust's saturating `as` cast (NaN -> 0).
+ * ================================================================================================= */
+typedef enum symgpu_sample_format {
+    SYMGPU_FMT_F32 = 0, /* f32, interleaved only                                   4 bytes / sample */
+    SYMGPU_FMT_S16 = 1, /* (s.clamped() * 32768.0) as i16                          2 bytes / sample */
+    SYMGPU_FMT_S24 = 2, /* i24::from((s.clamped() * 8388608.0) as i32).inner()     4 bytes / sample */
+    SYMGPU_FMT_S32 = 3, /* (s.clamped() as f64 * 2147483648.0) as i32              4 bytes / sample */
+    SYMGPU_FMT_U8 = 4   /* ((s.clamped() + 1.0) * 128.0) as u8                     1 byte  / sample */
+} symgpu_sample_format;
+
+/* One decoded packet of one stream.  32 bytes. */
+typedef struct symgpu_pcm_span {
+    uint64_t src;          /* float index, in `pcm`, of plane 0 of this packet                      */
+    uint32_t plane_stride; /* floats from plane c to plane c + 1                                    */
+    uint32_t frames;       /* decoded frames: 1152 (MP3), 1024 (AAC), (prev_n + n) / 4 (Vorbis)     */
+    uint32_t trim_start;   /* Packet::trim_start                                                    */
+    uint32_t trim_end;     /* Packet::trim_end                                                      */
+    uint64_t dst_frame;    /* index of the packet's first surviving frame in `out`                  */
+} symgpu_pcm_span;
+
+/* Frames of a span that survive the trim: truncate(frames.saturating_sub(end)), then shift(start). */
+uint32_t symgpu_pcm_span_kept(const symgpu_pcm_span* span);
+size_t symgpu_sample_bytes(int format); /* 0 for an unknown format */
+
+/* out[(dst_frame + i) * channels + c] = convert(pcm[src + c * plane_stride + trim_start + i]) for
+ * every kept frame i of every span; 1 <= channels <= 8.  `spans` may be NULL: then the n_spans packets
+ * are uniform, packet p at src = p * channels * plane_stride with `frames` frames, untrimmed, written
+ * back to back (dst_frame = p * frames).
+ * Device variant: pcm, spans and out are device memory; asynchronous on the context stream.
+ * Host variant: host memory (pcm_floats / out_bytes give the extents to copy). */
+symgpu_status symgpu_pcm_pack_dev(symgpu_ctx* ctx, const float* pcm, const symgpu_pcm_span* spans, uint32_t n_spans,
+                                  uint32_t channels, uint32_t plane_stride, uint32_t frames, int format, void* out);
+symgpu_status symgpu_pcm_pack_host(symgpu_ctx* ctx, const float* pcm, size_t pcm_floats, const symgpu_pcm_span* spans,
+                                   uint32_t n_spans, uint32_t channels, uint32_t plane_stride, uint32_t frames,
+                                   int format, void* out, size_t out_bytes);
+
+/* symgpu_mp3_synth_host with the output stage in the pipeline: the stereo PCM of frame f is written to
+ * out as interleaved samples [f * 1152 .. f * 1152 + 1152) of `format` (no trim); only the packed
+ * samples cross PCIe on the way back.  Runs must be 2-granule, 2-channel. */
+symgpu_status symgpu_mp3_synth_host_packed(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
+                                           const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
+                                           int format, void* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,5 @@
 // ORACLE (test infrastructure, NOT product code).  C surface of liboracle.so; see the headers of
-// oracle_mp3.cpp / oracle_mdct.cpp / oracle_aac.cpp / oracle_vorbis.cpp for what each restates.
+// oracle_mp3.cpp / oracle_mdct.cpp / oracle_aac.cpp / oracle_vorbis.cpp / oracle_conv.cpp for what each restates.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -60,6 +60,14 @@ int oracle_vorbis_batch(oracle_vorbis_state* states, const symgpu_vorbis_stream*
                         int n_threads);
 const float* oracle_vorbis_window(int bs);
 float oracle_vorbis_inverse_db(int i);
+
+// ---- output stage (oracle_conv.cpp) ----
+int16_t oracle_conv_s16(float s);
+int32_t oracle_conv_s24(float s);
+int32_t oracle_conv_s32(float s);
+uint8_t oracle_conv_u8(float s);
+int oracle_pcm_pack(const float* pcm, const symgpu_pcm_span* spans, uint32_t n_spans, uint32_t channels,
+                    uint32_t plane_stride, uint32_t frames, int format, void* out);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,12 @@ VORBIS_RUN_DTYPE = np.dtype([("stream", "<u4"), ("first_packet", "<u4"), ("n_pac
 assert AAC_UNIT_DTYPE.itemsize == 16 and AAC_TNS_DTYPE.itemsize == 88 and AAC_RUN_DTYPE.itemsize == 16
 assert VORBIS_FLOOR1_DTYPE.itemsize == 332 and VORBIS_STREAM_DTYPE.itemsize == 4
 assert VORBIS_UNIT_DTYPE.itemsize == 16 and VORBIS_RUN_DTYPE.itemsize == 16
+# `symgpu_pcm_span`, 32 bytes; sample formats of the output stage
+PCM_SPAN_DTYPE = np.dtype([("src", "<u8"), ("plane_stride", "<u4"), ("frames", "<u4"), ("trim_start", "<u4"),
+                           ("trim_end", "<u4"), ("dst_frame", "<u8")])
+assert PCM_SPAN_DTYPE.itemsize == 32
+FMT_F32, FMT_S16, FMT_S24, FMT_S32, FMT_U8 = 0, 1, 2, 3, 4
+FMT_NUMPY = {FMT_F32: np.float32, FMT_S16: np.int16, FMT_S24: np.int32, FMT_S32: np.int32, FMT_U8: np.uint8}
 AAC_ONLY_LONG, AAC_LONG_START, AAC_EIGHT_SHORT, AAC_LONG_STOP = 0, 1, 2, 3
 
 MP3_LONG, MP3_START, MP3_SHORT, MP3_END = 0, 1, 2, 3
@@ -114,6 +120,14 @@ def lib():
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, vp]
+    L.symgpu_sample_bytes.restype = sz
+    L.symgpu_sample_bytes.argtypes = [ctypes.c_int]
+    L.symgpu_pcm_pack_dev.restype = ctypes.c_int
+    L.symgpu_pcm_pack_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, ctypes.c_int, vp]
+    L.symgpu_pcm_pack_host.restype = ctypes.c_int
+    L.symgpu_pcm_pack_host.argtypes = [vp, vp, sz, vp, u32, u32, u32, u32, ctypes.c_int, vp, sz]
+    L.symgpu_mp3_synth_host_packed.restype = ctypes.c_int
+    L.symgpu_mp3_synth_host_packed.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
     _LIB = L
     return L
 

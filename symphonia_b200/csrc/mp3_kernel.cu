@@ -88,7 +88,7 @@ __device__ __forceinline__ int kind_of(const symgpu_mp3_gc& g) {
     return (g.flags & SYMGPU_MP3_F_MIXED) ? kKindMixed : kKindShort;
 }
 
-// ---- 9-point SDCT-II (hybrid_synthesis.rs:721-779); y[j] is the reference's y[2j] ----------
+// ---- 9-point SDCT-II (hybrid_synthesis.rs:721-779); y[j] is the reference's y[2j] ----------  // PHASE: B imdct36
 __device__ __forceinline__ void sdct9(const float (&x)[9], float (&y)[9]) {
     const float a01 = x[3] + x[5], a02 = x[3] - x[5], a03 = x[6] + x[2], a04 = x[6] - x[2];
     const float a05 = x[1] + x[7], a06 = x[1] - x[7], a07 = x[8] + x[0], a08 = x[8] - x[0];
@@ -150,7 +150,7 @@ __device__ __forceinline__ void imdct36(const float (&x)[18], const float* __res
     for (int i = 27; i < 36; ++i) second[i - 18] = -dct[i - 27] * win[i];
 }
 
-// imdct12_win (hybrid_synthesis.rs:363-455) without the overlap add.
+// imdct12_win (hybrid_synthesis.rs:363-455) without the overlap add.  // PHASE: B imdct12
 __device__ __forceinline__ void imdct12x3(const float (&x)[18], float (&first)[18], float (&second)[18]) {
     float tmp[36];
 #pragma unroll
@@ -179,7 +179,7 @@ __device__ __forceinline__ void imdct12x3(const float (&x)[18], float (&first)[1
     }
 }
 
-// ---- Lee 32-point DCT (synthesis.rs:348-844) as the recursion the reference hand-flattens ----
+// ---- Lee 32-point DCT (synthesis.rs:348-844) as the recursion the reference hand-flattens ----  // PHASE: C dct32
 template <int N> struct LeeCoef;
 template <> struct LeeCoef<16> { static __device__ __forceinline__ float at(int i) { return c_mp3.lee16[i]; } };
 template <> struct LeeCoef<8> { static __device__ __forceinline__ float at(int i) { return c_mp3.lee8[i]; } };
@@ -211,7 +211,7 @@ __device__ __forceinline__ void lee_dct(const float (&x)[N], float (&y)[N]) {
     }
 }
 
-// Sign of the frequency inversion (hybrid_synthesis.rs:458-485): odd sample of odd sub-band.
+// Sign of the frequency inversion (hybrid_synthesis.rs:458-485): odd sample of odd sub-band.  // PHASE: B store
 __device__ __forceinline__ float finv(float v, int sb, int t) { return ((sb & t) & 1) ? -v : v; }
 
 } // namespace
@@ -219,7 +219,7 @@ __device__ __forceinline__ float finv(float v, int sb, int t) { return ((sb & t)
 // =============================================================================================
 namespace {
 
-// ---- mbarrier / TMA bulk-copy wrappers (PTX ISA 8.6, sm_90+) -----------------------------------
+// ---- mbarrier / TMA bulk-copy wrappers (PTX ISA 8.6, sm_90+) -----------------------------------  // PHASE: tma+mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -253,7 +253,7 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
     return v;
 }
 
-// Polyphase window of `total` consecutive time slots whose DCT vectors sit in XT rows row0 ..
+// Polyphase window of `total` consecutive time slots whose DCT vectors sit in XT rows row0 ..  // PHASE: D window
 // (with the 15 rows before row0 holding the history).  lane = PCM sample index i; each warp walks a
 // contiguous range of slots with a 16-deep register window of (V_lo[i], V_hi[i]) for both channels:
 //   V_lo[i] =  d[16+i] (i<16) | 0 (i=16, the constant column 32) | -d[48-i] (i>16)
@@ -324,13 +324,15 @@ __device__ __forceinline__ void window_phase(const float* xt, int row0, int tota
     }
 }
 
-template <int T, int NW>
+template <int T, int NW>  // PHASE: prologue+tile loop
 struct Mp3Smem {
     static constexpr int kRows = 18 * (T + 1);            // region 0 = granule g0-1 (history), then the tile
     float xt[kRows * kPitch * 2];                         // [row][33][2 channels]
     alignas(16) float spec[T + 2][2 * 576];               // TMA destination: spectra of the 2 halo + T granules
     alignas(16) symgpu_mp3_gc units[T + 2][2];            // TMA destination: their descriptors
     WarpScratch ws[NW];
+    alignas(16) Mp3Tile tile_stage[2];                    // descriptor of the tile in flight (by iteration parity)
+    uint32_t gen_stage[2];                                // state generation of its stream at launch
     alignas(8) uint64_t bar;
     bool is_last;
 };
@@ -350,17 +352,25 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
     const Mp3Tables* __restrict__ tab = a.tab;
     const int n_tiles = a.n_tiles;
 
-    auto issue_prefetch = [&](int ti) { // one thread: TMA descriptors + spectra of tile ti into the stage
+    // One thread: tile descriptor + stream generation into their stage (ordinary stores, published by the
+    // release of the mbarrier arrive), then TMA bulk copies of the tile's descriptors + spectra.
+    auto issue_prefetch = [&](int ti, int parity) {
         const Mp3Tile t = a.tiles[ti];
+        sm.tile_stage[parity] = t;
+        sm.gen_stage[parity] = a.gen[t.stream];
         const int j0 = (t.flags & kTileLoadState) ? 2 : 0;
-        const int shift = t.gpf == 2 ? 1 : 0;
-        const int gseq0 = ((int)t.first_frame << shift) + t.first_gr;
-        mbar_expect_tx(&sm.bar, (uint32_t)(t.n_granules + 2 - j0) * (4608u + 128u));
-        for (int j = j0; j < t.n_granules + 2; ++j) {
-            const int gseq = gseq0 - 2 + j;
-            const size_t slot = ((size_t)(gseq >> shift) * 2 + (gseq & (t.gpf - 1))); // [frame][gr]
-            tma_bulk_g2s(sm.spec[j], a.spectra + slot * 1152, 4608u, &sm.bar);
-            tma_bulk_g2s(sm.units[j], a.units + slot * 2, 128u, &sm.bar);
+        const int cnt = t.n_granules + 2 - j0;
+        mbar_expect_tx(&sm.bar, (uint32_t)cnt * (4608u + 128u));
+        if (t.gpf == 2) { // granules of consecutive frames are contiguous: [frame][gr][ch][576]
+            const size_t slot = (size_t)t.first_frame * 2 + t.first_gr - 2 + j0;
+            tma_bulk_g2s(sm.spec[j0], a.spectra + slot * 1152, (uint32_t)cnt * 4608u, &sm.bar);
+            tma_bulk_g2s(sm.units[j0], a.units + slot * 2, (uint32_t)cnt * 128u, &sm.bar);
+        } else {          // one granule per frame slot
+            for (int j = j0; j < t.n_granules + 2; ++j) {
+                const size_t slot = (size_t)((int)t.first_frame + t.first_gr - 2 + j) * 2;
+                tma_bulk_g2s(sm.spec[j], a.spectra + slot * 1152, 4608u, &sm.bar);
+                tma_bulk_g2s(sm.units[j], a.units + slot * 2, 128u, &sm.bar);
+            }
         }
     };
 
@@ -369,12 +379,13 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue_prefetch(blockIdx.x);
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue_prefetch(blockIdx.x, 0);
 
     WarpScratch& ws = sm.ws[warp];
     int it = 0;
     for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++it) {
-        const Mp3Tile tile = a.tiles[ti];
+        mbar_wait(&sm.bar, (uint32_t)(it & 1));
+        const Mp3Tile tile = sm.tile_stage[it & 1];
         const int n = tile.n_granules;
         const int n_ch = tile.n_ch;
         const int gpf_shift = tile.gpf == 2 ? 1 : 0;
@@ -382,11 +393,10 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
         const bool store_state = tile.flags & kTileStoreState;
         // Stream state is double-buffered: a launch reads generation g and writes generation g+1, so a
         // run-starting tile never races with the run-ending tile of the same stream.
-        const uint32_t gen = a.gen[tile.stream];
+        const uint32_t gen = sm.gen_stage[it & 1];
         const Mp3StreamState* st_in = a.states + (size_t)tile.stream * 2 + (gen & 1);
         Mp3StreamState* st_out = a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
         const int gseq0 = ((int)tile.first_frame << gpf_shift) + tile.first_gr; // first granule of the tile
-        mbar_wait(&sm.bar, (uint32_t)(it & 1));
 
         // --------------------------------------------------------------------------------------
         // Phase A+B: one warp per granule job j (j = 0, 1: halo granules g0-2, g0-1; j >= 2: the tile),
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
             const bool is = (n_ch == 2) && (g0.flags & SYMGPU_MP3_F_INTENSITY);
             int rz0 = g0.rzero, rz1 = (n_ch == 2) ? g1.rzero : 0;
 
-            // A1: per-interval requantisation scale (requantize.rs:240-355)
+            // A1: per-interval requantisation scale (requantize.rs:240-355)  // PHASE: A1 scale
             for (int ch = 0; ch < n_ch; ++ch) {
                 const symgpu_mp3_gc& gg = sm.units[g][ch];
                 const int kind = ch ? kind1 : kind0;
@@ -439,16 +449,16 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
             }
             __syncwarp();
 
-            // A2: my 18 lines of each channel, requantised.  The short-block reorder
+            // A2: my 18 lines of each channel, requantised.  The short-block reorder  // PHASE: A2 requant+reorder
             // (hybrid_synthesis.rs:153-215) is a permutation applied AFTER the element-wise requantise
             // and stereo steps, so it is folded into the load: line d of the sub-band comes from source
             // line s, and every per-line decision below is taken on s.
             float x[2][18];
+            uint32_t ivq[5] = {0u, 0u, 0u, 0u, 0u}; // interval of the source line behind my i-th value, 4 per word
             // stereo.rs:550-553 sets both rzero to max(rzero) before reorder / antialias / hybrid see them
             const int rz_joint = max(rz0, rz1);
             const int rze[2] = {(ms || is) ? rz_joint : rz0, (ms || is) ? rz_joint : rz1};
             int rzr[2] = {rze[0], rze[1]}; // rzero after the reorder step
-            int ro_start = 0, ro_end = 0;  // reordered line range of channel 1's block kind (joint stereo)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 if (ch >= n_ch) {
@@ -457,10 +467,9 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
                     continue;
                 }
                 const int kind = ch ? kind1 : kind0;
-                const uint8_t* ivm = tab->iv_of_line[sr][kind];
                 const float* Sc = S + ch * 576;
                 if (kind == kKindLong) {
-                    const uint16_t* iv2 = reinterpret_cast<const uint16_t*>(ivm + 18 * lane);
+                    const uint16_t* iv2 = reinterpret_cast<const uint16_t*>(tab->iv_of_line[sr][kind] + 18 * lane);
 #pragma unroll
                     for (int i = 0; i < 18; i += 2) {
                         const float2 v = *reinterpret_cast<const float2*>(Sc + 18 * lane + i);
@@ -468,9 +477,12 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
                         // lines at or beyond rzero are +0.0 by contract (requantize.rs:234): 0 * scale = 0
                         x[ch][i] = v.x * ws.scale[ch][ivp & 0xff];
                         x[ch][i + 1] = v.y * ws.scale[ch][ivp >> 8];
-                        if (ch && is) {
-                            if (x[ch][i] != 0.0f) ws.nz[ivp & 0xff] = 1;
-                            if (x[ch][i + 1] != 0.0f) ws.nz[ivp >> 8] = 1;
+                        if (ch) {
+                            ivq[i >> 2] |= ivp << (8 * (i & 3)); // i is even: the pair lands in one word
+                            if (is) {
+                                if (x[ch][i] != 0.0f) ws.nz[ivp & 0xff] = 1;
+                                if (x[ch][i + 1] != 0.0f) ws.nz[ivp >> 8] = 1;
+                            }
                         }
                     }
                 } else {
@@ -483,24 +495,26 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
                     const int n_done = __popc(__ballot_sync(0xffffffffu, below)); // reordered quads form a prefix
                     const int start = e[0], i_end = e[3 * n_done];
                     rzr[ch] = max(rz, i_end); // hybrid_synthesis.rs:213
-                    if (ch == n_ch - 1) { ro_start = start; ro_end = i_end; }
-                    const uint16_t* src = tab->reorder_src[sr][m];
+                    const uint32_t* map = tab->short_map[sr][m] + 18 * lane;
 #pragma unroll
                     for (int i = 0; i < 18; ++i) {
                         const int d = 18 * lane + i;
-                        const int s = (d >= start && d < i_end) ? (int)__ldg(src + d) : d;
-                        const int iv = __ldg(ivm + s);
+                        const uint32_t e3 = __ldg(map + i);
+                        const bool moved = d >= start && d < i_end;
+                        const int s = moved ? (int)(e3 & 1023u) : d;
+                        const int iv = moved ? (int)((e3 >> 10) & 63u) : (int)((e3 >> 16) & 63u);
                         x[ch][i] = Sc[s] * ws.scale[ch][iv];
-                        if (ch && is && x[ch][i] != 0.0f) ws.nz[iv] = 1;
+                        if (ch) {
+                            ivq[i >> 2] |= (uint32_t)iv << (8 * (i & 3));
+                            if (is && x[ch][i] != 0.0f) ws.nz[iv] = 1;
+                        }
                     }
                 }
             }
             __syncwarp();
 
-            // A3/A4: joint stereo (stereo.rs:485-556), decided per SOURCE line
+            // A3/A4: joint stereo (stereo.rs:485-556), decided per SOURCE line  // PHASE: A3 stereo
             if (ms || is) {
-                const int end = max(rz0, rz1);
-                int bound = end;
                 if (is) {
                     // Warp-parallel restatement of the two top-down scans (stereo.rs:198-261, :265-482).
                     const bool mpeg1 = g1.flags & SYMGPU_MP3_F_MPEG1;
@@ -520,7 +534,6 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
                         const int hb = nzmask ? 63 - __clzll((long long)nzmask) : -1; // highest non-zero band
                         is_lo = hb + 1;
                         first_is0 = first_is1 = first_is2 = hb + 1;
-                        if (hb < 21) bound = e[hb + 1];
                     } else {
                         const int sw = (kind1 == kKindMixed) ? c_mp3.mixed_switch[sr] : 0;
                         const int n_quads = (n_e - sw - 1) / 3;
@@ -537,79 +550,69 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
                         first_is0 = sw + 3 * (hq0 + 1);
                         first_is1 = sw + 3 * (hq1 + 1) + 1;
                         first_is2 = sw + 3 * (hq2 + 1) + 2;
-                        bound = e[is_lo];
                         if (qstop < 0 && kind1 == kKindMixed) { // continue into the long bands of a mixed block
                             const unsigned long long lmask = nzmask & ((1ull << sw) - 1ull);
                             const int hb = lmask ? 63 - __clzll((long long)lmask) : -1;
-                            if (hb < sw - 1) {
-                                is_lo = hb + 1;
-                                bound = e[hb + 1];
-                            }
+                            if (hb < sw - 1) is_lo = hb + 1;
                         }
                     }
+                    // Mode of every interval: below the intensity region plain / mid-side, inside it intensity
+                    // where the position is valid (process_intensity, stereo.rs:168-188), else plain / mid-side.
                     for (int iv = lane; iv < n_iv; iv += 32) {
-                        if (iv < is_lo) continue;
-                        bool coded;
-                        if (kind1 == kKindLong) {
-                            coded = true;
-                        } else {
-                            const int sw = (kind1 == kKindMixed) ? c_mp3.mixed_switch[sr] : 0;
-                            if (iv < sw) coded = true;
-                            else {
-                                const int w = (iv - sw) % 3;
-                                coded = iv >= (w == 0 ? first_is0 : w == 1 ? first_is1 : first_is2);
-                            }
-                        }
                         uint8_t mode = mode_hi;
-                        if (coded) {
-                            const int k = (kind1 == kKindLong) ? (iv == 21 ? 20 : iv) : (iv < 36 ? iv : iv - 3);
-                            const int pos = g1.scalefacs[k];
-                            if (pos < inv_pos) { // process_intensity, stereo.rs:168-188
-                                mode = 2;
-                                ws.sratio[iv] = make_float2(rt[pos][0], rt[pos][1]);
+                        if (iv >= is_lo) {
+                            bool coded;
+                            if (kind1 == kKindLong) {
+                                coded = true;
+                            } else {
+                                const int sw = (kind1 == kKindMixed) ? c_mp3.mixed_switch[sr] : 0;
+                                if (iv < sw) coded = true;
+                                else {
+                                    const int w = (iv - sw) % 3;
+                                    coded = iv >= (w == 0 ? first_is0 : w == 1 ? first_is1 : first_is2);
+                                }
+                            }
+                            if (coded) {
+                                const int k = (kind1 == kKindLong) ? (iv == 21 ? 20 : iv) : (iv < 36 ? iv : iv - 3);
+                                const int pos = g1.scalefacs[k];
+                                if (pos < inv_pos) {
+                                    mode = 2;
+                                    ws.sratio[iv] = make_float2(rt[pos][0], rt[pos][1]);
+                                }
                             }
                         }
                         ws.smode[iv] = mode;
                     }
                     __syncwarp();
-                }
-                // Source line of my i-th value: with joint stereo both channels share the block kind and the
-                // post-stereo rzero, hence the reorder map computed in A2.
-                const bool shortk = kind1 != kKindLong;
-                const int start = ro_start, i_end = ro_end;
-                const uint16_t* src = tab->reorder_src[sr][kind1 == kKindMixed ? 1 : 0];
-                const uint8_t* ivm1 = tab->iv_of_line[sr][kind1];
+                    // A line takes the mode of the interval of its SOURCE line (remembered from A2).  Lines at or
+                    // beyond max(rzero) are +0.0 in both channels and stay +0.0 under either transform.
 #pragma unroll
-                for (int i = 0; i < 18; ++i) {
-                    const int d = 18 * lane + i;
-                    int mode;
-                    if (!is) {
-                        // MS only: decided on the source line, but "below bound" is the same set before and
-                        // after the permutation only if we test the source line
-                        int s = d;
-                        if (shortk && d >= start && d < i_end) s = (int)__ldg(src + d);
-                        mode = (s < bound) ? 1 : 0;
-                    } else {
-                        int s = d;
-                        if (shortk && d >= start && d < i_end) s = (int)__ldg(src + d);
-                        mode = (s < bound) ? (ms ? 1 : 0) : (int)ws.smode[__ldg(ivm1 + s)];
+                    for (int i = 0; i < 18; ++i) {
+                        const int iv = (ivq[i >> 2] >> (8 * (i & 3))) & 0xff;
+                        const int mode = ws.smode[iv];
+                        const float l = x[0][i], r = x[1][i];
                         if (mode == 2) {
-                            const float2 r = ws.sratio[__ldg(ivm1 + s)];
-                            const float isv = x[0][i];
-                            x[0][i] = r.x * isv;
-                            x[1][i] = r.y * isv;
+                            const float2 ratio = ws.sratio[iv];
+                            x[0][i] = ratio.x * l;
+                            x[1][i] = ratio.y * l;
+                        } else if (mode == 1) { // process_mid_side, stereo.rs:143-152
+                            x[0][i] = (l + r) * kFrac1Sqrt2;
+                            x[1][i] = (l - r) * kFrac1Sqrt2;
                         }
                     }
-                    if (mode == 1) { // process_mid_side, stereo.rs:143-152
-                        const float left = (x[0][i] + x[1][i]) * kFrac1Sqrt2;
-                        const float right = (x[0][i] - x[1][i]) * kFrac1Sqrt2;
-                        x[0][i] = left;
-                        x[1][i] = right;
+                } else {
+                    // Mid-side only: every line below max(rzero); the lines above are +0.0 in both channels and
+                    // (0 + 0) * c = (0 - 0) * c = +0.0, so the bound needs no test.
+#pragma unroll
+                    for (int i = 0; i < 18; ++i) {
+                        const float l = x[0][i], r = x[1][i];
+                        x[0][i] = (l + r) * kFrac1Sqrt2;
+                        x[1][i] = (l - r) * kFrac1Sqrt2;
                     }
                 }
             }
 
-            // A6: antialias (hybrid_synthesis.rs:218-277) across neighbouring lanes
+            // A6: antialias (hybrid_synthesis.rs:218-277) across neighbouring lanes  // PHASE: A6 antialias
             int rzh[2]; // rzero seen by hybrid_synthesis
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
                 }
             }
 
-            // B: hybrid synthesis (hybrid_synthesis.rs:280-359)
+            // B: hybrid synthesis (hybrid_synthesis.rs:280-359)  // PHASE: B glue
             float* X = xt + (size_t)(18 * (g - 1)) * kPitch * 2; // unused by job 0 (it only hands its overlap on)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
@@ -677,11 +680,11 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();  // PHASE: handoff+barriers
         // The stage is free: fetch this CTA's next tile while the current one is in its DCT / window phases.
         if (threadIdx.x == NW * 32 - 32 && ti + (int)gridDim.x < n_tiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_prefetch(ti + gridDim.x);
+            issue_prefetch(ti + gridDim.x, (it + 1) & 1);
         }
         // overlap hand-off: region of job g+1 += second(g); the run's last granule feeds the stream state
         if (active) {
@@ -712,7 +715,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
         __syncthreads();
 
         // --------------------------------------------------------------------------------------
-        // Phase C: DCT-32 of every time slot of the tile, in place.  Half-warp = 16 slots of one
+        // Phase C: DCT-32 of every time slot of the tile, in place.  Half-warp = 16 slots of one  // PHASE: C glue
         // channel: the 32-bit accesses of a warp hit 32 distinct banks (row pitch 66 words).
         // --------------------------------------------------------------------------------------
         {
@@ -735,7 +738,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
         }
         __syncthreads();
 
-        // Phase D: polyphase window (synthesis.rs:247-263, :309-327), see window_phase().
+        // Phase D: polyphase window (synthesis.rs:247-263, :309-327), see window_phase().  // PHASE: D glue+epilogue
         window_phase<NW>(xt, 18, n * 18, warp, lane, tab->synth_d, a.pcm, gseq0 * 18, 18 << gpf_shift, n_ch == 2);
         __syncthreads();
         // The run's last tile publishes the polyphase history (last 15 DCT vectors) for the next batch.

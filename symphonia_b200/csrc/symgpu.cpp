@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "pack_kernel.h"
 
 
 using namespace symgpu;
@@ -256,19 +257,39 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
     return SYMGPU_OK;
 }
 
-symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
-                                    const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, float* pcm) {
-    if (!ctx || !units || !spectra || !runs || !pcm) return SYMGPU_ERR_ARG;
+} // extern "C"
+
+// Host-buffer MP3 synthesis.  format < 0: planar f32 into `out` (the AudioBuffer layout); otherwise the
+// output stage runs on the device after each slice's kernel and `out` receives interleaved samples.
+static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
+                                         const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, int format,
+                                         void* out) {
+    if (!ctx || !units || !spectra || !runs || !out) return SYMGPU_ERR_ARG;
+    const size_t sample_bytes = format < 0 ? sizeof(float) : symgpu_sample_bytes(format);
+    if (sample_bytes == 0) return SYMGPU_ERR_ARG;
     if (n_frames == 0) return SYMGPU_OK;
     DeviceGuard guard(ctx->device);
     const size_t unit_bytes = (size_t)n_frames * 4 * sizeof(symgpu_mp3_gc);
     const size_t spec_bytes = (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
-    symgpu_status s = ensure_stage(ctx, unit_bytes + 2 * spec_bytes);
+    const size_t packed_bytes = format < 0 ? 0 : (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sample_bytes;
+    symgpu_status s = ensure_stage(ctx, unit_bytes + 2 * spec_bytes + packed_bytes);
     if (s != SYMGPU_OK) return s;
     char* base = static_cast<char*>(ctx->d_stage);
     float* d_spec = reinterpret_cast<float*>(base);
     float* d_pcm = reinterpret_cast<float*>(base + spec_bytes);
     symgpu_mp3_gc* d_units = reinterpret_cast<symgpu_mp3_gc*>(base + 2 * spec_bytes);
+    char* d_packed = base + 2 * spec_bytes + unit_bytes; // unit_bytes is a multiple of 256
+    char* out_bytes = static_cast<char*>(out);
+    // Device source and per-frame size of what travels back to the host.
+    const char* d_result = format < 0 ? reinterpret_cast<const char*>(d_pcm) : d_packed;
+    const size_t frame_out_bytes = (size_t)SYMGPU_MP3_FRAME_FLOATS * sample_bytes;
+    auto pack = [&](uint32_t f0, uint32_t nf) -> cudaError_t {
+        if (format < 0) return cudaSuccess;
+        symgpu::PackArgs pa{d_pcm + (size_t)f0 * SYMGPU_MP3_FRAME_FLOATS, nullptr, nf, 2, 1152, 1152,
+                            d_packed + (size_t)f0 * frame_out_bytes};
+        ctx->launches += 1;
+        return symgpu::pack_launch(pa, format, ctx->stream);
+    };
     // Mono / MPEG-2 frames leave part of each PCM slot untouched: define it as zero.
     bool partial = false, sorted = true;
     uint64_t next = 0;
@@ -278,6 +299,7 @@ symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
         next += runs[r].n_frames;
     }
     sorted &= next == n_frames;
+    if (partial && format >= 0) return SYMGPU_ERR_UNSUPPORTED;
     if (partial) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
 
     if (!sorted || n_frames < 512 || n_runs < 2) {
@@ -286,7 +308,8 @@ symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
         CU(ctx, cudaMemcpyAsync(d_spec, spectra, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
         s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
         if (s != SYMGPU_OK) return s;
-        CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, pack(0, n_frames));
+        CU(ctx, cudaMemcpyAsync(out_bytes, d_result, (size_t)n_frames * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         return SYMGPU_OK;
     }
@@ -352,12 +375,90 @@ symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
                   ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
         CU(ctx, mp3_launch(a, ctx->stream));
         ctx->launches += 1;
+        CU(ctx, pack(sl.f0, (uint32_t)nf));
         CU(ctx, cudaEventRecord(ctx->ev_k[i], ctx->stream));
         CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
-        CU(ctx, cudaMemcpyAsync(pcm + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS, d_pcm + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS,
-                                nf * SYMGPU_MP3_FRAME_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+        CU(ctx, cudaMemcpyAsync(out_bytes + (size_t)sl.f0 * frame_out_bytes, d_result + (size_t)sl.f0 * frame_out_bytes,
+                                nf * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
     }
     CU(ctx, cudaStreamSynchronize(ctx->copy_out));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SYMGPU_OK;
+}
+
+extern "C" {
+
+symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
+                                    const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, float* pcm) {
+    return mp3_synth_host_impl(ctx, units, spectra, runs, n_runs, n_frames, -1, pcm);
+}
+
+symgpu_status symgpu_mp3_synth_host_packed(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
+                                           const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
+                                           int format, void* out) {
+    if (format < 0) return SYMGPU_ERR_ARG;
+    return mp3_synth_host_impl(ctx, units, spectra, runs, n_runs, n_frames, format, out);
+}
+
+uint32_t symgpu_pcm_span_kept(const symgpu_pcm_span* s) {
+    if (!s) return 0;
+    const uint32_t n = s->frames > s->trim_end ? s->frames - s->trim_end : 0;
+    return s->trim_start >= n ? 0 : n - s->trim_start;
+}
+
+size_t symgpu_sample_bytes(int format) {
+    switch (format) {
+    case SYMGPU_FMT_F32: case SYMGPU_FMT_S24: case SYMGPU_FMT_S32: return 4;
+    case SYMGPU_FMT_S16: return 2;
+    case SYMGPU_FMT_U8: return 1;
+    default: return 0;
+    }
+}
+
+symgpu_status symgpu_pcm_pack_dev(symgpu_ctx* ctx, const float* pcm, const symgpu_pcm_span* spans, uint32_t n_spans,
+                                  uint32_t channels, uint32_t plane_stride, uint32_t frames, int format, void* out) {
+    if (!ctx || !pcm || !out || channels == 0 || channels > 8) return SYMGPU_ERR_ARG;
+    if (symgpu_sample_bytes(format) == 0) return SYMGPU_ERR_ARG;
+    if (n_spans == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    symgpu::PackArgs pa{pcm, spans, n_spans, channels, plane_stride, frames, out};
+    CU(ctx, symgpu::pack_launch(pa, format, ctx->stream));
+    ctx->launches += 1;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_pcm_pack_host(symgpu_ctx* ctx, const float* pcm, size_t pcm_floats, const symgpu_pcm_span* spans,
+                                   uint32_t n_spans, uint32_t channels, uint32_t plane_stride, uint32_t frames,
+                                   int format, void* out, size_t out_bytes) {
+    if (!ctx || !pcm || !out || channels == 0 || channels > 8) return SYMGPU_ERR_ARG;
+    const size_t sb = symgpu_sample_bytes(format);
+    if (sb == 0) return SYMGPU_ERR_ARG;
+    if (n_spans == 0) return SYMGPU_OK;
+    // Every span must stay inside the buffers the caller described.
+    for (uint32_t p = 0; p < n_spans; ++p) {
+        symgpu_pcm_span sp;
+        if (spans) sp = spans[p];
+        else sp = symgpu_pcm_span{(uint64_t)p * channels * plane_stride, plane_stride, frames, 0, 0, (uint64_t)p * frames};
+        const uint32_t kept = symgpu_pcm_span_kept(&sp);
+        if (kept == 0) continue;
+        if (sp.src + (uint64_t)(channels - 1) * sp.plane_stride + sp.trim_start + kept > pcm_floats) return SYMGPU_ERR_LIMIT;
+        if ((sp.dst_frame + kept) * channels * sb > out_bytes) return SYMGPU_ERR_LIMIT;
+    }
+    DeviceGuard guard(ctx->device);
+    const size_t in_bytes = (pcm_floats * sizeof(float) + 255) & ~(size_t)255;
+    const size_t span_bytes = spans ? ((size_t)n_spans * sizeof(symgpu_pcm_span) + 255) & ~(size_t)255 : 0;
+    symgpu_status s = ensure_stage(ctx, in_bytes + span_bytes + out_bytes);
+    if (s != SYMGPU_OK) return s;
+    char* base = static_cast<char*>(ctx->d_stage);
+    CU(ctx, cudaMemcpyAsync(base, pcm, pcm_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (spans) CU(ctx, cudaMemcpyAsync(base + in_bytes, spans, (size_t)n_spans * sizeof(symgpu_pcm_span), cudaMemcpyHostToDevice, ctx->stream));
+    // Samples no span writes keep the caller's bytes.
+    CU(ctx, cudaMemcpyAsync(base + in_bytes + span_bytes, out, out_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    s = symgpu_pcm_pack_dev(ctx, reinterpret_cast<const float*>(base),
+                            spans ? reinterpret_cast<const symgpu_pcm_span*>(base + in_bytes) : nullptr, n_spans, channels,
+                            plane_stride, frames, format, base + in_bytes + span_bytes);
+    if (s != SYMGPU_OK) return s;
+    CU(ctx, cudaMemcpyAsync(out, base + in_bytes + span_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SYMGPU_OK;
 }

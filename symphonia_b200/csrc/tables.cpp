@@ -112,6 +112,9 @@ void build_line_maps(Mp3Tables& t) {
                 for (int k = 0; k < len; ++k)
                     for (int w = 0; w < 3; ++w) src[i++] = (uint16_t)(e[q + w] + k);
             }
+            const uint8_t* ivm = t.iv_of_line[sr][kind];
+            for (int line = 0; line < 576; ++line)
+                t.short_map[sr][m][line] = (uint32_t)src[line] | ((uint32_t)ivm[src[line]] << 10) | ((uint32_t)ivm[line] << 16);
         }
     }
 }

@@ -38,6 +38,9 @@ struct alignas(16) Mp3Tables {
     alignas(16) uint8_t iv_of_line[9][3][576];  // interval index of each spectral line (read as uchar4)
     alignas(16) uint16_t reorder_src[9][2][576]; // [..][0 short | 1 mixed][dest line] -> source line
     uint16_t reorder_start[9][2];
+    // One word per destination line of a short / mixed granule, so that the reordered load needs a single
+    // lookup: bits 0-9 source line, 10-15 interval of the source line, 16-21 interval of the line itself.
+    alignas(16) uint32_t short_map[9][2][576];
 };
 
 // Builds the tables (host libm).  Thread-safe, built once.

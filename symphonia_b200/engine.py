@@ -8,8 +8,8 @@ import ctypes
 import numpy as np
 
 from . import _native
-from ._native import (AAC_RUN_DTYPE, AAC_TNS_DTYPE, AAC_UNIT_DTYPE, MP3_GC_DTYPE, MP3_RUN_DTYPE, VORBIS_FLOOR1_DTYPE,
-                      VORBIS_RUN_DTYPE, VORBIS_STREAM_DTYPE, VORBIS_UNIT_DTYPE)
+from ._native import (AAC_RUN_DTYPE, AAC_TNS_DTYPE, AAC_UNIT_DTYPE, FMT_NUMPY, MP3_GC_DTYPE, MP3_RUN_DTYPE,
+                      PCM_SPAN_DTYPE, VORBIS_FLOOR1_DTYPE, VORBIS_RUN_DTYPE, VORBIS_STREAM_DTYPE, VORBIS_UNIT_DTYPE)
 
 
 class SymgpuError(RuntimeError):
@@ -110,6 +110,42 @@ class Engine:
         self._check(self._lib.symgpu_mp3_synth_dev(self._ctx, ctypes.c_void_p(units_t.data_ptr()),
                                                    ctypes.c_void_p(spectra_t.data_ptr()), _np_ptr(runs), len(runs),
                                                    n_frames, ctypes.c_void_p(pcm_t.data_ptr())))
+
+    def mp3_synth_host_packed(self, units, spectra, runs, fmt, out=None):
+        """Like mp3_synth_host, but the output stage runs on the device: returns [F*1152, 2] interleaved
+        samples of `fmt` (FMT_*); only those cross PCIe on the way back."""
+        units, runs, n_frames = self._mp3_args(units, spectra, runs)
+        spectra = np.ascontiguousarray(spectra, dtype=np.float32)
+        if spectra.size != n_frames * 2304:
+            raise ValueError("spectra must be [n_frames, 2, 2, 576]")
+        if out is None:
+            out = np.empty((n_frames * 1152, 2), dtype=FMT_NUMPY[fmt])
+        self._check(self._lib.symgpu_mp3_synth_host_packed(self._ctx, _np_ptr(units), _np_ptr(spectra), _np_ptr(runs),
+                                                           len(runs), n_frames, int(fmt), _np_ptr(out)))
+        return out
+
+    # -- output stage -------------------------------------------------------------------------
+    def pcm_pack_host(self, pcm, spans, channels, fmt, out_frames, plane_stride=0, frames=0, n_spans=None, out=None):
+        """Trim + interleave + convert planar f32 `pcm` (any shape, flat indexing) into [out_frames, channels]
+        samples.  spans: PCM_SPAN_DTYPE array, or None for uniform packets (plane_stride, frames, n_spans)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        if spans is not None:
+            spans = np.ascontiguousarray(spans, dtype=PCM_SPAN_DTYPE)
+            n_spans = len(spans)
+        if out is None:
+            out = np.zeros((out_frames, channels), dtype=FMT_NUMPY[fmt])
+        self._check(self._lib.symgpu_pcm_pack_host(self._ctx, _np_ptr(pcm), pcm.size,
+                                                   _np_ptr(spans) if spans is not None else None, n_spans, channels,
+                                                   plane_stride, frames, int(fmt), _np_ptr(out), out.nbytes))
+        return out
+
+    def pcm_pack_dev(self, pcm_t, spans_t, n_spans, channels, fmt, out_t, plane_stride=0, frames=0):
+        """Device-resident variant (torch CUDA tensors; spans_t may be None for uniform packets)."""
+        assert pcm_t.is_cuda and out_t.is_cuda
+        self._check(self._lib.symgpu_pcm_pack_dev(self._ctx, ctypes.c_void_p(pcm_t.data_ptr()),
+                                                  ctypes.c_void_p(spans_t.data_ptr()) if spans_t is not None else None,
+                                                  n_spans, channels, plane_stride, frames, int(fmt),
+                                                  ctypes.c_void_p(out_t.data_ptr())))
 
     # -- AAC --------------------------------------------------------------------------------
     def aac_streams_alloc(self, n_streams):

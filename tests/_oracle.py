@@ -71,7 +71,30 @@ def load(path=None):
                                                                 ctypes.c_int]
     lib.oracle_vorbis_window.restype = c_f32p
     lib.oracle_vorbis_inverse_db.restype = ctypes.c_float
+    lib.oracle_conv_s16.restype = ctypes.c_int16
+    lib.oracle_conv_s24.restype = ctypes.c_int32
+    lib.oracle_conv_s32.restype = ctypes.c_int32
+    lib.oracle_conv_u8.restype = ctypes.c_uint8
+    for fn in (lib.oracle_conv_s16, lib.oracle_conv_s24, lib.oracle_conv_s32, lib.oracle_conv_u8):
+        fn.argtypes = [ctypes.c_float]
+    lib.oracle_pcm_pack.restype = ctypes.c_int
+    lib.oracle_pcm_pack.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_uint32] * 4 + [ctypes.c_int,
+                                                                                                 ctypes.c_void_p]
     return lib
+
+
+def pcm_pack(lib, pcm, spans, channels, fmt, out_frames, plane_stride=0, frames=0, n_spans=None):
+    """oracle_pcm_pack with the same calling convention as Engine.pcm_pack_host."""
+    from symphonia_b200._native import FMT_NUMPY, PCM_SPAN_DTYPE
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    if spans is not None:
+        spans = np.ascontiguousarray(spans, dtype=PCM_SPAN_DTYPE)
+        n_spans = len(spans)
+    out = np.zeros((out_frames, channels), dtype=FMT_NUMPY[fmt])
+    rc = lib.oracle_pcm_pack(ptr(pcm), ptr(spans) if spans is not None else None, n_spans, channels, plane_stride,
+                             frames, fmt, ptr(out))
+    assert rc == 0
+    return out
 
 
 def mp3_batch(lib, units, spectra, runs, n_streams):
