@@ -28,7 +28,7 @@ struct symgpu_ctx {
     size_t tiles_cap = 0;
     std::vector<symgpu_mp3_run> cached_runs;
     uint32_t cached_frames = 0;
-    int cached_tiles = 0;
+    int cached_tiles = 0, cached_hdr = 0, cached_ctas = 0;
     // staging for the host entry points
     void* d_stage = nullptr;
     size_t stage_cap = 0;

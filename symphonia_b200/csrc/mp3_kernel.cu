@@ -331,6 +331,7 @@ struct Mp3Smem {
     alignas(16) float spec[T + 2][2 * 576];               // TMA destination: spectra of the 2 halo + T granules
     alignas(16) symgpu_mp3_gc units[T + 2][2];            // TMA destination: their descriptors
     WarpScratch ws[NW];
+    alignas(16) Mp3StreamState carry;                     // state handed from one tile of the chain to the next
     alignas(16) Mp3Tile tile_stage[2];                    // descriptor of the tile in flight (by iteration parity)
     uint32_t gen_stage[2];                                // state generation of its stream at launch
     alignas(8) uint64_t bar;
@@ -341,7 +342,7 @@ struct Mp3Smem {
 
 template <int T, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
-    static_assert(NW >= T + 2, "one warp per granule job (tile + 2 halo granules)");
+    static_assert(NW >= T, "one warp per granule job (a tile with a halo holds NW - 2 granules)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = Mp3Smem<T, NW>;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
         const Mp3Tile t = a.tiles[ti];
         sm.tile_stage[parity] = t;
         sm.gen_stage[parity] = a.gen[t.stream];
-        const int j0 = (t.flags & kTileLoadState) ? 2 : 0;
+        const int j0 = (t.flags & (kTileLoadState | kTileCarryIn)) ? 2 : 0;
         const int cnt = t.n_granules + 2 - j0;
         mbar_expect_tx(&sm.bar, (uint32_t)cnt * (4608u + 128u));
         if (t.gpf == 2) { // granules of consecutive frames are contiguous: [frame][gr][ch][576]
@@ -379,31 +380,36 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue_prefetch(blockIdx.x, 0);
+    const int t_begin = (int)a.cta_first[blockIdx.x], t_end = (int)a.cta_first[blockIdx.x + 1];
+    if (threadIdx.x == 0 && t_begin < t_end) issue_prefetch(t_begin, 0);
 
     WarpScratch& ws = sm.ws[warp];
     int it = 0;
-    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x, ++it) {
+    for (int ti = t_begin; ti < t_end; ++ti, ++it) {
         mbar_wait(&sm.bar, (uint32_t)(it & 1));
         const Mp3Tile tile = sm.tile_stage[it & 1];
         const int n = tile.n_granules;
         const int n_ch = tile.n_ch;
         const int gpf_shift = tile.gpf == 2 ? 1 : 0;
-        const bool load_state = tile.flags & kTileLoadState;
-        const bool store_state = tile.flags & kTileStoreState;
-        // Stream state is double-buffered: a launch reads generation g and writes generation g+1, so a
+        // State comes in from HBM (run start) or from the previous tile of this CTA's chain (shared memory),
+        // and goes out to HBM (run end) or to the next tile of the chain; with no input the tile recomputes
+        // a 2-granule halo.
+        const bool load_state = tile.flags & (kTileLoadState | kTileCarryIn);
+        const bool store_state = tile.flags & (kTileStoreState | kTileCarryOut);
+        // Stream state in HBM is double-buffered: a launch reads generation g and writes generation g+1, so a
         // run-starting tile never races with the run-ending tile of the same stream.
         const uint32_t gen = sm.gen_stage[it & 1];
-        const Mp3StreamState* st_in = a.states + (size_t)tile.stream * 2 + (gen & 1);
-        Mp3StreamState* st_out = a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
+        const Mp3StreamState* st_in = (tile.flags & kTileCarryIn) ? &sm.carry : a.states + (size_t)tile.stream * 2 + (gen & 1);
+        Mp3StreamState* st_out = (tile.flags & kTileCarryOut) ? &sm.carry : a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
+        const int j0 = load_state ? 2 : 0; // first granule job of the tile
         const int gseq0 = ((int)tile.first_frame << gpf_shift) + tile.first_gr; // first granule of the tile
 
         // --------------------------------------------------------------------------------------
         // Phase A+B: one warp per granule job j (j = 0, 1: halo granules g0-2, g0-1; j >= 2: the tile),
         // lane = sub-band, everything in registers.  Job j >= 1 owns XT region j-1 (rows 18(j-1)..).
         // --------------------------------------------------------------------------------------
-        const int g = warp; // job index
-        const bool active = g < n + 2 && (g >= 2 || !load_state);
+        const int g = warp + j0; // job index: stage slot g, XT region g - 1
+        const bool active = g < n + 2;
         float sec[2][18];
         if (active) {
             const symgpu_mp3_gc& g0 = sm.units[g][0];
@@ -682,9 +688,9 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
         }
         __syncthreads();  // PHASE: handoff+barriers
         // The stage is free: fetch this CTA's next tile while the current one is in its DCT / window phases.
-        if (threadIdx.x == NW * 32 - 32 && ti + (int)gridDim.x < n_tiles) {
+        if (threadIdx.x == NW * 32 - 32 && ti + 1 < t_end) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_prefetch(ti + gridDim.x, (it + 1) & 1);
+            issue_prefetch(ti + 1, (it + 1) & 1);
         }
         // overlap hand-off: region of job g+1 += second(g); the run's last granule feeds the stream state
         if (active) {
@@ -768,25 +774,32 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
 
 // ---------------------------------------------------------------------------------------------
 int mp3_tile_granules() { return kMp3TileGranules; }
+int mp3_halo_tile_granules() { return kMp3Warps - 2 < kMp3TileGranules ? kMp3Warps - 2 : kMp3TileGranules; }
 
-cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream) {
+int mp3_grid_size(cudaError_t* err) {
     constexpr size_t smem = sizeof(Mp3Smem<kMp3TileGranules, kMp3Warps>);
     static int grid_for_device[64] = {0};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (!grid_for_device[dev & 63]) {
-        e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    if (e == cudaSuccess && !grid_for_device[dev & 63]) {
         int n_sm = 0, per_sm = 0;
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, kMp3Warps * 32, smem);
-        if (e != cudaSuccess) return e;
-        grid_for_device[dev & 63] = n_sm * (per_sm > 0 ? per_sm : 1);
+        e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, kMp3Warps * 32, smem);
+        if (e == cudaSuccess) grid_for_device[dev & 63] = n_sm * (per_sm > 0 ? per_sm : 1);
     }
-    const int grid = a.n_tiles < grid_for_device[dev & 63] ? a.n_tiles : grid_for_device[dev & 63];
-    mp3_synth_kernel<kMp3TileGranules, kMp3Warps><<<grid, kMp3Warps * 32, smem, stream>>>(a);
+    if (err) *err = e;
+    return e == cudaSuccess ? grid_for_device[dev & 63] : 0;
+}
+
+cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream) {
+    constexpr size_t smem = sizeof(Mp3Smem<kMp3TileGranules, kMp3Warps>);
+    cudaError_t e = cudaSuccess;
+    const int max_grid = mp3_grid_size(&e);
+    if (e != cudaSuccess) return e;
+    if (a.n_ctas <= 0 || a.n_ctas > max_grid) return cudaErrorInvalidConfiguration;
+    mp3_synth_kernel<kMp3TileGranules, kMp3Warps><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -10,21 +10,27 @@
 namespace symgpu {
 
 // Granules per tile and warps per CTA.  One persistent CTA of 16 warps per SM (4 per scheduler: 5
-// would cap the kernel at 96 registers because registers are partitioned per scheduler): 13 + 2 halo
-// granule jobs in the hybrid phase; (15 + 234) time slots x 2 channels = 498 DCT jobs for 512
-// threads; 234 slots = 15 per warp in the window phase.  Shared memory: 252 XT rows (66.5 KB) + the
-// TMA stage of 15 granules (71 KB) + scratch.
+// would cap the kernel at 96 registers because registers are partitioned per scheduler).  A CTA walks a
+// CHAIN of consecutive tiles of the same stream and carries overlap + polyphase history from one tile
+// to the next through shared memory, so only the first tile of a chain that starts inside a run pays
+// the 2-granule halo.  14 granule jobs in the hybrid phase (16 with a halo); 252 time slots x 2
+// channels = 504 DCT jobs for 512 threads; 252 slots = 16 per warp in the window phase.  Shared
+// memory: 270 XT rows (71 KB) + the TMA stage of 16 granules (74 KB) + carry (8 KB) + scratch.
 #ifndef SYMGPU_MP3_T
-#define SYMGPU_MP3_T 13
+#define SYMGPU_MP3_T 16
 #define SYMGPU_MP3_NW 16
 #endif
 constexpr int kMp3TileGranules = SYMGPU_MP3_T;
 constexpr int kMp3Warps = SYMGPU_MP3_NW;
 
-enum : uint8_t { kTileLoadState = 1, kTileStoreState = 2 };
+// kTileLoadState / kTileStoreState: the tile starts / ends a run and exchanges state with HBM.
+// kTileCarryIn / kTileCarryOut: the tile continues / is continued by the neighbouring tile of the same
+// CTA's chain and exchanges state through shared memory.  A tile with neither input flag recomputes a
+// 2-granule halo (and then holds at most kMp3TileGranules granules with NW >= n + 2).
+enum : uint8_t { kTileLoadState = 1, kTileStoreState = 2, kTileCarryIn = 4, kTileCarryOut = 8 };
 
-// One CTA's work: `n_granules` consecutive granules of one stream.  Built on the host from the
-// caller's runs (symgpu.cpp: build_tiles).
+// One step of a CTA's work: `n_granules` consecutive granules of one stream.  Built on the host from
+// the caller's runs (symgpu.cpp: build_plan).
 struct Mp3Tile {
     uint32_t first_frame; // batch frame index holding the tile's first granule
     uint32_t stream;      // per-stream state slot
@@ -50,8 +56,10 @@ struct Mp3Args {
     const symgpu_mp3_gc* units;
     const float* spectra;
     float* pcm;
+    const uint32_t* cta_first; // [n_ctas + 1]: CTA b walks tiles cta_first[b] .. cta_first[b + 1] - 1 in order
     const Mp3Tile* tiles;
     int n_tiles;
+    int n_ctas;
     Mp3StreamState* states; // [n_streams][2] double-buffered, see gen
     uint32_t* gen;          // [n_streams] state generation; buffer (gen & 1) is current
     unsigned* done;         // retired-CTA counter (self-resetting)
@@ -61,5 +69,8 @@ struct Mp3Args {
 cudaError_t mp3_upload_const(const Mp3Tables& t, cudaStream_t stream);
 cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream);
 int mp3_tile_granules();
+int mp3_halo_tile_granules(); // limit for a tile that recomputes its halo (two warps go to the halo granules)
+// Persistent grid size of the kernel on the current device (SM count x resident CTAs), <= 0 on error.
+int mp3_grid_size(cudaError_t* err);
 
 } // namespace symgpu

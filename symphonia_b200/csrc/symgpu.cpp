@@ -21,13 +21,23 @@ using namespace symgpu_detail;
 
 namespace {
 
-// Cuts the caller's runs into per-CTA tiles (mp3_kernel.h).  Returns SYMGPU_OK or an argument /
-// limit error; never touches the device.
-symgpu_status build_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
-                          std::vector<Mp3Tile>& out, bool whole_batch = true) {
-    const int T = mp3_tile_granules();
-    uint64_t covered = 0;
-    out.clear();
+// The work plan of one launch, as the kernel reads it: a header of n_ctas + 1 tile indices followed by
+// the tiles (mp3_kernel.h).  The header is padded to whole 16-byte entries so that the tiles stay aligned.
+struct Mp3Plan {
+    std::vector<Mp3Tile> buf; // [header entries][tiles]
+    int hdr = 0;              // header size in Mp3Tile entries
+    int n_tiles = 0;
+    int n_ctas = 0;
+};
+
+// Cuts the caller's runs into CHAINS of tiles, one chain per CTA of the persistent grid: the batch's
+// granules (in run order) are split into n_ctas contiguous shares; inside a share every run segment is
+// cut into equal tiles that hand their state on through shared memory.  Only a segment that starts
+// inside a run recomputes the 2-granule halo.  Returns SYMGPU_OK or an argument / limit error.
+symgpu_status build_plan_for(int grid, uint32_t T, uint32_t n_streams, const symgpu_mp3_run* runs, uint32_t n_runs,
+                             uint32_t n_frames, Mp3Plan& plan, bool whole_batch) {
+    const uint32_t T_halo = (uint32_t)mp3_halo_tile_granules(); // a halo tile spends two of its warps on the halo
+    uint64_t covered = 0, total_gran = 0, plain_tiles = 0;
     for (uint32_t r = 0; r < n_runs; ++r) {
         const symgpu_mp3_run& run = runs[r];
         const int gpf = run.granules_per_frame ? run.granules_per_frame : 2;
@@ -35,62 +45,131 @@ symgpu_status build_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t 
         if (gpf < 1 || gpf > 2 || n_ch < 1 || n_ch > 2 || run.reserved != 0) return SYMGPU_ERR_ARG;
         if (run.n_frames == 0) continue;
         if ((uint64_t)run.first_frame + run.n_frames > n_frames) return SYMGPU_ERR_ARG;
-        if (run.stream >= ctx->n_mp3_streams) return SYMGPU_ERR_LIMIT;
+        if (run.stream >= n_streams) return SYMGPU_ERR_LIMIT;
         covered += run.n_frames;
-        const uint32_t n_gran = run.n_frames * (uint32_t)gpf;
-        // Equal-sized tiles (a 1-granule tail tile would still pay the 2-granule halo).
-        const uint32_t n_t = (n_gran + (uint32_t)T - 1) / (uint32_t)T;
-        uint32_t q0 = 0;
-        for (uint32_t k = 0; k < n_t; ++k) {
-            const uint32_t q1 = (uint32_t)(((uint64_t)n_gran * (k + 1)) / n_t);
-            Mp3Tile t{};
-            t.first_frame = run.first_frame + q0 / (uint32_t)gpf;
-            t.first_gr = (uint16_t)(q0 % (uint32_t)gpf);
-            t.stream = run.stream;
-            t.n_granules = (uint16_t)(q1 - q0);
-            t.gpf = (uint8_t)gpf;
-            t.n_ch = (uint8_t)n_ch;
-            t.flags = (uint8_t)((k == 0 ? kTileLoadState : 0) | (k + 1 == n_t ? kTileStoreState : 0));
-            out.push_back(t);
-            q0 = q1;
-        }
+        const uint64_t n_gran = (uint64_t)run.n_frames * (uint32_t)gpf;
+        total_gran += n_gran;
+        plain_tiles += (n_gran + T - 1) / T;
     }
     if (whole_batch && covered != n_frames) return SYMGPU_ERR_ARG; // runs must tile the batch exactly
+    plan.n_ctas = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(plain_tiles, 1));
+    plan.hdr = (plan.n_ctas + 1 + 3) / 4;
+    plan.buf.assign((size_t)plan.hdr, Mp3Tile{});
+    std::vector<uint32_t> first((size_t)plan.n_ctas + 1, 0);
+
+    uint64_t pos = 0;  // granules of earlier runs
+    int cta = 0;       // share being filled
+    uint32_t n_tiles = 0;
+    // End of share `c` in batch granules; a cut that would leave fewer than 2 granules of a run before
+    // it moves to the run's start (a halo needs two earlier granules of the same run in the batch).
+    auto share_end = [&](int c) { return total_gran * (uint64_t)(c + 1) / (uint64_t)plan.n_ctas; };
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_mp3_run& run = runs[r];
+        if (run.n_frames == 0) continue;
+        const uint32_t gpf = run.granules_per_frame ? run.granules_per_frame : 2;
+        const uint32_t n_ch = run.channels ? run.channels : 2;
+        const uint32_t n_gran = run.n_frames * gpf;
+        uint32_t q0 = 0;
+        while (q0 < n_gran) {
+            // this segment ends at the share boundary or at the end of the run
+            while (cta + 1 < plan.n_ctas && share_end(cta) <= pos + q0) first[(size_t)++cta] = n_tiles;
+            uint32_t q1 = n_gran;
+            if (cta + 1 < plan.n_ctas) {
+                const uint64_t cut = share_end(cta);
+                if (cut < pos + n_gran) {
+                    q1 = (uint32_t)(cut - pos);
+                    if (q1 < q0 + 1) q1 = q0 + 1;
+                    if (q1 < 2) q1 = n_gran < 2 ? n_gran : 2; // keep two granules before any mid-run cut
+                    if (n_gran - q1 < 1) q1 = n_gran;
+                }
+            }
+            const bool halo = q0 != 0;
+            const uint32_t len = q1 - q0;
+            // equal tiles; the first tile of a halo segment is capped at T_halo granules
+            uint32_t n_t = (len + T - 1) / T;
+            if (halo) n_t = len <= T_halo ? 1 : 1 + (len - T_halo + T - 1) / T;
+            const uint32_t head = halo ? std::min(T_halo, (len + n_t - 1) / n_t) : 0; // size of the halo tile
+            uint32_t a0 = q0;
+            for (uint32_t k = 0; k < n_t; ++k) {
+                uint32_t a1;
+                if (!halo) a1 = q0 + (uint32_t)(((uint64_t)len * (k + 1)) / n_t);
+                else if (n_t == 1) a1 = q1;
+                else a1 = q0 + head + (uint32_t)(((uint64_t)(len - head) * k) / (n_t - 1));
+                Mp3Tile t{};
+                t.first_frame = run.first_frame + a0 / gpf;
+                t.first_gr = (uint16_t)(a0 % gpf);
+                t.stream = run.stream;
+                t.n_granules = (uint16_t)(a1 - a0);
+                t.gpf = (uint8_t)gpf;
+                t.n_ch = (uint8_t)n_ch;
+                uint8_t fl = 0;
+                if (k == 0) fl |= halo ? 0 : kTileLoadState;
+                else fl |= kTileCarryIn;
+                if (k + 1 < n_t) fl |= kTileCarryOut;
+                else if (a1 == n_gran) fl |= kTileStoreState;
+                t.flags = fl;
+                plan.buf.push_back(t);
+                ++n_tiles;
+                a0 = a1;
+            }
+            q0 = q1;
+            if (q0 < n_gran) first[(size_t)++cta] = n_tiles; // the rest of the run belongs to the next share
+        }
+        pos += n_gran;
+    }
+    while (cta < plan.n_ctas) first[(size_t)++cta] = n_tiles;
+    plan.n_tiles = (int)n_tiles;
+    std::memcpy(plan.buf.data(), first.data(), first.size() * sizeof(uint32_t));
     return SYMGPU_OK;
 }
 
-symgpu_status ensure_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, int* n_tiles) {
+symgpu_status build_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, Mp3Plan& plan,
+                         bool whole_batch = true) {
+    cudaError_t ce = cudaSuccess;
+    const int grid = mp3_grid_size(&ce);
+    if (ce != cudaSuccess || grid <= 0) return cuda_fail(ctx, ce, "mp3_grid_size");
+    return build_plan_for(grid, (uint32_t)mp3_tile_granules(), ctx->n_mp3_streams, runs, n_runs, n_frames, plan, whole_batch);
+}
+
+// Makes room for `entries` plan entries in the device / pinned host buffers.
+symgpu_status reserve_plan(symgpu_ctx* ctx, size_t entries) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // the previous launch may still read d_tiles; h_tiles is rewritten
+    if (entries <= ctx->tiles_cap) return SYMGPU_OK;
+    if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+    if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
+    ctx->d_tiles = nullptr;
+    ctx->h_tiles = nullptr;
+    ctx->tiles_cap = 0;
+    const size_t cap = entries + entries / 2 + 64;
+    CU(ctx, cudaMalloc(&ctx->d_tiles, cap * sizeof(Mp3Tile)));
+    CU(ctx, cudaMallocHost(&ctx->h_tiles, cap * sizeof(Mp3Tile)));
+    ctx->tiles_cap = cap;
+    return SYMGPU_OK;
+}
+
+// Kernel arguments of a plan whose entries sit at `d_plan`.
+Mp3Args plan_args(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_tiles, int n_ctas, const symgpu_mp3_gc* units,
+                  const float* spectra, float* pcm) {
+    return Mp3Args{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas,
+                   ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
+}
+
+symgpu_status ensure_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames) {
     if (ctx->cached_frames == n_frames && ctx->cached_runs.size() == n_runs &&
-        (n_runs == 0 || std::memcmp(ctx->cached_runs.data(), runs, n_runs * sizeof *runs) == 0)) {
-        *n_tiles = ctx->cached_tiles;
+        (n_runs == 0 || std::memcmp(ctx->cached_runs.data(), runs, n_runs * sizeof *runs) == 0))
         return SYMGPU_OK;
-    }
-    std::vector<Mp3Tile> tiles;
-    symgpu_status s = build_tiles(ctx, runs, n_runs, n_frames, tiles);
+    Mp3Plan plan;
+    symgpu_status s = build_plan(ctx, runs, n_runs, n_frames, plan);
     if (s != SYMGPU_OK) return s;
-    if (tiles.size() > ctx->tiles_cap) {
-        // the previous launch may still be reading the old list
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_tiles) cudaFree(ctx->d_tiles);
-        if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
-        ctx->d_tiles = nullptr;
-        ctx->h_tiles = nullptr;
-        ctx->tiles_cap = 0;
-        const size_t cap = tiles.size() + tiles.size() / 2 + 64;
-        CU(ctx, cudaMalloc(&ctx->d_tiles, cap * sizeof(Mp3Tile)));
-        CU(ctx, cudaMallocHost(&ctx->h_tiles, cap * sizeof(Mp3Tile)));
-        ctx->tiles_cap = cap;
-    } else {
-        CU(ctx, cudaStreamSynchronize(ctx->stream)); // h_tiles is about to be rewritten
-    }
-    if (!tiles.empty()) {
-        std::memcpy(ctx->h_tiles, tiles.data(), tiles.size() * sizeof(Mp3Tile));
-        CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    s = reserve_plan(ctx, plan.buf.size());
+    if (s != SYMGPU_OK) return s;
+    std::memcpy(ctx->h_tiles, plan.buf.data(), plan.buf.size() * sizeof(Mp3Tile));
+    CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, plan.buf.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
     ctx->cached_runs.assign(runs, runs + n_runs);
     ctx->cached_frames = n_frames;
-    ctx->cached_tiles = (int)tiles.size();
-    *n_tiles = ctx->cached_tiles;
+    ctx->cached_tiles = plan.n_tiles;
+    ctx->cached_hdr = plan.hdr;
+    ctx->cached_ctas = plan.n_ctas;
     return SYMGPU_OK;
 }
 
@@ -99,6 +178,21 @@ symgpu_status ensure_tiles(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t
 extern "C" {
 
 int symgpu_abi_version(void) { return SYMGPU_ABI_VERSION; }
+
+// Test hook (not part of include/symgpu.h): the launch plan the host would build for a persistent grid of
+// `grid` CTAs, as n_ctas + 1 chain offsets followed by the tiles (16 bytes each, mp3_kernel.h).  Needs no
+// device.  Returns the number of 16-byte entries, writes at most `cap` of them, *n_ctas / *n_tiles / *hdr
+// describe the layout; 0 on an argument error.
+size_t symgpu_debug_mp3_plan(int grid, uint32_t n_streams, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
+                             void* out, size_t cap, int* n_ctas, int* n_tiles, int* hdr) {
+    Mp3Plan plan;
+    if (build_plan_for(grid, (uint32_t)mp3_tile_granules(), n_streams, runs, n_runs, n_frames, plan, true) != SYMGPU_OK) return 0;
+    if (out) std::memcpy(out, plan.buf.data(), std::min(cap, plan.buf.size()) * sizeof(Mp3Tile));
+    if (n_ctas) *n_ctas = plan.n_ctas;
+    if (n_tiles) *n_tiles = plan.n_tiles;
+    if (hdr) *hdr = plan.hdr;
+    return plan.buf.size();
+}
 
 const char* symgpu_strerror(symgpu_status status) {
     switch (status) {
@@ -247,11 +341,10 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
     if (!ctx || !units || !spectra || !runs || !pcm) return SYMGPU_ERR_ARG;
     if (n_frames == 0) return SYMGPU_OK;
     DeviceGuard guard(ctx->device);
-    int n_tiles = 0;
-    symgpu_status s = ensure_tiles(ctx, runs, n_runs, n_frames, &n_tiles);
+    symgpu_status s = ensure_plan(ctx, runs, n_runs, n_frames);
     if (s != SYMGPU_OK) return s;
-    Mp3Args a{units, spectra, pcm, ctx->d_tiles, n_tiles, ctx->d_mp3_states, ctx->d_mp3_gen,
-              ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
+    if (ctx->cached_tiles == 0) return SYMGPU_OK;
+    const Mp3Args a = plan_args(ctx, ctx->d_tiles, ctx->cached_hdr, ctx->cached_tiles, ctx->cached_ctas, units, spectra, pcm);
     CU(ctx, mp3_launch(a, ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;
@@ -326,40 +419,33 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         }
     }
     const int n_slices = (int)std::min<uint32_t>(symgpu_ctx::kMaxSlices, n_runs);
-    struct Slice { uint32_t r0, r1, f0, f1; int t0, t1; };
+    struct Slice { uint32_t r0, r1, f0, f1; int t0, hdr, n_tiles, n_ctas; };
     std::vector<Slice> slices;
-    std::vector<Mp3Tile> all_tiles, tiles;
+    std::vector<Mp3Tile> all_tiles;
+    Mp3Plan plan;
     uint32_t r = 0;
     for (int i = 0; i < n_slices; ++i) {
         const uint32_t target = (uint32_t)(((uint64_t)n_frames * (i + 1)) / n_slices);
-        Slice sl{r, r, runs[r].first_frame, 0, (int)all_tiles.size(), 0};
+        Slice sl{r, r, runs[r].first_frame, 0, (int)all_tiles.size(), 0, 0, 0};
         while (r < n_runs && (runs[r].first_frame + runs[r].n_frames <= target || sl.r1 == sl.r0)) {
             ++r;
             sl.r1 = r;
         }
         if (i + 1 == n_slices) { r = n_runs; sl.r1 = n_runs; }
         sl.f1 = sl.r1 < n_runs ? runs[sl.r1].first_frame : n_frames;
-        s = build_tiles(ctx, runs + sl.r0, sl.r1 - sl.r0, n_frames, tiles, false);
+        s = build_plan(ctx, runs + sl.r0, sl.r1 - sl.r0, n_frames, plan, false);
         if (s != SYMGPU_OK) return s;
-        all_tiles.insert(all_tiles.end(), tiles.begin(), tiles.end());
-        sl.t1 = (int)all_tiles.size();
-        if (sl.r1 > sl.r0) slices.push_back(sl);
+        all_tiles.insert(all_tiles.end(), plan.buf.begin(), plan.buf.end());
+        sl.hdr = plan.hdr;
+        sl.n_tiles = plan.n_tiles;
+        sl.n_ctas = plan.n_ctas;
+        if (sl.r1 > sl.r0 && sl.n_tiles > 0) slices.push_back(sl);
         if (r >= n_runs) break;
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->cached_runs.clear(); // the cached tile list of the device entry point is about to be replaced
+    s = reserve_plan(ctx, all_tiles.size());
+    if (s != SYMGPU_OK) return s;
+    ctx->cached_runs.clear(); // the cached plan of the device entry point is about to be replaced
     ctx->cached_frames = 0;
-    if (all_tiles.size() > ctx->tiles_cap) {
-        if (ctx->d_tiles) cudaFree(ctx->d_tiles);
-        if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
-        ctx->d_tiles = nullptr;
-        ctx->h_tiles = nullptr;
-        ctx->tiles_cap = 0;
-        const size_t cap = all_tiles.size() * 2 + 64;
-        CU(ctx, cudaMalloc(&ctx->d_tiles, cap * sizeof(Mp3Tile)));
-        CU(ctx, cudaMallocHost(&ctx->h_tiles, cap * sizeof(Mp3Tile)));
-        ctx->tiles_cap = cap;
-    }
     std::memcpy(ctx->h_tiles, all_tiles.data(), all_tiles.size() * sizeof(Mp3Tile));
     CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, all_tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
     for (size_t i = 0; i < slices.size(); ++i) {
@@ -371,8 +457,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
                                 nf * SYMGPU_MP3_FRAME_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
         CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
-        Mp3Args a{d_units, d_spec, d_pcm, ctx->d_tiles + sl.t0, sl.t1 - sl.t0, ctx->d_mp3_states, ctx->d_mp3_gen,
-                  ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
+        const Mp3Args a = plan_args(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, d_units, d_spec, d_pcm);
         CU(ctx, mp3_launch(a, ctx->stream));
         ctx->launches += 1;
         CU(ctx, pack(sl.f0, (uint32_t)nf));
