@@ -314,6 +314,17 @@ symgpu_status symgpu_mp3_synth_host_packed(symgpu_ctx* ctx, const symgpu_mp3_gc*
                                            const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
                                            int format, void* out);
 
+/* The same synthesis fed with the QUANTISED spectra, i.e. what the Huffman stage decodes before the
+ * reference turns it into f32 (read_huffman_samples: buf[i] = sign * POW43[x],
+ * symphonia-bundle-mp3/src/layer3/requantize.rs:23-32, :128, :144):
+ *   quant [n_frames][2][2][576] int16, |q| <= 8206, exactly 0 from rzero on;
+ * the POW43 lookup runs on the device, so half the bytes cross PCIe on the way in.
+ * format < 0: planar f32 PCM [n_frames][2][1152] as symgpu_mp3_synth_host; otherwise interleaved samples
+ * of `format` as symgpu_mp3_synth_host_packed. */
+symgpu_status symgpu_mp3_synth_host_quantized(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const int16_t* quant,
+                                              const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
+                                              int format, void* out);
+
 #ifdef __cplusplus
 }
 #endif

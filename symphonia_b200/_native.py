@@ -128,6 +128,8 @@ def lib():
     L.symgpu_pcm_pack_host.argtypes = [vp, vp, sz, vp, u32, u32, u32, u32, ctypes.c_int, vp, sz]
     L.symgpu_mp3_synth_host_packed.restype = ctypes.c_int
     L.symgpu_mp3_synth_host_packed.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
+    L.symgpu_mp3_synth_host_quantized.restype = ctypes.c_int
+    L.symgpu_mp3_synth_host_quantized.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
     _LIB = L
     return L
 

@@ -23,61 +23,198 @@ constexpr int kAacThreads = 64;
 constexpr int P0 = 512 - 64, P1 = 512 + 64; // SHORT_WIN_POINT0/1, aac/dsp.rs:19-20
 
 // ---- TNS ------------------------------------------------------------------------------------
-// coeffs[i] -= coeffs[i -/+ (j+1)] * lpc[j], j ascending, in place (tns.rs:183-196).  The last ORDER
-// outputs live in registers; the `j < m` guard reproduces `order.min(m)` for the first lines.
+// coeffs[i] -= coeffs[i -/+ (j+1)] * lpc[j], j ascending, in place (tns.rs:183-196): an all-pole recurrence
+// along frequency, serial per filter (one product on the previous output, then ORDER dependent
+// subtractions per line).  Filters are independent of each other, so the pre-pass packs one filter per LANE:
+//   aac_tns_prepare  copies the spectra of the channel-frames that carry filters into the scratch buffer
+//                    and records, for every filter, the channel-frame it belongs to;
+//   aac_tns_sort     counting sort of the filter indices by order, so that the lanes of a warp run the
+//                    same instantiation;
+//   aac_tns_apply    lane = filter, in place in the scratch buffer.
+// The filterbank kernel then reads those channel-frames from the scratch buffer.
+// One line with the full history (GUARD = false) or, for the first lines of a filter, with the `order.min(m)`
+// terms the reference uses (tns.rs:187, :193; subtracting a zero product instead would turn a -0.0 input into
+// +0.0 when the coefficient is negative).  h[j] = the output j + 1 lines back.
+template <int ORDER, bool GUARD>
+__device__ __forceinline__ float tns_line(float v, int m, float (&h)[20], const float (&lpc)[20]) {
+#pragma unroll
+    for (int j = 0; j < ORDER; ++j)
+        if (!GUARD || j < m) v -= h[j] * lpc[j];
+#pragma unroll
+    for (int j = ORDER - 1; j > 0; --j) h[j] = h[j - 1];
+    h[0] = v;
+    return v;
+}
+
+// `cnt` consecutive lines of one filter, held in a column of the warp's tile (row stride 33 floats).
 template <int ORDER>
-__device__ __forceinline__ void tns_filter(float* c, int start, int end, bool down, const float* __restrict__ lpc_g) {
-    float lpc[ORDER], h[ORDER];
+__device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h)[20], const float (&lpc)[20]) {
+    int k = 0;
+    for (; k < cnt && m0 + k < ORDER; ++k) col[33 * k] = tns_line<ORDER, true>(col[33 * k], m0 + k, h, lpc);
+    for (; k + 4 <= cnt; k += 4) { // four lines per trip: the loads are issued together
+        float x[4];
 #pragma unroll
-    for (int j = 0; j < ORDER; ++j) {
-        lpc[j] = lpc_g[j];
-        h[j] = 0.0f;
+        for (int u = 0; u < 4; ++u) x[u] = col[33 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = tns_line<ORDER, false>(x[u], 0, h, lpc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) col[33 * (k + u)] = x[u];
     }
-    const int len = end - start;
-    for (int m = 0; m < len; ++m) {
-        const int i = down ? end - 1 - m : start + m;
-        float v = c[i];
-#pragma unroll
-        for (int j = 0; j < ORDER; ++j)
-            if (j < m) v -= h[j] * lpc[j];
-#pragma unroll
-        for (int j = ORDER - 1; j > 0; --j) h[j] = h[j - 1];
-        h[0] = v;
-        c[i] = v;
-    }
+    for (; k < cnt; ++k) col[33 * k] = tns_line<ORDER, false>(col[33 * k], 0, h, lpc);
 }
 
-__device__ void tns_dispatch(float* c, const symgpu_aac_tns& f) {
-    const int start = f.start, end = f.end;
-    const bool down = f.direction != 0;
-    switch (f.order) {
-#define TNS_CASE(N) case N: tns_filter<N>(c, start, end, down, f.lpc); break;
-        TNS_CASE(1) TNS_CASE(2) TNS_CASE(3) TNS_CASE(4) TNS_CASE(5) TNS_CASE(6) TNS_CASE(7) TNS_CASE(8) TNS_CASE(9)
-        TNS_CASE(10) TNS_CASE(11) TNS_CASE(12) TNS_CASE(13) TNS_CASE(14) TNS_CASE(15) TNS_CASE(16) TNS_CASE(17)
-        TNS_CASE(18) TNS_CASE(19) TNS_CASE(20)
-#undef TNS_CASE
-        default: break;
-    }
-}
-
-// One warp per channel-frame; lanes = filters of that channel (their line ranges are disjoint).
-__global__ void __launch_bounds__(256) aac_tns_kernel(const symgpu_aac_unit* __restrict__ units,
-                                                      const symgpu_aac_tns* __restrict__ tns, const float* __restrict__ coeffs,
-                                                      float* __restrict__ scratch, uint32_t n_units) {
-    __shared__ float buf[8][1024];
+// One warp per channel-frame: copy the spectra that carry filters, note the owner of each filter.
+__global__ void __launch_bounds__(256) aac_tns_prepare(const symgpu_aac_unit* __restrict__ units, const float* __restrict__ coeffs,
+                                                       float* __restrict__ scratch, uint32_t* __restrict__ owner, uint32_t n_units,
+                                                       uint32_t n_tns) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t u = blockIdx.x * 8 + warp;
     if (u >= n_units) return;
     const symgpu_aac_unit unit = units[u];
     if (unit.n_tns == 0) return;
-    float* c = buf[warp];
     const float4* src = reinterpret_cast<const float4*>(coeffs + (size_t)u * 1024);
-    for (int i = lane; i < 256; i += 32) reinterpret_cast<float4*>(c)[i] = __ldg(src + i);
-    __syncwarp();
-    for (int f = lane; f < unit.n_tns; f += 32) tns_dispatch(c, tns[unit.tns_first + f]);
-    __syncwarp();
     float4* dst = reinterpret_cast<float4*>(scratch + (size_t)u * 1024);
-    for (int i = lane; i < 256; i += 32) dst[i] = reinterpret_cast<float4*>(c)[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[lane + 32 * i] = __ldg(src + lane + 32 * i);
+    for (uint32_t f = lane; f < unit.n_tns; f += 32)
+        if (unit.tns_first + f < n_tns) owner[unit.tns_first + f] = u;
+}
+
+// Counting sort of filter indices by order (one CTA; a batch holds a few thousand filters).  Lanes that hold
+// the same order are found with match.any and send ONE shared-memory atomic per group; the orders are read
+// eight at a time so that the strided global loads overlap.
+__global__ void __launch_bounds__(1024) aac_tns_sort(const symgpu_aac_tns* __restrict__ tns, uint32_t n_tns, uint32_t* __restrict__ sorted) {
+    __shared__ uint32_t bin[32];
+    const unsigned lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) bin[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n_pad = (n_tns + 31u) & ~31u; // whole warps enter the collectives
+    // Batches of 8 * blockDim filters; the orders of a batch stay in registers between the two passes when the
+    // whole list is one batch (the usual case), otherwise they are read again.
+    const bool one_batch = n_pad <= 8 * blockDim.x;
+    int keep[8];
+    for (int pass = 0; pass < 2; ++pass) {
+        for (uint32_t f0 = threadIdx.x; f0 < n_pad; f0 += 8 * blockDim.x) {
+            int o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t f = f0 + k * blockDim.x;
+                if (pass == 1 && one_batch) o[k] = keep[k];
+                else o[k] = f < n_tns ? min((int)tns[f].order, 30) : 31;
+                keep[k] = o[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t f = f0 + k * blockDim.x;
+                if (f - lane >= n_pad) continue; // warp-uniform
+                const unsigned peers = __match_any_sync(0xffffffffu, o[k]);
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&bin[o[k]], (uint32_t)__popc(peers));
+                if (pass == 1) {
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (f < n_tns) sorted[base + __popc(peers & ((1u << lane) - 1u))] = f;
+                }
+            }
+        }
+        __syncthreads();
+        if (pass == 0 && threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int b = 0; b < 32; ++b) {
+                const uint32_t n = bin[b];
+                bin[b] = acc;
+                acc += n;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// A warp takes kTnsPerWarp consecutive entries of the order-sorted list, one filter per lane (the recurrence is
+// serial, so a scheduler needs several such warps to stay busy: 8 filters per warp gives ~1.5 warps per
+// scheduler on this batch), in place in the scratch buffer.  The lines are moved between global and shared
+// memory by the whole warp, 32 lines of every filter per round: for filter j the lanes fetch 32 consecutive
+// lines (one coalesced request), and the fetch of round r+1 overlaps the recurrences of round r.
+constexpr int kTnsWarps = 4;
+constexpr int kTnsPerWarp = 8;
+__global__ void __launch_bounds__(kTnsWarps * 32) aac_tns_apply(const symgpu_aac_tns* __restrict__ tns, const uint32_t* __restrict__ sorted,
+                                                                const uint32_t* __restrict__ owner, float* __restrict__ scratch,
+                                                                uint32_t n_tns, uint32_t n_units) {
+    __shared__ float tile_s[kTnsWarps][32 * 33];
+    __shared__ float* first_s[kTnsWarps][kTnsPerWarp]; // address of each filter's first line (in processing order)
+    __shared__ int len_s[kTnsWarps][kTnsPerWarp];      // lines, negated when the filter runs downwards
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = tile_s[warp];
+    const uint32_t i = (blockIdx.x * kTnsWarps + warp) * kTnsPerWarp + lane;
+    int len = 0, order = 0;
+    bool down = false;
+    float* first = scratch;
+    float lpc[20], h[20];
+#pragma unroll
+    for (int j = 0; j < 20; ++j) lpc[j] = h[j] = 0.0f;
+    if (lane < kTnsPerWarp && i < n_tns) {
+        const uint32_t f = sorted[i];
+        const uint32_t u = owner[f];
+        const symgpu_aac_tns* t = tns + f;
+        int start = t->start, end = t->end;
+        if (end > 1024) end = 1024; // a malformed filter must not leave its channel-frame
+        order = t->order;
+        if (u < n_units && start < end && order >= 1 && order <= 20) {
+            len = end - start;
+            down = t->direction != 0;
+            first = scratch + (size_t)u * 1024 + (down ? end - 1 : start);
+#pragma unroll
+            for (int j = 0; j < 20; ++j)
+                if (j < order) lpc[j] = __ldg(t->lpc + j);
+        }
+    }
+    if (lane < kTnsPerWarp) {
+        first_s[warp][lane] = first;
+        len_s[warp][lane] = down ? -len : len;
+    }
+    int max_len = len;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, d));
+    __syncwarp();
+
+    float r[kTnsPerWarp]; // lines in flight: r[j] = line (round * 32 + lane) of filter j
+    auto fetch = [&](int round) {
+        const int m = round * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < kTnsPerWarp; ++j) {
+            const int lj = len_s[warp][j];
+            r[j] = 0.0f;
+            if (m < abs(lj)) r[j] = first_s[warp][j][lj < 0 ? -m : m];
+        }
+    };
+    fetch(0);
+    for (int round = 0; round * 32 < max_len; ++round) {
+#pragma unroll
+        for (int j = 0; j < kTnsPerWarp; ++j) tile[33 * lane + j] = r[j]; // row = line in the round, column = filter
+        __syncwarp();
+        if ((round + 1) * 32 < max_len) fetch(round + 1);
+        const int m0 = round * 32;
+        const int cnt = min(32, len - m0);
+        if (cnt > 0) {
+            float* col = tile + lane;
+            switch (order) {
+#define TNS_CASE(N) case N: tns_lines<N>(col, cnt, m0, h, lpc); break;
+                TNS_CASE(1) TNS_CASE(2) TNS_CASE(3) TNS_CASE(4) TNS_CASE(5) TNS_CASE(6) TNS_CASE(7) TNS_CASE(8) TNS_CASE(9)
+                TNS_CASE(10) TNS_CASE(11) TNS_CASE(12) TNS_CASE(13) TNS_CASE(14) TNS_CASE(15) TNS_CASE(16) TNS_CASE(17)
+                TNS_CASE(18) TNS_CASE(19) TNS_CASE(20)
+#undef TNS_CASE
+                default: break;
+            }
+        }
+        __syncwarp();
+        const int m = m0 + lane;
+#pragma unroll
+        for (int j = 0; j < kTnsPerWarp; ++j) {
+            const int lj = len_s[warp][j];
+            if (m < abs(lj)) first_s[warp][j][lj < 0 ? -m : m] = tile[33 * lane + j];
+        }
+        __syncwarp();
+    }
 }
 
 // ---- filterbank --------------------------------------------------------------------------------
@@ -97,6 +234,8 @@ struct alignas(16) AacTabSmem {
     float2 fft[8 + 16 + 480]; // FftTables prefix: lit16, lit32, merge tables of sizes 64..512
     float2 tw_long[512];
     float2 tw_short[64];
+    float win_long[2][1024];  // [0] sine, [1] KBD (window_shape)
+    float win_short[2][128];
 };
 
 // delay[i] after a frame with IMDCT output `out` (aac/dsp.rs:131-157) -- what the NEXT frame overlaps with.
@@ -109,24 +248,26 @@ __device__ __forceinline__ float aac_new_delay(int seq, const float* out, const 
 __device__ __forceinline__ float aac_pcm_short(const float* out, const float* __restrict__ sw,
                                                const float* __restrict__ psw, int x) {
     const int w = x >> 7, i = x & 127;
-    if (w == 0) return out[i] * __ldg(psw + i);
-    const float t2 = out[256 * (w - 1) + 128 + i] * __ldg(sw + 127 - i);
+    if (w == 0) return out[i] * psw[i];
+    const float t2 = out[256 * (w - 1) + 128 + i] * sw[127 - i];
     const float prev = (w == 1) ? t2 : 0.0f + t2;
     if (w == 8) return prev;
-    return prev + out[256 * w + i] * __ldg(sw + i);
+    return prev + out[256 * w + i] * sw[i];
 }
 
 __device__ __forceinline__ float aac_new_delay(int seq, const float* out, const float* __restrict__ lw,
                                                const float* __restrict__ sw, const float* __restrict__ psw, int i) {
     switch (seq) {
         case SYMGPU_AAC_ONLY_LONG:
-        case SYMGPU_AAC_LONG_STOP: return out[i + 1024] * __ldg(lw + 1023 - i);
+        case SYMGPU_AAC_LONG_STOP: return out[i + 1024] * lw[1023 - i];
         case SYMGPU_AAC_EIGHT_SHORT: return i < P1 ? aac_pcm_short(out, sw, psw, i + 512 + 64) : 0.0f;
         default: // LONG_START
-            return i < P0 ? out[i + 1024] : i < P1 ? out[i + 1024] * __ldg(sw + 127 - (i - P0)) : 0.0f;
+            return i < P0 ? out[i + 1024] : i < P1 ? out[i + 1024] * sw[127 - (i - P0)] : 0.0f;
     }
 }
 
+// Persistent: gridDim.x CTAs (two per SM) walk the chunks blockIdx.x, blockIdx.x + gridDim.x, ...; the twiddle
+// and window tables are staged in shared memory once per CTA.
 __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs a) {
     extern __shared__ __align__(16) unsigned char aac_raw[];
     AacFrameSmem* fs = reinterpret_cast<AacFrameSmem*>(aac_raw);
@@ -134,8 +275,6 @@ __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs 
     __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int grp = tid >> 6, gt = tid & 63; // frame slot of this thread, thread within the slot's group
-    const CodecChunk ck = a.chunks[blockIdx.x];
-    const int ch = ck.channel;
     const CodecTables* __restrict__ tab = a.tab;
     {
         const float2* g_fft = reinterpret_cast<const float2*>(tab->fft_lit16);
@@ -144,80 +283,104 @@ __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs 
         for (int i = tid; i < 504; i += blockDim.x) ts.fft[i] = __ldg(g_fft + i);
         for (int i = tid; i < 512; i += blockDim.x) ts.tw_long[i] = __ldg(g_twl + i);
         if (tid < 64) ts.tw_short[tid] = __ldg(g_tws + tid);
+        for (int i = tid; i < 1024; i += blockDim.x) {
+            ts.win_long[0][i] = __ldg(tab->aac_sine_long + i);
+            ts.win_long[1][i] = __ldg(tab->aac_kbd_long + i);
+        }
+        if (tid < 128) {
+            ts.win_short[0][tid] = __ldg(tab->aac_sine_short + tid);
+            ts.win_short[1][tid] = __ldg(tab->aac_kbd_short + tid);
+        }
     }
     __syncthreads();
     const FftTables* ft = reinterpret_cast<const FftTables*>(ts.fft);
-    const uint32_t gen = a.gen[ck.stream];
-    const float* st_in = a.states + (((size_t)ck.stream * 2 + (gen & 1)) * 2 + ch) * 1024;
-    float* st_out = a.states + (((size_t)ck.stream * 2 + ((gen + 1) & 1)) * 2 + ch) * 1024;
-    const bool load_state = ck.flags & kChunkLoadState;
-    const int count = ck.count;
 
-    // slot 0 = the frame before the chunk (or the stream state), slot k = chunk frame k-1
-    const int f = (int)ck.first - 1 + grp;
-    const bool have_frame = grp <= count && (grp > 0 || !load_state);
-    symgpu_aac_unit u = {};
-    if (have_frame) {
-        const size_t unit_idx = 2 * (size_t)f + ch;
-        u = a.units[unit_idx];
-        AacFrameSmem& me = fs[grp];
-        const float* src = (u.n_tns ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
-        for (int i = gt; i < 256; i += 64) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        NamedSync sync{1 + grp, 64};
-        sync();
-        // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
-        if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-            imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
-        else
-            imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 64, sync);
-    } else if (grp == 0) {
-        // run start: slot 0 holds the delay line itself (stored in out[1024..2048))
-        for (int i = gt; i < 1024; i += 64) fs[0].out[1024 + i] = st_in[i];
-    }
-    __syncthreads();
+    for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
+        const CodecChunk ck = a.chunks[c];
+        const int ch = ck.channel;
+        const uint32_t gen = a.gen[ck.stream];
+        const float* st_in = a.states + (((size_t)ck.stream * 2 + (gen & 1)) * 2 + ch) * 1024;
+        float* st_out = a.states + (((size_t)ck.stream * 2 + ((gen + 1) & 1)) * 2 + ch) * 1024;
+        const bool load_state = ck.flags & kChunkLoadState;
+        const int count = ck.count;
 
-    // window + overlap-add (aac/dsp.rs:103-129): thread = (frame slot, sample)
-    if (grp >= 1 && grp <= count) {
-        const float* out = fs[grp].out;
-        const float* pout = fs[grp - 1].out;
-        const symgpu_aac_unit pu = (grp > 1 || !load_state) ? a.units[2 * (size_t)(f - 1) + ch] : symgpu_aac_unit{};
-        const bool prev_is_state = grp == 1 && load_state;
-        const int seq = u.window_sequence, pseq = pu.window_sequence;
-        const float* sw = u.window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
-        const float* plw = u.prev_window_shape ? tab->aac_kbd_long : tab->aac_sine_long;
-        const float* psw = u.prev_window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
-        // windows of the PREVIOUS frame, for its delay line
-        const float* q_lw = pu.window_shape ? tab->aac_kbd_long : tab->aac_sine_long;
-        const float* q_sw = pu.window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
-        const float* q_psw = pu.prev_window_shape ? tab->aac_kbd_short : tab->aac_sine_short;
-        float* dst = a.pcm + (2 * (size_t)f + ch) * 1024;
-#pragma unroll 4
-        for (int i = gt; i < 1024; i += 64) {
-            const float d = prev_is_state ? pout[1024 + i] : aac_new_delay(pseq, pout, q_lw, q_sw, q_psw, i);
-            float y;
-            switch (seq) {
-                case SYMGPU_AAC_ONLY_LONG:
-                case SYMGPU_AAC_LONG_START: y = d + (out[i] * __ldg(plw + i)); break;
-                case SYMGPU_AAC_EIGHT_SHORT: y = i < P0 ? d : d + aac_pcm_short(out, sw, psw, i - P0); break;
-                default: y = i < P0 ? d : i < P1 ? d + out[i] * __ldg(psw + i - P0) : d + out[i]; break; // LONG_STOP
+        // slot 0 = the frame before the chunk (or the stream state), slot k = chunk frame k-1
+        const int f = (int)ck.first - 1 + grp;
+        const bool have_frame = grp <= count && (grp > 0 || !load_state);
+        symgpu_aac_unit u = {};
+        if (have_frame) {
+            const size_t unit_idx = 2 * (size_t)f + ch;
+            u = a.units[unit_idx];
+            AacFrameSmem& me = fs[grp];
+            const float* src = (u.n_tns ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
+            for (int i = gt; i < 256; i += 64) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            NamedSync sync{1 + grp, 64};
+            sync();
+            // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
+            if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
+                imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
+            else
+                imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 64, sync);
+        } else if (grp == 0) {
+            // run start: slot 0 holds the delay line itself (stored in out[1024..2048))
+            for (int i = gt; i < 1024; i += 64) fs[0].out[1024 + i] = st_in[i];
+        }
+        __syncthreads();
+
+        // Pull the next chunk's spectra towards the SM (HBM -> L2) while this chunk is windowed.
+        if (c + (int)gridDim.x < a.n_chunks && gt < 32) {
+            const CodecChunk nk = a.chunks[c + gridDim.x];
+            const int nf = (int)nk.first - 1 + grp;
+            if (grp <= nk.count && (grp > 0 || !(nk.flags & kChunkLoadState))) {
+                const size_t nidx = 2 * (size_t)nf + nk.channel;
+                const float* nsrc = (a.units[nidx].n_tns ? a.tns_scratch : a.coeffs) + nidx * 1024;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 32 * gt));
             }
-            dst[i] = y;
         }
-        if (grp == count && (ck.flags & kChunkStoreState)) { // the run's last frame leaves its delay line in the state
-            const float* lw = u.window_shape ? tab->aac_kbd_long : tab->aac_sine_long;
-            for (int i = gt; i < 1024; i += 64) st_out[i] = aac_new_delay(seq, out, lw, sw, psw, i);
+
+        // window + overlap-add (aac/dsp.rs:103-129): thread = (frame slot, sample)
+        if (grp >= 1 && grp <= count) {
+            const float* out = fs[grp].out;
+            const float* pout = fs[grp - 1].out;
+            const symgpu_aac_unit pu = (grp > 1 || !load_state) ? a.units[2 * (size_t)(f - 1) + ch] : symgpu_aac_unit{};
+            const bool prev_is_state = grp == 1 && load_state;
+            const int seq = u.window_sequence, pseq = pu.window_sequence;
+            const float* sw = ts.win_short[u.window_shape ? 1 : 0];
+            const float* plw = ts.win_long[u.prev_window_shape ? 1 : 0];
+            const float* psw = ts.win_short[u.prev_window_shape ? 1 : 0];
+            // windows of the PREVIOUS frame, for its delay line
+            const float* q_lw = ts.win_long[pu.window_shape ? 1 : 0];
+            const float* q_sw = ts.win_short[pu.window_shape ? 1 : 0];
+            const float* q_psw = ts.win_short[pu.prev_window_shape ? 1 : 0];
+            float* dst = a.pcm + (2 * (size_t)f + ch) * 1024;
+#pragma unroll 4
+            for (int i = gt; i < 1024; i += 64) {
+                const float d = prev_is_state ? pout[1024 + i] : aac_new_delay(pseq, pout, q_lw, q_sw, q_psw, i);
+                float y;
+                switch (seq) {
+                    case SYMGPU_AAC_ONLY_LONG:
+                    case SYMGPU_AAC_LONG_START: y = d + (out[i] * plw[i]); break;
+                    case SYMGPU_AAC_EIGHT_SHORT: y = i < P0 ? d : d + aac_pcm_short(out, sw, psw, i - P0); break;
+                    default: y = i < P0 ? d : i < P1 ? d + out[i] * psw[i - P0] : d + out[i]; break; // LONG_STOP
+                }
+                dst[i] = y;
+            }
+            if (grp == count && (ck.flags & kChunkStoreState)) { // the run's last frame leaves its delay line in the state
+                const float* lw = ts.win_long[u.window_shape ? 1 : 0];
+                for (int i = gt; i < 1024; i += 64) st_out[i] = aac_new_delay(seq, out, lw, sw, psw, i);
+            }
         }
+        __syncthreads(); // the frame slots are reused by the next chunk
     }
 
     // launch epilogue: the last CTA publishes the new state generation (see mp3_kernel.cu)
-    __syncthreads();
     if (tid == 0) {
         __threadfence();
         is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (is_last) {
-        for (unsigned i = tid; i < gridDim.x; i += blockDim.x)
+        for (int i = tid; i < a.n_chunks; i += blockDim.x)
             if ((a.chunks[i].flags & kChunkStoreState) && a.chunks[i].channel == 0) a.gen[a.chunks[i].stream] += 1;
         if (tid == 0) *a.done = 0;
     }
@@ -227,18 +390,29 @@ __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs 
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, cudaStream_t stream) {
     if (any_tns) {
-        aac_tns_kernel<<<(n_units + 7) / 8, 256, 0, stream>>>(a.units, a.tns, a.coeffs, a.tns_scratch_rw, n_units);
-        cudaError_t e = cudaGetLastError();
+        // owner[] starts at "no owner" so that filters outside every channel-frame's range are skipped
+        cudaError_t e = cudaMemsetAsync(a.tns_owner, 0xff, (size_t)a.n_tns * sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+        aac_tns_sort<<<1, 1024, 0, stream>>>(a.tns, a.n_tns, a.tns_sorted);
+        aac_tns_prepare<<<(n_units + 7) / 8, 256, 0, stream>>>(a.units, a.coeffs, a.tns_scratch_rw, a.tns_owner, n_units, a.n_tns);
+        aac_tns_apply<<<(a.n_tns + kTnsWarps * kTnsPerWarp - 1) / (kTnsWarps * kTnsPerWarp), kTnsWarps * 32, 0, stream>>>(a.tns, a.tns_sorted, a.tns_owner, a.tns_scratch_rw, a.n_tns, n_units);
+        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     constexpr size_t smem = (kAacK + 1) * sizeof(AacFrameSmem) + sizeof(AacTabSmem);
-    static bool configured = false;
-    if (!configured) {
+    static int max_grid = 0;
+    if (!max_grid) {
         cudaError_t e = cudaFuncSetAttribute(aac_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int dev = 0, n_sm = 0, per_sm = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aac_synth_kernel, (kAacK + 1) * 64, smem)) != cudaSuccess) return e;
+        max_grid = n_sm * (per_sm > 0 ? per_sm : 1);
     }
-    aac_synth_kernel<<<n_chunks, (kAacK + 1) * 64, smem, stream>>>(a);
+    AacArgs b = a;
+    b.n_chunks = n_chunks;
+    aac_synth_kernel<<<n_chunks < max_grid ? n_chunks : max_grid, (kAacK + 1) * 64, smem, stream>>>(b);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,10 @@ struct AacArgs {
     const float* coeffs;
     const float* tns_scratch;   // same buffer as tns_scratch_rw, read side
     float* tns_scratch_rw;
+    uint32_t* tns_sorted;       // [n_tns] filter indices ordered by filter order
+    uint32_t* tns_owner;        // [n_tns] channel-frame of each filter
+    uint32_t n_tns;
+    int n_chunks;               // filled in by aac_launch
     float* pcm;
     const CodecChunk* chunks;
     float* states;              // [n_streams][2 generations][2 channels][1024]
@@ -39,6 +43,15 @@ struct AacArgs {
     unsigned* done;
     const CodecTables* tab;
 };
+
+// Per floor-1 setup, computed on the host when the setup is registered: post i (>= 2) depends on its two
+// neighbours among the earlier posts; level[i] = 1 + max(level[low[i]], level[high[i]]), level[0] = level[1] = 0.
+struct FloorAux {
+    uint8_t level[65];
+    uint8_t max_level;
+    uint8_t pad[6];
+};
+static_assert(sizeof(FloorAux) == 72, "FloorAux is 72 bytes");
 
 struct VorbisArgs {
     const symgpu_vorbis_unit* units;
@@ -48,6 +61,7 @@ struct VorbisArgs {
     const CodecChunk* chunks;
     const symgpu_vorbis_stream* streams;
     const symgpu_vorbis_floor1* floors;
+    const FloorAux* floor_aux;
     uint32_t n_floors;
     uint32_t slot;              // floats per channel slot in residue / pcm
     float* states;              // [n_streams][2 generations][kVorbisStateFloats]

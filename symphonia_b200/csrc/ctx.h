@@ -33,7 +33,8 @@ struct symgpu_ctx {
     void* d_stage = nullptr;
     size_t stage_cap = 0;
     // copy pipeline of the host entry points: H2D on copy_in, kernels on `stream`, D2H on copy_out
-    static constexpr int kMaxSlices = 8;
+    static constexpr int kMaxSlices = 32;
+    int n_slices = 8; // slices of a host batch in the copy pipeline (SYMGPU_SLICES overrides, for tuning)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
     // ---- AAC / Vorbis ----
@@ -46,9 +47,12 @@ struct symgpu_ctx {
     uint32_t n_aac_streams = 0;
     float* d_aac_scratch = nullptr;  // TNS output, same shape as the batch spectra
     size_t aac_scratch_cap = 0;
+    uint32_t* d_aac_tns_idx = nullptr; // [2][cap]: filter indices sorted by order, owner of each filter
+    size_t aac_tns_idx_cap = 0;
     symgpu_vorbis_stream* d_vorbis_streams = nullptr;
     std::vector<symgpu_vorbis_stream> h_vorbis_streams;
     symgpu_vorbis_floor1* d_vorbis_floors = nullptr;
+    symgpu::FloorAux* d_vorbis_floor_aux = nullptr;
     uint32_t n_vorbis_floors = 0;
     float* d_vorbis_states = nullptr; // [n][2 gen][kVorbisStateFloats]
     uint32_t* d_vorbis_gen = nullptr;

@@ -341,7 +341,7 @@ struct Mp3Smem {
 } // namespace
 
 template <int T, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) mp3_synth_kernel(Mp3Args a) {
+__global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) {
     static_assert(NW >= T, "one warp per granule job (a tile with a halo holds NW - 2 granules)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = Mp3Smem<T, NW>;

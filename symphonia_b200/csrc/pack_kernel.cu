@@ -113,7 +113,36 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     }
 }
 
+// Quantised spectra -> f32: value = sign(q) * POW43[|q|] (requantize.rs:23-32, :128, :144), eight lines per
+// thread.  q = 0 gives +0.0, as read_huffman_samples does (requantize.rs:131-133).
+__global__ void __launch_bounds__(256) dequant_kernel(const int4* __restrict__ q8, float4* __restrict__ out, size_t n8,
+                                                      const float* __restrict__ pow43) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 w = __ldg(q8 + i);
+        const int words[4] = {w.x, w.y, w.z, w.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lo = (int)(short)(words[k] & 0xffff), hi = words[k] >> 16;
+            const float a = __ldg(pow43 + min(abs(lo), 8207)), b = __ldg(pow43 + min(abs(hi), 8207));
+            v[2 * k] = lo < 0 ? -a : a;
+            v[2 * k + 1] = hi < 0 ? -b : b;
+        }
+        out[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        out[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
 } // namespace
+
+cudaError_t dequant_launch(const int16_t* q, float* spectra, size_t n, const float* pow43, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (n % 8) return cudaErrorInvalidValue;
+    const size_t n8 = n / 8;
+    const unsigned grid = (unsigned)((n8 + 255) / 256 < 148u * 16u ? (n8 + 255) / 256 : 148u * 16u);
+    dequant_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const int4*>(q), reinterpret_cast<float4*>(spectra), n8, pow43);
+    return cudaGetLastError();
+}
 
 cudaError_t pack_launch(const PackArgs& a, int format, cudaStream_t stream) {
     if (a.n_spans == 0) return cudaSuccess;

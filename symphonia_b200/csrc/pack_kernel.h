@@ -19,5 +19,7 @@ struct PackArgs {
 };
 
 cudaError_t pack_launch(const PackArgs& a, int format, cudaStream_t stream);
+// spectra[i] = sign(q[i]) * pow43[|q[i]|] for n values (n a multiple of 8, both pointers 16-byte aligned).
+cudaError_t dequant_launch(const int16_t* q, float* spectra, size_t n, const float* pow43, cudaStream_t stream);
 
 } // namespace symgpu

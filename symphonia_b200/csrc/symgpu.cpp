@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -254,6 +255,10 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
     symgpu_ctx* ctx = new (std::nothrow) symgpu_ctx();
     if (!ctx) return SYMGPU_ERR_LIMIT;
     ctx->device = device;
+    if (const char* env = std::getenv("SYMGPU_SLICES")) {
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= symgpu_ctx::kMaxSlices) ctx->n_slices = v;
+    }
     DeviceGuard guard(device);
     auto fail = [&](cudaError_t err, const char* where) {
         std::fprintf(stderr, "symgpu: %s failed: %s\n", where, cudaGetErrorString(err));
@@ -285,8 +290,10 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (ctx->d_aac_states) cudaFree(ctx->d_aac_states);
     if (ctx->d_aac_gen) cudaFree(ctx->d_aac_gen);
     if (ctx->d_aac_scratch) cudaFree(ctx->d_aac_scratch);
+    if (ctx->d_aac_tns_idx) cudaFree(ctx->d_aac_tns_idx);
     if (ctx->d_vorbis_streams) cudaFree(ctx->d_vorbis_streams);
     if (ctx->d_vorbis_floors) cudaFree(ctx->d_vorbis_floors);
+    if (ctx->d_vorbis_floor_aux) cudaFree(ctx->d_vorbis_floor_aux);
     if (ctx->d_vorbis_states) cudaFree(ctx->d_vorbis_states);
     if (ctx->d_vorbis_gen) cudaFree(ctx->d_vorbis_gen);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -352,12 +359,15 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
 
 } // extern "C"
 
+static inline float* d_spec_base(char* stage_base) { return reinterpret_cast<float*>(stage_base); }
+
 // Host-buffer MP3 synthesis.  format < 0: planar f32 into `out` (the AudioBuffer layout); otherwise the
 // output stage runs on the device after each slice's kernel and `out` receives interleaved samples.
-static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
+static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra, const int16_t* quant,
                                          const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, int format,
                                          void* out) {
-    if (!ctx || !units || !spectra || !runs || !out) return SYMGPU_ERR_ARG;
+    // exactly one of `spectra` (f32) and `quant` (i16, expanded on the device) describes the input
+    if (!ctx || !units || (!spectra == !quant) || !runs || !out) return SYMGPU_ERR_ARG;
     const size_t sample_bytes = format < 0 ? sizeof(float) : symgpu_sample_bytes(format);
     if (sample_bytes == 0) return SYMGPU_ERR_ARG;
     if (n_frames == 0) return SYMGPU_OK;
@@ -365,9 +375,20 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     const size_t unit_bytes = (size_t)n_frames * 4 * sizeof(symgpu_mp3_gc);
     const size_t spec_bytes = (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
     const size_t packed_bytes = format < 0 ? 0 : (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sample_bytes;
-    symgpu_status s = ensure_stage(ctx, unit_bytes + 2 * spec_bytes + packed_bytes);
+    const size_t quant_bytes = quant ? spec_bytes / 2 : 0;
+    symgpu_status s = ensure_stage(ctx, unit_bytes + 2 * spec_bytes + packed_bytes + quant_bytes);
     if (s != SYMGPU_OK) return s;
     char* base = static_cast<char*>(ctx->d_stage);
+    int16_t* d_quant = reinterpret_cast<int16_t*>(base + 2 * spec_bytes + unit_bytes + packed_bytes);
+    // H2D copy of frames [f0, f0 + nf): the f32 spectra, or the quantised values followed by their expansion
+    auto copy_in = [&](uint32_t f0, size_t nf, cudaStream_t cs) -> cudaError_t {
+        const size_t off = (size_t)f0 * SYMGPU_MP3_FRAME_FLOATS, cnt = nf * SYMGPU_MP3_FRAME_FLOATS;
+        if (!quant) return cudaMemcpyAsync(d_spec_base(base) + off, spectra + off, cnt * sizeof(float), cudaMemcpyHostToDevice, cs);
+        cudaError_t e = cudaMemcpyAsync(d_quant + off, quant + off, cnt * sizeof(int16_t), cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) return e;
+        ctx->launches += 1;
+        return symgpu::dequant_launch(d_quant + off, d_spec_base(base) + off, cnt, ctx->d_mp3_tab->pow43, cs);
+    };
     float* d_spec = reinterpret_cast<float*>(base);
     float* d_pcm = reinterpret_cast<float*>(base + spec_bytes);
     symgpu_mp3_gc* d_units = reinterpret_cast<symgpu_mp3_gc*>(base + 2 * spec_bytes);
@@ -398,7 +419,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     if (!sorted || n_frames < 512 || n_runs < 2) {
         // small or unsorted batch: one copy in, one launch, one copy out
         CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(d_spec, spectra, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, copy_in(0, n_frames, ctx->stream));
         s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
         if (s != SYMGPU_OK) return s;
         CU(ctx, pack(0, n_frames));
@@ -418,7 +439,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
             CU(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
         }
     }
-    const int n_slices = (int)std::min<uint32_t>(symgpu_ctx::kMaxSlices, n_runs);
+    const int n_slices = (int)std::min<uint32_t>((uint32_t)ctx->n_slices, n_runs);
     struct Slice { uint32_t r0, r1, f0, f1; int t0, hdr, n_tiles, n_ctas; };
     std::vector<Slice> slices;
     std::vector<Mp3Tile> all_tiles;
@@ -453,8 +474,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         const size_t nf = sl.f1 - sl.f0;
         CU(ctx, cudaMemcpyAsync(d_units + (size_t)sl.f0 * 4, units + (size_t)sl.f0 * 4, nf * 4 * sizeof(symgpu_mp3_gc),
                                 cudaMemcpyHostToDevice, ctx->copy_in));
-        CU(ctx, cudaMemcpyAsync(d_spec + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS, spectra + (size_t)sl.f0 * SYMGPU_MP3_FRAME_FLOATS,
-                                nf * SYMGPU_MP3_FRAME_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(ctx, copy_in(sl.f0, nf, ctx->copy_in));
         CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
         const Mp3Args a = plan_args(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, d_units, d_spec, d_pcm);
@@ -475,14 +495,20 @@ extern "C" {
 
 symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
                                     const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, float* pcm) {
-    return mp3_synth_host_impl(ctx, units, spectra, runs, n_runs, n_frames, -1, pcm);
+    return mp3_synth_host_impl(ctx, units, spectra, nullptr, runs, n_runs, n_frames, -1, pcm);
 }
 
 symgpu_status symgpu_mp3_synth_host_packed(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
                                            const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
                                            int format, void* out) {
     if (format < 0) return SYMGPU_ERR_ARG;
-    return mp3_synth_host_impl(ctx, units, spectra, runs, n_runs, n_frames, format, out);
+    return mp3_synth_host_impl(ctx, units, spectra, nullptr, runs, n_runs, n_frames, format, out);
+}
+
+symgpu_status symgpu_mp3_synth_host_quantized(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const int16_t* quant,
+                                              const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
+                                              int format, void* out) {
+    return mp3_synth_host_impl(ctx, units, nullptr, quant, runs, n_runs, n_frames, format, out);
 }
 
 uint32_t symgpu_pcm_span_kept(const symgpu_pcm_span* s) {

@@ -127,10 +127,20 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
         CU(ctx, cudaMalloc(&ctx->d_aac_scratch, spec_bytes));
         ctx->aac_scratch_cap = spec_bytes;
     }
-    AacArgs a{units, tns, coeffs, ctx->d_aac_scratch, ctx->d_aac_scratch, pcm, ctx->d_chunks, ctx->d_aac_states,
-              ctx->d_aac_gen, ctx->d_aac_gen + ctx->n_aac_streams, ctx->d_codec_tab};
+    if (n_tns > ctx->aac_tns_idx_cap) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_aac_tns_idx) cudaFree(ctx->d_aac_tns_idx);
+        ctx->d_aac_tns_idx = nullptr;
+        ctx->aac_tns_idx_cap = 0;
+        const size_t cap = (size_t)n_tns + n_tns / 2 + 256;
+        CU(ctx, cudaMalloc(&ctx->d_aac_tns_idx, 2 * cap * sizeof(uint32_t)));
+        ctx->aac_tns_idx_cap = cap;
+    }
+    AacArgs a{units, tns, coeffs, ctx->d_aac_scratch, ctx->d_aac_scratch,
+              ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0,
+              pcm, ctx->d_chunks, ctx->d_aac_states, ctx->d_aac_gen, ctx->d_aac_gen + ctx->n_aac_streams, ctx->d_codec_tab};
     CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, (int)chunks.size(), ctx->stream));
-    ctx->launches += n_tns ? 2 : 1;
+    ctx->launches += n_tns ? 4 : 1;
     return SYMGPU_OK;
 }
 
@@ -198,19 +208,41 @@ symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_str
 
 symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
     if (!ctx || !floors || n_floors == 0) return SYMGPU_ERR_ARG;
+    // A setup is what Floor1Setup holds after the reference's own checks (floor.rs:300-420): distinct x
+    // positions, sort_order a permutation by ascending x that starts at x = 0, and for every post >= 2 the
+    // nearest lower / higher neighbours among the EARLIER posts.  The kernel divides by x differences and
+    // sweeps the posts by dependency level, so none of this may be taken on trust.
+    std::vector<FloorAux> aux(n_floors);
     for (uint32_t i = 0; i < n_floors; ++i) {
         const symgpu_vorbis_floor1& f = floors[i];
         if (f.multiplier < 1 || f.multiplier > 4 || f.n_posts < 2 || f.n_posts > 65) return SYMGPU_ERR_ARG;
-        for (int k = 0; k < f.n_posts; ++k)
-            if (f.low[k] >= f.n_posts || f.high[k] >= f.n_posts || f.sort_order[k] >= f.n_posts) return SYMGPU_ERR_ARG;
+        bool seen[65] = {false};
+        for (int k = 0; k < f.n_posts; ++k) {
+            if (f.sort_order[k] >= f.n_posts || seen[f.sort_order[k]] || f.x_list[k] > 4096) return SYMGPU_ERR_ARG;
+            seen[f.sort_order[k]] = true;
+            if (k && f.x_list[f.sort_order[k]] <= f.x_list[f.sort_order[k - 1]]) return SYMGPU_ERR_ARG;
+        }
+        if (f.x_list[f.sort_order[0]] != 0) return SYMGPU_ERR_ARG;
+        FloorAux& a = aux[i];
+        std::memset(&a, 0, sizeof a);
+        for (int k = 2; k < f.n_posts; ++k) {
+            const int lo = f.low[k], hi = f.high[k];
+            if (lo >= k || hi >= k || !(f.x_list[lo] < f.x_list[k] && f.x_list[k] < f.x_list[hi])) return SYMGPU_ERR_ARG;
+            a.level[k] = (uint8_t)(1 + std::max(a.level[lo], a.level[hi]));
+            a.max_level = std::max(a.max_level, a.level[k]);
+        }
     }
     DeviceGuard guard(ctx->device);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->d_vorbis_floors) cudaFree(ctx->d_vorbis_floors);
+    if (ctx->d_vorbis_floor_aux) cudaFree(ctx->d_vorbis_floor_aux);
     ctx->d_vorbis_floors = nullptr;
+    ctx->d_vorbis_floor_aux = nullptr;
     ctx->n_vorbis_floors = 0;
     CU(ctx, cudaMalloc(&ctx->d_vorbis_floors, (size_t)n_floors * sizeof *floors));
     CU(ctx, cudaMemcpy(ctx->d_vorbis_floors, floors, (size_t)n_floors * sizeof *floors, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMalloc(&ctx->d_vorbis_floor_aux, (size_t)n_floors * sizeof(FloorAux)));
+    CU(ctx, cudaMemcpy(ctx->d_vorbis_floor_aux, aux.data(), (size_t)n_floors * sizeof(FloorAux), cudaMemcpyHostToDevice));
     ctx->n_vorbis_floors = n_floors;
     return SYMGPU_OK;
 }
@@ -260,7 +292,7 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
     symgpu_status s = upload_chunks(ctx, chunks);
     if (s != SYMGPU_OK) return s;
     VorbisArgs a{units, floor_y, residue, pcm, ctx->d_chunks, ctx->d_vorbis_streams, ctx->d_vorbis_floors,
-                 ctx->n_vorbis_floors, slot, ctx->d_vorbis_states, ctx->d_vorbis_gen,
+                 ctx->d_vorbis_floor_aux, ctx->n_vorbis_floors, slot, ctx->d_vorbis_states, ctx->d_vorbis_gen,
                  ctx->d_vorbis_gen + ctx->n_vorbis_streams, ctx->d_codec_tab};
     CU(ctx, vorbis_launch(a, (int)chunks.size(), max_bs1, ctx->stream));
     ctx->launches += 1;

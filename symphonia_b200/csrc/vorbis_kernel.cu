@@ -11,8 +11,8 @@
 // (double-buffered) stream state instead.  The number of packet slots adapts to the block size
 // (8 slots of 22 KB at blocksize_1 = 2048).
 //
-// Floor step 1 is an integer recurrence over <= 65 posts (one lane per channel); step 2 is evaluated
-// per spectral line in closed form: after d steps of render_line's error accumulator,
+// Floor step 1 is an integer recurrence over <= 65 posts, swept level by level of its dependency forest with
+// one lane per post; step 2 is evaluated per spectral line in closed form: after d steps of render_line's error accumulator,
 //   y(d) = y0 + d*base + sign(dy) * floor(d*ady / adx)
 // which is the same integer the reference's loop reaches, so the table lookup is identical.
 #include <cuda_runtime.h>
@@ -29,99 +29,163 @@ namespace {
 
 constexpr int kVorbisThreads = 64;
 
-struct FloorPoints { // active posts in X order, built by step 1/2 of one channel
-    int x[68];
-    int16_t y[68];
-    int16_t final_y[66]; // step-1 amplitudes (kept in shared memory: indexed dynamically)
+// One segment of the rendered curve: the line from (x0, y0) to the next point.  16 bytes, read as one word group.
+struct alignas(16) FloorSeg {
+    int x0;
+    int16_t y0;
+    int16_t base;   // dy / adx, truncated toward zero (floor.rs:790)
+    int16_t ady;    // |dy| - |base| * adx
+    int16_t adx_s;  // adx, negated when dy < 0
+    float inv;      // ~ 1 / adx: seeds the exact integer division below
+};
+
+struct alignas(16) FloorPoints { // curve of one channel: seg[0 .. n-2] plus a sentinel; built by one warp
+    FloorSeg seg[68];
+    int16_t final_y[66]; // step-1 amplitudes
     int n;
 };
 
-// floor(a / b) for 0 <= a < 2^23, 1 <= b < 2^14, exactly: float estimate + fix-up.
-__device__ __forceinline__ int div_small(int a, int b) {
-    int q = (int)__fdividef((float)a, (float)b); // estimate only (no FFMA sequence); made exact below
-    while (q * b > a) --q;
-    while ((q + 1) * b <= a) ++q;
+// floor(a / b) for 0 <= a < 2^24, 1 <= b <= 2^12, exactly: `inv` ~ 1/b seeds an estimate that is off by at
+// most one (a and the product are exact or within 2^-20 relative), the two tests make it exact.
+__device__ __forceinline__ int div_seeded(int a, int b, float inv) {
+    int q = __float2int_rz(__int2float_rn(a) * inv);
+    if (q * b > a) --q;
+    if ((q + 1) * b <= a) ++q;
     return q;
 }
 
 __device__ __forceinline__ int render_point(int x0, int y0, int x1, int y1, int x) { // floor.rs:776-782
     const int dy = y1 - y0;
     const int adx = x1 - x0;
-    const int off = div_small(abs(dy) * (x - x0), adx);
+    const int off = div_seeded(abs(dy) * (x - x0), adx, __fdividef(1.0f, (float)adx));
     return dy < 0 ? y0 - off : y0 + off;
 }
 
-// Step 1 (floor.rs:568-625) + the sort-order walk of step 2 (floor.rs:627-653): one thread.
-__device__ void floor1_points(const symgpu_vorbis_floor1& s, const uint16_t* __restrict__ fy, int n_half, FloorPoints& out) {
-    unsigned long long flag = 3ull; // floor_step2_flag[0] = [1] = true
+// Floor synthesis step 1 (floor.rs:568-625), the sort-order walk of step 2 (floor.rs:627-653) and the
+// per-segment constants of render_line (floor.rs:785-800), by one warp.
+//   Step 1 is a recurrence over the posts, but post i only needs its two neighbours among the EARLIER posts:
+//   the posts form a dependency forest whose levels the host computed when the setup was registered
+//   (FloorAux.level), so the warp sweeps level by level, one lane per post.
+//   step2_flag[i] ends up true iff post i's own value is non-zero or a LATER post with a non-zero value has
+//   it as a neighbour (later writes only ever set the flag), which is an OR over lanes.
+__device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, const FloorAux& aux, const uint16_t* __restrict__ fy,
+                                             int n_half, FloorPoints& out, int lane) {
     const int count = s.n_posts;
     const int mult = s.multiplier;
     const int range = mult == 1 ? 256 : mult == 2 ? 128 : mult == 3 ? 86 : 64;
     int16_t* final_y = out.final_y;
-    final_y[0] = (int16_t)fy[0];
-    final_y[1] = (int16_t)fy[1];
-    for (int i = 2; i < count; ++i) {
-        const int lo = s.low[i], hi = s.high[i];
-        const int predicted = render_point(s.x_list[lo], final_y[lo], s.x_list[hi], final_y[hi], s.x_list[i]);
-        const int val = fy[i];
-        const int highroom = range - predicted, lowroom = predicted;
-        int fin = predicted;
-        if (val != 0) {
-            const int room = 2 * (highroom < lowroom ? highroom : lowroom);
-            flag |= (1ull << lo) | (1ull << hi) | (1ull << i);
-            if (val >= room) fin = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
-            else fin = (val & 1) ? predicted - ((val + 1) / 2) : predicted + (val / 2);
+    // my posts: i = lane, lane + 32, lane + 64
+    int px[3], plo[3], phi[3], pxlo[3], pxhi[3], pval[3], plvl[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = lane + 32 * k;
+        px[k] = plo[k] = phi[k] = pxlo[k] = pxhi[k] = pval[k] = 0;
+        plvl[k] = 0xff;
+        if (i < count) {
+            px[k] = s.x_list[i];
+            pval[k] = fy[i];
+            if (i >= 2) {
+                plo[k] = s.low[i];
+                phi[k] = s.high[i];
+                pxlo[k] = s.x_list[plo[k]];
+                pxhi[k] = s.x_list[phi[k]];
+                plvl[k] = aux.level[i];
+            } else {
+                final_y[i] = (int16_t)pval[k];
+            }
+        }
+    }
+    __syncwarp();
+    unsigned long long bits = 0ull;
+    const int max_level = aux.max_level;
+    for (int level = 1; level <= max_level; ++level) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (plvl[k] == level) {
+                const int predicted = render_point(pxlo[k], final_y[plo[k]], pxhi[k], final_y[phi[k]], px[k]);
+                const int val = pval[k];
+                const int highroom = range - predicted, lowroom = predicted;
+                int fin = predicted;
+                if (val != 0) {
+                    const int room = 2 * (highroom < lowroom ? highroom : lowroom);
+                    bits |= (1ull << plo[k]) | (1ull << phi[k]) | (1ull << (lane + 32 * k));
+                    if (val >= room) fin = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
+                    else fin = (val & 1) ? predicted - ((val + 1) / 2) : predicted + (val / 2);
+                }
+                final_y[lane + 32 * k] = (int16_t)fin;
+            }
+        }
+        __syncwarp();
+    }
+    const unsigned f_lo = __reduce_or_sync(0xffffffffu, (unsigned)bits) | 3u; // floor_step2_flag[0] = [1] = true
+    const unsigned f_hi = __reduce_or_sync(0xffffffffu, (unsigned)(bits >> 32));
+    const unsigned long long flag = ((unsigned long long)f_hi << 32) | f_lo;
+
+    // points in X order: the flagged posts, amplitudes scaled and clamped (floor.rs:631-648)
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int r = lane + 32 * k;
+        int i = 0;
+        bool on = false;
+        if (r < count) {
+            i = s.sort_order[r];
+            on = (flag >> i) & 1ull;
+        }
+        const unsigned vote = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            FloorSeg& g = out.seg[n + __popc(vote & ((1u << lane) - 1u))];
+            g.x0 = s.x_list[i];
+            g.y0 = (int16_t)min(max((int)final_y[i] * mult, 0), 255);
+        }
+        n += __popc(vote);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const int hx = out.seg[n - 1].x0, hy = out.seg[n - 1].y0;
+        if (hx < n_half) { // render_line(hx, hy, n, hy): a flat tail (floor.rs:650-652)
+            out.seg[n].x0 = n_half;
+            out.seg[n].y0 = (int16_t)hy;
+            out.seg[n + 1].x0 = 0x7fffffff;
         } else {
-            flag &= ~(1ull << i);
+            out.seg[n].x0 = 0x7fffffff; // sentinel for the segment walk
         }
-        final_y[i] = (int16_t)fin;
+        out.n = hx < n_half ? n + 1 : n;
     }
-    int n = 1;
-    int hx = 0, hy = 0;
-    out.x[0] = 0;
-    out.y[0] = (int16_t)min(max((int)final_y[s.sort_order[0]] * mult, 0), 255);
-    for (int k = 1; k < count; ++k) {
-        const int i = s.sort_order[k];
-        if ((flag >> i) & 1ull) {
-            hy = min(max((int)final_y[i] * mult, 0), 255);
-            hx = s.x_list[i];
-            out.x[n] = hx;
-            out.y[n] = (int16_t)hy;
-            ++n;
+    __syncwarp();
+    n = out.n;
+    // per-segment constants
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int sgi = lane + 32 * k;
+        if (sgi + 1 < n) {
+            const int x0 = out.seg[sgi].x0, y0 = out.seg[sgi].y0, x1 = out.seg[sgi + 1].x0, y1 = out.seg[sgi + 1].y0;
+            const int dy = y1 - y0, adx = x1 - x0;
+            const int base = dy / adx;
+            out.seg[sgi].base = (int16_t)base;
+            out.seg[sgi].ady = (int16_t)(abs(dy) - abs(base) * adx);
+            out.seg[sgi].adx_s = (int16_t)(dy < 0 ? -adx : adx);
+            out.seg[sgi].inv = __fdividef(1.0f, (float)adx);
         }
     }
-    if (hx < n_half) { // render_line(hx, hy, n, hy): a flat tail
-        out.x[n] = n_half;
-        out.y[n] = (int16_t)hy;
-        ++n;
-    }
-    out.x[n] = 0x7fffffff; // sentinel for the segment walk
-    out.n = n;
+    __syncwarp();
 }
 
-// Renders the curve for lines x = lane, lane + 32, ... < n_half: each lane walks the segments in
-// ascending x (floor.rs:785-825 in closed form: after d steps of render_line's error accumulator,
+// Renders the curve for lines x = lane, lane + 32, ... < n_half: each lane walks the segments in ascending x
+// (floor.rs:785-825 in closed form: after d steps of render_line's error accumulator,
 // y(d) = y0 + d*base + sign(dy) * floor(d*ady / adx)).
 __device__ __forceinline__ void floor1_render(const FloorPoints& p, int n_half, int lane, float* spec,
                                               const float* __restrict__ inv_db) {
     int seg = 0;
-    int x0 = p.x[0], y0 = p.y[0], x1 = p.x[1], y1 = p.y[1];
-    int dy = y1 - y0, adx = x1 - x0, base = dy / adx, ady = abs(dy) - abs(base) * adx;
+    int x1 = p.seg[1].x0;
     for (int x = lane; x < n_half; x += 32) {
-        while (x >= x1) { // advance to the segment containing x (at most 66 advances per lane in total)
-            ++seg;
-            x0 = x1;
-            y0 = y1;
-            x1 = p.x[seg + 1];
-            y1 = p.y[seg + 1];
-            dy = y1 - y0;
-            adx = x1 - x0;
-            base = dy / adx;
-            ady = abs(dy) - abs(base) * adx;
-        }
+        while (x >= x1) x1 = p.seg[++seg + 1].x0; // at most 66 advances per lane in total
+        const int4 w = *reinterpret_cast<const int4*>(&p.seg[seg]);
+        const int x0 = w.x, y0 = (int)(short)(w.y & 0xffff), base = w.y >> 16;
+        const int ady = (int)(short)(w.z & 0xffff), adx_s = w.z >> 16;
         const int d = x - x0;
-        const int carries = div_small(d * ady, adx);
-        const int y = y0 + d * base + (dy < 0 ? -carries : carries);
+        const int carries = div_seeded(d * ady, abs(adx_s), __int_as_float(w.w));
+        const int y = y0 + d * base + (adx_s < 0 ? -carries : carries);
         spec[x] = __ldg(inv_db + y);
     }
 }
@@ -151,8 +215,9 @@ __device__ void imdct_dispatch(int log2_n2, const float* spec, float* out, float
 // out[2][2*slot_smem] (the spectrum of a channel lives in the first half of its `out` until the
 // pre-twiddle has consumed it) | z | floor points of both channels.
 __host__ __device__ inline size_t vorbis_slot_bytes(int slot_smem) {
-    size_t b = sizeof(float) * 4 * (size_t)slot_smem + sizeof(float2) * zpad_len(slot_smem / 2) + 2 * sizeof(FloorPoints);
-    return (b + 15) & ~(size_t)15;
+    size_t b = sizeof(float) * 4 * (size_t)slot_smem + sizeof(float2) * zpad_len(slot_smem / 2);
+    b = (b + 15) & ~(size_t)15; // the floor points are read 16 bytes at a time
+    return b + 2 * sizeof(FloorPoints);
 }
 
 __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slot_smem) {
@@ -162,7 +227,7 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
     const size_t slot_bytes = vorbis_slot_bytes(slot_smem);
     auto slot_out = [&](int k, int ch) { return reinterpret_cast<float*>(raw + k * slot_bytes) + (size_t)ch * 2 * slot_smem; };
     float2* z = reinterpret_cast<float2*>(reinterpret_cast<float*>(raw + grp * slot_bytes) + 4 * slot_smem);
-    FloorPoints* pts = reinterpret_cast<FloorPoints*>(z + zpad_len(slot_smem / 2));
+    FloorPoints* pts = reinterpret_cast<FloorPoints*>(raw + (grp + 1) * slot_bytes - 2 * sizeof(FloorPoints));
 
     const CodecChunk ck = a.chunks[blockIdx.x];
     const symgpu_vorbis_stream cfg = a.streams[ck.stream];
@@ -192,8 +257,7 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
             float* spec = slot_out(grp, ch);
             const bool used = u.floor[ch] != 0xffff && u.floor[ch] < a.n_floors;
             if (used) {
-                if (lane == 0) floor1_points(a.floors[u.floor[ch]], a.floor_y + ((size_t)p * 2 + ch) * 65, n2, pts[ch]);
-                __syncwarp();
+                floor1_build(a.floors[u.floor[ch]], a.floor_aux[u.floor[ch]], a.floor_y + ((size_t)p * 2 + ch) * 65, n2, pts[ch], lane);
                 floor1_render(pts[ch], n2, lane, spec, tab->vorbis_inverse_db);
             } else {
                 for (int x = lane; x < n2; x += 32) spec[x] = 0.0f; // ch.floor[..n2].fill(0.0)

@@ -124,6 +124,21 @@ class Engine:
                                                            len(runs), n_frames, int(fmt), _np_ptr(out)))
         return out
 
+    def mp3_synth_host_quantized(self, units, quant, runs, fmt=None, out=None):
+        """Like mp3_synth_host / mp3_synth_host_packed, fed with the quantised spectra [F,2,2,576] int16 (value =
+        sign(q) * |q|^(4/3), looked up on the device).  fmt None: planar f32 [F,2,1152]; else interleaved [F*1152,2]."""
+        units, runs, n_frames = self._mp3_args(units, quant, runs)
+        quant = np.ascontiguousarray(quant, dtype=np.int16)
+        if quant.size != n_frames * 2304:
+            raise ValueError("quant must be [n_frames, 2, 2, 576]")
+        if out is None:
+            out = (np.empty((n_frames, 2, 1152), dtype=np.float32) if fmt is None
+                   else np.empty((n_frames * 1152, 2), dtype=FMT_NUMPY[fmt]))
+        self._check(self._lib.symgpu_mp3_synth_host_quantized(self._ctx, _np_ptr(units), _np_ptr(quant), _np_ptr(runs),
+                                                              len(runs), n_frames, -1 if fmt is None else int(fmt),
+                                                              _np_ptr(out)))
+        return out
+
     # -- output stage -------------------------------------------------------------------------
     def pcm_pack_host(self, pcm, spans, channels, fmt, out_frames, plane_stride=0, frames=0, n_spans=None, out=None):
         """Trim + interleave + convert planar f32 `pcm` (any shape, flat indexing) into [out_frames, channels]

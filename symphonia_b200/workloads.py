@@ -103,6 +103,18 @@ def mp3_batch(n_streams=64, frames_per_stream=128, seed=SEED_BASE + 1, sample_ra
     return units, spectra, runs
 
 
+def mp3_quantize(spectra, pow43=None):
+    """Inverse of read_huffman_samples' table lookup: the int16 q with sign(q) * POW43[|q|] == spectra, exactly."""
+    if pow43 is None:
+        pow43 = _native.mp3_pow43()
+    mag = np.abs(spectra)
+    idx = np.searchsorted(pow43, mag)
+    idx = np.minimum(idx, len(pow43) - 1)
+    if not (pow43[idx] == mag).all():
+        raise ValueError("spectra hold values that are not sign * POW43[q]")
+    return np.where(np.signbit(spectra), -idx, idx).astype(np.int16)
+
+
 def mp3_audio_seconds(n_frames, sample_rate_idx=0):
     rate = [44100, 48000, 32000, 22050, 24000, 16000, 11025, 12000, 8000][sample_rate_idx]
     per_frame = 1152 if sample_rate_idx < 3 else 576

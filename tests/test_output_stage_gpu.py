@@ -110,6 +110,25 @@ def test_mp3_host_packed(engine, oracle, fmt, shape):
         assert mag.max() >= 32767 and (mag < 32767).mean() > 0.05 and (mag > 0).mean() > 0.5
 
 
+@pytest.mark.parametrize("shape", [(3, 20), (16, 40)])
+def test_mp3_host_quantized_input(engine, oracle, shape):
+    """i16 quantised spectra in (POW43 lookup on the device), f32 planar or i16 interleaved out."""
+    from symphonia_b200 import workloads
+    S, F = shape
+    units, spectra, runs = workloads.mp3_batch(S, F, seed=500 + S)
+    quant = workloads.mp3_quantize(spectra)
+    # the device table is the oracle's table (f32 powf of an f32 exponent, requantize.rs:23-32)
+    ref43 = np.array([oracle.oracle_mp3_pow43(int(i)) for i in np.unique(np.abs(quant))], dtype=np.float32)
+    assert (ref43 == workloads._native.mp3_pow43()[np.unique(np.abs(quant))]).all()
+    rc, pcm, _ = _oracle.mp3_batch(oracle, units, spectra, runs, S)
+    assert rc == 0 and np.abs(quant).max() > 100
+    engine.mp3_streams_alloc(S)
+    _same(engine.mp3_synth_host_quantized(units, quant, runs), pcm, "quantised in, f32 out")
+    want16 = _oracle.pcm_pack(oracle, pcm, None, 2, FMT_S16, S * F * 1152, plane_stride=1152, frames=1152, n_spans=S * F)
+    engine.mp3_streams_alloc(S)
+    _same(engine.mp3_synth_host_quantized(units, quant, runs, FMT_S16), want16, "quantised in, i16 out")
+
+
 def test_mixed_corpus_on_one_context(engine, oracle):
     """SURVEY §8d config 5 in miniature: MP3, AAC and Vorbis streams served by one context back to back, twice
     (state carried across calls), and the Vorbis PCM -- variable frames per packet -- packed to i16 with a
