@@ -42,6 +42,9 @@ struct symgpu_ctx {
     symgpu::CodecChunk* d_chunks = nullptr;
     symgpu::CodecChunk* h_chunks = nullptr;
     size_t chunks_cap = 0;
+    // the chunk list on the device is reused while the caller repeats the same runs (tag + raw run bytes)
+    std::vector<unsigned char> chunk_key;
+    int cached_chunks = 0;
     float* d_aac_states = nullptr;   // [n][2 gen][2 ch][1024]
     uint32_t* d_aac_gen = nullptr;   // [n] + retired-CTA counter
     uint32_t n_aac_streams = 0;
@@ -57,6 +60,7 @@ struct symgpu_ctx {
     float* d_vorbis_states = nullptr; // [n][2 gen][kVorbisStateFloats]
     uint32_t* d_vorbis_gen = nullptr;
     uint32_t n_vorbis_streams = 0;
+    uint32_t vorbis_cfg_epoch = 0;   // bumped by streams_set: chunk sizes depend on the stream block sizes
 };
 
 namespace symgpu_detail {

@@ -14,6 +14,16 @@ using namespace symgpu_detail;
 
 namespace {
 
+// Key of a chunk list: which codec built it, from which runs, with which parameters.
+std::vector<unsigned char> chunk_key_of(uint32_t tag, uint32_t a, uint32_t b, const void* runs, size_t run_bytes) {
+    std::vector<unsigned char> k(12 + run_bytes);
+    std::memcpy(k.data(), &tag, 4);
+    std::memcpy(k.data() + 4, &a, 4);
+    std::memcpy(k.data() + 8, &b, 4);
+    if (run_bytes) std::memcpy(k.data() + 12, runs, run_bytes);
+    return k;
+}
+
 symgpu_status upload_chunks(symgpu_ctx* ctx, const std::vector<CodecChunk>& chunks) {
     // Chunk lists are small; rewriting them needs the previous launch to have consumed the old list.
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -76,6 +86,7 @@ symgpu_status symgpu_aac_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams) {
     CU(ctx, cudaMalloc(&ctx->d_aac_gen, ((size_t)n_streams + 1) * sizeof(uint32_t)));
     CU(ctx, cudaMemset(ctx->d_aac_gen, 0, ((size_t)n_streams + 1) * sizeof(uint32_t)));
     ctx->n_aac_streams = n_streams;
+    ctx->chunk_key.clear();
     return SYMGPU_OK;
 }
 
@@ -96,7 +107,9 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
     DeviceGuard guard(ctx->device);
     std::vector<CodecChunk> chunks;
     uint64_t covered = 0;
-    for (uint32_t r = 0; r < n_runs; ++r) {
+    const std::vector<unsigned char> key = chunk_key_of(0x41414300u, n_frames, ctx->n_aac_streams, runs, (size_t)n_runs * sizeof *runs);
+    const bool reuse = key == ctx->chunk_key;
+    for (uint32_t r = 0; r < n_runs && !reuse; ++r) {
         const symgpu_aac_run& run = runs[r];
         const int n_ch = run.channels ? run.channels : 2;
         if (n_ch < 1 || n_ch > 2) return SYMGPU_ERR_ARG;
@@ -115,9 +128,15 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
                 chunks.push_back(c);
             });
     }
-    if (covered != n_frames) return SYMGPU_ERR_ARG;
-    symgpu_status s = upload_chunks(ctx, chunks);
-    if (s != SYMGPU_OK) return s;
+    symgpu_status s = SYMGPU_OK;
+    if (!reuse) {
+        if (covered != n_frames) return SYMGPU_ERR_ARG;
+        ctx->chunk_key.clear();
+        s = upload_chunks(ctx, chunks);
+        if (s != SYMGPU_OK) return s;
+        ctx->chunk_key = key;
+        ctx->cached_chunks = (int)chunks.size();
+    }
     const size_t spec_bytes = (size_t)n_frames * 2 * 1024 * sizeof(float);
     if (n_tns && spec_bytes > ctx->aac_scratch_cap) {
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -139,7 +158,7 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
     AacArgs a{units, tns, coeffs, ctx->d_aac_scratch, ctx->d_aac_scratch,
               ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0,
               pcm, ctx->d_chunks, ctx->d_aac_states, ctx->d_aac_gen, ctx->d_aac_gen + ctx->n_aac_streams, ctx->d_codec_tab};
-    CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, (int)chunks.size(), ctx->stream));
+    CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, ctx->cached_chunks, ctx->stream));
     ctx->launches += n_tns ? 4 : 1;
     return SYMGPU_OK;
 }
@@ -202,6 +221,8 @@ symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_str
     CU(ctx, cudaMalloc(&ctx->d_vorbis_gen, ((size_t)n_streams + 1) * sizeof(uint32_t)));
     CU(ctx, cudaMemset(ctx->d_vorbis_gen, 0, ((size_t)n_streams + 1) * sizeof(uint32_t)));
     ctx->h_vorbis_streams.assign(streams, streams + n_streams);
+    ctx->vorbis_cfg_epoch = (ctx->vorbis_cfg_epoch + 1) & 0xffu;
+    ctx->chunk_key.clear();
     ctx->n_vorbis_streams = n_streams;
     return SYMGPU_OK;
 }
@@ -270,14 +291,15 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
         if (runs[r].n_packets && runs[r].stream < ctx->n_vorbis_streams)
             max_bs1 = std::max(max_bs1, (int)ctx->h_vorbis_streams[runs[r].stream].bs1_exp);
     const uint32_t per_chunk = (uint32_t)vorbis_slots_for(max_bs1) - 1; // one slot is the packet before the chunk
-    for (uint32_t r = 0; r < n_runs; ++r) {
+    const std::vector<unsigned char> key = chunk_key_of(0x564f5200u + ctx->vorbis_cfg_epoch, n_packets, slot, runs, (size_t)n_runs * sizeof *runs);
+    const bool reuse = key == ctx->chunk_key;
+    for (uint32_t r = 0; r < n_runs && !reuse; ++r) {
         const symgpu_vorbis_run& run = runs[r];
         if (run.n_packets == 0) continue;
         if ((uint64_t)run.first_packet + run.n_packets > n_packets || run.reserved) return SYMGPU_ERR_ARG;
         if (run.stream >= ctx->n_vorbis_streams) return SYMGPU_ERR_LIMIT;
         const symgpu_vorbis_stream& cfg = ctx->h_vorbis_streams[run.stream];
         if ((1u << (cfg.bs1_exp - 1)) > slot) return SYMGPU_ERR_ARG; // slot too small for this stream
-        max_bs1 = std::max(max_bs1, (int)cfg.bs1_exp);
         covered += run.n_packets;
         split_even(run.n_packets, per_chunk, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
             CodecChunk c{};
@@ -288,13 +310,18 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
             chunks.push_back(c);
         });
     }
-    if (covered != n_packets) return SYMGPU_ERR_ARG;
-    symgpu_status s = upload_chunks(ctx, chunks);
-    if (s != SYMGPU_OK) return s;
+    if (!reuse) {
+        if (covered != n_packets) return SYMGPU_ERR_ARG;
+        ctx->chunk_key.clear();
+        symgpu_status s = upload_chunks(ctx, chunks);
+        if (s != SYMGPU_OK) return s;
+        ctx->chunk_key = key;
+        ctx->cached_chunks = (int)chunks.size();
+    }
     VorbisArgs a{units, floor_y, residue, pcm, ctx->d_chunks, ctx->d_vorbis_streams, ctx->d_vorbis_floors,
                  ctx->d_vorbis_floor_aux, ctx->n_vorbis_floors, slot, ctx->d_vorbis_states, ctx->d_vorbis_gen,
                  ctx->d_vorbis_gen + ctx->n_vorbis_streams, ctx->d_codec_tab};
-    CU(ctx, vorbis_launch(a, (int)chunks.size(), max_bs1, ctx->stream));
+    CU(ctx, vorbis_launch(a, ctx->cached_chunks, max_bs1, ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;
 }
