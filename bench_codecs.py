@@ -37,7 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--codec", default="both", choices=["aac", "vorbis", "both"])
+    ap.add_argument("--codec", default="both", choices=["aac", "vorbis", "both", "mp3-short", "mixed", "all"])
     ap.add_argument("--tns", type=float, default=0.2)
     args = ap.parse_args()
     import torch
@@ -48,7 +48,54 @@ def main():
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     S, F, SETS = 64, 128, 4
-    if args.codec in ("aac", "both"):
+    if args.codec in ("mp3-short", "all"):
+        # SURVEY 8d worst case: 8192 streams x 1 frame -- every tile loads and stores its stream's state, which is
+        # therefore counted in the algorithmic bytes (overlap 4608 B + 15 history slots 3840 B, read + written).
+        S1 = 8192
+        units, spectra, runs = workloads.mp3_batch(S1, 1, seed=workloads.SEED_BASE + 11)
+        eng.mp3_streams_alloc(S1)
+        sets = []
+        for _ in range(SETS):
+            sets.append((torch.from_numpy(units.view(np.uint8).reshape(-1).copy()).to(dev), torch.from_numpy(spectra).to(dev),
+                         torch.empty((S1, 2, 1152), dtype=torch.float32, device=dev)))
+        ms = _time_steps(eng, lambda i: eng.mp3_synth_dev(sets[i % SETS][0], sets[i % SETS][1], runs, sets[i % SETS][2]),
+                         args.steps, args.warmup)
+        algo = S1 * (workloads.MP3_ALGO_BYTES_PER_FRAME + 2 * (4608 + 3840))
+        audio = workloads.mp3_audio_seconds(S1)
+        ach = algo / (ms * 1e-3) / 1e9
+        print(json.dumps({"codec": "mp3", "workload": "MP3 44.1kHz stereo, 8192 streams x 1 frame (state in and out of HBM for every frame)",
+                          "value": audio / (ms * 1e-3), "unit": "audio-s/s", "kernel_ms": ms,
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                       "algorithmic_bytes_per_launch": algo}}), flush=True)
+    if args.codec in ("mixed", "all"):
+        # SURVEY 8d config 5 at 1/16 scale: 4096 streams x 16 frames, 50 % MP3 / 30 % AAC / 20 % Vorbis, on ONE context;
+        # a step = the three launches back to back.
+        Fm = 16
+        n_mp3, n_aac, n_vor = 2048, 1229, 819
+        mu, ms_, mr = workloads.mp3_batch(n_mp3, Fm, seed=workloads.SEED_BASE + 51)
+        au, at, ac, ar = workloads.aac_batch(n_aac, Fm, seed=workloads.SEED_BASE + 52)
+        wl = workloads.vorbis_batch(n_vor, Fm, seed=workloads.SEED_BASE + 53)
+        eng.mp3_streams_alloc(n_mp3)
+        eng.aac_streams_alloc(n_aac)
+        eng.vorbis_streams_set(wl["streams"])
+        eng.vorbis_floors_set(wl["floors"])
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d_mu, d_ms, d_mp = t(mu.view(np.uint8).reshape(-1)), t(ms_), torch.empty((n_mp3 * Fm, 2, 1152), dtype=torch.float32, device=dev)
+        d_au, d_at, d_ac = t(au.view(np.uint8).reshape(-1)), t(at.view(np.uint8).reshape(-1)), t(ac)
+        d_ap = torch.empty((n_aac * Fm, 2, 1024), dtype=torch.float32, device=dev)
+        d_vu, d_vy, d_vr = t(wl["units"].view(np.uint8).reshape(-1)), t(wl["floor_y"].view(np.int16)), t(wl["residue"])
+        d_vp = torch.zeros((n_vor * Fm, 2, wl["slot"]), dtype=torch.float32, device=dev)
+
+        def step(i):
+            eng.mp3_synth_dev(d_mu, d_ms, mr, d_mp)
+            eng.aac_synth_dev(d_au, d_at, len(at), d_ac, ar, d_ap)
+            eng.vorbis_synth_dev(d_vu, d_vy, d_vr, wl["runs"], wl["slot"], d_vp)
+        ms = _time_steps(eng, step, args.steps, args.warmup)
+        audio = (workloads.mp3_audio_seconds(n_mp3 * Fm) + n_aac * Fm * 1024 / 48000.0 + float(wl["out_len"].sum()) / 44100.0)
+        print(json.dumps({"codec": "mixed", "workload": "4096 streams x 16 frames on one context: 2048 MP3 + 1229 AAC-LC + 819 Vorbis "
+                          "(SURVEY config 5 at 1/16 scale; 0.57 GB in + 0.57 GB out per step, far beyond the 126 MB L2)",
+                          "value": audio / (ms * 1e-3), "unit": "audio-s/s", "step_ms": ms, "audio_s_per_step": audio}), flush=True)
+    if args.codec in ("aac", "both", "all"):
         units, tns, coeffs, runs = workloads.aac_batch(S, F, tns_prob=args.tns)
         eng.aac_streams_alloc(S)
         sets = []
@@ -65,7 +112,7 @@ def main():
                           "value": audio / (ms * 1e-3), "unit": "audio-s/s", "kernel_ms": ms, "n_tns_filters": int(len(tns)),
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                        "algorithmic_bytes_per_launch": algo}}), flush=True)
-    if args.codec in ("vorbis", "both"):
+    if args.codec in ("vorbis", "both", "all"):
         wl = workloads.vorbis_batch(S, F)
         eng.vorbis_streams_set(wl["streams"])
         eng.vorbis_floors_set(wl["floors"])
