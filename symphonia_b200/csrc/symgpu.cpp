@@ -445,8 +445,18 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     std::vector<Mp3Tile> all_tiles;
     Mp3Plan plan;
     uint32_t r = 0;
+    // Both PCIe directions carry about the same bytes, so the run is as long as the D2H chain, which cannot start
+    // before the first slice is in and cannot end before the last slice is out: the slices taper at both ends
+    // (weights 0.25, 0.5, 1, ..., 1, 0.5, 0.25); every extra slice costs two copy set-ups (~20 us each).
+    double w_total = 0.0, w_acc = 0.0;
+    auto weight = [&](int i) {
+        const int edge = std::min(i, n_slices - 1 - i);
+        return n_slices < 4 ? 1.0 : edge == 0 ? 0.25 : edge == 1 ? 0.5 : 1.0;
+    };
+    for (int i = 0; i < n_slices; ++i) w_total += weight(i);
     for (int i = 0; i < n_slices; ++i) {
-        const uint32_t target = (uint32_t)(((uint64_t)n_frames * (i + 1)) / n_slices);
+        w_acc += weight(i);
+        const uint32_t target = (uint32_t)((double)n_frames * (w_acc / w_total));
         Slice sl{r, r, runs[r].first_frame, 0, (int)all_tiles.size(), 0, 0, 0};
         while (r < n_runs && (runs[r].first_frame + runs[r].n_frames <= target || sl.r1 == sl.r0)) {
             ++r;
@@ -469,11 +479,10 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     ctx->cached_frames = 0;
     std::memcpy(ctx->h_tiles, all_tiles.data(), all_tiles.size() * sizeof(Mp3Tile));
     CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, all_tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->copy_in)); // 256 B per frame: one copy
     for (size_t i = 0; i < slices.size(); ++i) {
         const Slice& sl = slices[i];
         const size_t nf = sl.f1 - sl.f0;
-        CU(ctx, cudaMemcpyAsync(d_units + (size_t)sl.f0 * 4, units + (size_t)sl.f0 * 4, nf * 4 * sizeof(symgpu_mp3_gc),
-                                cudaMemcpyHostToDevice, ctx->copy_in));
         CU(ctx, copy_in(sl.f0, nf, ctx->copy_in));
         CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));

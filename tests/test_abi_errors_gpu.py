@@ -66,3 +66,42 @@ def test_vorbis_rejects_unsupported_configurations(engine):
     with pytest.raises(sb.SymgpuError) as e:
         engine.vorbis_streams_set(s)
     assert e.value.status == 6
+
+
+def test_vorbis_floor_setups_are_validated(engine):
+    """The kernel divides by x differences and sweeps posts by dependency level: a setup that the reference's
+    own parser would have refused (floor.rs:300-420) must be refused here, not hang or corrupt a launch."""
+    import symphonia_b200 as sb
+    from symphonia_b200 import workloads
+    from symphonia_b200._native import VORBIS_FLOOR1_DTYPE
+    good = np.array([workloads.make_floor1_setup([0, 128, 64, 32, 96, 16], 2)], dtype=VORBIS_FLOOR1_DTYPE)
+    engine.vorbis_floors_set(good)
+
+    def rejected(mutate):
+        bad = good.copy()
+        mutate(bad[0])
+        with pytest.raises(sb.SymgpuError) as e:
+            engine.vorbis_floors_set(bad)
+        assert e.value.status == 6
+
+    def dup_x(f):
+        f["x_list"][3] = f["x_list"][2]                 # two posts at the same x: a zero-length segment
+
+    def self_neighbour(f):
+        f["low"][4] = 4                                  # neighbour that is not an earlier post
+
+    def wrong_side(f):
+        f["low"][2], f["high"][2] = f["high"][2], f["low"][2]
+
+    def unsorted(f):
+        f["sort_order"][1], f["sort_order"][2] = f["sort_order"][2], f["sort_order"][1]
+
+    def not_a_permutation(f):
+        f["sort_order"][2] = f["sort_order"][1]
+
+    def no_origin(f):
+        f["x_list"][0] = 5
+
+    for m in (dup_x, self_neighbour, wrong_side, unsorted, not_a_permutation, no_origin):
+        rejected(m)
+    engine.vorbis_floors_set(good)  # the context still accepts a valid set afterwards
