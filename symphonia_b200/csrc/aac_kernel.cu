@@ -3,10 +3,11 @@
 // sequences, overlap-add through the per-channel `delay` line.
 //
 // Work decomposition: `delay` is overwritten from the current frame only, so a
-// channel's frames are cut into chunks of consecutive frames; one 64-thread CTA walks one chunk with
-// the delay line in shared memory.  A chunk that does not start its run recomputes the previous
-// frame's delay (one halo frame, output suppressed).  TNS is a serial recurrence along frequency:
-// it runs in a pre-pass, one LANE per filter, into a scratch copy of the spectra it touches.
+// channel's frames are cut into chunks of consecutive frames; a persistent CTA walks chunks, one group of
+// 64 threads per frame of the chunk plus one for the frame before it (whose IMDCT output is the delay
+// line the chunk's first frame overlaps with; a run's first chunk takes it from the stream state).
+// TNS is a serial recurrence along frequency: it runs in a pre-pass, one LANE per filter, on a scratch
+// copy of the channel-frames that carry filters.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -19,7 +20,6 @@
 namespace symgpu {
 namespace {
 
-constexpr int kAacThreads = 64;
 constexpr int P0 = 512 - 64, P1 = 512 + 64; // SHORT_WIN_POINT0/1, aac/dsp.rs:19-20
 
 // ---- TNS ------------------------------------------------------------------------------------
