@@ -165,6 +165,14 @@ def run_ours(args):
 
     u_host = torch.from_numpy(units.view(np.uint8).reshape(-1))
     s_host = torch.from_numpy(spectra)
+    # pinned host buffers of the end-to-end legs (allocated before anything is timed)
+    u_pin = u_host.pin_memory()
+    s_pin = s_host.pin_memory()
+    p_pin = torch.empty((N_FRAMES, 2, 1152), dtype=torch.float32).pin_memory()
+    q_pin = torch.empty((N_FRAMES * 1152, 2), dtype=torch.int16).pin_memory()
+    g_pin = torch.from_numpy(workloads.mp3_quantize(spectra)).pin_memory()
+    u_np = u_pin.numpy().view(sb._native.MP3_GC_DTYPE).reshape(N_FRAMES, 2, 2)
+    s_np, p_np, q_np, g_np = s_pin.numpy(), p_pin.numpy(), q_pin.numpy(), g_pin.numpy()
     sets = []
     for _ in range(N_BUFFER_SETS):
         sets.append((u_host.to(dev), s_host.to(dev), torch.empty((N_FRAMES, 2, 1152), dtype=torch.float32, device=dev)))
@@ -223,11 +231,6 @@ def run_ours(args):
     sampler.join(timeout=6)
 
     # ---- end to end through the host entry point (pinned host buffers, copies inside) ----------
-    u_pin = u_host.pin_memory()
-    s_pin = s_host.pin_memory()
-    p_pin = torch.empty((N_FRAMES, 2, 1152), dtype=torch.float32).pin_memory()
-    u_np = u_pin.numpy().view(sb._native.MP3_GC_DTYPE).reshape(N_FRAMES, 2, 2)
-    s_np, p_np = s_pin.numpy(), p_pin.numpy()
     e2e_steps = max(3, min(args.steps, 20))
 
     def host_timed(call):
@@ -246,12 +249,8 @@ def run_ours(args):
     e2e_s, e2e_med = host_timed(lambda: eng.mp3_synth_host(u_np, s_np, runs, out=p_np))
     checksum = float(np.abs(p_np[::512]).sum())
     # Same, with the output stage on the device (interleaved i16 crosses PCIe instead of planar f32).
-    q_pin = torch.empty((N_FRAMES * 1152, 2), dtype=torch.int16).pin_memory()
-    q_np = q_pin.numpy()
     e2e16_s, e2e16_med = host_timed(lambda: eng.mp3_synth_host_packed(u_np, s_np, runs, sb._native.FMT_S16, out=q_np))
     # Compact both ways: quantised i16 spectra in (POW43 lookup on the device), interleaved i16 out.
-    g_pin = torch.from_numpy(workloads.mp3_quantize(spectra)).pin_memory()
-    g_np = g_pin.numpy()
     e2ec_s, e2ec_med = host_timed(lambda: eng.mp3_synth_host_quantized(u_np, g_np, runs, sb._native.FMT_S16, out=q_np))
 
     # ---- max over ranks ------------------------------------------------------------------------

@@ -29,6 +29,7 @@ struct symgpu_ctx {
     std::vector<symgpu_mp3_run> cached_runs;
     uint32_t cached_frames = 0;
     int cached_tiles = 0, cached_hdr = 0, cached_ctas = 0;
+    bool cached_multi = false;
     // staging for the host entry points
     void* d_stage = nullptr;
     size_t stage_cap = 0;

@@ -81,6 +81,10 @@ struct WarpScratch {
     float2 sratio[40];
     uint8_t smode[40]; // 0 none, 1 mid/side, 2 intensity
     uint8_t nz[40];    // channel-1 interval holds a non-zero line
+    // what this warp's job does with its `second` half after the hybrid phase (parked here so that it does not
+    // occupy registers during the phase): XT region it is added into, or -1, and the state it is stored to, or null
+    int next_region;
+    Mp3StreamState* st_out;
 };
 
 __device__ __forceinline__ int kind_of(const symgpu_mp3_gc& g) {
@@ -262,8 +266,7 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
 // The signs are folded into the per-lane coefficients ((-d)*D == d*(-D) exactly).  `slot_seq0` is the
 // batch-wide sequence number of the first slot: slots of a frame are contiguous in a PCM plane
 // (plane[gr*576 + t*32 + i]) and frames are SYMGPU_MP3_FRAME_FLOATS apart.
-template <int NW>
-__device__ __forceinline__ void window_phase(const float* xt, int row0, int total, int warp, int lane,
+__device__ __forceinline__ void window_phase(const float* xt, int row0, int begin, int end, int lane,
                                              const float* __restrict__ synth_d, float* __restrict__ pcm, int slot_seq0,
                                              int slots_per_frame, bool stereo) {
     const int col_lo = lane < 16 ? 16 + lane : (lane == 16 ? 32 : 48 - lane);
@@ -275,10 +278,7 @@ __device__ __forceinline__ void window_phase(const float* xt, int row0, int tota
         dlo[j] = lane > 16 ? -a0 : a0;
         dhi[j] = -__ldg(synth_d + 64 * j + 32 + lane);
     }
-    const int per = (total + NW - 1) / NW;
-    const int begin = warp * per;                  // slot index relative to row0
-    const int end = min(total, begin + per);
-    if (begin >= end) return;
+    if (begin >= end) return; // [begin, end): slot indices relative to row0
     constexpr uint32_t kRowBytes = kPitch * 8;
     uint32_t a_lo = smem_u32(xt) + (uint32_t)((row0 + begin - 15) * kPitch + col_lo) * 8u;
     uint32_t a_hi = smem_u32(xt) + (uint32_t)((row0 + begin - 15) * kPitch + col_hi) * 8u;
@@ -326,21 +326,24 @@ __device__ __forceinline__ void window_phase(const float* xt, int row0, int tota
 
 template <int T, int NW>  // PHASE: prologue+tile loop
 struct Mp3Smem {
-    static constexpr int kRows = 18 * (T + 1);            // region 0 = granule g0-1 (history), then the tile
+    static constexpr int kRows = 18 * kMp3GroupRegions;   // every piece of the group: one history region + one per granule
     float xt[kRows * kPitch * 2];                         // [row][33][2 channels]
-    alignas(16) float spec[T + 2][2 * 576];               // TMA destination: spectra of the 2 halo + T granules
-    alignas(16) symgpu_mp3_gc units[T + 2][2];            // TMA destination: their descriptors
+    alignas(16) float spec[NW][2 * 576];                  // TMA destination: spectra of the group's granule jobs
+    alignas(16) symgpu_mp3_gc units[NW][2];               // TMA destination: their descriptors
     WarpScratch ws[NW];
-    alignas(16) Mp3StreamState carry;                     // state handed from one tile of the chain to the next
-    alignas(16) Mp3Tile tile_stage[2];                    // descriptor of the tile in flight (by iteration parity)
-    uint32_t gen_stage[2];                                // state generation of its stream at launch
+    alignas(16) Mp3StreamState carry;                     // state handed from one group of the chain to the next
+    alignas(16) Mp3Tile seg_stage[2][kMp3GroupTiles];     // descriptors of the group in flight (by iteration parity)
+    uint32_t gen_stage[2][kMp3GroupTiles];                // state generation of their streams at launch
+    int nseg_stage[2];
     alignas(8) uint64_t bar;
     bool is_last;
 };
 
 } // namespace
 
-template <int T, int NW>
+// MULTI = false: every group of the plan is a single tile (the shape of large batches); the loops over the
+// pieces of a group then fold away at compile time.
+template <int T, int NW, bool MULTI>
 __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) {
     static_assert(NW >= T, "one warp per granule job (a tile with a halo holds NW - 2 granules)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -353,25 +356,39 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
     const Mp3Tables* __restrict__ tab = a.tab;
     const int n_tiles = a.n_tiles;
 
-    // One thread: tile descriptor + stream generation into their stage (ordinary stores, published by the
-    // release of the mbarrier arrive), then TMA bulk copies of the tile's descriptors + spectra.
+    // One thread: the descriptors of the group that starts at tile `ti` (up to and including the tile flagged
+    // kTileGroupEnd) and their streams' generations into the stage (ordinary stores, published by the release of
+    // the mbarrier arrive), then TMA bulk copies of every piece's descriptors + spectra.  Job slots are handed
+    // out in order: a piece with a halo takes n + 2, any other piece n.
     auto issue_prefetch = [&](int ti, int parity) {
-        const Mp3Tile t = a.tiles[ti];
-        sm.tile_stage[parity] = t;
-        sm.gen_stage[parity] = a.gen[t.stream];
-        const int j0 = (t.flags & (kTileLoadState | kTileCarryIn)) ? 2 : 0;
-        const int cnt = t.n_granules + 2 - j0;
-        mbar_expect_tx(&sm.bar, (uint32_t)cnt * (4608u + 128u));
-        if (t.gpf == 2) { // granules of consecutive frames are contiguous: [frame][gr][ch][576]
-            const size_t slot = (size_t)t.first_frame * 2 + t.first_gr - 2 + j0;
-            tma_bulk_g2s(sm.spec[j0], a.spectra + slot * 1152, (uint32_t)cnt * 4608u, &sm.bar);
-            tma_bulk_g2s(sm.units[j0], a.units + slot * 2, (uint32_t)cnt * 128u, &sm.bar);
-        } else {          // one granule per frame slot
-            for (int j = j0; j < t.n_granules + 2; ++j) {
-                const size_t slot = (size_t)((int)t.first_frame + t.first_gr - 2 + j) * 2;
-                tma_bulk_g2s(sm.spec[j], a.spectra + slot * 1152, 4608u, &sm.bar);
-                tma_bulk_g2s(sm.units[j], a.units + slot * 2, 128u, &sm.bar);
+        int nseg = 0, jobs = 0;
+        for (;;) {
+            const Mp3Tile t = a.tiles[ti + nseg];
+            sm.seg_stage[parity][nseg] = t;
+            sm.gen_stage[parity][nseg] = a.gen[t.stream];
+            jobs += t.n_granules + ((t.flags & (kTileLoadState | kTileCarryIn)) ? 0 : 2);
+            ++nseg;
+            if (!MULTI || (t.flags & kTileGroupEnd) || nseg == kMp3GroupTiles) break;
+        }
+        sm.nseg_stage[parity] = nseg;
+        mbar_expect_tx(&sm.bar, (uint32_t)jobs * (4608u + 128u));
+        int slot0 = 0;
+        for (int k = 0; k < nseg; ++k) {
+            const Mp3Tile t = sm.seg_stage[parity][k];
+            const int halo = (t.flags & (kTileLoadState | kTileCarryIn)) ? 0 : 2;
+            const int cnt = t.n_granules + halo;
+            if (t.gpf == 2) { // granules of consecutive frames are contiguous: [frame][gr][ch][576]
+                const size_t src = (size_t)t.first_frame * 2 + t.first_gr - halo;
+                tma_bulk_g2s(sm.spec[slot0], a.spectra + src * 1152, (uint32_t)cnt * 4608u, &sm.bar);
+                tma_bulk_g2s(sm.units[slot0], a.units + src * 2, (uint32_t)cnt * 128u, &sm.bar);
+            } else {          // one granule per frame slot
+                for (int j = 0; j < cnt; ++j) {
+                    const size_t src = (size_t)((int)t.first_frame + t.first_gr - halo + j) * 2;
+                    tma_bulk_g2s(sm.spec[slot0 + j], a.spectra + src * 1152, 4608u, &sm.bar);
+                    tma_bulk_g2s(sm.units[slot0 + j], a.units + src * 2, 128u, &sm.bar);
+                }
             }
+            slot0 += cnt;
         }
     };
 
@@ -385,36 +402,60 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
 
     WarpScratch& ws = sm.ws[warp];
     int it = 0;
-    for (int ti = t_begin; ti < t_end; ++ti, ++it) {
-        mbar_wait(&sm.bar, (uint32_t)(it & 1));
-        const Mp3Tile tile = sm.tile_stage[it & 1];
+    for (int ti = t_begin; ti < t_end; ++it) {
+        const int par = it & 1;
+        mbar_wait(&sm.bar, (uint32_t)par);
+        // A GROUP of consecutive tiles of the chain is processed together: each tile ("piece") is a run of
+        // consecutive granules of one stream with its own state in / out; together they hold at most NW granule
+        // jobs and kMp3GroupRegions XT regions (one history region + one region per granule, per piece).
+        const int nseg = MULTI ? sm.nseg_stage[par] : 1;
+        // My granule job: warp w takes job w of the group; find its piece.
+        Mp3Tile tile = sm.seg_stage[par][0];
+        int seg = -1, job0 = 0, reg0 = 0; // my piece, its first job slot and its first XT region
+        {
+            int jobs = 0, regions = 0;
+            for (int k = 0; k < nseg; ++k) {
+                const Mp3Tile t = sm.seg_stage[par][k];
+                const int cnt = t.n_granules + ((t.flags & (kTileLoadState | kTileCarryIn)) ? 0 : 2);
+                if (seg < 0 && warp < jobs + cnt) {
+                    seg = k;
+                    job0 = jobs;
+                    reg0 = regions;
+                    tile = t;
+                }
+                jobs += cnt;
+                regions += t.n_granules + 1;
+            }
+        }
         const int n = tile.n_granules;
         const int n_ch = tile.n_ch;
-        const int gpf_shift = tile.gpf == 2 ? 1 : 0;
-        // State comes in from HBM (run start) or from the previous tile of this CTA's chain (shared memory),
-        // and goes out to HBM (run end) or to the next tile of the chain; with no input the tile recomputes
+        // State comes in from HBM (run start) or from the previous group of this CTA's chain (shared memory),
+        // and goes out to HBM (run end) or to the next group of the chain; with no input the piece recomputes
         // a 2-granule halo.
         const bool load_state = tile.flags & (kTileLoadState | kTileCarryIn);
         const bool store_state = tile.flags & (kTileStoreState | kTileCarryOut);
         // Stream state in HBM is double-buffered: a launch reads generation g and writes generation g+1, so a
         // run-starting tile never races with the run-ending tile of the same stream.
-        const uint32_t gen = sm.gen_stage[it & 1];
+        const uint32_t gen = sm.gen_stage[par][seg < 0 ? 0 : seg];
         const Mp3StreamState* st_in = (tile.flags & kTileCarryIn) ? &sm.carry : a.states + (size_t)tile.stream * 2 + (gen & 1);
         Mp3StreamState* st_out = (tile.flags & kTileCarryOut) ? &sm.carry : a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
-        const int j0 = load_state ? 2 : 0; // first granule job of the tile
-        const int gseq0 = ((int)tile.first_frame << gpf_shift) + tile.first_gr; // first granule of the tile
+        const int j0 = load_state ? 2 : 0; // index of the piece's first job (0, 1 = halo granules)
 
         // --------------------------------------------------------------------------------------
-        // Phase A+B: one warp per granule job j (j = 0, 1: halo granules g0-2, g0-1; j >= 2: the tile),
-        // lane = sub-band, everything in registers.  Job j >= 1 owns XT region j-1 (rows 18(j-1)..).
+        // Phase A+B: one warp per granule job (of a piece: g = 0, 1: halo granules g0-2, g0-1; g >= 2: the
+        // piece's granules), lane = sub-band, everything in registers.  Job g >= 1 owns XT region reg0 + g - 1.
         // --------------------------------------------------------------------------------------
-        const int g = warp + j0; // job index: stage slot g, XT region g - 1
-        const bool active = g < n + 2;
+        const int g = warp - job0 + j0; // job index inside my piece; stage slot = warp
+        const bool active = seg >= 0;
+        if (lane == 0) {
+            ws.next_region = (active && g + 1 < n + 2) ? reg0 + g : -1;
+            ws.st_out = (active && g + 1 >= n + 2 && store_state) ? st_out : nullptr;
+        }
         float sec[2][18];
         if (active) {
-            const symgpu_mp3_gc& g0 = sm.units[g][0];
-            const symgpu_mp3_gc& g1 = sm.units[g][1];
-            const float* S = sm.spec[g];
+            const symgpu_mp3_gc& g0 = sm.units[warp][0];
+            const symgpu_mp3_gc& g1 = sm.units[warp][1];
+            const float* S = sm.spec[warp];
             if (lane < 10) reinterpret_cast<uint32_t*>(ws.smode)[lane] = 0;
             if (lane >= 16 && lane < 26) reinterpret_cast<uint32_t*>(ws.nz)[lane - 16] = 0;
             const int sr = g0.sample_rate_idx;
@@ -425,7 +466,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
 
             // A1: per-interval requantisation scale (requantize.rs:240-355)  // PHASE: A1 scale
             for (int ch = 0; ch < n_ch; ++ch) {
-                const symgpu_mp3_gc& gg = sm.units[g][ch];
+                const symgpu_mp3_gc& gg = sm.units[warp][ch];
                 const int kind = ch ? kind1 : kind0;
                 const int n_iv = c_mp3.n_edges[sr][kind] - 1;
                 const int gain = (int)gg.global_gain - 210;
@@ -645,12 +686,12 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
             }
 
             // B: hybrid synthesis (hybrid_synthesis.rs:280-359)  // PHASE: B glue
-            float* X = xt + (size_t)(18 * (g - 1)) * kPitch * 2; // unused by job 0 (it only hands its overlap on)
+            float* X = xt + (size_t)(18 * (reg0 + g - 1)) * kPitch * 2; // unused by job 0 (it only hands its overlap on)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 float first[18];
                 if (ch < n_ch) {
-                    const symgpu_mp3_gc& gg = sm.units[g][ch];
+                    const symgpu_mp3_gc& gg = sm.units[warp][ch];
                     const int kind = ch ? kind1 : kind0;
                     const int rz = rzh[ch];
                     const int sb_limit = (rz + 17) / 18;
@@ -687,15 +728,17 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
             }
         }
         __syncthreads();  // PHASE: handoff+barriers
-        // The stage is free: fetch this CTA's next tile while the current one is in its DCT / window phases.
-        if (threadIdx.x == NW * 32 - 32 && ti + 1 < t_end) {
+        // The stage is free: fetch this CTA's next group while the current one is in its DCT / window phases.
+        if (threadIdx.x == NW * 32 - 32 && ti + nseg < t_end) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_prefetch(ti + 1, (it + 1) & 1);
+            issue_prefetch(ti + nseg, (it + 1) & 1);
         }
-        // overlap hand-off: region of job g+1 += second(g); the run's last granule feeds the stream state
-        if (active) {
-            if (g + 1 < n + 2) {
-                float* Xn = xt + (size_t)(18 * g) * kPitch * 2;
+        // overlap hand-off: region of job g+1 += second(g); the piece's last granule feeds the stream state
+        {
+            const int next_region = ws.next_region;
+            Mp3StreamState* so = ws.st_out;
+            if (next_region >= 0) {
+                float* Xn = xt + (size_t)(18 * next_region) * kPitch * 2;
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
@@ -703,59 +746,116 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
                         float* p = Xn + (t * kPitch + lane) * 2 + ch;
                         *p = *p + finv(sec[ch][t], lane, t);
                     }
-            } else if (store_state) {
+            } else if (so) {
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-                    for (int t = 0; t < 18; ++t) st_out->overlap[ch][lane][t] = sec[ch][t];
+                    for (int t = 0; t < 18; ++t) so->overlap[ch][lane][t] = sec[ch][t];
             }
         }
-        if (load_state) { // polyphase history (rows 3..17 of region 0) from the stream state
-            for (int idx = threadIdx.x; idx < 15 * kPitch; idx += NW * 32) {
-                const int s = idx / kPitch, col = idx - s * kPitch;
-                float2 v = make_float2(0.0f, 0.0f);
-                if (col < 32) v = st_in->dhist[s][col];
-                *reinterpret_cast<float2*>(xt + (size_t)((3 + s) * kPitch + col) * 2) = v;
+        // polyphase history (rows 3..17 of a piece's first region) from the state of every piece that has one
+        {
+            int regions = 0;
+            for (int k = 0; k < nseg; ++k) {
+                const Mp3Tile t = sm.seg_stage[par][k];
+                if (t.flags & (kTileLoadState | kTileCarryIn)) {
+                    const uint32_t gk = sm.gen_stage[par][k];
+                    const Mp3StreamState* st = (t.flags & kTileCarryIn) ? &sm.carry : a.states + (size_t)t.stream * 2 + (gk & 1);
+                    for (int idx = threadIdx.x; idx < 15 * kPitch; idx += NW * 32) {
+                        const int srow = idx / kPitch, col = idx - srow * kPitch;
+                        float2 v = make_float2(0.0f, 0.0f);
+                        if (col < 32) v = st->dhist[srow][col];
+                        *reinterpret_cast<float2*>(xt + (size_t)((18 * regions + 3 + srow) * kPitch + col) * 2) = v;
+                    }
+                }
+                regions += t.n_granules + 1;
             }
         }
         __syncthreads();
 
         // --------------------------------------------------------------------------------------
-        // Phase C: DCT-32 of every time slot of the tile, in place.  Half-warp = 16 slots of one  // PHASE: C glue
-        // channel: the 32-bit accesses of a warp hit 32 distinct banks (row pitch 66 words).
+        // Phase C: DCT-32 of every time slot of the group, in place.  Half-warp = 16 slots of one  // PHASE: C glue
+        // channel: the 32-bit accesses of a warp hit 32 distinct banks (row pitch 66 words).  The rows of the
+        // pieces are enumerated back to back: a piece with state has 18 n rows from its second region on, a
+        // piece with a halo also recomputes the 15 history rows of its first region.
         // --------------------------------------------------------------------------------------
         {
-            const int row_begin = load_state ? 18 : 3;
-            const int row_end = 18 * (n + 1);
+            int total_rows = 0;
+            for (int k = 0; k < nseg; ++k) {
+                const Mp3Tile t = sm.seg_stage[par][k];
+                total_rows += 18 * t.n_granules + ((t.flags & (kTileLoadState | kTileCarryIn)) ? 0 : 15);
+            }
             const int chn = lane >> 4;
-            for (int base = row_begin + warp * 16; base < row_end; base += NW * 16) {
-                const int s = base + (lane & 15);
-                if (s < row_end) {
-                    float* row = xt + (size_t)s * kPitch * 2 + chn;
+            for (int base = warp * 16; base < total_rows; base += NW * 16) {
+                int r = base + (lane & 15);
+                if (r < total_rows) {
+                    int regions = 0, row = 0;
+                    for (int k = 0; k < nseg; ++k) { // piece that holds enumerated row r
+                        const Mp3Tile t = sm.seg_stage[par][k];
+                        const int lead = (t.flags & (kTileLoadState | kTileCarryIn)) ? 0 : 15;
+                        const int cnt = 18 * t.n_granules + lead;
+                        if (r < cnt) {
+                            row = 18 * regions + 18 - lead + r;
+                            break;
+                        }
+                        r -= cnt;
+                        regions += t.n_granules + 1;
+                    }
+                    float* rowp = xt + (size_t)row * kPitch * 2 + chn;
                     float v[32], y[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = row[2 * i];
+                    for (int i = 0; i < 32; ++i) v[i] = rowp[2 * i];
                     lee_dct<32>(v, y);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) row[2 * i] = y[i];
-                    row[64] = 0.0f; // column 32: V[16] = 0.0 (synthesis.rs:263)
+                    for (int i = 0; i < 32; ++i) rowp[2 * i] = y[i];
+                    rowp[64] = 0.0f; // column 32: V[16] = 0.0 (synthesis.rs:263)
                 }
             }
         }
         __syncthreads();
 
-        // Phase D: polyphase window (synthesis.rs:247-263, :309-327), see window_phase().  // PHASE: D glue+epilogue
-        window_phase<NW>(xt, 18, n * 18, warp, lane, tab->synth_d, a.pcm, gseq0 * 18, 18 << gpf_shift, n_ch == 2);
-        __syncthreads();
-        // The run's last tile publishes the polyphase history (last 15 DCT vectors) for the next batch.
-        if (store_state) {
-            const float* last = xt + (size_t)(18 * (n + 1) - 15) * kPitch * 2;
-            for (int idx = threadIdx.x; idx < 15 * 32; idx += NW * 32) {
-                const int s = idx >> 5, col = idx & 31;
-                st_out->dhist[s][col] = *reinterpret_cast<const float2*>(last + (size_t)(s * kPitch + col) * 2);
+        // Phase D: polyphase window (synthesis.rs:247-263, :309-327), see window_phase().  The group's slots are  // PHASE: D glue+epilogue
+        // enumerated back to back and dealt out in equal shares; a warp's share may span pieces.
+        {
+            int total_slots = 0;
+            for (int k = 0; k < nseg; ++k) total_slots += 18 * sm.seg_stage[par][k].n_granules;
+            const int per = (total_slots + NW - 1) / NW;
+            const int my_begin = warp * per, my_end = min(total_slots, my_begin + per);
+            int regions = 0, first = 0;
+            for (int k = 0; k < nseg; ++k) {
+                const Mp3Tile t = sm.seg_stage[par][k];
+                const int cnt = 18 * t.n_granules;
+                const int b = max(my_begin, first) - first, e = min(my_end, first + cnt) - first;
+                if (b < e) {
+                    const int shift = t.gpf == 2 ? 1 : 0;
+                    const int gseq = ((int)t.first_frame << shift) + t.first_gr;
+                    window_phase(xt, 18 * (regions + 1), b, e, lane, tab->synth_d, a.pcm, gseq * 18, 18 << shift, t.n_ch == 2);
+                }
+                first += cnt;
+                regions += t.n_granules + 1;
             }
         }
-        __syncthreads(); // XT and the stage descriptors are reused by the next tile
+        __syncthreads();
+        // A piece that ends its run (or hands over to the next group) publishes the polyphase history: its last 15
+        // DCT vectors.
+        {
+            int regions = 0;
+            for (int k = 0; k < nseg; ++k) {
+                const Mp3Tile t = sm.seg_stage[par][k];
+                if (t.flags & (kTileStoreState | kTileCarryOut)) {
+                    const uint32_t gk = sm.gen_stage[par][k];
+                    Mp3StreamState* st = (t.flags & kTileCarryOut) ? &sm.carry : a.states + (size_t)t.stream * 2 + ((gk + 1) & 1);
+                    const float* last = xt + (size_t)(18 * (regions + t.n_granules + 1) - 15) * kPitch * 2;
+                    for (int idx = threadIdx.x; idx < 15 * 32; idx += NW * 32) {
+                        const int srow = idx >> 5, col = idx & 31;
+                        st->dhist[srow][col] = *reinterpret_cast<const float2*>(last + (size_t)(srow * kPitch + col) * 2);
+                    }
+                }
+                regions += t.n_granules + 1;
+            }
+        }
+        ti += nseg;
+        __syncthreads(); // XT and the stage descriptors are reused by the next group
     }
 
     // Launch epilogue: the last CTA to retire publishes the new state generation of every run.
@@ -774,6 +874,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
 
 // ---------------------------------------------------------------------------------------------
 int mp3_tile_granules() { return kMp3TileGranules; }
+int mp3_cta_warps() { return kMp3Warps; }
 int mp3_halo_tile_granules() { return kMp3Warps - 2 < kMp3TileGranules ? kMp3Warps - 2 : kMp3TileGranules; }
 
 int mp3_grid_size(cudaError_t* err) {
@@ -783,10 +884,12 @@ int mp3_grid_size(cudaError_t* err) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess && !grid_for_device[dev & 63]) {
         int n_sm = 0, per_sm = 0;
-        e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp3_synth_kernel<kMp3TileGranules, kMp3Warps>, kMp3Warps * 32, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp3_synth_kernel<kMp3TileGranules, kMp3Warps, true>, kMp3Warps * 32, smem);
         if (e == cudaSuccess) grid_for_device[dev & 63] = n_sm * (per_sm > 0 ? per_sm : 1);
     }
     if (err) *err = e;
@@ -799,7 +902,10 @@ cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream) {
     const int max_grid = mp3_grid_size(&e);
     if (e != cudaSuccess) return e;
     if (a.n_ctas <= 0 || a.n_ctas > max_grid) return cudaErrorInvalidConfiguration;
-    mp3_synth_kernel<kMp3TileGranules, kMp3Warps><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
+    if (a.multi_tile_groups)
+        mp3_synth_kernel<kMp3TileGranules, kMp3Warps, true><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
+    else
+        mp3_synth_kernel<kMp3TileGranules, kMp3Warps, false><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -13,9 +13,10 @@ namespace symgpu {
 // would cap the kernel at 96 registers because registers are partitioned per scheduler).  A CTA walks a
 // CHAIN of consecutive tiles of the same stream and carries overlap + polyphase history from one tile
 // to the next through shared memory, so only the first tile of a chain that starts inside a run pays
-// the 2-granule halo.  14 granule jobs in the hybrid phase (16 with a halo); 252 time slots x 2
-// channels = 504 DCT jobs for 512 threads; 252 slots = 16 per warp in the window phase.  Shared
-// memory: 270 XT rows (71 KB) + the TMA stage of 16 granules (74 KB) + carry (8 KB) + scratch.
+// the 2-granule halo.  Short runs (a few frames per stream, the serving shape) are packed several to a
+// group, so that all 16 warps have a granule job.  16 granule jobs in the hybrid phase; 288 time slots
+// x 2 channels = 576 DCT jobs for 512 threads; 288 slots = 18 per warp in the window phase.  Shared
+// memory: 432 XT rows (114 KB) + the TMA stage of 16 granules (74 KB) + carry (8 KB) + scratch.
 #ifndef SYMGPU_MP3_T
 #define SYMGPU_MP3_T 16
 #define SYMGPU_MP3_NW 16
@@ -27,7 +28,12 @@ constexpr int kMp3Warps = SYMGPU_MP3_NW;
 // kTileCarryIn / kTileCarryOut: the tile continues / is continued by the neighbouring tile of the same
 // CTA's chain and exchanges state through shared memory.  A tile with neither input flag recomputes a
 // 2-granule halo (and then holds at most kMp3TileGranules granules with NW >= n + 2).
-enum : uint8_t { kTileLoadState = 1, kTileStoreState = 2, kTileCarryIn = 4, kTileCarryOut = 8 };
+// kTileGroupEnd: the CTA processes its chain in GROUPS of consecutive tiles (pieces of possibly different
+// streams) that together hold at most kMp3Warps granule jobs and kMp3GroupRegions XT regions; the flag marks
+// a group's last tile.  kTileCarryIn only on a group's first tile, kTileCarryOut only on its last.
+enum : uint8_t { kTileLoadState = 1, kTileStoreState = 2, kTileCarryIn = 4, kTileCarryOut = 8, kTileGroupEnd = 16 };
+constexpr int kMp3GroupTiles = 8;    // pieces per group
+constexpr int kMp3GroupRegions = 24; // XT regions per group: one history region + one per granule, per piece
 
 // One step of a CTA's work: `n_granules` consecutive granules of one stream.  Built on the host from
 // the caller's runs (symgpu.cpp: build_plan).
@@ -60,6 +66,7 @@ struct Mp3Args {
     const Mp3Tile* tiles;
     int n_tiles;
     int n_ctas;
+    int multi_tile_groups;     // some group of the plan holds more than one tile (see kTileGroupEnd)
     Mp3StreamState* states; // [n_streams][2] double-buffered, see gen
     uint32_t* gen;          // [n_streams] state generation; buffer (gen & 1) is current
     unsigned* done;         // retired-CTA counter (self-resetting)
@@ -70,6 +77,7 @@ cudaError_t mp3_upload_const(const Mp3Tables& t, cudaStream_t stream);
 cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream);
 int mp3_tile_granules();
 int mp3_halo_tile_granules(); // limit for a tile that recomputes its halo (two warps go to the halo granules)
+int mp3_cta_warps();           // warps per CTA = granule jobs per group
 // Persistent grid size of the kernel on the current device (SM count x resident CTAs), <= 0 on error.
 int mp3_grid_size(cudaError_t* err);
 

@@ -29,6 +29,7 @@ struct Mp3Plan {
     int hdr = 0;              // header size in Mp3Tile entries
     int n_tiles = 0;
     int n_ctas = 0;
+    bool multi = false;       // some group holds more than one tile
 };
 
 // Cuts the caller's runs into CHAINS of tiles, one chain per CTA of the persistent grid: the batch's
@@ -53,6 +54,7 @@ symgpu_status build_plan_for(int grid, uint32_t T, uint32_t n_streams, const sym
         plain_tiles += (n_gran + T - 1) / T;
     }
     if (whole_batch && covered != n_frames) return SYMGPU_ERR_ARG; // runs must tile the batch exactly
+    plan.multi = false;
     plan.n_ctas = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(plain_tiles, 1));
     plan.hdr = (plan.n_ctas + 1 + 3) / 4;
     plan.buf.assign((size_t)plan.hdr, Mp3Tile{});
@@ -120,6 +122,33 @@ symgpu_status build_plan_for(int grid, uint32_t T, uint32_t n_streams, const sym
     }
     while (cta < plan.n_ctas) first[(size_t)++cta] = n_tiles;
     plan.n_tiles = (int)n_tiles;
+    // Groups: consecutive tiles of a chain that the CTA processes together (mp3_kernel.h).  Greedy: a tile
+    // joins the open group unless the group would exceed its job / region / tile budget, the tile takes its
+    // state from the previous group (kTileCarryIn starts a group) or the previous tile hands its state on
+    // (kTileCarryOut ends one).
+    {
+        const int n_warps = mp3_cta_warps(); // granule jobs per group
+        Mp3Tile* tiles = plan.buf.data() + plan.hdr;
+        for (int c = 0; c < plan.n_ctas; ++c) {
+            int jobs = 0, regions = 0, count = 0;
+            for (uint32_t i = first[(size_t)c]; i < first[(size_t)c + 1]; ++i) {
+                Mp3Tile& t = tiles[i];
+                const int tj = t.n_granules + ((t.flags & (kTileLoadState | kTileCarryIn)) ? 0 : 2);
+                const int tr = t.n_granules + 1;
+                const bool fits = count > 0 && count < kMp3GroupTiles && jobs + tj <= n_warps && regions + tr <= kMp3GroupRegions &&
+                                  !(t.flags & kTileCarryIn) && !(tiles[i - 1].flags & kTileCarryOut);
+                if (!fits && count > 0) {
+                    tiles[i - 1].flags |= kTileGroupEnd;
+                    jobs = regions = count = 0;
+                }
+                if (fits) plan.multi = true;
+                jobs += tj;
+                regions += tr;
+                ++count;
+            }
+            if (count > 0) tiles[first[(size_t)c + 1] - 1].flags |= kTileGroupEnd;
+        }
+    }
     std::memcpy(plan.buf.data(), first.data(), first.size() * sizeof(uint32_t));
     return SYMGPU_OK;
 }
@@ -149,9 +178,9 @@ symgpu_status reserve_plan(symgpu_ctx* ctx, size_t entries) {
 }
 
 // Kernel arguments of a plan whose entries sit at `d_plan`.
-Mp3Args plan_args(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_tiles, int n_ctas, const symgpu_mp3_gc* units,
+Mp3Args plan_args(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_tiles, int n_ctas, bool multi, const symgpu_mp3_gc* units,
                   const float* spectra, float* pcm) {
-    return Mp3Args{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas,
+    return Mp3Args{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas, multi ? 1 : 0,
                    ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
 }
 
@@ -171,6 +200,7 @@ symgpu_status ensure_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t 
     ctx->cached_tiles = plan.n_tiles;
     ctx->cached_hdr = plan.hdr;
     ctx->cached_ctas = plan.n_ctas;
+    ctx->cached_multi = plan.multi;
     return SYMGPU_OK;
 }
 
@@ -351,7 +381,7 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
     symgpu_status s = ensure_plan(ctx, runs, n_runs, n_frames);
     if (s != SYMGPU_OK) return s;
     if (ctx->cached_tiles == 0) return SYMGPU_OK;
-    const Mp3Args a = plan_args(ctx, ctx->d_tiles, ctx->cached_hdr, ctx->cached_tiles, ctx->cached_ctas, units, spectra, pcm);
+    const Mp3Args a = plan_args(ctx, ctx->d_tiles, ctx->cached_hdr, ctx->cached_tiles, ctx->cached_ctas, ctx->cached_multi, units, spectra, pcm);
     CU(ctx, mp3_launch(a, ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;
@@ -440,7 +470,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         }
     }
     const int n_slices = (int)std::min<uint32_t>((uint32_t)ctx->n_slices, n_runs);
-    struct Slice { uint32_t r0, r1, f0, f1; int t0, hdr, n_tiles, n_ctas; };
+    struct Slice { uint32_t r0, r1, f0, f1; int t0, hdr, n_tiles, n_ctas; bool multi; };
     std::vector<Slice> slices;
     std::vector<Mp3Tile> all_tiles;
     Mp3Plan plan;
@@ -457,7 +487,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     for (int i = 0; i < n_slices; ++i) {
         w_acc += weight(i);
         const uint32_t target = (uint32_t)((double)n_frames * (w_acc / w_total));
-        Slice sl{r, r, runs[r].first_frame, 0, (int)all_tiles.size(), 0, 0, 0};
+        Slice sl{r, r, runs[r].first_frame, 0, (int)all_tiles.size(), 0, 0, 0, false};
         while (r < n_runs && (runs[r].first_frame + runs[r].n_frames <= target || sl.r1 == sl.r0)) {
             ++r;
             sl.r1 = r;
@@ -470,6 +500,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         sl.hdr = plan.hdr;
         sl.n_tiles = plan.n_tiles;
         sl.n_ctas = plan.n_ctas;
+        sl.multi = plan.multi;
         if (sl.r1 > sl.r0 && sl.n_tiles > 0) slices.push_back(sl);
         if (r >= n_runs) break;
     }
@@ -486,7 +517,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         CU(ctx, copy_in(sl.f0, nf, ctx->copy_in));
         CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
-        const Mp3Args a = plan_args(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, d_units, d_spec, d_pcm);
+        const Mp3Args a = plan_args(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, sl.multi, d_units, d_spec, d_pcm);
         CU(ctx, mp3_launch(a, ctx->stream));
         ctx->launches += 1;
         CU(ctx, pack(sl.f0, (uint32_t)nf));

@@ -10,7 +10,8 @@ from symphonia_b200._native import MP3_RUN_DTYPE
 
 TILE_DTYPE = np.dtype([("first_frame", "<u4"), ("stream", "<u4"), ("first_gr", "<u2"), ("n_granules", "<u2"),
                        ("gpf", "u1"), ("n_ch", "u1"), ("flags", "u1"), ("pad", "u1")])
-LOAD, STORE, CARRY_IN, CARRY_OUT = 1, 2, 4, 8
+LOAD, STORE, CARRY_IN, CARRY_OUT, GROUP_END = 1, 2, 4, 8, 16
+GROUP_TILES, GROUP_REGIONS = 8, 24
 T, NW = 16, 16
 
 
@@ -76,6 +77,22 @@ def _check(runs, n_frames, n_streams, grid):
         if fl & CARRY_OUT:
             assert i + 1 < len(tiles) and chain_of_tile[i + 1] == chain_of_tile[i] and int(tiles[i + 1]["flags"]) & CARRY_IN
         prev = (t, key, q0 + n)
+    # groups: what the CTA processes in one trip
+    for c in range(len(first) - 1):
+        jobs = regions = count = 0
+        for i in range(int(first[c]), int(first[c + 1])):
+            fl, n = int(tiles[i]["flags"]), int(tiles[i]["n_granules"])
+            if count and fl & CARRY_IN:
+                raise AssertionError("a tile that takes its state from the previous group must start a group")
+            jobs += n + (0 if fl & (LOAD | CARRY_IN) else 2)
+            regions += n + 1
+            count += 1
+            assert jobs <= NW and regions <= GROUP_REGIONS and count <= GROUP_TILES
+            if fl & GROUP_END:
+                jobs = regions = count = 0
+            else:
+                assert not fl & CARRY_OUT, "a tile that hands its state on must end its group"
+                assert i + 1 < int(first[c + 1]), "the last tile of a chain ends a group"
     for key, run in run_of_frame.items():
         assert progress.get(key, 0) == int(run["n_frames"]) * int(run["granules_per_frame"] or 2)
     # load balance: no chain carries much more than its share
@@ -106,7 +123,8 @@ def test_bench_shape_has_one_halo_per_chain_at_most():
 def test_single_frame_streams():
     runs, nf = _runs([1] * 8192)
     first, tiles = _check(runs, nf, 8192, 148)
-    assert len(tiles) == 8192 and (tiles["flags"] == (LOAD | STORE)).all()
+    assert len(tiles) == 8192 and ((tiles["flags"] & 15) == (LOAD | STORE)).all()
+    assert ((tiles["flags"] & GROUP_END) != 0).sum() <= 8192 // 8 + 2 * 148  # eight single-frame runs per trip
 
 
 @pytest.mark.parametrize("seed", range(12))

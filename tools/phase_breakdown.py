@@ -16,7 +16,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def line_of_each_instruction(so):
+def line_of_each_instruction(so, variant=None):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
     sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, "mp3_kernel.sm_100a.cubin")],
@@ -24,7 +24,7 @@ def line_of_each_instruction(so):
     out, cur, infn = [], 0, False
     for ln in sass.splitlines():
         if ln.startswith("\t.text.") or ".text." in ln and ln.strip().startswith(".section"):
-            infn = "mp3_synth_kernel" in ln
+            infn = "mp3_synth_kernel" in ln and (variant is None or variant in ln)
         m = re.search(r'//## File ".*mp3_kernel.cu", line (\d+)', ln)
         if m:
             cur = int(m.group(1))
@@ -48,9 +48,12 @@ def phase_table(src):
 def main():
     rep = sys.argv[1]
     so = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "symphonia_b200/libsymgpu.so")
-    lines = line_of_each_instruction(so)
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
+    # the kernel has a single-tile-group and a multi-tile-group instantiation (last template argument)
+    name = next((r[1] for r in rows if r and r[0] == "Kernel Name"), "")
+    variant = "Lb1E" if re.search(r"(true|1)\s*>", name) else "Lb0E"
+    lines = line_of_each_instruction(so, variant)
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     body = rows[hdr_i + 1:]
