@@ -31,9 +31,9 @@ FRAMES_PER_STREAM = 128
 N_FRAMES = N_STREAMS * FRAMES_PER_STREAM
 N_BUFFER_SETS = 4  # rotating input/output sets: 4 x 151 MB = 604 MB > 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum of one mp3_synth_kernel launch on this workload, from the
-# `ncu --set full` capture summarised in profiles/r01c_mp3_ncu_summary.csv (79.7 MB + 32.4 MB; below the
+# `ncu --set full` capture summarised in profiles/r01d_mp3_ncu_summary.csv (79.7 MB + 30.2 MB; below the
 # algorithmic 153 MB because most of the PCM is still in the 126 MB L2 when the launch ends).
-NCU_DRAM_TRAFFIC_BYTES = 112_028_672
+NCU_DRAM_TRAFFIC_BYTES = 109_878_016
 WORKLOAD = "MP3 MPEG-1 Layer III 44.1kHz stereo, batch=8192 frames (64 streams x 128 frames), synthetic spectra"
 
 
