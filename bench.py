@@ -148,6 +148,7 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     eng = sb.Engine(local_rank)
 
