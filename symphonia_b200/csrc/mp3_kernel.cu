@@ -566,7 +566,9 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
                     // Warp-parallel restatement of the two top-down scans (stereo.rs:198-261, :265-482).
                     const bool mpeg1 = g1.flags & SYMGPU_MP3_F_MPEG1;
                     const int inv_pos = mpeg1 ? 7 : 31;
-                    const float(*rt)[2] = mpeg1 ? c_mp3.is_mpeg1 : c_mp3.is_mpeg2[(g1.flags & SYMGPU_MP3_F_SFC_LSB) ? 1 : 0];
+                    // ratio table in GLOBAL memory: the position differs from lane to lane, and a constant-bank
+                    // operand with a lane-dependent index is replayed once per distinct address
+                    const float(*rt)[2] = mpeg1 ? tab->is_mpeg1 : tab->is_mpeg2[(g1.flags & SYMGPU_MP3_F_SFC_LSB) ? 1 : 0];
                     const uint16_t* e = tab->edges[sr][kind1];
                     const int n_e = c_mp3.n_edges[sr][kind1];
                     const int n_iv = n_e - 1;
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
                                 const int pos = g1.scalefacs[k];
                                 if (pos < inv_pos) {
                                     mode = 2;
-                                    ws.sratio[iv] = make_float2(rt[pos][0], rt[pos][1]);
+                                    ws.sratio[iv] = __ldg(reinterpret_cast<const float2*>(rt[pos]));
                                 }
                             }
                         }
