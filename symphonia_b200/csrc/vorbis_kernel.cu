@@ -177,9 +177,13 @@ __device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, cons
 __device__ __forceinline__ void floor1_render(const FloorPoints& p, int n_half, int lane, float* spec,
                                               const float* __restrict__ inv_db) {
     int seg = 0;
-    int x1 = p.seg[1].x0;
+    int x1 = p.seg[1].x0, x2 = p.seg[2].x0; // the boundary after next is fetched ahead of its use
     for (int x = lane; x < n_half; x += 32) {
-        while (x >= x1) x1 = p.seg[++seg + 1].x0; // at most 66 advances per lane in total
+        while (x >= x1) { // at most 66 advances per lane in total
+            ++seg;
+            x1 = x2;
+            x2 = p.seg[min(seg + 2, 67)].x0;
+        }
         const int4 w = *reinterpret_cast<const int4*>(&p.seg[seg]);
         const int x0 = w.x, y0 = (int)(short)(w.y & 0xffff), base = w.y >> 16;
         const int ady = (int)(short)(w.z & 0xffff), adx_s = w.z >> 16;
@@ -251,6 +255,9 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
         bs = u.block_flag ? bs1 : bs0;
         const int n2 = bs >> 1;
         NamedSync sync{1 + grp, kVorbisThreads};
+        // pull this packet's residue (both channels) towards the SM while the floors are built
+        for (uint32_t i = 32u * gt; i < 2u * a.slot; i += 32u * kVorbisThreads)
+            if ((i % a.slot) < (uint32_t)n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residue + (size_t)p * 2 * a.slot + i));
         // (1) floor curves: warp = channel, rendered into the channel's spectrum area
         if (warp_in_grp < n_ch) {
             const int ch = warp_in_grp;
