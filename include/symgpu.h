@@ -314,6 +314,27 @@ symgpu_status symgpu_mp3_synth_host_packed(symgpu_ctx* ctx, const symgpu_mp3_gc*
                                            const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
                                            int format, void* out);
 
+/* ===================================================================================================
+ * MPEG Layer I / II: the polyphase synthesis bank alone, i.e. `synthesis::synthesis`
+ * (symphonia-bundle-mp3/src/synthesis.rs:158-344) as the Layer I / II decoders call it after dequantising
+ * their sub-band samples (layer1/mod.rs:184-194 with 12 time slots per frame, layer2/mod.rs:374-384 with 36).
+ *   subbands [n_frames][2][32][n_slots]   = the decoders' samples[ch][n_slots * sb + s]
+ *   pcm      [n_frames][2][1152]          plane(ch)[0 .. 32 * n_slots) written (384 or 1152 samples)
+ * Streams use the Layer III state slots (symgpu_mp3_streams_alloc / symgpu_mp3_stream_reset): every layer
+ * owns the same `synthesis: [SynthesisState; 2]` (layer1/mod.rs:63, layer2/mod.rs:220, layer3/mod.rs:257).
+ * ================================================================================================= */
+typedef struct symgpu_mpa12_run {
+    uint32_t stream;
+    uint32_t first_frame;
+    uint32_t n_frames;
+    uint8_t channels;     /* 1 or 2 */
+    uint8_t reserved[3];
+} symgpu_mpa12_run;
+symgpu_status symgpu_mpa12_synth_host(symgpu_ctx* ctx, const float* subbands, const symgpu_mpa12_run* runs, uint32_t n_runs,
+                                      uint32_t n_frames, uint32_t n_slots, float* pcm);
+symgpu_status symgpu_mpa12_synth_dev(symgpu_ctx* ctx, const float* subbands, const symgpu_mpa12_run* runs, uint32_t n_runs,
+                                     uint32_t n_frames, uint32_t n_slots, float* pcm);
+
 /* The same synthesis fed with the QUANTISED spectra, i.e. what the Huffman stage decodes before the
  * reference turns it into f32 (read_huffman_samples: buf[i] = sign * POW43[x],
  * symphonia-bundle-mp3/src/layer3/requantize.rs:23-32, :128, :144):

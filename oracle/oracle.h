@@ -24,6 +24,8 @@ int oracle_mp3_batch(oracle_mp3_state* states, const symgpu_mp3_gc* units, const
                      const symgpu_mp3_run* runs, uint32_t n_runs, float* pcm);
 int oracle_mp3_batch_mt(oracle_mp3_state* states, const symgpu_mp3_gc* units, const float* spectra,
                         const symgpu_mp3_run* runs, uint32_t n_runs, float* pcm, int n_threads);
+int oracle_mpa12_batch(oracle_mp3_state* states, const float* subbands, const symgpu_mpa12_run* runs, uint32_t n_runs,
+                       uint32_t n_slots, float* pcm);
 void oracle_mp3_dct32(const float* x, float* y);
 void oracle_mp3_imdct36(float* x, const float* window, float* overlap);
 void oracle_mp3_imdct12_win(float* x, const float* window, float* overlap);

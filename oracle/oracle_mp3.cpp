@@ -611,6 +611,23 @@ int oracle_mp3_batch_mt(oracle_mp3_state* states, const symgpu_mp3_gc* units, co
     return rc;
 }
 
+// Layer I / II: polyphase synthesis of the decoders' sub-band samples, frame by frame and channel by channel
+// (layer1/mod.rs:184-194 with n_slots = 12, layer2/mod.rs:374-384 with n_slots = 36).  Same contract as
+// symgpu_mpa12_synth_host: subbands [n_frames][2][32][n_slots] -> pcm [n_frames][2][1152].
+int oracle_mpa12_batch(oracle_mp3_state* states, const float* subbands, const symgpu_mpa12_run* runs, uint32_t n_runs,
+                       uint32_t n_slots, float* pcm) {
+    if (n_slots != 12 && n_slots != 36) return 1;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        oracle_mp3_state* st = states + runs[r].stream;
+        const int n_ch = runs[r].channels ? runs[r].channels : 2;
+        for (uint32_t f = runs[r].first_frame; f < runs[r].first_frame + runs[r].n_frames; ++f)
+            for (int ch = 0; ch < n_ch; ++ch)
+                polyphase(st, ch, (int)n_slots, subbands + ((size_t)f * 2 + ch) * 32 * n_slots,
+                          pcm + ((size_t)f * 2 + ch) * 1152);
+    }
+    return 0;
+}
+
 // Building blocks exposed for the known-answer tests.
 void oracle_mp3_dct32(const float* x, float* y) { lee_dct(x, y, 32); }
 void oracle_mp3_imdct36(float* x, const float* window, float* overlap) { imdct36(x, window, overlap); }

@@ -30,6 +30,11 @@ MP3_RUN_DTYPE = np.dtype([
 ])
 assert MP3_RUN_DTYPE.itemsize == 16
 
+# `symgpu_mpa12_run`, 16 bytes (Layer I / II)
+MPA12_RUN_DTYPE = np.dtype([("stream", "<u4"), ("first_frame", "<u4"), ("n_frames", "<u4"), ("channels", "u1"),
+                            ("reserved", "u1", (3,))])
+assert MPA12_RUN_DTYPE.itemsize == 16
+
 # AAC / Vorbis structs (include/symgpu.h)
 AAC_UNIT_DTYPE = np.dtype([("window_sequence", "u1"), ("window_shape", "u1"), ("prev_window_shape", "u1"),
                            ("n_tns", "u1"), ("tns_first", "<u4"), ("reserved", "<u4", (2,))])
@@ -128,6 +133,10 @@ def lib():
     L.symgpu_pcm_pack_host.argtypes = [vp, vp, sz, vp, u32, u32, u32, u32, ctypes.c_int, vp, sz]
     L.symgpu_mp3_synth_host_packed.restype = ctypes.c_int
     L.symgpu_mp3_synth_host_packed.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
+    for name in ("symgpu_mpa12_synth_host", "symgpu_mpa12_synth_dev"):
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [vp, vp, vp, u32, u32, u32, vp]
     L.symgpu_mp3_synth_host_quantized.restype = ctypes.c_int
     L.symgpu_mp3_synth_host_quantized.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
     _LIB = L

@@ -266,6 +266,8 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
 // The signs are folded into the per-lane coefficients ((-d)*D == d*(-D) exactly).  `slot_seq0` is the
 // batch-wide sequence number of the first slot: slots of a frame are contiguous in a PCM plane
 // (plane[gr*576 + t*32 + i]) and frames are SYMGPU_MP3_FRAME_FLOATS apart.
+// TWO_JUMPS: a block of 16 slots may cross two frame boundaries (Layer I: 12 slots per frame).
+template <bool TWO_JUMPS = false>
 __device__ __forceinline__ void window_phase(const float* xt, int row0, int begin, int end, int lane,
                                              const float* __restrict__ synth_d, float* __restrict__ pcm, int slot_seq0,
                                              int slots_per_frame, bool stereo) {
@@ -315,6 +317,7 @@ __device__ __forceinline__ void window_phase(const float* xt, int row0, int begi
                     o1 += v1.y * dhi[j];
                 }
                 float* o = (u < kj ? out0 : out1) + u * 32;
+                if (TWO_JUMPS && u >= kj + slots_per_frame) o += frame_jump;
                 o[off1] = o1;
                 o[0] = o0;
             }
@@ -872,6 +875,143 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
             if (a.tiles[i].flags & kTileStoreState) a.gen[a.tiles[i].stream] += 1;
         if (threadIdx.x == 0) *a.done = 0;
     }
+}
+
+// =============================================================================================
+// MPEG Layer I / II: polyphase synthesis only (synthesis.rs:158-344 called with n_frames = 12 / 36 from
+// layer1/mod.rs:184-194 and layer2/mod.rs:374-384).  The sub-band samples the layer decoders produce go
+// straight into XT rows; phases C (DCT-32) and D (window) are the Layer III kernel's.  A CTA walks a chain of
+// tiles of whole frames of one stream; the 15 history vectors come from the stream state (run start), stay in
+// shared memory between the tiles of a chain, or are recomputed from the previous frames' samples (a chain
+// that starts inside a run).
+// =============================================================================================
+namespace {
+constexpr int kMpa12Slots = 288; // time slots per tile: 8 Layer II frames or 24 Layer I frames
+struct Mpa12Smem {
+    float xt[(18 + kMpa12Slots) * kPitch * 2];
+    bool is_last;
+};
+} // namespace
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) mpa12_synth_kernel(Mpa12Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Mpa12Smem& sm = *reinterpret_cast<Mpa12Smem*>(smem_raw);
+    float* xt = sm.xt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_slots = a.n_slots;
+    const Mp3Tables* __restrict__ tab = a.tab;
+    const int t_begin = (int)a.cta_first[blockIdx.x], t_end = (int)a.cta_first[blockIdx.x + 1];
+    for (int ti = t_begin; ti < t_end; ++ti) {
+        const Mp3Tile tile = a.tiles[ti];
+        const int n = tile.n_granules; // frames
+        const int total = n * n_slots;
+        const bool from_state = tile.flags & kTileLoadState, carried = tile.flags & kTileCarryIn;
+        const uint32_t gen = a.gen[tile.stream];
+        const Mp3StreamState* st_in = a.states + (size_t)tile.stream * 2 + (gen & 1);
+        Mp3StreamState* st_out = a.states + (size_t)tile.stream * 2 + ((gen + 1) & 1);
+        const float* in = a.subbands + (size_t)tile.first_frame * 64 * n_slots;
+        // history rows 3..17: DCT vectors from the state, or (halo) the raw samples of the 15 slots before the tile
+        if (from_state) {
+            for (int idx = threadIdx.x; idx < 15 * kPitch; idx += NW * 32) {
+                const int srow = idx / kPitch, col = idx - srow * kPitch;
+                float2 v = make_float2(0.0f, 0.0f);
+                if (col < 32) v = st_in->dhist[srow][col];
+                *reinterpret_cast<float2*>(xt + (size_t)((3 + srow) * kPitch + col) * 2) = v;
+            }
+        } else if (!carried) {
+            for (int idx = threadIdx.x; idx < 15 * 64; idx += NW * 32) {
+                const int j = idx >> 6, sb = (idx >> 1) & 31, ch = idx & 1;
+                const int gslot = (int)tile.first_frame * n_slots - 15 + j; // >= 0: two earlier frames of the run are in the batch
+                const int f = gslot / n_slots, s = gslot - f * n_slots;
+                float v = 0.0f;
+                if (ch < tile.n_ch) v = __ldg(a.subbands + ((size_t)(f * 2 + ch) * 32 + sb) * n_slots + s);
+                xt[((3 + j) * kPitch + sb) * 2 + ch] = v;
+            }
+        }
+        // the tile's samples: in[((f * 2 + ch) * 32 + sb) * n_slots + s] -> row 18 + f * n_slots + s, column sb
+        {
+            const int per_frame = 64 * n_slots, count = n * per_frame;
+            for (int idx = threadIdx.x; idx < count; idx += NW * 32) {
+                const int f = idx / per_frame, r = idx - f * per_frame;
+                const int chsb = r / n_slots, s = r - chsb * n_slots;
+                const int ch = chsb >> 5, sb = chsb & 31;
+                const float v = ch < tile.n_ch ? __ldg(in + idx) : 0.0f;
+                xt[((18 + f * n_slots + s) * kPitch + sb) * 2 + ch] = v;
+            }
+        }
+        __syncthreads();
+        { // Phase C
+            const int row_begin = (from_state || carried) ? 18 : 3;
+            const int row_end = 18 + total;
+            const int chn = lane >> 4;
+            for (int base = row_begin + warp * 16; base < row_end; base += NW * 16) {
+                const int r = base + (lane & 15);
+                if (r < row_end) {
+                    float* rowp = xt + (size_t)r * kPitch * 2 + chn;
+                    float v[32], y[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = rowp[2 * i];
+                    lee_dct<32>(v, y);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) rowp[2 * i] = y[i];
+                    rowp[64] = 0.0f;
+                }
+            }
+        }
+        __syncthreads();
+        { // Phase D
+            const int per = (total + NW - 1) / NW;
+            const int b = warp * per, e = min(total, b + per);
+            window_phase<true>(xt, 18, b, e, lane, tab->synth_d, a.pcm, (int)tile.first_frame * n_slots, n_slots, tile.n_ch == 2);
+        }
+        __syncthreads();
+        // the last 15 DCT vectors: rows 3 + total .. 17 + total (older history rows included when total < 15)
+        if (tile.flags & (kTileStoreState | kTileCarryOut)) {
+            float2 keep[(15 * kPitch + NW * 32 - 1) / (NW * 32)];
+            int k = 0;
+            for (int idx = threadIdx.x; idx < 15 * kPitch; idx += NW * 32, ++k) {
+                const int srow = idx / kPitch, col = idx - srow * kPitch;
+                keep[k] = *reinterpret_cast<const float2*>(xt + (size_t)((3 + total + srow) * kPitch + col) * 2);
+            }
+            __syncthreads();
+            k = 0;
+            for (int idx = threadIdx.x; idx < 15 * kPitch; idx += NW * 32, ++k) {
+                const int srow = idx / kPitch, col = idx - srow * kPitch;
+                if (tile.flags & kTileStoreState) {
+                    if (col < 32) st_out->dhist[srow][col] = keep[k];
+                } else {
+                    *reinterpret_cast<float2*>(xt + (size_t)((3 + srow) * kPitch + col) * 2) = keep[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        sm.is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (sm.is_last) {
+        for (int i = threadIdx.x; i < a.n_tiles; i += NW * 32)
+            if (a.tiles[i].flags & kTileStoreState) a.gen[a.tiles[i].stream] += 1;
+        if (threadIdx.x == 0) *a.done = 0;
+    }
+}
+
+int mpa12_tile_frames(int n_slots) { return n_slots > 0 ? kMpa12Slots / n_slots : 0; }
+
+cudaError_t mpa12_launch(const Mpa12Args& a, cudaStream_t stream) {
+    constexpr size_t smem = sizeof(Mpa12Smem);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mpa12_synth_kernel<kMp3Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (a.n_ctas <= 0) return cudaErrorInvalidConfiguration;
+    mpa12_synth_kernel<kMp3Warps><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

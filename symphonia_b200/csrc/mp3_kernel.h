@@ -73,6 +73,24 @@ struct Mp3Args {
     const Mp3Tables* tab;
 };
 
+// MPEG Layer I / II polyphase synthesis (mpa12_synth_kernel): tiles are whole frames of one stream, `n_granules`
+// counts frames; per-stream state = Mp3StreamState.dhist (the overlap part is unused).
+struct Mpa12Args {
+    const float* subbands;     // [n_frames][2][32][n_slots]: samples[ch][n_slots * sb + s] of the layer decoders
+    float* pcm;                // [n_frames][2][1152], the first 32 * n_slots samples of a plane are written
+    const uint32_t* cta_first;
+    const Mp3Tile* tiles;
+    int n_tiles;
+    int n_ctas;
+    int n_slots;               // 12 (Layer I) or 36 (Layer II)
+    Mp3StreamState* states;
+    uint32_t* gen;
+    unsigned* done;
+    const Mp3Tables* tab;
+};
+cudaError_t mpa12_launch(const Mpa12Args& a, cudaStream_t stream);
+int mpa12_tile_frames(int n_slots); // frames per tile
+
 cudaError_t mp3_upload_const(const Mp3Tables& t, cudaStream_t stream);
 cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream);
 int mp3_tile_granules();

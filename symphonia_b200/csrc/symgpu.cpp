@@ -36,9 +36,10 @@ struct Mp3Plan {
 // granules (in run order) are split into n_ctas contiguous shares; inside a share every run segment is
 // cut into equal tiles that hand their state on through shared memory.  Only a segment that starts
 // inside a run recomputes the 2-granule halo.  Returns SYMGPU_OK or an argument / limit error.
-symgpu_status build_plan_for(int grid, uint32_t T, uint32_t n_streams, const symgpu_mp3_run* runs, uint32_t n_runs,
-                             uint32_t n_frames, Mp3Plan& plan, bool whole_batch) {
-    const uint32_t T_halo = (uint32_t)mp3_halo_tile_granules(); // a halo tile spends two of its warps on the halo
+// T: units (granules; whole frames for Layer I / II) per tile; T_halo: limit for a tile that recomputes its halo;
+// group: mark groups of tiles for the Layer III kernel.
+symgpu_status build_plan_for(int grid, uint32_t T, uint32_t T_halo, bool group, uint32_t n_streams, const symgpu_mp3_run* runs,
+                             uint32_t n_runs, uint32_t n_frames, Mp3Plan& plan, bool whole_batch) {
     uint64_t covered = 0, total_gran = 0, plain_tiles = 0;
     for (uint32_t r = 0; r < n_runs; ++r) {
         const symgpu_mp3_run& run = runs[r];
@@ -126,7 +127,7 @@ symgpu_status build_plan_for(int grid, uint32_t T, uint32_t n_streams, const sym
     // joins the open group unless the group would exceed its job / region / tile budget, the tile takes its
     // state from the previous group (kTileCarryIn starts a group) or the previous tile hands its state on
     // (kTileCarryOut ends one).
-    {
+    if (group) {
         const int n_warps = mp3_cta_warps(); // granule jobs per group
         Mp3Tile* tiles = plan.buf.data() + plan.hdr;
         for (int c = 0; c < plan.n_ctas; ++c) {
@@ -158,7 +159,8 @@ symgpu_status build_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n
     cudaError_t ce = cudaSuccess;
     const int grid = mp3_grid_size(&ce);
     if (ce != cudaSuccess || grid <= 0) return cuda_fail(ctx, ce, "mp3_grid_size");
-    return build_plan_for(grid, (uint32_t)mp3_tile_granules(), ctx->n_mp3_streams, runs, n_runs, n_frames, plan, whole_batch);
+    return build_plan_for(grid, (uint32_t)mp3_tile_granules(), (uint32_t)mp3_halo_tile_granules(), true, ctx->n_mp3_streams, runs,
+                          n_runs, n_frames, plan, whole_batch);
 }
 
 // Makes room for `entries` plan entries in the device / pinned host buffers.
@@ -217,7 +219,9 @@ int symgpu_abi_version(void) { return SYMGPU_ABI_VERSION; }
 size_t symgpu_debug_mp3_plan(int grid, uint32_t n_streams, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
                              void* out, size_t cap, int* n_ctas, int* n_tiles, int* hdr) {
     Mp3Plan plan;
-    if (build_plan_for(grid, (uint32_t)mp3_tile_granules(), n_streams, runs, n_runs, n_frames, plan, true) != SYMGPU_OK) return 0;
+    if (build_plan_for(grid, (uint32_t)mp3_tile_granules(), (uint32_t)mp3_halo_tile_granules(), true, n_streams, runs, n_runs,
+                       n_frames, plan, true) != SYMGPU_OK)
+        return 0;
     if (out) std::memcpy(out, plan.buf.data(), std::min(cap, plan.buf.size()) * sizeof(Mp3Tile));
     if (n_ctas) *n_ctas = plan.n_ctas;
     if (n_tiles) *n_tiles = plan.n_tiles;
@@ -610,6 +614,65 @@ symgpu_status symgpu_pcm_pack_host(symgpu_ctx* ctx, const float* pcm, size_t pcm
                             plane_stride, frames, format, base + in_bytes + span_bytes);
     if (s != SYMGPU_OK) return s;
     CU(ctx, cudaMemcpyAsync(out, base + in_bytes + span_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SYMGPU_OK;
+}
+
+// ---- MPEG Layer I / II ---------------------------------------------------------------------------------
+static symgpu_status mpa12_plan(symgpu_ctx* ctx, const symgpu_mpa12_run* runs, uint32_t n_runs, uint32_t n_frames, uint32_t n_slots,
+                                Mp3Plan& plan) {
+    if (n_slots != 12 && n_slots != 36) return SYMGPU_ERR_ARG;
+    cudaError_t ce = cudaSuccess;
+    const int grid = mp3_grid_size(&ce);
+    if (ce != cudaSuccess || grid <= 0) return cuda_fail(ctx, ce, "mp3_grid_size");
+    std::vector<symgpu_mp3_run> as_frames(n_runs); // units of the planner = frames
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        if (runs[r].reserved[0] || runs[r].reserved[1] || runs[r].reserved[2]) return SYMGPU_ERR_ARG;
+        as_frames[r] = symgpu_mp3_run{runs[r].stream, runs[r].first_frame, runs[r].n_frames, 1, runs[r].channels, 0};
+    }
+    const uint32_t T = (uint32_t)mpa12_tile_frames((int)n_slots);
+    return build_plan_for(grid, T, T, false, ctx->n_mp3_streams, as_frames.data(), n_runs, n_frames, plan, true);
+}
+
+symgpu_status symgpu_mpa12_synth_dev(symgpu_ctx* ctx, const float* subbands, const symgpu_mpa12_run* runs, uint32_t n_runs,
+                                     uint32_t n_frames, uint32_t n_slots, float* pcm) {
+    if (!ctx || !subbands || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (n_frames == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    Mp3Plan plan;
+    symgpu_status s = mpa12_plan(ctx, runs, n_runs, n_frames, n_slots, plan);
+    if (s != SYMGPU_OK) return s;
+    s = reserve_plan(ctx, plan.buf.size());
+    if (s != SYMGPU_OK) return s;
+    ctx->cached_runs.clear(); // the Layer III plan on the device is being replaced
+    ctx->cached_frames = 0;
+    std::memcpy(ctx->h_tiles, plan.buf.data(), plan.buf.size() * sizeof(Mp3Tile));
+    CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, plan.buf.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
+    if (plan.n_tiles == 0) return SYMGPU_OK;
+    Mpa12Args a{subbands, pcm, reinterpret_cast<const uint32_t*>(ctx->d_tiles), ctx->d_tiles + plan.hdr, plan.n_tiles, plan.n_ctas,
+                (int)n_slots, ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
+    CU(ctx, mpa12_launch(a, ctx->stream));
+    ctx->launches += 1;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_mpa12_synth_host(symgpu_ctx* ctx, const float* subbands, const symgpu_mpa12_run* runs, uint32_t n_runs,
+                                      uint32_t n_frames, uint32_t n_slots, float* pcm) {
+    if (!ctx || !subbands || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (n_slots != 12 && n_slots != 36) return SYMGPU_ERR_ARG;
+    if (n_frames == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    const size_t in_bytes = (size_t)n_frames * 64 * n_slots * sizeof(float);
+    const size_t out_bytes = (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
+    symgpu_status s = ensure_stage(ctx, in_bytes + out_bytes);
+    if (s != SYMGPU_OK) return s;
+    float* d_in = static_cast<float*>(ctx->d_stage);
+    float* d_out = reinterpret_cast<float*>(static_cast<char*>(ctx->d_stage) + in_bytes);
+    CU(ctx, cudaMemcpyAsync(d_in, subbands, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream)); // the part of a plane a layer does not fill is defined as zero
+    s = symgpu_mpa12_synth_dev(ctx, d_in, runs, n_runs, n_frames, n_slots, d_out);
+    if (s != SYMGPU_OK) return s;
+    CU(ctx, cudaMemcpyAsync(pcm, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SYMGPU_OK;
 }

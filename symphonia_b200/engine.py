@@ -8,7 +8,7 @@ import ctypes
 import numpy as np
 
 from . import _native
-from ._native import (AAC_RUN_DTYPE, AAC_TNS_DTYPE, AAC_UNIT_DTYPE, FMT_NUMPY, MP3_GC_DTYPE, MP3_RUN_DTYPE,
+from ._native import (AAC_RUN_DTYPE, AAC_TNS_DTYPE, AAC_UNIT_DTYPE, FMT_NUMPY, MP3_GC_DTYPE, MP3_RUN_DTYPE, MPA12_RUN_DTYPE,
                       PCM_SPAN_DTYPE, VORBIS_FLOOR1_DTYPE, VORBIS_RUN_DTYPE, VORBIS_STREAM_DTYPE, VORBIS_UNIT_DTYPE)
 
 
@@ -138,6 +138,28 @@ class Engine:
                                                               len(runs), n_frames, -1 if fmt is None else int(fmt),
                                                               _np_ptr(out)))
         return out
+
+    # -- MPEG Layer I / II ---------------------------------------------------------------------
+    def mpa12_synth_host(self, subbands, runs, out=None):
+        """subbands [F,2,32,n_slots] f32 (n_slots 12: Layer I, 36: Layer II), runs MPA12_RUN_DTYPE -> pcm [F,2,1152]
+        (the first 32*n_slots samples of a plane are the frame's PCM).  Uses the MP3 stream state slots."""
+        subbands = np.ascontiguousarray(subbands, dtype=np.float32)
+        runs = np.ascontiguousarray(runs, dtype=MPA12_RUN_DTYPE)
+        n_frames, n_slots = subbands.shape[0], subbands.shape[-1]
+        if subbands.shape[1:3] != (2, 32):
+            raise ValueError("subbands must be [n_frames, 2, 32, n_slots]")
+        if out is None:
+            out = np.empty((n_frames, 2, 1152), dtype=np.float32)
+        self._check(self._lib.symgpu_mpa12_synth_host(self._ctx, _np_ptr(subbands), _np_ptr(runs), len(runs), n_frames,
+                                                      n_slots, _np_ptr(out)))
+        return out
+
+    def mpa12_synth_dev(self, subbands_t, runs, n_slots, pcm_t):
+        runs = np.ascontiguousarray(runs, dtype=MPA12_RUN_DTYPE)
+        n_frames = subbands_t.numel() // (64 * n_slots)
+        assert subbands_t.is_cuda and pcm_t.is_cuda and pcm_t.numel() == n_frames * 2304
+        self._check(self._lib.symgpu_mpa12_synth_dev(self._ctx, ctypes.c_void_p(subbands_t.data_ptr()), _np_ptr(runs), len(runs),
+                                                     n_frames, n_slots, ctypes.c_void_p(pcm_t.data_ptr())))
 
     # -- output stage -------------------------------------------------------------------------
     def pcm_pack_host(self, pcm, spans, channels, fmt, out_frames, plane_stride=0, frames=0, n_spans=None, out=None):

@@ -103,6 +103,29 @@ def mp3_batch(n_streams=64, frames_per_stream=128, seed=SEED_BASE + 1, sample_ra
     return units, spectra, runs
 
 
+def mpa12_batch(n_streams=64, frames_per_stream=128, layer=2, seed=SEED_BASE + 4, channels=2):
+    """MPEG Layer I (12 time slots per frame) / Layer II (36) batch: dequantised, scaled sub-band samples as the layer
+    decoders hand them to the synthesis bank (layer1/mod.rs:150-180, layer2/mod.rs:330-372): amplitudes falling with
+    the sub-band index, the top sub-bands unallocated (exact zeros).
+    Returns (subbands [S*F,2,32,n_slots] f32, runs [S] MPA12_RUN_DTYPE)."""
+    from ._native import MPA12_RUN_DTYPE
+    rng = np.random.Generator(np.random.PCG64(seed))
+    S, F = int(n_streams), int(frames_per_stream)
+    n_slots = 12 if layer == 1 else 36
+    env = (2.0 ** (-np.arange(32) / 4.0))[None, None, :, None]
+    x = (rng.standard_normal((S * F, 2, 32, n_slots)) * env).astype(np.float32)
+    sblimit = rng.integers(8, 33, size=(S * F, 1, 1, 1))
+    x = np.where(np.arange(32)[None, None, :, None] < sblimit, x, np.float32(0.0)).astype(np.float32)
+    if channels == 1:
+        x[:, 1] = 0.0
+    runs = np.zeros(S, dtype=MPA12_RUN_DTYPE)
+    runs["stream"] = np.arange(S)
+    runs["first_frame"] = np.arange(S) * F
+    runs["n_frames"] = F
+    runs["channels"] = channels
+    return x, runs
+
+
 def mp3_quantize(spectra, pow43=None):
     """Inverse of read_huffman_samples' table lookup: the int16 q with sign(q) * POW43[|q|] == spectra, exactly."""
     if pow43 is None:

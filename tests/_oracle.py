@@ -97,6 +97,19 @@ def pcm_pack(lib, pcm, spans, channels, fmt, out_frames, plane_stride=0, frames=
     return out
 
 
+def mpa12_batch(lib, subbands, runs, n_streams, states=None):
+    """oracle_mpa12_batch with fresh (or the given) per-stream synthesis state."""
+    if states is None:
+        states = (Mp3State * n_streams)()
+    subbands = np.ascontiguousarray(subbands, dtype=np.float32)
+    runs = np.ascontiguousarray(runs)
+    pcm = np.zeros((subbands.shape[0], 2, 1152), dtype=np.float32)
+    lib.oracle_mpa12_batch.restype = ctypes.c_int
+    lib.oracle_mpa12_batch.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+    rc = lib.oracle_mpa12_batch(ctypes.byref(states), ptr(subbands), ptr(runs), len(runs), subbands.shape[-1], ptr(pcm))
+    return rc, pcm, states
+
+
 def mp3_batch(lib, units, spectra, runs, n_streams):
     """Runs the oracle over a batch laid out as symgpu_mp3_synth_host expects; fresh stream state."""
     n_frames = spectra.shape[0]

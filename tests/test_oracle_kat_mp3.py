@@ -118,3 +118,22 @@ def test_pow43_table(oracle):
     # f32 powf with the f32 exponent 4.0/3.0 (slightly above 4/3), as the reference computes it:
     # 8^(4/3) is 16.000002, not 16.  Pinned so nobody "fixes" it.
     assert np.float32(oracle.oracle_mp3_pow43(8)) == np.float32(16.000002)
+
+
+def test_layer12_batch_is_the_pinned_polyphase_bank(oracle):
+    """oracle_mpa12_batch (Layer I / II, layer1/mod.rs:184-194, layer2/mod.rs:374-384) is the polyphase bank pinned
+    above, fed frame by frame with samples[ch][n_slots * sb + s]; the FIFO runs on across frames."""
+    import ctypes
+    from symphonia_b200 import workloads
+    from tests import _oracle
+    for layer, n_slots in ((1, 12), (2, 36)):
+        x, runs = workloads.mpa12_batch(2, 5, layer=layer, seed=90 + layer)
+        rc, pcm, _ = _oracle.mpa12_batch(oracle, x, runs, 2)
+        assert rc == 0
+        st = _oracle.Mp3State()
+        out = np.zeros(32 * n_slots, dtype=np.float32)
+        for f in range(5):  # stream 0, channel 1
+            frame = np.ascontiguousarray(x[f, 1])
+            oracle.oracle_mp3_polyphase(ctypes.byref(st), 1, n_slots, _oracle.ptr(frame), _oracle.ptr(out))
+            assert (out.view(np.uint32) == pcm[f, 1, :32 * n_slots].view(np.uint32)).all()
+        assert np.abs(pcm).max() > 0.1
