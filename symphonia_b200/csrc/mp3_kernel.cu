@@ -929,15 +929,24 @@ __global__ void __launch_bounds__(NW * 32, 1) mpa12_synth_kernel(Mpa12Args a) {
                 xt[((3 + j) * kPitch + sb) * 2 + ch] = v;
             }
         }
-        // the tile's samples: in[((f * 2 + ch) * 32 + sb) * n_slots + s] -> row 18 + f * n_slots + s, column sb
+        // the tile's samples: in[((f * 2 + ch) * 32 + sb) * n_slots + s] -> row 18 + f * n_slots + s, column sb.
+        // A thread takes one (frame, sub-band): it reads the n_slots samples of both channels (two contiguous runs
+        // of 48 / 144 bytes, float4 loads) and writes (ch0, ch1) pairs -- 64-bit stores, lanes on distinct banks.
         {
-            const int per_frame = 64 * n_slots, count = n * per_frame;
-            for (int idx = threadIdx.x; idx < count; idx += NW * 32) {
-                const int f = idx / per_frame, r = idx - f * per_frame;
-                const int chsb = r / n_slots, s = r - chsb * n_slots;
-                const int ch = chsb >> 5, sb = chsb & 31;
-                const float v = ch < tile.n_ch ? __ldg(in + idx) : 0.0f;
-                xt[((18 + f * n_slots + s) * kPitch + sb) * 2 + ch] = v;
+            const bool stereo = tile.n_ch == 2;
+            for (int pair = threadIdx.x; pair < n * 32; pair += NW * 32) {
+                const int f = pair >> 5, sb = pair & 31;
+                const float4* s0 = reinterpret_cast<const float4*>(in + ((size_t)(f * 2) * 32 + sb) * n_slots);
+                const float4* s1 = reinterpret_cast<const float4*>(in + ((size_t)(f * 2 + 1) * 32 + sb) * n_slots);
+                float2* dst = reinterpret_cast<float2*>(xt) + (size_t)(18 + f * n_slots) * kPitch + sb;
+                for (int q = 0; q < n_slots / 4; ++q) {
+                    const float4 a0 = __ldg(s0 + q);
+                    const float4 a1 = stereo ? __ldg(s1 + q) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    dst[(4 * q + 0) * kPitch] = make_float2(a0.x, a1.x);
+                    dst[(4 * q + 1) * kPitch] = make_float2(a0.y, a1.y);
+                    dst[(4 * q + 2) * kPitch] = make_float2(a0.z, a1.z);
+                    dst[(4 * q + 3) * kPitch] = make_float2(a0.w, a1.w);
+                }
             }
         }
         __syncthreads();
