@@ -37,7 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--codec", default="both", choices=["aac", "vorbis", "both", "mp3-short", "mixed", "mpa2", "all"])
+    ap.add_argument("--codec", default="both", choices=["aac", "vorbis", "both", "mp3-short", "mixed", "mpa2", "flac", "all"])
     ap.add_argument("--tns", type=float, default=0.2)
     args = ap.parse_args()
     import torch
@@ -77,6 +77,52 @@ def main():
         audio = S * F * 1152 / 44100.0
         ach = algo / (ms * 1e-3) / 1e9
         print(json.dumps({"codec": "mp2", "workload": "MPEG Layer II 44.1kHz stereo, 8192 frames (64 streams x 128), polyphase synthesis",
+                          "value": audio / (ms * 1e-3), "unit": "audio-s/s", "kernel_ms": ms,
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                       "algorithmic_bytes_per_launch": algo}}), flush=True)
+    if args.codec == "flac":  # not part of "all": the kernel's last fix has not been re-run on a GPU yet
+        # FLAC 16-bit stereo, 2048 frames of 4096 samples: prediction + decorrelation + scaling, in place
+        NF, BS = 2048, 4096
+        frames, subs, samples = workloads.flac_batch(64, BS, seed=workloads.SEED_BASE + 6)
+        reps = NF // 64  # the 64 generated frames repeated (the generator's exact-integer encoder is slow)
+        fr = np.tile(frames, reps)
+        sb_ = np.tile(subs, reps)
+        fr["first_subframe"] = np.arange(NF) * 2
+        sb_["offset"] = np.arange(NF * 2, dtype=np.uint64) * BS
+        smp = np.tile(samples, reps)
+        d_fr = torch.from_numpy(fr.view(np.uint8).reshape(-1).copy()).to(dev)
+        d_sb = torch.from_numpy(sb_.view(np.uint8).reshape(-1).copy()).to(dev)
+        src = torch.from_numpy(smp).to(dev)
+        work = [torch.empty_like(src) for _ in range(SETS)]
+
+        for w in work:  # restoration is in place: every step starts from the residuals again
+            w.copy_(src)
+        # time copy alone, then copy + restore; the difference is the restoration
+        ext = torch.cuda.ExternalStream(eng.cuda_stream)
+        def timed(fn, n):
+            with torch.cuda.stream(ext):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(n):
+                    fn(i)
+                b.record()
+            eng.sync()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        def both(i):
+            with torch.cuda.stream(ext):
+                work[i % SETS].copy_(src)
+            eng.flac_restore_dev(d_fr, NF, d_sb, NF * 2, work[i % SETS])
+        def copy_only(i):
+            with torch.cuda.stream(ext):
+                work[i % SETS].copy_(src)
+        timed(both, 3)
+        ms = timed(both, args.steps) - timed(copy_only, args.steps)
+        n_samples = int(sb_["n"].sum())
+        algo = n_samples * 8 + NF * 2 * 144
+        audio = float(sb_["n"][0::2].sum()) / 44100.0
+        ach = algo / (ms * 1e-3) / 1e9
+        print(json.dumps({"codec": "flac", "workload": "FLAC 16-bit stereo, 2048 frames x 4096 samples: prediction, decorrelation, scaling (in place)",
                           "value": audio / (ms * 1e-3), "unit": "audio-s/s", "kernel_ms": ms,
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                        "algorithmic_bytes_per_launch": algo}}), flush=True)

@@ -335,6 +335,46 @@ symgpu_status symgpu_mpa12_synth_host(symgpu_ctx* ctx, const float* subbands, co
 symgpu_status symgpu_mpa12_synth_dev(symgpu_ctx* ctx, const float* subbands, const symgpu_mpa12_run* runs, uint32_t n_runs,
                                      uint32_t n_frames, uint32_t n_slots, float* pcm);
 
+/* ===================================================================================================
+ * FLAC: what FlacDecoder::decode_inner does after the Rice residuals are decoded --
+ * integer prediction, wasted-bits shift, channel decorrelation, scaling to 32 bits.  Bit-exact (integers).
+ * EXPERIMENTAL in this revision: see tests/test_flac_parity_gpu.py for what has and has not been verified.
+ *   fixed_predict / lpc_predict         symphonia-bundle-flac/src/decoder.rs:663-752
+ *   samples_shl (dropped_bps)           decoder.rs:384-394
+ *   decorrelate_left_side / mid_side / right_side   decoder.rs:32-82
+ *   output scaling `sample << (32 - bps)`            decoder.rs:232-241
+ * `samples` is one int32 buffer; a sub-frame owns `n` consecutive samples at `offset`: on entry its warm-up
+ * samples followed by the residuals (what decode_verbatim + decode_residual leave in the plane, decoder.rs:437-
+ * 443, :459-481), or its constant in samples[offset], or the verbatim samples; on return the channel's PCM.
+ * ================================================================================================= */
+typedef enum symgpu_flac_subframe_type { SYMGPU_FLAC_CONSTANT = 0, SYMGPU_FLAC_VERBATIM = 1, SYMGPU_FLAC_FIXED = 2, SYMGPU_FLAC_LPC = 3 } symgpu_flac_subframe_type;
+typedef enum symgpu_flac_assignment { SYMGPU_FLAC_INDEPENDENT = 0, SYMGPU_FLAC_LEFT_SIDE = 1, SYMGPU_FLAC_MID_SIDE = 2, SYMGPU_FLAC_RIGHT_SIDE = 3 } symgpu_flac_assignment;
+typedef struct symgpu_flac_subframe {   /* 144 bytes */
+    uint64_t offset;     /* first sample of the sub-frame in `samples`                                   */
+    uint32_t n;          /* block size                                                                  */
+    uint8_t type;        /* symgpu_flac_subframe_type                                                   */
+    uint8_t order;       /* FIXED: 0..4, LPC: 1..32; must not exceed n (decoder.rs:429, :456)           */
+    uint8_t shift;       /* LPC: qlp_coeff_shift, 0..15 (negative shifts are unsupported, decoder.rs:504) */
+    uint8_t wasted;      /* dropped_bps: samples are shifted left by it after prediction (decoder.rs:382) */
+    int32_t coeffs[32];  /* LPC: coeffs[j] multiplies sample i-1-j (the reference keeps them reversed)    */
+} symgpu_flac_subframe;
+typedef struct symgpu_flac_frame {      /* 16 bytes */
+    uint32_t first_subframe; /* index of channel 0's sub-frame; channel c is first_subframe + c          */
+    uint8_t channels;        /* 1..8; LEFT_SIDE / MID_SIDE / RIGHT_SIDE need 2                            */
+    uint8_t assignment;      /* symgpu_flac_assignment                                                   */
+    uint8_t bits_per_sample; /* 4..32 of the frame; the output is scaled by 32 - bits_per_sample          */
+    uint8_t reserved;
+    uint32_t reserved2[2];
+} symgpu_flac_frame;
+/* In place on `samples` (n_samples int32).  Host variant: host memory; device variant: frames, subframes and
+ * samples in device memory, asynchronous on the context stream (descriptors are then not validated). */
+symgpu_status symgpu_flac_restore_host(symgpu_ctx* ctx, const symgpu_flac_frame* frames, uint32_t n_frames,
+                                       const symgpu_flac_subframe* subframes, uint32_t n_subframes, int32_t* samples,
+                                       size_t n_samples);
+symgpu_status symgpu_flac_restore_dev(symgpu_ctx* ctx, const symgpu_flac_frame* frames, uint32_t n_frames,
+                                      const symgpu_flac_subframe* subframes, uint32_t n_subframes, int32_t* samples,
+                                      size_t n_samples);
+
 /* The same synthesis fed with the QUANTISED spectra, i.e. what the Huffman stage decodes before the
  * reference turns it into f32 (read_huffman_samples: buf[i] = sign * POW43[x],
  * symphonia-bundle-mp3/src/layer3/requantize.rs:23-32, :128, :144):

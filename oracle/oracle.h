@@ -1,5 +1,5 @@
 // ORACLE (test infrastructure, NOT product code).  C surface of liboracle.so; see the headers of
-// oracle_mp3.cpp / oracle_mdct.cpp / oracle_aac.cpp / oracle_vorbis.cpp / oracle_conv.cpp for what each restates.
+// oracle_mp3.cpp / oracle_mdct.cpp / oracle_aac.cpp / oracle_vorbis.cpp / oracle_conv.cpp / oracle_flac.cpp for what each restates.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -62,6 +62,10 @@ int oracle_vorbis_batch(oracle_vorbis_state* states, const symgpu_vorbis_stream*
                         int n_threads);
 const float* oracle_vorbis_window(int bs);
 float oracle_vorbis_inverse_db(int i);
+
+// ---- FLAC integer restoration (oracle_flac.cpp) ----
+int oracle_flac_restore(const symgpu_flac_frame* frames, uint32_t n_frames, const symgpu_flac_subframe* subframes,
+                        uint32_t n_subframes, int32_t* samples, size_t n_samples);
 
 // ---- output stage (oracle_conv.cpp) ----
 int16_t oracle_conv_s16(float s);

@@ -35,6 +35,15 @@ MPA12_RUN_DTYPE = np.dtype([("stream", "<u4"), ("first_frame", "<u4"), ("n_frame
                             ("reserved", "u1", (3,))])
 assert MPA12_RUN_DTYPE.itemsize == 16
 
+# FLAC (include/symgpu.h): `symgpu_flac_subframe` 144 bytes, `symgpu_flac_frame` 16 bytes
+FLAC_SUBFRAME_DTYPE = np.dtype([("offset", "<u8"), ("n", "<u4"), ("type", "u1"), ("order", "u1"), ("shift", "u1"),
+                                ("wasted", "u1"), ("coeffs", "<i4", (32,))])
+FLAC_FRAME_DTYPE = np.dtype([("first_subframe", "<u4"), ("channels", "u1"), ("assignment", "u1"), ("bits_per_sample", "u1"),
+                             ("reserved", "u1"), ("reserved2", "<u4", (2,))])
+assert FLAC_SUBFRAME_DTYPE.itemsize == 144 and FLAC_FRAME_DTYPE.itemsize == 16
+FLAC_CONSTANT, FLAC_VERBATIM, FLAC_FIXED, FLAC_LPC = 0, 1, 2, 3
+FLAC_INDEPENDENT, FLAC_LEFT_SIDE, FLAC_MID_SIDE, FLAC_RIGHT_SIDE = 0, 1, 2, 3
+
 # AAC / Vorbis structs (include/symgpu.h)
 AAC_UNIT_DTYPE = np.dtype([("window_sequence", "u1"), ("window_shape", "u1"), ("prev_window_shape", "u1"),
                            ("n_tns", "u1"), ("tns_first", "<u4"), ("reserved", "<u4", (2,))])
@@ -137,6 +146,10 @@ def lib():
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, vp, vp, u32, u32, u32, vp]
+    for name in ("symgpu_flac_restore_host", "symgpu_flac_restore_dev"):
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [vp, vp, u32, vp, u32, vp, sz]
     L.symgpu_mp3_synth_host_quantized.restype = ctypes.c_int
     L.symgpu_mp3_synth_host_quantized.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
     _LIB = L

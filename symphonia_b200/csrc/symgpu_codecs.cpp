@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "flac_kernel.h"
 
 using namespace symgpu;
 using namespace symgpu_detail;
@@ -349,6 +350,62 @@ symgpu_status symgpu_vorbis_synth_host(symgpu_ctx* ctx, const symgpu_vorbis_unit
     s = symgpu_vorbis_synth_dev(ctx, d_units, d_fy, d_res, runs, n_runs, n_packets, slot, d_pcm);
     if (s != SYMGPU_OK) return s;
     CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SYMGPU_OK;
+}
+
+// ---- FLAC integer restoration --------------------------------------------------------------
+symgpu_status symgpu_flac_restore_dev(symgpu_ctx* ctx, const symgpu_flac_frame* frames, uint32_t n_frames,
+                                      const symgpu_flac_subframe* subframes, uint32_t n_subframes, int32_t* samples,
+                                      size_t n_samples) {
+    if (!ctx || !frames || !subframes || !samples) return SYMGPU_ERR_ARG;
+    if (n_frames == 0 && n_subframes == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    CU(ctx, flac_launch(frames, n_frames, subframes, n_subframes, samples, n_samples, ctx->stream));
+    ctx->launches += (n_subframes ? 1 : 0) + (n_frames ? 1 : 0);
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_flac_restore_host(symgpu_ctx* ctx, const symgpu_flac_frame* frames, uint32_t n_frames,
+                                       const symgpu_flac_subframe* subframes, uint32_t n_subframes, int32_t* samples,
+                                       size_t n_samples) {
+    if (!ctx || !frames || !subframes || !samples) return SYMGPU_ERR_ARG;
+    // What read_subframe / decode_linear / decode_fixed_linear refuse (decoder.rs:335-347, :429-431, :456-474,
+    // :503-505) is refused here; the kernels additionally never leave the buffer.
+    for (uint32_t k = 0; k < n_subframes; ++k) {
+        const symgpu_flac_subframe& sf = subframes[k];
+        if (sf.n == 0 || sf.offset > n_samples || sf.n > n_samples - sf.offset) return SYMGPU_ERR_ARG;
+        if (sf.type > SYMGPU_FLAC_LPC || sf.wasted > 32) return SYMGPU_ERR_DECODE;
+        if (sf.type == SYMGPU_FLAC_FIXED && (sf.order > 4 || sf.order > sf.n)) return SYMGPU_ERR_DECODE;
+        if (sf.type == SYMGPU_FLAC_LPC && (sf.order < 1 || sf.order > 32 || sf.order > sf.n)) return SYMGPU_ERR_DECODE;
+        if (sf.type == SYMGPU_FLAC_LPC && sf.shift > 15) return SYMGPU_ERR_UNSUPPORTED;
+    }
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        const symgpu_flac_frame& fr = frames[f];
+        if (fr.channels < 1 || fr.channels > 8 || (uint64_t)fr.first_subframe + fr.channels > n_subframes) return SYMGPU_ERR_ARG;
+        if (fr.bits_per_sample < 1 || fr.bits_per_sample > 32) return SYMGPU_ERR_DECODE;
+        if (fr.assignment > SYMGPU_FLAC_RIGHT_SIDE) return SYMGPU_ERR_DECODE;
+        if (fr.assignment != SYMGPU_FLAC_INDEPENDENT &&
+            (fr.channels != 2 || subframes[fr.first_subframe].n != subframes[fr.first_subframe + 1].n))
+            return SYMGPU_ERR_DECODE;
+    }
+    if (n_frames == 0 && n_subframes == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    const size_t sample_bytes = (n_samples * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t sub_bytes = ((size_t)n_subframes * sizeof(symgpu_flac_subframe) + 255) & ~(size_t)255;
+    const size_t frame_bytes = (size_t)n_frames * sizeof(symgpu_flac_frame);
+    symgpu_status s = ensure_stage(ctx, sample_bytes + sub_bytes + frame_bytes);
+    if (s != SYMGPU_OK) return s;
+    char* base = static_cast<char*>(ctx->d_stage);
+    int32_t* d_samples = reinterpret_cast<int32_t*>(base);
+    symgpu_flac_subframe* d_subs = reinterpret_cast<symgpu_flac_subframe*>(base + sample_bytes);
+    symgpu_flac_frame* d_frames = reinterpret_cast<symgpu_flac_frame*>(base + sample_bytes + sub_bytes);
+    CU(ctx, cudaMemcpyAsync(d_samples, samples, n_samples * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_subs, subframes, (size_t)n_subframes * sizeof(symgpu_flac_subframe), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_frames, frames, frame_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    s = symgpu_flac_restore_dev(ctx, d_frames, n_frames, d_subs, n_subframes, d_samples, n_samples);
+    if (s != SYMGPU_OK) return s;
+    CU(ctx, cudaMemcpyAsync(samples, d_samples, n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SYMGPU_OK;
 }

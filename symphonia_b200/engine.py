@@ -161,6 +161,23 @@ class Engine:
         self._check(self._lib.symgpu_mpa12_synth_dev(self._ctx, ctypes.c_void_p(subbands_t.data_ptr()), _np_ptr(runs), len(runs),
                                                      n_frames, n_slots, ctypes.c_void_p(pcm_t.data_ptr())))
 
+    # -- FLAC ---------------------------------------------------------------------------------
+    def flac_restore_host(self, frames, subframes, samples):
+        """In place on `samples` (int32): prediction, wasted-bits shift, channel decorrelation, scaling to 32 bits."""
+        from ._native import FLAC_FRAME_DTYPE, FLAC_SUBFRAME_DTYPE
+        frames = np.ascontiguousarray(frames, dtype=FLAC_FRAME_DTYPE)
+        subframes = np.ascontiguousarray(subframes, dtype=FLAC_SUBFRAME_DTYPE)
+        assert samples.dtype == np.int32 and samples.flags.c_contiguous
+        self._check(self._lib.symgpu_flac_restore_host(self._ctx, _np_ptr(frames), len(frames), _np_ptr(subframes), len(subframes),
+                                                       _np_ptr(samples), samples.size))
+        return samples
+
+    def flac_restore_dev(self, frames_t, n_frames, subframes_t, n_subframes, samples_t):
+        assert frames_t.is_cuda and subframes_t.is_cuda and samples_t.is_cuda
+        self._check(self._lib.symgpu_flac_restore_dev(self._ctx, ctypes.c_void_p(frames_t.data_ptr()), n_frames,
+                                                      ctypes.c_void_p(subframes_t.data_ptr()), n_subframes,
+                                                      ctypes.c_void_p(samples_t.data_ptr()), samples_t.numel()))
+
     # -- output stage -------------------------------------------------------------------------
     def pcm_pack_host(self, pcm, spans, channels, fmt, out_frames, plane_stride=0, frames=0, n_spans=None, out=None):
         """Trim + interleave + convert planar f32 `pcm` (any shape, flat indexing) into [out_frames, channels]

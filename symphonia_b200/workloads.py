@@ -126,6 +126,91 @@ def mpa12_batch(n_streams=64, frames_per_stream=128, layer=2, seed=SEED_BASE + 4
     return x, runs
 
 
+def flac_batch(n_frames=64, block_size=4096, seed=SEED_BASE + 5, bps=16, channels=2, return_pcm=False):
+    """FLAC frames as the Rice stage leaves them: per sub-frame the warm-up samples followed by the residuals of an
+    ENCODER written from the format definition (residual = sample - (sum(c[j] * s[i-1-j]) >> shift), exact Python /
+    int64 arithmetic), so that restoring them must give back the PCM generated here.
+    Returns (frames, subframes, samples [int32]) and, with return_pcm, the expected planes scaled to 32 bits."""
+    from ._native import (FLAC_CONSTANT, FLAC_FIXED, FLAC_FRAME_DTYPE, FLAC_INDEPENDENT, FLAC_LEFT_SIDE, FLAC_LPC, FLAC_MID_SIDE,
+                          FLAC_RIGHT_SIDE, FLAC_SUBFRAME_DTYPE, FLAC_VERBATIM)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    frames = np.zeros(n_frames, dtype=FLAC_FRAME_DTYPE)
+    subs = np.zeros(n_frames * channels, dtype=FLAC_SUBFRAME_DTYPE)
+    samples = np.zeros(n_frames * channels * block_size, dtype=np.int32)
+    expect = np.zeros_like(samples)
+    fixed = {0: [], 1: [1], 2: [2, -1], 3: [3, -3, 1], 4: [4, -6, 4, -1]}
+    t = np.arange(block_size)
+    for f in range(n_frames):
+        n = block_size if f % 7 else max(channels and 40, block_size // 3 + 1)  # some short blocks
+        amp = (1 << (bps - 2)) - 1
+        # a smooth signal plus noise, per channel, in `bps` bits
+        pcm = [np.round(amp * 0.6 * np.sin(2 * np.pi * (rng.uniform(20, 2000) / 44100.0) * t[:n] + rng.uniform(0, 6))
+                        + rng.normal(0, amp * 0.02, n)).astype(np.int64) for _ in range(channels)]
+        assignment = int(rng.integers(0, 4)) if channels == 2 else FLAC_INDEPENDENT
+        frames[f] = (f * channels, channels, assignment, bps, 0, (0, 0))
+        if assignment == FLAC_LEFT_SIDE:
+            planes = [pcm[0], pcm[0] - pcm[1]]
+        elif assignment == FLAC_MID_SIDE:
+            planes = [(pcm[0] + pcm[1]) >> 1, pcm[0] - pcm[1]]
+        elif assignment == FLAC_RIGHT_SIDE:
+            planes = [pcm[0] - pcm[1], pcm[1]]
+        else:
+            planes = pcm
+        for c in range(channels):
+            k = f * channels + c
+            off = k * block_size
+            x = planes[c].copy()
+            kind = int(rng.choice([FLAC_LPC, FLAC_LPC, FLAC_LPC, FLAC_FIXED, FLAC_VERBATIM, FLAC_CONSTANT]))
+            wasted = int(rng.choice([0, 0, 0, 1, 3]))
+            if wasted:  # the encoder drops low zero bits: make them zero in the signal this plane carries
+                x = (x >> wasted) << wasted
+            if kind == FLAC_CONSTANT:
+                x[:] = x[0]
+            # what the other channel / the listener must end up with follows from the planes actually coded
+            planes[c] = x
+            y = x >> wasted
+            sub = subs[k]
+            sub["offset"], sub["n"], sub["type"], sub["wasted"] = off, n, kind, wasted
+            if kind == FLAC_CONSTANT:
+                samples[off] = y[0]
+            elif kind == FLAC_VERBATIM:
+                samples[off:off + n] = y
+            else:
+                if kind == FLAC_FIXED:
+                    order = int(rng.integers(0, 5))
+                    coeffs, shift = fixed[order], 0
+                else:
+                    order = int(rng.integers(1, 33)) if rng.random() < 0.3 else int(rng.integers(1, 13))
+                    order = min(order, n)
+                    prec, shift = int(rng.integers(5, 16)), int(rng.integers(0, 15))
+                    coeffs = [int(v) for v in rng.integers(-(1 << (prec - 1)), 1 << (prec - 1), size=order)]
+                    # keep the recursion stable-ish: scale so that sum |c| >> shift stays around 1
+                    while sum(abs(v) for v in coeffs) >> shift > 2 and shift < 15:
+                        shift += 1
+                    sub["coeffs"][:order] = coeffs
+                sub["order"], sub["shift"] = order, shift
+                res = y.copy()
+                for i in range(order, n):
+                    pred = sum(coeffs[j] * int(y[i - 1 - j]) for j in range(order)) >> shift
+                    res[i] = y[i] - pred
+                samples[off:off + n] = ((res + (1 << 31)) % (1 << 32) - (1 << 31)).astype(np.int32)  # residuals as i32
+        # expected output planes after decorrelation of the planes actually coded, scaled to 32 bits
+        if assignment == FLAC_LEFT_SIDE:
+            out = [planes[0], planes[0] - planes[1]]
+        elif assignment == FLAC_MID_SIDE:
+            mid = (planes[0] << 1) | (planes[1] & 1)
+            out = [(mid + planes[1]) >> 1, (mid - planes[1]) >> 1]
+        elif assignment == FLAC_RIGHT_SIDE:
+            out = [planes[0] + planes[1], planes[1]]
+        else:
+            out = planes
+        for c in range(channels):
+            off = (f * channels + c) * block_size
+            v = (out[c] << (32 - bps)) if bps < 32 else out[c]
+            expect[off:off + n] = ((v + (1 << 31)) % (1 << 32) - (1 << 31)).astype(np.int32)
+    return (frames, subs, samples, expect) if return_pcm else (frames, subs, samples)
+
+
 def mp3_quantize(spectra, pow43=None):
     """Inverse of read_huffman_samples' table lookup: the int16 q with sign(q) * POW43[|q|] == spectra, exactly."""
     if pow43 is None:
