@@ -314,6 +314,15 @@ symgpu_status symgpu_mp3_synth_host_packed(symgpu_ctx* ctx, const symgpu_mp3_gc*
                                            const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
                                            int format, void* out);
 
+/* Descriptor checks of the host entry points, callable on their own (no device needed): what the reference's
+ * parsers guarantee about the units they hand to synthesis (3-bit subblock_gain, block types 0..3, rzero <= 576,
+ * sample-rate index 0..8, equal block types on a joint-stereo pair -- stereo.rs:503-505; AAC window sequence 0..3,
+ * window shape 0..1, TNS filters inside the 1024 lines with order <= 20 -- tns.rs:17-20).  SYMGPU_ERR_DECODE for a
+ * malformed unit; the host entry points run them before anything is sent to the device (the device entry points
+ * cannot: their descriptors are already in HBM). */
+symgpu_status symgpu_mp3_units_check(const symgpu_mp3_gc* units, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames);
+symgpu_status symgpu_aac_units_check(const symgpu_aac_unit* units, const symgpu_aac_tns* tns, uint32_t n_tns, uint32_t n_frames);
+
 /* ===================================================================================================
  * MPEG Layer I / II: the polyphase synthesis bank alone, i.e. `synthesis::synthesis`
  * (symphonia-bundle-mp3/src/synthesis.rs:158-344) as the Layer I / II decoders call it after dequantising

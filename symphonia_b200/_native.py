@@ -150,6 +150,10 @@ def lib():
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, vp, u32, vp, u32, vp, sz]
+    L.symgpu_mp3_units_check.restype = ctypes.c_int
+    L.symgpu_mp3_units_check.argtypes = [vp, vp, u32, u32]
+    L.symgpu_aac_units_check.restype = ctypes.c_int
+    L.symgpu_aac_units_check.argtypes = [vp, vp, u32, u32]
     L.symgpu_mp3_synth_host_quantized.restype = ctypes.c_int
     L.symgpu_mp3_synth_host_quantized.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
     _LIB = L

@@ -405,6 +405,10 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     const size_t sample_bytes = format < 0 ? sizeof(float) : symgpu_sample_bytes(format);
     if (sample_bytes == 0) return SYMGPU_ERR_ARG;
     if (n_frames == 0) return SYMGPU_OK;
+    {
+        const symgpu_status chk = symgpu_mp3_units_check(units, runs, n_runs, n_frames);
+        if (chk != SYMGPU_OK) return chk;
+    }
     DeviceGuard guard(ctx->device);
     const size_t unit_bytes = (size_t)n_frames * 4 * sizeof(symgpu_mp3_gc);
     const size_t spec_bytes = (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
@@ -536,6 +540,33 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
 }
 
 extern "C" {
+
+symgpu_status symgpu_mp3_units_check(const symgpu_mp3_gc* units, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames) {
+    if (!units || !runs) return SYMGPU_ERR_ARG;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_mp3_run& run = runs[r];
+        const int gpf = run.granules_per_frame ? run.granules_per_frame : 2;
+        const int n_ch = run.channels ? run.channels : 2;
+        if (gpf < 1 || gpf > 2 || n_ch < 1 || n_ch > 2) return SYMGPU_ERR_ARG;
+        if ((uint64_t)run.first_frame + run.n_frames > n_frames) return SYMGPU_ERR_ARG;
+        for (uint32_t f = run.first_frame; f < run.first_frame + run.n_frames; ++f)
+            for (int gr = 0; gr < gpf; ++gr) {
+                const symgpu_mp3_gc* u = units + ((size_t)f * 2 + gr) * 2;
+                for (int ch = 0; ch < n_ch; ++ch) {
+                    const symgpu_mp3_gc& g = u[ch];
+                    if (g.block_type > SYMGPU_MP3_END || g.sample_rate_idx > 8 || g.rzero > 576) return SYMGPU_ERR_DECODE;
+                    if (g.subblock_gain[0] > 7 || g.subblock_gain[1] > 7 || g.subblock_gain[2] > 7) return SYMGPU_ERR_DECODE;
+                }
+                // stereo.rs:503-505: joint stereo needs the same block type (and mixed flag) on both channels
+                if (n_ch == 2 && (u[0].flags & (SYMGPU_MP3_F_MID_SIDE | SYMGPU_MP3_F_INTENSITY)) &&
+                    (u[0].block_type != u[1].block_type ||
+                     ((u[0].flags ^ u[1].flags) & SYMGPU_MP3_F_MIXED && u[0].block_type == SYMGPU_MP3_SHORT)))
+                    return SYMGPU_ERR_DECODE;
+                if (n_ch == 2 && u[0].sample_rate_idx != u[1].sample_rate_idx) return SYMGPU_ERR_DECODE;
+            }
+    }
+    return SYMGPU_OK;
+}
 
 symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units, const float* spectra,
                                     const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, float* pcm) {

@@ -164,11 +164,27 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
     return SYMGPU_OK;
 }
 
+symgpu_status symgpu_aac_units_check(const symgpu_aac_unit* units, const symgpu_aac_tns* tns, uint32_t n_tns, uint32_t n_frames) {
+    if (!units || (n_tns && !tns)) return SYMGPU_ERR_ARG;
+    for (size_t k = 0; k < (size_t)n_frames * 2; ++k) {
+        const symgpu_aac_unit& u = units[k];
+        if (u.window_sequence > SYMGPU_AAC_LONG_STOP || u.window_shape > 1 || u.prev_window_shape > 1) return SYMGPU_ERR_DECODE;
+        if (u.n_tns && ((uint64_t)u.tns_first + u.n_tns > n_tns)) return SYMGPU_ERR_DECODE;
+    }
+    for (uint32_t f = 0; f < n_tns; ++f)
+        if (tns[f].order > 20 || tns[f].start > tns[f].end || tns[f].end > 1024) return SYMGPU_ERR_DECODE;
+    return SYMGPU_OK;
+}
+
 symgpu_status symgpu_aac_synth_host(symgpu_ctx* ctx, const symgpu_aac_unit* units, const symgpu_aac_tns* tns,
                                     uint32_t n_tns, const float* coeffs, const symgpu_aac_run* runs, uint32_t n_runs,
                                     uint32_t n_frames, float* pcm) {
     if (!ctx || !units || !coeffs || !runs || !pcm || (n_tns && !tns)) return SYMGPU_ERR_ARG;
     if (n_frames == 0) return SYMGPU_OK;
+    {
+        const symgpu_status chk = symgpu_aac_units_check(units, tns, n_tns, n_frames);
+        if (chk != SYMGPU_OK) return chk;
+    }
     DeviceGuard guard(ctx->device);
     const size_t unit_bytes = (size_t)n_frames * 2 * sizeof(symgpu_aac_unit);
     const size_t spec_bytes = (size_t)n_frames * 2 * 1024 * sizeof(float);
