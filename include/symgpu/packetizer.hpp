@@ -1,0 +1,753 @@
+// symgpu packetisers: cut MPEG audio, ADTS and Ogg byte streams into codec packets the way
+// the reference's format readers do, but as INDEX BUILDERS over one resident byte buffer.
+//
+// The reference pulls packets one at a time out of a consuming reader and copies each into its own allocation
+// (symphonia-bundle-mp3/src/demuxer.rs:598-604, symphonia-codec-aac/src/adts.rs:303-308,
+// symphonia-format-ogg/src/logical.rs:577-597).  A batched device decoder wants the opposite: the whole file
+// goes to HBM in ONE copy and the front-end kernels are handed a table of (offset, length) references into it.
+// So nothing here copies payload bytes: an MPEG / ADTS packet is a byte range of the source, an Ogg packet --
+// which may straddle pages -- is a short gather list of ranges.  The byte RULES (what counts as sync, what is
+// skipped as junk, which frames are tags, how packets continue across pages, where the time stamps and trims come
+// from) are the reference's, cited at each function, and are checked bit for bit against oracle/packetizer_oracle.py.
+//
+// Header-only C++17, no dependencies, no device code.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace symgpu {
+namespace packet {
+
+enum class Status : uint8_t {
+    Ok = 0,
+    EndOfStream,  // the bytes ran out (the reference: IoError UnexpectedEof)
+    DecodeError,  // malformed stream (Error::DecodeError)
+    Unsupported,  // well-formed but not handled by the reference either (Error::Unsupported)
+};
+
+// A byte range of the source buffer.
+struct Piece {
+    uint64_t offset;
+    uint32_t len;
+};
+
+namespace detail {
+inline uint32_t be32(const uint8_t* p) { return uint32_t(p[0]) << 24 | uint32_t(p[1]) << 16 | uint32_t(p[2]) << 8 | p[3]; }
+inline uint32_t be24(const uint8_t* p) { return uint32_t(p[0]) << 16 | uint32_t(p[1]) << 8 | p[2]; }
+inline uint32_t be16(const uint8_t* p) { return uint32_t(p[0]) << 8 | p[1]; }
+inline uint32_t le32(const uint8_t* p) { return uint32_t(p[3]) << 24 | uint32_t(p[2]) << 16 | uint32_t(p[1]) << 8 | p[0]; }
+inline uint64_t le64(const uint8_t* p) { return uint64_t(le32(p + 4)) << 32 | le32(p); }
+
+struct Crc32Table {  // slicing-by-8: t[k][b] = contribution of byte b seen k bytes before the end of an 8-byte block
+    uint32_t t[8][256];
+    constexpr Crc32Table() : t() {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i << 24;
+            for (int k = 0; k < 8; ++k) c = (c & 0x80000000u) ? (c << 1) ^ 0x04c11db7u : c << 1;
+            t[0][i] = c;
+        }
+        for (int k = 1; k < 8; ++k)
+            for (uint32_t i = 0; i < 256; ++i) t[k][i] = (t[k - 1][i] << 8) ^ t[0][t[k - 1][i] >> 24];
+    }
+};
+struct Crc16Table {
+    uint16_t t[256];
+    constexpr Crc16Table() : t() {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0xa001u : c >> 1;
+            t[i] = uint16_t(c);
+        }
+    }
+};
+}  // namespace detail
+
+// CRC-32, polynomial 0x04c11db7, most-significant bit first, no final xor; the caller supplies the initial state
+// (Ogg pages: 0).  symphonia-core/src/checksum/crc32.rs:543-570.
+inline uint32_t crc32_update(uint32_t state, const uint8_t* p, size_t n) {
+    static constexpr detail::Crc32Table tab{};
+    for (; n >= 8; p += 8, n -= 8) {
+        const uint32_t hi = state ^ detail::be32(p), lo = detail::be32(p + 4);
+        state = tab.t[7][hi >> 24] ^ tab.t[6][(hi >> 16) & 0xff] ^ tab.t[5][(hi >> 8) & 0xff] ^ tab.t[4][hi & 0xff] ^
+                tab.t[3][lo >> 24] ^ tab.t[2][(lo >> 16) & 0xff] ^ tab.t[1][(lo >> 8) & 0xff] ^ tab.t[0][lo & 0xff];
+    }
+    for (size_t i = 0; i < n; ++i) state = (state << 8) ^ tab.t[0][(state >> 24) ^ p[i]];
+    return state;
+}
+
+// CRC-16, polynomial 0x8005, least-significant bit first, no final xor (the LAME tag's checksum).
+// symphonia-core/src/checksum/crc16.rs:377-404.
+inline uint16_t crc16_ansi_le_update(uint16_t state, const uint8_t* p, size_t n) {
+    static constexpr detail::Crc16Table tab{};
+    for (size_t i = 0; i < n; ++i) state = uint16_t((state >> 8) ^ tab.t[(state ^ p[i]) & 0xff]);
+    return state;
+}
+
+// =====================================================================================================================
+// MPEG audio (Layers I-III)
+// =====================================================================================================================
+
+enum class MpaVersion : uint8_t { Mpeg1 = 0, Mpeg2 = 1, Mpeg2p5 = 2 };
+enum class MpaMode : uint8_t { Stereo = 0, JointStereo = 1, DualMono = 2, Mono = 3 };
+
+// The 32-bit frame header, decoded.  symphonia-bundle-mp3/src/header.rs:107-233, common.rs:155-212.
+struct MpaHeader {
+    MpaVersion version;
+    uint8_t layer;            // 1, 2 or 3
+    MpaMode mode;
+    uint8_t sample_rate_idx;  // 0..8: 44.1 / 48 / 32 kHz, then the halved and quartered rates (the reference's table index)
+    bool mid_side;            // Layer III joint stereo
+    bool intensity;           // Layer III joint stereo
+    uint8_t bound;            // Layers I / II joint stereo: first sub-band coded in intensity stereo, else 32
+    uint8_t emphasis;         // 0 none, 1 50/15 us, 3 CCITT J.17
+    bool copyrighted, original, padding, crc;
+    uint32_t bitrate;         // bit/s
+    uint32_t sample_rate;     // Hz
+    uint32_t frame_size;      // bytes AFTER the 4-byte header word
+
+    int n_channels() const { return mode == MpaMode::Mono ? 1 : 2; }
+    int n_granules() const { return version == MpaVersion::Mpeg1 ? 2 : 1; }
+    uint32_t samples_per_frame() const { return layer == 1 ? 384u : layer == 2 ? 1152u : 576u * uint32_t(n_granules()); }
+    uint32_t header_size() const { return 4u + (crc ? 2u : 0u); }
+    uint32_t side_info_len() const {
+        const bool mono = mode == MpaMode::Mono;
+        return version == MpaVersion::Mpeg1 ? (mono ? 17u : 32u) : (mono ? 9u : 17u);
+    }
+};
+
+// header.rs:71-75: eleven set bits.
+inline bool mpa_is_synced(uint32_t w) { return (w & 0xffe00000u) == 0xffe00000u; }
+
+// header.rs:49-69: the cheap plausibility test applied while hunting for sync.
+inline bool mpa_check_header(uint32_t w) {
+    return ((w >> 19) & 3) != 1 && ((w >> 17) & 3) != 0 && ((w >> 12) & 15) != 15 && ((w >> 10) & 3) != 3;
+}
+
+inline Status mpa_parse_header(uint32_t w, MpaHeader& h) {
+    static constexpr uint16_t kbps[5][15] = {
+        {0, 32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384, 416, 448},  // MPEG-1 Layer I
+        {0, 32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384},     // MPEG-1 Layer II
+        {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320},      // MPEG-1 Layer III
+        {0, 32, 48, 56, 64, 80, 96, 112, 128, 144, 160, 176, 192, 224, 256},     // MPEG-2 / 2.5 Layer I
+        {0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160},          // MPEG-2 / 2.5 Layers II, III
+    };
+    static constexpr uint32_t rates[3] = {44100, 48000, 32000};
+    const uint32_t v = (w >> 19) & 3, l = (w >> 17) & 3, bi = (w >> 12) & 15, ri = (w >> 10) & 3, m = (w >> 6) & 3;
+    if (v == 1 || l == 0) return Status::DecodeError;
+    h.version = v == 3 ? MpaVersion::Mpeg1 : v == 2 ? MpaVersion::Mpeg2 : MpaVersion::Mpeg2p5;
+    h.layer = uint8_t(4 - l);
+    if (bi == 0) return Status::Unsupported;  // free format
+    if (bi == 15) return Status::DecodeError;
+    const int row = h.version == MpaVersion::Mpeg1 ? h.layer - 1 : (h.layer == 1 ? 3 : 4);
+    h.bitrate = uint32_t(kbps[row][bi]) * 1000u;
+    if (ri == 3) return Status::DecodeError;
+    const int shift = int(h.version);  // 0, 1, 2: full, half, quarter rate
+    h.sample_rate = rates[ri] >> shift;
+    h.sample_rate_idx = uint8_t(ri + 3 * shift);
+    h.mode = MpaMode(m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : 3);
+    h.mid_side = h.intensity = false;
+    h.bound = 32;
+    if (h.mode == MpaMode::JointStereo) {
+        if (h.layer == 3) {
+            h.mid_side = (w & 0x20) != 0;
+            h.intensity = (w & 0x10) != 0;
+        } else {
+            h.bound = uint8_t((1 + ((w >> 4) & 3)) << 2);
+        }
+    }
+    if (h.layer == 2) {  // header.rs:176-187: combinations Layer II forbids
+        const uint32_t k = h.bitrate / 1000;
+        if (h.mode == MpaMode::Mono ? (k == 224 || k == 256 || k == 320 || k == 384) : (k == 32 || k == 48 || k == 56 || k == 80))
+            return Status::DecodeError;
+    }
+    const uint32_t e = w & 3;
+    h.emphasis = uint8_t(e == 1 ? 1 : e == 3 ? 3 : 0);
+    h.copyrighted = (w & 8) != 0;
+    h.original = (w & 4) != 0;
+    h.padding = (w & 0x200) != 0;
+    h.crc = (w & 0x10000) == 0;
+    const uint32_t factor = h.layer == 1 ? 12u : (h.layer == 3 && h.version != MpaVersion::Mpeg1) ? 72u : 144u;
+    const uint32_t slots = factor * h.bitrate / h.sample_rate + (h.padding ? 1u : 0u);
+    h.frame_size = slots * (h.layer == 1 ? 4u : 1u) - 4u;
+    return Status::Ok;
+}
+
+// Longest frame the format can express, header included (header.rs:17).
+constexpr uint32_t kMpaMaxFrameSize = 2881;
+
+struct MpaLameInfo {
+    char encoder[9];
+    uint32_t delay, padding;  // samples the decoder output starts / ends with that are not audio
+    uint32_t peak;            // raw 9.23 fixed-point replay-gain peak, 0 = absent
+};
+
+// Xing / Info tag of a Layer III frame (demuxer.rs:761-925).
+struct MpaInfoTag {
+    bool has_num_frames, has_num_bytes, has_toc, has_quality, is_cbr, has_lame;
+    uint32_t num_frames, num_bytes, quality;
+    MpaLameInfo lame;
+};
+struct MpaVbriTag {
+    uint32_t num_bytes, num_mpeg_frames;
+};
+
+// demuxer.rs:942-968.  `f` = the whole frame, header word first.
+inline bool mpa_is_maybe_info_tag(const uint8_t* f, size_t n, const MpaHeader& h) {
+    if (h.layer != 3) return false;
+    const size_t at = 4 + h.side_info_len();
+    if (n < at + 8) return false;
+    if (std::memcmp(f + at, "Xing", 4) != 0 && std::memcmp(f + at, "Info", 4) != 0) return false;
+    for (size_t i = h.header_size(); i < at; ++i)
+        if (f[i]) return false;
+    return true;
+}
+
+// True when the frame is a tag the reference would act on; false for everything else, INCLUDING a tag whose
+// flagged fields do not fit the frame (the reference flattens that read error to "no tag").
+inline bool mpa_read_info_tag(const uint8_t* f, size_t n, const MpaHeader& h, MpaInfoTag& t) {
+    if (!mpa_is_maybe_info_tag(f, n, h)) return false;
+    const size_t base = 4 + h.side_info_len();
+    size_t at = base;
+    auto need = [&](size_t k) { return at + k <= n; };
+    t = MpaInfoTag{};
+    t.is_cbr = std::memcmp(f + at, "Info", 4) == 0;
+    const uint32_t flags = detail::be32(f + at + 4);
+    at += 8;
+    if (flags & 1) {
+        if (!need(4)) return false;
+        t.has_num_frames = true, t.num_frames = detail::be32(f + at), at += 4;
+    }
+    if (flags & 2) {
+        if (!need(4)) return false;
+        t.has_num_bytes = true, t.num_bytes = detail::be32(f + at), at += 4;
+    }
+    if (flags & 4) {
+        if (!need(100)) return false;
+        t.has_toc = true, at += 100;
+    }
+    if (flags & 8) {
+        if (!need(4)) return false;
+        t.has_quality = true, t.quality = detail::be32(f + at), at += 4;
+    }
+    // LAME extension: 24 bytes up to the delay / padding field, 12 more up to its CRC-16 (over everything before it).
+    if (n - at >= 24) {
+        const uint8_t* e = f + at;
+        MpaLameInfo li{};
+        std::memcpy(li.encoder, e, 9);
+        li.peak = detail::be32(e + 11);
+        const uint32_t trim = detail::be24(e + 21);
+        const bool known = !std::memcmp(e, "LAME", 4) || !std::memcmp(e, "Lavf", 4) || !std::memcmp(e, "Lavc", 4);
+        if (known) {
+            li.delay = 528 + 1 + (trim >> 12);
+            const uint32_t pad = trim & 0xfff;
+            li.padding = pad > 529 ? pad - 529 : 0;
+        }
+        at += 24;
+        bool ok = true;
+        if (n - at >= 12) {
+            at += 10;
+            if (h.crc || !std::memcmp(e, "LAME", 4)) {
+                const uint32_t written = detail::be16(f + at);
+                ok = written == 0 || written == crc16_ansi_le_update(0, f, at);
+            }
+        }
+        if (ok) t.has_lame = true, t.lame = li;
+    }
+    return true;
+}
+
+// demuxer.rs:1023-1047, 980-1019.
+inline bool mpa_is_maybe_vbri_tag(const uint8_t* f, size_t n, const MpaHeader& h) {
+    if (h.layer != 3 || n < 36 + 26 || std::memcmp(f + 36, "VBRI", 4) != 0) return false;
+    for (size_t i = h.header_size(); i < 36; ++i)
+        if (f[i]) return false;
+    return true;
+}
+inline bool mpa_read_vbri_tag(const uint8_t* f, size_t n, const MpaHeader& h, MpaVbriTag& t) {
+    if (!mpa_is_maybe_vbri_tag(f, n, h) || detail::be16(f + 40) != 1) return false;
+    t.num_bytes = detail::be32(f + 46);
+    t.num_mpeg_frames = detail::be32(f + 50);
+    return true;
+}
+
+// main_data_begin of a Layer III frame: how many bytes of THIS frame's main data live in earlier frames
+// (demuxer.rs:664-680).  The bit-reservoir front end needs it per frame; -1 when the frame is too short.
+inline int mpa_main_data_begin(const uint8_t* f, size_t n, const MpaHeader& h) {
+    const size_t at = h.header_size();
+    if (h.version == MpaVersion::Mpeg1) return at + 2 <= n ? int(detail::be16(f + at) >> 7) : -1;
+    return at + 1 <= n ? int(f[at]) : -1;
+}
+
+// One packet = one frame, a byte range of the source.
+struct MpaPacket {
+    uint64_t offset;      // of the header word
+    uint32_t size;        // header word included
+    uint32_t header;      // the header word
+    int64_t pts;          // in samples; starts at -delay
+    uint32_t dur;         // samples the frame decodes to
+    uint32_t trim_start;  // leading samples to drop (encoder delay)
+    uint64_t trim_end;    // trailing samples to drop; NOT capped to dur, as in the reference (packet.rs:334-338)
+};
+
+struct MpaTrack {
+    MpaHeader first;           // codec parameters come from the first frame
+    uint32_t first_word;
+    bool has_delay, has_num_frames;
+    uint32_t delay, padding;
+    uint64_t num_frames;       // samples of audio, delay and padding removed (exact, from a tag) or estimated
+    enum Tag : uint8_t { None, Xing, Info, Vbri } tag;
+    uint64_t first_packet_pos;
+};
+
+// The reference's MpaReader over a resident buffer: open() = try_new, next() = next_packet.
+class MpaIndexer {
+  public:
+    MpaIndexer(const uint8_t* data, size_t n) : d_(data), n_(n) {}
+
+    // demuxer.rs:414-487.  EndOfStream: the buffer holds no frame.  `seekable` = the reference's is_seekable():
+    // without it no duration is estimated for an untagged stream and nothing is trimmed from its end.
+    Status open(bool seekable = true) {
+        size_t at = 0, size = 0;
+        MpaHeader h;
+        uint32_t w;
+        // demuxer.rs:610-640: accept a first frame only when the next word looks like the same kind of stream;
+        // rejected candidates restart the hunt one byte further.
+        for (size_t from = 0;;) {
+            if (!find_frame(from, at, w, h)) return Status::EndOfStream;
+            size = 4 + size_t(h.frame_size);
+            if (at + size + 4 <= n_) {
+                const uint32_t nxt = detail::be32(d_ + at + size);
+                MpaHeader c;
+                const bool similar = mpa_is_synced(nxt) && mpa_parse_header(nxt, c) == Status::Ok && c.version == h.version &&
+                                     c.layer == h.layer && c.sample_rate == h.sample_rate && c.n_channels() == h.n_channels();
+                if (!similar) {
+                    from = at + 1;
+                    continue;
+                }
+            }
+            break;
+        }
+        track_ = MpaTrack{};
+        track_.first = h;
+        track_.first_word = w;
+        track_.tag = MpaTrack::None;
+        pos_ = at + size;
+        MpaInfoTag info;
+        MpaVbriTag vbri;
+        if (mpa_read_info_tag(d_ + at, size, h, info)) {
+            track_.tag = info.is_cbr ? MpaTrack::Info : MpaTrack::Xing;
+            if (info.has_lame) track_.has_delay = true, track_.delay = info.lame.delay, track_.padding = info.lame.padding;
+            if (info.has_num_frames) {
+                const uint64_t total = uint64_t(info.num_frames) * h.samples_per_frame();
+                const uint64_t cut = uint64_t(track_.delay) + track_.padding;
+                track_.has_num_frames = true, track_.num_frames = total > cut ? total - cut : 0;
+            }
+        } else if (mpa_read_vbri_tag(d_ + at, size, h, vbri)) {
+            track_.tag = MpaTrack::Vbri;
+            track_.has_num_frames = true, track_.num_frames = uint64_t(vbri.num_mpeg_frames) * h.samples_per_frame();
+        } else {
+            pos_ = at;  // an ordinary frame: it is the first packet
+            uint64_t frames;
+            if (seekable && estimate_frames(at, frames)) track_.has_num_frames = true, track_.num_frames = frames * h.samples_per_frame();
+        }
+        track_.first_packet_pos = pos_;
+        ts_ = -int64_t(track_.delay);
+        open_ = true;
+        return Status::Ok;
+    }
+
+    const MpaTrack& track() const { return track_; }
+
+    // demuxer.rs:160-218.  Frames that are Xing / Info / VBRI tags are dropped wherever they turn up.
+    Status next(MpaPacket& p) {
+        if (!open_) return Status::DecodeError;
+        for (;;) {
+            size_t at;
+            MpaHeader h;
+            uint32_t w;
+            if (!find_frame(pos_, at, w, h)) return Status::EndOfStream;
+            const size_t size = 4 + size_t(h.frame_size);
+            pos_ = at + size;
+            MpaInfoTag info;
+            MpaVbriTag vbri;
+            if (mpa_is_maybe_info_tag(d_ + at, size, h)) {
+                if (mpa_read_info_tag(d_ + at, size, h, info)) continue;
+            } else if (mpa_read_vbri_tag(d_ + at, size, h, vbri)) {
+                continue;
+            }
+            const uint32_t dur = h.samples_per_frame();
+            p.offset = at, p.size = uint32_t(size), p.header = w, p.pts = ts_, p.dur = dur;
+            p.trim_start = ts_ < 0 ? uint32_t(-ts_ < int64_t(dur) ? -ts_ : int64_t(dur)) : 0u;
+            p.trim_end = 0;
+            if (track_.has_num_frames) {
+                const int64_t over = ts_ + int64_t(dur) - int64_t(track_.num_frames);
+                if (over > 0) p.trim_end = uint64_t(over);
+            }
+            ts_ += dur;
+            return Status::Ok;
+        }
+    }
+
+    // Everything at once.
+    static Status index(const uint8_t* data, size_t n, MpaTrack& track, std::vector<MpaPacket>& out, bool seekable = true) {
+        MpaIndexer ix(data, n);
+        const Status s = ix.open(seekable);
+        if (s != Status::Ok) return s;
+        track = ix.track();
+        MpaPacket p;
+        while (ix.next(p) == Status::Ok) out.push_back(p);
+        return Status::Ok;
+    }
+
+  private:
+    // header.rs:77-103 + demuxer.rs:585-607 as a window search: the first offset >= from whose word has the sync
+    // bits and passes the plausibility test; a word that then fails the full parse (free format, a forbidden Layer II
+    // combination) costs its 4 bytes, and a frame whose body runs past the buffer ends the stream.
+    bool find_frame(size_t from, size_t& at, uint32_t& w, MpaHeader& h) const {
+        for (size_t q = from; q + 4 <= n_;) {
+            // cheap reject on the first byte keeps the scan at memchr speed through payload bytes
+            if (d_[q] != 0xff) {
+                const void* hit = std::memchr(d_ + q, 0xff, n_ - q);
+                if (!hit) return false;
+                q = size_t(static_cast<const uint8_t*>(hit) - d_);
+                if (q + 4 > n_) return false;
+            }
+            const uint32_t word = detail::be32(d_ + q);
+            if (!mpa_is_synced(word) || !mpa_check_header(word)) {
+                ++q;
+                continue;
+            }
+            if (mpa_parse_header(word, h) != Status::Ok) {
+                q += 4;
+                continue;
+            }
+            if (q + 4 + size_t(h.frame_size) > n_) return false;
+            at = q, w = word;
+            return true;
+        }
+        return false;
+    }
+
+    // demuxer.rs:683-733: average the first frames (more than 16 of them or more than 16 KiB) and extrapolate.
+    bool estimate_frames(size_t from, uint64_t& frames) const {
+        const double total_len = double(n_ - from);
+        size_t q = from, len = 0;
+        unsigned count = 0;
+        for (;;) {
+            MpaHeader h;
+            if (q + 4 > n_ || mpa_parse_header(detail::be32(d_ + q), h) != Status::Ok) return false;
+            len += 4 + h.frame_size, ++count;
+            if (q + 4 + h.frame_size > n_) return false;
+            q += 4 + h.frame_size;
+            if (count > 16 || len > 16 * 1024) break;
+        }
+        frames = uint64_t(total_len / (double(len) / double(count)));
+        return true;
+    }
+
+    const uint8_t* d_;
+    size_t n_;
+    size_t pos_ = 0;
+    int64_t ts_ = 0;
+    bool open_ = false;
+    MpaTrack track_{};
+};
+
+// =====================================================================================================================
+// ADTS (AAC)
+// =====================================================================================================================
+
+struct AdtsHeader {
+    uint8_t profile;       // MPEG-4 audio object type: 1 Main, 2 LC, 3 SSR, 4 LTP
+    uint8_t channels;      // 0: configured in-band (program config element)
+    uint8_t header_len;    // 7, or 9 with a CRC
+    bool has_crc;
+    uint16_t crc;
+    uint16_t frame_len;    // sync word, header and payload
+    uint32_t sample_rate;
+    uint32_t payload_len() const { return uint32_t(frame_len) - header_len; }
+};
+
+// adts.rs:202-204: 0xfff, layer bits zero; the MPEG-2/4 bit and the protection bit are free.
+inline bool adts_is_sync(uint32_t w16) { return (w16 & 0xfff6u) == 0xfff0u; }
+
+// adts.rs:137-198.  `p` points at the sync word; `n` bytes are readable.  EndOfStream: fewer than header_len bytes.
+inline Status adts_parse_header(const uint8_t* p, size_t n, AdtsHeader& h) {
+    static constexpr uint32_t rates[13] = {96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000, 7350};
+    static constexpr uint8_t chans[8] = {0, 1, 2, 3, 4, 5, 6, 8};
+    if (n < 2) return Status::EndOfStream;
+    h.has_crc = (p[1] & 1) == 0;
+    h.header_len = h.has_crc ? 9 : 7;
+    if (n < h.header_len) return Status::EndOfStream;
+    h.profile = uint8_t((p[2] >> 6) + 1);
+    const uint32_t ri = (p[2] >> 2) & 15;
+    if (ri > 12) return Status::DecodeError;  // 15 is the escape ADTS forbids, 13 / 14 are reserved
+    h.sample_rate = rates[ri];
+    h.channels = chans[((p[2] & 1) << 2) | (p[3] >> 6)];
+    h.frame_len = uint16_t(((p[3] & 3) << 11) | (p[4] << 3) | (p[5] >> 5));
+    if (h.frame_len < h.header_len) return Status::DecodeError;
+    if ((p[6] & 3) != 0) return Status::Unsupported;  // more than one raw data block per frame
+    h.crc = h.has_crc ? uint16_t(detail::be16(p + 7)) : 0;
+    return Status::Ok;
+}
+
+struct AdtsPacket {
+    uint64_t offset;  // of the PAYLOAD (the raw data block), as the reference's packets carry no ADTS header
+    uint32_t size;
+    int64_t pts;      // 1024 samples per packet
+    uint32_t sample_rate;
+    uint8_t channels, profile;
+};
+
+// adts.rs:278-309 over a resident buffer.
+class AdtsIndexer {
+  public:
+    AdtsIndexer(const uint8_t* data, size_t n) : d_(data), n_(n) {}
+
+    // EndOfStream at the end of the bytes (truncated() tells a clean end from a cut payload); DecodeError /
+    // Unsupported leave the cursor behind the offending header, as the reference's reader does, so that a caller
+    // that chooses to carry on resynchronises from there.
+    Status next(AdtsPacket& p) {
+        size_t q = pos_;
+        for (;; ++q) {
+            if (q + 2 > n_) return pos_ = n_, Status::EndOfStream;
+            if (d_[q] != 0xff) {
+                const void* hit = std::memchr(d_ + q, 0xff, n_ - q);
+                if (!hit) return pos_ = n_, Status::EndOfStream;
+                q = size_t(static_cast<const uint8_t*>(hit) - d_);
+                if (q + 2 > n_) return pos_ = n_, Status::EndOfStream;
+            }
+            if (adts_is_sync(detail::be16(d_ + q))) break;
+        }
+        AdtsHeader h;
+        const Status s = adts_parse_header(d_ + q, n_ - q, h);
+        if (s == Status::EndOfStream) return pos_ = n_, s;
+        pos_ = q + h.header_len;
+        if (s != Status::Ok) return s;
+        if (pos_ + h.payload_len() > n_) return truncated_ = true, pos_ = n_, Status::EndOfStream;
+        p.offset = pos_, p.size = h.payload_len(), p.pts = ts_, p.sample_rate = h.sample_rate, p.channels = h.channels, p.profile = h.profile;
+        pos_ += h.payload_len();
+        ts_ += 1024;
+        return Status::Ok;
+    }
+    bool truncated() const { return truncated_; }
+
+    // Up to the first non-Ok status, which is returned.
+    static Status index(const uint8_t* data, size_t n, std::vector<AdtsPacket>& out, bool* truncated = nullptr) {
+        AdtsIndexer ix(data, n);
+        AdtsPacket p;
+        Status s;
+        while ((s = ix.next(p)) == Status::Ok) out.push_back(p);
+        if (truncated) *truncated = ix.truncated();
+        return s;
+    }
+
+  private:
+    const uint8_t* d_;
+    size_t n_;
+    size_t pos_ = 0;
+    int64_t ts_ = 0;
+    bool truncated_ = false;
+};
+
+// =====================================================================================================================
+// Ogg
+// =====================================================================================================================
+
+constexpr size_t kOggHeaderSize = 27;
+constexpr size_t kOggMaxPageSize = kOggHeaderSize + 255 + 255 * 255;  // page.rs:17
+constexpr uint64_t kOggMaxPacketLen = 16u * 1024 * 1024;              // logical.rs:61
+
+struct OggPage {
+    uint64_t offset;       // of the capture pattern
+    uint64_t absgp;        // granule position
+    uint32_t serial, sequence, crc;
+    uint8_t n_segments;
+    bool continuation, first, last;
+    uint64_t body_offset;  // first body byte
+    uint32_t body_len;
+    uint16_t n_packets;    // packets that END on this page
+    uint16_t packet_len[255];
+    uint32_t partial_len() const {  // body bytes after the last packet end: a packet continued on a later page
+        uint32_t used = 0;
+        for (unsigned i = 0; i < n_packets; ++i) used += packet_len[i];
+        return body_len - used;
+    }
+};
+
+// page.rs:166-271 over a resident buffer.
+class OggPageReader {
+  public:
+    OggPageReader(const uint8_t* data, size_t n) : d_(data), n_(n) {}
+
+    // One attempt (try_next_page): DecodeError for a bad version / flag byte (the search resumes after that header)
+    // or a checksum mismatch (the search resumes right after the capture pattern that led here).
+    Status try_next(OggPage& pg) {
+        size_t q = pos_;
+        for (;; ++q) {
+            if (q + 4 > n_) return pos_ = n_, Status::EndOfStream;
+            if (d_[q] != 'O') {
+                const void* hit = std::memchr(d_ + q, 'O', n_ - q);
+                if (!hit) return pos_ = n_, Status::EndOfStream;
+                q = size_t(static_cast<const uint8_t*>(hit) - d_);
+                if (q + 4 > n_) return pos_ = n_, Status::EndOfStream;
+            }
+            if (std::memcmp(d_ + q, "OggS", 4) == 0) break;
+        }
+        if (q + kOggHeaderSize > n_) return pos_ = n_, Status::EndOfStream;
+        const uint8_t* h = d_ + q;
+        pos_ = q + kOggHeaderSize;
+        if (h[4] != 0 || (h[5] & 0xf8)) return Status::DecodeError;
+        pg.offset = q;
+        pg.continuation = h[5] & 1, pg.first = (h[5] & 2) != 0, pg.last = (h[5] & 4) != 0;
+        pg.absgp = detail::le64(h + 6);
+        pg.serial = detail::le32(h + 14), pg.sequence = detail::le32(h + 18), pg.crc = detail::le32(h + 22);
+        pg.n_segments = h[26];
+        if (pos_ + pg.n_segments > n_) return pos_ = n_, Status::EndOfStream;
+        const uint8_t* lacing = d_ + pos_;
+        uint32_t body = 0, run = 0;
+        pg.n_packets = 0;
+        for (unsigned i = 0; i < pg.n_segments; ++i) {
+            body += lacing[i], run += lacing[i];
+            if (lacing[i] < 255) pg.packet_len[pg.n_packets++] = uint16_t(run), run = 0;  // a short segment closes a packet
+        }
+        pos_ += pg.n_segments;
+        if (pos_ + body > n_) return pos_ = n_, Status::EndOfStream;
+        pg.body_offset = pos_, pg.body_len = body;
+        // checksum over the page with its own checksum field read as zero
+        static const uint8_t zero[4] = {0, 0, 0, 0};
+        uint32_t crc = crc32_update(0, h, 22);
+        crc = crc32_update(crc, zero, 4);
+        crc = crc32_update(crc, h + 26, 1 + size_t(pg.n_segments) + body);
+        if (crc != pg.crc) {
+            pos_ = q + 4;
+            return Status::DecodeError;
+        }
+        pos_ += body;
+        return Status::Ok;
+    }
+
+    // next_page: skip whatever does not verify.
+    Status next(OggPage& pg) {
+        for (;;) {
+            const Status s = try_next(pg);
+            if (s == Status::Ok || s == Status::EndOfStream) return s;
+            ++n_rejected_;
+        }
+    }
+    size_t position() const { return pos_; }
+    size_t rejected() const { return n_rejected_; }
+
+  private:
+    const uint8_t* d_;
+    size_t n_;
+    size_t pos_ = 0;
+    size_t n_rejected_ = 0;
+};
+
+// A packet of a logical stream: pieces [first_piece, first_piece + n_pieces) of the stream's piece list.
+struct OggPacket {
+    uint32_t first_piece;
+    uint32_t n_pieces;
+    uint64_t len;
+    uint32_t page_sequence;  // of the page it ended on
+    uint64_t page_absgp;     // granule position of that page: the end time of its LAST completed packet
+    bool last_on_page;
+};
+
+// logical.rs:104-205, 577-620 without the codec mapper: reassembles the packets of one serial number.
+class OggLogicalStream {
+  public:
+    // DecodeError when an open packet would pass the reference's 16 MiB cap; the page's completed packets are kept.
+    Status read_page(const OggPage& pg) {
+        if (have_prev_ && (pg.sequence < prev_seq_ || pg.sequence - prev_seq_ > 1)) drop_partial();  // lost or re-ordered pages
+        have_prev_ = true, prev_seq_ = pg.sequence;
+        if (!pg.continuation && part_len_ > 0) drop_partial();  // the continuation never came
+        unsigned i = 0;
+        uint64_t at = pg.body_offset;
+        if (pg.continuation && part_len_ == 0) {
+            // the head of this packet was never seen: drop its tail, or the whole page when nothing else ends here
+            if (pg.n_packets == 0) return Status::Ok;
+            at += pg.packet_len[i++];
+        }
+        const size_t before = packets_.size();
+        for (; i < pg.n_packets; ++i) {
+            const uint32_t n = pg.packet_len[i];
+            pieces_.push_back(Piece{at, n});
+            OggPacket p;
+            p.first_piece = part_first_, p.n_pieces = uint32_t(pieces_.size()) - part_first_, p.len = part_len_ + n;
+            p.page_sequence = pg.sequence, p.page_absgp = pg.absgp, p.last_on_page = false;
+            packets_.push_back(p);
+            part_first_ = uint32_t(pieces_.size()), part_len_ = 0;
+            at += n;
+        }
+        if (packets_.size() > before) packets_.back().last_on_page = true;
+        const uint64_t rest = pg.body_offset + pg.body_len - at;
+        if (rest > 0) {
+            if (part_len_ + rest > kOggMaxPacketLen) return Status::DecodeError;
+            pieces_.push_back(Piece{at, uint32_t(rest)});
+            part_len_ += rest;
+        }
+        return Status::Ok;
+    }
+
+    const std::vector<OggPacket>& packets() const { return packets_; }
+    const std::vector<Piece>& pieces() const { return pieces_; }
+    uint64_t open_len() const { return part_len_; }  // bytes of a packet still waiting for its continuation
+
+    // Copy a packet out of the source buffer (tests, host-side header parsing); the device path gathers instead.
+    void gather(const uint8_t* src, const OggPacket& p, uint8_t* dst) const {
+        for (uint32_t k = 0; k < p.n_pieces; ++k) {
+            const Piece& pc = pieces_[p.first_piece + k];
+            std::memcpy(dst, src + pc.offset, pc.len);
+            dst += pc.len;
+        }
+    }
+
+  private:
+    void drop_partial() {
+        pieces_.resize(part_first_);
+        part_len_ = 0;
+    }
+    std::vector<OggPacket> packets_;
+    std::vector<Piece> pieces_;
+    uint32_t part_first_ = 0;  // pieces_[part_first_..] belong to the packet still open
+    uint64_t part_len_ = 0;
+    bool have_prev_ = false;
+    uint32_t prev_seq_ = 0;
+};
+
+// A physical stream: every page that verifies, routed by serial number.  A logical stream exists from its
+// beginning-of-stream page on (demuxer.rs:320-345); pages of serials never announced are counted and skipped.
+struct OggIndex {
+    std::vector<OggPage> pages;
+    std::map<uint32_t, OggLogicalStream> streams;
+    size_t rejected = 0;  // capture patterns that did not lead to a valid page
+    size_t orphans = 0;   // valid pages of unannounced serials
+
+    static Status build(const uint8_t* data, size_t n, OggIndex& ix, bool keep_pages = true) {
+        OggPageReader rd(data, n);
+        OggPage pg;
+        Status worst = Status::Ok;
+        while (rd.next(pg) == Status::Ok) {
+            if (keep_pages) ix.pages.push_back(pg);
+            auto it = ix.streams.find(pg.serial);
+            if (it == ix.streams.end()) {
+                if (!pg.first) {
+                    ++ix.orphans;
+                    continue;
+                }
+                it = ix.streams.emplace(pg.serial, OggLogicalStream{}).first;
+            }
+            if (it->second.read_page(pg) != Status::Ok) worst = Status::DecodeError;
+        }
+        ix.rejected = rd.rejected();
+        return worst;
+    }
+};
+
+}  // namespace packet
+}  // namespace symgpu
