@@ -749,5 +749,302 @@ struct OggIndex {
     }
 };
 
+// =====================================================================================================================
+// Vorbis in Ogg: what the container layer has to know about the codec
+// =====================================================================================================================
+// The mapper (symphonia-format-ogg/src/mappings/vorbis.rs) sorts a logical stream's packets into identification /
+// comment / setup headers and audio, hands the decoder its `extra_data` (identification packet followed by the
+// setup packet, consumed at symphonia-codec-vorbis/src/lib.rs:75-89) and derives every audio packet's duration
+// from its first bits: the mode number selects a short or long block, and a packet yields a quarter of the
+// previous block plus a quarter of its own.  For that it must walk the WHOLE setup header -- codebooks, floors,
+// residues, mappings -- just to reach the mode list at its end.
+
+// Bits least-significant first, as Vorbis packs them (symphonia-core/src/io/bit.rs:941-1027).
+class BitReaderRtl {
+  public:
+    BitReaderRtl(const uint8_t* p, size_t n) : p_(p), n_bits_(uint64_t(n) * 8) {}
+    bool ok() const { return ok_; }
+    uint64_t bits_left() const { return n_bits_ - at_; }
+    // Past the end: returns 0 and latches !ok() (every caller checks once per structure, not per field).
+    uint32_t read(unsigned width) {
+        if (width > bits_left()) return ok_ = false, at_ = n_bits_, 0u;
+        uint64_t v = 0;
+        const uint64_t byte = at_ >> 3;
+        const unsigned shift = unsigned(at_ & 7), need = (shift + width + 7) >> 3;
+        for (unsigned k = 0; k < need; ++k) v |= uint64_t(p_[byte + k]) << (8 * k);
+        at_ += width;
+        return uint32_t((v >> shift) & ((uint64_t(1) << width) - 1));
+    }
+    bool read_bool() { return read(1) != 0; }
+    void ignore(uint64_t width) {
+        if (width > bits_left()) ok_ = false, at_ = n_bits_;
+        else at_ += width;
+    }
+
+  private:
+    const uint8_t* p_;
+    uint64_t n_bits_, at_ = 0;
+    bool ok_ = true;
+};
+
+inline uint32_t vorbis_ilog(uint32_t x) {
+    uint32_t n = 0;
+    for (; x; x >>= 1) ++n;
+    return n;
+}
+
+struct VorbisIdent {
+    uint8_t n_channels;
+    uint32_t sample_rate;
+    uint8_t bs0_exp, bs1_exp;  // block sizes as powers of two, 6..13, short <= long
+};
+
+// mappings/vorbis.rs:293-360.  The Ogg mapper only accepts an identification packet of exactly 30 bytes (:113-117).
+inline Status vorbis_read_ident(const uint8_t* p, size_t n, VorbisIdent& id) {
+    if (n < 30) return Status::EndOfStream;
+    if (p[0] != 1 || std::memcmp(p + 1, "vorbis", 6) != 0) return Status::DecodeError;
+    if (detail::le32(p + 7) != 0) return Status::Unsupported;
+    id.n_channels = p[11];
+    id.sample_rate = detail::le32(p + 12);
+    if (id.n_channels == 0 || id.sample_rate == 0) return Status::DecodeError;
+    id.bs0_exp = p[28] & 15, id.bs1_exp = p[28] >> 4;
+    if (id.bs0_exp < 6 || id.bs0_exp > 13 || id.bs1_exp < 6 || id.bs1_exp > 13 || id.bs0_exp > id.bs1_exp) return Status::DecodeError;
+    if (p[29] != 1) return Status::DecodeError;  // framing
+    return Status::Ok;
+}
+
+namespace detail {
+// The largest v with v^dims <= entries (the reference computes it in f32 and asserts exactly this, :717-730).
+inline uint32_t vorbis_lookup1_values(uint32_t entries, uint32_t dims) {
+    uint32_t v = 0;
+    for (;;) {
+        uint64_t pw = 1;
+        bool over = false;
+        for (uint32_t k = 0; k < dims && !over; ++k) pw *= uint64_t(v) + 1, over = pw > entries;
+        if (over || pw > entries) return v;
+        ++v;
+    }
+}
+
+// mappings/vorbis.rs:426-500.
+inline bool vorbis_skip_codebook(BitReaderRtl& bs) {
+    if (bs.read(24) != 0x564342 || !bs.ok()) return false;
+    const uint32_t dims = bs.read(16), entries = bs.read(24);
+    if (!bs.read_bool()) {        // lengths in entry order
+        if (bs.read_bool()) {     // sparse: a used flag in front of every length
+            for (uint32_t i = 0; i < entries && bs.ok(); ++i)
+                if (bs.read_bool()) bs.read(5);
+        } else {
+            bs.ignore(uint64_t(entries) * 5);
+        }
+    } else {                      // lengths as run lengths of ascending code length
+        bs.read(5);
+        for (uint32_t cur = 0;;) {
+            cur += bs.read(entries > cur ? vorbis_ilog(entries - cur) : 0);
+            if (!bs.ok() || cur > entries) return false;
+            if (cur == entries) break;
+        }
+    }
+    const uint32_t lookup = bs.read(4);
+    if (!bs.ok()) return false;
+    if (lookup == 0) return true;
+    if (lookup > 2) return false;
+    bs.ignore(64);
+    const uint32_t value_bits = bs.read(4) + 1;
+    bs.read_bool();
+    if (!bs.ok()) return false;
+    if (lookup == 1 && dims == 0) return false;  // the reference's float root is meaningless here (it asserts)
+    const uint64_t values = lookup == 1 ? vorbis_lookup1_values(entries, dims) : uint64_t(entries) * dims;
+    bs.ignore(values * value_bits);
+    return bs.ok();
+}
+
+// :528-590
+inline bool vorbis_skip_floor(BitReaderRtl& bs) {
+    const uint32_t type = bs.read(16);
+    if (!bs.ok() || type > 1) return false;
+    if (type == 0) {
+        bs.ignore(8 + 16 + 16 + 6 + 8);
+        bs.ignore((uint64_t(bs.read(4)) + 1) * 8);
+        return bs.ok();
+    }
+    const uint32_t partitions = bs.read(5);
+    uint8_t cls[32] = {0}, dims[16] = {0};
+    if (partitions > 0) {
+        uint32_t max_class = 0;
+        for (uint32_t i = 0; i < partitions; ++i) {
+            cls[i] = uint8_t(bs.read(4));
+            if (cls[i] > max_class) max_class = cls[i];
+        }
+        for (uint32_t c = 0; c <= max_class; ++c) {
+            dims[c] = uint8_t(bs.read(3) + 1);
+            const uint32_t sub = bs.read(2);
+            if (sub) bs.read(8);
+            bs.ignore((uint64_t(1) << sub) * 8);
+        }
+    }
+    bs.read(2);
+    const uint32_t rangebits = bs.read(4);
+    for (uint32_t i = 0; i < partitions; ++i) bs.ignore(uint64_t(dims[cls[i]]) * rangebits);
+    return bs.ok();
+}
+
+// :592-620
+inline bool vorbis_skip_residue(BitReaderRtl& bs) {
+    bs.read(16);
+    bs.ignore(24 + 24 + 24);
+    const uint32_t classes = bs.read(6) + 1;
+    bs.ignore(8);
+    uint32_t books = 0;
+    for (uint32_t i = 0; i < classes && bs.ok(); ++i) {
+        uint32_t used = bs.read(3);
+        if (bs.read_bool()) used |= bs.read(5) << 3;
+        for (; used; used &= used - 1) ++books;
+    }
+    bs.ignore(uint64_t(books) * 8);
+    return bs.ok();
+}
+
+// :622-673
+inline bool vorbis_skip_mapping(BitReaderRtl& bs, uint8_t channels) {
+    if (bs.read(16) != 0 || !bs.ok()) return false;
+    const uint32_t submaps = bs.read_bool() ? bs.read(4) + 1 : 1;
+    if (bs.read_bool()) {
+        const uint32_t steps = bs.read(8) + 1, width = vorbis_ilog(uint32_t(channels) - 1);
+        bs.ignore(uint64_t(steps) * 2 * width);
+    }
+    if (bs.read(2) != 0 || !bs.ok()) return false;
+    if (submaps > 1) bs.ignore(uint64_t(channels) * 4);
+    bs.ignore(uint64_t(submaps) * 24);
+    return bs.ok();
+}
+}  // namespace detail
+
+// mappings/vorbis.rs:362-405, 675-708: the mode list of a setup packet, as a bit mask of "long block" flags.
+inline Status vorbis_read_setup_modes(const uint8_t* p, size_t n, const VorbisIdent& id, uint8_t& num_modes, uint64_t& long_block_mask) {
+    if (n < 7) return Status::EndOfStream;
+    if (p[0] != 5 || std::memcmp(p + 1, "vorbis", 6) != 0) return Status::DecodeError;
+    BitReaderRtl bs(p + 7, n - 7);
+    for (uint32_t i = 0, count = bs.read(8) + 1; i < count; ++i)
+        if (!detail::vorbis_skip_codebook(bs)) return Status::DecodeError;
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i)
+        if (bs.read(16) != 0 || !bs.ok()) return Status::DecodeError;  // time-domain transforms: placeholders
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i)
+        if (!detail::vorbis_skip_floor(bs)) return Status::DecodeError;
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i)
+        if (!detail::vorbis_skip_residue(bs)) return Status::DecodeError;
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i)
+        if (!detail::vorbis_skip_mapping(bs, id.n_channels)) return Status::DecodeError;
+    const uint32_t count = bs.read(6) + 1;
+    uint64_t mask = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        if (bs.read_bool()) mask |= uint64_t(1) << i;
+        const uint32_t window = bs.read(16), transform = bs.read(16);
+        bs.read(8);
+        if (!bs.ok() || window != 0 || transform != 0) return Status::DecodeError;
+    }
+    if (!bs.read_bool() || !bs.ok()) return Status::DecodeError;  // framing
+    num_modes = uint8_t(count), long_block_mask = mask;
+    return Status::Ok;
+}
+
+// mappings/vorbis.rs:45-107: (duration, leading samples to discard) of each audio packet in turn.
+class VorbisPacketTimer {
+  public:
+    VorbisPacketTimer() = default;
+    VorbisPacketTimer(const VorbisIdent& id, uint8_t num_modes, uint64_t long_block_mask)
+        : mask_(long_block_mask), num_modes_(num_modes), bs0_(id.bs0_exp), bs1_(id.bs1_exp) {}
+    void reset() { prev_exp_ = 0; }
+    // A packet that is not audio, names no valid mode or is cut short takes no time and leaves the state alone.
+    void next(const uint8_t* p, size_t n, uint64_t& dur, uint64_t& discard) {
+        dur = discard = 0;
+        BitReaderRtl bs(p, n);
+        if (bs.read_bool() || !bs.ok()) return;
+        const uint32_t mode = bs.read(vorbis_ilog(uint32_t(num_modes_) - 1)) & 0xff;
+        if (!bs.ok() || mode >= num_modes_) return;
+        const unsigned exp = (mask_ >> mode) & 1 ? bs1_ : bs0_;
+        const uint64_t cur = uint64_t(1) << exp;
+        if (prev_exp_) dur = ((uint64_t(1) << prev_exp_) >> 2) + (cur >> 2);
+        else dur = discard = cur >> 1;  // nothing to overlap with: the lapped half is thrown away
+        prev_exp_ = uint8_t(exp);
+    }
+
+  private:
+    uint64_t mask_ = 0;
+    uint8_t num_modes_ = 1, bs0_ = 6, bs1_ = 6, prev_exp_ = 0;
+};
+
+// symphonia-common/src/xiph/audio/vorbis/mod.rs:66-118: Matroska / WebM carry the three Vorbis headers in one
+// Xiph-laced blob (count byte 2, two lacing-coded lengths, then identification, comment and setup back to back).
+inline Status vorbis_unpack_xiph_laced(const uint8_t* p, size_t n, Piece& ident, Piece& setup) {
+    if (n == 0 || p[0] != 2) return Status::DecodeError;
+    size_t at = 1;
+    uint64_t len[2] = {0, 0};
+    for (int k = 0; k < 2; ++k) {
+        for (;;) {
+            if (at >= n) return Status::DecodeError;
+            const uint8_t v = p[at++];
+            len[k] += v;
+            if (v < 255) break;
+        }
+    }
+    const uint64_t rest = n - at;
+    if (rest == 0 || len[0] + len[1] > rest) return Status::DecodeError;
+    ident = Piece{at, uint32_t(len[0])};
+    setup = Piece{at + len[0] + len[1], uint32_t(rest - len[0] - len[1])};
+    return Status::Ok;
+}
+
+// mappings/vorbis.rs:109-285: the per-stream state machine.  detect() on the first packet of the first page,
+// map() on every later packet.
+class OggVorbisMapper {
+  public:
+    enum class Kind : uint8_t { Audio, Comment, Setup, Unknown, Error };
+    struct Mapped {
+        Kind kind;
+        uint64_t dur, discard;  // Audio only
+    };
+
+    // False: not a Vorbis stream (the packet is not a well-formed 30-byte identification header).
+    bool detect(const uint8_t* p, size_t n) {
+        if (n != 30 || vorbis_read_ident(p, n, ident_) != Status::Ok) return false;
+        extra_.assign(p, p + n);
+        return true;
+    }
+
+    Mapped map(const uint8_t* p, size_t n) {
+        Mapped m{Kind::Error, 0, 0};
+        if (n == 0) return m;
+        if ((p[0] & 1) == 0) {  // even packet types are audio; before the setup header they take no time
+            m.kind = Kind::Audio;
+            if (have_timer_) timer_.next(p, n, m.dur, m.discard);
+            return m;
+        }
+        if (n < 7 || std::memcmp(p + 1, "vorbis", 6) != 0) return m;
+        if (p[0] == 3) return m.kind = Kind::Comment, m;
+        if (p[0] != 5) return m.kind = Kind::Unknown, m;
+        extra_.insert(extra_.end(), p, p + n);  // appended whether or not it parses, as in the reference
+        uint8_t modes;
+        uint64_t mask;
+        if (vorbis_read_setup_modes(p, n, ident_, modes, mask) == Status::Ok) timer_ = VorbisPacketTimer(ident_, modes, mask), have_timer_ = true;
+        ready_ = true;
+        return m.kind = Kind::Setup, m;
+    }
+
+    void reset() { timer_.reset(); }
+    bool ready() const { return ready_; }  // a setup header was seen
+    const VorbisIdent& ident() const { return ident_; }
+    // Identification packet + setup packet(s): what the decoder is constructed from.
+    const std::vector<uint8_t>& extra_data() const { return extra_; }
+    // Largest gap between points a decoder can start from: half the long block (:156-164).
+    uint64_t max_rap_period() const { return have_timer_ ? (uint64_t(1) << ident_.bs1_exp) >> 1 : 0; }
+
+  private:
+    VorbisIdent ident_{};
+    VorbisPacketTimer timer_;
+    std::vector<uint8_t> extra_;
+    bool have_timer_ = false, ready_ = false;
+};
+
 }  // namespace packet
 }  // namespace symgpu

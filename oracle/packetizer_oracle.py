@@ -527,3 +527,273 @@ def ogg_index(data):
         if s is not None:
             s.read_page(header, lens, body_at, body_len)
     return pages, {k: v.packets for k, v in streams.items()}
+
+
+# ------------------------------------------------------------------------------------------------ Vorbis in Ogg
+# symphonia-format-ogg/src/mappings/vorbis.rs (identification header :293-360, setup walk :362-708, packet timing
+# :45-107, mapper :109-285) and symphonia-common/src/xiph/audio/vorbis/mod.rs:66-118 (Xiph-laced extra data).
+
+class BitsRtl:
+    """BitReaderRtl (symphonia-core/src/io/bit.rs:941-1027): least-significant bit first; reading or skipping past
+    the end is an error."""
+
+    def __init__(self, data):
+        self.v = int.from_bytes(bytes(data), "little")
+        self.n = len(data) * 8
+        self.at = 0
+
+    def read(self, width):
+        if self.at + width > self.n:
+            raise ReaderError(EOF, "bits")
+        out = (self.v >> self.at) & ((1 << width) - 1)
+        self.at += width
+        return out
+
+    def read_bool(self):
+        return self.read(1) == 1
+
+    def ignore(self, width):
+        if self.at + width > self.n:
+            raise ReaderError(EOF, "bits")
+        self.at += width
+
+
+def ilog(x):
+    return x.bit_length()
+
+
+def vorbis_read_ident(buf):
+    r = Reader(buf)
+    if r.read_u8() != 1:
+        raise ReaderError(DECODE, "packet type")
+    if r.read_exact(6) != b"vorbis":
+        raise ReaderError(DECODE, "signature")
+    if r.read_le(4) != 0:
+        raise ReaderError(UNSUPPORTED, "version")
+    ch = r.read_u8()
+    if ch == 0:
+        raise ReaderError(DECODE, "channels")
+    rate = r.read_le(4)
+    if rate == 0:
+        raise ReaderError(DECODE, "rate")
+    r.read_le(4), r.read_le(4), r.read_le(4)
+    bs = r.read_u8()
+    bs0, bs1 = bs & 15, bs >> 4
+    if not 6 <= bs0 <= 13 or not 6 <= bs1 <= 13 or bs0 > bs1:
+        raise ReaderError(DECODE, "block sizes")
+    if r.read_u8() != 1:
+        raise ReaderError(DECODE, "framing")
+    return dict(n_channels=ch, sample_rate=rate, bs0_exp=bs0, bs1_exp=bs1)
+
+
+def _lookup1_values(entries, dims):
+    """:717-730 -- the reference takes the float root and asserts v^dims <= entries < (v+1)^dims; that IS the definition."""
+    v = 0
+    while (v + 1) ** dims <= entries:
+        v += 1
+    return v
+
+
+def _skip_codebook(bs):
+    if bs.read(24) != 0x564342:
+        raise ReaderError(DECODE, "codebook sync")
+    dims, entries = bs.read(16), bs.read(24)
+    if not bs.read_bool():
+        if bs.read_bool():
+            for _ in range(entries):
+                if bs.read_bool():
+                    bs.read(5)
+        else:
+            bs.ignore(entries * 5)
+    else:
+        cur = 0
+        bs.read(5)
+        while True:
+            cur += bs.read(ilog(entries - cur) if entries > cur else 0)
+            if cur > entries:
+                raise ReaderError(DECODE, "codebook")
+            if cur == entries:
+                break
+    lookup = bs.read(4)
+    if lookup == 0:
+        return
+    if lookup > 2:
+        raise ReaderError(DECODE, "lookup type")
+    bs.read(32), bs.read(32)
+    value_bits = bs.read(4) + 1
+    bs.read_bool()
+    if lookup == 1 and dims == 0:
+        raise ReaderError(DECODE, "lookup 1 with no dimensions")  # the reference's assertion territory
+    bs.ignore((_lookup1_values(entries, dims) if lookup == 1 else entries * dims) * value_bits)
+
+
+def _skip_floor(bs):
+    kind = bs.read(16)
+    if kind == 0:
+        bs.ignore(8 + 16 + 16 + 6 + 8)
+        bs.ignore((bs.read(4) + 1) * 8)
+    elif kind == 1:
+        parts = bs.read(5)
+        classes = [bs.read(4) for _ in range(parts)]
+        dims = {}
+        if parts:
+            for c in range(max(classes) + 1):
+                dims[c] = bs.read(3) + 1
+                sub = bs.read(2)
+                if sub:
+                    bs.read(8)
+                bs.ignore((1 << sub) * 8)
+        bs.read(2)
+        rangebits = bs.read(4)
+        for c in classes:
+            bs.ignore(dims[c] * rangebits)
+    else:
+        raise ReaderError(DECODE, "floor type")
+
+
+def _skip_residue(bs):
+    bs.read(16)
+    bs.ignore(72)
+    classes = bs.read(6) + 1
+    bs.ignore(8)
+    books = 0
+    for _ in range(classes):
+        low = bs.read(3)
+        high = bs.read(5) if bs.read_bool() else 0
+        books += bin((high << 3) | low).count("1")
+    bs.ignore(books * 8)
+
+
+def _skip_mapping(bs, channels):
+    if bs.read(16) != 0:
+        raise ReaderError(DECODE, "mapping type")
+    submaps = bs.read(4) + 1 if bs.read_bool() else 1
+    if bs.read_bool():
+        steps = bs.read(8) + 1
+        width = ilog(channels - 1)
+        for _ in range(steps):
+            bs.read(width), bs.read(width)
+    if bs.read(2) != 0:
+        raise ReaderError(DECODE, "reserved")
+    if submaps > 1:
+        bs.ignore(channels * 4)
+    bs.ignore(submaps * 24)
+
+
+def vorbis_read_setup_modes(buf, ident):
+    """:362-405.  Returns the list of block flags."""
+    r = Reader(buf)
+    if r.read_u8() != 5:
+        raise ReaderError(DECODE, "packet type")
+    if r.read_exact(6) != b"vorbis":
+        raise ReaderError(DECODE, "signature")
+    bs = BitsRtl(buf[7:])
+    for _ in range(bs.read(8) + 1):
+        _skip_codebook(bs)
+    for _ in range(bs.read(6) + 1):
+        if bs.read(16) != 0:
+            raise ReaderError(DECODE, "time domain transform")
+    for _ in range(bs.read(6) + 1):
+        _skip_floor(bs)
+    for _ in range(bs.read(6) + 1):
+        _skip_residue(bs)
+    for _ in range(bs.read(6) + 1):
+        _skip_mapping(bs, ident["n_channels"])
+    modes = []
+    for _ in range(bs.read(6) + 1):
+        flag = bs.read_bool()
+        window, transform = bs.read(16), bs.read(16)
+        bs.read(8)
+        if window != 0 or transform != 0:
+            raise ReaderError(DECODE, "mode")
+        modes.append(flag)
+    if not bs.read_bool():
+        raise ReaderError(DECODE, "framing")
+    return modes
+
+
+class VorbisTimer:
+    """:45-107."""
+
+    def __init__(self, ident, modes):
+        self.ident, self.modes, self.prev = ident, modes, None
+
+    def next(self, packet):
+        bs = BitsRtl(packet)
+        try:
+            if bs.read_bool():
+                return 0, 0
+            mode = bs.read(ilog(len(self.modes) - 1))
+        except ReaderError:
+            return 0, 0
+        if mode >= len(self.modes):
+            return 0, 0
+        cur = 1 << (self.ident["bs1_exp"] if self.modes[mode] else self.ident["bs0_exp"])
+        if self.prev is not None:
+            out = ((self.prev >> 2) + (cur >> 2), 0)
+        else:
+            out = (cur >> 1, cur >> 1)
+        self.prev = cur
+        return out
+
+
+class VorbisMapper:
+    """:109-285 (comment contents are metadata and not looked at)."""
+
+    def __init__(self):
+        self.ident = self.timer = None
+        self.extra = b""
+        self.ready = False
+
+    def detect(self, packet):
+        if len(packet) != 30:
+            return False
+        try:
+            self.ident = vorbis_read_ident(packet)
+        except ReaderError:
+            return False
+        self.extra = bytes(packet)
+        return True
+
+    def map(self, packet):
+        if len(packet) == 0:
+            return ("error", 0, 0)
+        if packet[0] & 1 == 0:
+            dur, discard = self.timer.next(packet) if self.timer else (0, 0)
+            return ("audio", dur, discard)
+        if len(packet) < 7 or packet[1:7] != b"vorbis":
+            return ("error", 0, 0)
+        if packet[0] == 3:
+            return ("comment", 0, 0)
+        if packet[0] != 5:
+            return ("unknown", 0, 0)
+        self.extra += bytes(packet)
+        try:
+            self.timer = VorbisTimer(self.ident, vorbis_read_setup_modes(packet, self.ident))
+        except ReaderError:
+            pass
+        self.ready = True
+        return ("setup", 0, 0)
+
+
+def vorbis_unpack_xiph_laced(extradata):
+    """xiph/audio/vorbis/mod.rs:66-118.  Returns (identification packet, setup packet)."""
+    if len(extradata) == 0 or extradata[0] != 2:
+        raise ReaderError(DECODE, "lacing count")
+    at = 1
+    lengths = []
+    for _ in range(2):
+        total = 0
+        while True:
+            if at >= len(extradata):
+                raise ReaderError(DECODE, "truncated lacing")
+            v = extradata[at]
+            at += 1
+            total += v
+            if v < 255:
+                break
+        lengths.append(total)
+    rest = extradata[at:]
+    if len(rest) == 0 or lengths[0] + lengths[1] > len(rest):
+        raise ReaderError(DECODE, "lengths")
+    return rest[:lengths[0]], rest[lengths[0] + lengths[1]:]

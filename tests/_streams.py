@@ -199,3 +199,205 @@ def ogg_paginate(serial, packets, rng, max_segments=255, first_sequence=0, granu
         open_packet = not chunk[-1][2]
         seq += 1
     return pages
+
+
+# ---------------------------------------------------------------------------------------------------- Vorbis headers
+
+class BitWriterRtl:
+    """Vorbis bit packing (Vorbis I specification section 2): values go in least-significant bit first."""
+
+    def __init__(self):
+        self.v = 0
+        self.n = 0
+
+    def put(self, value, width):
+        assert 0 <= value < (1 << width) or width == 0
+        self.v |= value << self.n
+        self.n += width
+
+    def bytes(self):
+        return self.v.to_bytes((self.n + 7) // 8, "little")
+
+
+def vorbis_ident(channels=2, rate=44100, bs0=8, bs1=11, version=0, framing=1, sig=b"vorbis", ptype=1):
+    """Vorbis I 4.2.2."""
+    return bytes([ptype]) + sig + version.to_bytes(4, "little") + bytes([channels]) + rate.to_bytes(4, "little") + \
+        (0).to_bytes(4, "little") + (128000).to_bytes(4, "little") + (0).to_bytes(4, "little") + bytes([(bs1 << 4) | bs0, framing])
+
+
+def _ilog(x):
+    return x.bit_length()
+
+
+def _put_codebook(w, rng, style=None, lookup=None, sync=0x564342):
+    """Vorbis I 3.2.1.  `style`: plain | sparse | ordered."""
+    style = style or ["plain", "sparse", "ordered"][int(rng.integers(3))]
+    dims = int(rng.integers(1, 9))
+    entries = int(rng.integers(1, 400))
+    w.put(sync, 24), w.put(dims, 16), w.put(entries, 24)
+    if style == "ordered":
+        w.put(1, 1)
+        w.put(int(rng.integers(32)), 5)
+        cur = 0
+        while cur < entries:
+            num = int(rng.integers(0, entries - cur + 1))
+            w.put(num, _ilog(entries - cur))
+            cur += num
+    else:
+        w.put(0, 1)
+        w.put(int(style == "sparse"), 1)
+        for _ in range(entries):
+            if style == "sparse":
+                used = int(rng.integers(2))
+                w.put(used, 1)
+                if used:
+                    w.put(int(rng.integers(32)), 5)
+            else:
+                w.put(int(rng.integers(32)), 5)
+    lookup = int(rng.integers(3)) if lookup is None else lookup
+    w.put(lookup, 4)
+    if lookup in (1, 2):
+        w.put(int(rng.integers(1 << 32)), 32), w.put(int(rng.integers(1 << 32)), 32)
+        value_bits = int(rng.integers(1, 17))
+        w.put(value_bits - 1, 4), w.put(int(rng.integers(2)), 1)
+        if lookup == 1:
+            n = 0
+            while (n + 1) ** dims <= entries:
+                n += 1
+        else:
+            n = entries * dims
+        for _ in range(n):
+            w.put(int(rng.integers(1 << value_bits)), value_bits)
+
+
+def _put_floor(w, rng, kind=None):
+    """Vorbis I 6.2.1 / 7.2.2."""
+    kind = int(rng.integers(2)) if kind is None else kind
+    w.put(kind, 16)
+    if kind == 0:
+        w.put(int(rng.integers(256)), 8), w.put(int(rng.integers(65536)), 16), w.put(int(rng.integers(65536)), 16)
+        w.put(int(rng.integers(64)), 6), w.put(int(rng.integers(256)), 8)
+        books = int(rng.integers(1, 17))
+        w.put(books - 1, 4)
+        for _ in range(books):
+            w.put(int(rng.integers(256)), 8)
+        return
+    if kind != 1:
+        return
+    parts = int(rng.integers(0, 32))
+    classes = [int(rng.integers(0, 16)) for _ in range(parts)]
+    w.put(parts, 5)
+    for c in classes:
+        w.put(c, 4)
+    dims = {}
+    if parts:
+        for c in range(max(classes) + 1):
+            dims[c] = int(rng.integers(1, 9))
+            sub = int(rng.integers(4))
+            w.put(dims[c] - 1, 3), w.put(sub, 2)
+            if sub:
+                w.put(int(rng.integers(256)), 8)
+            for _ in range(1 << sub):
+                w.put(int(rng.integers(256)), 8)
+    w.put(int(rng.integers(4)), 2)
+    rangebits = int(rng.integers(16))
+    w.put(rangebits, 4)
+    for c in classes:
+        for _ in range(dims[c]):
+            w.put(int(rng.integers(1 << rangebits)) if rangebits else 0, rangebits)
+
+
+def _put_residue(w, rng):
+    """Vorbis I 8.6.1."""
+    w.put(int(rng.integers(3)), 16)
+    w.put(int(rng.integers(1 << 24)), 24), w.put(int(rng.integers(1 << 24)), 24), w.put(int(rng.integers(1 << 24)), 24)
+    classes = int(rng.integers(1, 65))
+    w.put(classes - 1, 6), w.put(int(rng.integers(256)), 8)
+    books = 0
+    for _ in range(classes):
+        low = int(rng.integers(8))
+        w.put(low, 3)
+        high = 0
+        if rng.integers(2):
+            high = int(rng.integers(32))
+            w.put(1, 1), w.put(high, 5)
+        else:
+            w.put(0, 1)
+        books += bin((high << 3) | low).count("1")
+    for _ in range(books):
+        w.put(int(rng.integers(256)), 8)
+
+
+def _put_mapping(w, rng, channels, kind=0, reserved=0):
+    """Vorbis I 4.2.4 (mappings)."""
+    w.put(kind, 16)
+    submaps = 1
+    if rng.integers(2):
+        submaps = int(rng.integers(1, 17))
+        w.put(1, 1), w.put(submaps - 1, 4)
+    else:
+        w.put(0, 1)
+    if rng.integers(2):
+        steps = int(rng.integers(1, 257))
+        w.put(1, 1), w.put(steps - 1, 8)
+        width = _ilog(channels - 1)
+        for _ in range(steps):
+            w.put(int(rng.integers(1 << width)) if width else 0, width), w.put(int(rng.integers(1 << width)) if width else 0, width)
+    else:
+        w.put(0, 1)
+    w.put(reserved, 2)
+    if submaps > 1:
+        for _ in range(channels):
+            w.put(int(rng.integers(16)), 4)
+    for _ in range(submaps):
+        w.put(0, 8), w.put(int(rng.integers(256)), 8), w.put(int(rng.integers(256)), 8)
+
+
+def vorbis_setup(rng, channels=2, modes=None, fault=None, n_codebooks=None):
+    """A random but well-formed setup header (Vorbis I 4.2.4) ending in the given mode block flags, or, with `fault`,
+    one broken in a named place.  Returns (packet, block flags)."""
+    modes = [bool(rng.integers(2)) for _ in range(int(rng.integers(1, 9)))] if modes is None else modes
+    w = BitWriterRtl()
+    n_codebooks = int(rng.integers(1, 12)) if n_codebooks is None else n_codebooks
+    w.put(n_codebooks - 1, 8)
+    for k in range(n_codebooks):
+        _put_codebook(w, rng, sync=0x564343 if fault == "codebook_sync" and k == n_codebooks - 1 else 0x564342,
+                      lookup=3 if fault == "lookup_type" and k == 0 else None)
+    n = int(rng.integers(1, 4))
+    w.put(n - 1, 6)
+    for k in range(n):
+        w.put(1 if fault == "time_domain" and k == n - 1 else 0, 16)
+    n = int(rng.integers(1, 5))
+    w.put(n - 1, 6)
+    for k in range(n):
+        _put_floor(w, rng, kind=2 if fault == "floor_type" and k == 0 else None)
+    n = int(rng.integers(1, 5))
+    w.put(n - 1, 6)
+    for _ in range(n):
+        _put_residue(w, rng)
+    n = int(rng.integers(1, 4))
+    w.put(n - 1, 6)
+    for k in range(n):
+        _put_mapping(w, rng, channels, kind=1 if fault == "mapping_type" and k == 0 else 0, reserved=2 if fault == "mapping_reserved" and k == n - 1 else 0)
+    w.put(len(modes) - 1, 6)
+    for k, flag in enumerate(modes):
+        w.put(int(flag), 1)
+        w.put(1 if fault == "window" and k == 0 else 0, 16)
+        w.put(1 if fault == "transform" and k == len(modes) - 1 else 0, 16)
+        w.put(int(rng.integers(256)), 8)
+    w.put(0 if fault == "framing" else 1, 1)
+    body = w.bytes()
+    if fault == "truncated":
+        body = body[:len(body) * 2 // 3]
+    return (b"\x05vorbis" if fault != "signature" else b"\x05vorbiz") + body, modes
+
+
+def vorbis_audio_packet(rng, n_modes, mode=None, n=None):
+    """An audio packet: type bit 0, the mode number, then opaque bits."""
+    w = BitWriterRtl()
+    w.put(0, 1)
+    mode = int(rng.integers(n_modes)) if mode is None else mode
+    w.put(mode, _ilog(n_modes - 1))
+    w.put(int(rng.integers(1 << 30)), 30)
+    body = w.bytes()
+    return body + rng.integers(0, 256, int(rng.integers(0, 400)) if n is None else n, dtype=np.uint8).tobytes(), mode

@@ -1,5 +1,6 @@
 // Test driver for include/symgpu/packetizer.hpp: prints what the index builders find in a file, one record per
 // line, for tests/test_packetizer.py to compare with oracle/packetizer_oracle.py.
+#include <chrono>
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -123,6 +124,79 @@ int main(int argc, char** argv) {
             }
         }
         std::printf("end %s rejected=%zu orphans=%zu\n", name(s), ix.rejected, ix.orphans);
+        return 0;
+    }
+    if (mode == "vsetup") {  // extra_data layout: the 30-byte identification packet, then the setup packet
+        VorbisIdent id;
+        const Status si = vorbis_read_ident(d.data(), d.size(), id);
+        if (si != Status::Ok) return std::printf("ident %s\n", name(si)), 0;
+        std::printf("ident ok ch=%d rate=%u bs=%d,%d\n", id.n_channels, id.sample_rate, id.bs0_exp, id.bs1_exp);
+        uint8_t modes = 0;
+        uint64_t mask = 0;
+        const Status ss = vorbis_read_setup_modes(d.data() + 30, d.size() - 30, id, modes, mask);
+        if (ss != Status::Ok) return std::printf("setup %s\n", name(ss)), 0;
+        std::printf("setup ok modes=%d mask=%" PRIx64 "\n", modes, mask);
+        return 0;
+    }
+    if (mode == "xiph") {
+        Piece a, b;
+        const Status s = vorbis_unpack_xiph_laced(d.data(), d.size(), a, b);
+        if (s != Status::Ok) return std::printf("%s\n", name(s)), 0;
+        std::printf("ok %" PRIu64 ":%u %" PRIu64 ":%u\n", a.offset, a.len, b.offset, b.len);
+        return 0;
+    }
+    if (mode == "oggvorbis") {  // pages -> packets -> mapper, per logical stream
+        OggIndex ix;
+        OggIndex::build(d.data(), d.size(), ix, false);
+        for (const auto& kv : ix.streams) {
+            const OggLogicalStream& ls = kv.second;
+            OggVorbisMapper mp;
+            bool detected = false;
+            std::vector<uint8_t> bytes;
+            static const char* kinds[] = {"audio", "comment", "setup", "unknown", "error"};
+            for (size_t i = 0; i < ls.packets().size(); ++i) {
+                const OggPacket& p = ls.packets()[i];
+                bytes.resize(p.len);
+                ls.gather(d.data(), p, bytes.data());
+                if (i == 0) {
+                    detected = mp.detect(bytes.data(), bytes.size());
+                    std::printf("stream %u vorbis=%d\n", kv.first, int(detected));
+                    if (!detected) break;
+                    continue;
+                }
+                const OggVorbisMapper::Mapped m = mp.map(bytes.data(), bytes.size());
+                std::printf("m %s %" PRIu64 " %" PRIu64 "\n", kinds[int(m.kind)], m.dur, m.discard);
+            }
+            if (detected)
+                std::printf("extra %zu %08x ready=%d rap=%" PRIu64 "\n", mp.extra_data().size(),
+                            crc32_update(0, mp.extra_data().data(), mp.extra_data().size()), int(mp.ready()), mp.max_rap_period());
+        }
+        return 0;
+    }
+    if (mode == "bench-mpa" || mode == "bench-adts" || mode == "bench-ogg") {  // host throughput of the index builders
+        const int reps = argc > 3 ? std::atoi(argv[3]) : 5;
+        size_t packets = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; ++r) {
+            if (mode == "bench-mpa") {
+                MpaTrack t;
+                std::vector<MpaPacket> pk;
+                MpaIndexer::index(d.data(), d.size(), t, pk);
+                packets = pk.size();
+            } else if (mode == "bench-adts") {
+                std::vector<AdtsPacket> pk;
+                AdtsIndexer::index(d.data(), d.size(), pk);
+                packets = pk.size();
+            } else {
+                OggIndex ix;
+                OggIndex::build(d.data(), d.size(), ix, false);
+                packets = 0;
+                for (const auto& kv : ix.streams) packets += kv.second.packets().size();
+            }
+        }
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+        std::printf("%s: %zu bytes, %zu packets, %.3f ms per pass, %.2f GB/s, %.2f M packets/s\n", mode.c_str(), d.size(), packets, s * 1e3,
+                    double(d.size()) / s * 1e-9, double(packets) / s * 1e-6);
         return 0;
     }
     return 2;

@@ -456,3 +456,122 @@ def test_ogg_page_checksum_is_the_published_one(exe, tmp_path):
     assert rem == crc
     got = run(exe, "ogg", page, tmp=tmp_path)
     assert got[0].startswith("page 0 1 0 0 1 0") and got[-1].startswith("end ok rejected=0")
+
+
+# ------------------------------------------------------------------------------------------- Vorbis in Ogg
+
+def test_oracle_xiph_lacing_reference_cases():
+    # symphonia-common/src/xiph/audio/vorbis/mod.rs:120-199, case by case
+    assert po.vorbis_unpack_xiph_laced(bytes([2, 9, 14]) + b"id_packet" + b"comment_packet" + b"setup_packet") == (b"id_packet", b"setup_packet")
+    assert po.vorbis_unpack_xiph_laced(bytes([2, 255, 0, 0]) + bytes(255) + b"setup") == (bytes(255), b"setup")
+    for bad in (bytes([2, 2, 7]) + b"id", b"", bytes([1, 30, 0]), bytes([2, 255]), bytes([2, 0, 0])):
+        with pytest.raises(po.ReaderError):
+            po.vorbis_unpack_xiph_laced(bad)
+
+
+def test_xiph_lacing_cpp(exe, tmp_path):
+    rng = np.random.default_rng(41)
+    cases = [bytes([2, 9, 14]) + b"id_packet" + b"comment_packet" + b"setup_packet", bytes([2, 255, 0, 0]) + bytes(255) + b"setup",
+             bytes([2, 2, 7]) + b"id", bytes([1, 30, 0]), bytes([2, 255]), bytes([2, 0, 0]), bytes([2, 0, 0, 9]), bytes([2, 1, 1, 9])]
+    for _ in range(30):
+        a, b, c = (int(rng.integers(0, 700)) for _ in range(3))
+        lace = lambda n: bytes([255] * (n // 255) + [n % 255])
+        blob = bytes([2]) + lace(a) + lace(b) + rng.integers(0, 256, a + b + c, dtype=np.uint8).tobytes()
+        cases.append(blob[:len(blob) - int(rng.integers(0, 3)) * int(rng.integers(0, 300))])
+    for blob in cases:
+        if len(blob) == 0:
+            continue
+        got = run(exe, "xiph", blob, tmp=tmp_path)
+        try:
+            ident, setup = po.vorbis_unpack_xiph_laced(blob)
+            at = blob.index(ident) if ident else None
+            f = got[0].split()
+            (ia, il), (sa, sl) = (map(int, x.split(":")) for x in f[1:3])
+            assert f[0] == "ok" and blob[ia:ia + il] == ident and blob[sa:sa + sl] == setup and sa + sl == len(blob)
+            del at
+        except po.ReaderError:
+            assert got == ["decode"]
+
+
+def _vsetup_expect(ident, setup):
+    try:
+        idh = po.vorbis_read_ident(ident)
+    except po.ReaderError as e:
+        return [f"ident {e.kind}"]
+    lines = [f"ident ok ch={idh['n_channels']} rate={idh['sample_rate']} bs={idh['bs0_exp']},{idh['bs1_exp']}"]
+    try:
+        modes = po.vorbis_read_setup_modes(setup, idh)
+    except po.ReaderError as e:
+        return lines + [f"setup {'decode' if e.kind == po.EOF else e.kind}"]  # out of bits is a malformed header
+    return lines + [f"setup ok modes={len(modes)} mask={sum(1 << i for i, m in enumerate(modes) if m):x}"]
+
+
+def test_vorbis_ident_and_setup_walk(exe, tmp_path):
+    rng = np.random.default_rng(42)
+    # identification headers: every rejection the reference makes
+    good_setup, _ = st.vorbis_setup(rng)
+    for kw in (dict(), dict(channels=1, rate=8000, bs0=6, bs1=6), dict(channels=255, rate=192000, bs0=13, bs1=13), dict(version=1),
+               dict(channels=0), dict(rate=0), dict(bs0=5), dict(bs1=14), dict(bs0=9, bs1=8), dict(framing=0), dict(sig=b"vorbiz"), dict(ptype=3)):
+        ident = st.vorbis_ident(**kw)
+        assert run(exe, "vsetup", ident + good_setup, tmp=tmp_path) == _vsetup_expect(ident, good_setup)[:2]
+    # setup headers: 150 random well-formed ones over the whole grammar, mode flags must come out right
+    for trial in range(150):
+        ch = int(rng.integers(1, 9))
+        ident = st.vorbis_ident(channels=ch)
+        setup, modes = st.vorbis_setup(rng, channels=ch, modes=[bool(rng.integers(2)) for _ in range(int(rng.integers(1, 65)))] if trial % 5 == 0 else None)
+        want = _vsetup_expect(ident, setup)
+        assert want[1] == f"setup ok modes={len(modes)} mask={sum(1 << i for i, m in enumerate(modes) if m):x}", want
+        assert run(exe, "vsetup", ident + setup, tmp=tmp_path) == want
+    # and broken ones: each named fault, plus cuts at every eighth of the packet and single-bit damage
+    for fault in ("codebook_sync", "lookup_type", "time_domain", "floor_type", "mapping_type", "mapping_reserved", "window", "transform", "framing",
+                  "truncated", "signature"):
+        for _ in range(4):
+            ident = st.vorbis_ident(channels=2)
+            setup, _ = st.vorbis_setup(rng, fault=fault)
+            want = _vsetup_expect(ident, setup)
+            assert want[1] == "setup decode", (fault, want)
+            assert run(exe, "vsetup", ident + setup, tmp=tmp_path) == want
+    ident = st.vorbis_ident(channels=3)
+    setup, _ = st.vorbis_setup(rng, channels=3)
+    for k in range(1, 8):
+        cut = setup[:len(setup) * k // 8]
+        assert run(exe, "vsetup", ident + cut, tmp=tmp_path) == _vsetup_expect(ident, cut)
+    for _ in range(200):
+        hit = bytearray(setup)
+        hit[int(rng.integers(7, len(hit)))] ^= 1 << int(rng.integers(8))
+        assert run(exe, "vsetup", ident + bytes(hit), tmp=tmp_path) == _vsetup_expect(ident, bytes(hit))
+
+
+def test_ogg_vorbis_stream_mapping(exe, tmp_path):
+    rng = np.random.default_rng(43)
+    for trial in range(8):
+        ch = int(rng.integers(1, 4))
+        bs0, bs1 = (8, 11) if trial % 2 == 0 else (int(rng.integers(6, 10)), int(rng.integers(10, 14)))
+        ident = st.vorbis_ident(channels=ch, bs0=bs0, bs1=bs1)
+        setup, modes = st.vorbis_setup(rng, channels=ch, fault="framing" if trial == 7 else None)
+        comment = b"\x03vorbis" + rng.integers(0, 256, 60, dtype=np.uint8).tobytes()
+        audio = [st.vorbis_audio_packet(rng, len(modes))[0] for _ in range(60)]
+        odd = [b"", b"\x07vorbis" + bytes(5), b"\x05vorbix", b"\x03vo", bytes([0x01])]  # things a mapper must survive
+        packets = [ident, comment, setup] + audio[:20] + odd + audio[20:]
+        if trial == 6:  # audio before the setup header takes no time
+            packets = [ident, comment] + audio[:3] + [setup] + audio[3:]
+        pages = st.ogg_paginate(77, packets[:1], rng, eos=False) + st.ogg_paginate(77, packets[1:], rng, max_segments=30, first_sequence=1, bos=False)
+        data = b"".join(pages)
+        # expected, from the oracle's own page / packet / mapper chain
+        _, streams = po.ogg_index(data)
+        m = po.VorbisMapper()
+        blobs = [b"".join(data[a:a + n] for a, n in pieces) for pieces, *_ in streams[77]]
+        assert blobs == packets
+        assert m.detect(blobs[0])
+        want = ["stream 77 vorbis=1"] + ["m %s %d %d" % m.map(b) for b in blobs[1:]]
+        rap = (1 << bs1) >> 1 if m.timer else 0
+        want.append(f"extra {len(m.extra)} {po.crc32_update(0, m.extra):08x} ready={int(m.ready)} rap={rap}")
+        assert run(exe, "oggvorbis", data, tmp=tmp_path) == want
+        if trial < 6:
+            # durations: half the first block, then a quarter of each neighbour; short = 2^bs0, long = 2^bs1
+            durs = [int(w.split()[2]) for w in want[1:-1] if w.startswith("m audio")]
+            assert durs[0] in ((1 << bs0) >> 1, (1 << bs1) >> 1) and all(d in {(1 << bs0) >> 1, (1 << bs1) >> 1, ((1 << bs0) + (1 << bs1)) >> 2} for d in durs[1:] if d)
+            assert m.extra == ident + setup
+    # a stream that is not Vorbis
+    data = b"".join(st.ogg_paginate(5, [b"OpusHead" + bytes(11), b"OpusTags" + bytes(20)], rng))
+    assert run(exe, "oggvorbis", data, tmp=tmp_path) == ["stream 5 vorbis=0"]
