@@ -395,6 +395,102 @@ symgpu_status symgpu_mp3_synth_host_quantized(symgpu_ctx* ctx, const symgpu_mp3_
                                               const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
                                               int format, void* out);
 
+/* ===================================================================================================
+ * Packetisers: file bytes -> packet tables, on the host, no context and no device needed.
+ * C entry points over include/symgpu/packetizer.hpp (which C++ callers can use directly).  Nothing is copied:
+ * a packet is a reference into `data`, so the file can go to the device in one piece.
+ *   MPEG audio  MpaReader::try_new / next_packet   symphonia-bundle-mp3/src/demuxer.rs:414-487, :160-218
+ *   ADTS        AdtsReader::next_packet            symphonia-codec-aac/src/adts.rs:278-309
+ *   Ogg         PageReader + LogicalStream         symphonia-format-ogg/src/page.rs:166-271, logical.rs:104-205
+ *   Vorbis      the Ogg mapper's header work       symphonia-format-ogg/src/mappings/vorbis.rs:45-405
+ * All index functions follow the two-call pattern: with cap == 0 they only count (*n_out = what a full run
+ * would write); otherwise they write at most cap records and still report the full count.
+ * ================================================================================================= */
+typedef struct symgpu_mpa_track {       /* 48 bytes: what try_new learns from the first frame                     */
+    uint32_t first_header;   /* header word of the first frame (codec parameters)                                 */
+    uint32_t sample_rate;
+    uint8_t version;         /* 0 MPEG-1, 1 MPEG-2, 2 MPEG-2.5                                                     */
+    uint8_t layer;           /* 1..3                                                                              */
+    uint8_t channels;
+    uint8_t tag;             /* 0 none, 1 Xing, 2 Info, 3 VBRI                                                     */
+    uint8_t has_delay;       /* delay / padding come from a LAME extension                                        */
+    uint8_t has_num_frames;  /* num_frames from a tag, or the reference's estimate when `seekable`                */
+    uint8_t reserved[2];
+    uint32_t delay, padding; /* samples                                                                           */
+    uint32_t reserved2[2];
+    uint64_t num_frames;     /* samples of audio, delay and padding already removed                               */
+    uint64_t first_packet_pos;
+} symgpu_mpa_track;
+typedef struct symgpu_mpa_packet {      /* 48 bytes: one frame                                                     */
+    uint64_t offset;         /* of the header word in `data`                                                      */
+    uint32_t size;           /* whole frame                                                                       */
+    uint32_t header;         /* the header word                                                                   */
+    int64_t pts;             /* samples; the first packet starts at -delay                                        */
+    uint32_t dur;            /* samples the frame decodes to                                                      */
+    uint32_t trim_start;     /* leading samples to drop                                                           */
+    uint64_t trim_end;       /* trailing samples to drop; may exceed dur (packet.rs:334-338 does not cap it)      */
+    int32_t main_data_begin; /* Layer III bit-reservoir back pointer, -1 for Layers I / II                        */
+    uint32_t reserved;
+} symgpu_mpa_packet;
+/* SYMGPU_ERR_DECODE: no frame in the data (track untouched). */
+symgpu_status symgpu_mpa_index(const uint8_t* data, size_t n, int seekable, symgpu_mpa_track* track,
+                               symgpu_mpa_packet* packets, size_t cap, size_t* n_out);
+
+typedef struct symgpu_adts_packet {     /* 32 bytes: one raw data block (no ADTS header)                          */
+    uint64_t offset;
+    uint32_t size;
+    uint32_t sample_rate;
+    int64_t pts;             /* 1024 samples per packet                                                           */
+    uint8_t channels;        /* 0: configured in-band                                                             */
+    uint8_t profile;         /* MPEG-4 audio object type, 2 = LC                                                  */
+    uint8_t reserved[6];
+} symgpu_adts_packet;
+/* Indexes up to the first thing the reference's reader would return an error for.  *stop: SYMGPU_OK = clean end of
+ * data, SYMGPU_ERR_LIMIT = the last frame's payload is cut short, SYMGPU_ERR_DECODE / _UNSUPPORTED = a bad header
+ * (adts.rs:155-191).  The function itself fails only on null arguments. */
+symgpu_status symgpu_adts_index(const uint8_t* data, size_t n, symgpu_adts_packet* packets, size_t cap, size_t* n_out,
+                                symgpu_status* stop);
+
+typedef struct symgpu_piece {           /* 16 bytes: a byte range of `data`                                        */
+    uint64_t offset;
+    uint32_t len;
+    uint32_t reserved;
+} symgpu_piece;
+typedef struct symgpu_ogg_packet {      /* 40 bytes: a packet = pieces[first_piece .. first_piece + n_pieces)      */
+    uint32_t serial;         /* logical stream                                                                    */
+    uint32_t page_sequence;  /* of the page the packet ends on                                                    */
+    uint64_t page_absgp;     /* that page's granule position                                                      */
+    uint64_t len;
+    uint32_t first_piece;
+    uint32_t n_pieces;
+    uint8_t last_on_page;    /* the page's granule position is THIS packet's end                                  */
+    uint8_t reserved[7];
+} symgpu_ogg_packet;
+/* Every page that verifies, every logical stream announced by a first-page flag; packets grouped by serial (ascending),
+ * in stream order within a serial. */
+symgpu_status symgpu_ogg_index(const uint8_t* data, size_t n, symgpu_ogg_packet* packets, size_t cap_packets,
+                               size_t* n_packets, symgpu_piece* pieces, size_t cap_pieces, size_t* n_pieces);
+
+typedef struct symgpu_vorbis_ident {    /* 8 bytes                                                                 */
+    uint32_t sample_rate;
+    uint8_t channels;
+    uint8_t bs0_exp, bs1_exp; /* block sizes 2^6 .. 2^13, short <= long                                            */
+    uint8_t reserved;
+} symgpu_vorbis_ident;
+/* The 30-byte identification packet.  SYMGPU_ERR_DECODE / _UNSUPPORTED as read_ident_header (mappings/vorbis.rs:293-360),
+ * SYMGPU_ERR_ARG if n < 30. */
+symgpu_status symgpu_vorbis_ident_parse(const uint8_t* packet, size_t n, symgpu_vorbis_ident* ident);
+/* Walks a setup packet to its mode list: *n_modes (1..64) and bit i of *long_block_mask = mode i uses the long block. */
+symgpu_status symgpu_vorbis_setup_modes(const uint8_t* packet, size_t n, const symgpu_vorbis_ident* ident, uint32_t* n_modes,
+                                        uint64_t* long_block_mask);
+/* Durations of a run of audio packets (VorbisPacketParser::parse_next_packet_dur, :62-106): heads[i] = the first
+ * byte(s) of packet i packed little-endian (two bytes always suffice: 1 type bit + at most 6 mode bits), head_len[i] =
+ * how many bytes of the packet exist (0, 1 or >= 2).  dur / discard in samples.  *prev_exp carries the previous block's
+ * exponent across calls: 0 on entry = no previous block (stream start, or after a reset); updated on return. */
+symgpu_status symgpu_vorbis_packet_durations(const symgpu_vorbis_ident* ident, uint32_t n_modes, uint64_t long_block_mask,
+                                             const uint16_t* heads, const uint8_t* head_len, size_t n_packets, uint8_t* prev_exp,
+                                             uint32_t* dur, uint32_t* discard);
+
 #ifdef __cplusplus
 }
 #endif

@@ -955,6 +955,12 @@ class VorbisPacketTimer {
     VorbisPacketTimer(const VorbisIdent& id, uint8_t num_modes, uint64_t long_block_mask)
         : mask_(long_block_mask), num_modes_(num_modes), bs0_(id.bs0_exp), bs1_(id.bs1_exp) {}
     void reset() { prev_exp_ = 0; }
+    // New headers, same overlap state (a chained stream restarts its modes but a caller batching one stream in
+    // several calls carries the previous block across them).
+    void rebind(const VorbisIdent& id, uint8_t num_modes, uint64_t long_block_mask) {
+        mask_ = long_block_mask, num_modes_ = num_modes, bs0_ = id.bs0_exp, bs1_ = id.bs1_exp;
+    }
+    uint8_t prev_exp() const { return prev_exp_; }  // 0: no previous block
     // A packet that is not audio, names no valid mode or is cut short takes no time and leaves the state alone.
     void next(const uint8_t* p, size_t n, uint64_t& dur, uint64_t& discard) {
         dur = discard = 0;

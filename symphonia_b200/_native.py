@@ -66,6 +66,20 @@ PCM_SPAN_DTYPE = np.dtype([("src", "<u8"), ("plane_stride", "<u4"), ("frames", "
 assert PCM_SPAN_DTYPE.itemsize == 32
 FMT_F32, FMT_S16, FMT_S24, FMT_S32, FMT_U8 = 0, 1, 2, 3, 4
 FMT_NUMPY = {FMT_F32: np.float32, FMT_S16: np.int16, FMT_S24: np.int32, FMT_S32: np.int32, FMT_U8: np.uint8}
+# packetisers (include/symgpu.h "Packetisers")
+MPA_TRACK_DTYPE = np.dtype([("first_header", "<u4"), ("sample_rate", "<u4"), ("version", "u1"), ("layer", "u1"), ("channels", "u1"),
+                            ("tag", "u1"), ("has_delay", "u1"), ("has_num_frames", "u1"), ("reserved", "u1", (2,)), ("delay", "<u4"),
+                            ("padding", "<u4"), ("reserved2", "<u4", (2,)), ("num_frames", "<u8"), ("first_packet_pos", "<u8")])
+MPA_PACKET_DTYPE = np.dtype([("offset", "<u8"), ("size", "<u4"), ("header", "<u4"), ("pts", "<i8"), ("dur", "<u4"), ("trim_start", "<u4"),
+                             ("trim_end", "<u8"), ("main_data_begin", "<i4"), ("reserved", "<u4")])
+ADTS_PACKET_DTYPE = np.dtype([("offset", "<u8"), ("size", "<u4"), ("sample_rate", "<u4"), ("pts", "<i8"), ("channels", "u1"),
+                              ("profile", "u1"), ("reserved", "u1", (6,))])
+PIECE_DTYPE = np.dtype([("offset", "<u8"), ("len", "<u4"), ("reserved", "<u4")])
+OGG_PACKET_DTYPE = np.dtype([("serial", "<u4"), ("page_sequence", "<u4"), ("page_absgp", "<u8"), ("len", "<u8"), ("first_piece", "<u4"),
+                             ("n_pieces", "<u4"), ("last_on_page", "u1"), ("reserved", "u1", (7,))])
+VORBIS_IDENT_DTYPE = np.dtype([("sample_rate", "<u4"), ("channels", "u1"), ("bs0_exp", "u1"), ("bs1_exp", "u1"), ("reserved", "u1")])
+assert MPA_TRACK_DTYPE.itemsize == 48 and MPA_PACKET_DTYPE.itemsize == 48 and ADTS_PACKET_DTYPE.itemsize == 32
+assert PIECE_DTYPE.itemsize == 16 and OGG_PACKET_DTYPE.itemsize == 40 and VORBIS_IDENT_DTYPE.itemsize == 8
 AAC_ONLY_LONG, AAC_LONG_START, AAC_EIGHT_SHORT, AAC_LONG_STOP = 0, 1, 2, 3
 
 MP3_LONG, MP3_START, MP3_SHORT, MP3_END = 0, 1, 2, 3
@@ -156,6 +170,19 @@ def lib():
     L.symgpu_aac_units_check.argtypes = [vp, vp, u32, u32]
     L.symgpu_mp3_synth_host_quantized.restype = ctypes.c_int
     L.symgpu_mp3_synth_host_quantized.argtypes = [vp, vp, vp, vp, u32, u32, ctypes.c_int, vp]
+    psz = ctypes.POINTER(sz)
+    L.symgpu_mpa_index.restype = ctypes.c_int
+    L.symgpu_mpa_index.argtypes = [vp, sz, ctypes.c_int, vp, vp, sz, psz]
+    L.symgpu_adts_index.restype = ctypes.c_int
+    L.symgpu_adts_index.argtypes = [vp, sz, vp, sz, psz, ctypes.POINTER(ctypes.c_int)]
+    L.symgpu_ogg_index.restype = ctypes.c_int
+    L.symgpu_ogg_index.argtypes = [vp, sz, vp, sz, psz, vp, sz, psz]
+    L.symgpu_vorbis_ident_parse.restype = ctypes.c_int
+    L.symgpu_vorbis_ident_parse.argtypes = [vp, sz, vp]
+    L.symgpu_vorbis_setup_modes.restype = ctypes.c_int
+    L.symgpu_vorbis_setup_modes.argtypes = [vp, sz, vp, ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_uint64)]
+    L.symgpu_vorbis_packet_durations.restype = ctypes.c_int
+    L.symgpu_vorbis_packet_durations.argtypes = [vp, u32, ctypes.c_uint64, vp, vp, sz, vp, vp, vp]
     _LIB = L
     return L
 

@@ -1,0 +1,147 @@
+// C entry points of the packetisers (include/symgpu.h "Packetisers"): thin adapters from the index builders of
+// include/symgpu/packetizer.hpp to flat, caller-owned tables.  Host only; no context, no device.
+#include <vector>
+
+#include "../../include/symgpu.h"
+#include "../../include/symgpu/packetizer.hpp"
+
+using namespace symgpu::packet;
+
+static symgpu_status to_status(Status s) {
+    switch (s) {
+        case Status::Ok: return SYMGPU_OK;
+        case Status::Unsupported: return SYMGPU_ERR_UNSUPPORTED;
+        default: return SYMGPU_ERR_DECODE;
+    }
+}
+
+extern "C" symgpu_status symgpu_mpa_index(const uint8_t* data, size_t n, int seekable, symgpu_mpa_track* track,
+                                          symgpu_mpa_packet* packets, size_t cap, size_t* n_out) {
+    if ((!data && n) || !track || !n_out || (cap && !packets)) return SYMGPU_ERR_ARG;
+    MpaIndexer ix(data, n);
+    if (ix.open(seekable != 0) != Status::Ok) return *n_out = 0, SYMGPU_ERR_DECODE;
+    const MpaTrack& t = ix.track();
+    *track = symgpu_mpa_track{};
+    track->first_header = t.first_word, track->sample_rate = t.first.sample_rate;
+    track->version = uint8_t(t.first.version), track->layer = t.first.layer, track->channels = uint8_t(t.first.n_channels());
+    track->tag = uint8_t(t.tag), track->has_delay = t.has_delay, track->has_num_frames = t.has_num_frames;
+    track->delay = t.delay, track->padding = t.padding, track->num_frames = t.num_frames, track->first_packet_pos = t.first_packet_pos;
+    size_t count = 0;
+    MpaPacket p;
+    while (ix.next(p) == Status::Ok) {
+        if (count < cap) {
+            symgpu_mpa_packet& o = packets[count];
+            o = symgpu_mpa_packet{};
+            o.offset = p.offset, o.size = p.size, o.header = p.header, o.pts = p.pts, o.dur = p.dur, o.trim_start = p.trim_start, o.trim_end = p.trim_end;
+            MpaHeader h{};
+            mpa_parse_header(p.header, h);
+            o.main_data_begin = h.layer == 3 ? mpa_main_data_begin(data + p.offset, p.size, h) : -1;
+        }
+        ++count;
+    }
+    *n_out = count;
+    return SYMGPU_OK;
+}
+
+extern "C" symgpu_status symgpu_adts_index(const uint8_t* data, size_t n, symgpu_adts_packet* packets, size_t cap, size_t* n_out,
+                                           symgpu_status* stop) {
+    if ((!data && n) || !n_out || !stop || (cap && !packets)) return SYMGPU_ERR_ARG;
+    AdtsIndexer ix(data, n);
+    AdtsPacket p;
+    size_t count = 0;
+    Status s;
+    while ((s = ix.next(p)) == Status::Ok) {
+        if (count < cap) {
+            symgpu_adts_packet& o = packets[count];
+            o = symgpu_adts_packet{};
+            o.offset = p.offset, o.size = p.size, o.sample_rate = p.sample_rate, o.pts = p.pts, o.channels = p.channels, o.profile = p.profile;
+        }
+        ++count;
+    }
+    *n_out = count;
+    *stop = s == Status::EndOfStream ? (ix.truncated() ? SYMGPU_ERR_LIMIT : SYMGPU_OK) : to_status(s);
+    return SYMGPU_OK;
+}
+
+extern "C" symgpu_status symgpu_ogg_index(const uint8_t* data, size_t n, symgpu_ogg_packet* packets, size_t cap_packets,
+                                          size_t* n_packets, symgpu_piece* pieces, size_t cap_pieces, size_t* n_pieces) {
+    if ((!data && n) || !n_packets || !n_pieces || (cap_packets && !packets) || (cap_pieces && !pieces)) return SYMGPU_ERR_ARG;
+    OggIndex ix;
+    const Status s = OggIndex::build(data, n, ix, false);
+    size_t np = 0, nq = 0;
+    for (const auto& kv : ix.streams) {
+        const OggLogicalStream& ls = kv.second;
+        const size_t piece_base = nq;
+        size_t used = 0;  // pieces of completed packets (an open packet's pieces trail the list and are not reported)
+        for (const OggPacket& p : ls.packets()) {
+            if (np < cap_packets) {
+                symgpu_ogg_packet& o = packets[np];
+                o = symgpu_ogg_packet{};
+                o.serial = kv.first, o.page_sequence = p.page_sequence, o.page_absgp = p.page_absgp, o.len = p.len;
+                o.first_piece = uint32_t(piece_base + p.first_piece), o.n_pieces = p.n_pieces, o.last_on_page = p.last_on_page;
+            }
+            ++np;
+            used = size_t(p.first_piece) + p.n_pieces;
+        }
+        for (size_t k = 0; k < used; ++k, ++nq)
+            if (nq < cap_pieces) pieces[nq] = symgpu_piece{ls.pieces()[k].offset, ls.pieces()[k].len, 0};
+    }
+    *n_packets = np, *n_pieces = nq;
+    return to_status(s);
+}
+
+extern "C" symgpu_status symgpu_vorbis_ident_parse(const uint8_t* packet, size_t n, symgpu_vorbis_ident* ident) {
+    if (!packet || !ident || n < 30) return SYMGPU_ERR_ARG;
+    VorbisIdent id;
+    const Status s = vorbis_read_ident(packet, n, id);
+    if (s != Status::Ok) return to_status(s);
+    *ident = symgpu_vorbis_ident{id.sample_rate, id.n_channels, id.bs0_exp, id.bs1_exp, 0};
+    return SYMGPU_OK;
+}
+
+static bool ident_ok(const symgpu_vorbis_ident* i) {
+    return i && i->channels && i->bs0_exp >= 6 && i->bs1_exp <= 13 && i->bs0_exp <= i->bs1_exp;
+}
+
+extern "C" symgpu_status symgpu_vorbis_setup_modes(const uint8_t* packet, size_t n, const symgpu_vorbis_ident* ident, uint32_t* n_modes,
+                                                   uint64_t* long_block_mask) {
+    if (!packet || !n_modes || !long_block_mask || !ident_ok(ident)) return SYMGPU_ERR_ARG;
+    VorbisIdent id{ident->channels, ident->sample_rate, ident->bs0_exp, ident->bs1_exp};
+    uint8_t modes = 0;
+    const Status s = vorbis_read_setup_modes(packet, n, id, modes, *long_block_mask);
+    if (s != Status::Ok) return SYMGPU_ERR_DECODE;
+    *n_modes = modes;
+    return SYMGPU_OK;
+}
+
+extern "C" symgpu_status symgpu_vorbis_packet_durations(const symgpu_vorbis_ident* ident, uint32_t n_modes, uint64_t long_block_mask,
+                                                        const uint16_t* heads, const uint8_t* head_len, size_t n_packets, uint8_t* prev_exp,
+                                                        uint32_t* dur, uint32_t* discard) {
+    if (!ident_ok(ident) || n_modes == 0 || n_modes > 64 || !prev_exp || (n_packets && (!heads || !head_len || !dur || !discard)))
+        return SYMGPU_ERR_ARG;
+    const bool have_prev = *prev_exp != 0;
+    if (have_prev && (*prev_exp < 6 || *prev_exp > 13)) return SYMGPU_ERR_ARG;
+    const VorbisIdent id{ident->channels, ident->sample_rate, ident->bs0_exp, ident->bs1_exp};
+    // the timer has no way to be seeded; replay the previous block through a one-mode timer of that size instead
+    VorbisPacketTimer timer(id, uint8_t(n_modes), long_block_mask);
+    if (have_prev) {
+        VorbisIdent seed = id;
+        seed.bs0_exp = seed.bs1_exp = *prev_exp;
+        timer = VorbisPacketTimer(seed, 1, 0);
+        const uint8_t zero = 0;
+        uint64_t a, b;
+        timer.next(&zero, 1, a, b);
+        timer.rebind(id, uint8_t(n_modes), long_block_mask);
+    }
+    for (size_t i = 0; i < n_packets; ++i) {
+        const uint8_t bytes[2] = {uint8_t(heads[i] & 0xff), uint8_t(heads[i] >> 8)};
+        uint64_t a, b;
+        timer.next(bytes, head_len[i] > 2 ? 2 : head_len[i], a, b);
+        dur[i] = uint32_t(a), discard[i] = uint32_t(b);
+    }
+    *prev_exp = timer.prev_exp();
+    return SYMGPU_OK;
+}
+
+static_assert(sizeof(symgpu_mpa_track) == 48 && sizeof(symgpu_mpa_packet) == 48 && sizeof(symgpu_adts_packet) == 32, "record sizes are ABI");
+static_assert(sizeof(symgpu_piece) == 16 && sizeof(symgpu_ogg_packet) == 40 && sizeof(symgpu_vorbis_ident) == 8, "record sizes are ABI");

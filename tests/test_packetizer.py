@@ -575,3 +575,84 @@ def test_ogg_vorbis_stream_mapping(exe, tmp_path):
     # a stream that is not Vorbis
     data = b"".join(st.ogg_paginate(5, [b"OpusHead" + bytes(11), b"OpusTags" + bytes(20)], rng))
     assert run(exe, "oggvorbis", data, tmp=tmp_path) == ["stream 5 vorbis=0"]
+
+
+# ------------------------------------------------------------------------------------------- the C ABI (libsymgpu.so, no device)
+
+def test_c_abi_tables_match_the_oracle():
+    import ctypes
+
+    import symphonia_b200 as sb
+    from symphonia_b200 import _native as nat
+    from symphonia_b200 import packetizer as pk
+    rng = np.random.default_rng(51)
+    # MPEG audio: a LAME-tagged stream with junk, against the oracle's table
+    params = dict(version="1", layer=3, bitrate_idx=9, rate_idx=0, mode=1)
+    frames = [st.mpa_frame(rng, params) for _ in range(40)]
+    noise = lambda n: rng.integers(0, 255, n, dtype=np.uint8).tobytes()  # no 0xff: nothing in it can pass for a frame
+    data = noise(120) + st.mpa_tag_frame(rng, params, num_frames=40) + b"".join(frames[:25]) + noise(77) + b"".join(frames[25:])
+    track, packets = pk.mpa_index(data)
+    otrack, opackets = po.mpa_index(data)
+    assert (int(track["delay"]), int(track["padding"]), int(track["num_frames"]), int(track["tag"])) == (otrack["delay"], otrack["padding"], otrack["num_frames"], 1)
+    assert int(track["first_header"]) == otrack["word"] and int(track["first_packet_pos"]) == otrack["first_packet_pos"]
+    assert (int(track["sample_rate"]), int(track["layer"]), int(track["channels"]), int(track["version"])) == (44100, 3, 2, 0)
+    got = [tuple(int(p[k]) for k in ("offset", "size", "header", "pts", "dur", "trim_start", "trim_end")) for p in packets]
+    assert got == opackets
+    for p, (off, size, w, *_) in zip(packets, opackets):
+        h = po.mpa_parse_header(w)  # (the junk may hold a decoy frame of another layer: no reservoir pointer there)
+        assert int(p["main_data_begin"]) == (po.mpa_main_data_begin(data[off:off + size], h) if h["layer"] == 3 else -1)
+    # the trims are what the output stage takes: kept samples add up to the tagged length
+    assert sum(int(p["dur"]) - int(p["trim_start"]) - min(int(p["trim_end"]), int(p["dur"])) for p in packets) == int(track["num_frames"])
+    # counting call and short table
+    L = nat.lib()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    tr = np.zeros(1, dtype=nat.MPA_TRACK_DTYPE)
+    few = np.zeros(3, dtype=nat.MPA_PACKET_DTYPE)
+    assert L.symgpu_mpa_index(buf.ctypes.data, buf.size, 1, tr.ctypes.data, few.ctypes.data, 3, ctypes.byref(n)) == 0
+    assert n.value == len(opackets) and [int(x) for x in few["offset"]] == [p[0] for p in opackets[:3]]
+    assert L.symgpu_mpa_index(buf.ctypes.data, buf.size, 1, None, None, 0, ctypes.byref(n)) == 6  # SYMGPU_ERR_ARG
+    with pytest.raises(sb.SymgpuError) as e:
+        pk.mpa_index(st.mpa_junk(rng, 3000)[:40] + bytes(500))
+    assert e.value.status == 1
+    # ADTS
+    data = b"".join(st.adts_frame(rng, int(rng.integers(100, 500)), protected=bool(k % 3 == 0), channels=1 + k % 2) for k in range(30))
+    for blob, stop in ((data, 0), (data[:-7], 3), (data + st.adts_frame(rng, 50, rate_idx=14), 1), (data + st.adts_frame(rng, 50, blocks=2), 2)):
+        packets, got_stop = pk.adts_index(blob)
+        want, ostop = po.adts_index(blob)
+        assert got_stop == stop and {"eof": 0, "truncated": 3, "decode": 1, "unsupported": 2}[ostop] == stop
+        assert [tuple(int(p[k]) for k in ("offset", "size", "pts", "sample_rate", "channels", "profile")) for p in packets] == want
+    # Ogg: two logical streams, packets gathered through the piece table
+    a = [rng.integers(0, 256, int(n), dtype=np.uint8).tobytes() for n in rng.integers(0, 3000, 50)] + [bytes(70000)]
+    b = [rng.integers(0, 256, int(n), dtype=np.uint8).tobytes() for n in rng.integers(200, 400, 30)]
+    pa, pb = st.ogg_paginate(20, a, rng, max_segments=9), st.ogg_paginate(10, b, rng, max_segments=5)
+    data = pa[0] + pb[0] + b"".join(x for pair in zip(pa[1:], pb[1:] + [b""] * len(pa)) for x in pair) + b"".join(pa[1 + len(pb[1:]):][0:0])
+    data += b"".join(pa[len(pb):]) if len(pa) > len(pb) else b""
+    packets, pieces = pk.ogg_index(data)
+    _, ostreams = po.ogg_index(data)
+    want = [(serial, b"".join(data[o:o + n] for o, n in pcs), seq, absgp, last) for serial in sorted(ostreams) for pcs, seq, absgp, last in ostreams[serial]]
+    got = [(int(p["serial"]), pk.gather(data, p, pieces), int(p["page_sequence"]), int(p["page_absgp"]), bool(p["last_on_page"])) for p in packets]
+    assert got == want and [g[1] for g in got if g[0] == 10] == b
+    assert int(pieces["len"].sum()) == sum(len(g[1]) for g in got) and (packets["len"] == [len(g[1]) for g in got]).all()
+    # Vorbis helpers
+    ident_pkt = st.vorbis_ident(channels=2, bs0=7, bs1=12)
+    setup, modes = st.vorbis_setup(rng, channels=2)
+    ident = pk.vorbis_ident(ident_pkt)
+    assert (int(ident["channels"]), int(ident["sample_rate"]), int(ident["bs0_exp"]), int(ident["bs1_exp"])) == (2, 44100, 7, 12)
+    n_modes, mask = pk.vorbis_setup_modes(setup, ident)
+    assert n_modes == len(modes) and mask == sum(1 << i for i, m in enumerate(modes) if m)
+    audio = [st.vorbis_audio_packet(rng, n_modes)[0] for _ in range(50)] + [b"", b"\x01", bytes([0x00])]
+    timer = po.VorbisTimer(po.vorbis_read_ident(ident_pkt), modes)
+    want = [timer.next(x) for x in audio]
+    dur, discard, prev = pk.vorbis_packet_durations(ident, n_modes, mask, audio)
+    assert [(int(a_), int(b_)) for a_, b_ in zip(dur, discard)] == want
+    # the same run in two calls, state carried through prev_exp
+    d1, c1, prev1 = pk.vorbis_packet_durations(ident, n_modes, mask, audio[:17])
+    d2, c2, prev2 = pk.vorbis_packet_durations(ident, n_modes, mask, audio[17:], prev_exp=prev1)
+    assert (np.concatenate([d1, d2]) == dur).all() and (np.concatenate([c1, c2]) == discard).all() and prev2 == prev and prev1 in (7, 12)
+    for bad in (st.vorbis_ident(bs0=5), st.vorbis_ident(version=3)):
+        with pytest.raises(sb.SymgpuError) as e:
+            pk.vorbis_ident(bad)
+        assert e.value.status == (1 if bad[7] == 0 else 2)
+    with pytest.raises(sb.SymgpuError):
+        pk.vorbis_setup_modes(st.vorbis_setup(rng, fault="framing")[0], ident)
