@@ -491,6 +491,43 @@ symgpu_status symgpu_vorbis_packet_durations(const symgpu_vorbis_ident* ident, u
                                              const uint16_t* heads, const uint8_t* head_len, size_t n_packets, uint8_t* prev_exp,
                                              uint32_t* dur, uint32_t* discard);
 
+/* ===================================================================================================
+ * MP3 entropy front-end: MPEG frame bytes -> the batch format of the synthesis entry points --
+ * 4 x symgpu_mp3_gc + the QUANTISED spectrum (int16, as symgpu_mp3_synth_host_quantized takes it).  CPU only,
+ * one object per stream (it owns the bit reservoir); no context, no device.
+ *   MpaDecoder::decode_inner (header, size and spec checks)   symphonia-bundle-mp3/src/decoder.rs:84-131
+ *   Layer3::decode up to the synthesis seam                    layer3/mod.rs:373-418
+ *   BitResevoir::fill / consume                                layer3/mod.rs:42-108
+ *   read_side_info, read_scale_factors_mpeg1 / _mpeg2          layer3/bitstream.rs:57-427
+ *   read_main_data, read_huffman_samples (without POW43)       layer3/mod.rs:272-370, requantize.rs:47-237
+ * ================================================================================================= */
+typedef struct symgpu_mp3_fe symgpu_mp3_fe;
+typedef struct symgpu_mp3_frame_info {  /* 16 bytes */
+    uint32_t sample_rate;
+    uint8_t channels;          /* 1 or 2                                                                    */
+    uint8_t granules;          /* 2 (MPEG-1) or 1: symgpu_mp3_run.granules_per_frame                         */
+    uint8_t sample_rate_idx;
+    uint8_t version;           /* 0 MPEG-1, 1 MPEG-2, 2 MPEG-2.5                                             */
+    uint32_t underflow_bytes;  /* main_data_begin pointed this many bytes before what the reservoir holds   */
+    uint32_t main_data_bytes;  /* bytes of main data this frame consumed from the reservoir                  */
+} symgpu_mp3_frame_info;
+symgpu_status symgpu_mp3_fe_create(symgpu_mp3_fe** out);
+void symgpu_mp3_fe_destroy(symgpu_mp3_fe* fe);
+void symgpu_mp3_fe_reset(symgpu_mp3_fe* fe);   /* AudioDecoder::reset: empty reservoir, no signal spec yet */
+/* One packet = one whole frame, header word first.
+ *   units [2][2]       as the synthesis takes them; absent units (mono channel 1, MPEG-2 granule 1) get F_MUTE
+ *   quant [2][2][576]  sign * x, |x| <= 8206; 0 from rzero on and in absent units
+ * SYMGPU_ERR_DECODE: the reference would return an error for this packet and produce no audio (the reservoir is
+ * cleared where the reference clears it); units / quant are then unspecified. */
+symgpu_status symgpu_mp3_fe_decode(symgpu_mp3_fe* fe, const uint8_t* frame, size_t n, symgpu_mp3_gc* units, int16_t* quant,
+                                   symgpu_mp3_frame_info* info);
+/* A stream's packets in one call: packet i = data[packets[i].offset .. + size).  Good frames are written densely
+ * (units / quant of the k-th good frame at index k) and frame_of[k] = its packet index; *n_good = how many.
+ * `info` describes the first good frame.  Fails only on bad arguments. */
+symgpu_status symgpu_mp3_fe_decode_packets(symgpu_mp3_fe* fe, const uint8_t* data, size_t n, const symgpu_mpa_packet* packets,
+                                           size_t n_packets, symgpu_mp3_gc* units, int16_t* quant, uint32_t* frame_of,
+                                           size_t* n_good, symgpu_mp3_frame_info* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,9 @@ OGG_PACKET_DTYPE = np.dtype([("serial", "<u4"), ("page_sequence", "<u4"), ("page
                              ("n_pieces", "<u4"), ("last_on_page", "u1"), ("reserved", "u1", (7,))])
 VORBIS_IDENT_DTYPE = np.dtype([("sample_rate", "<u4"), ("channels", "u1"), ("bs0_exp", "u1"), ("bs1_exp", "u1"), ("reserved", "u1")])
 assert MPA_TRACK_DTYPE.itemsize == 48 and MPA_PACKET_DTYPE.itemsize == 48 and ADTS_PACKET_DTYPE.itemsize == 32
+MP3_FRAME_INFO_DTYPE = np.dtype([("sample_rate", "<u4"), ("channels", "u1"), ("granules", "u1"), ("sample_rate_idx", "u1"), ("version", "u1"),
+                                 ("underflow_bytes", "<u4"), ("main_data_bytes", "<u4")])
+assert MP3_FRAME_INFO_DTYPE.itemsize == 16
 assert PIECE_DTYPE.itemsize == 16 and OGG_PACKET_DTYPE.itemsize == 40 and VORBIS_IDENT_DTYPE.itemsize == 8
 AAC_ONLY_LONG, AAC_LONG_START, AAC_EIGHT_SHORT, AAC_LONG_STOP = 0, 1, 2, 3
 
@@ -183,6 +186,16 @@ def lib():
     L.symgpu_vorbis_setup_modes.argtypes = [vp, sz, vp, ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_uint64)]
     L.symgpu_vorbis_packet_durations.restype = ctypes.c_int
     L.symgpu_vorbis_packet_durations.argtypes = [vp, u32, ctypes.c_uint64, vp, vp, sz, vp, vp, vp]
+    L.symgpu_mp3_fe_create.restype = ctypes.c_int
+    L.symgpu_mp3_fe_create.argtypes = [ctypes.POINTER(vp)]
+    L.symgpu_mp3_fe_destroy.restype = None
+    L.symgpu_mp3_fe_destroy.argtypes = [vp]
+    L.symgpu_mp3_fe_reset.restype = None
+    L.symgpu_mp3_fe_reset.argtypes = [vp]
+    L.symgpu_mp3_fe_decode.restype = ctypes.c_int
+    L.symgpu_mp3_fe_decode.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.symgpu_mp3_fe_decode_packets.restype = ctypes.c_int
+    L.symgpu_mp3_fe_decode_packets.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, psz, vp]
     _LIB = L
     return L
 

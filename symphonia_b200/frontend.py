@@ -1,0 +1,64 @@
+"""MP3 entropy front-end through the C ABI (`symgpu_mp3_fe_*`, include/symgpu.h): MPEG frame bytes ->
+`symgpu_mp3_gc` units + int16 quantised spectra, the input of `Engine.mp3_synth_host_quantized`.  CPU only; mirrors
+`MpaDecoder::decode_inner` + `Layer3::decode` up to the synthesis seam (symphonia-bundle-mp3/src/decoder.rs:84-131,
+layer3/mod.rs:373-418)."""
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+from .engine import SymgpuError
+
+_vp = ctypes.c_void_p
+
+
+class Mp3Frontend:
+    """One stream's front-end state (the bit reservoir and the signal specification of its first frame)."""
+
+    def __init__(self):
+        self._L = nat.lib()
+        h = _vp()
+        rc = self._L.symgpu_mp3_fe_create(ctypes.byref(h))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_mp3_fe_create")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._L.symgpu_mp3_fe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def reset(self):
+        self._L.symgpu_mp3_fe_reset(self._h)
+
+    def decode(self, frame):
+        """(units[2][2], quant[2][2][576] int16, info) of one packet; SymgpuError(status 1 / 2) where the reference errors."""
+        a = np.frombuffer(bytes(frame), dtype=np.uint8)
+        units = np.zeros((2, 2), dtype=nat.MP3_GC_DTYPE)
+        quant = np.zeros((2, 2, 576), dtype=np.int16)
+        info = np.zeros(1, dtype=nat.MP3_FRAME_INFO_DTYPE)
+        rc = self._L.symgpu_mp3_fe_decode(self._h, _vp(a.ctypes.data) if a.size else None, a.size, _vp(units.ctypes.data), _vp(quant.ctypes.data),
+                                          _vp(info.ctypes.data))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_mp3_fe_decode")
+        return units, quant, info[0]
+
+    def decode_packets(self, data, packets):
+        """A whole stream: (units[n_good][2][2], quant[n_good][2][2][576], frame_of[n_good], info of the first good frame)."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        packets = np.ascontiguousarray(packets, dtype=nat.MPA_PACKET_DTYPE)
+        n = len(packets)
+        units = np.zeros((n, 2, 2), dtype=nat.MP3_GC_DTYPE)
+        quant = np.zeros((n, 2, 2, 576), dtype=np.int16)
+        frame_of = np.zeros(n, dtype=np.uint32)
+        info = np.zeros(1, dtype=nat.MP3_FRAME_INFO_DTYPE)
+        good = ctypes.c_size_t(0)
+        rc = self._L.symgpu_mp3_fe_decode_packets(self._h, _vp(a.ctypes.data), a.size, _vp(packets.ctypes.data), n, _vp(units.ctypes.data),
+                                                  _vp(quant.ctypes.data), _vp(frame_of.ctypes.data), ctypes.byref(good), _vp(info.ctypes.data))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_mp3_fe_decode_packets")
+        g = good.value
+        return units[:g], quant[:g], frame_of[:g], info[0]
