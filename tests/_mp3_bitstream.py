@@ -76,7 +76,7 @@ def _mpeg2_partition(sfc, intensity_channel, block):
     return slen, row[block], preflag
 
 
-def gen_granule_channel(rng, version, rate_idx9, budget_bits, gr, scfsi, gr0_scalefacs, intensity_channel, rich=True):
+def gen_granule_channel(rng, version, rate_idx9, budget_bits, gr, scfsi, gr0_scalefacs, intensity_channel, rich=True, like=None):
     """One granule-channel: returns a dict with the side-information fields, `bits` (a BitWriterMsb holding part 2 +
     part 3 + stuffing) and the ground truth (`scalefacs`, `quant`, `rzero`, `preflag`)."""
     mpeg1 = version == "1"
@@ -86,6 +86,9 @@ def gen_granule_channel(rng, version, rate_idx9, budget_bits, gr, scfsi, gr0_sca
         g["block_type"] = int(rng.integers(1, 4))
         g["mixed_bit"] = int(rng.integers(2))
         g["subblock_gain"] = [int(x) for x in rng.integers(0, 8, 3)]
+    if like is not None:  # joint stereo wants one window sequence for the pair (ISO 11172-3 2.4.3.4.10)
+        g.update(window_switching=like["window_switching"], block_type=like["block_type"], mixed_bit=like["mixed_bit"])
+        g["subblock_gain"] = [int(x) for x in rng.integers(0, 8, 3)] if g["window_switching"] else [0, 0, 0]
     short = g["block_type"] == 2
     mixed = short and g["mixed_bit"] == 1
     bits = BitWriterMsb()
@@ -248,7 +251,8 @@ def side_info_bytes(version, n_ch, main_data_begin, scfsi, granules):
     return out
 
 
-def gen_stream(rng, n_frames, version="1", mode=1, rate_idx=0, bitrate_idx=9, protected=False, fill=(0.3, 1.0), padding=None, rich=True):
+def gen_stream(rng, n_frames, version="1", mode=1, rate_idx=0, bitrate_idx=9, protected=False, fill=(0.3, 1.0), padding=None, rich=True,
+               pair_blocks=False):
     """A stream of frames with a bit reservoir.  Returns (list of frame bytes, list of per-frame truth dicts)."""
     n_ch = 1 if mode == 3 else 2
     n_gr = 2 if version == "1" else 1
@@ -279,7 +283,8 @@ def gen_stream(rng, n_frames, version="1", mode=1, rate_idx=0, bitrate_idx=9, pr
                 row = []
                 for ch in range(n_ch):
                     row.append(gen_granule_channel(rng, version, rate_idx9, int(shares[gr * n_ch + ch]), gr, scfsi[ch],
-                                                   granules[0][ch]["scalefacs"] if gr == 1 else None, ch == 1 and intensity, rich=rich))
+                                                   granules[0][ch]["scalefacs"] if gr == 1 else None, ch == 1 and intensity, rich=rich,
+                                                   like=row[0] if (pair_blocks and ch == 1) else None))
                 granules.append(row)
             md = BitWriterMsb()
             for row in granules:

@@ -1,0 +1,76 @@
+"""The whole chain SURVEY §8 draws: file bytes -> packetiser (N2) -> entropy front-end (N1) -> fused synthesis kernel
+-> PCM, against the oracle's synthesis of the same units.  The CPU test checks everything up to the launch (the
+tables are well-formed, the oracle synthesises them); the GPU test adds the device and compares every PCM word.
+(Named to run last: it spans every layer below it.)"""
+import numpy as np
+import pytest
+
+from symphonia_b200 import _native as nat
+from symphonia_b200 import frontend, packetizer
+from tests import _mp3_bitstream as bw
+from tests import _oracle
+from tests import _streams as st
+
+
+def _corpus():
+    """Three files: MPEG-1 joint stereo with a LAME tag and junk, MPEG-2 mono, MPEG-1 dual channel with CRCs."""
+    rng = np.random.default_rng(77)
+    files = []
+    frames, _ = bw.gen_stream(rng, 30, version="1", mode=1, bitrate_idx=9, pair_blocks=True)
+    tag = st.mpa_tag_frame(rng, dict(version="1", layer=3, bitrate_idx=9, rate_idx=0, mode=1), num_frames=30)
+    noise = rng.integers(0, 255, 200, dtype=np.uint8).tobytes()
+    files.append(noise + tag + b"".join(frames[:17]) + noise[:33] + b"".join(frames[17:]))
+    frames, _ = bw.gen_stream(rng, 24, version="2", mode=3, bitrate_idx=8, rate_idx=1)
+    files.append(b"".join(frames))
+    frames, _ = bw.gen_stream(rng, 20, version="1", mode=2, bitrate_idx=11, rate_idx=1, protected=True)
+    files.append(b"".join(frames))
+    return files
+
+
+def _batch(files):
+    units, quant, runs, spans = [], [], [], []
+    at = 0
+    for s, data in enumerate(files):
+        track, packets = packetizer.mpa_index(data)
+        fe = frontend.Mp3Frontend()
+        u, q, frame_of, info = fe.decode_packets(data, packets)
+        assert len(frame_of) == len(packets)  # every packet of these files decodes
+        units.append(u), quant.append(q)
+        runs.append((s, at, len(u), int(info["granules"]), int(info["channels"]), 0))
+        kept = packets[frame_of]
+        spans.append((kept["dur"].astype(np.int64), kept["trim_start"].astype(np.int64), np.minimum(kept["trim_end"], kept["dur"]).astype(np.int64)))
+        at += len(u)
+    return np.concatenate(units), np.concatenate(quant), np.array(runs, dtype=nat.MP3_RUN_DTYPE), spans
+
+
+def _spectra(quant):
+    pow43 = nat.mp3_pow43()
+    mag = pow43[np.abs(quant.astype(np.int32))]
+    return np.where(quant < 0, -mag, mag).astype(np.float32)  # read_huffman_samples: (1 - 2 * sign) * POW43[x], +0.0 for x = 0
+
+
+def test_chain_up_to_the_launch(oracle):
+    files = _corpus()
+    units, quant, runs, spans = _batch(files)
+    assert len(units) == 74 and runs["granules_per_frame"].tolist() == [2, 1, 2] and runs["channels"].tolist() == [2, 1, 2]
+    assert nat.lib().symgpu_mp3_units_check(units.ctypes.data, runs.ctypes.data, len(runs), len(units)) == 0
+    rc, pcm, _ = _oracle.mp3_batch(oracle, units.reshape(-1), _spectra(quant), runs, len(files))
+    assert rc == 0 and np.isfinite(pcm).all() and np.abs(pcm).max() > 0
+    # gapless: the LAME tag's delay / padding arrive as per-packet trims that leave exactly the tagged length
+    dur, t0, t1 = spans[0]
+    assert int((dur - t0 - t1).sum()) == 30 * 1152 - 1105 - 471 and int(t0[0]) == 1105
+
+
+@pytest.mark.gpu
+def test_file_bytes_to_pcm_on_the_device(oracle):
+    import symphonia_b200 as sb
+    files = _corpus()
+    units, quant, runs, _ = _batch(files)
+    rc, want, _ = _oracle.mp3_batch(oracle, units.reshape(-1), _spectra(quant), runs, len(files))
+    assert rc == 0
+    with sb.Engine(0) as eng:
+        eng.mp3_streams_alloc(len(files))
+        got = eng.mp3_synth_host_quantized(units.reshape(-1), quant, runs)
+        assert eng.launch_count >= 2  # dequantise + synthesis
+    same = got.view(np.uint32) == want.view(np.uint32)
+    assert same.all(), f"{int((~same).sum())} PCM words differ, first at {np.argwhere(~same)[0]}"
