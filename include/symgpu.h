@@ -528,6 +528,32 @@ symgpu_status symgpu_mp3_fe_decode_packets(symgpu_mp3_fe* fe, const uint8_t* dat
                                            size_t n_packets, symgpu_mp3_gc* units, int16_t* quant, uint32_t* frame_of,
                                            size_t* n_good, symgpu_mp3_frame_info* info);
 
+/* ---- the same front-end as a PLAN + parallel jobs (what the device path executes) --------------------------------
+ * A granule-channel's first bit follows from the side information alone (the part2_3_length fields before it), and
+ * so does every step of the bit reservoir.  symgpu_mp3_entropy_plan therefore walks a stream's packets once WITHOUT
+ * touching the Huffman data and emits
+ *   md    the main data of the good frames, concatenated: a frame's reservoir is one contiguous window of it
+ *   jobs  4 per good frame (64 bytes each, layout: symphonia_b200/csrc/mp3_entropy.h GcJob), independent of each other
+ * which symgpu_mp3_entropy_run_cpu (host threads of the caller's choosing; the test model) or the device kernel turn into
+ * units + quantised spectra, one job per thread.  A job that fails at decode time ("huffman decode overrun",
+ * layer3/mod.rs:345-358) makes the reference drop the frame AND empty the reservoir, which changes the plan of the frames
+ * behind it: pass the failed packets back in `bad` and plan again (symgpu_mp3_entropy_decode_cpu does this loop). */
+typedef struct symgpu_mp3_gc_job { uint64_t opaque[8]; } symgpu_mp3_gc_job;
+/* bad: n_packets flags (1 = known to fail at decode time) or NULL.  md_cap >= the packets' total size is always enough.
+ * frame_of[k] = packet index of good frame k; jobs / frame_of may be NULL to count only.  *md_len, *n_good: results. */
+symgpu_status symgpu_mp3_entropy_plan(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets,
+                                      const uint8_t* bad, uint8_t* md, size_t md_cap, size_t* md_len, symgpu_mp3_gc_job* jobs,
+                                      uint32_t* frame_of, size_t* n_good, symgpu_mp3_frame_info* info);
+/* Runs jobs [0, n_jobs): unit / quant slot of a job = its out_index (frame * 4 + granule * 2 + channel, frames counted from
+ * the first job's frame).  failed[f] = 1 when a job of good frame f failed.  Pure function of its inputs: callers may
+ * split the job range over threads. */
+symgpu_status symgpu_mp3_entropy_run_cpu(const uint8_t* md, size_t md_len, const symgpu_mp3_gc_job* jobs, size_t n_jobs,
+                                         symgpu_mp3_gc* units, int16_t* quant, uint8_t* failed);
+/* plan -> run -> re-plan until no job fails; results as symgpu_mp3_fe_decode_packets (a fresh stream: no state carried). */
+symgpu_status symgpu_mp3_entropy_decode_cpu(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets,
+                                            symgpu_mp3_gc* units, int16_t* quant, uint32_t* frame_of, size_t* n_good,
+                                            symgpu_mp3_frame_info* info, uint32_t* n_rounds);
+
 #ifdef __cplusplus
 }
 #endif

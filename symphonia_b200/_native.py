@@ -196,6 +196,12 @@ def lib():
     L.symgpu_mp3_fe_decode.argtypes = [vp, vp, sz, vp, vp, vp]
     L.symgpu_mp3_fe_decode_packets.restype = ctypes.c_int
     L.symgpu_mp3_fe_decode_packets.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, psz, vp]
+    L.symgpu_mp3_entropy_plan.restype = ctypes.c_int
+    L.symgpu_mp3_entropy_plan.argtypes = [vp, sz, vp, sz, vp, vp, sz, psz, vp, vp, psz, vp]
+    L.symgpu_mp3_entropy_run_cpu.restype = ctypes.c_int
+    L.symgpu_mp3_entropy_run_cpu.argtypes = [vp, sz, vp, sz, vp, vp, vp]
+    L.symgpu_mp3_entropy_decode_cpu.restype = ctypes.c_int
+    L.symgpu_mp3_entropy_decode_cpu.argtypes = [vp, sz, vp, sz, vp, vp, vp, psz, vp, ctypes.POINTER(u32)]
     _LIB = L
     return L
 

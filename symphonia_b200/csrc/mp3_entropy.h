@@ -11,6 +11,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "../../include/symgpu.h"
+
 #ifdef __CUDACC__
 #define SYMGPU_HD __host__ __device__ __forceinline__
 #define SYMGPU_UNROLL _Pragma("unroll")
@@ -49,6 +51,13 @@ struct Bits {
     SYMGPU_HD Bits(const uint8_t* data, size_t n_bytes, size_t start_bit = 0) : p(data), n_bits(n_bytes * 8), at(start_bit) {}
     SYMGPU_HD uint32_t window() const {  // the next 32 bits, left-aligned
         const size_t byte = at >> 3, n = n_bits >> 3;
+#ifndef __CUDA_ARCH__
+        if (byte + 8 <= n) {  // host fast path: one unaligned load
+            uint64_t w;
+            __builtin_memcpy(&w, p + byte, 8);
+            return uint32_t((__builtin_bswap64(w) << (at & 7)) >> 32);
+        }
+#endif
         uint64_t v = 0;
 SYMGPU_UNROLL
         for (int k = 0; k < 5; ++k) v = v << 8 | (byte + k < n ? p[byte + k] : 0);
@@ -224,6 +233,86 @@ SYMGPU_UNROLL
     }
     for (int k = i; k < 576; ++k) q[k] = 0;
     return i;
+}
+
+// ---- one granule-channel as a unit of parallel work ---------------------------------------------------------------
+// The host walks the frames once (headers, side information, bit-reservoir arithmetic: none of it needs the Huffman
+// data) and emits one job per unit slot; the main data of all frames is compacted into one byte stream `md`, in which
+// a frame's reservoir -- the bytes main_data_begin reaches back to plus its own -- is one contiguous window.
+enum : uint8_t { kJobDecode = 0, kJobSilent = 1, kJobMute = 2 };
+struct GcJob {  // 64 bytes
+    uint64_t seg_begin;      // byte offset in md of the frame's reservoir window
+    uint32_t seg_len;        // its length: reads beyond it fail exactly where the reference's reservoir ends
+    uint32_t bit_begin;      // first bit of this granule-channel's part 2, from seg_begin
+    uint32_t gr0_bit_begin;  // MPEG-1 granule 1 with scfsi: where granule 0's part 2 (same channel) starts; ~0u = it was never read
+    uint32_t out_index;      // unit slot: frame * 4 + granule * 2 + channel
+    GcSide side;             // 22 bytes
+    uint16_t gr0_scalefac_compress;
+    uint8_t gr0_block_type, gr0_mixed;
+    uint8_t kind;            // kJobDecode | kJobSilent (bits lost to an underflow: zeros, side information kept) | kJobMute (absent unit)
+    uint8_t mpeg1, intensity_channel, scfsi;
+    uint8_t unit_flags;      // frame-level SYMGPU_MP3_F_* bits
+    uint8_t sample_rate_idx;
+    uint8_t reserved[8];
+};
+static_assert(sizeof(GcJob) == 64, "GcJob is 64 bytes");
+
+// Fills one unit and its 576 quantised lines.  Returns 0, or 1 when the reference would refuse the frame here
+// ("part2_3_length is not valid", "huffman decode overrun", an offset past the reservoir: layer3/mod.rs:318-358).
+SYMGPU_HD int decode_gc_job(const GcJob& j, const uint8_t* md, const HuffSet& hs, symgpu_mp3_gc* unit, int16_t* q) {
+    symgpu_mp3_gc u;
+    u.rzero = 0, u.global_gain = 0, u.block_type = 0, u.flags = j.unit_flags, u.sample_rate_idx = j.sample_rate_idx;
+    for (int k = 0; k < 3; ++k) u.subblock_gain[k] = 0;
+    for (int k = 0; k < 39; ++k) u.scalefacs[k] = 0;
+    for (int k = 0; k < 16; ++k) u.reserved[k] = 0;
+    int status = 0;
+    if (j.kind == kJobMute) {
+        u.flags |= SYMGPU_MP3_F_MUTE;
+        for (int k = 0; k < 576; ++k) q[k] = 0;
+    } else {
+        const GcSide& c = j.side;
+        uint8_t preflag = c.preflag;
+        int rzero = 0;
+        if (j.kind == kJobSilent) {
+            for (int k = 0; k < 576; ++k) q[k] = 0;
+        } else {
+            const uint8_t* seg = md + j.seg_begin;
+            Bits bs(seg, j.seg_len, j.bit_begin);
+            int part2 = -1;
+            if ((j.bit_begin >> 3) <= j.seg_len && bs.at <= bs.n_bits) {
+                if (j.mpeg1) {
+                    uint8_t first[39];
+                    const uint8_t* copy_from = nullptr;
+                    if (j.scfsi && c.block_type != 2 && (j.out_index & 2)) {  // granule 1 repeating groups of granule 0
+                        for (int k = 0; k < 39; ++k) first[k] = 0;
+                        copy_from = first;
+                        if (j.gr0_bit_begin != ~0u) {
+                            GcSide g0 = c;
+                            g0.scalefac_compress = j.gr0_scalefac_compress, g0.block_type = j.gr0_block_type, g0.mixed = j.gr0_mixed;
+                            Bits b0(seg, j.seg_len, j.gr0_bit_begin);
+                            read_scale_factors_mpeg1(b0, g0, nullptr, 0, first);  // its own failure is granule 0's job to report
+                        }
+                    }
+                    part2 = read_scale_factors_mpeg1(bs, c, copy_from, j.scfsi, u.scalefacs);
+                } else {
+                    part2 = read_scale_factors_mpeg2(bs, j.intensity_channel != 0, c, &preflag, u.scalefacs);
+                }
+            }
+            if (part2 < 0 || uint32_t(part2) > c.part2_3_length) {
+                status = 1;
+                for (int k = 0; k < 576; ++k) q[k] = 0;
+            } else {
+                rzero = read_huffman(bs, hs, c, uint32_t(c.part2_3_length) - uint32_t(part2), q);
+                if (rzero < 0) status = 1, rzero = 0;
+            }
+        }
+        u.rzero = uint16_t(rzero), u.global_gain = c.global_gain, u.block_type = c.block_type;
+        u.flags |= uint8_t((c.mixed ? SYMGPU_MP3_F_MIXED : 0) | (c.scalefac_scale ? SYMGPU_MP3_F_SCALEFAC_SCALE : 0) | (preflag ? SYMGPU_MP3_F_PREFLAG : 0) |
+                           ((c.scalefac_compress & 1) ? SYMGPU_MP3_F_SFC_LSB : 0));
+        for (int k = 0; k < 3; ++k) u.subblock_gain[k] = c.subblock_gain[k];
+    }
+    *unit = u;
+    return status;
 }
 
 }  // namespace mp3e

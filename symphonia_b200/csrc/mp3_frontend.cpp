@@ -169,14 +169,41 @@ bool read_side_info(Bits& bs, const MpaHeader& h, Frame& f) {
     return true;
 }
 
+// decoder.rs:84-131: synchronise inside the packet, parse, insist that the packet is exactly one frame of the stream's
+// signal specification (fixed by the first packet ever shown, good or bad) and of Layer III; skip the CRC.
+struct Spec {
+    bool have = false;
+    uint32_t rate = 0;
+    int channels = 0;
+};
+symgpu_status open_packet(Spec& spec, const uint8_t* frame, size_t n, MpaHeader& h, const uint8_t*& buf, size_t& buf_len) {
+    using namespace symgpu::packet;
+    size_t q = 0;
+    uint32_t word = 0;
+    for (;; ++q) {
+        if (q + 4 > n) return SYMGPU_ERR_DECODE;
+        word = detail::be32(frame + q);
+        if (mpa_is_synced(word) && mpa_check_header(word)) break;
+    }
+    const Status hs = mpa_parse_header(word, h);
+    if (hs != Status::Ok) return hs == Status::Unsupported ? SYMGPU_ERR_UNSUPPORTED : SYMGPU_ERR_DECODE;
+    const size_t body_len = n - q - 4;
+    if (h.frame_size != body_len) return SYMGPU_ERR_DECODE;
+    if (!spec.have) spec.have = true, spec.rate = h.sample_rate, spec.channels = h.n_channels();
+    else if (spec.rate != h.sample_rate || spec.channels != h.n_channels()) return SYMGPU_ERR_DECODE;
+    if (h.layer != 3) return SYMGPU_ERR_DECODE;
+    const size_t crc_len = h.crc ? 2 : 0;
+    if (body_len < crc_len) return SYMGPU_ERR_DECODE;
+    buf = frame + q + 4 + crc_len, buf_len = body_len - crc_len;
+    return SYMGPU_OK;
+}
+
 }  // namespace
 
 struct symgpu_mp3_fe {
     uint8_t reservoir[2048];
     size_t len = 0, consumed = 0;
-    bool have_spec = false;
-    uint32_t spec_rate = 0;
-    int spec_channels = 0;
+    Spec spec;
     void clear() { len = consumed = 0; }
 };
 
@@ -193,36 +220,20 @@ extern "C" symgpu_status symgpu_mp3_fe_create(symgpu_mp3_fe** out) {
 }
 extern "C" void symgpu_mp3_fe_destroy(symgpu_mp3_fe* fe) { delete fe; }
 extern "C" void symgpu_mp3_fe_reset(symgpu_mp3_fe* fe) {
-    if (fe) fe->clear(), fe->have_spec = false;
+    if (fe) fe->clear(), fe->spec = Spec{};
 }
 
 extern "C" symgpu_status symgpu_mp3_fe_decode(symgpu_mp3_fe* fe, const uint8_t* frame, size_t n, symgpu_mp3_gc* units, int16_t* quant,
                                               symgpu_mp3_frame_info* info) {
     using namespace symgpu::packet;
     if (!fe || (!frame && n) || !units || !quant) return SYMGPU_ERR_ARG;
-    // decoder.rs:87-93: synchronise inside the packet, parse, and insist that the packet is exactly one frame
-    size_t q = 0;
-    uint32_t word = 0;
-    for (;; ++q) {
-        if (q + 4 > n) return SYMGPU_ERR_DECODE;
-        word = detail::be32(frame + q);
-        if (mpa_is_synced(word) && mpa_check_header(word)) break;
-    }
     MpaHeader h{};
-    const Status hs = mpa_parse_header(word, h);
-    if (hs != Status::Ok) return hs == Status::Unsupported ? SYMGPU_ERR_UNSUPPORTED : SYMGPU_ERR_DECODE;
-    const uint8_t* body = frame + q + 4;
-    const size_t body_len = n - q - 4;
-    if (h.frame_size != body_len) return SYMGPU_ERR_DECODE;
-    // decoder.rs:96-108: the signal specification (rate, channel layout) is fixed by the first frame
-    if (!fe->have_spec) fe->have_spec = true, fe->spec_rate = h.sample_rate, fe->spec_channels = h.n_channels();
-    else if (fe->spec_rate != h.sample_rate || fe->spec_channels != h.n_channels()) return SYMGPU_ERR_DECODE;
-    if (h.layer != 3) return SYMGPU_ERR_DECODE;
-
-    const size_t crc_len = h.crc ? 2 : 0;
-    if (body_len < crc_len) return SYMGPU_ERR_DECODE;
-    const uint8_t* buf = body + crc_len;
-    const size_t buf_len = body_len - crc_len;
+    const uint8_t* buf = nullptr;
+    size_t buf_len = 0;
+    {
+        const symgpu_status hs = open_packet(fe->spec, frame, n, h, buf, buf_len);
+        if (hs != SYMGPU_OK) return hs;
+    }
     Frame f{};
     Bits side(buf, buf_len);
     if (!read_side_info(side, h, f)) return fe->clear(), SYMGPU_ERR_DECODE;
@@ -318,5 +329,146 @@ extern "C" symgpu_status symgpu_mp3_fe_decode_packets(symgpu_mp3_fe* fe, const u
         frame_of[good++] = uint32_t(i);
     }
     *n_good = good;
+    return SYMGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- plan + jobs
+static_assert(sizeof(symgpu_mp3_gc_job) == sizeof(symgpu::mp3e::GcJob), "the public job record is the GcJob");
+
+extern "C" symgpu_status symgpu_mp3_entropy_plan(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets,
+                                                 const uint8_t* bad, uint8_t* md, size_t md_cap, size_t* md_len, symgpu_mp3_gc_job* jobs_out,
+                                                 uint32_t* frame_of, size_t* n_good, symgpu_mp3_frame_info* info) {
+    using namespace symgpu::mp3e;
+    if ((!data && n) || (n_packets && !packets) || !md_len || !n_good || (!md && md_cap)) return SYMGPU_ERR_ARG;
+    GcJob* jobs = reinterpret_cast<GcJob*>(jobs_out);
+    Spec spec;
+    size_t len = 0, consumed = 0;  // the reservoir, as byte counts only
+    size_t md_at = 0, good = 0;
+    for (size_t i = 0; i < n_packets; ++i) {
+        if (packets[i].offset > n || packets[i].size > n - packets[i].offset) return SYMGPU_ERR_ARG;
+        MpaHeader h{};
+        const uint8_t* buf = nullptr;
+        size_t buf_len = 0;
+        if (open_packet(spec, data + packets[i].offset, packets[i].size, h, buf, buf_len) != SYMGPU_OK) continue;
+        Frame f{};
+        Bits side(buf, buf_len);
+        const size_t side_len = h.side_info_len();
+        if (!read_side_info(side, h, f) || side_len > buf_len) {
+            len = consumed = 0;
+            continue;
+        }
+        const size_t slot = buf_len - side_len, begin = f.main_data_begin;
+        if (begin + slot > 2048) continue;  // refused before the reservoir is touched (mod.rs:49-51)
+        const size_t unread = len - consumed;
+        const size_t reuse = begin <= unread ? begin : unread;
+        const uint32_t underflow = uint32_t(begin - reuse);
+        if (bad && bad[i]) {  // known to fail while its main data is read: the reference then empties the reservoir (mod.rs:409-414)
+            len = consumed = 0;
+            continue;
+        }
+        if (md_at + slot > md_cap) return SYMGPU_ERR_LIMIT;
+        if (md) std::memcpy(md + md_at, buf + side_len, slot);
+        const uint64_t seg_begin = md_at - reuse;
+        const uint32_t seg_len = uint32_t(reuse + slot);
+        md_at += slot;
+        len = seg_len, consumed = 0;
+
+        const int n_ch = h.n_channels(), n_gr = h.n_granules();
+        const bool mpeg1 = h.version == MpaVersion::Mpeg1;
+        const bool intensity = h.mode == symgpu::packet::MpaMode::JointStereo && h.intensity;
+        const uint8_t frame_flags = uint8_t((mpeg1 ? SYMGPU_MP3_F_MPEG1 : 0) | (h.mode == symgpu::packet::MpaMode::JointStereo && h.mid_side ? SYMGPU_MP3_F_MID_SIDE : 0) |
+                                            (intensity ? SYMGPU_MP3_F_INTENSITY : 0));
+        const uint32_t underflow_bits = 8 * underflow;
+        uint32_t skipped = 0, gr0_begin[2] = {~0u, ~0u};
+        size_t part_begin = 0;
+        for (int gr = 0; gr < 2; ++gr) {
+            const bool silent = gr < n_gr && skipped < underflow_bits;
+            for (int ch = 0; ch < 2; ++ch) {
+                GcJob j{};
+                j.seg_begin = seg_begin, j.seg_len = seg_len, j.out_index = uint32_t(good * 4 + gr * 2 + ch);
+                j.unit_flags = frame_flags, j.sample_rate_idx = h.sample_rate_idx, j.mpeg1 = mpeg1, j.gr0_bit_begin = ~0u;
+                if (gr >= n_gr || ch >= n_ch) {
+                    j.kind = kJobMute;
+                } else {
+                    j.side = f.gc[gr][ch];
+                    j.intensity_channel = ch > 0 && intensity, j.scfsi = uint8_t(f.scfsi[ch]);
+                    if (silent) {
+                        j.kind = kJobSilent;
+                        skipped += f.gc[gr][ch].part2_3_length;
+                    } else {
+                        j.kind = kJobDecode;
+                        j.bit_begin = uint32_t(part_begin);
+                        if (gr == 0) gr0_begin[ch] = j.bit_begin;
+                        else {
+                            j.gr0_bit_begin = gr0_begin[ch];
+                            j.gr0_scalefac_compress = f.gc[0][ch].scalefac_compress, j.gr0_block_type = f.gc[0][ch].block_type, j.gr0_mixed = f.gc[0][ch].mixed;
+                        }
+                        part_begin += f.gc[gr][ch].part2_3_length;
+                    }
+                }
+                if (jobs) jobs[good * 4 + gr * 2 + ch] = j;
+            }
+            if (silent && skipped > underflow_bits) part_begin = skipped - underflow_bits;
+        }
+        consumed = std::min(len, (part_begin + 7) >> 3);
+        if (good == 0 && info) {
+            info->sample_rate = h.sample_rate, info->channels = uint8_t(n_ch), info->granules = uint8_t(n_gr);
+            info->sample_rate_idx = h.sample_rate_idx, info->version = uint8_t(h.version), info->underflow_bytes = underflow;
+            info->main_data_bytes = uint32_t((part_begin + 7) >> 3);
+        }
+        if (frame_of) frame_of[good] = uint32_t(i);
+        ++good;
+    }
+    *md_len = md_at, *n_good = good;
+    return SYMGPU_OK;
+}
+
+extern "C" symgpu_status symgpu_mp3_entropy_run_cpu(const uint8_t* md, size_t md_len, const symgpu_mp3_gc_job* jobs_in, size_t n_jobs,
+                                                    symgpu_mp3_gc* units, int16_t* quant, uint8_t* failed) {
+    using namespace symgpu::mp3e;
+    if ((n_jobs && (!jobs_in || !units || !quant)) || (!md && md_len)) return SYMGPU_ERR_ARG;
+    const GcJob* jobs = reinterpret_cast<const GcJob*>(jobs_in);
+    const HuffSet& hs = host_tables().set;
+    const uint32_t first = n_jobs ? jobs[0].out_index & ~3u : 0;
+    for (size_t k = 0; k < n_jobs; ++k) {
+        const GcJob& j = jobs[k];
+        if (j.out_index < first || j.seg_begin > md_len || j.seg_len > md_len - j.seg_begin) return SYMGPU_ERR_ARG;
+        const uint32_t slot = j.out_index - first;
+        if (decode_gc_job(j, md, hs, units + slot, quant + size_t(slot) * 576) && failed) failed[slot >> 2] = 1;
+    }
+    return SYMGPU_OK;
+}
+
+extern "C" symgpu_status symgpu_mp3_entropy_decode_cpu(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets,
+                                                       symgpu_mp3_gc* units, int16_t* quant, uint32_t* frame_of, size_t* n_good,
+                                                       symgpu_mp3_frame_info* info, uint32_t* n_rounds) {
+    if ((!data && n) || !n_good || (n_packets && (!packets || !units || !quant || !frame_of))) return SYMGPU_ERR_ARG;
+    size_t total = 0;
+    for (size_t i = 0; i < n_packets; ++i) total += packets[i].size;
+    std::vector<uint8_t> md(total + 8), bad(n_packets, 0), failed;
+    std::vector<symgpu_mp3_gc_job> jobs(n_packets * 4);
+    uint32_t rounds = 0;
+    for (;;) {
+        ++rounds;
+        size_t md_len = 0, good = 0;
+        const symgpu_status s = symgpu_mp3_entropy_plan(data, n, packets, n_packets, bad.data(), md.data(), md.size(), &md_len, jobs.data(), frame_of, &good, info);
+        if (s != SYMGPU_OK) return s;
+        failed.assign(good, 0);
+        const symgpu_status r = symgpu_mp3_entropy_run_cpu(md.data(), md_len, jobs.data(), good * 4, units, quant, failed.data());
+        if (r != SYMGPU_OK) return r;
+        // only the FIRST failure is certain: frames behind it were planned with a reservoir the reference would have emptied
+        size_t first_bad = good;
+        for (size_t f = 0; f < good; ++f)
+            if (failed[f]) {
+                first_bad = f;
+                break;
+            }
+        if (first_bad == good) {
+            *n_good = good;
+            break;
+        }
+        bad[frame_of[first_bad]] = 1;
+    }
+    if (n_rounds) *n_rounds = rounds;
     return SYMGPU_OK;
 }

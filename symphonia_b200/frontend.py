@@ -62,3 +62,61 @@ class Mp3Frontend:
             raise SymgpuError(rc, "symgpu_mp3_fe_decode_packets")
         g = good.value
         return units[:g], quant[:g], frame_of[:g], info[0]
+
+
+def _u8(data):
+    return np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+
+
+def entropy_plan(data, packets, bad=None):
+    """The side-information pass: (md bytes, jobs [n_good*4] of 64 opaque bytes, frame_of, info).  No Huffman data is read."""
+    L = nat.lib()
+    a = _u8(data)
+    packets = np.ascontiguousarray(packets, dtype=nat.MPA_PACKET_DTYPE)
+    n = len(packets)
+    md = np.zeros(int(packets["size"].sum()) + 8, dtype=np.uint8)
+    jobs = np.zeros((n * 4, 8), dtype=np.uint64)
+    frame_of = np.zeros(n, dtype=np.uint32)
+    info = np.zeros(1, dtype=nat.MP3_FRAME_INFO_DTYPE)
+    md_len, good = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    badp = None if bad is None else _vp(np.ascontiguousarray(bad, dtype=np.uint8).ctypes.data)
+    rc = L.symgpu_mp3_entropy_plan(_vp(a.ctypes.data), a.size, _vp(packets.ctypes.data), n, badp, _vp(md.ctypes.data), md.size, ctypes.byref(md_len),
+                                   _vp(jobs.ctypes.data), _vp(frame_of.ctypes.data), ctypes.byref(good), _vp(info.ctypes.data))
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_mp3_entropy_plan")
+    return md[:md_len.value], jobs[:good.value * 4], frame_of[:good.value], info[0]
+
+
+def entropy_run_cpu(md, jobs):
+    """The kernel body on the host: (units[F][2][2], quant[F][2][2][576], failed[F])."""
+    L = nat.lib()
+    md = np.ascontiguousarray(md, dtype=np.uint8)
+    jobs = np.ascontiguousarray(jobs, dtype=np.uint64)
+    n_frames = (len(jobs) + 3) // 4  # slots are relative to the first job's frame
+    units = np.zeros((n_frames, 2, 2), dtype=nat.MP3_GC_DTYPE)
+    quant = np.zeros((n_frames, 2, 2, 576), dtype=np.int16)
+    failed = np.zeros(n_frames, dtype=np.uint8)
+    rc = L.symgpu_mp3_entropy_run_cpu(_vp(md.ctypes.data) if md.size else None, md.size, _vp(jobs.ctypes.data), len(jobs), _vp(units.ctypes.data),
+                                      _vp(quant.ctypes.data), _vp(failed.ctypes.data))
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_mp3_entropy_run_cpu")
+    return units, quant, failed
+
+
+def entropy_decode_cpu(data, packets):
+    """plan -> jobs -> re-plan until nothing fails: (units, quant, frame_of, info, rounds), equal to Mp3Frontend.decode_packets on a fresh stream."""
+    L = nat.lib()
+    a = _u8(data)
+    packets = np.ascontiguousarray(packets, dtype=nat.MPA_PACKET_DTYPE)
+    n = len(packets)
+    units = np.zeros((n, 2, 2), dtype=nat.MP3_GC_DTYPE)
+    quant = np.zeros((n, 2, 2, 576), dtype=np.int16)
+    frame_of = np.zeros(n, dtype=np.uint32)
+    info = np.zeros(1, dtype=nat.MP3_FRAME_INFO_DTYPE)
+    good, rounds = ctypes.c_size_t(0), ctypes.c_uint32(0)
+    rc = L.symgpu_mp3_entropy_decode_cpu(_vp(a.ctypes.data), a.size, _vp(packets.ctypes.data), n, _vp(units.ctypes.data), _vp(quant.ctypes.data),
+                                         _vp(frame_of.ctypes.data), ctypes.byref(good), _vp(info.ctypes.data), ctypes.byref(rounds))
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_mp3_entropy_decode_cpu")
+    g = good.value
+    return units[:g], quant[:g], frame_of[:g], info[0], rounds.value

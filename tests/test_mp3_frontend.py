@@ -313,3 +313,74 @@ def test_file_to_batch_through_packetiser_and_front_end():
     rc = nat.lib().symgpu_mp3_units_check(units.ctypes.data, runs.ctypes.data, 1, len(frame_of))
     assert rc in (0, 1)  # 1: a joint-stereo pair with unequal block types, which stereo.rs:503-505 refuses as well
     assert po.mpa_index(data)[1][0][0] == int(packets[0]["offset"])
+
+
+# ------------------------------------------------------------------------------------------- plan + independent jobs
+
+def _packets_of(frames):
+    """A packet table over the concatenated frames (what the packetiser would return for a clean file)."""
+    p = np.zeros(len(frames), dtype=nat.MPA_PACKET_DTYPE)
+    at = 0
+    for k, f in enumerate(frames):
+        p[k]["offset"], p[k]["size"] = at, len(f)
+        at += len(f)
+    return b"".join(frames), p
+
+
+def _same_as_serial(frames, where):
+    data, packets = _packets_of(frames)
+    su, sq, sf, sinfo = frontend.Mp3Frontend().decode_packets(data, packets)
+    pu, pq, pf, pinfo, rounds = frontend.entropy_decode_cpu(data, packets)
+    assert pf.tolist() == sf.tolist(), where
+    assert pu.tobytes() == su.tobytes() and (pq == sq).all(), where
+    if len(sf):
+        assert pinfo.tobytes() == sinfo.tobytes(), where
+    return rounds, len(sf)
+
+
+def test_planned_jobs_equal_the_serial_front_end():
+    rng = np.random.default_rng(31)
+    for version, mode, br, prot in (("1", 1, 9, False), ("1", 3, 5, True), ("1", 0, 14, False), ("2", 1, 8, False), ("2", 3, 3, False),
+                                    ("2.5", 1, 6, True), ("2.5", 3, 1, False)):
+        frames, truth = bw.gen_stream(rng, 80, version=version, mode=mode, bitrate_idx=br, protected=prot)
+        rounds, good = _same_as_serial(frames, f"{version}/{mode}")
+        assert (rounds, good) == (1, 80)
+        _same_as_serial(frames[7:], "joined late")            # underflow: silent granules, partial first granule
+        _same_as_serial(frames[:30] + frames[31:], "a frame lost")
+    # the jobs really are independent: run them in a shuffled order, one at a time
+    frames, _ = bw.gen_stream(rng, 40, version="1", mode=1, bitrate_idx=9)
+    data, packets = _packets_of(frames)
+    md, jobs, frame_of, _ = frontend.entropy_plan(data, packets)
+    assert len(jobs) == 160 and md.size == sum(len(f) - 4 - 32 for f in frames)   # main data only: headers and side info stay behind
+    want_u, want_q, failed = frontend.entropy_run_cpu(md, jobs)
+    assert not failed.any()
+    got_u, got_q = np.zeros_like(want_u), np.zeros_like(want_q)
+    for k in rng.permutation(len(jobs)):
+        frame = k // 4
+        u, q, f = frontend.entropy_run_cpu(md, jobs[frame * 4:frame * 4 + 4][[k % 4]])  # a single job; its slot is relative to its own frame
+        got_u[frame].reshape(-1)[k % 4] = u[0].reshape(-1)[k % 4]
+        got_q[frame].reshape(4, 576)[k % 4] = q[0].reshape(4, 576)[k % 4]
+    assert got_u.tobytes() == want_u.tobytes() and (got_q == want_q).all()
+
+
+def test_planned_jobs_on_damaged_streams():
+    rng = np.random.default_rng(32)
+    replanned = 0
+    for version, mode, br in (("1", 1, 9), ("2", 1, 8), ("1", 3, 6), ("2.5", 3, 5)):
+        frames, _ = bw.gen_stream(rng, 120, version=version, mode=mode, bitrate_idx=br)
+        hit = []
+        for f in frames:
+            b = bytearray(f)
+            kind = int(rng.integers(8))
+            if kind == 0:
+                b[4 + int(rng.integers(1, 9))] |= int(rng.choice([0xFF, 0xF0, 0x3F]))   # side information forced high
+            elif kind == 1:
+                b[4 + int(rng.integers(0, 9))] ^= 1 << int(rng.integers(8))
+            elif kind == 2:
+                for _ in range(3):
+                    b[int(rng.integers(40, len(b)))] ^= 1 << int(rng.integers(8))
+            hit.append(bytes(b))
+        rounds, good = _same_as_serial(hit, f"damaged {version}")
+        replanned += rounds > 1
+        assert 60 < good <= 120
+    assert replanned >= 2  # decode-time failures occurred and the re-plan reproduced the emptied reservoir
