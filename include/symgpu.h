@@ -539,7 +539,8 @@ symgpu_status symgpu_mp3_fe_decode_packets(symgpu_mp3_fe* fe, const uint8_t* dat
  * layer3/mod.rs:345-358) makes the reference drop the frame AND empty the reservoir, which changes the plan of the frames
  * behind it: pass the failed packets back in `bad` and plan again (symgpu_mp3_entropy_decode_cpu does this loop). */
 typedef struct symgpu_mp3_gc_job { uint64_t opaque[8]; } symgpu_mp3_gc_job;
-/* bad: n_packets flags (1 = known to fail at decode time) or NULL.  md_cap >= the packets' total size is always enough.
+/* bad: n_packets flags or NULL: 1 = known to fail while its main data is read (reservoir emptied, as the reference does);
+ * 2 = to be left out although its main data is consumed normally (a frame the synthesis stage refuses).  md_cap >= the packets' total size is always enough.
  * frame_of[k] = packet index of good frame k; jobs / frame_of may be NULL to count only.  *md_len, *n_good: results. */
 symgpu_status symgpu_mp3_entropy_plan(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets,
                                       const uint8_t* bad, uint8_t* md, size_t md_cap, size_t* md_len, symgpu_mp3_gc_job* jobs,
@@ -553,6 +554,28 @@ symgpu_status symgpu_mp3_entropy_run_cpu(const uint8_t* md, size_t md_len, const
 symgpu_status symgpu_mp3_entropy_decode_cpu(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets,
                                             symgpu_mp3_gc* units, int16_t* quant, uint32_t* frame_of, size_t* n_good,
                                             symgpu_mp3_frame_info* info, uint32_t* n_rounds);
+
+/* ---- the device path of the front-end.  EXPERIMENTAL in this revision: compiled for sm_100a, not yet run on a GPU
+ * (tests/test_mp3_entropy_gpu.py is opt-in, SYMGPU_TEST_ENTROPY=1). ------------------------------------------------ */
+/* One thread per job, the same decode functions as symgpu_mp3_entropy_run_cpu.  All pointers are device memory;
+ * d_failed[n_jobs / 4] must be zeroed by the caller; asynchronous on the context stream. */
+symgpu_status symgpu_mp3_entropy_dev(symgpu_ctx* ctx, const uint8_t* d_md, size_t md_len, const symgpu_mp3_gc_job* d_jobs, size_t n_jobs,
+                                     symgpu_mp3_gc* d_units, int16_t* d_quant, uint32_t* d_failed);
+typedef struct symgpu_mp3_file {        /* one stream's bytes and packet table (symgpu_mpa_index), all host memory          */
+    const uint8_t* data;
+    size_t n;
+    const symgpu_mpa_packet* packets;
+    size_t n_packets;
+    uint32_t stream;                    /* synthesis state slot (symgpu_mp3_streams_alloc)                                  */
+    uint32_t reserved;
+} symgpu_mp3_file;
+/* File bytes -> planar f32 PCM with nothing but the side-information pass on the CPU: plan, upload main data + jobs,
+ * entropy kernel, POW43 lookup, synthesis kernel, PCM back.  pcm [sum of good frames][2][1152] (pcm_frames_cap >= total
+ * packets is always enough); good_per_file[f] frames of file f, in order; frame_of = their packet indices, concatenated.
+ * Frames the reference refuses are left out as symgpu_mp3_fe_decode_packets leaves them out; additionally a joint-stereo
+ * frame whose channels disagree on the window sequence (refused by the reference's stereo stage) is left out whole. */
+symgpu_status symgpu_mp3_decode_files_host(symgpu_ctx* ctx, const symgpu_mp3_file* files, uint32_t n_files, float* pcm, size_t pcm_frames_cap,
+                                           uint32_t* good_per_file, uint32_t* frame_of, uint32_t* n_rounds);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,8 @@ assert MPA_TRACK_DTYPE.itemsize == 48 and MPA_PACKET_DTYPE.itemsize == 48 and AD
 MP3_FRAME_INFO_DTYPE = np.dtype([("sample_rate", "<u4"), ("channels", "u1"), ("granules", "u1"), ("sample_rate_idx", "u1"), ("version", "u1"),
                                  ("underflow_bytes", "<u4"), ("main_data_bytes", "<u4")])
 assert MP3_FRAME_INFO_DTYPE.itemsize == 16
+MP3_FILE_DTYPE = np.dtype([("data", "<u8"), ("n", "<u8"), ("packets", "<u8"), ("n_packets", "<u8"), ("stream", "<u4"), ("reserved", "<u4")])
+assert MP3_FILE_DTYPE.itemsize == 40
 assert PIECE_DTYPE.itemsize == 16 and OGG_PACKET_DTYPE.itemsize == 40 and VORBIS_IDENT_DTYPE.itemsize == 8
 AAC_ONLY_LONG, AAC_LONG_START, AAC_EIGHT_SHORT, AAC_LONG_STOP = 0, 1, 2, 3
 
@@ -202,6 +204,10 @@ def lib():
     L.symgpu_mp3_entropy_run_cpu.argtypes = [vp, sz, vp, sz, vp, vp, vp]
     L.symgpu_mp3_entropy_decode_cpu.restype = ctypes.c_int
     L.symgpu_mp3_entropy_decode_cpu.argtypes = [vp, sz, vp, sz, vp, vp, vp, psz, vp, ctypes.POINTER(u32)]
+    L.symgpu_mp3_entropy_dev.restype = ctypes.c_int
+    L.symgpu_mp3_entropy_dev.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
+    L.symgpu_mp3_decode_files_host.restype = ctypes.c_int
+    L.symgpu_mp3_decode_files_host.argtypes = [vp, vp, u32, vp, sz, vp, vp, ctypes.POINTER(u32)]
     _LIB = L
     return L
 

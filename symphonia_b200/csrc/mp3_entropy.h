@@ -15,9 +15,12 @@
 
 #ifdef __CUDACC__
 #define SYMGPU_HD __host__ __device__ __forceinline__
-#define SYMGPU_UNROLL _Pragma("unroll")
 #else
 #define SYMGPU_HD inline
+#endif
+#ifdef __CUDA_ARCH__
+#define SYMGPU_UNROLL _Pragma("unroll")
+#else
 #define SYMGPU_UNROLL
 #endif
 

@@ -362,10 +362,11 @@ extern "C" symgpu_status symgpu_mp3_entropy_plan(const uint8_t* data, size_t n, 
         const size_t unread = len - consumed;
         const size_t reuse = begin <= unread ? begin : unread;
         const uint32_t underflow = uint32_t(begin - reuse);
-        if (bad && bad[i]) {  // known to fail while its main data is read: the reference then empties the reservoir (mod.rs:409-414)
+        if (bad && bad[i] == 1) {  // known to fail while its main data is read: the reference then empties the reservoir (mod.rs:409-414)
             len = consumed = 0;
             continue;
         }
+        const bool leave_out = bad && bad[i] == 2;  // refused AFTER its main data was read (stereo.rs:503-505): the reservoir moves on, no audio
         if (md_at + slot > md_cap) return SYMGPU_ERR_LIMIT;
         if (md) std::memcpy(md + md_at, buf + side_len, slot);
         const uint64_t seg_begin = md_at - reuse;
@@ -406,11 +407,12 @@ extern "C" symgpu_status symgpu_mp3_entropy_plan(const uint8_t* data, size_t n, 
                         part_begin += f.gc[gr][ch].part2_3_length;
                     }
                 }
-                if (jobs) jobs[good * 4 + gr * 2 + ch] = j;
+                if (jobs && !leave_out) jobs[good * 4 + gr * 2 + ch] = j;
             }
             if (silent && skipped > underflow_bits) part_begin = skipped - underflow_bits;
         }
         consumed = std::min(len, (part_begin + 7) >> 3);
+        if (leave_out) continue;
         if (good == 0 && info) {
             info->sample_rate = h.sample_rate, info->channels = uint8_t(n_ch), info->granules = uint8_t(n_gr);
             info->sample_rate_idx = h.sample_rate_idx, info->version = uint8_t(h.version), info->underflow_bytes = underflow;

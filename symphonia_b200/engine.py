@@ -139,6 +139,26 @@ class Engine:
                                                               _np_ptr(out)))
         return out
 
+    def mp3_decode_files_host(self, files):
+        """EXPERIMENTAL device front-end: files = [(bytes, packets (MPA_PACKET_DTYPE), stream slot)] -> (pcm [F,2,1152],
+        good_per_file, frame_of, rounds); only the side-information pass runs on the CPU."""
+        from ._native import MP3_FILE_DTYPE, MPA_PACKET_DTYPE
+        keep, recs = [], np.zeros(len(files), dtype=MP3_FILE_DTYPE)
+        for k, (data, packets, stream) in enumerate(files):
+            a = np.frombuffer(data, dtype=np.uint8)
+            p = np.ascontiguousarray(packets, dtype=MPA_PACKET_DTYPE)
+            keep += [a, p]
+            recs[k] = (a.ctypes.data, a.size, p.ctypes.data, len(p), stream, 0)
+        total = int(recs["n_packets"].sum())
+        pcm = np.zeros((total, 2, 1152), dtype=np.float32)
+        good = np.zeros(len(files), dtype=np.uint32)
+        frame_of = np.zeros(max(total, 1), dtype=np.uint32)
+        rounds = ctypes.c_uint32(0)
+        self._check(self._lib.symgpu_mp3_decode_files_host(self._ctx, _np_ptr(recs), len(files), _np_ptr(pcm), total, _np_ptr(good), _np_ptr(frame_of),
+                                                           ctypes.byref(rounds)))
+        n = int(good.sum())
+        return pcm[:n], good, frame_of[:n], rounds.value
+
     # -- MPEG Layer I / II ---------------------------------------------------------------------
     def mpa12_synth_host(self, subbands, runs, out=None):
         """subbands [F,2,32,n_slots] f32 (n_slots 12: Layer I, 36: Layer II), runs MPA12_RUN_DTYPE -> pcm [F,2,1152]
