@@ -816,12 +816,13 @@ inline Status vorbis_read_ident(const uint8_t* p, size_t n, VorbisIdent& id) {
 namespace detail {
 // The largest v with v^dims <= entries (the reference computes it in f32 and asserts exactly this, :717-730).
 inline uint32_t vorbis_lookup1_values(uint32_t entries, uint32_t dims) {
+    if (dims == 1) return entries;  // (untrusted input: keep the search short -- for dims >= 2 the root of 2^24 is <= 4096)
     uint32_t v = 0;
     for (;;) {
         uint64_t pw = 1;
         bool over = false;
         for (uint32_t k = 0; k < dims && !over; ++k) pw *= uint64_t(v) + 1, over = pw > entries;
-        if (over || pw > entries) return v;
+        if (over) return v;
         ++v;
     }
 }
