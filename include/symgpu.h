@@ -577,6 +577,24 @@ typedef struct symgpu_mp3_file {        /* one stream's bytes and packet table (
 symgpu_status symgpu_mp3_decode_files_host(symgpu_ctx* ctx, const symgpu_mp3_file* files, uint32_t n_files, float* pcm, size_t pcm_frames_cap,
                                            uint32_t* good_per_file, uint32_t* frame_of, uint32_t* n_rounds);
 
+/* ===================================================================================================
+ * MPEG Layer I / II sample decoders (SURVEY 8f N1 for the Layer I / II path): a packet becomes the sub-band samples
+ * symgpu_mpa12_synth_* take.  CPU only, stateless apart from the stream's signal specification.
+ *   Layer1::decode up to the synthesis call   symphonia-bundle-mp3/src/layer1/mod.rs:19-176
+ *   Layer2::decode up to the synthesis call   layer2/mod.rs:45-369; scale factors layer12.rs:9-75
+ * ================================================================================================= */
+/* One packet.  subbands [2][32][n_slots] f32 (n_slots = 12 Layer I, 36 Layer II: samples[ch][n_slots * sb + s]), fully
+ * written (zeros where nothing is allocated and in the absent channel of a mono frame).  `layer` = the stream's layer
+ * (1 or 2): a packet of another layer is refused as the reference's decoder refuses it (decoder.rs:113-128). */
+symgpu_status symgpu_mpa12_fe_decode(const uint8_t* frame, size_t n, int layer, float* subbands, symgpu_mp3_frame_info* info);
+/* A stream's packets: good frames densely in `subbands` ([n_good][2][32][n_slots]), frame_of[k] = packet index.  The signal
+ * specification is fixed by the first packet (decoder.rs:96-108). */
+symgpu_status symgpu_mpa12_fe_decode_packets(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets, int layer,
+                                             float* subbands, uint32_t* frame_of, size_t* n_good, symgpu_mp3_frame_info* info);
+/* The decoders' constants (for tests): 64 scale factors, then C and D of the 17 quantisation classes in the order of
+ * ISO 11172-3 Table 3-B.4 (3, 5, 7, 9, 15, ... 65535 levels).  Returns 98 = the number of floats. */
+size_t symgpu_mpa12_constants(float* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

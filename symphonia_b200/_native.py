@@ -208,6 +208,12 @@ def lib():
     L.symgpu_mp3_entropy_dev.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
     L.symgpu_mp3_decode_files_host.restype = ctypes.c_int
     L.symgpu_mp3_decode_files_host.argtypes = [vp, vp, u32, vp, sz, vp, vp, ctypes.POINTER(u32)]
+    L.symgpu_mpa12_fe_decode.restype = ctypes.c_int
+    L.symgpu_mpa12_fe_decode.argtypes = [vp, sz, ctypes.c_int, vp, vp]
+    L.symgpu_mpa12_fe_decode_packets.restype = ctypes.c_int
+    L.symgpu_mpa12_fe_decode_packets.argtypes = [vp, sz, vp, sz, ctypes.c_int, vp, vp, psz, vp]
+    L.symgpu_mpa12_constants.restype = sz
+    L.symgpu_mpa12_constants.argtypes = [vp, sz]
     _LIB = L
     return L
 

@@ -120,3 +120,37 @@ def entropy_decode_cpu(data, packets):
         raise SymgpuError(rc, "symgpu_mp3_entropy_decode_cpu")
     g = good.value
     return units[:g], quant[:g], frame_of[:g], info[0], rounds.value
+
+
+def mpa12_decode(frame, layer):
+    """One Layer I / II packet -> (subbands [2][32][n_slots] f32, info); SymgpuError where the reference errors."""
+    a = _u8(bytes(frame))
+    n_slots = 12 if layer == 1 else 36
+    out = np.zeros((2, 32, n_slots), dtype=np.float32)
+    info = np.zeros(1, dtype=nat.MP3_FRAME_INFO_DTYPE)
+    rc = nat.lib().symgpu_mpa12_fe_decode(_vp(a.ctypes.data) if a.size else None, a.size, layer, _vp(out.ctypes.data), _vp(info.ctypes.data))
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_mpa12_fe_decode")
+    return out, info[0]
+
+
+def mpa12_decode_packets(data, packets, layer):
+    """A Layer I / II stream -> (subbands [n_good][2][32][n_slots], frame_of, info): the input of Engine.mpa12_synth_host."""
+    a = _u8(data)
+    packets = np.ascontiguousarray(packets, dtype=nat.MPA_PACKET_DTYPE)
+    n, n_slots = len(packets), 12 if layer == 1 else 36
+    out = np.zeros((n, 2, 32, n_slots), dtype=np.float32)
+    frame_of = np.zeros(n, dtype=np.uint32)
+    info = np.zeros(1, dtype=nat.MP3_FRAME_INFO_DTYPE)
+    good = ctypes.c_size_t(0)
+    rc = nat.lib().symgpu_mpa12_fe_decode_packets(_vp(a.ctypes.data), a.size, _vp(packets.ctypes.data), n, layer, _vp(out.ctypes.data), _vp(frame_of.ctypes.data),
+                                                  ctypes.byref(good), _vp(info.ctypes.data))
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_mpa12_fe_decode_packets")
+    return out[:good.value], frame_of[:good.value], info[0]
+
+
+def mpa12_constants():
+    out = np.zeros(98, dtype=np.float32)
+    nat.lib().symgpu_mpa12_constants(_vp(out.ctypes.data), 98)
+    return out[:64], out[64:81], out[81:]

@@ -74,3 +74,50 @@ def test_file_bytes_to_pcm_on_the_device(oracle):
         assert eng.launch_count >= 2  # dequantise + synthesis
     same = got.view(np.uint32) == want.view(np.uint32)
     assert same.all(), f"{int((~same).sum())} PCM words differ, first at {np.argwhere(~same)[0]}"
+
+
+# ------------------------------------------------------------------------------------------- Layer I / II files
+
+def _mpa12_corpus():
+    from tests import _mpa12_bitstream as b12
+    rng = np.random.default_rng(78)
+    l2 = [b12.gen_layer2_frame(rng, "1", 12, 0, 1, mode_ext=k % 4)[0] for k in range(20)]   # 256 kbit/s joint stereo, table b
+    l2m = [b12.gen_layer2_frame(rng, "2", 6, 1, 3)[0] for _ in range(16)]                    # MPEG-2 mono
+    l1 = [b12.gen_layer1_frame(rng, "1", 9, 1, 0)[0] for _ in range(24)]
+    noise = rng.integers(0, 255, 90, dtype=np.uint8).tobytes()
+    return [(2, noise + b"".join(l2)), (2, b"".join(l2m)), (1, b"".join(l1[:10]) + noise + b"".join(l1[10:]))]
+
+
+def _mpa12_batches():
+    out = []
+    for layer, data in _mpa12_corpus():
+        track, packets = packetizer.mpa_index(data)
+        assert int(track["layer"]) == layer
+        sub, frame_of, info = frontend.mpa12_decode_packets(data, packets, layer)
+        assert len(frame_of) == len(packets) > 0
+        runs = np.zeros(1, dtype=nat.MPA12_RUN_DTYPE)
+        runs[0] = (0, 0, len(sub), int(info["channels"]), (0, 0, 0))
+        out.append((layer, sub, runs))
+    return out
+
+
+def test_layer12_chain_up_to_the_launch(oracle):
+    for layer, sub, runs in _mpa12_batches():
+        rc, pcm, _ = _oracle.mpa12_batch(oracle, sub, runs, 1)
+        assert rc == 0 and np.isfinite(pcm).all() and np.abs(pcm).max() > 0.01
+        assert not pcm[:, :, 32 * sub.shape[-1]:].any()  # a Layer I frame fills 384 of the 1152 samples of its slot
+
+
+@pytest.mark.gpu
+def test_layer12_file_bytes_to_pcm_on_the_device(oracle):
+    import symphonia_b200 as sb
+    with sb.Engine(0) as eng:
+        for layer, sub, runs in _mpa12_batches():
+            rc, want, _ = _oracle.mpa12_batch(oracle, sub, runs, 1)
+            assert rc == 0
+            eng.mp3_streams_alloc(1)
+            got = eng.mpa12_synth_host(sub, runs)
+            n = 32 * sub.shape[-1]
+            ch = int(runs[0]["channels"])
+            same = got[:, :ch, :n].view(np.uint32) == want[:, :ch, :n].view(np.uint32)
+            assert same.all(), (layer, int((~same).sum()))
