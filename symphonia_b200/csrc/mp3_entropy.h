@@ -54,8 +54,8 @@ struct Bits {
     SYMGPU_HD Bits(const uint8_t* data, size_t n_bytes, size_t start_bit = 0) : p(data), n_bits(n_bytes * 8), at(start_bit) {}
     SYMGPU_HD uint32_t window() const {  // the next 32 bits, left-aligned
         const size_t byte = at >> 3, n = n_bits >> 3;
-#ifndef __CUDA_ARCH__
-        if (byte + 8 <= n) {  // host fast path: one unaligned load
+#if !defined(__CUDA_ARCH__) && !defined(SYMGPU_MP3E_DEVICE_WINDOW)
+        if (byte + 8 <= n) {  // host fast path: one unaligned load (SYMGPU_MP3E_DEVICE_WINDOW: build the host code with the device's path, for tests)
             uint64_t w;
             __builtin_memcpy(&w, p + byte, 8);
             return uint32_t((__builtin_bswap64(w) << (at & 7)) >> 32);

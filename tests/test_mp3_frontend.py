@@ -384,3 +384,36 @@ def test_planned_jobs_on_damaged_streams():
         replanned += rounds > 1
         assert 60 < good <= 120
     assert replanned >= 2  # decode-time failures occurred and the re-plan reproduced the emptied reservoir
+
+
+def test_the_device_bit_window_on_the_host(tmp_path):
+    """The kernel composes its 32-bit window from five byte loads; the host normally takes one 8-byte load instead.  Build the
+    front-end once more with the device's path forced (SYMGPU_MP3E_DEVICE_WINDOW) and require identical output: every
+    arithmetic step the device thread performs has then run on the CPU."""
+    import ctypes
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libfe_devwin.so")
+    csrc = os.path.join(root, "symphonia_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-DSYMGPU_MP3E_DEVICE_WINDOW", "-I/usr/local/cuda/include",
+                           "-o", so, os.path.join(csrc, "mp3_frontend.cpp"), os.path.join(csrc, "packetizer.cpp"), os.path.join(csrc, "tables.cpp")])
+    L = ctypes.CDLL(so)
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    L.symgpu_mp3_entropy_decode_cpu.restype = ctypes.c_int
+    L.symgpu_mp3_entropy_decode_cpu.argtypes = [vp, sz, vp, sz, vp, vp, vp, ctypes.POINTER(sz), vp, ctypes.POINTER(ctypes.c_uint32)]
+    rng = np.random.default_rng(41)
+    for version, mode, br in (("1", 1, 9), ("2", 3, 4), ("2.5", 0, 8), ("1", 0, 14)):
+        frames, _ = bw.gen_stream(rng, 60, version=version, mode=mode, bitrate_idx=br)
+        hit = [bytes(bytearray(f[:9]) + bytearray([f[9] ^ 0x10]) + bytearray(f[10:])) if k % 9 == 4 else f for k, f in enumerate(frames)]
+        data, packets = _packets_of(hit)
+        want_u, want_q, want_f, _, _ = frontend.entropy_decode_cpu(data, packets)
+        a = np.frombuffer(data, dtype=np.uint8)
+        n = len(packets)
+        units, quant = np.zeros((n, 2, 2), dtype=nat.MP3_GC_DTYPE), np.zeros((n, 2, 2, 576), dtype=np.int16)
+        frame_of, info = np.zeros(n, dtype=np.uint32), np.zeros(1, dtype=nat.MP3_FRAME_INFO_DTYPE)
+        good, rounds = sz(0), ctypes.c_uint32(0)
+        assert L.symgpu_mp3_entropy_decode_cpu(a.ctypes.data, a.size, packets.ctypes.data, n, units.ctypes.data, quant.ctypes.data, frame_of.ctypes.data,
+                                               ctypes.byref(good), info.ctypes.data, ctypes.byref(rounds)) == 0
+        g = good.value
+        assert frame_of[:g].tolist() == want_f.tolist() and units[:g].tobytes() == want_u.tobytes() and (quant[:g] == want_q).all()
