@@ -595,6 +595,34 @@ symgpu_status symgpu_mpa12_fe_decode_packets(const uint8_t* data, size_t n, cons
  * ISO 11172-3 Table 3-B.4 (3, 5, 7, 9, 15, ... 65535 levels).  Returns 98 = the number of floats. */
 size_t symgpu_mpa12_constants(float* out, size_t cap);
 
+/* ===================================================================================================
+ * FLAC front-end (SURVEY 8f N1 for the FLAC row): a packet (one frame) becomes the descriptors and the residual /
+ * warm-up / verbatim samples symgpu_flac_restore_* take.  CPU only, stateless.
+ *   sync_frame, read_frame_header (CRC-8, UTF-8 coded sequence number)   symphonia-bundle-flac/src/frame.rs:66-233, :281-333
+ *   FlacDecoder::decode_inner up to the restoration                       decoder.rs:139-228
+ *   read_subframe, decode_constant / _verbatim / _fixed_linear / _linear  decoder.rs:340-520
+ *   decode_residual, decode_rice_partition, rice_signed_to_i32            decoder.rs:522-640
+ * ================================================================================================= */
+typedef struct symgpu_flac_frame_info {  /* 24 bytes */
+    uint64_t sequence;        /* frame number (fixed block size streams) or first sample number (variable)              */
+    uint32_t block_size;
+    uint32_t sample_rate;     /* 0: not in the frame header, take it from the stream information                        */
+    uint8_t by_sample;        /* sequence counts samples                                                                */
+    uint8_t reserved[7];
+} symgpu_flac_frame_info;
+/* A stream's packets: packet i = data[packets[i].offset .. + len).  For every packet the reference decodes, in order:
+ *   frames[k], infos[k], frame_of[k] = i; its sub-frames appended to `subs` (frames[k].first_subframe), each sub-frame's n
+ *   samples appended to `samples` (subs[].offset) -- residuals behind the warm-up samples, a constant in the first slot, or
+ *   the verbatim samples, exactly the input of symgpu_flac_restore_*.
+ * stream_bps / stream_channels / max_block: from the stream information block (0 = unknown; a frame that relies on a
+ * missing value, has more channels than the stream or a larger block is refused as the reference refuses it).
+ * SYMGPU_ERR_LIMIT if subs_cap / samples_cap are too small (a refused packet's partial output is discarded). */
+symgpu_status symgpu_flac_fe_decode_packets(const uint8_t* data, size_t n, const symgpu_piece* packets, size_t n_packets,
+                                            uint32_t stream_bps, uint32_t stream_channels, uint32_t max_block,
+                                            symgpu_flac_frame* frames, symgpu_flac_frame_info* infos, uint32_t* frame_of,
+                                            symgpu_flac_subframe* subs, size_t subs_cap, int32_t* samples, size_t samples_cap,
+                                            size_t* n_good, size_t* n_subs, size_t* n_samples);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ assert MPA_TRACK_DTYPE.itemsize == 48 and MPA_PACKET_DTYPE.itemsize == 48 and AD
 MP3_FRAME_INFO_DTYPE = np.dtype([("sample_rate", "<u4"), ("channels", "u1"), ("granules", "u1"), ("sample_rate_idx", "u1"), ("version", "u1"),
                                  ("underflow_bytes", "<u4"), ("main_data_bytes", "<u4")])
 assert MP3_FRAME_INFO_DTYPE.itemsize == 16
+FLAC_FRAME_INFO_DTYPE = np.dtype([("sequence", "<u8"), ("block_size", "<u4"), ("sample_rate", "<u4"), ("by_sample", "u1"), ("reserved", "u1", (7,))])
+assert FLAC_FRAME_INFO_DTYPE.itemsize == 24
 MP3_FILE_DTYPE = np.dtype([("data", "<u8"), ("n", "<u8"), ("packets", "<u8"), ("n_packets", "<u8"), ("stream", "<u4"), ("reserved", "<u4")])
 assert MP3_FILE_DTYPE.itemsize == 40
 assert PIECE_DTYPE.itemsize == 16 and OGG_PACKET_DTYPE.itemsize == 40 and VORBIS_IDENT_DTYPE.itemsize == 8
@@ -214,6 +216,8 @@ def lib():
     L.symgpu_mpa12_fe_decode_packets.argtypes = [vp, sz, vp, sz, ctypes.c_int, vp, vp, psz, vp]
     L.symgpu_mpa12_constants.restype = sz
     L.symgpu_mpa12_constants.argtypes = [vp, sz]
+    L.symgpu_flac_fe_decode_packets.restype = ctypes.c_int
+    L.symgpu_flac_fe_decode_packets.argtypes = [vp, sz, vp, sz, u32, u32, u32, vp, vp, vp, vp, sz, vp, sz, psz, psz, psz]
     _LIB = L
     return L
 

@@ -154,3 +154,29 @@ def mpa12_constants():
     out = np.zeros(98, dtype=np.float32)
     nat.lib().symgpu_mpa12_constants(_vp(out.ctypes.data), 98)
     return out[:64], out[64:81], out[81:]
+
+
+def flac_decode_packets(data, packets, stream_bps=0, stream_channels=0, max_block=0):
+    """FLAC packets (PIECE_DTYPE offset / len table over `data`) -> (frames, infos, frame_of, subframes, samples): the input of
+    Engine.flac_restore_host.  Packets the reference refuses are left out."""
+    a = _u8(data)
+    packets = np.ascontiguousarray(packets, dtype=nat.PIECE_DTYPE)
+    n = len(packets)
+    frames = np.zeros(n, dtype=nat.FLAC_FRAME_DTYPE)
+    infos = np.zeros(n, dtype=nat.FLAC_FRAME_INFO_DTYPE)
+    frame_of = np.zeros(n, dtype=np.uint32)
+    subs = np.zeros(n * 8, dtype=nat.FLAC_SUBFRAME_DTYPE)
+    cap = 1 << 16
+    while True:
+        samples = np.zeros(cap, dtype=np.int32)
+        good, n_subs, n_smp = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+        rc = nat.lib().symgpu_flac_fe_decode_packets(_vp(a.ctypes.data), a.size, _vp(packets.ctypes.data), n, stream_bps, stream_channels, max_block,
+                                                     _vp(frames.ctypes.data), _vp(infos.ctypes.data), _vp(frame_of.ctypes.data), _vp(subs.ctypes.data), len(subs),
+                                                     _vp(samples.ctypes.data), cap, ctypes.byref(good), ctypes.byref(n_subs), ctypes.byref(n_smp))
+        if rc == 3 and cap < (1 << 31):
+            cap *= 4
+            continue
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_flac_fe_decode_packets")
+        g = good.value
+        return frames[:g], infos[:g], frame_of[:g], subs[:n_subs.value], samples[:n_smp.value]
