@@ -13,10 +13,13 @@
 //   Error                   symphonia-core/src/errors.rs:43-57
 //   Packet                  symphonia-core/src/packet.rs:146-170 (PacketRef)
 //
-// Until the CPU entropy front-ends exist in C++, a packet handed to the GPU decoders
-// carries the *parsed* frame -- the state the reference has at layer3/mod.rs:421 -- as bytes:
-//   MP3: symgpu_mp3_gc[2][2] (256 B) followed by f32 spectra [2][2][576].
+// A packet handed to GpuMpaDecoder is what the reference's MpaReader emits: one whole MPEG audio frame, header word
+// first (Layers I, II and III; the entropy front-ends of SURVEY.md §8f N1 run on the CPU inside decode(), the
+// synthesis on the GPU).  For tests and for hosts with their own bit reader it also accepts the *parsed* Layer III
+// frame -- the state the reference has at layer3/mod.rs:421 -- as bytes: symgpu_mp3_gc[2][2] (256 B) followed by
+// f32 spectra [2][2][576]; the two cannot be confused, a real frame is at most 2881 bytes.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -55,7 +58,7 @@ inline Error map_status(symgpu_status st) {
 }
 
 // Codec ids, symphonia-core/src/codecs/audio.rs:404-418.
-constexpr uint32_t CODEC_ID_VORBIS = 0x1000, CODEC_ID_MP3 = 0x1006, CODEC_ID_AAC = 0x1007;
+constexpr uint32_t CODEC_ID_VORBIS = 0x1000, CODEC_ID_MP1 = 0x1004, CODEC_ID_MP2 = 0x1005, CODEC_ID_MP3 = 0x1006, CODEC_ID_AAC = 0x1007;
 
 struct AudioCodecParameters {
     uint32_t codec = 0;
@@ -148,31 +151,41 @@ class GpuContext {
     std::vector<int> free_;
 };
 
-// MPEG Layer III decoder whose synthesis stage runs on the GPU (mirrors MpaDecoder,
-// symphonia-bundle-mp3/src/decoder.rs:138-197).  See the packet format note at the top of this file.
+// MPEG audio decoder (Layers I-III by codec id) whose synthesis stage runs on the GPU (mirrors MpaDecoder,
+// symphonia-bundle-mp3/src/decoder.rs:66-197).  See the packet format note at the top of this file.
 class GpuMpaDecoder final : public AudioDecoder {
   public:
     static constexpr size_t kPacketBytes = 4 * sizeof(symgpu_mp3_gc) + SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
 
     static Result<std::unique_ptr<AudioDecoder>> try_new(std::shared_ptr<GpuContext> gpu, const AudioCodecParameters& p,
                                                          const AudioDecoderOptions& o) {
-        if (p.codec != CODEC_ID_MP3) return {nullptr, {ErrorKind::Unsupported, "mpa: invalid codec type"}};
+        if (p.codec != CODEC_ID_MP3 && p.codec != CODEC_ID_MP2 && p.codec != CODEC_ID_MP1)
+            return {nullptr, {ErrorKind::Unsupported, "mpa: invalid codec type"}};
         const int slot = gpu->acquire_stream();
         if (slot < 0) return {nullptr, {ErrorKind::LimitError, "symgpu: no free stream slot"}};
-        return {std::unique_ptr<AudioDecoder>(new GpuMpaDecoder(std::move(gpu), p, o, (uint32_t)slot)), {}};
+        symgpu_mp3_fe* fe = nullptr;
+        if (p.codec == CODEC_ID_MP3 && symgpu_mp3_fe_create(&fe) != SYMGPU_OK) {
+            gpu->release_stream(slot);
+            return {nullptr, {ErrorKind::LimitError, "symgpu: out of memory"}};
+        }
+        return {std::unique_ptr<AudioDecoder>(new GpuMpaDecoder(std::move(gpu), p, o, (uint32_t)slot, fe)), {}};
     }
     ~GpuMpaDecoder() override {
         symgpu_mp3_stream_reset(gpu_->raw(), stream_);
         gpu_->release_stream((int)stream_);
+        symgpu_mp3_fe_destroy(fe_);
     }
-    void reset() override { // decoder.rs:152-155
+    void reset() override { // decoder.rs:152-155: the whole decoder state starts over
         symgpu_mp3_stream_reset(gpu_->raw(), stream_);
+        symgpu_mp3_fe_reset(fe_);
+        have_spec_ = false;
         frames_ = 0;
     }
     const AudioCodecParameters& codec_params() const override { return params_; }
     Result<AudioBufferRef> decode(const Packet& packet) override {
         frames_ = 0; // buf.clear(): on any error the buffer stays empty (codecs/audio.rs:278)
-        if (packet.len != kPacketBytes) return {{}, {ErrorKind::DecodeError, "mpa: invalid packet length"}};
+        if (packet.len != kPacketBytes) return decode_frame(packet);
+        if (params_.codec != CODEC_ID_MP3) return {{}, {ErrorKind::DecodeError, "mpa: invalid mpeg audio layer"}};
         symgpu_mp3_gc units[4];
         std::memcpy(units, packet.data, sizeof units);
         const float* spectra = reinterpret_cast<const float*>(packet.data + sizeof units);
@@ -192,7 +205,58 @@ class GpuMpaDecoder final : public AudioDecoder {
         run.channels = mono ? 1 : 2;
         const symgpu_status st = symgpu_mp3_synth_host(gpu_->raw(), units, spectra, &run, 1, 1, pcm_.data());
         if (st != SYMGPU_OK) return {{}, map_status(st)};
-        frames_ = mpeg1 ? 1152 : 576;
+        return finish(packet, mpeg1 ? 1152 : 576, mono ? 1 : 2);
+    }
+    AudioBufferRef last_decoded() const override {
+        AudioBufferRef r;
+        r.n_planes = planes_;
+        r.frames = frames_;
+        r.planes[0] = pcm_.data() + first_;
+        r.planes[1] = pcm_.data() + 1152 + first_;
+        return r;
+    }
+
+  private:
+    GpuMpaDecoder(std::shared_ptr<GpuContext> gpu, AudioCodecParameters p, AudioDecoderOptions o, uint32_t stream, symgpu_mp3_fe* fe)
+        : gpu_(std::move(gpu)), params_(std::move(p)), opts_(o), stream_(stream), fe_(fe), pcm_(SYMGPU_MP3_FRAME_FLOATS, 0.0f),
+          planes_(params_.channels ? params_.channels : 2) {}
+
+    // A real frame: entropy front-end on the CPU (MpaDecoder::decode_inner up to the synthesis call), synthesis on the GPU.
+    Result<AudioBufferRef> decode_frame(const Packet& packet) {
+        symgpu_mp3_frame_info info{};
+        symgpu_status st;
+        size_t frames;
+        if (params_.codec == CODEC_ID_MP3) {
+            symgpu_mp3_gc units[4];
+            st = symgpu_mp3_fe_decode(fe_, packet.data, packet.len, units, quant_, &info);
+            if (st != SYMGPU_OK) return {{}, map_status(st)};
+            const bool joint = units[0].flags & (SYMGPU_MP3_F_MID_SIDE | SYMGPU_MP3_F_INTENSITY);
+            for (int gr = 0; gr < info.granules && joint && info.channels == 2; ++gr)  // stereo.rs:503-505
+                if (units[2 * gr].block_type != units[2 * gr + 1].block_type ||
+                    (units[2 * gr].block_type == SYMGPU_MP3_SHORT && ((units[2 * gr].flags ^ units[2 * gr + 1].flags) & SYMGPU_MP3_F_MIXED)))
+                    return {{}, {ErrorKind::DecodeError, "mpa: stereo channel pair block_type mismatch"}};
+            symgpu_mp3_run run{};
+            run.stream = stream_, run.n_frames = 1, run.granules_per_frame = info.granules, run.channels = info.channels;
+            st = symgpu_mp3_synth_host_quantized(gpu_->raw(), units, quant_, &run, 1, 1, -1, pcm_.data());
+            frames = info.granules == 2 ? 1152 : 576;
+        } else {
+            const int layer = params_.codec == CODEC_ID_MP1 ? 1 : 2, n_slots = layer == 1 ? 12 : 36;
+            st = symgpu_mpa12_fe_decode(packet.data, packet.len, layer, sub_, &info);
+            if (st != SYMGPU_OK) return {{}, map_status(st)};
+            // decoder.rs:96-108: the signal specification is fixed by the first frame
+            if (!have_spec_) have_spec_ = true, spec_rate_ = info.sample_rate, spec_channels_ = info.channels;
+            else if (spec_rate_ != info.sample_rate || spec_channels_ != info.channels)
+                return {{}, {ErrorKind::DecodeError, "mpa: invalid audio buffer signal spec for packet"}};
+            symgpu_mpa12_run run{};
+            run.stream = stream_, run.n_frames = 1, run.channels = info.channels;
+            st = symgpu_mpa12_synth_host(gpu_->raw(), sub_, &run, 1, 1, (uint32_t)n_slots, pcm_.data());
+            frames = 32 * (size_t)n_slots;
+        }
+        if (st != SYMGPU_OK) return {{}, map_status(st)};
+        return finish(packet, frames, info.channels);
+    }
+    Result<AudioBufferRef> finish(const Packet& packet, size_t frames, size_t planes) {
+        frames_ = frames, planes_ = planes;
         // gapless trimming (decoder.rs:130-132)
         size_t begin = 0, end = frames_;
         if (opts_.gapless) {
@@ -203,32 +267,26 @@ class GpuMpaDecoder final : public AudioDecoder {
         frames_ = end - begin;
         return {last_decoded(), {}};
     }
-    AudioBufferRef last_decoded() const override {
-        AudioBufferRef r;
-        r.n_planes = params_.channels ? params_.channels : 2;
-        r.frames = frames_;
-        r.planes[0] = pcm_.data() + first_;
-        r.planes[1] = pcm_.data() + 1152 + first_;
-        return r;
-    }
 
-  private:
-    GpuMpaDecoder(std::shared_ptr<GpuContext> gpu, AudioCodecParameters p, AudioDecoderOptions o, uint32_t stream)
-        : gpu_(std::move(gpu)), params_(std::move(p)), opts_(o), stream_(stream), pcm_(SYMGPU_MP3_FRAME_FLOATS, 0.0f) {}
     std::shared_ptr<GpuContext> gpu_;
     AudioCodecParameters params_;
     AudioDecoderOptions opts_;
     uint32_t stream_;
+    symgpu_mp3_fe* fe_;
     std::vector<float> pcm_;
-    size_t frames_ = 0, first_ = 0;
+    int16_t quant_[4 * 576];
+    float sub_[2 * 32 * 36];
+    size_t frames_ = 0, first_ = 0, planes_ = 2;
+    bool have_spec_ = false;
+    uint32_t spec_rate_ = 0, spec_channels_ = 0;
 };
 
 // What an application does next to symphonia::default::register_enabled_codecs (symphonia/src/lib.rs:234-255).
 inline void register_gpu_decoders(CodecRegistry& registry, std::shared_ptr<GpuContext> gpu) {
-    registry.register_audio_decoder_at_tier(Tier::Preferred, CODEC_ID_MP3,
-                                            [gpu](const AudioCodecParameters& p, const AudioDecoderOptions& o) {
-                                                return GpuMpaDecoder::try_new(gpu, p, o);
-                                            });
+    for (uint32_t codec : {CODEC_ID_MP1, CODEC_ID_MP2, CODEC_ID_MP3})
+        registry.register_audio_decoder_at_tier(Tier::Preferred, codec, [gpu](const AudioCodecParameters& p, const AudioDecoderOptions& o) {
+            return GpuMpaDecoder::try_new(gpu, p, o);
+        });
 }
 
 } // namespace symgpu_host

@@ -2,12 +2,15 @@
 //   decoder_host registry            CPU tier: tier ordering / Unsupported / no-GPU error behaviour
 //   decoder_host decode IN OUT       GPU tier: decode a stream of parsed MP3 packets one decode() call at a
 //                                    time (BASELINE config 0 "plumbing") and write planar PCM
+//   decoder_host file LAYER IN OUT   GPU tier: an MPEG audio FILE end to end in C++ -- packetiser (packetizer.hpp), registry,
+//                                    GpuMpaDecoder::decode on real frames with the packetiser's gapless trims -- planar PCM out
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <vector>
 
 #include "../../include/symgpu/decoder.hpp"
+#include "../../include/symgpu/packetizer.hpp"
 
 using namespace symgpu_host;
 
@@ -107,9 +110,45 @@ static int run_decode(const char* in_path, const char* out_path) {
     return 0;
 }
 
+static int run_file(int layer, const char* in_path, const char* out_path) {
+    std::ifstream in(in_path, std::ios::binary);
+    std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    symgpu::packet::MpaTrack track;
+    std::vector<symgpu::packet::MpaPacket> packets;
+    if (symgpu::packet::MpaIndexer::index(bytes.data(), bytes.size(), track, packets) != symgpu::packet::Status::Ok) return 5;
+    auto gpu = GpuContext::create(0, 2);
+    if (!gpu.ok()) {
+        std::fprintf(stderr, "%s\n", gpu.error.message);
+        return 2;
+    }
+    CodecRegistry reg;
+    register_gpu_decoders(reg, gpu.value);
+    AudioCodecParameters params;
+    params.codec = layer == 1 ? CODEC_ID_MP1 : layer == 2 ? CODEC_ID_MP2 : CODEC_ID_MP3;
+    params.sample_rate = track.first.sample_rate;
+    params.channels = (uint32_t)track.first.n_channels();
+    auto dec = reg.make_audio_decoder(params, AudioDecoderOptions{});  // gapless: the tag's delay and padding are trimmed
+    if (!dec.ok()) return 3;
+    std::ofstream out(out_path, std::ios::binary);
+    size_t good = 0, samples = 0;
+    for (const auto& pk : packets) {
+        Packet p;
+        p.data = bytes.data() + pk.offset, p.len = pk.size, p.pts = (uint64_t)pk.pts, p.dur = pk.dur;
+        p.trim_start = pk.trim_start, p.trim_end = (uint32_t)std::min<uint64_t>(pk.trim_end, pk.dur);
+        auto res = dec.value->decode(p);
+        if (!res.ok()) continue;  // a refused frame yields no audio, the stream goes on (what a player does)
+        ++good, samples += res.value.frames;
+        for (size_t ch = 0; ch < res.value.n_planes; ++ch)
+            out.write(reinterpret_cast<const char*>(res.value.planes[ch]), (std::streamsize)(res.value.frames * sizeof(float)));
+    }
+    std::printf("decoded %zu of %zu packets, %zu samples per channel, delay %u padding %u\n", good, packets.size(), samples, track.delay, track.padding);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "registry") return test_registry();
     if (argc >= 4 && std::string(argv[1]) == "decode") return run_decode(argv[2], argv[3]);
-    std::fprintf(stderr, "usage: decoder_host registry | decode IN OUT\n");
+    if (argc >= 5 && std::string(argv[1]) == "file") return run_file(std::atoi(argv[2]), argv[3], argv[4]);
+    std::fprintf(stderr, "usage: decoder_host registry | decode IN OUT | file LAYER IN OUT\n");
     return 64;
 }

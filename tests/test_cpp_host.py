@@ -16,7 +16,8 @@ def _build():
     src = os.path.join(ROOT, "tests", "cpp", "decoder_host.cpp")
     lib = os.path.join(ROOT, "symphonia_b200", "libsymgpu.so")
     hdr = os.path.join(ROOT, "include", "symgpu", "decoder.hpp")
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(lib), os.path.getmtime(hdr)):
+    hdr2 = os.path.join(ROOT, "include", "symgpu", "packetizer.hpp")
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(lib), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", EXE, src, "-L" + os.path.dirname(lib), "-lsymgpu",
                                "-Wl,-rpath," + os.path.dirname(lib)])
     return EXE

@@ -133,3 +133,39 @@ def test_layer12_file_bytes_to_pcm_on_the_device(oracle):
             ch = int(runs[0]["channels"])
             same = got[:, :ch, :n].view(np.uint32) == want[:, :ch, :n].view(np.uint32)
             assert same.all(), (layer, int((~same).sum()))
+
+
+# ------------------------------------------------------------------------------------------- the C++ plug-in interface on files
+
+@pytest.mark.gpu
+def test_cpp_decoder_on_real_files(tmp_path, oracle):
+    """include/symgpu/decoder.hpp end to end in C++: MpaIndexer cuts the file, the registry hands out GpuMpaDecoder at
+    Tier::Preferred, decode() takes one real frame at a time (front-end on the CPU, synthesis on the GPU) and applies the
+    gapless trims the packetiser derived from the LAME tag -- against the oracle's PCM with the same trims."""
+    import subprocess
+
+    from tests import test_cpp_host
+    exe = test_cpp_host._build()
+    # Layer III: the tagged joint-stereo file
+    data = _corpus()[0]
+    units, quant, runs, spans = _batch([data])
+    rc, want, _ = _oracle.mp3_batch(oracle, units.reshape(-1), _spectra(quant), runs, 1)
+    assert rc == 0
+    dur, t0, t1 = spans[0]
+    expect = b"".join(want[k, ch, int(t0[k]):int(dur[k] - t1[k])].tobytes() for k in range(len(want)) for ch in range(2))
+    inp, outp = tmp_path / "in.mp3", tmp_path / "out.bin"
+    inp.write_bytes(data)
+    res = subprocess.run([exe, "file", "3", str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "delay 1105 padding 471" in res.stdout
+    assert outp.read_bytes() == expect
+    # Layer II and Layer I
+    for (layer, blob), (_, sub, runs12) in zip(_mpa12_corpus(), _mpa12_batches()):
+        rc, want, _ = _oracle.mpa12_batch(oracle, sub, runs12, 1)
+        assert rc == 0
+        ch, n = int(runs12[0]["channels"]), 32 * sub.shape[-1]
+        expect = b"".join(want[k, c, :n].tobytes() for k in range(len(want)) for c in range(ch))
+        inp.write_bytes(blob)
+        res = subprocess.run([exe, "file", str(layer), str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert outp.read_bytes() == expect, layer
