@@ -623,6 +623,29 @@ symgpu_status symgpu_flac_fe_decode_packets(const uint8_t* data, size_t n, const
                                             symgpu_flac_subframe* subs, size_t subs_cap, int32_t* samples, size_t samples_cap,
                                             size_t* n_good, size_t* n_subs, size_t* n_samples);
 
+/* FLAC native container (include/symgpu/packetizer.hpp FlacIndexer): "fLaC", metadata blocks, frames split where the
+ * CRC-16 vouches for the boundary.  Same packets as the reference's parser (symphonia-bundle-flac/src/parser.rs) on
+ * well-formed files; a plain checksum-validated splitter on damaged ones. */
+typedef struct symgpu_flac_stream_info {   /* 56 bytes: STREAMINFO, symphonia-common/src/xiph/audio/flac/mod.rs:78-186 */
+    uint64_t n_samples;        /* 0 = unknown                                                                        */
+    uint64_t first_frame_pos;
+    uint32_t sample_rate;
+    uint32_t frame_min, frame_max;
+    uint16_t block_min, block_max;
+    uint8_t channels, bits_per_sample, has_md5, reserved;
+    uint8_t md5[16];
+    uint8_t reserved2[4];
+} symgpu_flac_stream_info;
+typedef struct symgpu_flac_packet {        /* 24 bytes */
+    uint64_t offset;
+    uint64_t ts;               /* first sample of the frame (parser.rs:566-584)                                       */
+    uint32_t size;
+    uint32_t dur;              /* samples                                                                            */
+} symgpu_flac_packet;
+/* SYMGPU_ERR_UNSUPPORTED: no "fLaC" marker; SYMGPU_ERR_DECODE: bad or missing STREAMINFO / cut metadata.  Two-call pattern. */
+symgpu_status symgpu_flac_index(const uint8_t* data, size_t n, symgpu_flac_stream_info* info, symgpu_flac_packet* packets, size_t cap,
+                                size_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1053,5 +1053,259 @@ class OggVorbisMapper {
     bool have_timer_ = false, ready_ = false;
 };
 
+// =====================================================================================================================
+// FLAC (native container)
+// =====================================================================================================================
+// "fLaC", metadata blocks (STREAMINFO first), then frames back to back.  A frame carries no length: its end is where
+// the next frame starts, and the only proof of that is the CRC-16 in front of it.  The reference finds packets with a
+// fragment-merging parser driven by moving averages of the frame size (symphonia-bundle-flac/src/parser.rs:149-560);
+// this is a plain CRC-validated splitter instead: a frame starts at a sync code whose header parses, checks out (CRC-8)
+// and fits the stream (parser.rs:586-648: rate, bit depth, channel count, block size, blocking strategy, monotonic
+// sequence number), and ends at the first later such header -- or the end of the data -- in front of which the CRC-16
+// of everything since the start matches.  On a well-formed file both give the same packets, time stamps and durations;
+// on a damaged one this splitter drops exactly the frames whose checksum fails, which is not promised to be what the
+// reference's heuristics do.
+
+struct FlacStreamInfo {  // symphonia-common/src/xiph/audio/flac/mod.rs:78-186
+    uint16_t block_min, block_max;
+    uint32_t frame_min, frame_max;  // bytes, 0 = unknown
+    uint32_t sample_rate;
+    uint8_t channels, bits_per_sample;
+    uint64_t n_samples;             // 0 = unknown
+    uint8_t md5[16];
+    bool has_md5;
+};
+
+inline Status flac_read_stream_info(const uint8_t* p, size_t n, FlacStreamInfo& si) {
+    if (n < 34) return Status::EndOfStream;
+    si.block_min = uint16_t(detail::be16(p)), si.block_max = uint16_t(detail::be16(p + 2));
+    if (si.block_min < 16 || si.block_max < 16 || si.block_max < si.block_min) return Status::DecodeError;
+    si.frame_min = detail::be24(p + 4), si.frame_max = detail::be24(p + 7);
+    if (si.frame_min && si.frame_max && si.frame_max < si.frame_min) return Status::DecodeError;
+    const uint64_t bits = uint64_t(detail::be32(p + 10)) << 32 | detail::be32(p + 14);  // 20 + 3 + 5 + 36 bits
+    si.sample_rate = uint32_t(bits >> 44);
+    if (si.sample_rate < 1 || si.sample_rate > 655350) return Status::DecodeError;
+    si.channels = uint8_t(((bits >> 41) & 7) + 1);
+    si.bits_per_sample = uint8_t(((bits >> 36) & 31) + 1);
+    if (si.bits_per_sample < 4) return Status::DecodeError;
+    si.n_samples = bits & 0xfffffffffull;
+    std::memcpy(si.md5, p + 18, 16);
+    si.has_md5 = false;
+    for (int k = 0; k < 16; ++k) si.has_md5 |= si.md5[k] != 0;
+    return Status::Ok;
+}
+
+inline uint8_t crc8_ccitt(const uint8_t* p, size_t n) {  // polynomial 0x07 (symphonia-core/src/checksum/crc8.rs:32-65)
+    uint8_t c = 0;
+    for (size_t i = 0; i < n; ++i) {
+        c ^= p[i];
+        for (int k = 0; k < 8; ++k) c = uint8_t(c & 0x80 ? (c << 1) ^ 0x07 : c << 1);
+    }
+    return c;
+}
+namespace detail {
+struct Crc16Msb {
+    uint16_t t[256];
+    constexpr Crc16Msb() : t() {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i << 8;
+            for (int k = 0; k < 8; ++k) c = (c & 0x8000) ? (c << 1) ^ 0x8005 : c << 1;
+            t[i] = uint16_t(c);
+        }
+    }
+};
+}  // namespace detail
+inline uint16_t crc16_ansi_update(uint16_t state, const uint8_t* p, size_t n) {  // polynomial 0x8005, most-significant bit first
+    static constexpr detail::Crc16Msb tab{};
+    for (size_t i = 0; i < n; ++i) state = uint16_t((state << 8) ^ tab.t[(state >> 8) ^ p[i]]);
+    return state;
+}
+
+struct FlacFrameHeader {
+    uint64_t sequence;
+    bool by_sample;
+    uint32_t block, sample_rate, bits_per_sample;  // rate / depth 0: not in the header
+    uint8_t channels;
+    uint8_t size;  // bytes, sync code to CRC-8
+};
+
+// frame.rs:81-233 at p[0..n): false unless a complete header with a matching CRC-8 starts here.
+inline bool flac_parse_frame_header(const uint8_t* p, size_t n, FlacFrameHeader& h) {
+    if (n < 6 || p[0] != 0xff || (p[1] & 0xfc) != 0xf8 || (p[3] & 1)) return false;
+    size_t at = 4;
+    h.by_sample = p[1] & 1;
+    const unsigned bs = p[2] >> 4, sr = p[2] & 15, ch = p[3] >> 4, bd = (p[3] >> 1) & 7;
+    uint64_t v = p[at++];
+    int more;
+    if (v < 0x80) more = 0;
+    else if (v >= 0xc0 && v <= 0xdf) more = 1, v &= 0x1f;
+    else if (v >= 0xe0 && v <= 0xef) more = 2, v &= 0x0f;
+    else if (v >= 0xf0 && v <= 0xf7) more = 3, v &= 0x07;
+    else if (v >= 0xf8 && v <= 0xfb) more = 4, v &= 0x03;
+    else if (v >= 0xfc && v <= 0xfd) more = 5, v &= 0x01;
+    else if (v == 0xfe) more = 6, v = 0;
+    else return false;
+    for (int k = 0; k < more; ++k) {
+        if (at >= n) return false;
+        v = v << 6 | (p[at++] & 0x3f);
+    }
+    if (v > (h.by_sample ? 0xfffffffffull : 0x7fffffffull)) return false;
+    h.sequence = v;
+    if (bs == 0) return false;
+    if (bs == 1) h.block = 192;
+    else if (bs <= 5) h.block = 576u << (bs - 2);
+    else if (bs == 6) {
+        if (at + 1 > n) return false;
+        h.block = uint32_t(p[at++]) + 1;
+    } else if (bs == 7) {
+        if (at + 2 > n) return false;
+        const uint32_t x = detail::be16(p + at);
+        at += 2;
+        if (x == 0xffff) return false;
+        h.block = x + 1;
+    } else h.block = 256u << (bs - 8);
+    static constexpr uint32_t rates[12] = {0, 88200, 176400, 192000, 8000, 16000, 22050, 24000, 32000, 44100, 48000, 96000};
+    if (sr < 12) h.sample_rate = rates[sr];
+    else if (sr == 12) {
+        if (at + 1 > n) return false;
+        h.sample_rate = uint32_t(p[at++]) * 1000;
+    } else if (sr == 15) return false;
+    else {
+        if (at + 2 > n) return false;
+        h.sample_rate = detail::be16(p + at) * (sr == 14 ? 10u : 1u);
+        at += 2;
+    }
+    if (sr != 0 && (h.sample_rate < 1 || h.sample_rate > 655350)) return false;
+    static constexpr uint8_t widths[8] = {0, 8, 12, 255, 16, 20, 24, 32};
+    if (widths[bd] == 255) return false;
+    h.bits_per_sample = widths[bd];
+    if (ch <= 7) h.channels = uint8_t(ch + 1);
+    else if (ch <= 10) h.channels = 2;
+    else return false;
+    if (at + 1 > n || p[at] != crc8_ccitt(p, at)) return false;
+    h.size = uint8_t(at + 1);
+    return true;
+}
+
+struct FlacPacket {
+    uint64_t offset;
+    uint32_t size;
+    uint64_t ts;   // first sample (parser.rs:566-584)
+    uint32_t dur;  // block size
+};
+
+class FlacIndexer {
+  public:
+    FlacIndexer(const uint8_t* data, size_t n) : d_(data), n_(n) {}
+
+    // demuxer.rs:60-170: the stream marker, then metadata blocks up to the one flagged last; the first must be STREAMINFO.
+    Status open() {
+        if (n_ < 4 || std::memcmp(d_, "fLaC", 4) != 0) return Status::Unsupported;
+        size_t at = 4;
+        bool first = true;
+        for (;;) {
+            if (at + 4 > n_) return Status::EndOfStream;
+            const bool last = d_[at] & 0x80;
+            const unsigned type = d_[at] & 0x7f;
+            const size_t len = detail::be24(d_ + at + 1);
+            at += 4;
+            if (at + len > n_) return Status::EndOfStream;
+            if (first) {
+                if (type != 0 || len != 34) return Status::DecodeError;
+                const Status s = flac_read_stream_info(d_ + at, len, info_);
+                if (s != Status::Ok) return s;
+                first = false;
+            }
+            at += len;
+            if (last) break;
+        }
+        pos_ = first_frame_ = at;
+        have_last_ = false;
+        return Status::Ok;
+    }
+    const FlacStreamInfo& info() const { return info_; }
+    size_t first_frame_pos() const { return first_frame_; }
+    size_t skipped_bytes() const { return skipped_; }  // bytes between packets that belonged to no valid frame
+
+    Status next(FlacPacket& pk) {
+        for (size_t start = pos_; start + 2 <= n_;) {
+            FlacFrameHeader h;
+            if (!candidate(start, h)) {
+                const size_t q = next_sync(start + 1);
+                skipped_ += q - start;
+                start = pos_ = q;
+                continue;
+            }
+            // the end: the next plausible header (or the end of the data) that the CRC-16 vouches for
+            uint16_t crc = 0;
+            size_t done = start;  // crc covers [start, done)
+            for (size_t q = next_sync(start + h.size);; q = next_sync(q + 1)) {
+                FlacFrameHeader nh;
+                const bool at_end = q >= n_;
+                if (at_end) q = n_;
+                if (q - start >= 2 + size_t(h.size) && (at_end || candidate(q, nh, &h))) {
+                    crc = crc16_ansi_update(crc, d_ + done, q - 2 - done), done = q - 2;
+                    if (crc == detail::be16(d_ + q - 2)) {
+                        pk.offset = start, pk.size = uint32_t(q - start), pk.dur = h.block;
+                        const bool fixed = info_.block_min == info_.block_max;
+                        pk.ts = h.by_sample ? h.sequence : h.sequence * (fixed ? info_.block_min : h.block);
+                        last_ = h, have_last_ = true, pos_ = q;
+                        return Status::Ok;
+                    }
+                }
+                if (at_end || q - start > kMaxFrame) break;
+            }
+            const size_t q = next_sync(start + 1);  // no end vouched for: this was not a frame
+            skipped_ += q - start;
+            start = pos_ = q;
+        }
+        return Status::EndOfStream;
+    }
+
+    static Status index(const uint8_t* data, size_t n, FlacStreamInfo& info, std::vector<FlacPacket>& out) {
+        FlacIndexer ix(data, n);
+        const Status s = ix.open();
+        if (s != Status::Ok) return s;
+        info = ix.info();
+        FlacPacket p;
+        while (ix.next(p) == Status::Ok) out.push_back(p);
+        return Status::Ok;
+    }
+
+  private:
+    static constexpr size_t kMaxFrame = 16u * 1024 * 1024;  // frame.rs:17
+
+    size_t next_sync(size_t from) const {
+        for (size_t q = from; q + 2 <= n_;) {
+            const void* hit = std::memchr(d_ + q, 0xff, n_ - q);
+            if (!hit) break;
+            q = size_t(static_cast<const uint8_t*>(hit) - d_);
+            if (q + 2 > n_) break;
+            if ((d_[q + 1] & 0xfc) == 0xf8) return q;
+            ++q;
+        }
+        return n_;
+    }
+    // A header at `at` that fits the stream (parser.rs:586-648) and follows `prev` (default: the last accepted frame).
+    bool candidate(size_t at, FlacFrameHeader& h, const FlacFrameHeader* prev = nullptr) const {
+        if (at + 6 > n_ || !flac_parse_frame_header(d_ + at, n_ - at, h)) return false;
+        if (h.sample_rate && h.sample_rate != info_.sample_rate) return false;
+        if (h.bits_per_sample && h.bits_per_sample != info_.bits_per_sample) return false;
+        if (h.block > info_.block_max || h.channels != info_.channels) return false;
+        const bool fixed = info_.block_min == info_.block_max;
+        if (h.by_sample == fixed) return false;
+        const FlacFrameHeader* before = prev ? prev : (have_last_ ? &last_ : nullptr);
+        const uint64_t last_seq = before ? before->sequence : 0;
+        return h.sequence > last_seq || h.sequence == 0;
+    }
+
+    const uint8_t* d_;
+    size_t n_;
+    size_t pos_ = 0, first_frame_ = 0, skipped_ = 0;
+    FlacStreamInfo info_{};
+    FlacFrameHeader last_{};
+    bool have_last_ = false;
+};
+
 }  // namespace packet
 }  // namespace symgpu

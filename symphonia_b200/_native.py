@@ -84,6 +84,11 @@ MP3_FRAME_INFO_DTYPE = np.dtype([("sample_rate", "<u4"), ("channels", "u1"), ("g
 assert MP3_FRAME_INFO_DTYPE.itemsize == 16
 FLAC_FRAME_INFO_DTYPE = np.dtype([("sequence", "<u8"), ("block_size", "<u4"), ("sample_rate", "<u4"), ("by_sample", "u1"), ("reserved", "u1", (7,))])
 assert FLAC_FRAME_INFO_DTYPE.itemsize == 24
+FLAC_STREAM_INFO_DTYPE = np.dtype([("n_samples", "<u8"), ("first_frame_pos", "<u8"), ("sample_rate", "<u4"), ("frame_min", "<u4"), ("frame_max", "<u4"),
+                                   ("block_min", "<u2"), ("block_max", "<u2"), ("channels", "u1"), ("bits_per_sample", "u1"), ("has_md5", "u1"),
+                                   ("reserved", "u1"), ("md5", "u1", (16,)), ("reserved2", "u1", (4,))])
+FLAC_PACKET_DTYPE = np.dtype([("offset", "<u8"), ("ts", "<u8"), ("size", "<u4"), ("dur", "<u4")])
+assert FLAC_STREAM_INFO_DTYPE.itemsize == 56 and FLAC_PACKET_DTYPE.itemsize == 24
 MP3_FILE_DTYPE = np.dtype([("data", "<u8"), ("n", "<u8"), ("packets", "<u8"), ("n_packets", "<u8"), ("stream", "<u4"), ("reserved", "<u4")])
 assert MP3_FILE_DTYPE.itemsize == 40
 assert PIECE_DTYPE.itemsize == 16 and OGG_PACKET_DTYPE.itemsize == 40 and VORBIS_IDENT_DTYPE.itemsize == 8
@@ -218,6 +223,8 @@ def lib():
     L.symgpu_mpa12_constants.argtypes = [vp, sz]
     L.symgpu_flac_fe_decode_packets.restype = ctypes.c_int
     L.symgpu_flac_fe_decode_packets.argtypes = [vp, sz, vp, sz, u32, u32, u32, vp, vp, vp, vp, sz, vp, sz, psz, psz, psz]
+    L.symgpu_flac_index.restype = ctypes.c_int
+    L.symgpu_flac_index.argtypes = [vp, sz, vp, vp, sz, psz]
     _LIB = L
     return L
 

@@ -143,5 +143,28 @@ extern "C" symgpu_status symgpu_vorbis_packet_durations(const symgpu_vorbis_iden
     return SYMGPU_OK;
 }
 
+extern "C" symgpu_status symgpu_flac_index(const uint8_t* data, size_t n, symgpu_flac_stream_info* info, symgpu_flac_packet* packets, size_t cap,
+                                           size_t* n_out) {
+    if ((!data && n) || !info || !n_out || (cap && !packets)) return SYMGPU_ERR_ARG;
+    FlacIndexer ix(data, n);
+    const Status s = ix.open();
+    if (s != Status::Ok) return *n_out = 0, s == Status::Unsupported ? SYMGPU_ERR_UNSUPPORTED : SYMGPU_ERR_DECODE;
+    const FlacStreamInfo& si = ix.info();
+    *info = symgpu_flac_stream_info{};
+    info->n_samples = si.n_samples, info->first_frame_pos = ix.first_frame_pos(), info->sample_rate = si.sample_rate;
+    info->frame_min = si.frame_min, info->frame_max = si.frame_max, info->block_min = si.block_min, info->block_max = si.block_max;
+    info->channels = si.channels, info->bits_per_sample = si.bits_per_sample, info->has_md5 = si.has_md5;
+    std::memcpy(info->md5, si.md5, 16);
+    size_t count = 0;
+    FlacPacket p;
+    while (ix.next(p) == Status::Ok) {
+        if (count < cap) packets[count] = symgpu_flac_packet{p.offset, p.ts, p.size, p.dur};
+        ++count;
+    }
+    *n_out = count;
+    return SYMGPU_OK;
+}
+
+static_assert(sizeof(symgpu_flac_stream_info) == 56 && sizeof(symgpu_flac_packet) == 24, "record sizes are ABI");
 static_assert(sizeof(symgpu_mpa_track) == 48 && sizeof(symgpu_mpa_packet) == 48 && sizeof(symgpu_adts_packet) == 32, "record sizes are ABI");
 static_assert(sizeof(symgpu_piece) == 16 && sizeof(symgpu_ogg_packet) == 40 && sizeof(symgpu_vorbis_ident) == 8, "record sizes are ABI");

@@ -98,3 +98,16 @@ def vorbis_packet_durations(ident, n_modes, mask, packets, prev_exp=0):
                                                     _vp(prev.ctypes.data), _vp(dur.ctypes.data), _vp(discard.ctypes.data)),
            "symgpu_vorbis_packet_durations")
     return dur, discard, int(prev[0])
+
+
+def flac_index(data):
+    """(stream info record, packets) of a native FLAC file; SymgpuError status 2 without the "fLaC" marker, 1 for bad metadata."""
+    L = nat.lib()
+    a, p = _buf(data)
+    info = np.zeros(1, dtype=nat.FLAC_STREAM_INFO_DTYPE)
+    n = ctypes.c_size_t(0)
+    _check(L.symgpu_flac_index(p, a.size, _vp(info.ctypes.data), None, 0, ctypes.byref(n)), "symgpu_flac_index")
+    packets = np.zeros(n.value, dtype=nat.FLAC_PACKET_DTYPE)
+    if n.value:
+        _check(L.symgpu_flac_index(p, a.size, _vp(info.ctypes.data), _vp(packets.ctypes.data), n.value, ctypes.byref(n)), "symgpu_flac_index")
+    return info[0], packets

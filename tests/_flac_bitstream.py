@@ -138,3 +138,19 @@ def write_frame(rng, frame, subs, samples, number, sample_rate=44100, stream_bps
     body = w.bytes()
     frame_bytes = hdr + body
     return frame_bytes + crc16(frame_bytes).to_bytes(2, "big")
+
+
+def stream_info_block(block_min, block_max, sample_rate, channels, bps, n_samples, frame_min=0, frame_max=0, md5=bytes(16)):
+    """STREAMINFO body, 34 bytes (FLAC format: METADATA_BLOCK_STREAMINFO)."""
+    bits = (sample_rate << 44) | ((channels - 1) << 41) | ((bps - 1) << 36) | n_samples
+    return block_min.to_bytes(2, "big") + block_max.to_bytes(2, "big") + frame_min.to_bytes(3, "big") + frame_max.to_bytes(3, "big") + \
+        bits.to_bytes(8, "big") + md5
+
+
+def native_file(frames, info_block, extra_blocks=()):
+    """"fLaC", STREAMINFO, optional further metadata blocks (type, body), frames."""
+    blocks = [(0, info_block)] + list(extra_blocks)
+    out = b"fLaC"
+    for k, (kind, body) in enumerate(blocks):
+        out += bytes([(0x80 if k == len(blocks) - 1 else 0) | kind]) + len(body).to_bytes(3, "big") + body
+    return out + b"".join(frames)

@@ -136,3 +136,75 @@ def test_damage_and_stream_limits():
         b[hdr_len] = fw.crc8(bytes(b[:hdr_len]))
         cases.append(bytes(b))
     assert _check_against_oracle(cases, stream_bps=16)[0] == []
+
+
+# ------------------------------------------------------------------------------------------- native container -> PCM
+
+def test_native_file_to_pcm(oracle):
+    """A .flac file end to end on the CPU side of the boundary: marker + STREAMINFO + metadata, frames split by checksum,
+    front-end, restoration oracle -- back to the PCM the encoder started from."""
+    import symphonia_b200 as sb
+    from symphonia_b200 import packetizer
+    rng = np.random.default_rng(88)
+    for bps, channels, block, fixed in ((16, 2, 1152, True), (24, 2, 4096, True), (16, 1, 576, True)):
+        n_frames = 14
+        frames, subs, samples, expect = workloads.flac_batch(n_frames, block, seed=300 + bps + block, bps=bps, channels=channels, return_pcm=True)
+        # fixed-block-size stream: every block but the last has the stream's size (flac_batch makes every 7th short; keep the shape
+        # a real encoder produces by re-encoding those positions at full size would change the data -- use a stream whose only short
+        # block is the last one instead)
+        order = [f for f in range(n_frames) if f % 7] + [0]
+        pk = []
+        for number, f in enumerate(order):
+            fr = frames[f]
+            ss = subs[int(fr["first_subframe"]):int(fr["first_subframe"]) + channels]
+            pk.append(fw.write_frame(rng, fr, ss, samples, number, stream_bps=bps))
+        total = sum(int(subs[int(frames[f]["first_subframe"])]["n"]) for f in order)
+        info_block = fw.stream_info_block(block, block, 44100, channels, bps, total, min(map(len, pk)), max(map(len, pk)), md5=bytes(range(1, 17)))
+        data = fw.native_file(pk, info_block, extra_blocks=[(4, b"\x07\x00\x00\x00example\x00\x00\x00\x00"), (1, bytes(300))])
+        info, packets = packetizer.flac_index(data)
+        assert (int(info["sample_rate"]), int(info["channels"]), int(info["bits_per_sample"]), int(info["block_max"]), int(info["n_samples"])) == \
+            (44100, channels, bps, block, total) and bool(info["has_md5"])
+        at = int(info["first_frame_pos"])
+        assert data[at:at + 2] in (b"\xff\xf8", b"\xff\xf9")
+        # the packets are the frames as written, time stamps count samples
+        assert [int(p["size"]) for p in packets] == [len(x) for x in pk]
+        assert [int(p["ts"]) for p in packets] == [k * block for k in range(len(pk))]
+        assert int(packets[-1]["ts"]) + int(packets[-1]["dur"]) == total
+        table = np.zeros(len(packets), dtype=nat.PIECE_DTYPE)
+        table["offset"], table["len"] = packets["offset"], packets["size"]
+        gf, gi, gof, gs, gsm = frontend.flac_decode_packets(data, table, int(info["bits_per_sample"]), int(info["channels"]), int(info["block_max"]))
+        assert len(gf) == len(pk)
+        rc, pcm = kat._restore(oracle, gf, gs, gsm.copy())
+        assert rc == 0
+        for k, f in enumerate(order):
+            for c in range(channels):
+                a, b = subs[f * channels + c], gs[int(gf[k]["first_subframe"]) + c]
+                n = int(a["n"])
+                assert (pcm[int(b["offset"]):int(b["offset"]) + n] == expect[int(a["offset"]):int(a["offset"]) + n]).all(), (k, c)
+        # damage: a flipped payload bit fails that frame's CRC-16 and only that frame goes
+        hurt = bytearray(data)
+        victim = packets[5]
+        hurt[int(victim["offset"]) + int(victim["size"]) // 2] ^= 0x20
+        _, p2 = packetizer.flac_index(bytes(hurt))
+        assert [int(p["ts"]) for p in p2] == [int(p["ts"]) for k, p in enumerate(packets) if k != 5]
+        cut = int(packets[8]["offset"])
+        _, p3 = packetizer.flac_index(data[:cut] + rng.integers(0, 256, 333, dtype=np.uint8).tobytes() + data[cut:])
+        # (the frame in FRONT of the junk goes with it: nothing behind its checksum looks like a frame, so nothing vouches for its end --
+        #  the reference's fragment parser cuts at sync codes too and loses it the same way)
+        assert [int(p["ts"]) for p in p3] == [int(p["ts"]) for k, p in enumerate(packets) if k != 7]
+        _, p4 = packetizer.flac_index(data[:-7])  # a cut last frame has no checksum to vouch for it
+        assert len(p4) == len(packets) - 1
+    # container-level refusals
+    with pytest.raises(sb.SymgpuError) as e:
+        packetizer.flac_index(b"OggS" + bytes(100))
+    assert e.value.status == 2
+    for bad_block in (fw.stream_info_block(8, 4096, 44100, 2, 16, 0), fw.stream_info_block(4096, 1024, 44100, 2, 16, 0),
+                      fw.stream_info_block(4096, 4096, 0, 2, 16, 0), fw.stream_info_block(4096, 4096, 44100, 2, 3, 0),
+                      fw.stream_info_block(4096, 4096, 44100, 2, 16, 0, frame_min=900, frame_max=100)):
+        with pytest.raises(sb.SymgpuError) as e:
+            packetizer.flac_index(fw.native_file([], bad_block))
+        assert e.value.status == 1
+    with pytest.raises(sb.SymgpuError):
+        packetizer.flac_index(b"fLaC" + bytes([0x84]) + (10).to_bytes(3, "big") + bytes(10))  # first block is not STREAMINFO
+    with pytest.raises(sb.SymgpuError):
+        packetizer.flac_index(b"fLaC" + bytes([0x00]) + (34).to_bytes(3, "big") + fw.stream_info_block(4096, 4096, 44100, 2, 16, 0))  # metadata never ends
