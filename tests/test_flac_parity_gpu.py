@@ -62,3 +62,31 @@ def test_malformed_descriptors(engine):
     assert e.value.status == 6
     good = engine.flac_restore_host(frames, subs, samples.copy())  # still healthy
     assert good.shape == samples.shape
+
+
+def test_flac_file_bytes_to_pcm(engine):
+    """.flac bytes -> container splitter -> front-end (both CPU) -> restoration kernel == the PCM the encoder started from."""
+    from symphonia_b200 import _native as nat
+    from symphonia_b200 import frontend, packetizer
+    from tests import _flac_bitstream as fw
+    rng = np.random.default_rng(61)
+    bps, channels, block, n_frames = 16, 2, 1152, 40
+    frames, subs, samples, expect = workloads.flac_batch(n_frames, block, seed=777, bps=bps, channels=channels, return_pcm=True)
+    order = [f for f in range(n_frames) if f % 7] + [0]
+    pk = []
+    for number, f in enumerate(order):
+        fr = frames[f]
+        pk.append(fw.write_frame(rng, fr, subs[int(fr["first_subframe"]):int(fr["first_subframe"]) + channels], samples, number, stream_bps=bps))
+    total = sum(int(subs[int(frames[f]["first_subframe"])]["n"]) for f in order)
+    data = fw.native_file(pk, fw.stream_info_block(block, block, 44100, channels, bps, total))
+    info, packets = packetizer.flac_index(data)
+    assert len(packets) == len(pk)
+    table = np.zeros(len(packets), dtype=nat.PIECE_DTYPE)
+    table["offset"], table["len"] = packets["offset"], packets["size"]
+    gf, gi, gof, gs, gsm = frontend.flac_decode_packets(data, table, bps, channels, block)
+    got = engine.flac_restore_host(gf, gs, gsm.copy())
+    for k, f in enumerate(order):
+        for c in range(channels):
+            a, b = subs[f * channels + c], gs[int(gf[k]["first_subframe"]) + c]
+            n = int(a["n"])
+            assert (got[int(b["offset"]):int(b["offset"]) + n] == expect[int(a["offset"]):int(a["offset"]) + n]).all(), (k, c)
