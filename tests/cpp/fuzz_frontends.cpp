@@ -1,0 +1,151 @@
+// Sanitizer fuzz driver for the host-side parsers (packetisers, MP3 / Layer I-II / FLAC front-ends, plan + jobs):
+//   g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-sanitize-recover=all ... tests/cpp/fuzz_frontends.cpp <csrc/*.cpp>
+//   fuzz_frontends SEEDFILE... : every seed is mutated (bit flips, byte runs, truncation, splices) ITER times and pushed through
+// every entry point; any out-of-bounds access, overflow or leak aborts.  Run by tests/test_fuzz_sanitized.py.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <vector>
+
+#include "../../include/symgpu.h"
+#include "../../include/symgpu/packetizer.hpp"
+
+using namespace symgpu::packet;
+
+static void run_all(const std::vector<uint8_t>& d) {
+    const uint8_t* p = d.data();
+    const size_t n = d.size();
+    // ---- MPEG audio: index, serial front-end, plan + jobs, Layer I / II
+    {
+        symgpu_mpa_track track;
+        size_t count = 0;
+        if (symgpu_mpa_index(p, n, 1, &track, nullptr, 0, &count) == SYMGPU_OK && count) {
+            std::vector<symgpu_mpa_packet> pk(count);
+            symgpu_mpa_index(p, n, 1, &track, pk.data(), count, &count);
+            std::vector<symgpu_mp3_gc> units(count * 4);
+            std::vector<int16_t> quant(count * 4 * 576);
+            std::vector<uint32_t> frame_of(count);
+            size_t good = 0;
+            symgpu_mp3_frame_info info;
+            symgpu_mp3_fe* fe = nullptr;
+            symgpu_mp3_fe_create(&fe);
+            symgpu_mp3_fe_decode_packets(fe, p, n, pk.data(), count, units.data(), quant.data(), frame_of.data(), &good, &info);
+            symgpu_mp3_fe_destroy(fe);
+            uint32_t rounds = 0;
+            symgpu_mp3_entropy_decode_cpu(p, n, pk.data(), count, units.data(), quant.data(), frame_of.data(), &good, &info, &rounds);
+            std::vector<float> sub(count * 2 * 32 * 36);
+            for (int layer = 1; layer <= 2; ++layer)
+                symgpu_mpa12_fe_decode_packets(p, n, pk.data(), count, layer, sub.data(), frame_of.data(), &good, &info);
+        }
+        // a packet that is just the raw bytes
+        symgpu_mp3_gc u[4];
+        std::vector<int16_t> q(4 * 576);
+        symgpu_mp3_fe* fe = nullptr;
+        symgpu_mp3_fe_create(&fe);
+        symgpu_mp3_frame_info info;
+        symgpu_mp3_fe_decode(fe, p, n < 3000 ? n : 3000, u, q.data(), &info);
+        symgpu_mp3_fe_destroy(fe);
+    }
+    // ---- ADTS, Ogg (+ Vorbis mapping), FLAC
+    {
+        size_t count = 0;
+        symgpu_status stop;
+        symgpu_adts_index(p, n, nullptr, 0, &count, &stop);
+        OggIndex ix;
+        OggIndex::build(p, n, ix, false);
+        for (auto& kv : ix.streams) {
+            OggVorbisMapper mp;
+            std::vector<uint8_t> bytes;
+            bool first = true;
+            for (const OggPacket& pk : kv.second.packets()) {
+                if (pk.len > (1u << 22)) continue;
+                bytes.resize(pk.len);
+                kv.second.gather(p, pk, bytes.data());
+                if (first) {
+                    first = false;
+                    if (!mp.detect(bytes.data(), bytes.size())) break;
+                } else {
+                    mp.map(bytes.data(), bytes.size());
+                }
+            }
+        }
+        // the raw bytes as a Vorbis setup packet and as Xiph-laced extra data
+        VorbisIdent id{2, 44100, 8, 11};
+        uint8_t modes;
+        uint64_t mask;
+        vorbis_read_setup_modes(p, n, id, modes, mask);
+        Piece a, b;
+        vorbis_unpack_xiph_laced(p, n, a, b);
+        symgpu_flac_stream_info si;
+        symgpu_flac_index(p, n, &si, nullptr, 0, &count);
+        if (count) {
+            std::vector<symgpu_flac_packet> fp(count);
+            symgpu_flac_index(p, n, &si, fp.data(), count, &count);
+            std::vector<symgpu_piece> tab(count);
+            size_t total = 0;
+            for (size_t i = 0; i < count; ++i) tab[i] = symgpu_piece{fp[i].offset, fp[i].size, 0}, total += size_t(fp[i].dur) * si.channels;
+            std::vector<symgpu_flac_frame> fr(count);
+            std::vector<symgpu_flac_frame_info> fi(count);
+            std::vector<uint32_t> fo(count);
+            std::vector<symgpu_flac_subframe> sf(count * 8);
+            std::vector<int32_t> smp(total + 8);
+            size_t g, ns, nm;
+            symgpu_flac_fe_decode_packets(p, n, tab.data(), count, si.bits_per_sample, si.channels, si.block_max, fr.data(), fi.data(), fo.data(), sf.data(), sf.size(),
+                                          smp.data(), smp.size(), &g, &ns, &nm);
+        }
+        // the raw bytes as one FLAC packet
+        symgpu_piece one{0, uint32_t(n), 0};
+        symgpu_flac_frame fr;
+        symgpu_flac_frame_info fi;
+        uint32_t fo;
+        symgpu_flac_subframe sf[8];
+        std::vector<int32_t> smp(8 * 65536);
+        size_t g, ns, nm;
+        symgpu_flac_fe_decode_packets(p, n, &one, 1, 16, 0, 0, &fr, &fi, &fo, sf, 8, smp.data(), smp.size(), &g, &ns, &nm);
+    }
+}
+
+int main(int argc, char** argv) {
+    const int iters = std::getenv("FUZZ_ITERS") ? std::atoi(std::getenv("FUZZ_ITERS")) : 200;
+    std::mt19937_64 rng(12345);
+    size_t runs = 0;
+    for (int a = 1; a < argc; ++a) {
+        std::ifstream in(argv[a], std::ios::binary);
+        const std::vector<uint8_t> seed((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        run_all(seed), ++runs;
+        for (int it = 0; it < iters && !seed.empty(); ++it) {
+            std::vector<uint8_t> d = seed;
+            const int kinds = 1 + int(rng() % 3);
+            for (int k = 0; k < kinds; ++k) {
+                const size_t at = rng() % d.size();
+                switch (rng() % 6) {
+                    case 0: d[at] ^= uint8_t(1u << (rng() % 8)); break;
+                    case 1: d[at] = uint8_t(rng()); break;
+                    case 2: {
+                        const size_t len = std::min<size_t>(1 + rng() % 16, d.size() - at);
+                        std::memset(d.data() + at, (rng() & 1) ? 0xff : 0x00, len);
+                        break;
+                    }
+                    case 3: d.resize(1 + at); break;
+                    case 4: {
+                        const size_t from = rng() % d.size(), len = std::min<size_t>(1 + rng() % 64, std::min(d.size() - from, d.size() - at));
+                        std::memmove(d.data() + at, d.data() + from, len);
+                        break;
+                    }
+                    default: {
+                        const size_t len = 1 + rng() % 32;
+                        std::vector<uint8_t> junk(len);
+                        for (auto& x : junk) x = uint8_t(rng());
+                        d.insert(d.begin() + at, junk.begin(), junk.end());
+                    }
+                }
+                if (d.empty()) break;
+            }
+            if (!d.empty()) run_all(d), ++runs;
+        }
+    }
+    std::printf("fuzz: %zu inputs, no sanitizer report\n", runs);
+    return 0;
+}
