@@ -550,6 +550,9 @@ symgpu_status symgpu_mp3_entropy_plan(const uint8_t* data, size_t n, const symgp
  * split the job range over threads. */
 symgpu_status symgpu_mp3_entropy_run_cpu(const uint8_t* md, size_t md_len, const symgpu_mp3_gc_job* jobs, size_t n_jobs,
                                          symgpu_mp3_gc* units, int16_t* quant, uint8_t* failed);
+/* The same over `n_threads` host threads (0 = hardware concurrency): jobs are cut into contiguous ranges of whole frames. */
+symgpu_status symgpu_mp3_entropy_run_cpu_mt(const uint8_t* md, size_t md_len, const symgpu_mp3_gc_job* jobs, size_t n_jobs,
+                                            symgpu_mp3_gc* units, int16_t* quant, uint8_t* failed, uint32_t n_threads);
 /* plan -> run -> re-plan until no job fails; results as symgpu_mp3_fe_decode_packets (a fresh stream: no state carried). */
 symgpu_status symgpu_mp3_entropy_decode_cpu(const uint8_t* data, size_t n, const symgpu_mpa_packet* packets, size_t n_packets,
                                             symgpu_mp3_gc* units, int16_t* quant, uint32_t* frame_of, size_t* n_good,

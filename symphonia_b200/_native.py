@@ -209,6 +209,8 @@ def lib():
     L.symgpu_mp3_entropy_plan.argtypes = [vp, sz, vp, sz, vp, vp, sz, psz, vp, vp, psz, vp]
     L.symgpu_mp3_entropy_run_cpu.restype = ctypes.c_int
     L.symgpu_mp3_entropy_run_cpu.argtypes = [vp, sz, vp, sz, vp, vp, vp]
+    L.symgpu_mp3_entropy_run_cpu_mt.restype = ctypes.c_int
+    L.symgpu_mp3_entropy_run_cpu_mt.argtypes = [vp, sz, vp, sz, vp, vp, vp, u32]
     L.symgpu_mp3_entropy_decode_cpu.restype = ctypes.c_int
     L.symgpu_mp3_entropy_decode_cpu.argtypes = [vp, sz, vp, sz, vp, vp, vp, psz, vp, ctypes.POINTER(u32)]
     L.symgpu_mp3_entropy_dev.restype = ctypes.c_int

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/symgpu.h"
@@ -438,6 +439,27 @@ extern "C" symgpu_status symgpu_mp3_entropy_run_cpu(const uint8_t* md, size_t md
         const uint32_t slot = j.out_index - first;
         if (decode_gc_job(j, md, hs, units + slot, quant + size_t(slot) * 576) && failed) failed[slot >> 2] = 1;
     }
+    return SYMGPU_OK;
+}
+
+extern "C" symgpu_status symgpu_mp3_entropy_run_cpu_mt(const uint8_t* md, size_t md_len, const symgpu_mp3_gc_job* jobs, size_t n_jobs,
+                                                       symgpu_mp3_gc* units, int16_t* quant, uint8_t* failed, uint32_t n_threads) {
+    if (n_jobs % 4) return SYMGPU_ERR_ARG;
+    const size_t n_frames = n_jobs / 4;
+    if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
+    n_threads = uint32_t(std::min<size_t>(n_threads, std::max<size_t>(n_frames, 1)));
+    if (n_threads <= 1) return symgpu_mp3_entropy_run_cpu(md, md_len, jobs, n_jobs, units, quant, failed);
+    host_tables();  // built before the threads start
+    std::vector<symgpu_status> status(n_threads, SYMGPU_OK);
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < n_threads; ++t)
+        pool.emplace_back([&, t] {
+            const size_t a = n_frames * t / n_threads, b = n_frames * (t + 1) / n_threads;  // whole frames: a job's slot is relative to its range's first frame
+            status[t] = symgpu_mp3_entropy_run_cpu(md, md_len, jobs + a * 4, (b - a) * 4, units + a * 4, quant + a * 4 * 576, failed ? failed + a : nullptr);
+        });
+    for (auto& th : pool) th.join();
+    for (symgpu_status s : status)
+        if (s != SYMGPU_OK) return s;
     return SYMGPU_OK;
 }
 

@@ -87,8 +87,8 @@ def entropy_plan(data, packets, bad=None):
     return md[:md_len.value], jobs[:good.value * 4], frame_of[:good.value], info[0]
 
 
-def entropy_run_cpu(md, jobs):
-    """The kernel body on the host: (units[F][2][2], quant[F][2][2][576], failed[F])."""
+def entropy_run_cpu(md, jobs, threads=1):
+    """The kernel body on the host: (units[F][2][2], quant[F][2][2][576], failed[F]); threads > 1 (0 = all cores) splits the jobs."""
     L = nat.lib()
     md = np.ascontiguousarray(md, dtype=np.uint8)
     jobs = np.ascontiguousarray(jobs, dtype=np.uint64)
@@ -96,8 +96,12 @@ def entropy_run_cpu(md, jobs):
     units = np.zeros((n_frames, 2, 2), dtype=nat.MP3_GC_DTYPE)
     quant = np.zeros((n_frames, 2, 2, 576), dtype=np.int16)
     failed = np.zeros(n_frames, dtype=np.uint8)
-    rc = L.symgpu_mp3_entropy_run_cpu(_vp(md.ctypes.data) if md.size else None, md.size, _vp(jobs.ctypes.data), len(jobs), _vp(units.ctypes.data),
-                                      _vp(quant.ctypes.data), _vp(failed.ctypes.data))
+    if threads == 1:
+        rc = L.symgpu_mp3_entropy_run_cpu(_vp(md.ctypes.data) if md.size else None, md.size, _vp(jobs.ctypes.data), len(jobs), _vp(units.ctypes.data),
+                                          _vp(quant.ctypes.data), _vp(failed.ctypes.data))
+    else:
+        rc = L.symgpu_mp3_entropy_run_cpu_mt(_vp(md.ctypes.data) if md.size else None, md.size, _vp(jobs.ctypes.data), len(jobs), _vp(units.ctypes.data),
+                                             _vp(quant.ctypes.data), _vp(failed.ctypes.data), threads)
     if rc != 0:
         raise SymgpuError(rc, "symgpu_mp3_entropy_run_cpu")
     return units, quant, failed

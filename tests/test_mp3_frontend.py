@@ -417,3 +417,14 @@ def test_the_device_bit_window_on_the_host(tmp_path):
                                                ctypes.byref(good), info.ctypes.data, ctypes.byref(rounds)) == 0
         g = good.value
         assert frame_of[:g].tolist() == want_f.tolist() and units[:g].tobytes() == want_u.tobytes() and (quant[:g] == want_q).all()
+
+
+def test_threaded_job_executor_gives_the_same_tables():
+    rng = np.random.default_rng(51)
+    frames, _ = bw.gen_stream(rng, 90, version="1", mode=1, bitrate_idx=9)
+    data, packets = _packets_of(frames[3:])  # joined late: silent jobs, scfsi re-reads across the thread cut points
+    md, jobs, frame_of, _ = frontend.entropy_plan(data, packets)
+    want = frontend.entropy_run_cpu(md, jobs)
+    for threads in (2, 3, 8, 0, 500):
+        got = frontend.entropy_run_cpu(md, jobs, threads=threads)
+        assert got[0].tobytes() == want[0].tobytes() and (got[1] == want[1]).all() and (got[2] == want[2]).all()
