@@ -656,3 +656,25 @@ def test_c_abi_tables_match_the_oracle():
         assert e.value.status == (1 if bad[7] == 0 else 2)
     with pytest.raises(sb.SymgpuError):
         pk.vorbis_setup_modes(st.vorbis_setup(rng, fault="framing")[0], ident)
+
+
+def test_mpa_a_refused_header_word_costs_four_bytes(exe, tmp_path):
+    """header.rs:77-103 + demuxer.rs:585-596: a word that passes the quick check but not the full parse (free format here) is
+    consumed whole before the hunt resumes -- so a real frame beginning inside those four bytes is lost.  (Found by mutating
+    the product: the randomised corpus did not tell "+4" from "+1" apart.)"""
+    rng = np.random.default_rng(61)
+    params = dict(version="1", layer=3, bitrate_idx=9, rate_idx=0, mode=0)
+    frames = [st.mpa_frame(rng, params, protected=False) for _ in range(8)]
+    # free format (bit-rate index 0), twice; the same behind a junk byte; Layer II at 224 kbit/s which -- with the mode bits of the
+    # following 0xff read as "mono" -- is a combination Layer II forbids.  The real frame starts at byte 3 of the refused word.
+    for lead in (b"\xff\xfb\x00", b"\xff\xfb\x02", b"\x11\xff\xfb\x00", b"\xff\xfd\xb0"):
+        for tail in (b"".join(frames), b"".join(frames[:4]) + lead + b"".join(frames[4:])):
+            data = lead + tail
+            want = _check_mpa(exe, tmp_path, data)
+            offs = [int(line.split()[1]) for line in want[1:]]
+            first_real = len(lead)
+            assert first_real not in offs and first_real + len(frames[0]) in offs  # frame 0 went with the refused word, frame 1 is found
+    # whereas a word that already fails the QUICK check costs one byte: the frame right behind it is found
+    data = b"\xff\xfb\xf0" + b"".join(frames)
+    want = _check_mpa(exe, tmp_path, data)
+    assert int(want[1].split()[1]) == 3
