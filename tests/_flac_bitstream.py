@@ -45,16 +45,16 @@ def _put_signed(w, v, bits):
         w.put(v & ((1 << bits) - 1), bits)
 
 
-def _put_residuals(w, rng, res, order, n):
+def _put_residuals(w, rng, res, order, n, force_po=None):
     big = max((abs(int(x)) for x in res[order:]), default=0) >= 1 << 13
     method = 1 if big else int(rng.integers(2))  # 4-bit parameters stop at 14: large residuals need the 5-bit form
     width = 5 if method else 4
     choices = [po for po in range(0, 9) if n % (1 << po) == 0 and (n >> po) >= max(order, 1)]
-    po = int(rng.choice(choices)) if choices else 0
+    po = (int(rng.choice(choices)) if choices else 0) if force_po is None else force_po
     w.put(method, 2), w.put(po, 4)
     per = n >> po
     for part in range(1 << po):
-        a, b = (part * per if part else order), (part + 1) * per
+        a, b = (part * per if part else min(order, per)), (part + 1) * per
         seg = [int(x) for x in res[a:b]]
         zig = [(x << 1) ^ (x >> 63) for x in seg]
         mean = (sum(zig) / len(zig)) if zig else 0
@@ -74,7 +74,7 @@ def _put_residuals(w, rng, res, order, n):
                 w.put(z & ((1 << k) - 1), k)
 
 
-def write_frame(rng, frame, subs, samples, number, sample_rate=44100, stream_bps=None):
+def write_frame(rng, frame, subs, samples, number, sample_rate=44100, stream_bps=None, lpc_precision=None, force_po=None):
     """One frame.  `subs` = the frame's sub-frame records, `samples` the global residual / warm-up array they point into."""
     n = int(subs[0]["n"])
     bps = int(frame["bits_per_sample"])
@@ -130,11 +130,11 @@ def write_frame(rng, frame, subs, samples, number, sample_rate=44100, stream_bps
             if kind == LPC:
                 coeffs = [int(v) for v in sf["coeffs"][:order]]
                 precision = max(max((v.bit_length() + 1 for v in coeffs), default=1), 1)
-                precision = min(max(precision, int(rng.integers(1, 16))), 15)
+                precision = min(max(precision, int(rng.integers(1, 16))), 15) if lpc_precision is None else lpc_precision
                 w.put(precision - 1, 4), w.put(int(sf["shift"]), 5)
                 for v in coeffs:
                     _put_signed(w, v, precision)
-            _put_residuals(w, rng, x, order, n)
+            _put_residuals(w, rng, x, order, n, force_po)
     body = w.bytes()
     frame_bytes = hdr + body
     return frame_bytes + crc16(frame_bytes).to_bytes(2, "big")

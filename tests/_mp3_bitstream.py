@@ -76,7 +76,7 @@ def _mpeg2_partition(sfc, intensity_channel, block):
     return slen, row[block], preflag
 
 
-def gen_granule_channel(rng, version, rate_idx9, budget_bits, gr, scfsi, gr0_scalefacs, intensity_channel, rich=True, like=None):
+def gen_granule_channel(rng, version, rate_idx9, budget_bits, gr, scfsi, gr0_scalefacs, intensity_channel, rich=True, like=None, force_sfc=None):
     """One granule-channel: returns a dict with the side-information fields, `bits` (a BitWriterMsb holding part 2 +
     part 3 + stuffing) and the ground truth (`scalefacs`, `quant`, `rzero`, `preflag`)."""
     mpeg1 = version == "1"
@@ -115,7 +115,7 @@ def gen_granule_channel(rng, version, rate_idx9, budget_bits, gr, scfsi, gr0_sca
                         scalefacs[i] = int(rng.integers(1 << s))
                         bits.put(scalefacs[i], s)
     else:
-        g["scalefac_compress"] = int(rng.integers(512))
+        g["scalefac_compress"] = int(rng.integers(512)) if force_sfc is None else int(force_sfc)
         slen, counts, preflag = _mpeg2_partition(g["scalefac_compress"], intensity_channel, 2 if mixed else 1 if short else 0)
         g["preflag"] = int(preflag)
         at = 0
@@ -252,7 +252,7 @@ def side_info_bytes(version, n_ch, main_data_begin, scfsi, granules):
 
 
 def gen_stream(rng, n_frames, version="1", mode=1, rate_idx=0, bitrate_idx=9, protected=False, fill=(0.3, 1.0), padding=None, rich=True,
-               pair_blocks=False):
+               pair_blocks=False, force_sfc=None, force_mode_ext=None):
     """A stream of frames with a bit reservoir.  Returns (list of frame bytes, list of per-frame truth dicts)."""
     n_ch = 1 if mode == 3 else 2
     n_gr = 2 if version == "1" else 1
@@ -265,7 +265,7 @@ def gen_stream(rng, n_frames, version="1", mode=1, rate_idx=0, bitrate_idx=9, pr
     payload = bytearray()  # the concatenated slots
     for k in range(n_frames):
         pad = int(rng.integers(2)) if padding is None else padding
-        mode_ext = int(rng.integers(4))
+        mode_ext = int(rng.integers(4)) if force_mode_ext is None else int(force_mode_ext(k))
         word = st.mpa_word(version=version, layer=3, bitrate_idx=bitrate_idx, rate_idx=rate_idx, mode=mode, mode_ext=mode_ext, padding=pad,
                            protected=protected, copyright=int(rng.integers(2)), original=int(rng.integers(2)), emphasis=int(rng.integers(4)))
         total = st.mpa_frame_len(version, 3, bitrate_idx, rate_idx, pad)
@@ -284,7 +284,8 @@ def gen_stream(rng, n_frames, version="1", mode=1, rate_idx=0, bitrate_idx=9, pr
                 for ch in range(n_ch):
                     row.append(gen_granule_channel(rng, version, rate_idx9, int(shares[gr * n_ch + ch]), gr, scfsi[ch],
                                                    granules[0][ch]["scalefacs"] if gr == 1 else None, ch == 1 and intensity, rich=rich,
-                                                   like=row[0] if (pair_blocks and ch == 1) else None))
+                                                   like=row[0] if (pair_blocks and ch == 1) else None,
+                                                   force_sfc=None if force_sfc is None else force_sfc(k, gr, ch)))
                 granules.append(row)
             md = BitWriterMsb()
             for row in granules:

@@ -208,3 +208,31 @@ def test_native_file_to_pcm(oracle):
         packetizer.flac_index(b"fLaC" + bytes([0x84]) + (10).to_bytes(3, "big") + bytes(10))  # first block is not STREAMINFO
     with pytest.raises(sb.SymgpuError):
         packetizer.flac_index(b"fLaC" + bytes([0x00]) + (34).to_bytes(3, "big") + fw.stream_info_block(4096, 4096, 44100, 2, 16, 0))  # metadata never ends
+
+
+def test_lpc_precision_code_1111_is_refused():
+    """decoder.rs:478-482: a quantised-coefficient precision of 16 bits (code 1111) is a reserved value."""
+    rng = np.random.default_rng(99)
+    frames, subs, samples = workloads.flac_batch(40, 576, seed=41, bps=16, channels=2)
+    lpc = [f for f in range(40) if any(int(subs[f * 2 + c]["type"]) == 3 for c in range(2))]
+    assert len(lpc) > 10
+    ok = [fw.write_frame(rng, frames[f], subs[f * 2:f * 2 + 2], samples, k, stream_bps=16, lpc_precision=15) for k, f in enumerate(lpc)]
+    bad = [fw.write_frame(rng, frames[f], subs[f * 2:f * 2 + 2], samples, k, stream_bps=16, lpc_precision=16) for k, f in enumerate(lpc)]
+    assert _check_against_oracle(ok, stream_bps=16)[0] == list(range(len(lpc)))
+    assert _check_against_oracle(bad, stream_bps=16)[0] == []
+
+
+def test_partition_smaller_than_the_predictor_order_is_refused():
+    """decoder.rs:548-557: the first partition holds (block >> order) - predictor order residuals; a negative count is an error,
+    as is a partition order that does not divide the block."""
+    rng = np.random.default_rng(98)
+    frames, subs, samples = workloads.flac_batch(30, 64, seed=43, bps=16, channels=1)
+    high = [f for f in range(30) if int(subs[f]["type"]) == 3 and int(subs[f]["order"]) > 4 and int(subs[f]["n"]) == 64]
+    assert len(high) >= 3
+    ok = [fw.write_frame(rng, frames[f], subs[f:f + 1], samples, k, stream_bps=16, force_po=2) for k, f in enumerate(high)]   # 16 per partition
+    bad = [fw.write_frame(rng, frames[f], subs[f:f + 1], samples, k, stream_bps=16, force_po=4) for k, f in enumerate(high)]  # 4 per partition < order
+    odd = [fw.write_frame(rng, frames[f], subs[f:f + 1], samples, k, stream_bps=16, force_po=7) for k, f in enumerate(high)]  # 64 >> 7 = 0
+    good_orders = [f for f in high if int(subs[f]["order"]) <= 16]
+    assert _check_against_oracle(ok, stream_bps=16)[0] == [k for k, f in enumerate(high) if f in good_orders]
+    assert _check_against_oracle(bad, stream_bps=16)[0] == []
+    assert _check_against_oracle(odd, stream_bps=16)[0] == []

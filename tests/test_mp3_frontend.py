@@ -428,3 +428,22 @@ def test_threaded_job_executor_gives_the_same_tables():
     for threads in (2, 3, 8, 0, 500):
         got = frontend.entropy_run_cpu(md, jobs, threads=threads)
         assert got[0].tobytes() == want[0].tobytes() and (got[1] == want[1]).all() and (got[2] == want[2]).all()
+
+
+def test_every_mpeg2_scalefac_compress_value():
+    """All 512 values of the 9-bit field, on an ordinary channel and on the intensity channel (three partition tables each, with
+    their switch points at 400 / 500 and 360 / 488), over random block types.  (A mutant moving one switch point survived the
+    randomised streams.)"""
+    rng = np.random.default_rng(81)
+    for mode in (1, 0):  # joint stereo (channel 1 is the intensity channel when the mode extension says so), plain stereo
+        frames, truth = bw.gen_stream(rng, 1024, version="2", mode=mode, bitrate_idx=12, rate_idx=0, fill=(0.2, 0.5), rich=False,
+                                      force_sfc=lambda k, gr, ch: k % 512, force_mode_ext=lambda k: 1 + 2 * (k // 512))  # intensity on, mid/side off then on
+        seen = {(t["granules"][0][1]["scalefac_compress"], bool(t["mode"] == 1 and t["mode_ext"] & 1)) for t in truth}
+        assert seen == {(v, mode == 1) for v in range(512)}
+        assert all(_run_both(frames, f"sfc sweep mode {mode}"))
+        cfe = frontend.Mp3Frontend()
+        for f, t in zip(frames, truth):
+            units, quant, _ = cfe.decode(f)
+            for ch in range(2):
+                g = t["granules"][0][ch]
+                assert [int(x) for x in units[0, ch]["scalefacs"]] == g["scalefacs"] and bool(int(units[0, ch]["flags"]) & nat.F_PREFLAG) == bool(g["preflag"])

@@ -115,6 +115,7 @@ def test_layer1_streams(version, bitrate_idx, rate_idx, mode, protected):
     ("1", 8, 0, 0, False),    # 64 kbit/s per channel: table a
     ("1", 14, 0, 1, True),    # 192 per channel at 44.1 kHz: table b, joint stereo
     ("1", 12, 1, 0, False),   # 48 kHz: table a above 80 kbit/s as well
+    ("1", 9, 0, 0, False),    # exactly 80 kbit/s per channel at 44.1 kHz: still table a (b starts above 80)
     ("1", 2, 0, 3, False),    # 48 kbit/s mono: table c
     ("1", 1, 2, 3, False),    # 32 kbit/s mono at 32 kHz: table d
     ("1", 6, 2, 1, False),    # 96 kbit/s stereo = 48 per channel at 32 kHz: table d, joint stereo bound above sblimit

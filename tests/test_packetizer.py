@@ -678,3 +678,56 @@ def test_mpa_a_refused_header_word_costs_four_bytes(exe, tmp_path):
     data = b"\xff\xfb\xf0" + b"".join(frames)
     want = _check_mpa(exe, tmp_path, data)
     assert int(want[1].split()[1]) == 3
+
+
+def test_ogg_checksum_failure_resumes_four_bytes_on(exe, tmp_path):
+    """page.rs:236-249: when a page fails its checksum the reader goes back to just behind the capture pattern that led there, so
+    a real page starting within the false page's 27 header bytes is still found.  (A surviving mutant showed the randomised
+    corpus never put a page that close behind a false capture pattern.)"""
+    rng = np.random.default_rng(71)
+    pages = st.ogg_paginate(3, _packets(rng, 30, [40, 300, 900]), rng, max_segments=6)
+    for gap in (0, 1, 7, 16, 20):
+        out = [pages[0]]
+        for pg in pages[1:]:
+            out.append(b"OggS\x00\x00" + rng.integers(0, 256, gap, dtype=np.uint8).tobytes())  # plausible version / flags: gets as far as the checksum
+            out.append(pg)
+        data = b"".join(out) + bytes(70000)
+        streams, tail = _check_ogg(exe, tmp_path, data)
+        assert len(streams[3]) == 30, gap
+
+
+def test_mpa_lame_extension_cut_by_a_short_frame(exe, tmp_path):
+    """demuxer.rs:812-820: the first 24 bytes of the LAME extension (up to the delay / padding field) are read whenever the FRAME
+    has that many bytes left, the last 12 only when it has those too.  A 48-byte frame (MPEG-2.5, 8 kbit/s at 12 kHz, mono: tag at
+    byte 13) leaves 27: delay and padding are taken, no checksum is looked for."""
+    rng = np.random.default_rng(62)
+    params = dict(version="2.5", layer=3, bitrate_idx=1, rate_idx=1, mode=3)
+    audio = [st.mpa_frame(rng, params, protected=False, padding=0) for _ in range(20)]
+    tag = st.mpa_tag_frame(rng, params, flags=0x0, lame_ext=36, delay=700, padding=900)
+    assert len(tag) == 48
+    want = _check_mpa(exe, tmp_path, tag + b"".join(audio))
+    assert "delay=1:1229:371" in want[0] and "tag=1" in want[0]
+    h = po.mpa_parse_header(int.from_bytes(tag[:4], "big"))
+    assert po.mpa_read_info_tag(tag, h)["lame"]["delay"] == 528 + 1 + 700
+    assert run(exe, "tag", tag, tmp=tmp_path)[1].endswith("lame=1 delay=1229 padding=371 peak=4194304")
+    # 72-byte stereo frame (8 kbit/s at 8 kHz), two 4-byte fields: 35 bytes left for the extension -- 24 read, 11 left over, one
+    # short of the 12 the checksum part needs: it must not be looked for (it would lie past the frame)
+    params = dict(version="2.5", layer=3, bitrate_idx=1, rate_idx=2, mode=0)
+    audio = [st.mpa_frame(rng, params, protected=False, padding=0) for _ in range(20)]
+    tag = st.mpa_tag_frame(rng, params, flags=0x3, lame_ext=36, delay=100, padding=600)
+    assert len(tag) == 72
+    want = _check_mpa(exe, tmp_path, tag + b"".join(audio))
+    assert "delay=1:629:71" in want[0]
+
+
+def test_mpa_rejected_first_frame_restarts_one_byte_on(exe, tmp_path):
+    """demuxer.rs:628-633: when the word behind the first frame candidate does not fit, the hunt restarts at the candidate's SECOND
+    byte -- a real frame starting inside the decoy's header word is found.  (Surviving mutant: restart four bytes on.)"""
+    rng = np.random.default_rng(63)
+    params = dict(version="1", layer=3, bitrate_idx=9, rate_idx=0, mode=0)
+    frames = [st.mpa_frame(rng, params, protected=False) for _ in range(6)]
+    # FF FF 90 FF: MPEG-1 Layer I, 288 kbit/s, 44.1 kHz, mono -- a 312-byte "frame" that no similar header follows
+    assert po.mpa_parse_header(0xFFFF90FF)["layer"] == 1
+    data = b"\xff\xff\x90" + b"".join(frames)
+    want = _check_mpa(exe, tmp_path, data)
+    assert int(want[1].split()[1]) == 3 and len(want) - 1 == 6
