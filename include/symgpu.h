@@ -483,6 +483,18 @@ symgpu_status symgpu_vorbis_ident_parse(const uint8_t* packet, size_t n, symgpu_
 /* Walks a setup packet to its mode list: *n_modes (1..64) and bit i of *long_block_mask = mode i uses the long block. */
 symgpu_status symgpu_vorbis_setup_modes(const uint8_t* packet, size_t n, const symgpu_vorbis_ident* ident, uint32_t* n_modes,
                                         uint64_t* long_block_mask);
+/* The decoder's reading of a setup packet (symphonia-codec-vorbis/src/lib.rs:490-770, floor.rs:455-560): counts, modes, and for
+ * every floor of type 1 the record symgpu_vorbis_floors_set takes (X list, neighbours, sort order, multiplier); floors of type
+ * 0 are reported in floor_type and left zeroed.  Codebook CONTENTS are only syntax-checked.  floors: room for 64 records. */
+typedef struct symgpu_vorbis_setup_info {   /* 160 bytes */
+    uint32_t n_codebooks, n_floors, n_residues, n_mappings, n_modes;
+    uint32_t reserved;
+    uint64_t long_block_mask;       /* bit i: mode i uses the long block                  */
+    uint8_t mode_mapping[64];       /* mapping of mode i                                  */
+    uint8_t floor_type[64];         /* 0 or 1                                             */
+} symgpu_vorbis_setup_info;
+symgpu_status symgpu_vorbis_setup_parse(const uint8_t* packet, size_t n, const symgpu_vorbis_ident* ident, symgpu_vorbis_setup_info* info,
+                                        symgpu_vorbis_floor1* floors);
 /* Durations of a run of audio packets (VorbisPacketParser::parse_next_packet_dur, :62-106): heads[i] = the first
  * byte(s) of packet i packed little-endian (two bytes always suffice: 1 type bit + at most 6 mode bits), head_len[i] =
  * how many bytes of the packet exist (0, 1 or >= 2).  dur / discard in samples.  *prev_exp carries the previous block's

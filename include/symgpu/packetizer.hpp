@@ -12,10 +12,12 @@
 //
 // Header-only C++17, no dependencies, no device code.
 #pragma once
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <vector>
 
 namespace symgpu {
@@ -946,6 +948,183 @@ inline Status vorbis_read_setup_modes(const uint8_t* p, size_t n, const VorbisId
     }
     if (!bs.read_bool() || !bs.ok()) return Status::DecodeError;  // framing
     num_modes = uint8_t(count), long_block_mask = mask;
+    return Status::Ok;
+}
+
+// ---- the decoder's view of the setup header ---------------------------------------------------------------------------
+// symphonia-codec-vorbis/src/lib.rs:490-770 (read_setup: floors, residues, mappings, modes with their cross checks),
+// floor.rs:160-201 (floor 0), :455-560 (floor 1: classes, X list, neighbours, sort order), residue.rs:73-140.
+// Everything the synthesis configuration needs EXCEPT the codebooks' contents, which are walked over with the same
+// syntax checks as above but not built (their Huffman trees and VQ tables belong to the packet decoder).
+struct VorbisFloor1Setup {
+    uint8_t multiplier;  // 1..4
+    uint8_t n_posts;     // 2..65
+    uint16_t x_list[65];
+    uint8_t low[65], high[65];   // neighbours among the earlier posts (0, 0 for the first two, as find_neighbors leaves them)
+    uint8_t sort_order[65];      // posts by ascending x (stable)
+    uint8_t partitions;
+    uint8_t partition_class[32];
+    struct Class {
+        uint8_t dimensions, subclass_bits, mainbook, subbook_used;
+        uint8_t subbooks[8];
+    } classes[16];
+};
+struct VorbisResidueSetup {
+    uint16_t type;
+    uint32_t begin, end, partition_size;
+    uint8_t classifications, classbook, max_pass;
+    uint8_t used[64];
+    uint8_t books[64][8];
+};
+struct VorbisMappingSetup {
+    uint8_t n_submaps;
+    std::vector<std::pair<uint8_t, uint8_t>> couplings;  // (magnitude channel, angle channel)
+    std::vector<uint8_t> multiplex;                      // sub-map of each channel
+    uint8_t submap_floor[16], submap_residue[16];
+};
+struct VorbisSetup {
+    uint32_t n_codebooks = 0;
+    std::vector<uint8_t> floor_type;          // 0 or 1 per floor
+    std::vector<VorbisFloor1Setup> floor1;    // per floor; zeroed for type-0 floors
+    std::vector<VorbisResidueSetup> residues;
+    std::vector<VorbisMappingSetup> mappings;
+    std::vector<std::pair<bool, uint8_t>> modes;  // (long block, mapping)
+};
+
+inline Status vorbis_read_setup(const uint8_t* p, size_t n, const VorbisIdent& id, VorbisSetup& out) {
+    if (n < 7) return Status::EndOfStream;
+    if (p[0] != 5 || std::memcmp(p + 1, "vorbis", 6) != 0) return Status::DecodeError;
+    BitReaderRtl bs(p + 7, n - 7);
+    out = VorbisSetup{};
+    out.n_codebooks = bs.read(8) + 1;
+    for (uint32_t i = 0; i < out.n_codebooks; ++i)
+        if (!detail::vorbis_skip_codebook(bs)) return Status::DecodeError;
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i)
+        if (bs.read(16) != 0 || !bs.ok()) return Status::DecodeError;
+    const uint8_t max_book = uint8_t(out.n_codebooks);  // `codebooks.len() as u8` (lib.rs:517): 256 codebooks wrap to 0
+    // ---- floors
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i) {
+        const uint32_t type = bs.read(16);
+        if (!bs.ok() || type > 1) return Status::DecodeError;
+        VorbisFloor1Setup f{};
+        if (type == 0) {
+            bs.ignore(8 + 16 + 16 + 6 + 8);
+            for (uint32_t k = 0, books = bs.read(4) + 1; k < books; ++k)
+                if (bs.read(8) >= max_book || !bs.ok()) return Status::DecodeError;
+        } else {
+            f.partitions = uint8_t(bs.read(5));
+            if (f.partitions) {
+                uint8_t max_class = 0;
+                for (int k = 0; k < f.partitions; ++k) f.partition_class[k] = uint8_t(bs.read(4)), max_class = std::max(max_class, f.partition_class[k]);
+                for (int c = 0; c <= max_class; ++c) {
+                    auto& cl = f.classes[c];
+                    cl.dimensions = uint8_t(bs.read(3) + 1), cl.subclass_bits = uint8_t(bs.read(2));
+                    if (cl.subclass_bits) {
+                        cl.mainbook = uint8_t(bs.read(8));
+                        if (cl.mainbook >= max_book) return Status::DecodeError;
+                    }
+                    for (int k = 0; k < (1 << cl.subclass_bits); ++k) {
+                        uint8_t book = uint8_t(bs.read(8));
+                        if (book > 0) {  // 0 = no codebook for this sub-class; otherwise the number minus one
+                            if (--book >= max_book) return Status::DecodeError;
+                            cl.subbook_used |= uint8_t(1 << k);
+                        }
+                        cl.subbooks[k] = book;
+                    }
+                }
+            }
+            f.multiplier = uint8_t(bs.read(2) + 1);
+            const uint32_t rangebits = bs.read(4);
+            if (!bs.ok()) return Status::DecodeError;
+            int np = 0;
+            f.x_list[np++] = 0, f.x_list[np++] = uint16_t(1u << rangebits);
+            for (int k = 0; k < f.partitions; ++k) {
+                const int dims = f.classes[f.partition_class[k]].dimensions;
+                if (np + dims > 65) return Status::DecodeError;
+                for (int d = 0; d < dims; ++d) {
+                    const uint32_t x = bs.read(rangebits);
+                    // every READ element must be new among the read ones; the two implied ends are not in that set
+                    // (floor.rs:519-536 inserts only what it reads)
+                    for (int e = 2; e < np; ++e)
+                        if (f.x_list[e] == x) return Status::DecodeError;
+                    f.x_list[np++] = uint16_t(x);
+                }
+            }
+            if (!bs.ok()) return Status::DecodeError;
+            f.n_posts = uint8_t(np);
+            for (int i2 = 0; i2 < np; ++i2) {  // floor.rs:748-773
+                uint32_t lo = 0, hi = 0xffffffffu;
+                for (int e = 0; e < i2; ++e) {
+                    const uint32_t xv = f.x_list[e];
+                    if (xv > lo && xv < f.x_list[i2]) lo = xv, f.low[i2] = uint8_t(e);
+                    if (xv < hi && xv > f.x_list[i2]) hi = xv, f.high[i2] = uint8_t(e);
+                }
+                f.sort_order[i2] = uint8_t(i2);
+            }
+            std::stable_sort(f.sort_order, f.sort_order + np, [&](uint8_t a, uint8_t b) { return f.x_list[a] < f.x_list[b]; });
+        }
+        out.floor_type.push_back(uint8_t(type)), out.floor1.push_back(f);
+    }
+    // ---- residues
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i) {
+        VorbisResidueSetup r{};
+        r.type = uint16_t(bs.read(16));
+        if (!bs.ok() || r.type > 2) return Status::DecodeError;
+        r.begin = bs.read(24), r.end = bs.read(24), r.partition_size = bs.read(24) + 1;
+        r.classifications = uint8_t(bs.read(6) + 1), r.classbook = uint8_t(bs.read(8));
+        if (!bs.ok() || r.classbook >= max_book || r.end < r.begin) return Status::DecodeError;
+        for (int c = 0; c < r.classifications; ++c) {
+            const uint32_t low = bs.read(3);
+            r.used[c] = uint8_t((bs.read_bool() ? bs.read(5) << 3 : 0) | low);
+        }
+        for (int c = 0; c < r.classifications; ++c)
+            for (int j = 0; j < 8; ++j)
+                if (r.used[c] & (1 << j)) {
+                    r.books[c][j] = uint8_t(bs.read(8));
+                    if (!bs.ok() || r.books[c][j] == 0 || r.books[c][j] >= max_book) return Status::DecodeError;
+                    r.max_pass = std::max<uint8_t>(r.max_pass, uint8_t(j));
+                }
+        if (!bs.ok()) return Status::DecodeError;
+        out.residues.push_back(r);
+    }
+    // ---- mappings
+    const uint8_t max_floor = uint8_t(out.floor_type.size()), max_residue = uint8_t(out.residues.size());
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i) {
+        if (bs.read(16) != 0 || !bs.ok()) return Status::DecodeError;
+        VorbisMappingSetup m{};
+        m.n_submaps = uint8_t(bs.read_bool() ? bs.read(4) + 1 : 1);
+        if (bs.read_bool()) {
+            const uint32_t steps = bs.read(8) + 1, width = vorbis_ilog(uint32_t(id.n_channels) - 1), max_ch = uint32_t(id.n_channels) - 1;
+            for (uint32_t k = 0; k < steps; ++k) {
+                const uint32_t mag = bs.read(width) & 0xff, ang = bs.read(width) & 0xff;
+                if (!bs.ok() || mag == ang || mag > max_ch || ang > max_ch) return Status::DecodeError;
+                m.couplings.emplace_back(uint8_t(mag), uint8_t(ang));
+            }
+        }
+        if (bs.read(2) != 0 || !bs.ok()) return Status::DecodeError;
+        m.multiplex.assign(id.n_channels, 0);
+        if (m.n_submaps > 1)
+            for (int c = 0; c < id.n_channels; ++c) {
+                m.multiplex[c] = uint8_t(bs.read(4));
+                if (!bs.ok() || m.multiplex[c] >= m.n_submaps) return Status::DecodeError;
+            }
+        for (int k = 0; k < m.n_submaps; ++k) {
+            bs.read(8);
+            m.submap_floor[k] = uint8_t(bs.read(8)), m.submap_residue[k] = uint8_t(bs.read(8));
+            if (!bs.ok() || m.submap_floor[k] >= max_floor) return Status::DecodeError;
+            if (m.submap_residue[k] >= max_residue) return Status::DecodeError;
+        }
+        out.mappings.push_back(std::move(m));
+    }
+    // ---- modes
+    const uint8_t max_mapping = uint8_t(out.mappings.size());
+    for (uint32_t i = 0, count = bs.read(6) + 1; i < count; ++i) {
+        const bool flag = bs.read_bool();
+        const uint32_t window = bs.read(16), transform = bs.read(16), mapping = bs.read(8);
+        if (!bs.ok() || window != 0 || transform != 0 || mapping >= max_mapping) return Status::DecodeError;
+        out.modes.emplace_back(flag, uint8_t(mapping));
+    }
+    if (!bs.read_bool() || !bs.ok()) return Status::DecodeError;
     return Status::Ok;
 }
 

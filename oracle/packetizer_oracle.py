@@ -797,3 +797,144 @@ def vorbis_unpack_xiph_laced(extradata):
     if len(rest) == 0 or lengths[0] + lengths[1] > len(rest):
         raise ReaderError(DECODE, "lengths")
     return rest[:lengths[0]], rest[lengths[0] + lengths[1]:]
+
+
+# ------------------------------------------------------------------------------------------------ Vorbis setup, decoder view
+# symphonia-codec-vorbis/src/lib.rs:490-770, floor.rs:160-201 / :455-560 / :748-773, residue.rs:73-140.  Codebook contents are
+# walked with the syntax checks of the mapper (above), not built.
+
+def _find_neighbors(vec, x):
+    """floor.rs:748-773."""
+    bound = vec[x]
+    low, high = 0, 0xFFFFFFFF
+    res = [0, 0]
+    for i, xv in enumerate(vec[:x]):
+        if low < xv < bound:
+            low, res[0] = xv, i
+        if bound < xv < high:
+            high, res[1] = xv, i
+    return res
+
+
+def vorbis_read_setup(buf, ident):
+    """Returns dict(n_codebooks, floors [dict], n_residues, mappings [dict], modes [(flag, mapping)]) or raises ReaderError."""
+    r = Reader(buf)
+    if r.read_u8() != 5:
+        raise ReaderError(DECODE, "packet type")
+    if r.read_exact(6) != b"vorbis":
+        raise ReaderError(DECODE, "signature")
+    bs = BitsRtl(buf[7:])
+    n_books = bs.read(8) + 1
+    for _ in range(n_books):
+        _skip_codebook(bs)
+    for _ in range(bs.read(6) + 1):
+        if bs.read(16) != 0:
+            raise ReaderError(DECODE, "time domain transform")
+    max_book = n_books & 0xFF
+    floors = []
+    for _ in range(bs.read(6) + 1):
+        kind = bs.read(16)
+        if kind == 0:
+            bs.ignore(8 + 16 + 16 + 6 + 8)
+            for _ in range(bs.read(4) + 1):
+                if bs.read(8) >= max_book:
+                    raise ReaderError(DECODE, "floor0 book")
+            floors.append(dict(type=0))
+        elif kind == 1:
+            parts = bs.read(5)
+            classes = [bs.read(4) for _ in range(parts)]
+            dims = {}
+            if parts:
+                for c in range(max(classes) + 1):
+                    dims[c] = bs.read(3) + 1
+                    sub = bs.read(2)
+                    if sub and bs.read(8) >= max_book:
+                        raise ReaderError(DECODE, "floor1 master book")
+                    for _ in range(1 << sub):
+                        book = bs.read(8)
+                        if book > 0 and book - 1 >= max_book:
+                            raise ReaderError(DECODE, "floor1 sub book")
+            mult = bs.read(2) + 1
+            rangebits = bs.read(4)
+            x_list = [0, 1 << rangebits]
+            seen = set()
+            for c in classes:
+                if len(x_list) + dims[c] > 65:
+                    raise ReaderError(DECODE, "x_list too long")
+                for _ in range(dims[c]):
+                    x = bs.read(rangebits)
+                    if x in seen:
+                        raise ReaderError(DECODE, "x_list not unique")
+                    seen.add(x)
+                    x_list.append(x)
+            nb = [_find_neighbors(x_list, i) for i in range(len(x_list))]
+            order = sorted(range(len(x_list)), key=lambda i: x_list[i])
+            floors.append(dict(type=1, multiplier=mult, x_list=x_list, low=[a for a, _ in nb], high=[b for _, b in nb], sort_order=order))
+        else:
+            raise ReaderError(DECODE, "floor type")
+    n_res = bs.read(6) + 1
+    for _ in range(n_res):
+        if bs.read(16) > 2:
+            raise ReaderError(DECODE, "residue type")
+        begin, end = bs.read(24), bs.read(24)
+        bs.read(24)
+        ncls = bs.read(6) + 1
+        if bs.read(8) >= max_book:
+            raise ReaderError(DECODE, "classbook")
+        if end < begin:
+            raise ReaderError(DECODE, "residue range")
+        used = []
+        for _ in range(ncls):
+            low = bs.read(3)
+            high = bs.read(5) if bs.read_bool() else 0
+            used.append(((high << 3) & 0xFF) | low)
+        for u in used:
+            for j in range(8):
+                if u >> j & 1:
+                    book = bs.read(8)
+                    if book == 0 or book >= max_book:
+                        raise ReaderError(DECODE, "residue book")
+    mappings = []
+    n_floors = len(floors) & 0xFF
+    for _ in range(bs.read(6) + 1):
+        if bs.read(16) != 0:
+            raise ReaderError(DECODE, "mapping type")
+        submaps = bs.read(4) + 1 if bs.read_bool() else 1
+        couplings = []
+        if bs.read_bool():
+            steps = bs.read(8) + 1
+            width = ilog(ident["n_channels"] - 1)
+            for _ in range(steps):
+                mag, ang = bs.read(width), bs.read(width)
+                if mag == ang or mag > ident["n_channels"] - 1 or ang > ident["n_channels"] - 1:
+                    raise ReaderError(DECODE, "coupling")
+                couplings.append((mag, ang))
+        if bs.read(2) != 0:
+            raise ReaderError(DECODE, "reserved")
+        mux = [0] * ident["n_channels"]
+        if submaps > 1:
+            for c in range(ident["n_channels"]):
+                mux[c] = bs.read(4)
+                if mux[c] >= submaps:
+                    raise ReaderError(DECODE, "multiplex")
+        sm = []
+        for _ in range(submaps):
+            bs.read(8)
+            fl = bs.read(8)
+            if fl >= n_floors:
+                raise ReaderError(DECODE, "submap floor")
+            rs = bs.read(8)
+            if rs >= n_res:
+                raise ReaderError(DECODE, "submap residue")
+            sm.append((fl, rs))
+        mappings.append(dict(couplings=couplings, multiplex=mux, submaps=sm))
+    modes = []
+    for _ in range(bs.read(6) + 1):
+        flag = bs.read_bool()
+        window, transform, mapping = bs.read(16), bs.read(16), bs.read(8)
+        if window != 0 or transform != 0 or mapping >= len(mappings):
+            raise ReaderError(DECODE, "mode")
+        modes.append((flag, mapping))
+    if not bs.read_bool():
+        raise ReaderError(DECODE, "framing")
+    return dict(n_codebooks=n_books, floors=floors, n_residues=n_res, mappings=mappings, modes=modes)

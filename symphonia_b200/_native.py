@@ -91,6 +91,9 @@ FLAC_PACKET_DTYPE = np.dtype([("offset", "<u8"), ("ts", "<u8"), ("size", "<u4"),
 assert FLAC_STREAM_INFO_DTYPE.itemsize == 56 and FLAC_PACKET_DTYPE.itemsize == 24
 MP3_FILE_DTYPE = np.dtype([("data", "<u8"), ("n", "<u8"), ("packets", "<u8"), ("n_packets", "<u8"), ("stream", "<u4"), ("reserved", "<u4")])
 assert MP3_FILE_DTYPE.itemsize == 40
+VORBIS_SETUP_INFO_DTYPE = np.dtype([("n_codebooks", "<u4"), ("n_floors", "<u4"), ("n_residues", "<u4"), ("n_mappings", "<u4"), ("n_modes", "<u4"),
+                                    ("reserved", "<u4"), ("long_block_mask", "<u8"), ("mode_mapping", "u1", (64,)), ("floor_type", "u1", (64,))])
+assert VORBIS_SETUP_INFO_DTYPE.itemsize == 160
 assert PIECE_DTYPE.itemsize == 16 and OGG_PACKET_DTYPE.itemsize == 40 and VORBIS_IDENT_DTYPE.itemsize == 8
 AAC_ONLY_LONG, AAC_LONG_START, AAC_EIGHT_SHORT, AAC_LONG_STOP = 0, 1, 2, 3
 
@@ -193,6 +196,8 @@ def lib():
     L.symgpu_vorbis_ident_parse.argtypes = [vp, sz, vp]
     L.symgpu_vorbis_setup_modes.restype = ctypes.c_int
     L.symgpu_vorbis_setup_modes.argtypes = [vp, sz, vp, ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_uint64)]
+    L.symgpu_vorbis_setup_parse.restype = ctypes.c_int
+    L.symgpu_vorbis_setup_parse.argtypes = [vp, sz, vp, vp, vp]
     L.symgpu_vorbis_packet_durations.restype = ctypes.c_int
     L.symgpu_vorbis_packet_durations.argtypes = [vp, u32, ctypes.c_uint64, vp, vp, sz, vp, vp, vp]
     L.symgpu_mp3_fe_create.restype = ctypes.c_int

@@ -114,6 +114,32 @@ extern "C" symgpu_status symgpu_vorbis_setup_modes(const uint8_t* packet, size_t
     return SYMGPU_OK;
 }
 
+extern "C" symgpu_status symgpu_vorbis_setup_parse(const uint8_t* packet, size_t n, const symgpu_vorbis_ident* ident, symgpu_vorbis_setup_info* info,
+                                                   symgpu_vorbis_floor1* floors) {
+    if (!packet || !info || !floors || !ident_ok(ident)) return SYMGPU_ERR_ARG;
+    const VorbisIdent id{ident->channels, ident->sample_rate, ident->bs0_exp, ident->bs1_exp};
+    VorbisSetup st;
+    if (vorbis_read_setup(packet, n, id, st) != Status::Ok) return SYMGPU_ERR_DECODE;
+    *info = symgpu_vorbis_setup_info{};
+    info->n_codebooks = st.n_codebooks, info->n_floors = uint32_t(st.floor_type.size()), info->n_residues = uint32_t(st.residues.size());
+    info->n_mappings = uint32_t(st.mappings.size()), info->n_modes = uint32_t(st.modes.size());
+    for (size_t i = 0; i < st.modes.size(); ++i) {
+        if (st.modes[i].first) info->long_block_mask |= uint64_t(1) << i;
+        info->mode_mapping[i] = st.modes[i].second;
+    }
+    for (size_t i = 0; i < st.floor_type.size(); ++i) {
+        info->floor_type[i] = st.floor_type[i];
+        symgpu_vorbis_floor1& o = floors[i];
+        std::memset(&o, 0, sizeof o);
+        if (st.floor_type[i] != 1) continue;
+        const VorbisFloor1Setup& f = st.floor1[i];
+        o.multiplier = f.multiplier, o.n_posts = f.n_posts;
+        std::memcpy(o.x_list, f.x_list, sizeof o.x_list), std::memcpy(o.low, f.low, 65), std::memcpy(o.high, f.high, 65), std::memcpy(o.sort_order, f.sort_order, 65);
+    }
+    return SYMGPU_OK;
+}
+static_assert(sizeof(symgpu_vorbis_setup_info) == 160, "record sizes are ABI");
+
 extern "C" symgpu_status symgpu_vorbis_packet_durations(const symgpu_vorbis_ident* ident, uint32_t n_modes, uint64_t long_block_mask,
                                                         const uint16_t* heads, const uint8_t* head_len, size_t n_packets, uint8_t* prev_exp,
                                                         uint32_t* dur, uint32_t* discard) {

@@ -111,3 +111,14 @@ def flac_index(data):
     if n.value:
         _check(L.symgpu_flac_index(p, a.size, _vp(info.ctypes.data), _vp(packets.ctypes.data), n.value, ctypes.byref(n)), "symgpu_flac_index")
     return info[0], packets
+
+
+def vorbis_setup_parse(packet, ident):
+    """(info record, floors [n_floors] VORBIS_FLOOR1_DTYPE): the decoder's reading of a setup packet; floors of type 1 are ready for
+    Engine.vorbis_floors_set."""
+    a, p = _buf(packet)
+    idb = np.array([ident], dtype=nat.VORBIS_IDENT_DTYPE)
+    info = np.zeros(1, dtype=nat.VORBIS_SETUP_INFO_DTYPE)
+    floors = np.zeros(64, dtype=nat.VORBIS_FLOOR1_DTYPE)
+    _check(nat.lib().symgpu_vorbis_setup_parse(p, a.size, _vp(idb.ctypes.data), _vp(info.ctypes.data), _vp(floors.ctypes.data)), "symgpu_vorbis_setup_parse")
+    return info[0], floors[:int(info[0]["n_floors"])]

@@ -401,3 +401,126 @@ def vorbis_audio_packet(rng, n_modes, mode=None, n=None):
     w.put(int(rng.integers(1 << 30)), 30)
     body = w.bytes()
     return body + rng.integers(0, 256, int(rng.integers(0, 400)) if n is None else n, dtype=np.uint8).tobytes(), mode
+
+
+def vorbis_setup_valid(rng, channels=2, bs_exp=(8, 11), n_codebooks=None, floor_types=None, fault=None):
+    """A setup header a DECODER accepts (Vorbis I 4.2.4 with every cross reference in range: codebook numbers, floor /
+    residue / mapping indices, distinct X positions, distinct coupled channels), and what it says.  `fault` breaks one
+    cross reference.  Returns (packet, truth dict)."""
+    w = BitWriterRtl()
+    n_books = int(rng.integers(2, 10)) if n_codebooks is None else n_codebooks
+    w.put(n_books - 1, 8)
+    for _ in range(n_books):
+        _put_codebook(w, rng)
+    w.put(0, 6), w.put(0, 16)
+    n_floors = int(rng.integers(1, 5)) if floor_types is None else len(floor_types)
+    w.put(n_floors - 1, 6)
+    floors = []
+    for fi in range(n_floors):
+        kind = (int(rng.integers(5) > 0) if floor_types is None else floor_types[fi])
+        w.put(kind, 16)
+        if kind == 0:
+            w.put(int(rng.integers(256)), 8), w.put(int(rng.integers(65536)), 16), w.put(int(rng.integers(65536)), 16)
+            w.put(int(rng.integers(64)), 6), w.put(int(rng.integers(256)), 8)
+            books = int(rng.integers(1, 17))
+            w.put(books - 1, 4)
+            for k in range(books):
+                w.put(n_books if (fault == "floor0_book" and fi == 0 and k == 0) else int(rng.integers(n_books)), 8)
+            floors.append(dict(type=0))
+            continue
+        rangebits = int(rng.integers(6, 13))
+        parts = int(rng.integers(0, 12))
+        classes = [int(rng.integers(0, 5)) for _ in range(parts)]
+        dims = {c: int(rng.integers(1, 5)) for c in range(max(classes) + 1)} if parts else {}
+        while 2 + sum(dims[c] for c in classes) > min(65, (1 << rangebits) - 1):
+            classes.pop()
+            parts -= 1
+        w.put(parts, 5)
+        for c in classes:
+            w.put(c, 4)
+        if parts:
+            for c in range(max(classes) + 1):
+                sub = int(rng.integers(4))
+                w.put(dims[c] - 1, 3), w.put(sub, 2)
+                if sub:
+                    w.put(n_books if (fault == "floor1_mainbook" and fi == 0 and c == 0) else int(rng.integers(n_books)), 8)
+                for _ in range(1 << sub):
+                    w.put(int(rng.integers(0, n_books + 1)), 8)  # 0 = none, else book + 1
+        mult = int(rng.integers(1, 5))
+        w.put(mult - 1, 2), w.put(rangebits, 4)
+        n_x = sum(dims[c] for c in classes)
+        xs = [int(v) for v in rng.choice(np.arange(1, 1 << rangebits), size=n_x, replace=False)]
+        if fault == "floor1_duplicate_x" and fi == 0 and n_x >= 2:
+            xs[-1] = xs[0]
+        for x in xs:
+            w.put(x, rangebits)
+        floors.append(dict(type=1, multiplier=mult, x_list=[0, 1 << rangebits] + xs, fault_applicable=n_x >= 2))
+    n_res = int(rng.integers(1, 4))
+    w.put(n_res - 1, 6)
+    for ri in range(n_res):
+        w.put(int(rng.integers(3)) if not (fault == "residue_type" and ri == 0) else 3, 16)
+        begin = int(rng.integers(0, 1000))
+        w.put(begin, 24), w.put(begin + int(rng.integers(0, 2000)) if not (fault == "residue_range" and ri == 0) else max(begin - 1, 0), 24)
+        w.put(int(rng.integers(1, 64)), 24)
+        ncls = int(rng.integers(1, 9))
+        w.put(ncls - 1, 6), w.put(int(rng.integers(n_books)), 8)
+        used = []
+        for _ in range(ncls):
+            low, high = int(rng.integers(8)), (int(rng.integers(32)) if rng.integers(2) else None)
+            w.put(low, 3)
+            if high is None:
+                w.put(0, 1)
+            else:
+                w.put(1, 1), w.put(high, 5)
+            used.append(((high or 0) << 3) | low)
+        first = True
+        for u in used:
+            for j in range(8):
+                if u >> j & 1:
+                    w.put(0 if (fault == "residue_book_zero" and ri == 0 and first) else int(rng.integers(1, n_books)), 8)
+                    first = False
+    n_map = int(rng.integers(1, 4))
+    w.put(n_map - 1, 6)
+    mappings = []
+    for mi in range(n_map):
+        w.put(0, 16)
+        submaps = int(rng.integers(1, 4)) if channels > 1 else 1
+        if submaps > 1:
+            w.put(1, 1), w.put(submaps - 1, 4)
+        else:
+            w.put(0, 1)
+        couplings = []
+        if channels > 1 and rng.integers(2):
+            steps = int(rng.integers(1, 4))
+            w.put(1, 1), w.put(steps - 1, 8)
+            width = _ilog(channels - 1)
+            for k in range(steps):
+                a, b = (int(v) for v in rng.choice(channels, size=2, replace=False))
+                if fault == "coupling_same" and mi == 0 and k == 0:
+                    b = a
+                w.put(a, width), w.put(b, width)
+                couplings.append((a, b))
+        else:
+            w.put(0, 1)
+        w.put(0, 2)
+        mux = [0] * channels
+        if submaps > 1:
+            for c in range(channels):
+                mux[c] = int(rng.integers(submaps)) if not (fault == "mux" and mi == 0 and c == 0) else submaps
+                w.put(mux[c], 4)
+        sm = []
+        for k in range(submaps):
+            fl = int(rng.integers(n_floors)) if not (fault == "submap_floor" and mi == 0 and k == 0) else n_floors
+            rs = int(rng.integers(n_res)) if not (fault == "submap_residue" and mi == 0 and k == 0) else n_res
+            w.put(int(rng.integers(256)), 8), w.put(fl, 8), w.put(rs, 8)
+            sm.append((fl, rs))
+        mappings.append(dict(couplings=couplings, multiplex=mux, submaps=sm))
+    n_modes = int(rng.integers(1, 6))
+    w.put(n_modes - 1, 6)
+    modes = []
+    for k in range(n_modes):
+        flag, mp = int(rng.integers(2)), (int(rng.integers(n_map)) if not (fault == "mode_mapping" and k == 0) else n_map)
+        w.put(flag, 1), w.put(0, 16), w.put(0, 16), w.put(mp, 8)
+        modes.append((bool(flag), mp))
+    w.put(1, 1)
+    return b"\x05vorbis" + w.bytes(), dict(n_codebooks=n_books, floors=floors, n_residues=n_res, mappings=mappings, modes=modes)

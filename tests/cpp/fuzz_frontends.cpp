@@ -76,6 +76,12 @@ static void run_all(const std::vector<uint8_t>& d) {
         uint8_t modes;
         uint64_t mask;
         vorbis_read_setup_modes(p, n, id, modes, mask);
+        VorbisSetup full;
+        vorbis_read_setup(p, n, id, full);
+        symgpu_vorbis_ident cid{44100, 2, 8, 11, 0};
+        symgpu_vorbis_setup_info sinfo;
+        std::vector<symgpu_vorbis_floor1> fl(64);
+        symgpu_vorbis_setup_parse(p, n, &cid, &sinfo, fl.data());
         Piece a, b;
         vorbis_unpack_xiph_laced(p, n, a, b);
         symgpu_flac_stream_info si;

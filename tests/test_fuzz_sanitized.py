@@ -30,6 +30,7 @@ def _seeds(rng):
     pk = [ident, b"\x03vorbis" + bytes(30), setup] + [st.vorbis_audio_packet(rng, len(modes))[0] for _ in range(30)]
     seeds["ogg"] = b"".join(st.ogg_paginate(9, pk[:1], rng, eos=False) + st.ogg_paginate(9, pk[1:], rng, max_segments=20, first_sequence=1, bos=False))
     seeds["vsetup"] = setup
+    seeds["vsetup_valid"] = st.vorbis_setup_valid(rng, channels=2)[0]
     frames, subs, samples = workloads.flac_batch(8, 576, seed=3, bps=16, channels=2)
     order = [f for f in range(8) if f % 7] + [0]
     fp = [fw.write_frame(rng, frames[f], subs[int(frames[f]["first_subframe"]):int(frames[f]["first_subframe"]) + 2], samples, k, stream_bps=16)
@@ -54,4 +55,4 @@ def test_parsers_under_address_and_ub_sanitizers(tmp_path):
     env = dict(os.environ, FUZZ_ITERS="250", ASAN_OPTIONS="detect_leaks=1:abort_on_error=1")
     res = subprocess.run([exe] + paths, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
-    assert "no sanitizer report" in res.stdout and "2510 inputs" in res.stdout
+    assert "no sanitizer report" in res.stdout and "2761 inputs" in res.stdout

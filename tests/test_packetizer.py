@@ -731,3 +731,95 @@ def test_mpa_rejected_first_frame_restarts_one_byte_on(exe, tmp_path):
     data = b"\xff\xff\x90" + b"".join(frames)
     want = _check_mpa(exe, tmp_path, data)
     assert int(want[1].split()[1]) == 3 and len(want) - 1 == 6
+
+
+# ------------------------------------------------------------------------------------------- Vorbis setup, the decoder's reading
+
+def _setup_expect(setup, ident_pkt):
+    idh = po.vorbis_read_ident(ident_pkt)
+    try:
+        return po.vorbis_read_setup(setup, idh)
+    except po.ReaderError:
+        return None
+
+
+def test_vorbis_setup_to_floor_configurations():
+    import symphonia_b200 as sb
+    from symphonia_b200 import _native as nat
+    from symphonia_b200 import packetizer as pk
+    from symphonia_b200 import workloads
+    rng = np.random.default_rng(91)
+    accepted = 0
+    for trial in range(120):
+        ch = int(rng.integers(1, 7))
+        ident_pkt = st.vorbis_ident(channels=ch)
+        ident = pk.vorbis_ident(ident_pkt)
+        setup, truth = st.vorbis_setup_valid(rng, channels=ch)
+        want = _setup_expect(setup, ident_pkt)
+        assert want is not None, trial
+        info, floors = pk.vorbis_setup_parse(setup, ident)
+        accepted += 1
+        assert (int(info["n_codebooks"]), int(info["n_floors"]), int(info["n_residues"]), int(info["n_mappings"]), int(info["n_modes"])) == \
+            (truth["n_codebooks"], len(truth["floors"]), truth["n_residues"], len(truth["mappings"]), len(truth["modes"]))
+        assert [bool(int(info["long_block_mask"]) >> i & 1) for i in range(len(truth["modes"]))] == [f for f, _ in truth["modes"]]
+        assert [int(x) for x in info["mode_mapping"][:len(truth["modes"])]] == [m for _, m in truth["modes"]] == [m for _, m in want["modes"]]
+        assert want["mappings"] == truth["mappings"]
+        for fi, (t, w) in enumerate(zip(truth["floors"], want["floors"])):
+            assert int(info["floor_type"][fi]) == t["type"] == w["type"]
+            f = floors[fi]
+            if t["type"] == 0:
+                assert int(f["n_posts"]) == 0
+                continue
+            n = len(t["x_list"])
+            assert (int(f["multiplier"]), int(f["n_posts"])) == (t["multiplier"], n) and [int(x) for x in f["x_list"][:n]] == t["x_list"] == w["x_list"]
+            assert [int(x) for x in f["low"][:n]] == w["low"] and [int(x) for x in f["high"][:n]] == w["high"] and [int(x) for x in f["sort_order"][:n]] == w["sort_order"]
+            # the same record the synthetic workloads build from an X list (their own statement of floor.rs:546-560)
+            mine = workloads.make_floor1_setup(t["x_list"], t["multiplier"])
+            assert f.tobytes() == mine.tobytes()
+            # neighbours by the Vorbis I definition (9.2.4 / 9.2.5), written out directly
+            for i in range(2, n):
+                below = [k for k in range(i) if t["x_list"][k] < t["x_list"][i]]
+                above = [k for k in range(i) if t["x_list"][k] > t["x_list"][i]]
+                assert int(f["low"][i]) == max(below, key=lambda k: t["x_list"][k]) and int(f["high"][i]) == min(above, key=lambda k: t["x_list"][k])
+    assert accepted == 120
+    # every broken cross reference is refused, by both
+    refused = 0
+    for fault in ("floor0_book", "floor1_mainbook", "floor1_duplicate_x", "residue_type", "residue_range", "residue_book_zero", "coupling_same", "mux",
+                  "submap_floor", "submap_residue", "mode_mapping"):
+        for _ in range(6):
+            ident_pkt = st.vorbis_ident(channels=3)
+            setup, truth = st.vorbis_setup_valid(rng, channels=3, fault=fault, floor_types=[0, 1, 1] if fault.startswith("floor") else None)
+            want = _setup_expect(setup, ident_pkt)
+            try:
+                pk.vorbis_setup_parse(setup, pk.vorbis_ident(ident_pkt))
+                got_ok = True
+            except sb.SymgpuError as e:
+                assert e.status == 1
+                got_ok = False
+            assert got_ok == (want is not None), fault
+            refused += not got_ok
+    assert refused > 40  # (a fault that needs a feature the random header did not draw leaves the header valid)
+    # the mapper-level walk accepts what the decoder-level reading refuses: it only needs the mode list
+    setup, _ = st.vorbis_setup_valid(rng, channels=2, fault="mode_mapping")
+    assert pk.vorbis_setup_modes(setup, pk.vorbis_ident(st.vorbis_ident(channels=2)))[0] >= 1
+    # 200 single-bit hits and cuts: same accept / refuse decision
+    ident_pkt = st.vorbis_ident(channels=2)
+    ident = pk.vorbis_ident(ident_pkt)
+    setup, _ = st.vorbis_setup_valid(rng, channels=2)
+    for k in range(200):
+        hit = bytearray(setup)
+        if k % 4 == 3:
+            hit = hit[:int(rng.integers(8, len(hit)))]
+        else:
+            hit[int(rng.integers(7, len(hit)))] ^= 1 << int(rng.integers(8))
+        want = _setup_expect(bytes(hit), ident_pkt)
+        try:
+            info, floors = pk.vorbis_setup_parse(bytes(hit), ident)
+            assert want is not None, k
+            assert int(info["n_modes"]) == len(want["modes"]) and int(info["n_floors"]) == len(want["floors"])
+            for fi, w in enumerate(want["floors"]):
+                if w["type"] == 1:
+                    n = len(w["x_list"])
+                    assert [int(x) for x in floors[fi]["x_list"][:n]] == w["x_list"] and [int(x) for x in floors[fi]["sort_order"][:n]] == w["sort_order"]
+        except sb.SymgpuError:
+            assert want is None, k
