@@ -172,3 +172,39 @@ def test_cpp_decoder_on_real_files(tmp_path, oracle):
         res = subprocess.run([exe, "file", str(layer), str(inp), str(outp)], capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stdout + res.stderr
         assert outp.read_bytes() == expect, layer
+
+
+# ------------------------------------------------------------------------------------------- the one-call file decoder
+
+def _decode_expect(oracle, data, fmt):
+    from symphonia_b200 import decode
+    layer, payload, runs, spans, rate, channels, total = decode.mpeg_audio_plan(data)
+    if layer == 3:
+        rc, pcm, _ = _oracle.mp3_batch(oracle, payload[0], _spectra(payload[1]), runs, 1)
+    else:
+        rc, pcm, _ = _oracle.mpa12_batch(oracle, payload, runs, 1)
+    assert rc == 0
+    return _oracle.pcm_pack(oracle, pcm, spans, channels, fmt, total), rate, channels, total
+
+
+def test_one_call_decoder_plan(oracle):
+    """CPU half of symphonia_b200.decode: spans tile the output exactly and the oracle renders them."""
+    for data in [_corpus()[0], _corpus()[1]] + [blob for _, blob in _mpa12_corpus()]:
+        want, rate, channels, total = _decode_expect(oracle, data, nat.FMT_S16)
+        assert want.shape == (total, channels) and rate in (44100, 48000, 24000) and np.abs(want).max() > 0
+    want, rate, channels, total = _decode_expect(oracle, _corpus()[0], nat.FMT_S16)
+    assert total == 30 * 1152 - 1105 - 471  # the LAME tag's delay and padding are gone
+
+
+@pytest.mark.gpu
+def test_one_call_decoder_on_the_device(oracle):
+    import symphonia_b200 as sb
+    from symphonia_b200 import decode
+    with sb.Engine(0) as eng:
+        eng.mp3_streams_alloc(2)
+        for data in [_corpus()[0], _corpus()[1]] + [blob for _, blob in _mpa12_corpus()]:
+            for fmt in (nat.FMT_S16, nat.FMT_F32):
+                want, rate, channels, total = _decode_expect(oracle, data, fmt)
+                got, got_rate = decode.decode_mpeg_audio(eng, data, fmt, stream=1)
+                assert got_rate == rate and got.shape == want.shape
+                assert (got.view(np.uint8) == want.view(np.uint8)).all()
