@@ -27,6 +27,14 @@ def _corpus():
     return files
 
 
+def _config0_file():
+    """BASELINE.json configs[0]: MP3 CBR 320 kbit/s, 44.1 kHz, stereo, one stream."""
+    rng = np.random.default_rng(79)
+    frames, _ = bw.gen_stream(rng, 40, version="1", mode=0, bitrate_idx=14, rate_idx=0, padding=0, fill=(0.7, 1.0))
+    assert all(len(f) == 1044 for f in frames)
+    return b"".join(frames)
+
+
 def _batch(files):
     units, quant, runs, spans = [], [], [], []
     at = 0
@@ -146,19 +154,20 @@ def test_cpp_decoder_on_real_files(tmp_path, oracle):
 
     from tests import test_cpp_host
     exe = test_cpp_host._build()
-    # Layer III: the tagged joint-stereo file
-    data = _corpus()[0]
-    units, quant, runs, spans = _batch([data])
-    rc, want, _ = _oracle.mp3_batch(oracle, units.reshape(-1), _spectra(quant), runs, 1)
-    assert rc == 0
-    dur, t0, t1 = spans[0]
-    expect = b"".join(want[k, ch, int(t0[k]):int(dur[k] - t1[k])].tobytes() for k in range(len(want)) for ch in range(2))
     inp, outp = tmp_path / "in.mp3", tmp_path / "out.bin"
-    inp.write_bytes(data)
-    res = subprocess.run([exe, "file", "3", str(inp), str(outp)], capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0, res.stdout + res.stderr
-    assert "delay 1105 padding 471" in res.stdout
-    assert outp.read_bytes() == expect
+    # Layer III: the tagged joint-stereo file, and BASELINE config 0 -- MP3 CBR 320 kbit/s 44.1 kHz stereo, one stream, one
+    # Decoder::decode call per packet ("plumbing") -- with real frames
+    for data, note in ((_corpus()[0], "delay 1105 padding 471"), (_config0_file(), "decoded 40 of 40 packets")):
+        units, quant, runs, spans = _batch([data])
+        rc, want, _ = _oracle.mp3_batch(oracle, units.reshape(-1), _spectra(quant), runs, 1)
+        assert rc == 0
+        dur, t0, t1 = spans[0]
+        expect = b"".join(want[k, ch, int(t0[k]):int(dur[k] - t1[k])].tobytes() for k in range(len(want)) for ch in range(2))
+        inp.write_bytes(data)
+        res = subprocess.run([exe, "file", "3", str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert note in res.stdout
+        assert outp.read_bytes() == expect
     # Layer II and Layer I
     for (layer, blob), (_, sub, runs12) in zip(_mpa12_corpus(), _mpa12_batches()):
         rc, want, _ = _oracle.mpa12_batch(oracle, sub, runs12, 1)
