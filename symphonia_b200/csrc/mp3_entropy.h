@@ -187,8 +187,23 @@ SYMGPU_HD int read_huffman(Bits& bs, const HuffSet& hs, const GcSide& c, uint32_
         }
         while (i < region_end && bs.at < end) {
             unsigned value, len;
-            huff_decode(hs, table, bs.window(), value, len);
+            const uint32_t win = bs.window();
+            huff_decode(hs, table, win, value, len);
             if (len > bs.left()) return -1;
+            if (!linbits) {
+                // tables without linbits (0..15): the code (<= 19 bits) and its at most two sign bits sit in one window
+                const unsigned x = value >> 4, y = value & 15;
+                const unsigned need = len + (x != 0) + (y != 0);
+                if (need > bs.left()) return -1;
+                uint32_t tail = win << len;  // the bits behind the code, left-aligned
+                int16_t ox = 0, oy = 0;
+                if (x) ox = int16_t((tail >> 31) ? -int(x) : int(x)), tail <<= 1;
+                if (y) oy = int16_t((tail >> 31) ? -int(y) : int(y));
+                q[i] = ox, q[i + 1] = oy;
+                bs.at += need;
+                i += 2;
+                continue;
+            }
             bs.at += len;
 SYMGPU_UNROLL
             for (int k = 0; k < 2; ++k) {
@@ -196,7 +211,7 @@ SYMGPU_UNROLL
                 int16_t out = 0;
                 if (x) {
                     uint32_t extra, sign;
-                    if (x == 15 && linbits) {
+                    if (x == 15) {
                         if (!bs.read(linbits, extra)) return -1;
                         x += extra;
                     }
