@@ -661,6 +661,29 @@ typedef struct symgpu_flac_packet {        /* 24 bytes */
 symgpu_status symgpu_flac_index(const uint8_t* data, size_t n, symgpu_flac_stream_info* info, symgpu_flac_packet* packets, size_t cap,
                                 size_t* n_out);
 
+/* ===================================================================================================
+ * Vorbis entropy front-end: audio packets -> the batch format of symgpu_vorbis_synth_* (unit, floor-1 Y
+ * values, residue vectors BEFORE inverse coupling).  CPU only; one object per stream (codebooks, setup, previous block).
+ *   VorbisCodebook::read, synthesize_codewords, VQ unpack   symphonia-codec-vorbis/src/codebook.rs:16-400
+ *   Floor1::read_channel                                     floor.rs:655-722
+ *   Residue::read_residue (types 0, 1, 2)                    residue.rs:142-543
+ *   VorbisDecoder::decode_inner up to inverse coupling       lib.rs:146-250
+ * What the synthesis kernel supports bounds what this accepts: 1 or 2 channels, floor type 1, at most one coupling step
+ * (magnitude = channel 0, angle = channel 1); anything else is SYMGPU_ERR_UNSUPPORTED at create time.
+ * ================================================================================================= */
+typedef struct symgpu_vorbis_fe symgpu_vorbis_fe;
+/* ident: the 30-byte identification packet; setup: the setup packet (together: the stream's extra data). */
+symgpu_status symgpu_vorbis_fe_create(const uint8_t* ident, size_t n_ident, const uint8_t* setup, size_t n_setup, symgpu_vorbis_fe** out);
+void symgpu_vorbis_fe_destroy(symgpu_vorbis_fe* fe);
+void symgpu_vorbis_fe_reset(symgpu_vorbis_fe* fe);   /* AudioDecoder::reset: no previous block */
+/* The stream record and the floor records to register with the context (floors: room for 64; *n_floors written). */
+symgpu_status symgpu_vorbis_fe_config(const symgpu_vorbis_fe* fe, symgpu_vorbis_stream* stream, symgpu_vorbis_floor1* floors, uint32_t* n_floors);
+/* One audio packet.  floor_y [2][65], residue [2][slot] (slot >= blocksize_1 / 2; fully written, zeros where nothing was coded);
+ * unit->floor[] index the records of symgpu_vorbis_fe_config (+ floor_base).  SYMGPU_ERR_DECODE where the reference errors
+ * (not an audio packet, bad mode number); a packet that merely ends early is decoded as far as it goes, as in the reference. */
+symgpu_status symgpu_vorbis_fe_decode(symgpu_vorbis_fe* fe, const uint8_t* packet, size_t n, uint32_t slot, uint32_t floor_base,
+                                      symgpu_vorbis_unit* unit, uint16_t* floor_y, float* residue);
+
 #ifdef __cplusplus
 }
 #endif

@@ -844,16 +844,26 @@ def vorbis_read_setup(buf, ident):
             parts = bs.read(5)
             classes = [bs.read(4) for _ in range(parts)]
             dims = {}
+            class_info = {}
             if parts:
                 for c in range(max(classes) + 1):
                     dims[c] = bs.read(3) + 1
                     sub = bs.read(2)
-                    if sub and bs.read(8) >= max_book:
-                        raise ReaderError(DECODE, "floor1 master book")
-                    for _ in range(1 << sub):
+                    mainbook = 0
+                    if sub:
+                        mainbook = bs.read(8)
+                        if mainbook >= max_book:
+                            raise ReaderError(DECODE, "floor1 master book")
+                    subbooks, used = [0] * 8, 0
+                    for k in range(1 << sub):
                         book = bs.read(8)
-                        if book > 0 and book - 1 >= max_book:
-                            raise ReaderError(DECODE, "floor1 sub book")
+                        if book > 0:
+                            book -= 1
+                            if book >= max_book:
+                                raise ReaderError(DECODE, "floor1 sub book")
+                            used |= 1 << k
+                        subbooks[k] = book
+                    class_info[c] = dict(dimensions=dims[c], subclass_bits=sub, mainbook=mainbook, subbooks=subbooks, used=used)
             mult = bs.read(2) + 1
             rangebits = bs.read(4)
             x_list = [0, 1 << rangebits]
@@ -869,17 +879,21 @@ def vorbis_read_setup(buf, ident):
                     x_list.append(x)
             nb = [_find_neighbors(x_list, i) for i in range(len(x_list))]
             order = sorted(range(len(x_list)), key=lambda i: x_list[i])
-            floors.append(dict(type=1, multiplier=mult, x_list=x_list, low=[a for a, _ in nb], high=[b for _, b in nb], sort_order=order))
+            floors.append(dict(type=1, multiplier=mult, x_list=x_list, low=[a for a, _ in nb], high=[b for _, b in nb], sort_order=order,
+                               partition_class=classes, classes=class_info))
         else:
             raise ReaderError(DECODE, "floor type")
     n_res = bs.read(6) + 1
+    residues = []
     for _ in range(n_res):
-        if bs.read(16) > 2:
+        rtype = bs.read(16)
+        if rtype > 2:
             raise ReaderError(DECODE, "residue type")
         begin, end = bs.read(24), bs.read(24)
-        bs.read(24)
+        part_size = bs.read(24) + 1
         ncls = bs.read(6) + 1
-        if bs.read(8) >= max_book:
+        classbook = bs.read(8)
+        if classbook >= max_book:
             raise ReaderError(DECODE, "classbook")
         if end < begin:
             raise ReaderError(DECODE, "residue range")
@@ -888,12 +902,18 @@ def vorbis_read_setup(buf, ident):
             low = bs.read(3)
             high = bs.read(5) if bs.read_bool() else 0
             used.append(((high << 3) & 0xFF) | low)
-        for u in used:
+        books = [[0] * 8 for _ in used]
+        max_pass = 0
+        for ci, u in enumerate(used):
             for j in range(8):
                 if u >> j & 1:
                     book = bs.read(8)
                     if book == 0 or book >= max_book:
                         raise ReaderError(DECODE, "residue book")
+                    books[ci][j] = book
+                    max_pass = max(max_pass, j)
+        residues.append(dict(type=rtype, begin=begin, end=end, partition_size=part_size, classifications=ncls, classbook=classbook, used=used, books=books,
+                             max_pass=max_pass))
     mappings = []
     n_floors = len(floors) & 0xFF
     for _ in range(bs.read(6) + 1):
@@ -937,4 +957,4 @@ def vorbis_read_setup(buf, ident):
         modes.append((flag, mapping))
     if not bs.read_bool():
         raise ReaderError(DECODE, "framing")
-    return dict(n_codebooks=n_books, floors=floors, n_residues=n_res, mappings=mappings, modes=modes)
+    return dict(n_codebooks=n_books, floors=floors, n_residues=n_res, residues=residues, mappings=mappings, modes=modes)

@@ -232,6 +232,16 @@ def lib():
     L.symgpu_flac_fe_decode_packets.argtypes = [vp, sz, vp, sz, u32, u32, u32, vp, vp, vp, vp, sz, vp, sz, psz, psz, psz]
     L.symgpu_flac_index.restype = ctypes.c_int
     L.symgpu_flac_index.argtypes = [vp, sz, vp, vp, sz, psz]
+    L.symgpu_vorbis_fe_create.restype = ctypes.c_int
+    L.symgpu_vorbis_fe_create.argtypes = [vp, sz, vp, sz, ctypes.POINTER(vp)]
+    L.symgpu_vorbis_fe_destroy.restype = None
+    L.symgpu_vorbis_fe_destroy.argtypes = [vp]
+    L.symgpu_vorbis_fe_reset.restype = None
+    L.symgpu_vorbis_fe_reset.argtypes = [vp]
+    L.symgpu_vorbis_fe_config.restype = ctypes.c_int
+    L.symgpu_vorbis_fe_config.argtypes = [vp, vp, vp, ctypes.POINTER(u32)]
+    L.symgpu_vorbis_fe_decode.restype = ctypes.c_int
+    L.symgpu_vorbis_fe_decode.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp]
     _LIB = L
     return L
 

@@ -184,3 +184,46 @@ def flac_decode_packets(data, packets, stream_bps=0, stream_channels=0, max_bloc
             raise SymgpuError(rc, "symgpu_flac_fe_decode_packets")
         g = good.value
         return frames[:g], infos[:g], frame_of[:g], subs[:n_subs.value], samples[:n_smp.value]
+
+
+class VorbisFrontend:
+    """One Vorbis stream's entropy front-end (codebooks, setup, previous block): identification + setup packets in, then audio
+    packets -> (unit, floor_y [2][65], residue [2][slot]), the input of Engine.vorbis_synth_host."""
+
+    def __init__(self, ident_packet, setup_packet):
+        self._L = nat.lib()
+        a, b = _u8(bytes(ident_packet)), _u8(bytes(setup_packet))
+        h = _vp()
+        rc = self._L.symgpu_vorbis_fe_create(_vp(a.ctypes.data), a.size, _vp(b.ctypes.data), b.size, ctypes.byref(h))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_vorbis_fe_create")
+        self._h = h
+        stream = np.zeros(1, dtype=nat.VORBIS_STREAM_DTYPE)
+        floors = np.zeros(64, dtype=nat.VORBIS_FLOOR1_DTYPE)
+        n = ctypes.c_uint32(0)
+        self._L.symgpu_vorbis_fe_config(self._h, _vp(stream.ctypes.data), _vp(floors.ctypes.data), ctypes.byref(n))
+        self.stream, self.floors = stream[0], floors[:n.value]
+        self.slot = (1 << int(self.stream["bs1_exp"])) >> 1
+
+    def close(self):
+        if self._h:
+            self._L.symgpu_vorbis_fe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def reset(self):
+        self._L.symgpu_vorbis_fe_reset(self._h)
+
+    def decode(self, packet, slot=None, floor_base=0):
+        slot = self.slot if slot is None else slot
+        a = _u8(bytes(packet))
+        unit = np.zeros(1, dtype=nat.VORBIS_UNIT_DTYPE)
+        floor_y = np.zeros((2, 65), dtype=np.uint16)
+        residue = np.zeros((2, slot), dtype=np.float32)
+        rc = self._L.symgpu_vorbis_fe_decode(self._h, _vp(a.ctypes.data) if a.size else None, a.size, slot, floor_base, _vp(unit.ctypes.data),
+                                             _vp(floor_y.ctypes.data), _vp(residue.ctypes.data))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_vorbis_fe_decode")
+        return unit[0], floor_y, residue
