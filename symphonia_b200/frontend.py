@@ -191,6 +191,7 @@ class VorbisFrontend:
     packets -> (unit, floor_y [2][65], residue [2][slot]), the input of Engine.vorbis_synth_host."""
 
     def __init__(self, ident_packet, setup_packet):
+        self._h = None
         self._L = nat.lib()
         a, b = _u8(bytes(ident_packet)), _u8(bytes(setup_packet))
         h = _vp()
