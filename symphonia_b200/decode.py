@@ -45,3 +45,95 @@ def decode_mpeg_audio(engine, data, fmt=nat.FMT_S16, stream=0):
     engine.mp3_stream_reset(stream)
     pcm = engine.mp3_synth_host_quantized(payload[0], payload[1], runs) if layer == 3 else engine.mpa12_synth_host(payload, runs)
     return engine.pcm_pack_host(pcm, spans, channels, fmt, total), rate
+
+
+def ogg_vorbis_plan(data, serial=None):
+    """CPU half for a Vorbis-in-Ogg file: pages -> packets (symgpu_ogg_index) -> identification / setup headers -> entropy front-end
+    (symgpu_vorbis_fe_*) -> the synthesis stage's batch, plus the reader's time line: per-packet duration and leading discard
+    (mappings/vorbis.rs:45-107) and the end trim against each page's granule position (symphonia-format-ogg/src/logical.rs:164-302;
+    a page whose predecessor completed no packet starts at end - total duration, a stream whose audio sits on one page starts at
+    -discard when that leaves padding).  Returns dict(stream, floors, units, floor_y, residue, runs, slot, spans, channels,
+    sample_rate, total_frames).  Packets the front-end refuses are dropped, as a caller of the reference drops a DecodeError."""
+    packets, pieces = packetizer.ogg_index(data)
+    if len(packets) == 0:
+        raise ValueError("no Ogg packets")
+    serial = int(packets["serial"][0]) if serial is None else serial
+    mine = packets[packets["serial"] == serial]
+    blobs = [packetizer.gather(data, pk, pieces) for pk in mine]
+    ident_b = blobs[0]
+    ident = packetizer.vorbis_ident(ident_b)
+    at = 1
+    while at < len(blobs) and not (len(blobs[at]) >= 7 and blobs[at][0] == 5 and blobs[at][1:7] == b"vorbis"):
+        at += 1
+    if at == len(blobs):
+        raise ValueError("no Vorbis setup header")
+    setup_b = blobs[at]
+    n_modes, mask = packetizer.vorbis_setup_modes(setup_b, ident)
+    audio = [(pk, b) for pk, b in zip(mine[at + 1:], blobs[at + 1:]) if len(b) and (b[0] & 1) == 0]
+    dur, discard, _ = packetizer.vorbis_packet_durations(ident, n_modes, mask, [b for _, b in audio])
+    dur, discard = dur.astype(np.int64), discard.astype(np.int64)
+    # time line, page by page
+    trim_end = np.zeros(len(audio), dtype=np.int64)
+    seqs = np.array([int(pk["page_sequence"]) for pk, _ in audio], dtype=np.int64)
+    single_page = len(set(seqs.tolist())) == 1
+    prev_seq, prev_end, i = None, None, 0
+    while i < len(audio):
+        j = i
+        while j < len(audio) and seqs[j] == seqs[i]:
+            j += 1
+        page_end = int(np.int64(np.uint64(audio[i][0]["page_absgp"])))
+        tot, disc = int(dur[i:j].sum()), int(discard[i:j].sum())
+        if prev_end is not None and prev_seq + 1 == seqs[i]:
+            start = prev_end
+        elif single_page and tot >= disc + page_end:
+            start = -disc
+        else:
+            start = page_end - tot
+        nxt = start
+        for k in range(i, j):
+            nxt += int(dur[k])
+            left = int(dur[k]) - int(discard[k])
+            if nxt > page_end:
+                trim_end[k] = min(nxt - page_end, left)
+        prev_seq, prev_end, i = int(seqs[i]), page_end, j
+    fe = frontend.VorbisFrontend(ident_b, setup_b)
+    slot = fe.slot
+    units, fy, res, keep = [], [], [], []
+    for k, (_, b) in enumerate(audio):
+        try:
+            u, y, r = fe.decode(b)
+        except frontend.SymgpuError:
+            continue
+        units.append(u), fy.append(y), res.append(r), keep.append(k)
+    n = len(units)
+    stream, floors = np.array([fe.stream], dtype=nat.VORBIS_STREAM_DTYPE), fe.floors.copy()
+    fe.close()
+    bs = {0: 1 << int(ident["bs0_exp"]), 1: 1 << int(ident["bs1_exp"])}
+    spans = np.zeros(n, dtype=nat.PCM_SPAN_DTYPE)
+    total = 0
+    for o, k in enumerate(keep):
+        frames = (bs[int(units[o]["prev_block_flag"])] + bs[int(units[o]["block_flag"])]) // 4
+        if o == 0:
+            ts, te = frames, 0  # the first packet after a reset is silenced in gapless mode (codec-vorbis lib.rs:318-322)
+        else:
+            ts = min(int(discard[k]), frames)
+            te = min(int(trim_end[k]), frames - ts)
+        spans[o] = (o * 2 * slot, slot, frames, ts, te, total)
+        total += frames - ts - te
+    runs = np.zeros(1, dtype=nat.VORBIS_RUN_DTYPE)
+    runs["n_packets"] = n
+    return dict(stream=stream, floors=floors, units=np.array(units, dtype=nat.VORBIS_UNIT_DTYPE).reshape(n),
+                floor_y=np.array(fy, dtype=np.uint16).reshape(n, 2, 65), residue=np.array(res, dtype=np.float32).reshape(n, 2, slot),
+                runs=runs, slot=slot, spans=spans, channels=int(ident["channels"]), sample_rate=int(ident["sample_rate"]), total_frames=total)
+
+
+def decode_ogg_vorbis(engine, data, fmt=nat.FMT_S16, serial=None):
+    """(samples [frames, channels] of `fmt`, sample_rate) of one Vorbis logical stream (mono / stereo, floor 1: what the synthesis
+    kernel takes).  Registers the stream as slot 0 of `engine` with its floors from index 0."""
+    plan = ogg_vorbis_plan(data, serial)
+    if len(plan["units"]) == 0:
+        return np.zeros((0, plan["channels"]), dtype=nat.FMT_NUMPY[fmt]), plan["sample_rate"]
+    engine.vorbis_streams_set(plan["stream"])
+    engine.vorbis_floors_set(plan["floors"])
+    pcm = engine.vorbis_synth_host(plan["units"], plan["floor_y"], plan["residue"], plan["runs"], plan["slot"])
+    return engine.pcm_pack_host(pcm, plan["spans"], plan["channels"], fmt, plan["total_frames"]), plan["sample_rate"]

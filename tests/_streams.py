@@ -175,9 +175,10 @@ def ogg_page(serial, sequence, absgp, lacing, body, continuation=False, first=Fa
     return h[:22] + crc.to_bytes(4, "little") + h[26:] + body
 
 
-def ogg_paginate(serial, packets, rng, max_segments=255, first_sequence=0, granule_step=1024, bos=True, eos=True):
+def ogg_paginate(serial, packets, rng, max_segments=255, first_sequence=0, granule_step=1024, bos=True, eos=True, granule_of=None):
     """Pack packets into pages the way a muxer does: lacing values of 255 continue, a packet may spill over any number
-    of pages, pages close at random fill levels.  Returns the list of page byte strings."""
+    of pages, pages close at random fill levels.  Returns the list of page byte strings.  granule_of[k] (optional): the granule
+    position once packet k is complete; a page then carries that of the last packet ending on it."""
     segs = []  # (lacing value, bytes, closes-a-packet)
     for p in packets:
         n = len(p)
@@ -188,12 +189,16 @@ def ogg_paginate(serial, packets, rng, max_segments=255, first_sequence=0, granu
         segs.append((n - at, p[at:], True))
     pages, seq, absgp, i = [], first_sequence, 0, 0
     open_packet = False
+    done = 0
     while i < len(segs):
         take = int(rng.integers(1, max_segments + 1))
         chunk = segs[i:i + take]
         i += len(chunk)
         ends = sum(1 for s in chunk if s[2])
         absgp += ends * granule_step
+        done += ends
+        if granule_of is not None and ends:
+            absgp = granule_of[done - 1]
         pages.append(ogg_page(serial, seq, absgp if ends else 0xFFFFFFFFFFFFFFFF, [s[0] for s in chunk], b"".join(s[1] for s in chunk),
                               continuation=open_packet, first=bos and seq == first_sequence, last=eos and i >= len(segs)))
         open_packet = not chunk[-1][2]

@@ -1,4 +1,4 @@
-// Sanitizer fuzz driver for the host-side parsers (packetisers, MP3 / Layer I-II / FLAC front-ends, plan + jobs):
+// Sanitizer fuzz driver for the host-side parsers (packetisers, MP3 / Layer I-II / FLAC / Vorbis front-ends, plan + jobs):
 //   g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-sanitize-recover=all ... tests/cpp/fuzz_frontends.cpp <csrc/*.cpp>
 //   fuzz_frontends SEEDFILE... : every seed is mutated (bit flips, byte runs, truncation, splices) ITER times and pushed through
 // every entry point; any out-of-bounds access, overflow or leak aborts.  Run by tests/test_fuzz_sanitized.py.
@@ -110,6 +110,34 @@ static void run_all(const std::vector<uint8_t>& d) {
         std::vector<int32_t> smp(8 * 65536);
         size_t g, ns, nm;
         symgpu_flac_fe_decode_packets(p, n, &one, 1, 16, 0, 0, &fr, &fi, &fo, sf, 8, smp.data(), smp.size(), &g, &ns, &nm);
+    }
+    // ---- Vorbis entropy front-end: "VFE1", then length-prefixed (u16 LE) identification, setup and audio packets
+    if (n > 8 && std::memcmp(p, "VFE1", 4) == 0) {
+        std::vector<Piece> parts;
+        size_t at = 4;
+        while (at + 2 <= n) {
+            const size_t len = size_t(p[at]) | size_t(p[at + 1]) << 8;
+            at += 2;
+            const size_t take = len < n - at ? len : n - at;
+            parts.push_back(Piece{at, uint32_t(take)});
+            at += take;
+        }
+        symgpu_vorbis_fe* fe = nullptr;
+        if (parts.size() >= 2 && symgpu_vorbis_fe_create(p + parts[0].offset, parts[0].len, p + parts[1].offset, parts[1].len, &fe) == SYMGPU_OK) {
+            symgpu_vorbis_stream st;
+            std::vector<symgpu_vorbis_floor1> fl(64);
+            uint32_t nf = 0;
+            symgpu_vorbis_fe_config(fe, &st, fl.data(), &nf);
+            const uint32_t slot = (1u << st.bs1_exp) >> 1;
+            std::vector<uint16_t> fy(2 * 65);
+            std::vector<float> res(2 * size_t(slot));
+            symgpu_vorbis_unit unit;
+            for (size_t k = 2; k < parts.size(); ++k) {
+                symgpu_vorbis_fe_decode(fe, p + parts[k].offset, parts[k].len, slot, 0, &unit, fy.data(), res.data());
+                if (k % 5 == 0) symgpu_vorbis_fe_reset(fe);
+            }
+            symgpu_vorbis_fe_destroy(fe);
+        }
     }
 }
 

@@ -1,4 +1,4 @@
-"""Untrusted input: every host-side parser (packetisers, MP3 / Layer I-II / FLAC front-ends, plan + jobs, Vorbis mapping) built
+"""Untrusted input: every host-side parser (packetisers, MP3 / Layer I-II / FLAC / Vorbis front-ends, plan + jobs, Vorbis mapping) built
 with AddressSanitizer + UndefinedBehaviorSanitizer and driven with mutated streams (tests/cpp/fuzz_frontends.cpp).  Any
 out-of-bounds access, signed overflow, misaligned access or leak aborts the driver.  A 60 000-input run was clean when this
 was written; the suite runs a shorter one."""
@@ -12,6 +12,7 @@ from tests import _flac_bitstream as fw
 from tests import _mp3_bitstream as bw
 from tests import _mpa12_bitstream as b12
 from tests import _streams as st
+from tests import _vorbis_bitstream as vb
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -37,6 +38,10 @@ def _seeds(rng):
           for k, f in enumerate(order)]
     seeds["flac"] = fw.native_file(fp, fw.stream_info_block(576, 576, 44100, 2, 16, 0))
     seeds["flac_frame"] = fp[1]
+    for k, rtype in enumerate((0, 1, 2)):
+        vs = vb.Stream(np.random.default_rng(40 + k), residue_type=rtype)
+        parts = [vs.ident, vs.setup] + [vs.packet()[0] for _ in range(10)]
+        seeds[f"vorbis_fe{rtype}"] = b"VFE1" + b"".join(len(q).to_bytes(2, "little") + q for q in parts)
     return seeds
 
 
@@ -45,7 +50,7 @@ def test_parsers_under_address_and_ub_sanitizers(tmp_path):
     exe = str(tmp_path / "fuzz_frontends")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-ffp-contract=off",
                            "-I/usr/local/cuda/include", "-o", exe, os.path.join(ROOT, "tests", "cpp", "fuzz_frontends.cpp")] +
-                          [os.path.join(csrc, f) for f in ("mp3_frontend.cpp", "mpa12_frontend.cpp", "flac_frontend.cpp", "packetizer.cpp", "tables.cpp")])
+                          [os.path.join(csrc, f) for f in ("mp3_frontend.cpp", "mpa12_frontend.cpp", "flac_frontend.cpp", "vorbis_frontend.cpp", "packetizer.cpp", "tables.cpp")])
     paths = []
     for name, blob in _seeds(np.random.default_rng(1)).items():
         path = str(tmp_path / (name + ".bin"))
@@ -55,4 +60,4 @@ def test_parsers_under_address_and_ub_sanitizers(tmp_path):
     env = dict(os.environ, FUZZ_ITERS="250", ASAN_OPTIONS="detect_leaks=1:abort_on_error=1")
     res = subprocess.run([exe] + paths, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
-    assert "no sanitizer report" in res.stdout and "2761 inputs" in res.stdout
+    assert "no sanitizer report" in res.stdout and "3514 inputs" in res.stdout
