@@ -684,6 +684,29 @@ symgpu_status symgpu_vorbis_fe_config(const symgpu_vorbis_fe* fe, symgpu_vorbis_
 symgpu_status symgpu_vorbis_fe_decode(symgpu_vorbis_fe* fe, const uint8_t* packet, size_t n, uint32_t slot, uint32_t floor_base,
                                       symgpu_vorbis_unit* unit, uint16_t* floor_y, float* residue);
 
+/* ===================================================================================================
+ * AAC-LC entropy front-end: one raw_data_block per packet (an ADTS frame's payload, or an MP4 sample) ->
+ * the batch format of symgpu_aac_synth_* (two channel units, resolved TNS filters, 2 x 1024 dequantised lines after
+ * joint stereo and pulse restoration).  CPU only; one object per stream (window history, element layout, noise generator).
+ *   AacDecoder::try_new (no extra data), set_pair, decode_ga   symphonia-codec-aac/src/aac/mod.rs:52-229
+ *   ChannelPair::decode_ga_sce / decode_ga_cpe                  aac/cpe.rs:51-161
+ *   IcsInfo::decode, Ics::decode (sections, scale factors, spectrum, PNS)   aac/ics/mod.rs:120-447
+ *   Pulse::read / synth, Tns::read, the line ranges of Tns::synth           aac/ics/pulse.rs:35-105, aac/ics/tns.rs:35-199
+ * 1 or 2 channels (mod.rs:101-108); a packet whose elements do not cover exactly the configured channels is
+ * SYMGPU_ERR_UNSUPPORTED (the reference renders the channels it found; the batch format carries all of a frame).
+ * ================================================================================================= */
+typedef struct symgpu_aac_fe symgpu_aac_fe;
+symgpu_status symgpu_aac_fe_create(uint32_t sample_rate, uint32_t channels, symgpu_aac_fe** out);
+void symgpu_aac_fe_destroy(symgpu_aac_fe* fe);
+void symgpu_aac_fe_reset(symgpu_aac_fe* fe);   /* AudioDecoder::reset: window history forgotten (pair with symgpu_aac_stream_reset) */
+/* units [2], tns: room for 16 records (*n_tns written; units[].tns_first = tns_base + position), coeffs [2][1024] (channel 1
+ * zero for a mono stream).  SYMGPU_ERR_DECODE / _UNSUPPORTED where the reference's decode returns that error; the stream
+ * state is then left as the reference leaves it (changed up to the point of failure). */
+symgpu_status symgpu_aac_fe_decode(symgpu_aac_fe* fe, const uint8_t* packet, size_t n, uint32_t tns_base, symgpu_aac_unit* units,
+                                   symgpu_aac_tns* tns, uint32_t* n_tns, float* coeffs);
+/* The dequantisation tables the front-end uses (for tests): x^(4/3) [8192], 2^((i-156)/4) [256], 0.5^((i-155)/4) [256]. */
+void symgpu_aac_fe_tables(float* pow43, float* normal_scf, float* intensity_scf);
+
 #ifdef __cplusplus
 }
 #endif

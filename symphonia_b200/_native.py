@@ -242,6 +242,16 @@ def lib():
     L.symgpu_vorbis_fe_config.argtypes = [vp, vp, vp, ctypes.POINTER(u32)]
     L.symgpu_vorbis_fe_decode.restype = ctypes.c_int
     L.symgpu_vorbis_fe_decode.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp]
+    L.symgpu_aac_fe_create.restype = ctypes.c_int
+    L.symgpu_aac_fe_create.argtypes = [u32, u32, ctypes.POINTER(vp)]
+    L.symgpu_aac_fe_destroy.restype = None
+    L.symgpu_aac_fe_destroy.argtypes = [vp]
+    L.symgpu_aac_fe_reset.restype = None
+    L.symgpu_aac_fe_reset.argtypes = [vp]
+    L.symgpu_aac_fe_decode.restype = ctypes.c_int
+    L.symgpu_aac_fe_decode.argtypes = [vp, vp, sz, u32, vp, vp, ctypes.POINTER(u32), vp]
+    L.symgpu_aac_fe_tables.restype = None
+    L.symgpu_aac_fe_tables.argtypes = [vp, vp, vp]
     _LIB = L
     return L
 

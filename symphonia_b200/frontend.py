@@ -228,3 +228,47 @@ class VorbisFrontend:
         if rc != 0:
             raise SymgpuError(rc, "symgpu_vorbis_fe_decode")
         return unit[0], floor_y, residue
+
+
+class AacFrontend:
+    """One AAC-LC stream's entropy front-end (window history, element layout, noise generator): raw_data_block packets ->
+    (units [2], tns [n], coeffs [2][1024]), the input of Engine.aac_synth_host."""
+
+    def __init__(self, sample_rate, channels):
+        self._h = None
+        self._L = nat.lib()
+        h = _vp()
+        rc = self._L.symgpu_aac_fe_create(int(sample_rate), int(channels), ctypes.byref(h))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_aac_fe_create")
+        self._h, self.channels = h, int(channels)
+
+    def close(self):
+        if self._h:
+            self._L.symgpu_aac_fe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def reset(self):
+        self._L.symgpu_aac_fe_reset(self._h)
+
+    def decode(self, packet, tns_base=0):
+        a = _u8(bytes(packet))
+        units = np.zeros(2, dtype=nat.AAC_UNIT_DTYPE)
+        tns = np.zeros(16, dtype=nat.AAC_TNS_DTYPE)
+        coeffs = np.zeros((2, 1024), dtype=np.float32)
+        n = ctypes.c_uint32(0)
+        rc = self._L.symgpu_aac_fe_decode(self._h, _vp(a.ctypes.data) if a.size else None, a.size, int(tns_base), _vp(units.ctypes.data),
+                                          _vp(tns.ctypes.data), ctypes.byref(n), _vp(coeffs.ctypes.data))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_aac_fe_decode")
+        return units, tns[:n.value], coeffs
+
+
+def aac_tables():
+    """(x^(4/3) [8192], normal scale factors [256], intensity scale factors [256]) as the front-end holds them."""
+    p43, a, b = np.zeros(8192, dtype=np.float32), np.zeros(256, dtype=np.float32), np.zeros(256, dtype=np.float32)
+    nat.lib().symgpu_aac_fe_tables(_vp(p43.ctypes.data), _vp(a.ctypes.data), _vp(b.ctypes.data))
+    return p43, a, b

@@ -1,4 +1,4 @@
-// Sanitizer fuzz driver for the host-side parsers (packetisers, MP3 / Layer I-II / FLAC / Vorbis front-ends, plan + jobs):
+// Sanitizer fuzz driver for the host-side parsers (packetisers, MP3 / Layer I-II / FLAC / Vorbis / AAC front-ends, plan + jobs):
 //   g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-sanitize-recover=all ... tests/cpp/fuzz_frontends.cpp <csrc/*.cpp>
 //   fuzz_frontends SEEDFILE... : every seed is mutated (bit flips, byte runs, truncation, splices) ITER times and pushed through
 // every entry point; any out-of-bounds access, overflow or leak aborts.  Run by tests/test_fuzz_sanitized.py.
@@ -110,6 +110,46 @@ static void run_all(const std::vector<uint8_t>& d) {
         std::vector<int32_t> smp(8 * 65536);
         size_t g, ns, nm;
         symgpu_flac_fe_decode_packets(p, n, &one, 1, 16, 0, 0, &fr, &fi, &fo, sf, 8, smp.data(), smp.size(), &g, &ns, &nm);
+    }
+    // ---- AAC entropy front-end: "AFE1", rate index byte, channel byte, then length-prefixed (u16 LE) raw_data_blocks;
+    //      and every ADTS frame of the input as a packet
+    if (n > 8 && std::memcmp(p, "AFE1", 4) == 0) {
+        static const uint32_t rates[8] = {44100, 48000, 8000, 96000, 22050, 32000, 16000, 64000};
+        symgpu_aac_fe* fe = nullptr;
+        if (symgpu_aac_fe_create(rates[p[4] & 7], 1 + (p[5] & 1), &fe) == SYMGPU_OK) {
+            symgpu_aac_unit units[2];
+            std::vector<symgpu_aac_tns> tns(16);
+            std::vector<float> co(2048);
+            uint32_t nt = 0;
+            size_t at = 6, k = 0;
+            while (at + 2 <= n) {
+                const size_t len = size_t(p[at]) | size_t(p[at + 1]) << 8;
+                at += 2;
+                const size_t take = len < n - at ? len : n - at;
+                symgpu_aac_fe_decode(fe, p + at, take, 0, units, tns.data(), &nt, co.data());
+                if (++k % 5 == 0) symgpu_aac_fe_reset(fe);
+                at += take;
+            }
+            symgpu_aac_fe_destroy(fe);
+        }
+    }
+    {
+        size_t count = 0;
+        symgpu_status stop;
+        if (symgpu_adts_index(p, n, nullptr, 0, &count, &stop) == SYMGPU_OK && count) {
+            std::vector<symgpu_adts_packet> pk(count);
+            symgpu_adts_index(p, n, pk.data(), count, &count, &stop);
+            symgpu_aac_fe* fe = nullptr;
+            if (symgpu_aac_fe_create(pk[0].sample_rate, pk[0].channels == 1 ? 1 : 2, &fe) == SYMGPU_OK) {
+                symgpu_aac_unit units[2];
+                std::vector<symgpu_aac_tns> tns(16);
+                std::vector<float> co(2048);
+                uint32_t nt = 0;
+                for (size_t i = 0; i < count; ++i)
+                    if (pk[i].offset + pk[i].size <= n) symgpu_aac_fe_decode(fe, p + pk[i].offset, pk[i].size, 0, units, tns.data(), &nt, co.data());
+                symgpu_aac_fe_destroy(fe);
+            }
+        }
     }
     // ---- Vorbis entropy front-end: "VFE1", then length-prefixed (u16 LE) identification, setup and audio packets
     if (n > 8 && std::memcmp(p, "VFE1", 4) == 0) {

@@ -1,0 +1,258 @@
+"""AAC-LC entropy front-end (`symgpu_aac_fe_*`, SURVEY §8f N1 for the AAC path) against oracle/aac_frontend_oracle.py (the reference's
+sequence, numpy f32 arithmetic) and against an independent raw_data_block writer's ground truth.  Every value is a short chain of
+single IEEE operations on table entries, so the bar is bit equality.  The oracle is pinned by the reference's own unit test for
+this path (ics/mod.rs:612-635) and by the writer.  CPU only."""
+import numpy as np
+import pytest
+
+import symphonia_b200 as sb
+from oracle import aac_frontend_oracle as ao
+from symphonia_b200 import _native as nat
+from symphonia_b200 import frontend
+from symphonia_b200.engine import SymgpuError
+from tests import _aac_bitstream as ab
+from tests import _oracle
+
+RATES = [44100, 48000, 8000, 96000, 22050, 32000, 16000, 64000, 11025, 24000, 88200, 12000]
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ---- tables ---------------------------------------------------------------------------------------------------------------
+
+def test_tables_equal_the_oracle_and_the_closed_forms():
+    p43, normal, intensity = frontend.aac_tables()
+    assert np.array_equal(u32(p43), u32(np.array(ao.POW43)))
+    assert np.array_equal(u32(normal), u32(np.array(ao.NORMAL_SCF)))
+    assert np.array_equal(u32(intensity), u32(np.array(ao.INTENSITY_SCF)))
+    # the scale-factor tables are the correctly rounded powers of two -- whichever libm routine computes them
+    assert np.array_equal(u32(normal), u32(np.array([ab.scale_normal(i) for i in range(256)])))
+    assert np.array_equal(u32(intensity), u32(np.array([ab.scale_intensity(i) for i in range(256)])))
+    assert float(normal[156]) == 1.0 and float(intensity[155]) == 1.0 and float(normal[160]) == 2.0 and float(intensity[159]) == 0.5
+    # x^(4/3) is the C library's powf with the exponent 4/3 rounded to f32 (1.3333334), as in the reference: never more than one
+    # unit in the last place from the correctly rounded value of THAT power -- so 8^(4/3) is one step above 16
+    cr = np.array([ab.pow43_correctly_rounded(i) for i in range(8192)], dtype=np.float32)
+    off = np.abs(p43.view(np.int32).astype(np.int64) - cr.view(np.int32))
+    assert off.max() <= 1 and int((off != 0).sum()) <= 32
+    assert float(p43[0]) == 0.0 and float(p43[1]) == 1.0 and float(p43[8]) == float(np.nextafter(np.float32(16), np.float32(17)))
+
+
+# ---- the reference's unit test for this path ------------------------------------------------------------------------------
+
+def test_section_data_rejects_excess_zero_length_sections():
+    # ics/mod.rs decode_section_data_rejects_excess_zero_length_sections: long window, one group, max_sfb = 1, an all-zero stream
+    # (codebook 0, length 0, for ever) must fail cleanly after MAX_SFBS sections
+    ics = ao.Ics(ao.L48, ao.S48)
+    ics.long_win, ics.window_groups, ics.max_sfb = True, 1, 1
+    with pytest.raises(ao.AacError) as e:
+        ics.decode_section_data(ao.BitsLtr(bytes(65 * 9 // 8 + 1)))
+    assert e.value.kind == ao.DECODE
+    # the same through the front-end: SCE, global gain, ics_info (long, max_sfb = 1), then zeros
+    w = ab.BitWriterMsb()
+    w.put(0, 3), w.put(0, 4), w.put(100, 8), w.put(0, 1), w.put(0, 2), w.put(0, 1), w.put(1, 6), w.put(0, 1)
+    pkt = w.bytes() + bytes(80)
+    with pytest.raises(ao.AacError):
+        ao.AacFrontend(44100, 1).decode(pkt)
+    fe = frontend.AacFrontend(44100, 1)
+    with pytest.raises(SymgpuError) as e2:
+        fe.decode(pkt)
+    assert e2.value.status == 1
+    fe.close()
+
+
+# ---- oracle and front-end against the writer's ground truth ---------------------------------------------------------------
+
+def _check_channel(truth, want, units, tns, coeffs, c, what):
+    for key in ("window_sequence", "window_shape", "prev_window_shape"):
+        assert truth is None or truth[key] == want[key], (what, key)
+        assert want[key] == int(units[c][key]), (what, key)
+    if truth is not None:
+        assert np.array_equal(u32(truth["coeffs"]), u32(want["coeffs"])), what
+        assert len(truth["tns"]) == len(want["tns"]), what
+        for a, b in zip(truth["tns"], want["tns"]):
+            assert tuple(a[:4]) == tuple(b[:4]) and np.array_equal(u32(np.array(a[4])), u32(np.array(b[4]))), what
+    assert np.array_equal(u32(coeffs[c]), u32(want["coeffs"])), what
+    assert len(want["tns"]) == int(units[c]["n_tns"]), what
+    for j, b in enumerate(want["tns"]):
+        r = tns[int(units[c]["tns_first"]) - what[-1] + j]
+        assert (int(r["start"]), int(r["end"]), int(r["order"]), int(r["direction"])) == tuple(b[:4]), what
+        assert np.array_equal(u32(r["lpc"]), u32(np.array(b[4]))), what
+
+
+def _streams(base, n):
+    for seed in range(n):
+        rng = np.random.default_rng(base + seed)
+        ch = 1 if seed % 4 == 3 else 2
+        layout = ["sce", "sce"] if (seed % 7 == 5 and ch == 2) else None
+        yield seed, ab.Stream(rng, rate=RATES[seed % len(RATES)], channels=ch, layout=layout), rng
+
+
+def test_oracle_and_frontend_equal_the_writer_truth():
+    kinds = set()
+    for seed, s, _ in _streams(100, 48):
+        o, fe = ao.AacFrontend(s.rate, s.channels), frontend.AacFrontend(s.rate, s.channels)
+        for k in range(6):
+            pkt, truth = s.packet()
+            covered, want = o.decode(pkt)
+            assert covered == s.channels
+            base = 1000 * k
+            units, tns, coeffs = fe.decode(pkt, tns_base=base)
+            for c in range(s.channels):
+                _check_channel(truth[c], want[c], units, tns, coeffs, c, (seed, k, c, base))
+                kinds.add((truth[c]["window_sequence"], bool(truth[c]["tns"])))
+            if s.channels == 1:
+                assert not coeffs[1].any() and units[1].tobytes() == bytes(16)
+            assert int(units["n_tns"].sum()) == len(tns)
+        fe.close()
+    assert len(kinds) == 8  # every window sequence with and without TNS
+
+
+def test_truncated_and_damaged_packets():
+    """The reference fails a packet at the first read past its end or the first rule it breaks; what it had changed by then (window
+    history, noise generator) stays changed.  Both sides see the same packets in the same order, so the histories stay in step."""
+    refused = accepted = 0
+    for seed, s, rng in _streams(200, 24):
+        o, fe = ao.AacFrontend(s.rate, s.channels), frontend.AacFrontend(s.rate, s.channels)
+        for k in range(12):
+            pkt, _ = s.packet()
+            mode = k % 3
+            if mode == 1:
+                pkt = pkt[:int(rng.integers(0, len(pkt)))]
+            elif mode == 2:
+                b = bytearray(pkt)
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(len(b)))] ^= 1 << int(rng.integers(8))
+                pkt = bytes(b)
+            try:
+                covered, want = o.decode(pkt)
+                status = 0 if covered == s.channels else 2
+            except ao.AacError as e:
+                status = 1 if e.kind == ao.DECODE else 2
+            if status:
+                with pytest.raises(SymgpuError) as e2:
+                    fe.decode(pkt)
+                assert e2.value.status == status, (seed, k, mode)
+                refused += 1
+            else:
+                units, tns, coeffs = fe.decode(pkt)
+                for c in range(s.channels):
+                    _check_channel(None, want[c], units, tns, coeffs, c, (seed, k, c, 0))
+                accepted += 1
+        fe.close()
+    assert refused > 60 and accepted > 120
+
+
+def test_reset_forgets_the_window_history():
+    for seed, s, _ in _streams(300, 6):
+        o, fe = ao.AacFrontend(s.rate, s.channels), frontend.AacFrontend(s.rate, s.channels)
+        for k in range(8):
+            if k == 4:
+                o.reset(), fe.reset(), s.forget_windows()
+            pkt, truth = s.packet()
+            _, want = o.decode(pkt)
+            units, tns, coeffs = fe.decode(pkt)
+            for c in range(s.channels):
+                _check_channel(truth[c], want[c], units, tns, coeffs, c, (seed, k, c, 0))
+                if k == 4:
+                    assert int(units[c]["prev_window_shape"]) == 0
+        fe.close()
+
+
+def test_element_layout_rules():
+    rng = np.random.default_rng(5)
+    stereo = ab.Stream(rng, 44100, 2)
+    mono = ab.Stream(rng, 44100, 1)
+    two = ab.Stream(rng, 44100, 2, layout=["sce", "sce"])
+    # a channel pair in a mono stream: too many channels (mod.rs:123-124)
+    for cls in (lambda: ao.AacFrontend(44100, 1), lambda: frontend.AacFrontend(44100, 1)):
+        with pytest.raises((ao.AacError, SymgpuError)) as e:
+            cls().decode(stereo.packet(extras=False)[0])
+        assert getattr(e.value, "kind", None) == ao.DECODE or getattr(e.value, "status", None) == 1
+    # one single-channel element in a stereo stream: decodes in the reference (one plane rendered); refused here as unsupported
+    covered, _ = ao.AacFrontend(44100, 2).decode(mono.packet(extras=False)[0])
+    assert covered == 1
+    fe = frontend.AacFrontend(44100, 2)
+    with pytest.raises(SymgpuError) as e:
+        fe.decode(mono.packet(extras=False)[0])
+    assert e.value.status == 2
+    # ... after which the first element of the stream is pinned as a single channel: a pair in its place is a decode error (:117-121)
+    o = ao.AacFrontend(44100, 2)
+    o.decode(two.packet(extras=False)[0])
+    with pytest.raises(ao.AacError):
+        o.decode(stereo.packet(extras=False)[0])
+    with pytest.raises(SymgpuError) as e:
+        fe.decode(stereo.packet(extras=False)[0])
+    assert e.value.status == 1
+    fe.close()
+    # coupling channel and program config elements are unsupported (:154-157, :177-180); more than two channels at create
+    for eid in (2, 5):
+        w = ab.BitWriterMsb()
+        w.put(eid, 3), w.put(0, 13)
+        fe = frontend.AacFrontend(48000, 2)
+        with pytest.raises(SymgpuError) as e:
+            fe.decode(w.bytes())
+        assert e.value.status == 2
+        with pytest.raises(ao.AacError) as e3:
+            ao.AacFrontend(48000, 2).decode(w.bytes())
+        assert e3.value.kind == ao.UNSUPPORTED
+        fe.close()
+    for ch in (0, 3, 6):
+        with pytest.raises(SymgpuError) as e:
+            frontend.AacFrontend(44100, ch)
+        assert e.value.status == 2
+    # an empty packet and a lone terminator carry no element: nothing covered
+    fe = frontend.AacFrontend(44100, 2)
+    for pkt in (b"", b"\xe0"):
+        with pytest.raises(SymgpuError) as e:
+            fe.decode(pkt)
+        assert e.value.status == 2
+    fe.close()
+
+
+def test_predictor_and_gain_control_bits():
+    # predictor_data_present in a long-window ics_info is unsupported (ltp.rs:20-54), gain control data a decode error (ics/mod.rs:438-441)
+    def sce(predictor, gain):
+        w = ab.BitWriterMsb()
+        w.put(0, 3), w.put(0, 4), w.put(120, 8)
+        w.put(0, 1), w.put(0, 2), w.put(1, 1), w.put(0, 6), w.put(predictor, 1)   # ics_info, max_sfb = 0
+        w.put(0, 1), w.put(0, 1), w.put(gain, 1)                                  # pulse, tns, gain control
+        w.put(7, 3)
+        return w.bytes()
+    fe = frontend.AacFrontend(44100, 1)
+    units, tns, coeffs = fe.decode(sce(0, 0))
+    assert int(units[0]["window_shape"]) == 1 and len(tns) == 0 and not coeffs.any()
+    for pkt, status, kind in ((sce(1, 0), 2, ao.UNSUPPORTED), (sce(0, 1), 1, ao.DECODE)):
+        with pytest.raises(SymgpuError) as e:
+            fe.decode(pkt)
+        assert e.value.status == status
+        with pytest.raises(ao.AacError) as e2:
+            ao.AacFrontend(44100, 1).decode(pkt)
+        assert e2.value.kind == kind
+    fe.close()
+
+
+# ---- packets -> front-end -> synthesis oracle ------------------------------------------------------------------------------
+
+def test_front_end_output_feeds_the_synthesis_stage():
+    lib = _oracle.load()
+    for seed, s, _ in _streams(400, 6):
+        fe = frontend.AacFrontend(s.rate, s.channels)
+        n = 10
+        units = np.zeros((n, 2), dtype=nat.AAC_UNIT_DTYPE)
+        coeffs = np.zeros((n, 2, 1024), dtype=np.float32)
+        tns = []
+        for k in range(n):
+            u, t, c = fe.decode(s.packet()[0], tns_base=sum(len(x) for x in tns))
+            units[k], coeffs[k] = u, c
+            tns.append(t)
+        tns = np.concatenate(tns) if tns else np.zeros(0, dtype=nat.AAC_TNS_DTYPE)
+        fe.close()
+        # the host entry point's descriptor check accepts what the front-end emits
+        assert sb.lib().symgpu_aac_units_check(units.ctypes.data, tns.ctypes.data if len(tns) else None, len(tns), n) == 0
+        runs = np.zeros(1, dtype=nat.AAC_RUN_DTYPE)
+        runs[0]["n_frames"], runs[0]["channels"] = n, s.channels
+        rc, pcm = _oracle.aac_batch(lib, units, tns, coeffs, runs, 1)
+        assert rc == 0 and pcm.shape[0] == n
+        assert np.abs(pcm[np.isfinite(pcm)]).max() > 0

@@ -1,4 +1,4 @@
-"""Untrusted input: every host-side parser (packetisers, MP3 / Layer I-II / FLAC / Vorbis front-ends, plan + jobs, Vorbis mapping) built
+"""Untrusted input: every host-side parser (packetisers, MP3 / Layer I-II / FLAC / Vorbis / AAC front-ends, plan + jobs, Vorbis mapping) built
 with AddressSanitizer + UndefinedBehaviorSanitizer and driven with mutated streams (tests/cpp/fuzz_frontends.cpp).  Any
 out-of-bounds access, signed overflow, misaligned access or leak aborts the driver.  A 60 000-input run was clean when this
 was written; the suite runs a shorter one."""
@@ -11,6 +11,7 @@ from symphonia_b200 import workloads
 from tests import _flac_bitstream as fw
 from tests import _mp3_bitstream as bw
 from tests import _mpa12_bitstream as b12
+from tests import _aac_bitstream as ab
 from tests import _streams as st
 from tests import _vorbis_bitstream as vb
 
@@ -42,6 +43,10 @@ def _seeds(rng):
         vs = vb.Stream(np.random.default_rng(40 + k), residue_type=rtype)
         parts = [vs.ident, vs.setup] + [vs.packet()[0] for _ in range(10)]
         seeds[f"vorbis_fe{rtype}"] = b"VFE1" + b"".join(len(q).to_bytes(2, "little") + q for q in parts)
+    for k in range(3):
+        a = ab.Stream(np.random.default_rng(60 + k), rate=[44100, 48000, 8000][k], channels=2 - k % 2)
+        parts = [a.packet()[0] for _ in range(8)]
+        seeds[f"aac_fe{k}"] = b"AFE1" + bytes([k, 1 - k % 2]) + b"".join(len(q).to_bytes(2, "little") + q for q in parts)
     return seeds
 
 
@@ -50,7 +55,7 @@ def test_parsers_under_address_and_ub_sanitizers(tmp_path):
     exe = str(tmp_path / "fuzz_frontends")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-ffp-contract=off",
                            "-I/usr/local/cuda/include", "-o", exe, os.path.join(ROOT, "tests", "cpp", "fuzz_frontends.cpp")] +
-                          [os.path.join(csrc, f) for f in ("mp3_frontend.cpp", "mpa12_frontend.cpp", "flac_frontend.cpp", "vorbis_frontend.cpp", "packetizer.cpp", "tables.cpp")])
+                          [os.path.join(csrc, f) for f in ("mp3_frontend.cpp", "mpa12_frontend.cpp", "flac_frontend.cpp", "vorbis_frontend.cpp", "aac_frontend.cpp", "packetizer.cpp", "tables.cpp")])
     paths = []
     for name, blob in _seeds(np.random.default_rng(1)).items():
         path = str(tmp_path / (name + ".bin"))
@@ -60,4 +65,4 @@ def test_parsers_under_address_and_ub_sanitizers(tmp_path):
     env = dict(os.environ, FUZZ_ITERS="250", ASAN_OPTIONS="detect_leaks=1:abort_on_error=1")
     res = subprocess.run([exe] + paths, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
-    assert "no sanitizer report" in res.stdout and "3514 inputs" in res.stdout
+    assert "no sanitizer report" in res.stdout and "4267 inputs" in res.stdout
