@@ -137,3 +137,49 @@ def decode_ogg_vorbis(engine, data, fmt=nat.FMT_S16, serial=None):
     engine.vorbis_floors_set(plan["floors"])
     pcm = engine.vorbis_synth_host(plan["units"], plan["floor_y"], plan["residue"], plan["runs"], plan["slot"])
     return engine.pcm_pack_host(pcm, plan["spans"], plan["channels"], fmt, plan["total_frames"]), plan["sample_rate"]
+
+
+def adts_aac_plan(data):
+    """CPU half for an ADTS file: frames (symgpu_adts_index: header rules of adts.rs:130-309) -> raw_data_block payloads -> AAC-LC
+    entropy front-end (symgpu_aac_fe_*) -> the synthesis stage's batch.  The reader gives every frame 1024 samples and trims
+    nothing.  Returns dict(units [n,2], tns, coeffs [n,2,1024], runs, spans, channels, sample_rate, total_frames).  Packets the
+    front-end refuses are dropped, as a caller of the reference drops a DecodeError; the stream's parameters are the first
+    frame's (AdtsReader::try_new)."""
+    packets, _ = packetizer.adts_index(data)
+    if len(packets) == 0:
+        raise ValueError("no ADTS frames")
+    rate, channels = int(packets[0]["sample_rate"]), int(packets[0]["channels"])
+    if channels not in (1, 2):
+        raise ValueError("channel configuration outside AAC-LC mono / stereo")
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    fe = frontend.AacFrontend(rate, channels)
+    units, tns, coeffs, n_tns = [], [], [], 0
+    for pk in packets:
+        try:
+            u, t, c = fe.decode(buf[int(pk["offset"]):int(pk["offset"]) + int(pk["size"])].tobytes(), tns_base=n_tns)
+        except frontend.SymgpuError:
+            continue
+        units.append(u), tns.append(t), coeffs.append(c)
+        n_tns += len(t)
+    fe.close()
+    n = len(units)
+    runs = np.zeros(1, dtype=nat.AAC_RUN_DTYPE)
+    runs[0]["n_frames"], runs[0]["channels"] = n, channels
+    spans = np.zeros(n, dtype=nat.PCM_SPAN_DTYPE)
+    spans["src"] = np.arange(n, dtype=np.uint64) * 2048
+    spans["plane_stride"], spans["frames"] = 1024, 1024
+    spans["dst_frame"] = np.arange(n, dtype=np.uint64) * 1024
+    return dict(units=np.array(units, dtype=nat.AAC_UNIT_DTYPE).reshape(n, 2), tns=np.concatenate(tns) if n else np.zeros(0, dtype=nat.AAC_TNS_DTYPE),
+                coeffs=np.array(coeffs, dtype=np.float32).reshape(n, 2, 1024), runs=runs, spans=spans, channels=channels, sample_rate=rate,
+                total_frames=1024 * n)
+
+
+def decode_adts_aac(engine, data, fmt=nat.FMT_S16, stream=0):
+    """(samples [frames, channels] of `fmt`, sample_rate) of an ADTS AAC-LC file; stream slot `stream` of `engine` is reset first."""
+    plan = adts_aac_plan(data)
+    if len(plan["units"]) == 0:
+        return np.zeros((0, plan["channels"]), dtype=nat.FMT_NUMPY[fmt]), plan["sample_rate"]
+    plan["runs"]["stream"] = stream
+    engine.aac_stream_reset(stream)
+    pcm = engine.aac_synth_host(plan["units"], plan["tns"], plan["coeffs"], plan["runs"])
+    return engine.pcm_pack_host(pcm, plan["spans"], plan["channels"], fmt, plan["total_frames"]), plan["sample_rate"]

@@ -149,8 +149,10 @@ def mpa_tag_frame(rng, params, kind="Xing", flags=0xF, num_frames=1000, num_byte
 
 # ---------------------------------------------------------------------------------------------------- ADTS
 
-def adts_frame(rng, payload_len, rate_idx=4, channels=2, profile=1, protected=False, mpeg2=False, blocks=0, frame_len=None):
-    """ISO 13818-7 6.2 adts_fixed_header + adts_variable_header (+ crc), then a random payload."""
+def adts_frame(rng, payload_len, rate_idx=4, channels=2, profile=1, protected=False, mpeg2=False, blocks=0, frame_len=None, payload=None):
+    """ISO 13818-7 6.2 adts_fixed_header + adts_variable_header (+ crc), then a random payload (or `payload`)."""
+    if payload is not None:
+        payload_len = len(payload)
     hlen = 9 if protected else 7
     total = hlen + payload_len if frame_len is None else frame_len
     bits = (0xFFF << 44) | (int(mpeg2) << 43) | (0 << 41) | ((0 if protected else 1) << 40) | (profile << 38) | (rate_idx << 34) | \
@@ -158,7 +160,7 @@ def adts_frame(rng, payload_len, rate_idx=4, channels=2, profile=1, protected=Fa
     h = bits.to_bytes(7, "big")
     if protected:
         h += bytes(rng.integers(0, 256, 2, dtype=np.uint8))
-    return h + rng.integers(0, 256, payload_len, dtype=np.uint8).tobytes()
+    return h + (rng.integers(0, 256, payload_len, dtype=np.uint8).tobytes() if payload is None else bytes(payload))
 
 
 # ---------------------------------------------------------------------------------------------------- Ogg

@@ -15,3 +15,5 @@ SYMGPU_TEST_ENTROPY=1 timeout 600 python -m pytest tests/test_mp3_entropy_gpu.py
 timeout 600 python tools/mp3_file_e2e_bench.py > gpurun_out/mp3_file_e2e.json 2> gpurun_out/mp3_file_e2e.err; cat gpurun_out/mp3_file_e2e.json
 # 5. Vorbis-in-Ogg file bytes -> PCM (front-end on the CPU, verified synthesis + output stage on the GPU)
 SYMGPU_TEST_VORBIS_CHAIN=1 timeout 600 python -m pytest tests/test_zz_ogg_vorbis_to_pcm.py -m gpu -q > gpurun_out/vorbis_chain.log 2>&1; tail -3 gpurun_out/vorbis_chain.log
+# 6. ADTS file bytes -> PCM (AAC-LC front-end on the CPU, verified synthesis + output stage on the GPU)
+SYMGPU_TEST_AAC_CHAIN=1 timeout 600 python -m pytest tests/test_zz_adts_aac_to_pcm.py -m gpu -q > gpurun_out/aac_chain.log 2>&1; tail -3 gpurun_out/aac_chain.log
