@@ -495,6 +495,11 @@ typedef struct symgpu_vorbis_setup_info {   /* 160 bytes */
 } symgpu_vorbis_setup_info;
 symgpu_status symgpu_vorbis_setup_parse(const uint8_t* packet, size_t n, const symgpu_vorbis_ident* ident, symgpu_vorbis_setup_info* info,
                                         symgpu_vorbis_floor1* floors);
+/* End trims of the stream packets of ONE logical stream against the granule positions of the pages they end on
+ * (symphonia-format-ogg/src/logical.rs:164-302): page_sequence / page_absgp as in symgpu_ogg_packet, dur / discard from the
+ * codec mapping (symgpu_vorbis_packet_durations), all in stream order. */
+symgpu_status symgpu_ogg_page_end_trims(const uint32_t* page_sequence, const uint64_t* page_absgp, const uint32_t* dur,
+                                        const uint32_t* discard, size_t n, uint32_t* trim_end);
 /* Durations of a run of audio packets (VorbisPacketParser::parse_next_packet_dur, :62-106): heads[i] = the first
  * byte(s) of packet i packed little-endian (two bytes always suffice: 1 type bit + at most 6 mode bits), head_len[i] =
  * how many bytes of the packet exist (0, 1 or >= 2).  dur / discard in samples.  *prev_exp carries the previous block's

@@ -128,13 +128,15 @@ class GpuContext {
         symgpu_ctx* c = nullptr;
         symgpu_status st = symgpu_ctx_create(device, &c);
         if (st != SYMGPU_OK) return {nullptr, map_status(st)};
-        std::shared_ptr<GpuContext> g(new GpuContext(c, max_streams));
+        std::shared_ptr<GpuContext> g(new GpuContext(c, max_streams, device));
         st = symgpu_mp3_streams_alloc(c, max_streams);
+        if (st == SYMGPU_OK) st = symgpu_aac_streams_alloc(c, max_streams);
         if (st != SYMGPU_OK) return {nullptr, map_status(st)};
         return {g, {}};
     }
     ~GpuContext() { symgpu_ctx_destroy(ctx_); }
     symgpu_ctx* raw() const { return ctx_; }
+    int device() const { return device_; }
     int acquire_stream() {
         if (free_.empty()) return -1;
         const int s = free_.back();
@@ -144,10 +146,11 @@ class GpuContext {
     void release_stream(int s) { free_.push_back(s); }
 
   private:
-    GpuContext(symgpu_ctx* c, uint32_t n) : ctx_(c) {
+    GpuContext(symgpu_ctx* c, uint32_t n, int device) : ctx_(c), device_(device) {
         for (int i = (int)n - 1; i >= 0; --i) free_.push_back(i);
     }
     symgpu_ctx* ctx_;
+    int device_;
     std::vector<int> free_;
 };
 
@@ -281,12 +284,186 @@ class GpuMpaDecoder final : public AudioDecoder {
     uint32_t spec_rate_ = 0, spec_channels_ = 0;
 };
 
+// AAC-LC decoder whose filterbank runs on the GPU (mirrors AacDecoder, symphonia-codec-aac/src/aac/mod.rs:42-304).  A packet is
+// one raw_data_block, what the reference's AdtsReader and IsoMp4Reader emit.  Without extra data the stream parameters are the
+// codec parameters' (the ADTS case, mod.rs:64-78); with extra data the first two bytes of an AudioSpecificConfig are read:
+// object type (2 = LC), sampling-frequency index (an escape or an extension object type is Unsupported here), channel
+// configuration 1 or 2.
+class GpuAacDecoder final : public AudioDecoder {
+  public:
+    static Result<std::unique_ptr<AudioDecoder>> try_new(std::shared_ptr<GpuContext> gpu, const AudioCodecParameters& p,
+                                                         const AudioDecoderOptions&) {
+        if (p.codec != CODEC_ID_AAC) return {nullptr, {ErrorKind::Unsupported, "aac: invalid codec"}};
+        AudioCodecParameters params = p;
+        if (!p.extra_data.empty()) {
+            if (p.extra_data.size() < 2) return {nullptr, {ErrorKind::DecodeError, "aac: invalid data"}};
+            static const uint32_t kRates[13] = {96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000, 7350};
+            const uint32_t word = (uint32_t(p.extra_data[0]) << 8) | p.extra_data[1];
+            const uint32_t object_type = word >> 11, rate_idx = (word >> 7) & 15, channel_cfg = (word >> 3) & 15;
+            if (object_type != 2 || rate_idx > 12 || channel_cfg < 1 || channel_cfg > 2)
+                return {nullptr, {ErrorKind::Unsupported, "aac: aac too complex"}};
+            params.sample_rate = kRates[rate_idx], params.channels = channel_cfg;
+        }
+        if (params.sample_rate == 0) return {nullptr, {ErrorKind::Unsupported, "aac: sample rate is required"}};
+        if (params.channels == 0) return {nullptr, {ErrorKind::Unsupported, "aac: channels or channel layout is required"}};
+        if (params.channels > 2) return {nullptr, {ErrorKind::Unsupported, "aac: aac too complex"}};
+        const int slot = gpu->acquire_stream();
+        if (slot < 0) return {nullptr, {ErrorKind::LimitError, "symgpu: no free stream slot"}};
+        symgpu_aac_fe* fe = nullptr;
+        const symgpu_status st = symgpu_aac_fe_create(params.sample_rate, params.channels, &fe);
+        if (st != SYMGPU_OK) {
+            gpu->release_stream(slot);
+            return {nullptr, map_status(st)};
+        }
+        symgpu_aac_stream_reset(gpu->raw(), (uint32_t)slot);
+        return {std::unique_ptr<AudioDecoder>(new GpuAacDecoder(std::move(gpu), std::move(params), (uint32_t)slot, fe)), {}};
+    }
+    ~GpuAacDecoder() override {
+        gpu_->release_stream((int)stream_);
+        symgpu_aac_fe_destroy(fe_);
+    }
+    void reset() override {  // mod.rs:259-263: every pair's window history and delay lines
+        symgpu_aac_stream_reset(gpu_->raw(), stream_);
+        symgpu_aac_fe_reset(fe_);
+        frames_ = 0;
+    }
+    const AudioCodecParameters& codec_params() const override { return params_; }
+    Result<AudioBufferRef> decode(const Packet& packet) override {
+        frames_ = 0;  // buf.clear() on any error (mod.rs:274-277)
+        symgpu_aac_unit units[2];
+        uint32_t n_tns = 0;
+        symgpu_status st = symgpu_aac_fe_decode(fe_, packet.data, packet.len, 0, units, tns_, &n_tns, coeffs_.data());
+        if (st != SYMGPU_OK) return {{}, map_status(st)};
+        symgpu_aac_run run{};
+        run.stream = stream_, run.first_frame = 0, run.n_frames = 1, run.channels = (uint8_t)params_.channels;
+        st = symgpu_aac_synth_host(gpu_->raw(), units, n_tns ? tns_ : nullptr, n_tns, coeffs_.data(), &run, 1, 1, pcm_.data());
+        if (st != SYMGPU_OK) return {{}, map_status(st)};
+        frames_ = 1024;  // the reference's AAC decoder trims nothing (mod.rs:231-255)
+        return {last_decoded(), {}};
+    }
+    AudioBufferRef last_decoded() const override {
+        AudioBufferRef r;
+        r.n_planes = params_.channels;
+        r.frames = frames_;
+        r.planes[0] = pcm_.data();
+        r.planes[1] = pcm_.data() + 1024;
+        return r;
+    }
+
+  private:
+    GpuAacDecoder(std::shared_ptr<GpuContext> gpu, AudioCodecParameters p, uint32_t stream, symgpu_aac_fe* fe)
+        : gpu_(std::move(gpu)), params_(std::move(p)), stream_(stream), fe_(fe), coeffs_(2048, 0.0f), pcm_(2048, 0.0f) {}
+    std::shared_ptr<GpuContext> gpu_;
+    AudioCodecParameters params_;
+    uint32_t stream_;
+    symgpu_aac_fe* fe_;
+    symgpu_aac_tns tns_[16];
+    std::vector<float> coeffs_, pcm_;
+    size_t frames_ = 0;
+};
+
+// Vorbis decoder whose floor synthesis, inverse coupling, IMDCT and overlap-add run on the GPU (mirrors VorbisDecoder,
+// symphonia-codec-vorbis/src/lib.rs:48-420).  Extra data = the identification packet followed by the setup packet, as the Ogg
+// mapping hands them over (mappings/vorbis.rs:196-214).  The library registers Vorbis streams and floor tables per context, all
+// at once, so this decoder owns a context of its own on the shared context's device.
+class GpuVorbisDecoder final : public AudioDecoder {
+  public:
+    static Result<std::unique_ptr<AudioDecoder>> try_new(std::shared_ptr<GpuContext> gpu, const AudioCodecParameters& p,
+                                                         const AudioDecoderOptions& o) {
+        if (p.codec != CODEC_ID_VORBIS) return {nullptr, {ErrorKind::Unsupported, "vorbis: invalid codec type"}};
+        if (p.extra_data.size() <= 30) return {nullptr, {ErrorKind::Unsupported, "vorbis: missing extra data"}};
+        symgpu_vorbis_fe* fe = nullptr;
+        symgpu_status st = symgpu_vorbis_fe_create(p.extra_data.data(), 30, p.extra_data.data() + 30, p.extra_data.size() - 30, &fe);
+        if (st != SYMGPU_OK) return {nullptr, map_status(st)};
+        symgpu_vorbis_stream stream{};
+        std::vector<symgpu_vorbis_floor1> floors(64);
+        uint32_t n_floors = 0;
+        symgpu_vorbis_fe_config(fe, &stream, floors.data(), &n_floors);
+        symgpu_ctx* ctx = nullptr;
+        st = symgpu_ctx_create(gpu->device(), &ctx);
+        if (st == SYMGPU_OK) st = symgpu_vorbis_streams_set(ctx, &stream, 1);
+        if (st == SYMGPU_OK && n_floors) st = symgpu_vorbis_floors_set(ctx, floors.data(), n_floors);
+        if (st != SYMGPU_OK) {
+            symgpu_vorbis_fe_destroy(fe);
+            if (ctx) symgpu_ctx_destroy(ctx);
+            return {nullptr, map_status(st)};
+        }
+        AudioCodecParameters params = p;
+        params.channels = stream.channels;
+        return {std::unique_ptr<AudioDecoder>(new GpuVorbisDecoder(ctx, std::move(params), o, fe, stream)), {}};
+    }
+    ~GpuVorbisDecoder() override {
+        symgpu_vorbis_fe_destroy(fe_);
+        symgpu_ctx_destroy(ctx_);
+    }
+    void reset() override {  // lib.rs:336-338 -> dsp.rs:26-32: overlap cleared, no previous block
+        symgpu_vorbis_stream_reset(ctx_, 0);
+        symgpu_vorbis_fe_reset(fe_);
+        have_prev_ = false;
+        frames_ = 0;
+    }
+    const AudioCodecParameters& codec_params() const override { return params_; }
+    Result<AudioBufferRef> decode(const Packet& packet) override {
+        frames_ = first_ = 0;
+        symgpu_vorbis_unit unit;
+        symgpu_status st = symgpu_vorbis_fe_decode(fe_, packet.data, packet.len, slot_, 0, &unit, floor_y_, residue_.data());
+        if (st != SYMGPU_OK) return {{}, map_status(st)};
+        symgpu_vorbis_run run{};
+        run.stream = 0, run.first_packet = 0, run.n_packets = 1;
+        st = symgpu_vorbis_synth_host(ctx_, &unit, floor_y_, residue_.data(), &run, 1, 1, slot_, pcm_.data());
+        if (st != SYMGPU_OK) return {{}, map_status(st)};
+        const size_t prev_n = size_t(1) << (unit.prev_block_flag ? stream_.bs1_exp : stream_.bs0_exp);
+        const size_t n = size_t(1) << (unit.block_flag ? stream_.bs1_exp : stream_.bs0_exp);
+        frames_ = (prev_n + n) / 4;
+        if (opts_.gapless) {  // lib.rs:316-326
+            if (!have_prev_) {
+                frames_ = 0;  // the first packet after a reset is silenced
+            } else {
+                first_ = std::min<size_t>(packet.trim_start, frames_);
+                frames_ -= first_;
+                frames_ -= std::min<size_t>(packet.trim_end, frames_);
+            }
+        }
+        have_prev_ = true;
+        return {last_decoded(), {}};
+    }
+    AudioBufferRef last_decoded() const override {
+        AudioBufferRef r;
+        r.n_planes = params_.channels;
+        r.frames = frames_;
+        r.planes[0] = pcm_.data() + first_;
+        r.planes[1] = pcm_.data() + slot_ + first_;
+        return r;
+    }
+
+  private:
+    GpuVorbisDecoder(symgpu_ctx* ctx, AudioCodecParameters p, AudioDecoderOptions o, symgpu_vorbis_fe* fe, symgpu_vorbis_stream stream)
+        : ctx_(ctx), params_(std::move(p)), opts_(o), fe_(fe), stream_(stream), slot_((1u << stream.bs1_exp) >> 1),
+          residue_(2 * size_t(slot_), 0.0f), pcm_(2 * size_t(slot_), 0.0f) {}
+    symgpu_ctx* ctx_;
+    AudioCodecParameters params_;
+    AudioDecoderOptions opts_;
+    symgpu_vorbis_fe* fe_;
+    symgpu_vorbis_stream stream_;
+    uint32_t slot_;
+    uint16_t floor_y_[2 * 65];
+    std::vector<float> residue_, pcm_;
+    size_t frames_ = 0, first_ = 0;
+    bool have_prev_ = false;
+};
+
 // What an application does next to symphonia::default::register_enabled_codecs (symphonia/src/lib.rs:234-255).
 inline void register_gpu_decoders(CodecRegistry& registry, std::shared_ptr<GpuContext> gpu) {
     for (uint32_t codec : {CODEC_ID_MP1, CODEC_ID_MP2, CODEC_ID_MP3})
         registry.register_audio_decoder_at_tier(Tier::Preferred, codec, [gpu](const AudioCodecParameters& p, const AudioDecoderOptions& o) {
             return GpuMpaDecoder::try_new(gpu, p, o);
         });
+    registry.register_audio_decoder_at_tier(Tier::Preferred, CODEC_ID_AAC, [gpu](const AudioCodecParameters& p, const AudioDecoderOptions& o) {
+        return GpuAacDecoder::try_new(gpu, p, o);
+    });
+    registry.register_audio_decoder_at_tier(Tier::Preferred, CODEC_ID_VORBIS, [gpu](const AudioCodecParameters& p, const AudioDecoderOptions& o) {
+        return GpuVorbisDecoder::try_new(gpu, p, o);
+    });
 }
 
 } // namespace symgpu_host

@@ -1181,6 +1181,39 @@ inline Status vorbis_unpack_xiph_laced(const uint8_t* p, size_t n, Piece& ident,
     return Status::Ok;
 }
 
+// symphonia-format-ogg/src/logical.rs:164-302: end trims of the stream packets of one logical stream, page by page.  A page's
+// granule position is the time stamp one past the last valid sample of the last packet that ends on it; a packet whose end
+// (the running sum of decoded durations from the page's start) lies beyond that loses the excess, never more than it has left
+// after its leading discard.  A page starts where the previous page ended when that page also completed a stream packet (its
+// sequence number is the previous one's + 1), otherwise at end - total duration; a stream whose packets all end on one page
+// starts at -discard when that leaves padding at the end (the reference's single-page rule, applied here to "every stream
+// packet ends on the same page").
+inline void ogg_page_end_trims(const uint32_t* page_sequence, const uint64_t* page_absgp, const uint32_t* dur, const uint32_t* discard,
+                               size_t n, uint32_t* trim_end) {
+    bool single_page = true;
+    for (size_t i = 1; i < n; ++i) single_page = single_page && page_sequence[i] == page_sequence[0];
+    bool have_prev = false;
+    uint32_t prev_seq = 0;
+    int64_t prev_end = 0;
+    for (size_t i = 0; i < n;) {
+        size_t j = i;
+        int64_t tot = 0, disc = 0;
+        while (j < n && page_sequence[j] == page_sequence[i]) tot += dur[j], disc += discard[j], ++j;
+        const int64_t page_end = int64_t(page_absgp[i]);
+        int64_t start;
+        if (have_prev && prev_seq + 1 == page_sequence[i]) start = prev_end;
+        else if (single_page && tot >= disc + page_end) start = -disc;
+        else start = page_end - tot;
+        int64_t next = start;
+        for (size_t k = i; k < j; ++k) {
+            next += dur[k];
+            const int64_t left = int64_t(dur[k]) - int64_t(discard[k]);
+            trim_end[k] = next > page_end ? uint32_t(std::min<int64_t>(next - page_end, left < 0 ? 0 : left)) : 0u;
+        }
+        have_prev = true, prev_seq = page_sequence[i], prev_end = page_end, i = j;
+    }
+}
+
 // mappings/vorbis.rs:109-285: the per-stream state machine.  detect() on the first packet of the first page,
 // map() on every later packet.
 class OggVorbisMapper {

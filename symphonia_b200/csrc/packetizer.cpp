@@ -140,6 +140,13 @@ extern "C" symgpu_status symgpu_vorbis_setup_parse(const uint8_t* packet, size_t
 }
 static_assert(sizeof(symgpu_vorbis_setup_info) == 160, "record sizes are ABI");
 
+extern "C" symgpu_status symgpu_ogg_page_end_trims(const uint32_t* page_sequence, const uint64_t* page_absgp, const uint32_t* dur,
+                                                   const uint32_t* discard, size_t n, uint32_t* trim_end) {
+    if (n && (!page_sequence || !page_absgp || !dur || !discard || !trim_end)) return SYMGPU_ERR_ARG;
+    ogg_page_end_trims(page_sequence, page_absgp, dur, discard, n, trim_end);
+    return SYMGPU_OK;
+}
+
 extern "C" symgpu_status symgpu_vorbis_packet_durations(const symgpu_vorbis_ident* ident, uint32_t n_modes, uint64_t long_block_mask,
                                                         const uint16_t* heads, const uint8_t* head_len, size_t n_packets, uint8_t* prev_exp,
                                                         uint32_t* dur, uint32_t* discard) {

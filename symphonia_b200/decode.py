@@ -72,30 +72,8 @@ def ogg_vorbis_plan(data, serial=None):
     audio = [(pk, b) for pk, b in zip(mine[at + 1:], blobs[at + 1:]) if len(b) and (b[0] & 1) == 0]
     dur, discard, _ = packetizer.vorbis_packet_durations(ident, n_modes, mask, [b for _, b in audio])
     dur, discard = dur.astype(np.int64), discard.astype(np.int64)
-    # time line, page by page
-    trim_end = np.zeros(len(audio), dtype=np.int64)
-    seqs = np.array([int(pk["page_sequence"]) for pk, _ in audio], dtype=np.int64)
-    single_page = len(set(seqs.tolist())) == 1
-    prev_seq, prev_end, i = None, None, 0
-    while i < len(audio):
-        j = i
-        while j < len(audio) and seqs[j] == seqs[i]:
-            j += 1
-        page_end = int(np.int64(np.uint64(audio[i][0]["page_absgp"])))
-        tot, disc = int(dur[i:j].sum()), int(discard[i:j].sum())
-        if prev_end is not None and prev_seq + 1 == seqs[i]:
-            start = prev_end
-        elif single_page and tot >= disc + page_end:
-            start = -disc
-        else:
-            start = page_end - tot
-        nxt = start
-        for k in range(i, j):
-            nxt += int(dur[k])
-            left = int(dur[k]) - int(discard[k])
-            if nxt > page_end:
-                trim_end[k] = min(nxt - page_end, left)
-        prev_seq, prev_end, i = int(seqs[i]), page_end, j
+    trim_end = packetizer.ogg_page_end_trims([int(pk["page_sequence"]) for pk, _ in audio], [int(pk["page_absgp"]) for pk, _ in audio],
+                                             dur, discard).astype(np.int64)
     fe = frontend.VorbisFrontend(ident_b, setup_b)
     slot = fe.slot
     units, fy, res, keep = [], [], [], []

@@ -122,3 +122,14 @@ def vorbis_setup_parse(packet, ident):
     floors = np.zeros(64, dtype=nat.VORBIS_FLOOR1_DTYPE)
     _check(nat.lib().symgpu_vorbis_setup_parse(p, a.size, _vp(idb.ctypes.data), _vp(info.ctypes.data), _vp(floors.ctypes.data)), "symgpu_vorbis_setup_parse")
     return info[0], floors[:int(info[0]["n_floors"])]
+
+
+def ogg_page_end_trims(page_sequence, page_absgp, dur, discard):
+    """End trims of one logical stream's packets against the granule positions of the pages they end on (logical.rs:164-302)."""
+    seq = np.ascontiguousarray(page_sequence, dtype=np.uint32)
+    gp = np.ascontiguousarray(page_absgp, dtype=np.uint64)
+    d, c = np.ascontiguousarray(dur, dtype=np.uint32), np.ascontiguousarray(discard, dtype=np.uint32)
+    out = np.zeros(len(seq), dtype=np.uint32)
+    _check(nat.lib().symgpu_ogg_page_end_trims(_vp(seq.ctypes.data), _vp(gp.ctypes.data), _vp(d.ctypes.data), _vp(c.ctypes.data), len(seq),
+                                               _vp(out.ctypes.data)), "symgpu_ogg_page_end_trims")
+    return out

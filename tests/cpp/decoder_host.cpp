@@ -4,6 +4,9 @@
 //                                    time (BASELINE config 0 "plumbing") and write planar PCM
 //   decoder_host file LAYER IN OUT   GPU tier: an MPEG audio FILE end to end in C++ -- packetiser (packetizer.hpp), registry,
 //                                    GpuMpaDecoder::decode on real frames with the packetiser's gapless trims -- planar PCM out
+//   decoder_host file aac IN OUT     GPU tier: an ADTS file: frame index, registry, GpuAacDecoder::decode per raw_data_block
+//   decoder_host file vorbis IN OUT  GPU tier: a Vorbis-in-Ogg file: pages -> packets -> mapping (durations, discards, end trims
+//                                    against the page granule positions), registry, GpuVorbisDecoder::decode per audio packet
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -145,10 +148,107 @@ static int run_file(int layer, const char* in_path, const char* out_path) {
     return 0;
 }
 
+static int write_planes(std::ofstream& out, const AudioBufferRef& b) {
+    for (size_t ch = 0; ch < b.n_planes; ++ch) out.write(reinterpret_cast<const char*>(b.planes[ch]), (std::streamsize)(b.frames * sizeof(float)));
+    return 0;
+}
+
+static int run_adts(const char* in_path, const char* out_path) {
+    std::ifstream in(in_path, std::ios::binary);
+    std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    size_t count = 0;
+    symgpu_status stop;
+    if (symgpu_adts_index(bytes.data(), bytes.size(), nullptr, 0, &count, &stop) != SYMGPU_OK || count == 0) return 5;
+    std::vector<symgpu_adts_packet> packets(count);
+    symgpu_adts_index(bytes.data(), bytes.size(), packets.data(), count, &count, &stop);
+    auto gpu = GpuContext::create(0, 2);
+    if (!gpu.ok()) {
+        std::fprintf(stderr, "%s\n", gpu.error.message);
+        return 2;
+    }
+    CodecRegistry reg;
+    register_gpu_decoders(reg, gpu.value);
+    AudioCodecParameters params;
+    params.codec = CODEC_ID_AAC, params.sample_rate = packets[0].sample_rate, params.channels = packets[0].channels;
+    auto dec = reg.make_audio_decoder(params, AudioDecoderOptions{});
+    if (!dec.ok()) return 3;
+    std::ofstream out(out_path, std::ios::binary);
+    size_t good = 0, samples = 0;
+    for (const auto& pk : packets) {
+        Packet p;
+        p.data = bytes.data() + pk.offset, p.len = pk.size, p.pts = (uint64_t)pk.pts, p.dur = 1024;
+        auto res = dec.value->decode(p);
+        if (!res.ok()) continue;
+        ++good, samples += res.value.frames;
+        write_planes(out, res.value);
+    }
+    std::printf("decoded %zu of %zu packets, %zu samples per channel\n", good, packets.size(), samples);
+    return 0;
+}
+
+static int run_ogg_vorbis(const char* in_path, const char* out_path) {
+    using namespace symgpu::packet;
+    std::ifstream in(in_path, std::ios::binary);
+    std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    OggIndex ix;
+    OggIndex::build(bytes.data(), bytes.size(), ix, false);
+    if (ix.streams.empty()) return 5;
+    auto& stream = ix.streams.begin()->second;
+    OggVorbisMapper mapper;
+    std::vector<std::vector<uint8_t>> audio;
+    std::vector<uint32_t> seq, dur, discard;
+    std::vector<uint64_t> absgp;
+    bool first = true;
+    for (const OggPacket& pk : stream.packets()) {
+        std::vector<uint8_t> b(pk.len);
+        stream.gather(bytes.data(), pk, b.data());
+        if (first) {
+            first = false;
+            if (!mapper.detect(b.data(), b.size())) return 6;
+            continue;
+        }
+        const auto m = mapper.map(b.data(), b.size());
+        if (m.kind != OggVorbisMapper::Kind::Audio || !mapper.ready()) continue;
+        seq.push_back(pk.page_sequence), absgp.push_back(pk.page_absgp), dur.push_back((uint32_t)m.dur), discard.push_back((uint32_t)m.discard);
+        audio.push_back(std::move(b));
+    }
+    std::vector<uint32_t> trim_end(audio.size());
+    symgpu_ogg_page_end_trims(seq.data(), absgp.data(), dur.data(), discard.data(), audio.size(), trim_end.data());
+    auto gpu = GpuContext::create(0, 2);
+    if (!gpu.ok()) {
+        std::fprintf(stderr, "%s\n", gpu.error.message);
+        return 2;
+    }
+    CodecRegistry reg;
+    register_gpu_decoders(reg, gpu.value);
+    AudioCodecParameters params;
+    params.codec = CODEC_ID_VORBIS, params.sample_rate = mapper.ident().sample_rate, params.channels = mapper.ident().n_channels;
+    params.extra_data = mapper.extra_data();
+    auto dec = reg.make_audio_decoder(params, AudioDecoderOptions{});
+    if (!dec.ok()) {
+        std::fprintf(stderr, "%s\n", dec.error.message);
+        return 3;
+    }
+    std::ofstream out(out_path, std::ios::binary);
+    size_t good = 0, samples = 0;
+    for (size_t k = 0; k < audio.size(); ++k) {
+        Packet p;
+        p.data = audio[k].data(), p.len = audio[k].size(), p.dur = dur[k], p.trim_start = discard[k], p.trim_end = trim_end[k];
+        auto res = dec.value->decode(p);
+        if (!res.ok()) continue;
+        ++good, samples += res.value.frames;
+        write_planes(out, res.value);
+    }
+    std::printf("decoded %zu of %zu packets, %zu samples per channel\n", good, audio.size(), samples);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "registry") return test_registry();
     if (argc >= 4 && std::string(argv[1]) == "decode") return run_decode(argv[2], argv[3]);
+    if (argc >= 5 && std::string(argv[1]) == "file" && std::string(argv[2]) == "aac") return run_adts(argv[3], argv[4]);
+    if (argc >= 5 && std::string(argv[1]) == "file" && std::string(argv[2]) == "vorbis") return run_ogg_vorbis(argv[3], argv[4]);
     if (argc >= 5 && std::string(argv[1]) == "file") return run_file(std::atoi(argv[2]), argv[3], argv[4]);
-    std::fprintf(stderr, "usage: decoder_host registry | decode IN OUT | file LAYER IN OUT\n");
+    std::fprintf(stderr, "usage: decoder_host registry | decode IN OUT | file LAYER|aac|vorbis IN OUT\n");
     return 64;
 }
