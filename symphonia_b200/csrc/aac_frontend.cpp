@@ -27,11 +27,15 @@ namespace {
 struct Book {
     std::vector<int32_t> node;  // pairs: child for bit 0, child for bit 1; >= 0 inner node index, < 0: ~value
     uint32_t max_len = 0;
+    uint16_t lut[1024];         // the next 10 bits -> value << 5 | length for codes of <= 10 bits, 0 for longer ones
     void build(const uint32_t* words, size_t n) {
         node.assign(2, 0);
+        std::memset(lut, 0, sizeof lut);
         for (size_t v = 0; v < n; ++v) {
             const uint32_t len = words[v] >> 24, code = words[v] & 0xffffff;
             if (len > max_len) max_len = len;
+            if (len <= 10)
+                for (uint32_t k = 0; k < (1u << (10 - len)); ++k) lut[(code << (10 - len)) | k] = uint16_t(v << 5 | len);
             size_t at = 0;
             for (uint32_t b = len; b-- > 0;) {
                 const uint32_t bit = (code >> b) & 1;
@@ -106,15 +110,26 @@ const uint8_t kTnsMaxShort[12] = {9, 9, 10, 14, 14, 14, 14, 14, 14, 14, 14, 14};
 // ---- BitReaderLtr + FiniteBitStream: a failed read fails the packet, so only positions matter ----------------------------
 struct Bits {
     const uint8_t* p;
-    size_t n_bits, at = 0;
+    size_t n_bytes, n_bits, at = 0;
     bool ok = true;  // false: a read ran past the end (end_of_bitstream_error)
-    Bits(const uint8_t* d, size_t n) : p(d), n_bits(n * 8) {}
+    Bits(const uint8_t* d, size_t n) : p(d), n_bytes(n), n_bits(n * 8) {}
     size_t left() const { return n_bits - at; }
-    uint32_t bit_at(size_t i) const { return i < n_bits ? (p[i >> 3] >> (7 - (i & 7))) & 1u : 0u; }
-    uint32_t read(uint32_t w) {
+    // The stream from `at` on, first bit in bit 63, zeros past the end; at least 57 bits are real or padding.
+    uint64_t peek() const {
+        const size_t byte = at >> 3;
+        uint64_t v = 0;
+        if (byte + 8 <= n_bytes) {
+            std::memcpy(&v, p + byte, 8);
+            v = __builtin_bswap64(v);
+        } else {
+            for (size_t k = 0; k < 8; ++k) v = (v << 8) | (byte + k < n_bytes ? p[byte + k] : 0u);
+        }
+        return v << (at & 7);
+    }
+    uint32_t read(uint32_t w) {  // w <= 32
         if (!ok || w > left()) return ok = false, 0;
-        uint32_t v = 0;
-        for (uint32_t k = 0; k < w; ++k) v = (v << 1) | bit_at(at + k);
+        if (w == 0) return 0;
+        const uint32_t v = uint32_t(peek() >> (64 - w));
         at += w;
         return v;
     }
@@ -128,15 +143,30 @@ struct Bits {
         uint32_t n = 0;
         for (;;) {
             if (!ok || at >= n_bits) return ok = false, 0;
-            if (!bit_at(at++)) return n;
-            ++n;
+            const uint64_t v = peek() | ((uint64_t(1) << 7) - 1);  // only the top 57 bits are the stream
+            const uint32_t ones = uint32_t(__builtin_clzll(~v));    // <= 57
+            if (ones >= 57) {
+                n += 57, at += 57;
+                continue;
+            }
+            if (at + ones >= n_bits) return ok = false, 0;  // the ones run into the end: no terminating zero
+            n += ones, at += ones + 1;
+            return n;
         }
     }
     uint32_t codebook(const Book& b) {  // bit.rs:771-808: matched against the data padded with zeros, then must fit
         if (!ok) return 0;
+        const uint64_t v = peek();
+        const uint32_t e = b.lut[v >> 54];
+        if (e) {
+            const uint32_t len = e & 31;
+            if (len > left()) return ok = false, 0;
+            at += len;
+            return e >> 5;
+        }
         size_t node = 0;
         for (uint32_t len = 1; len <= b.max_len; ++len) {
-            const int32_t next = b.node[2 * node + bit_at(at + len - 1)];
+            const int32_t next = b.node[2 * node + ((v >> (64 - len)) & 1)];
             if (next < 0) {
                 if (len > left()) return ok = false, 0;
                 at += len;
