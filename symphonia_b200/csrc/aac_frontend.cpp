@@ -144,7 +144,7 @@ struct Bits {
         for (;;) {
             if (!ok || at >= n_bits) return ok = false, 0;
             const uint64_t v = peek() | ((uint64_t(1) << 7) - 1);  // only the top 57 bits are the stream
-            const uint32_t ones = uint32_t(__builtin_clzll(~v));    // <= 57
+            const uint32_t ones = ~v ? uint32_t(__builtin_clzll(~v)) : 64u;  // the run of ones at the front
             if (ones >= 57) {
                 n += 57, at += 57;
                 continue;

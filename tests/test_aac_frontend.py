@@ -256,3 +256,47 @@ def test_front_end_output_feeds_the_synthesis_stage():
         rc, pcm = _oracle.aac_batch(lib, units, tns, coeffs, runs, 1)
         assert rc == 0 and pcm.shape[0] == n
         assert np.abs(pcm[np.isfinite(pcm)]).max() > 0
+
+
+def test_escape_prefix_lengths():
+    """read_escape (ics/mod.rs:598-607): up to eight ones are a prefix, nine or more a decode error, ones to the end of the packet
+    the end of the bitstream -- including runs longer than one machine word."""
+    def packet(n_ones, tail_zero=True, word=0):
+        w = ab.BitWriterMsb()
+        w.put(0, 3), w.put(0, 4), w.put(140, 8)                                   # SCE, global gain
+        w.put(0, 1), w.put(0, 2), w.put(0, 1), w.put(1, 6), w.put(0, 1)           # ics_info: long, sine, max_sfb 1
+        w.put(11, 4), w.put(1, 5)                                                 # one section: book 11, one band
+        w.huff("scf", 60)                                                         # scale factor = global gain
+        w.put(0, 1), w.put(0, 1), w.put(0, 1)                                     # no pulse, no TNS, no gain control
+        w.huff("11", 17 * 16 + 1), w.put(1, 1), w.put(0, 1)                       # (16, 1): signs -, +
+        for _ in range(n_ones):
+            w.put(1, 1)
+        if tail_zero:
+            w.put(0, 1)
+            w.put(word, min(n_ones, 8) + 4)
+            w.huff("11", 0)                                                       # the band's second pair: (0, 0)
+            w.put(7, 3)
+        else:
+            while len(w.bits) % 8:                                                # ones all the way to the end of the packet
+                w.put(1, 1)
+        return w.bytes()
+    for n_ones, tail, status in ((0, True, 0), (8, True, 0), (9, True, 1), (56, True, 1), (57, True, 1), (58, True, 1), (130, True, 1),
+                                 (40, False, 1), (57, False, 1), (64, False, 1), (200, False, 1)):
+        pkt = packet(n_ones, tail, word=5)
+        fe, o = frontend.AacFrontend(44100, 1), ao.AacFrontend(44100, 1)
+        try:
+            _, want = o.decode(pkt)
+            got_status = 0
+        except ao.AacError as e:
+            got_status = 1 if e.kind == ao.DECODE else 2
+        assert got_status == status, (n_ones, tail)
+        if status:
+            with pytest.raises(SymgpuError) as e2:
+                fe.decode(pkt)
+            assert e2.value.status == status, (n_ones, tail)
+        else:
+            units, tns, coeffs = fe.decode(pkt)
+            assert np.array_equal(u32(coeffs[0]), u32(want[0]["coeffs"]))
+            v = (1 << (n_ones + 4)) + 5
+            assert float(coeffs[0][0]) == -float(ab.pow43(v) * ab.scale_normal(140)) and float(coeffs[0][1]) == float(ab.scale_normal(140))
+        fe.close()
