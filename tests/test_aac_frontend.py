@@ -300,3 +300,134 @@ def test_escape_prefix_lengths():
             v = (1 << (n_ones + 4)) + 5
             assert float(coeffs[0][0]) == -float(ab.pow43(v) * ab.scale_normal(140)) and float(coeffs[0][1]) == float(ab.scale_normal(140))
         fe.close()
+
+
+# ---- boundary cases found by mutating the front-end (tools/mutate_frontend.py): each pins one rule at its edge ---------------
+
+def _sce(gg, max_sfb, sections, scf=(), pulse=None, tns=None, spectral=(), short=False, trailing=((7, 3),), rate=44100, channels=1):
+    """A hand-built single_channel_element: sections [(book, length)], scf [('pcm', v) | ('d', diff)], pulse (start, [(off, amp)]),
+    tns [(value, width)] after the presence bit, spectral [(book, index)], trailing [(value, width)].  Returns the packet."""
+    w = ab.BitWriterMsb()
+    w.put(0, 3), w.put(0, 4), w.put(gg, 8)
+    if short:
+        w.put(0, 1), w.put(2, 2), w.put(0, 1), w.put(max_sfb, 4)
+        for _ in range(7):
+            w.put(1, 1)                                    # one group of eight windows
+    else:
+        w.put(0, 1), w.put(0, 2), w.put(0, 1), w.put(max_sfb, 6), w.put(0, 1)
+    for cb, n in sections:
+        w.put(cb, 4), w.put(n, 3 if short else 5)
+    for kind, v in scf:
+        w.put(v, 9) if kind == "pcm" else w.huff("scf", v + 60)
+    if pulse is None:
+        w.put(0, 1)
+    else:
+        w.put(1, 1), w.put(len(pulse[1]) - 1, 2), w.put(pulse[0], 6)
+        for off, amp in pulse[1]:
+            w.put(off, 5), w.put(amp, 4)
+    if tns is None:
+        w.put(0, 1)
+    else:
+        w.put(1, 1)
+        for v, width in tns:
+            w.put(v, width)
+    w.put(0, 1)
+    for book, idx in spectral:
+        w.huff(book, idx)
+    for v, width in trailing:
+        w.put(v, width)
+    return w.bytes()
+
+
+def _both_status(pkt, rate=44100, channels=1):
+    """(status, oracle result or None, front-end result or None); the two must agree."""
+    fe, o = frontend.AacFrontend(rate, channels), ao.AacFrontend(rate, channels)
+    try:
+        covered, want = o.decode(pkt)
+        status = 0 if covered == channels else 2
+    except ao.AacError as e:
+        status, want = (1 if e.kind == ao.DECODE else 2), None
+    try:
+        got = fe.decode(pkt)
+        got_status = 0
+    except SymgpuError as e:
+        got, got_status = None, e.status
+    fe.close()
+    assert got_status == status
+    if status == 0:
+        for c in range(channels):
+            assert np.array_equal(u32(got[2][c]), u32(want[c]["coeffs"]))
+    return status, want, got
+
+
+QUAD_ZERO = ("1", 40)   # book 1, the all-zero quad (digits 1 1 1 1)
+
+
+def test_element_loop_stops_with_three_bits_left():
+    # mod.rs:131 `while bs.bits_left() > 3`: 29 bits of element, 3 zero bits of padding -- which would read as another SCE id
+    pkt = _sce(120, 0, [], trailing=())
+    assert len(pkt) == 4
+    assert _both_status(pkt)[0] == 0
+    # four bits left: the loop goes round again, reads element id 0 and runs out of data
+    assert _both_status(_sce(120, 0, [], trailing=((0, 1),)) + b"")[0] == 0          # 30 bits + 2 padding
+    assert _both_status(_sce(120, 0, [], trailing=((0, 4),)) + b"\x00")[0] == 1       # a whole zero byte more: SCE, then nothing
+
+
+def test_section_rules_at_their_edges():
+    # 64 empty sections are the limit: the 65th is refused even though it would be valid (ics/mod.rs:243-246)
+    assert _both_status(_sce(120, 1, [(0, 0)] * 63 + [(0, 1)]))[0] == 0
+    assert _both_status(_sce(120, 1, [(0, 0)] * 64 + [(0, 1)]))[0] == 1
+    # book 12 is reserved (:251-253)
+    assert _both_status(_sce(120, 2, [(12, 2)], scf=[("d", 0), ("d", 0)]))[0] == 1    # complete but for the band type
+    assert _both_status(_sce(120, 2, [(15, 2)], scf=[("d", 0), ("d", 0)]))[0] == 0
+    assert _both_status(_sce(120, 2, [(0, 2)]))[0] == 0
+    # a section may end at max_sfb, not beyond (:265)
+    assert _both_status(_sce(120, 2, [(0, 3)]))[0] == 1
+    # max_sfb may name every band, not one more (:292-300): 14 short bands at 48 kHz
+    assert _both_status(_sce(120, 14, [(0, 6), (0, 6), (0, 2)], short=True), rate=48000)[0] == 0
+    assert _both_status(_sce(120, 15, [(0, 6), (0, 6), (0, 3)], short=True), rate=48000)[0] == 1
+
+
+def test_scale_factor_ranges_at_their_edges():
+    # normal: index 255 is the last valid (ics/mod.rs:344-347)
+    st, want, _ = _both_status(_sce(255, 1, [(1, 1)], scf=[("d", 0)], spectral=[QUAD_ZERO]))
+    assert st == 0
+    assert _both_status(_sce(255, 1, [(1, 1)], scf=[("d", 1)], spectral=[QUAD_ZERO]))[0] == 1
+    assert _both_status(_sce(0, 1, [(1, 1)], scf=[("d", -1)], spectral=[QUAD_ZERO]))[0] == 1
+    # noise: global gain 100 -> 110, first value 9 bits offset by 256 (:326-336); index 0 valid, -1 not
+    assert _both_status(_sce(100, 1, [(13, 1)], scf=[("pcm", 146)]))[0] == 0
+    assert _both_status(_sce(100, 1, [(13, 1)], scf=[("pcm", 145)]))[0] == 1
+    # intensity: starts at 155; 255 valid, 256 not (:316-323)
+    assert _both_status(_sce(100, 2, [(15, 2)], scf=[("d", 60), ("d", 40)]))[0] == 0
+    assert _both_status(_sce(100, 2, [(15, 2)], scf=[("d", 60), ("d", 41)]))[0] == 1
+
+
+def test_tns_order_and_pulse_rules_at_their_edges():
+    # long window, AAC-LC: order 12 is the limit (tns.rs:118-128, :52): n_filt 1, coef_res 0, length 10, order, direction 0, compress 0, 3-bit values
+    def tns(order):
+        return [(1, 2), (0, 1), (10, 6), (order, 5), (0, 1), (0, 1)] + [(3, 3)] * order
+    st, want, got = _both_status(_sce(120, 4, [(0, 4)], tns=tns(12)))
+    assert st == 0 and len(got[1]) == 1 and int(got[1][0]["order"]) == 12
+    assert _both_status(_sce(120, 4, [(0, 4)], tns=tns(13)))[0] == 1
+    # pulse data in a short window is refused (ics/mod.rs:427)
+    assert _both_status(_sce(120, 1, [(0, 1)], pulse=(0, [(1, 1)]), short=True))[0] == 1
+    assert _both_status(_sce(120, 1, [(0, 1)], pulse=(0, [(1, 1)])))[0] == 0
+    # pulses stop at line 1024 (pulse.rs:78-80): last band of the 48 kHz table starts at 928; 31 + 31 + 31 + 3 = 96
+    n_bands = len(ao.L48) - 1
+    st, want, got = _both_status(_sce(150, n_bands, [(0, 30), (0, n_bands - 30)], pulse=(n_bands - 1, [(31, 3), (31, 2), (31, 1), (3, 7)])), rate=48000)
+    assert st == 0 and np.count_nonzero(got[2][0]) == 0      # zero scale: every restored line is a signed zero
+    assert [bool(np.signbit(got[2][0][928 + k])) for k in (31, 62, 93)] == [True, True, True] and not np.signbit(got[2][0][1023])
+
+
+def test_ms_mask_three_is_refused():
+    def cpe(mask):
+        w = ab.BitWriterMsb()
+        w.put(1, 3), w.put(0, 4), w.put(1, 1)                                            # CPE, common window
+        w.put(0, 1), w.put(0, 2), w.put(0, 1), w.put(0, 6), w.put(0, 1)                   # ics_info, max_sfb 0
+        w.put(mask, 2)
+        for _ in range(2):
+            w.put(120, 8), w.put(0, 1), w.put(0, 1), w.put(0, 1)                          # gain, no pulse / TNS / gain control
+        w.put(7, 3)
+        return w.bytes()
+    assert _both_status(cpe(2), channels=2)[0] == 0
+    assert _both_status(cpe(3), channels=2)[0] == 1

@@ -47,6 +47,14 @@ def _seeds(rng):
         a = ab.Stream(np.random.default_rng(60 + k), rate=[44100, 48000, 8000][k], channels=2 - k % 2)
         parts = [a.packet()[0] for _ in range(8)]
         seeds[f"aac_fe{k}"] = b"AFE1" + bytes([k, 1 - k % 2]) + b"".join(len(q).to_bytes(2, "little") + q for q in parts)
+    # hand-built edge packets (pulses that run to line 1024, the last valid scale-factor indices, 64 sections, TNS order 12)
+    from tests.test_aac_frontend import _sce
+    n_bands = 49
+    edge = [_sce(150, n_bands, [(0, 30), (0, n_bands - 30)], pulse=(n_bands - 1, [(31, 3), (31, 2), (31, 1), (3, 7)])),
+            _sce(255, 1, [(1, 1)], scf=[("d", 0)], spectral=[("1", 40)]), _sce(100, 2, [(15, 2)], scf=[("d", 60), ("d", 40)]),
+            _sce(120, 1, [(0, 0)] * 63 + [(0, 1)]),
+            _sce(120, 4, [(0, 4)], tns=[(1, 2), (0, 1), (10, 6), (12, 5), (0, 1), (0, 1)] + [(3, 3)] * 12)]
+    seeds["aac_fe_edge"] = b"AFE1" + bytes([1, 0]) + b"".join(len(q).to_bytes(2, "little") + q for q in edge)
     return seeds
 
 
@@ -65,4 +73,4 @@ def test_parsers_under_address_and_ub_sanitizers(tmp_path):
     env = dict(os.environ, FUZZ_ITERS="250", ASAN_OPTIONS="detect_leaks=1:abort_on_error=1")
     res = subprocess.run([exe] + paths, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
-    assert "no sanitizer report" in res.stdout and "4267 inputs" in res.stdout
+    assert "no sanitizer report" in res.stdout and "4518 inputs" in res.stdout
