@@ -135,7 +135,7 @@ class Book:
 class Stream:
     """A whole logical stream's headers + a packet generator with ground truth."""
 
-    def __init__(self, rng, channels=2, bs_exp=(7, 9), residue_type=None, coupled=None, per_word=None):
+    def __init__(self, rng, channels=2, bs_exp=(7, 9), residue_type=None, coupled=None, per_word=None, residue_begin=None):
         self.rng, self.channels, self.bs_exp = rng, channels, bs_exp
         self.ident = vorbis_ident(channels=channels, bs0=bs_exp[0], bs1=bs_exp[1])
         books = []
@@ -203,8 +203,10 @@ class Stream:
             rtype = int(rng.integers(3)) if residue_type is None else residue_type
             n2_short = (1 << bs_exp[0]) >> 1
             part_size = int(rng.choice([8, 16]))
-            begin = int(rng.choice([0, part_size]))
+            begin = int(rng.choice([0, part_size])) if residue_begin is None else residue_begin
             end = int(rng.choice([n2_short, (1 << bs_exp[1]) >> 1, 1 << bs_exp[1], 3 * part_size + begin]))
+            if end < begin:   # (a setup header with end < begin is refused, residue.rs:88-90)
+                end = begin + 3 * part_size
             w.put(rtype, 16), w.put(begin, 24), w.put(end, 24), w.put(part_size - 1, 24)
             w.put(self.classifications - 1, 6), w.put(class_book, 8)
             used = []

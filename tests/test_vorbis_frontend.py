@@ -259,3 +259,100 @@ def test_front_end_output_feeds_the_synthesis_oracle():
         assert rc == 0
         assert np.isfinite(pcm).all()
         assert np.abs(pcm).max() > 0.0
+
+
+# ---- boundary cases found by mutating the front-end (tools/mutate_frontend.py) -----------------------------------------------
+
+def test_mode_number_beyond_the_mode_list_is_refused():
+    # lib.rs:158-163: with three modes the field is two bits wide and the value 3 names no mode
+    seed = 0
+    while True:
+        s = vb.Stream(np.random.default_rng(8000 + seed))
+        if len(s.modes) == 3:
+            break
+        seed += 1
+    fe, o = frontend.VorbisFrontend(s.ident, s.setup), vo.VorbisFrontend(s.ident, s.setup)
+    for mode, ok in ((0, True), (2, True), (3, False)):
+        pkt = bytes([mode << 1]) + bytes(40)       # audio packet, mode number, everything after it zero
+        if ok:
+            _both(fe, o, pkt, fe.slot, ("mode", mode))
+        else:
+            with pytest.raises(po.ReaderError):
+                o.decode(pkt, fe.slot)
+            with pytest.raises(SymgpuError) as e:
+                fe.decode(pkt)
+            assert e.value.status == 1
+    fe.close()
+
+
+def test_residue_that_begins_beyond_the_short_block():
+    # residue.rs:150-160: begin and end are both limited to the block's vector, a residue that starts beyond a short block codes
+    # nothing there (and everything it has in the long block)
+    for seed in range(6):
+        rng = np.random.default_rng(8100 + seed)
+        s = vb.Stream(rng, bs_exp=(7, 9), residue_begin=96, residue_type=seed % 3)   # short vectors are 64 long (128 interleaved)
+        fe, o = frontend.VorbisFrontend(s.ident, s.setup), vo.VorbisFrontend(s.ident, s.setup)
+        flags = set()
+        for k in range(12):
+            pkt, truth = s.packet()
+            want = _both(fe, o, pkt, fe.slot, (seed, k))
+            flags.add(bool(want["block_flag"]))
+            if s.per_word == 1:
+                _same(want, truth, (seed, k, "truth"))
+        fe.close()
+
+
+def _patched_book(monkeypatch, which, **change):
+    """Streams whose `which`-th codebook is built with changed arguments."""
+    real, count = vb.Book, [0]
+
+    def make(rng, entries, dims, vq=None, style=None, **kw):
+        count[0] += 1
+        if count[0] == which:
+            if "vq" in change and vq is not None:
+                vq = (change["vq"], vq[1])
+            style = change.get("style", style)
+        return real(rng, entries, dims, vq=vq, style=style, **kw)
+    monkeypatch.setattr(vb, "Book", make)
+
+
+def test_unknown_lookup_type_is_refused(monkeypatch):
+    # codebook.rs:290-352: lookup types 0, 1 and 2 exist
+    s = vb.Stream(np.random.default_rng(8200))
+    first_vq = next(k for k, b in enumerate(s.books) if b.vq is not None) + 1
+    _patched_book(monkeypatch, first_vq, vq=3)
+    bad = vb.Stream(np.random.default_rng(8200))
+    with pytest.raises(po.ReaderError):
+        vo.VorbisFrontend(bad.ident, bad.setup)
+    with pytest.raises(SymgpuError) as e:
+        frontend.VorbisFrontend(bad.ident, bad.setup)
+    assert e.value.status == 1
+
+
+def test_over_and_under_specified_codebooks_are_refused():
+    # codebook.rs:112-210: a plain-coded book's lengths sit in 5-bit fields; all ones = length 2 for every entry
+    for seed in range(200):
+        s = vb.Stream(np.random.default_rng(8300 + seed))
+        w = vb.BitWriterRtl()
+        b0 = s.books[0]
+        # is book 0 plain-coded (ordered flag 0, sparse flag 0)?
+        head = int.from_bytes(s.setup[7:], "little") >> 8
+        if (head >> 64) & 3 != 0 or b0.entries < 6:
+            continue
+        for new_len in (2, 5):                     # 6+ entries of length 2: over-specified; of length 5 (< 32 entries): under-specified
+            if new_len == 5 and b0.entries >= 32:
+                continue
+            body = int.from_bytes(s.setup[7:], "little")
+            at = 8 + 66
+            for k in range(b0.entries):
+                body &= ~(31 << (at + 5 * k))
+                body |= (new_len - 1) << (at + 5 * k)
+            setup = s.setup[:7] + body.to_bytes(len(s.setup) - 7, "little")
+            with pytest.raises(po.ReaderError):
+                vo.VorbisFrontend(s.ident, setup)
+            with pytest.raises(SymgpuError) as e:
+                frontend.VorbisFrontend(s.ident, setup)
+            assert e.value.status == 1
+        del w
+        return
+    raise AssertionError("no plain-coded first book among the seeds")

@@ -64,7 +64,43 @@ TARGETS = {
         ("CHECK(pairs[pair_no]->channel == channel);", ""),
         ("2.51984209978974632953f * scale", "2.5198421f * scale * 1.0000001f"),
     ]),
-    "vorbis": dict(src="vorbis_frontend.cpp", prefix="symgpu_vorbis_fe_", tests=["tests/test_vorbis_frontend.py", "tests/test_zz_ogg_vorbis_to_pcm.py"], mutants=[]),
+    "vorbis": dict(src="vorbis_frontend.cpp", prefix="symgpu_vorbis_fe_", tests=["tests/test_vorbis_frontend.py", "tests/test_zz_ogg_vorbis_to_pcm.py"], mutants=[
+        ("size_t k = (64 - left) >> 3;", "size_t k = (63 - left) >> 3;"),
+        ("            needed -= left;\n            if (!fetch()) return false;", "            if (!fetch()) return false;\n            needed -= left > needed ? needed : left;"),
+        ("if (left < 1 && !fetch()) return false;", "if (left < 2 && !fetch()) return false;"),
+        ("if (bs.left < max_len) bs.top_up();", "if (bs.left <= max_len) bs.top_up();"),
+        ("if (bs.left < max_len) bs.top_up();", "bs.top_up();"),
+        ("if (depth + 1 > bs.left) return false;", "if (depth > bs.left) return false;"),
+        ("if (free_nodes[k].depth > len) continue;", "if (free_nodes[k].depth >= len) continue;"),
+        ("if (v < best_value) best_value = v, best = int(k);", "if (v <= best_value) best_value = v, best = int(k);"),
+        ("return free_nodes.empty();", "return true;"),
+        ("if (best < 0) return false;  // over-specified", "if (best < 0) continue;"),
+        ("if (!bs.ok() || dims == 0 || dims > 32 || entries > 128 * 1024) return 1;", "if (!bs.ok() || dims == 0 || entries > 128 * 1024) return 1;"),
+        ("if (lens.size() == 1 && lens[0] == 1)", "if (lens.size() == 1 && lens[0] == 2)"),
+        ("if (!bs.ok() || lookup > 2) return 1;", "if (!bs.ok() || lookup > 3) return 1;"),
+        ("if (sequence) last = v;", "if (!sequence) last = v;"),
+        ("static const uint32_t ranges[4] = {256, 128, 86, 64};", "static const uint32_t ranges[4] = {256, 128, 85, 64};"),
+        ("static const uint32_t ranges[4] = {256, 128, 86, 64};", "static const uint32_t ranges[4] = {256, 129, 86, 64};"),
+        ("if (cbits && !fe.books[cl.mainbook].read(bs, cval)) return false;", "if (!fe.books[cl.mainbook].read(bs, cval)) return false;"),
+        ("            cval >>= cbits;\n", ""),
+        ("if (per_word > n_out) {", "if (per_word >= n_out) {"),
+        ("for (size_t k = 0, o = i; k < dim && o < n; ++k, o += step) out[o] += v[k];", "for (size_t k = 0, o = i; k < dim && o < n; ++k, o += step) out[o] = v[k];"),
+        ("for (size_t o = 0; o + dim <= n; o += dim) {", "for (size_t o = 0; o + dim < n; o += dim) {"),
+        ("const size_t begin = std::min<size_t>(r.begin, full), end = std::min<size_t>(r.end, full);", "const size_t begin = r.begin, end = std::min<size_t>(r.end, full);"),
+        ("const size_t begin = std::min<size_t>(r.begin, full), end = std::min<size_t>(r.end, full);", "const size_t begin = std::min<size_t>(r.begin, full), end = std::min<size_t>(r.end, n2);"),
+        ("for (unsigned pass = 0; pass <= r.max_pass && !ended; ++pass)", "for (unsigned pass = 0; pass < r.max_pass && !ended; ++pass)"),
+        ("                        if (r.type != 2 && do_not_decode[chans[c]]) continue;\n                        uint32_t code;", "                        uint32_t code;"),
+        ("const size_t base = first + size_t(c) * parts;", "const size_t base = first;"),
+        ("fe.part_classes.size() - base);", "parts - first);"),
+        ("if (!(r.used[cls] & (1u << pass))) continue;", "if (!(r.used[cls] & (1u << pass)) && pass) continue;"),
+        ("out[i] = fe.type2[i * size_t(n_chans) + size_t(c)];", "out[i] = fe.type2[i + size_t(c) * n2];"),
+        ("if (fe) fe->prev_block_flag = -1;", ""),
+        ("if (!bs.read_bool(flag) || flag) return SYMGPU_ERR_DECODE;  // lib.rs:151-154", "if (!bs.read_bool(flag)) return SYMGPU_ERR_DECODE;"),
+        ("|| mode_number >= n_modes) return SYMGPU_ERR_DECODE;", ") return SYMGPU_ERR_DECODE;"),
+        ("if (!bs.read_bool(flag) || !bs.read_bool(flag)) return SYMGPU_ERR_DECODE;", "if (!bs.read_bool(flag)) return SYMGPU_ERR_DECODE;"),
+        ("if (unit->do_not_decode[cp.first] != unit->do_not_decode[cp.second]) unit->do_not_decode[cp.first] = unit->do_not_decode[cp.second] = 0;", ""),
+        ("if (!used) std::memset(floor_y + ch * 65, 0, sizeof(uint16_t) * 65);", ""),
+    ]),
 }
 
 DRIVER = r'''
