@@ -688,6 +688,11 @@ symgpu_status symgpu_vorbis_fe_config(const symgpu_vorbis_fe* fe, symgpu_vorbis_
  * (not an audio packet, bad mode number); a packet that merely ends early is decoded as far as it goes, as in the reference. */
 symgpu_status symgpu_vorbis_fe_decode(symgpu_vorbis_fe* fe, const uint8_t* packet, size_t n, uint32_t slot, uint32_t floor_base,
                                       symgpu_vorbis_unit* unit, uint16_t* floor_y, float* residue);
+/* A stream's audio packets in one call (packet i = data[packets[i].offset .. + len)): units[k], floor_y[130k..], residue[2*slot*k..],
+ * packet_of[k] = i for every packet the front-end accepts, in order; refused packets are left out. */
+symgpu_status symgpu_vorbis_fe_decode_packets(symgpu_vorbis_fe* fe, const uint8_t* data, size_t n, const symgpu_piece* packets, size_t n_packets,
+                                              uint32_t slot, uint32_t floor_base, symgpu_vorbis_unit* units, uint16_t* floor_y, float* residue,
+                                              uint32_t* packet_of, size_t* n_good);
 
 /* ===================================================================================================
  * AAC-LC entropy front-end: one raw_data_block per packet (an ADTS frame's payload, or an MP4 sample) ->
@@ -709,6 +714,12 @@ void symgpu_aac_fe_reset(symgpu_aac_fe* fe);   /* AudioDecoder::reset: window hi
  * state is then left as the reference leaves it (changed up to the point of failure). */
 symgpu_status symgpu_aac_fe_decode(symgpu_aac_fe* fe, const uint8_t* packet, size_t n, uint32_t tns_base, symgpu_aac_unit* units,
                                    symgpu_aac_tns* tns, uint32_t* n_tns, float* coeffs);
+/* A stream's packets in one call: packet i = data[packets[i].offset .. + len).  For every packet the front-end accepts, in order:
+ * units[2k..], coeffs[2048k..], frame_of[k] = i, its TNS records appended to `tns` (tns_base + position); refused packets are left
+ * out, as a caller of the reference drops them.  SYMGPU_ERR_LIMIT if tns_cap is too small (16 per packet always suffice). */
+symgpu_status symgpu_aac_fe_decode_packets(symgpu_aac_fe* fe, const uint8_t* data, size_t n, const symgpu_piece* packets, size_t n_packets,
+                                           uint32_t tns_base, symgpu_aac_unit* units, symgpu_aac_tns* tns, size_t tns_cap, float* coeffs,
+                                           uint32_t* frame_of, size_t* n_good, size_t* n_tns);
 /* The dequantisation tables the front-end uses (for tests): x^(4/3) [8192], 2^((i-156)/4) [256], 0.5^((i-155)/4) [256]. */
 void symgpu_aac_fe_tables(float* pow43, float* normal_scf, float* intensity_scf);
 

@@ -731,6 +731,27 @@ symgpu_status symgpu_aac_fe_decode(symgpu_aac_fe* fe, const uint8_t* packet, siz
     return SYMGPU_OK;
 }
 
+symgpu_status symgpu_aac_fe_decode_packets(symgpu_aac_fe* fe, const uint8_t* data, size_t n, const symgpu_piece* packets, size_t n_packets,
+                                           uint32_t tns_base, symgpu_aac_unit* units, symgpu_aac_tns* tns, size_t tns_cap, float* coeffs,
+                                           uint32_t* frame_of, size_t* n_good, size_t* n_tns) {
+    if (!fe || (!data && n) || (n_packets && (!packets || !units || !coeffs || !frame_of)) || !n_good || !n_tns || (tns_cap && !tns)) return SYMGPU_ERR_ARG;
+    size_t good = 0, total = 0;
+    symgpu_aac_tns scratch[16];
+    for (size_t i = 0; i < n_packets; ++i) {
+        if (packets[i].offset > n || packets[i].len > n - packets[i].offset) continue;  // not inside the data: no packet
+        uint32_t nt = 0;
+        const symgpu_status st = symgpu_aac_fe_decode(fe, data + packets[i].offset, packets[i].len, uint32_t(tns_base + total), units + 2 * good, scratch,
+                                                      &nt, coeffs + 2048 * good);
+        if (st != SYMGPU_OK) continue;  // the caller of the reference drops the packet and goes on
+        if (total + nt > tns_cap) return SYMGPU_ERR_LIMIT;
+        std::memcpy(tns + total, scratch, nt * sizeof(symgpu_aac_tns));
+        total += nt;
+        frame_of[good++] = uint32_t(i);
+    }
+    *n_good = good, *n_tns = total;
+    return SYMGPU_OK;
+}
+
 void symgpu_aac_fe_tables(float* pow43, float* normal_scf, float* intensity_scf) {
     const Tables& T = tables();
     if (pow43) std::memcpy(pow43, T.pow43, sizeof T.pow43);

@@ -472,3 +472,20 @@ extern "C" symgpu_status symgpu_vorbis_fe_decode(symgpu_vorbis_fe* fe, const uin
     fe->prev_block_flag = long_block;
     return SYMGPU_OK;
 }
+
+extern "C" symgpu_status symgpu_vorbis_fe_decode_packets(symgpu_vorbis_fe* fe, const uint8_t* data, size_t n, const symgpu_piece* packets, size_t n_packets,
+                                                         uint32_t slot, uint32_t floor_base, symgpu_vorbis_unit* units, uint16_t* floor_y, float* residue,
+                                                         uint32_t* packet_of, size_t* n_good) {
+    if (!fe || (!data && n) || (n_packets && (!packets || !units || !floor_y || !residue || !packet_of)) || !n_good) return SYMGPU_ERR_ARG;
+    if (slot < ((1u << fe->ident.bs1_exp) >> 1)) return SYMGPU_ERR_ARG;
+    size_t good = 0;
+    for (size_t i = 0; i < n_packets; ++i) {
+        if (packets[i].offset > n || packets[i].len > n - packets[i].offset) continue;
+        const symgpu_status st = symgpu_vorbis_fe_decode(fe, data + packets[i].offset, packets[i].len, slot, floor_base, units + good, floor_y + 130 * good,
+                                                         residue + 2 * size_t(slot) * good);
+        if (st != SYMGPU_OK) continue;  // the caller of the reference drops the packet and goes on
+        packet_of[good++] = uint32_t(i);
+    }
+    *n_good = good;
+    return SYMGPU_OK;
+}

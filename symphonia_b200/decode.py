@@ -76,13 +76,11 @@ def ogg_vorbis_plan(data, serial=None):
                                              dur, discard).astype(np.int64)
     fe = frontend.VorbisFrontend(ident_b, setup_b)
     slot = fe.slot
-    units, fy, res, keep = [], [], [], []
-    for k, (_, b) in enumerate(audio):
-        try:
-            u, y, r = fe.decode(b)
-        except frontend.SymgpuError:
-            continue
-        units.append(u), fy.append(y), res.append(r), keep.append(k)
+    blob = b"".join(b for _, b in audio)
+    table = np.zeros(len(audio), dtype=nat.PIECE_DTYPE)
+    table["len"] = [len(b) for _, b in audio]
+    table["offset"] = np.concatenate([[0], np.cumsum(table["len"][:-1], dtype=np.uint64)]) if len(audio) else 0
+    units, fy, res, keep = fe.decode_packets(blob, table)
     n = len(units)
     stream, floors = np.array([fe.stream], dtype=nat.VORBIS_STREAM_DTYPE), fe.floors.copy()
     fe.close()
@@ -100,9 +98,7 @@ def ogg_vorbis_plan(data, serial=None):
         total += frames - ts - te
     runs = np.zeros(1, dtype=nat.VORBIS_RUN_DTYPE)
     runs["n_packets"] = n
-    return dict(stream=stream, floors=floors, units=np.array(units, dtype=nat.VORBIS_UNIT_DTYPE).reshape(n),
-                floor_y=np.array(fy, dtype=np.uint16).reshape(n, 2, 65), residue=np.array(res, dtype=np.float32).reshape(n, 2, slot),
-                runs=runs, slot=slot, spans=spans, channels=int(ident["channels"]), sample_rate=int(ident["sample_rate"]), total_frames=total)
+    return dict(stream=stream, floors=floors, units=units, floor_y=fy, residue=res, runs=runs, slot=slot, spans=spans, channels=int(ident["channels"]), sample_rate=int(ident["sample_rate"]), total_frames=total)
 
 
 def decode_ogg_vorbis(engine, data, fmt=nat.FMT_S16, serial=None):
@@ -129,16 +125,10 @@ def adts_aac_plan(data):
     rate, channels = int(packets[0]["sample_rate"]), int(packets[0]["channels"])
     if channels not in (1, 2):
         raise ValueError("channel configuration outside AAC-LC mono / stereo")
-    buf = np.frombuffer(bytes(data), dtype=np.uint8)
     fe = frontend.AacFrontend(rate, channels)
-    units, tns, coeffs, n_tns = [], [], [], 0
-    for pk in packets:
-        try:
-            u, t, c = fe.decode(buf[int(pk["offset"]):int(pk["offset"]) + int(pk["size"])].tobytes(), tns_base=n_tns)
-        except frontend.SymgpuError:
-            continue
-        units.append(u), tns.append(t), coeffs.append(c)
-        n_tns += len(t)
+    table = np.zeros(len(packets), dtype=nat.PIECE_DTYPE)
+    table["offset"], table["len"] = packets["offset"], packets["size"]
+    units, tns, coeffs, _ = fe.decode_packets(data, table)
     fe.close()
     n = len(units)
     runs = np.zeros(1, dtype=nat.AAC_RUN_DTYPE)
@@ -147,8 +137,7 @@ def adts_aac_plan(data):
     spans["src"] = np.arange(n, dtype=np.uint64) * 2048
     spans["plane_stride"], spans["frames"] = 1024, 1024
     spans["dst_frame"] = np.arange(n, dtype=np.uint64) * 1024
-    return dict(units=np.array(units, dtype=nat.AAC_UNIT_DTYPE).reshape(n, 2), tns=np.concatenate(tns) if n else np.zeros(0, dtype=nat.AAC_TNS_DTYPE),
-                coeffs=np.array(coeffs, dtype=np.float32).reshape(n, 2, 1024), runs=runs, spans=spans, channels=channels, sample_rate=rate,
+    return dict(units=units, tns=tns, coeffs=coeffs, runs=runs, spans=spans, channels=channels, sample_rate=rate,
                 total_frames=1024 * n)
 
 
@@ -161,3 +150,135 @@ def decode_adts_aac(engine, data, fmt=nat.FMT_S16, stream=0):
     engine.aac_stream_reset(stream)
     pcm = engine.aac_synth_host(plan["units"], plan["tns"], plan["coeffs"], plan["runs"])
     return engine.pcm_pack_host(pcm, plan["spans"], plan["channels"], fmt, plan["total_frames"]), plan["sample_rate"]
+
+
+# ---- many files at once: one synthesis launch per codec --------------------------------------------------------------------
+
+def sniff(data):
+    """'vorbis' (Ogg capture pattern), 'aac' (ADTS: 12 sync bits, layer field 00) or 'mpa' (anything else: the MPEG audio indexer looks
+    for a frame, skipping tags and junk)."""
+    head = bytes(data[:4])
+    if head == b"OggS":
+        return "vorbis"
+    if len(head) >= 2 and head[0] == 0xFF and (head[1] & 0xF6) == 0xF0:
+        return "aac"
+    return "mpa"
+
+
+def plan_file(data):
+    """CPU half of one file: dict(kind, ...) -- kind 'mp3' / 'mpa1' / 'mpa2' / 'aac' / 'vorbis'."""
+    kind = sniff(data)
+    if kind == "vorbis":
+        return dict(ogg_vorbis_plan(data), kind="vorbis")
+    if kind == "aac":
+        return dict(adts_aac_plan(data), kind="aac")
+    layer, payload, runs, spans, rate, channels, total = mpeg_audio_plan(data)
+    return dict(kind={1: "mpa1", 2: "mpa2", 3: "mp3"}[layer], payload=payload, runs=runs, spans=spans, sample_rate=rate, channels=channels, total_frames=total)
+
+
+def plan_files(files, threads=None):
+    """Plans every file (front-ends on `threads` host threads: the native calls release the interpreter lock) and merges the plans
+    into one batch per codec, every file a stream of its own.  Returns (plans, batches): batches[kind] = dict(members = indices into
+    `files`, first = each member's first unit in the batch, + the arrays of that codec's synthesis entry point)."""
+    import concurrent.futures
+    import os
+    with concurrent.futures.ThreadPoolExecutor(max_workers=threads or os.cpu_count()) as pool:
+        plans = list(pool.map(plan_file, files))
+    batches = {}
+    for kind in ("mp3", "mpa1", "mpa2", "aac", "vorbis"):
+        members = [i for i, p in enumerate(plans) if p["kind"] == kind and len(p["spans"])]
+        if not members:
+            continue
+        first, at = [], 0
+        for i in members:
+            first.append(at)
+            at += len(plans[i]["spans"])
+        b = dict(members=members, first=first)
+        if kind == "mp3":
+            b["units"] = np.concatenate([plans[i]["payload"][0] for i in members])
+            b["quant"] = np.concatenate([plans[i]["payload"][1] for i in members])
+            runs = np.concatenate([plans[i]["runs"] for i in members])
+        elif kind in ("mpa1", "mpa2"):
+            b["subbands"] = np.concatenate([plans[i]["payload"] for i in members])
+            runs = np.concatenate([plans[i]["runs"] for i in members])
+        elif kind == "aac":
+            units = [plans[i]["units"].copy() for i in members]
+            base = 0
+            for u, i in zip(units, members):
+                u["tns_first"] = np.where(u["n_tns"] > 0, u["tns_first"] + base, 0)
+                base += len(plans[i]["tns"])
+            b["units"], b["tns"] = np.concatenate(units), np.concatenate([plans[i]["tns"] for i in members])
+            b["coeffs"] = np.concatenate([plans[i]["coeffs"] for i in members])
+            runs = np.concatenate([plans[i]["runs"] for i in members])
+        else:
+            slot = max(plans[i]["slot"] for i in members)
+            units, res, base = [], [], 0
+            for i in members:
+                u = plans[i]["units"].copy()
+                u["floor"] = np.where(u["floor"] == 0xFFFF, 0xFFFF, u["floor"] + base).astype(np.uint16)
+                base += len(plans[i]["floors"])
+                units.append(u)
+                r = np.zeros((len(u), 2, slot), dtype=np.float32)
+                r[:, :, :plans[i]["slot"]] = plans[i]["residue"]
+                res.append(r)
+            b["streams"] = np.concatenate([plans[i]["stream"] for i in members])
+            b["floors"] = np.concatenate([plans[i]["floors"] for i in members])
+            b["units"], b["floor_y"], b["residue"], b["slot"] = np.concatenate(units), np.concatenate([plans[i]["floor_y"] for i in members]), np.concatenate(res), slot
+            runs = np.concatenate([plans[i]["runs"] for i in members])
+        runs = runs.copy()
+        runs["stream"] = np.arange(len(members))
+        runs["first_packet" if kind == "vorbis" else "first_frame"] = first
+        b["runs"] = runs
+        batches[kind] = b
+    return plans, batches
+
+
+def _file_spans(plan, batch, k, unit_floats, plane_stride=None):
+    """The file's spans, re-based onto its slice of the batch's PCM (unit_floats per unit)."""
+    sp = plan["spans"].copy()
+    sp["src"] = np.arange(len(sp), dtype=np.uint64) * unit_floats
+    if plane_stride is not None:
+        sp["plane_stride"] = plane_stride
+    return sp
+
+
+def pack_files(plans, batches, pcm, pack, fmt):
+    """Output stage per file: pcm[kind] = the batch's planar output, pack(pcm_slice, spans, channels, fmt, total_frames) the packer."""
+    out = [None] * len(plans)
+    for i, p in enumerate(plans):
+        if not len(p["spans"]):
+            out[i] = (np.zeros((0, p["channels"]), dtype=nat.FMT_NUMPY[fmt]), p["sample_rate"])
+    for kind, b in batches.items():
+        flat = np.ascontiguousarray(pcm[kind]).reshape(-1)
+        per = flat.size // len(pcm[kind])          # floats per unit: two planes
+        for k, i in enumerate(b["members"]):
+            p = plans[i]
+            n = len(p["spans"])
+            sl = flat[b["first"][k] * per:(b["first"][k] + n) * per]
+            sp = _file_spans(p, b, k, per, per // 2)
+            out[i] = (pack(sl, sp, p["channels"], fmt, p["total_frames"]), p["sample_rate"])
+    return out
+
+
+def decode_files(engine, files, fmt=nat.FMT_S16, threads=None):
+    """[(samples [frames, channels], sample_rate)] for a list of MPEG audio / ADTS AAC-LC / Ogg Vorbis files: front-ends on host threads,
+    ONE synthesis launch per codec over all files (every file a stream), output stage per file.  (Re)allocates the engine's stream
+    slots."""
+    plans, batches = plan_files(files, threads)
+    pcm = {}
+    for kind, b in batches.items():
+        n_streams = len(b["members"])
+        if kind == "mp3":
+            engine.mp3_streams_alloc(n_streams)
+            pcm[kind] = engine.mp3_synth_host_quantized(b["units"], b["quant"], b["runs"])
+        elif kind in ("mpa1", "mpa2"):
+            engine.mp3_streams_alloc(n_streams)
+            pcm[kind] = engine.mpa12_synth_host(b["subbands"], b["runs"])
+        elif kind == "aac":
+            engine.aac_streams_alloc(n_streams)
+            pcm[kind] = engine.aac_synth_host(b["units"], b["tns"], b["coeffs"], b["runs"])
+        else:
+            engine.vorbis_streams_set(b["streams"])
+            engine.vorbis_floors_set(b["floors"])
+            pcm[kind] = engine.vorbis_synth_host(b["units"], b["floor_y"], b["residue"], b["runs"], b["slot"])
+    return pack_files(plans, batches, pcm, engine.pcm_pack_host, fmt)

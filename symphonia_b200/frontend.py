@@ -229,6 +229,26 @@ class VorbisFrontend:
             raise SymgpuError(rc, "symgpu_vorbis_fe_decode")
         return unit[0], floor_y, residue
 
+    def decode_packets(self, data, packets, slot=None, floor_base=0):
+        """All audio packets of the stream in one call (PIECE_DTYPE table over `data`): (units [g], floor_y [g,2,65], residue [g,2,slot],
+        packet_of [g]); refused packets are left out."""
+        slot = self.slot if slot is None else slot
+        a = _u8(data)
+        packets = np.ascontiguousarray(packets, dtype=nat.PIECE_DTYPE)
+        n = len(packets)
+        units = np.zeros(n, dtype=nat.VORBIS_UNIT_DTYPE)
+        floor_y = np.zeros((n, 2, 65), dtype=np.uint16)
+        residue = np.zeros((n, 2, slot), dtype=np.float32)
+        packet_of = np.zeros(n, dtype=np.uint32)
+        good = ctypes.c_size_t(0)
+        rc = self._L.symgpu_vorbis_fe_decode_packets(self._h, _vp(a.ctypes.data) if a.size else None, a.size, _vp(packets.ctypes.data), n, slot, floor_base,
+                                                     _vp(units.ctypes.data), _vp(floor_y.ctypes.data), _vp(residue.ctypes.data), _vp(packet_of.ctypes.data),
+                                                     ctypes.byref(good))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_vorbis_fe_decode_packets")
+        g = good.value
+        return units[:g], floor_y[:g], residue[:g], packet_of[:g]
+
 
 class AacFrontend:
     """One AAC-LC stream's entropy front-end (window history, element layout, noise generator): raw_data_block packets ->
@@ -265,6 +285,25 @@ class AacFrontend:
         if rc != 0:
             raise SymgpuError(rc, "symgpu_aac_fe_decode")
         return units, tns[:n.value], coeffs
+
+    def decode_packets(self, data, packets, tns_base=0):
+        """All packets of the stream in one call (PIECE_DTYPE table over `data`): (units [g,2], tns [t], coeffs [g,2,1024], frame_of [g]);
+        refused packets are left out."""
+        a = _u8(data)
+        packets = np.ascontiguousarray(packets, dtype=nat.PIECE_DTYPE)
+        n = len(packets)
+        units = np.zeros((n, 2), dtype=nat.AAC_UNIT_DTYPE)
+        tns = np.zeros(16 * n, dtype=nat.AAC_TNS_DTYPE)
+        coeffs = np.zeros((n, 2, 1024), dtype=np.float32)
+        frame_of = np.zeros(n, dtype=np.uint32)
+        good, n_tns = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        rc = self._L.symgpu_aac_fe_decode_packets(self._h, _vp(a.ctypes.data) if a.size else None, a.size, _vp(packets.ctypes.data), n, int(tns_base),
+                                                  _vp(units.ctypes.data), _vp(tns.ctypes.data), len(tns), _vp(coeffs.ctypes.data), _vp(frame_of.ctypes.data),
+                                                  ctypes.byref(good), ctypes.byref(n_tns))
+        if rc != 0:
+            raise SymgpuError(rc, "symgpu_aac_fe_decode_packets")
+        g = good.value
+        return units[:g], tns[:n_tns.value], coeffs[:g], frame_of[:g]
 
 
 def aac_tables():

@@ -1,0 +1,102 @@
+"""Many files at once (`symphonia_b200.decode.plan_files` / `decode_files`): MPEG audio (Layers I-III), ADTS AAC-LC and Ogg Vorbis files
+planned on host threads and merged into ONE synthesis batch per codec, every file a stream of its own.  CPU test: the merged
+batches rendered by the synthesis and output oracles equal every file rendered alone (index re-basing of TNS records, floor tables,
+runs, spans; residues re-padded to a common slot).  GPU test (opt-in until it has run on a B200 once: SYMGPU_TEST_MANY_FILES=1):
+`decode_files` equals the same rendering byte for byte."""
+import os
+
+import numpy as np
+import pytest
+
+from symphonia_b200 import _native as nat
+from symphonia_b200 import decode
+from tests import _oracle
+from tests import test_zz_adts_aac_to_pcm as ta
+from tests import test_zz_file_to_pcm as tm
+from tests import test_zz_ogg_vorbis_to_pcm as tv
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return _oracle.load()
+
+
+def _files():
+    files = list(tm._corpus()) + [blob for _, blob in tm._mpa12_corpus()]
+    files += [ta._file(500, 44100, 2)[0], ta._file(502, 22050, 1)[0], ta._file(503, 8000, 2, n=5)[0]]
+    files += [tv._file(300)[0], tv._file(305, channels=1)[0], tv._file(302, n_packets=9)[0]]
+    # a second Vorbis block-size pair: slots differ inside one batch
+    rng = np.random.default_rng(12)
+    s = tv.vb.Stream(rng, bs_exp=(7, 10), per_word=1)
+    pk = [s.packet()[0] for _ in range(8)]
+    pages = tv.st.ogg_paginate(5, [s.ident], rng, eos=False) + tv.st.ogg_paginate(5, [b"\x03vorbis" + bytes(9), s.setup], rng, first_sequence=1, bos=False, eos=False)
+    pages += tv.st.ogg_paginate(5, pk, rng, first_sequence=len(pages), bos=False, granule_of=[10 ** 9] * len(pk))
+    files.append(b"".join(pages))
+    order = np.random.default_rng(3).permutation(len(files))
+    return [files[i] for i in order]
+
+
+def _render_batches(oracle, batches):
+    pcm = {}
+    for kind, b in batches.items():
+        n = len(b["members"])
+        if kind == "mp3":
+            rc, out, _ = _oracle.mp3_batch(oracle, b["units"], tm._spectra(b["quant"]), b["runs"], n)
+        elif kind in ("mpa1", "mpa2"):
+            rc, out, _ = _oracle.mpa12_batch(oracle, b["subbands"], b["runs"], n)
+        elif kind == "aac":
+            rc, out = _oracle.aac_batch(oracle, b["units"], b["tns"], b["coeffs"], b["runs"], n)
+        else:
+            rc, out = _oracle.vorbis_batch(oracle, dict(streams=b["streams"], floors=b["floors"], units=b["units"], floor_y=b["floor_y"],
+                                                        residue=b["residue"], runs=b["runs"], slot=b["slot"]))
+        assert rc == 0, kind
+        pcm[kind] = out
+    return pcm
+
+
+def _alone(oracle, data, fmt):
+    kind = decode.sniff(data)
+    if kind == "vorbis":
+        return tv._render(oracle, decode.ogg_vorbis_plan(data), fmt)
+    if kind == "aac":
+        return ta._render(oracle, decode.adts_aac_plan(data), fmt)
+    return tm._decode_expect(oracle, data, fmt)[0]
+
+
+def test_merged_batches_equal_files_alone(oracle):
+    files = _files()
+    assert {decode.sniff(f) for f in files} == {"mpa", "aac", "vorbis"}
+    plans, batches = decode.plan_files(files, threads=4)
+    assert set(batches) == {"mp3", "mpa1", "mpa2", "aac", "vorbis"}
+    assert sorted(i for b in batches.values() for i in b["members"]) == list(range(len(files)))
+    pcm = _render_batches(oracle, batches)
+    for fmt in (nat.FMT_S16, nat.FMT_F32):
+        got = decode.pack_files(plans, batches, pcm, lambda p, sp, ch, f, total: _oracle.pcm_pack(oracle, p, sp, ch, f, total), fmt)
+        for i, data in enumerate(files):
+            want = _alone(oracle, data, fmt)
+            assert got[i][0].shape == want.shape, (i, plans[i]["kind"])
+            assert (got[i][0].view(np.uint8) == want.view(np.uint8)).all(), (i, plans[i]["kind"])
+            assert got[i][1] == plans[i]["sample_rate"]
+
+
+def test_thread_count_does_not_change_the_plan():
+    files = _files()
+    _, a = decode.plan_files(files, threads=1)
+    _, b = decode.plan_files(files, threads=8)
+    for kind in a:
+        for key, v in a[kind].items():
+            w = b[kind][key]
+            assert (np.asarray(v).tobytes() == np.asarray(w).tobytes()) if isinstance(v, np.ndarray) else v == w, (kind, key)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("SYMGPU_TEST_MANY_FILES") != "1", reason="written after the round's GPU budget was spent; opt-in until verified on a B200")
+def test_many_files_on_the_device(oracle):
+    import symphonia_b200 as sb
+    files = _files()
+    with sb.Engine(0) as eng:
+        for fmt in (nat.FMT_S16, nat.FMT_F32):
+            got = decode.decode_files(eng, files, fmt, threads=4)
+            for i, data in enumerate(files):
+                want = _alone(oracle, data, fmt)
+                assert got[i][0].shape == want.shape and (got[i][0].view(np.uint8) == want.view(np.uint8)).all(), i

@@ -17,3 +17,5 @@ timeout 600 python tools/mp3_file_e2e_bench.py > gpurun_out/mp3_file_e2e.json 2>
 SYMGPU_TEST_VORBIS_CHAIN=1 timeout 600 python -m pytest tests/test_zz_ogg_vorbis_to_pcm.py -m gpu -q > gpurun_out/vorbis_chain.log 2>&1; tail -3 gpurun_out/vorbis_chain.log
 # 6. ADTS file bytes -> PCM (AAC-LC front-end on the CPU, verified synthesis + output stage on the GPU)
 SYMGPU_TEST_AAC_CHAIN=1 timeout 600 python -m pytest tests/test_zz_adts_aac_to_pcm.py -m gpu -q > gpurun_out/aac_chain.log 2>&1; tail -3 gpurun_out/aac_chain.log
+# 7. many files of all three codecs at once: one synthesis launch per codec
+SYMGPU_TEST_MANY_FILES=1 timeout 600 python -m pytest tests/test_zz_many_files.py -m gpu -q > gpurun_out/many_files.log 2>&1; tail -3 gpurun_out/many_files.log
