@@ -89,11 +89,19 @@ struct Codebook {
     std::vector<float> vq;           // [entries][dims]
     std::vector<int32_t> child;      // binary trie: child[2 * node + bit] = node index, or ~value for a leaf, or 0 = no such code
     uint32_t max_len = 0;
+    uint32_t lut[1024] = {};         // next ten stream bits (first bit = bit 0) -> (value + 1) << 6 | length, 0 = a longer code
     // One codeword, first stream bit = root of the tree (codebook.rs:366-369 "BitOrder::Reverse"; bit.rs:1211-1250): the cache is
     // topped up, the code is matched against it padded with zeros, and must then fit in what the cache really holds -- else the
     // packet has ended and nothing is consumed.
     bool read(PacketBits& bs, uint32_t& value) const {
         if (bs.left < max_len) bs.top_up();
+        const uint32_t e = lut[bs.bits & 1023];  // codes of up to ten bits: one look-up (the cache holds zeros above `left`)
+        if (e) {
+            const uint32_t len = e & 63;
+            if (len > bs.left) return false;
+            bs.consume(len);
+            return value = (e >> 6) - 1, true;
+        }
         int32_t node = 0;
         for (uint32_t depth = 0; depth < 64; ++depth) {
             const uint32_t bit = uint32_t(bs.bits >> depth) & 1;
@@ -228,6 +236,11 @@ int read_codebook(BitReaderRtl& bs, Codebook& cb) {
                     node = slot;
                 }
             }
+        }
+        if (lens[k] <= 10) {
+            uint32_t first = 0;  // the codeword in stream order: bit i of the index = the i-th bit read
+            for (int i = 0; i < lens[k]; ++i) first |= ((words[w] >> (lens[k] - 1 - i)) & 1u) << i;
+            for (uint32_t rest = 0; rest < (1u << (10 - lens[k])); ++rest) cb.lut[first | (rest << lens[k])] = (uint32_t(values[k]) + 1) << 6 | lens[k];
         }
         ++w;
     }
