@@ -282,3 +282,41 @@ def decode_files(engine, files, fmt=nat.FMT_S16, threads=None):
             engine.vorbis_floors_set(b["floors"])
             pcm[kind] = engine.vorbis_synth_host(b["units"], b["floor_y"], b["residue"], b["runs"], b["slot"])
     return pack_files(plans, batches, pcm, engine.pcm_pack_host, fmt)
+
+
+# ---- FLAC (integer path: restoration on the GPU, samples stay int32 as in the reference's AudioBuffer<i32>) ----------------------
+
+def flac_plan(data):
+    """CPU half for a native FLAC file: marker + STREAMINFO + checksum-validated frame split (symgpu_flac_index), frame / sub-frame / Rice
+    reader (symgpu_flac_fe_decode_packets) -> dict(frames, subframes, samples (int32: warm-up samples + residuals), info, channels,
+    sample_rate, bits_per_sample, total_frames): the input of Engine.flac_restore_host."""
+    info, packets = packetizer.flac_index(data)
+    table = np.zeros(len(packets), dtype=nat.PIECE_DTYPE)
+    table["offset"], table["len"] = packets["offset"], packets["size"]
+    frames, infos, frame_of, subs, samples = frontend.flac_decode_packets(data, table, int(info["bits_per_sample"]), int(info["channels"]), int(info["block_max"]))
+    total = int(sum(int(subs[int(f["first_subframe"])]["n"]) for f in frames))
+    return dict(frames=frames, subframes=subs, samples=samples, info=info, channels=int(info["channels"]), sample_rate=int(info["sample_rate"]),
+                bits_per_sample=int(info["bits_per_sample"]), total_frames=total)
+
+
+def flac_interleave(plan, restored):
+    """[total_frames, channels] int32 from the restored planes (each sub-frame's n samples at its offset), frames in stream order."""
+    out = np.zeros((plan["total_frames"], plan["channels"]), dtype=np.int32)
+    at = 0
+    for f in plan["frames"]:
+        first = int(f["first_subframe"])
+        n = int(plan["subframes"][first]["n"])
+        for c in range(int(f["channels"])):
+            sf = plan["subframes"][first + c]
+            out[at:at + n, c] = restored[int(sf["offset"]):int(sf["offset"]) + n]
+        at += n
+    return out
+
+
+def decode_flac(engine, data):
+    """(samples [frames, channels] int32 scaled to 32 bits as the reference's FLAC decoder leaves them, sample_rate)."""
+    plan = flac_plan(data)
+    if len(plan["frames"]) == 0:
+        return np.zeros((0, plan["channels"]), dtype=np.int32), plan["sample_rate"]
+    restored = engine.flac_restore_host(plan["frames"], plan["subframes"], plan["samples"].copy())
+    return flac_interleave(plan, restored), plan["sample_rate"]

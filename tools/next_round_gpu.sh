@@ -7,7 +7,7 @@ python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 |
 # 1. the file -> PCM chain through the verified entry points (front-ends on the CPU), incl. independent per-channel block types
 timeout 600 python -m pytest tests/test_zz_file_to_pcm.py -m gpu -q > gpurun_out/chain.log 2>&1; tail -3 gpurun_out/chain.log
 # 2. FLAC restoration kernel after the FIXED-order-1 fix, and the .flac file chain
-SYMGPU_TEST_FLAC=1 timeout 600 python -m pytest tests/test_flac_parity_gpu.py -q > gpurun_out/flac.log 2>&1; tail -3 gpurun_out/flac.log
+SYMGPU_TEST_FLAC=1 timeout 600 python -m pytest tests/test_flac_parity_gpu.py tests/test_flac_frontend.py -m gpu -q > gpurun_out/flac.log 2>&1; tail -3 gpurun_out/flac.log
 # 3. the device entropy front-end (never run before): under the sanitizer first, then plain
 SYMGPU_TEST_ENTROPY=1 timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_mp3_entropy_gpu.py -x -q > gpurun_out/entropy_memcheck.log 2>&1; tail -5 gpurun_out/entropy_memcheck.log
 SYMGPU_TEST_ENTROPY=1 timeout 600 python -m pytest tests/test_mp3_entropy_gpu.py -q > gpurun_out/entropy.log 2>&1; tail -3 gpurun_out/entropy.log
