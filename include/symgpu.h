@@ -707,6 +707,22 @@ symgpu_status symgpu_vorbis_fe_decode_packets(symgpu_vorbis_fe* fe, const uint8_
  * ================================================================================================= */
 typedef struct symgpu_aac_fe symgpu_aac_fe;
 symgpu_status symgpu_aac_fe_create(uint32_t sample_rate, uint32_t channels, symgpu_aac_fe** out);
+/* MPEG-4 AudioSpecificConfig as the reference reads it (symphonia-common/src/mpeg/audio/mod.rs:230-439): the extra data of AAC in MP4 /
+ * Matroska.  24 bytes. */
+typedef struct symgpu_aac_asc {
+    uint32_t sample_rate;
+    uint32_t ext_sample_rate;  /* of an explicit SBR / PS extension (has_ext)                                              */
+    uint16_t samples;          /* 1024 or 960 for the general-audio object types, else 0                                   */
+    uint8_t object_type;       /* MPEG-4 audio object type index after an SBR / PS prefix: 2 = AAC-LC                      */
+    uint8_t channels;          /* channel count of the configuration index (7 -> 8); 0 = defined in-band                   */
+    uint8_t sbr_present, ps_present, has_ext, ext_channels;
+    uint8_t reserved[8];
+} symgpu_aac_asc;
+/* SYMGPU_ERR_DECODE (invalid index, zero rate, data ends) / SYMGPU_ERR_UNSUPPORTED (object types and options the reference refuses). */
+symgpu_status symgpu_aac_asc_parse(const uint8_t* buf, size_t n, symgpu_aac_asc* out);
+/* AacDecoder::try_new with extra data (aac/mod.rs:59-108): parses it, then requires AAC-LC, no SBR, at most two channels, 1024-sample
+ * frames ("aac too complex" otherwise).  *asc (optional) receives what was parsed. */
+symgpu_status symgpu_aac_fe_create_asc(const uint8_t* extra, size_t n, symgpu_aac_fe** out, symgpu_aac_asc* asc);
 void symgpu_aac_fe_destroy(symgpu_aac_fe* fe);
 void symgpu_aac_fe_reset(symgpu_aac_fe* fe);   /* AudioDecoder::reset: window history forgotten (pair with symgpu_aac_stream_reset) */
 /* units [2], tns: room for 16 records (*n_tns written; units[].tns_first = tns_base + position), coeffs [2][1024] (channel 1

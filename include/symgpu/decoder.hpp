@@ -286,34 +286,35 @@ class GpuMpaDecoder final : public AudioDecoder {
 
 // AAC-LC decoder whose filterbank runs on the GPU (mirrors AacDecoder, symphonia-codec-aac/src/aac/mod.rs:42-304).  A packet is
 // one raw_data_block, what the reference's AdtsReader and IsoMp4Reader emit.  Without extra data the stream parameters are the
-// codec parameters' (the ADTS case, mod.rs:64-78); with extra data the first two bytes of an AudioSpecificConfig are read:
-// object type (2 = LC), sampling-frequency index (an escape or an extension object type is Unsupported here), channel
-// configuration 1 or 2.
+// codec parameters' (the ADTS case, mod.rs:64-78); with extra data they come from the AudioSpecificConfig, read and judged as the
+// reference does (symgpu_aac_fe_create_asc: AAC-LC, no SBR, at most two channels, 1024-sample frames).
 class GpuAacDecoder final : public AudioDecoder {
   public:
     static Result<std::unique_ptr<AudioDecoder>> try_new(std::shared_ptr<GpuContext> gpu, const AudioCodecParameters& p,
                                                          const AudioDecoderOptions&) {
         if (p.codec != CODEC_ID_AAC) return {nullptr, {ErrorKind::Unsupported, "aac: invalid codec"}};
         AudioCodecParameters params = p;
-        if (!p.extra_data.empty()) {
-            if (p.extra_data.size() < 2) return {nullptr, {ErrorKind::DecodeError, "aac: invalid data"}};
-            static const uint32_t kRates[13] = {96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000, 7350};
-            const uint32_t word = (uint32_t(p.extra_data[0]) << 8) | p.extra_data[1];
-            const uint32_t object_type = word >> 11, rate_idx = (word >> 7) & 15, channel_cfg = (word >> 3) & 15;
-            if (object_type != 2 || rate_idx > 12 || channel_cfg < 1 || channel_cfg > 2)
-                return {nullptr, {ErrorKind::Unsupported, "aac: aac too complex"}};
-            params.sample_rate = kRates[rate_idx], params.channels = channel_cfg;
+        symgpu_aac_fe* fe = nullptr;
+        if (!p.extra_data.empty()) {  // AudioSpecificConfig (mod.rs:59-62, :101-108)
+            symgpu_aac_asc asc;
+            const symgpu_status st = symgpu_aac_fe_create_asc(p.extra_data.data(), p.extra_data.size(), &fe, &asc);
+            if (st != SYMGPU_OK) return {nullptr, map_status(st)};
+            params.sample_rate = asc.sample_rate, params.channels = asc.channels;
         }
         if (params.sample_rate == 0) return {nullptr, {ErrorKind::Unsupported, "aac: sample rate is required"}};
         if (params.channels == 0) return {nullptr, {ErrorKind::Unsupported, "aac: channels or channel layout is required"}};
         if (params.channels > 2) return {nullptr, {ErrorKind::Unsupported, "aac: aac too complex"}};
         const int slot = gpu->acquire_stream();
-        if (slot < 0) return {nullptr, {ErrorKind::LimitError, "symgpu: no free stream slot"}};
-        symgpu_aac_fe* fe = nullptr;
-        const symgpu_status st = symgpu_aac_fe_create(params.sample_rate, params.channels, &fe);
-        if (st != SYMGPU_OK) {
-            gpu->release_stream(slot);
-            return {nullptr, map_status(st)};
+        if (slot < 0) {
+            symgpu_aac_fe_destroy(fe);
+            return {nullptr, {ErrorKind::LimitError, "symgpu: no free stream slot"}};
+        }
+        if (!fe) {
+            const symgpu_status st = symgpu_aac_fe_create(params.sample_rate, params.channels, &fe);
+            if (st != SYMGPU_OK) {
+                gpu->release_stream(slot);
+                return {nullptr, map_status(st)};
+            }
         }
         symgpu_aac_stream_reset(gpu->raw(), (uint32_t)slot);
         return {std::unique_ptr<AudioDecoder>(new GpuAacDecoder(std::move(gpu), std::move(params), (uint32_t)slot, fe)), {}};

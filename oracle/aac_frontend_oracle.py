@@ -11,8 +11,10 @@ intensity), pulse restoration and the resolution of TNS filters to line ranges -
   symphonia-core/src/io/bit.rs:771-808                 read_codebook on a stream that ends
 
 numpy float32 scalars carry the arithmetic, one IEEE operation per reference operation; powf / sinf are the C library's, which
-is what the reference's f32::powf / f32::sin call on this platform (tests/test_aac_frontend.py also shows every table entry to be
-the correctly rounded value, so the tables do not depend on which libm routine a compiler picks).  Pinned by the reference's
+is what the reference's f32::powf / f32::sin call on this platform (tests/test_aac_frontend.py shows the scale-factor tables to be the
+correctly rounded powers of two whichever routine computes them, and x^(4/3) to be within one unit in the last place of the correctly
+rounded value -- 10 of 8192 entries differ under glibc, so that table is a property of the platform's libm in the reference itself).
+AudioSpecificConfig::read (symphonia-common/src/mpeg/audio/mod.rs:230-439) is restated at the end.  Pinned by the reference's
 own unit test (decode_section_data_rejects_excess_zero_length_sections, ics/mod.rs:612-635) and by an independent stream
 writer's ground truth."""
 import ctypes
@@ -555,3 +557,91 @@ class AacFrontend:
                 out.append(dict(window_sequence=ics.window_sequence, window_shape=int(ics.window_shape), prev_window_shape=int(ics.prev_window_shape),
                                 tns=ics.tns_filters(self.rate_idx), coeffs=ics.coeffs.copy()))
         return cur_ch, out
+
+
+# ---- AudioSpecificConfig::read, symphonia-common/src/mpeg/audio/mod.rs:230-439 (object types by MPEG-4 index, :87-130) -----------
+ASC_RATES = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000, 7350]
+ASC_GA = {1, 2, 3, 6, 7, 17, 19, 20, 21, 22, 23}
+ASC_UNSUPPORTED = {8, 9, 12, 13, 14, 15, 16, 24, 25, 26, 27, 28, 30, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41}
+ASC_ER = {17, 19, 20, 21, 22, 23, 24, 25, 26, 27, 39}
+
+
+def read_asc(buf):
+    """dict(object_type, sample_rate, channels (0 = in-band), samples, sbr_present, ps_present, has_ext, ext_sample_rate, ext_channels)."""
+    bs = BitsLtr(buf)
+
+    def aot():
+        v = bs.read(5)
+        return v if v < 31 else bs.read(6) + 32
+
+    def rate():
+        i = bs.read(4)
+        if i <= 12:
+            return ASC_RATES[i]
+        if i == 15:
+            return bs.read(24)
+        raise AacError(DECODE, "sample rate index")
+
+    def chans():
+        i = bs.read(4)
+        if i > 7:
+            raise AacError(DECODE, "channel configuration")
+        return [0, 1, 2, 3, 4, 5, 6, 8][i]
+
+    a = dict(object_type=aot(), sample_rate=rate(), samples=0, sbr_present=0, ps_present=0, has_ext=0, ext_sample_rate=0, ext_channels=0)
+    if a["sample_rate"] == 0:
+        raise AacError(DECODE, "sample rate 0")
+    a["channels"] = chans()
+    if a["object_type"] in (5, 29):
+        a["sbr_present"], a["ps_present"], a["has_ext"] = 1, int(a["object_type"] == 29), 1
+        a["ext_sample_rate"] = rate()
+        a["object_type"] = aot()
+        if a["object_type"] == 22:
+            a["ext_channels"] = chans()
+    t = a["object_type"]
+    if t in ASC_GA:
+        a["samples"] = 960 if bs.read_bool() else 1024
+        if bs.read_bool():
+            bs.read(14)
+        ext = bs.read_bool()
+        if a["channels"] == 0:
+            raise AacError(UNSUPPORTED, "program config element")
+        if t in (6, 20):
+            bs.read(3)
+        if ext:
+            if t == 22:
+                bs.read(5), bs.read(11)
+            if t in (17, 19, 20, 23):
+                bs.read_bool(), bs.read_bool(), bs.read_bool()
+            if bs.read_bool():
+                raise AacError(UNSUPPORTED, "version3 extensions")
+    elif t in ASC_UNSUPPORTED:
+        raise AacError(UNSUPPORTED, "object type")
+    if t in ASC_ER:
+        if bs.read(2) >= 2:
+            raise AacError(UNSUPPORTED, "error protection")
+    if a["has_ext"] and bs.bits_left() >= 16:
+        if bs.read(11) == 0x2B7:
+            e = aot()
+            if e == 5:
+                a["sbr_present"] = int(bs.read_bool())
+                if a["sbr_present"]:
+                    rate()
+                    if bs.bits_left() >= 12 and bs.read(11) == 0x548:
+                        a["ps_present"] = int(bs.read_bool())
+            if e == 29:
+                a["sbr_present"] = int(bs.read_bool())
+                if a["sbr_present"]:
+                    rate()
+                bs.read(4)
+    a["object_type"] = min(a["object_type"], 255)
+    return a
+
+
+def decoder_accepts(asc):
+    """AacDecoder::try_new's judgement of a parsed configuration (aac/mod.rs:86-108): None, or the error kind."""
+    if asc["channels"] == 0:
+        return UNSUPPORTED
+    if asc["object_type"] != 2 or asc["sbr_present"] or asc["channels"] > 2 or asc["samples"] != 1024:
+        return UNSUPPORTED
+    return None

@@ -64,6 +64,9 @@ assert VORBIS_UNIT_DTYPE.itemsize == 16 and VORBIS_RUN_DTYPE.itemsize == 16
 PCM_SPAN_DTYPE = np.dtype([("src", "<u8"), ("plane_stride", "<u4"), ("frames", "<u4"), ("trim_start", "<u4"),
                            ("trim_end", "<u4"), ("dst_frame", "<u8")])
 assert PCM_SPAN_DTYPE.itemsize == 32
+AAC_ASC_DTYPE = np.dtype([("sample_rate", "<u4"), ("ext_sample_rate", "<u4"), ("samples", "<u2"), ("object_type", "u1"), ("channels", "u1"),
+                          ("sbr_present", "u1"), ("ps_present", "u1"), ("has_ext", "u1"), ("ext_channels", "u1"), ("reserved", "u1", (8,))])
+assert AAC_ASC_DTYPE.itemsize == 24
 FMT_F32, FMT_S16, FMT_S24, FMT_S32, FMT_U8 = 0, 1, 2, 3, 4
 FMT_NUMPY = {FMT_F32: np.float32, FMT_S16: np.int16, FMT_S24: np.int32, FMT_S32: np.int32, FMT_U8: np.uint8}
 # packetisers (include/symgpu.h "Packetisers")
@@ -246,6 +249,10 @@ def lib():
     L.symgpu_ogg_page_end_trims.argtypes = [vp, vp, vp, vp, sz, vp]
     L.symgpu_aac_fe_create.restype = ctypes.c_int
     L.symgpu_aac_fe_create.argtypes = [u32, u32, ctypes.POINTER(vp)]
+    L.symgpu_aac_asc_parse.restype = ctypes.c_int
+    L.symgpu_aac_asc_parse.argtypes = [vp, sz, vp]
+    L.symgpu_aac_fe_create_asc.restype = ctypes.c_int
+    L.symgpu_aac_fe_create_asc.argtypes = [vp, sz, ctypes.POINTER(vp), vp]
     L.symgpu_aac_fe_destroy.restype = None
     L.symgpu_aac_fe_destroy.argtypes = [vp]
     L.symgpu_aac_fe_reset.restype = None

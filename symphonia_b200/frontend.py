@@ -254,14 +254,24 @@ class AacFrontend:
     """One AAC-LC stream's entropy front-end (window history, element layout, noise generator): raw_data_block packets ->
     (units [2], tns [n], coeffs [2][1024]), the input of Engine.aac_synth_host."""
 
-    def __init__(self, sample_rate, channels):
+    def __init__(self, sample_rate=0, channels=0, extra_data=None):
+        """Stream parameters (the ADTS case), or `extra_data` = an AudioSpecificConfig (MP4 / Matroska)."""
         self._h = None
         self._L = nat.lib()
         h = _vp()
-        rc = self._L.symgpu_aac_fe_create(int(sample_rate), int(channels), ctypes.byref(h))
-        if rc != 0:
-            raise SymgpuError(rc, "symgpu_aac_fe_create")
-        self._h, self.channels = h, int(channels)
+        if extra_data is not None:
+            a = _u8(bytes(extra_data))
+            asc = np.zeros(1, dtype=nat.AAC_ASC_DTYPE)
+            rc = self._L.symgpu_aac_fe_create_asc(_vp(a.ctypes.data) if a.size else None, a.size, ctypes.byref(h), _vp(asc.ctypes.data))
+            if rc != 0:
+                raise SymgpuError(rc, "symgpu_aac_fe_create_asc")
+            self.asc = asc[0]
+            sample_rate, channels = int(asc[0]["sample_rate"]), int(asc[0]["channels"])
+        else:
+            rc = self._L.symgpu_aac_fe_create(int(sample_rate), int(channels), ctypes.byref(h))
+            if rc != 0:
+                raise SymgpuError(rc, "symgpu_aac_fe_create")
+        self._h, self.channels, self.sample_rate = h, int(channels), int(sample_rate)
 
     def close(self):
         if self._h:
@@ -311,3 +321,13 @@ def aac_tables():
     p43, a, b = np.zeros(8192, dtype=np.float32), np.zeros(256, dtype=np.float32), np.zeros(256, dtype=np.float32)
     nat.lib().symgpu_aac_fe_tables(_vp(p43.ctypes.data), _vp(a.ctypes.data), _vp(b.ctypes.data))
     return p43, a, b
+
+
+def aac_asc_parse(extra_data):
+    """The AudioSpecificConfig as the reference reads it (AAC_ASC_DTYPE record); SymgpuError(1 / 2) where it refuses."""
+    a = _u8(bytes(extra_data))
+    out = np.zeros(1, dtype=nat.AAC_ASC_DTYPE)
+    rc = nat.lib().symgpu_aac_asc_parse(_vp(a.ctypes.data) if a.size else None, a.size, _vp(out.ctypes.data))
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_aac_asc_parse")
+    return out[0]

@@ -111,6 +111,12 @@ static void run_all(const std::vector<uint8_t>& d) {
         size_t g, ns, nm;
         symgpu_flac_fe_decode_packets(p, n, &one, 1, 16, 0, 0, &fr, &fi, &fo, sf, 8, smp.data(), smp.size(), &g, &ns, &nm);
     }
+    {   // the raw bytes as an AudioSpecificConfig
+        symgpu_aac_asc asc;
+        symgpu_aac_asc_parse(p, n < 64 ? n : 64, &asc);
+        symgpu_aac_fe* fe = nullptr;
+        if (symgpu_aac_fe_create_asc(p, n < 64 ? n : 64, &fe, &asc) == SYMGPU_OK) symgpu_aac_fe_destroy(fe);
+    }
     // ---- AAC entropy front-end: "AFE1", rate index byte, channel byte, then length-prefixed (u16 LE) raw_data_blocks;
     //      and every ADTS frame of the input as a packet
     if (n > 8 && std::memcmp(p, "AFE1", 4) == 0) {

@@ -431,3 +431,96 @@ def test_ms_mask_three_is_refused():
         return w.bytes()
     assert _both_status(cpe(2), channels=2)[0] == 0
     assert _both_status(cpe(3), channels=2)[0] == 1
+
+
+# ---- AudioSpecificConfig ---------------------------------------------------------------------------------------------------------
+
+def _asc_bits(aot, rate_idx, ch_cfg, rate=None, tail=()):
+    w = ab.BitWriterMsb()
+    if aot < 31:
+        w.put(aot, 5)
+    else:
+        w.put(31, 5), w.put(aot - 32, 6)
+    w.put(rate_idx, 4)
+    if rate_idx == 15:
+        w.put(rate, 24)
+    w.put(ch_cfg, 4)
+    for v, width in tail:
+        w.put(v, width)
+    return w
+
+
+def _asc_both(blob):
+    try:
+        want = ao.read_asc(blob)
+        status = 0
+    except ao.AacError as e:
+        want, status = None, (1 if e.kind == ao.DECODE else 2)
+    try:
+        got = frontend.aac_asc_parse(blob)
+        got_status = 0
+    except SymgpuError as e:
+        got, got_status = None, e.status
+    assert got_status == status, blob.hex()
+    if status == 0:
+        for k, v in want.items():
+            assert int(got[k]) == v, (blob.hex(), k)
+        verdict = ao.decoder_accepts(want)
+        try:
+            fe = frontend.AacFrontend(extra_data=blob)
+            assert verdict is None and (fe.sample_rate, fe.channels) == (want["sample_rate"], want["channels"])
+            fe.close()
+        except SymgpuError as e:
+            assert verdict == ao.UNSUPPORTED and e.status == 2, blob.hex()
+    return status, want
+
+
+def test_audio_specific_config_known_answers():
+    # the two configurations every AAC-LC encoder writes: 0x1210 = LC, 44.1 kHz, stereo; 0x1190 = LC, 48 kHz, stereo
+    st_, a = _asc_both(bytes.fromhex("1210"))
+    assert st_ == 0 and (a["object_type"], a["sample_rate"], a["channels"], a["samples"], a["sbr_present"]) == (2, 44100, 2, 1024, 0)
+    st_, a = _asc_both(bytes.fromhex("1190"))
+    assert st_ == 0 and (a["object_type"], a["sample_rate"], a["channels"]) == (2, 48000, 2)
+    st_, a = _asc_both(bytes.fromhex("1208"))   # LC, 44.1 kHz, mono
+    assert st_ == 0 and a["channels"] == 1
+    # HE-AAC, explicit hierarchical signalling: SBR (5), core 24 kHz, stereo, extension rate 48 kHz, then LC + GASpecificConfig
+    w = _asc_bits(5, 6, 2, tail=((3, 4), (2, 5), (0, 1), (0, 1), (0, 1)))
+    st_, a = _asc_both(w.bytes())
+    assert st_ == 0 and (a["object_type"], a["sbr_present"], a["ext_sample_rate"], a["sample_rate"]) == (2, 1, 48000, 24000)
+    with pytest.raises(SymgpuError) as e:       # ... which the LC decoder refuses as too complex
+        frontend.AacFrontend(extra_data=w.bytes())
+    assert e.value.status == 2
+    # LC followed by the backward-compatible SBR signalling (sync 0x2b7) is only looked at after an explicit prefix: plain LC stays LC
+    w = _asc_bits(2, 4, 2, tail=((0, 3), (0x2B7, 11), (5, 5), (1, 1), (3, 4)))
+    st_, a = _asc_both(w.bytes())
+    assert st_ == 0 and a["sbr_present"] == 0
+    # escapes: explicit 24-bit rate; 960-sample frames refused by the decoder; channel configuration 0 needs a program config element
+    st_, a = _asc_both(_asc_bits(2, 15, 2, rate=44100, tail=((0, 3),)).bytes())
+    assert st_ == 0 and a["sample_rate"] == 44100
+    assert _asc_both(_asc_bits(2, 15, 2, rate=0, tail=((0, 3),)).bytes())[0] == 1
+    st_, a = _asc_both(_asc_bits(2, 4, 2, tail=((1, 1), (0, 2))).bytes())
+    assert st_ == 0 and a["samples"] == 960
+    assert _asc_both(_asc_bits(2, 4, 0, tail=((0, 3),)).bytes())[0] == 2
+    assert _asc_both(_asc_bits(2, 13, 2, tail=((0, 3),)).bytes())[0] == 1          # reserved rate index
+    assert _asc_both(_asc_bits(2, 4, 9, tail=((0, 3),)).bytes())[0] == 1           # reserved channel configuration
+    assert _asc_both(b"\x12")[0] == 1                                               # ends inside the configuration
+    with pytest.raises(SymgpuError) as e:                                           # aac/mod.rs:60: at least two bytes
+        frontend.AacFrontend(extra_data=b"\x12")
+    assert e.value.status == 1
+
+
+def test_audio_specific_config_every_object_type_and_random_tails():
+    rng = np.random.default_rng(77)
+    seen = set()
+    for aot in list(range(0, 31)) + list(range(32, 48)) + [95]:
+        for trial in range(12):
+            ch = int(rng.integers(0, 8)) if trial else 2
+            tail = [(int(rng.integers(2)), 1) for _ in range(int(rng.integers(0, 40)))]
+            blob = _asc_bits(aot, int(rng.choice([3, 4, 6, 11, 15])), ch, rate=int(rng.integers(1, 1 << 24)), tail=tail).bytes()
+            st_, a = _asc_both(blob)
+            seen.add((aot, st_))
+    assert {s for _, s in seen} == {0, 1, 2}
+    assert (2, 0) in seen and (8, 2) in seen and (39, 2) in seen and (4, 0) in seen
+    # random bytes
+    for _ in range(400):
+        _asc_both(rng.integers(0, 256, int(rng.integers(0, 9)), dtype=np.uint8).tobytes())
