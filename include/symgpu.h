@@ -495,6 +495,10 @@ typedef struct symgpu_vorbis_setup_info {   /* 160 bytes */
 } symgpu_vorbis_setup_info;
 symgpu_status symgpu_vorbis_setup_parse(const uint8_t* packet, size_t n, const symgpu_vorbis_ident* ident, symgpu_vorbis_setup_info* info,
                                         symgpu_vorbis_floor1* floors);
+/* Copies the packets' pieces back to back into `out` (cap bytes; the packets' `len` sum suffices) and writes table[i] = where packet i
+ * now lies: a contiguous copy of a logical stream for the per-stream front-end calls.  SYMGPU_ERR_LIMIT if cap is too small. */
+symgpu_status symgpu_ogg_gather(const uint8_t* data, size_t n, const symgpu_ogg_packet* packets, size_t n_packets, const symgpu_piece* pieces,
+                                size_t n_pieces, uint8_t* out, size_t cap, symgpu_piece* table, size_t* used);
 /* End trims of the stream packets of ONE logical stream against the granule positions of the pages they end on
  * (symphonia-format-ogg/src/logical.rs:164-302): page_sequence / page_absgp as in symgpu_ogg_packet, dur / discard from the
  * codec mapping (symgpu_vorbis_packet_durations), all in stream order. */

@@ -245,6 +245,8 @@ def lib():
     L.symgpu_vorbis_fe_config.argtypes = [vp, vp, vp, ctypes.POINTER(u32)]
     L.symgpu_vorbis_fe_decode.restype = ctypes.c_int
     L.symgpu_vorbis_fe_decode.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp]
+    L.symgpu_ogg_gather.restype = ctypes.c_int
+    L.symgpu_ogg_gather.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, ctypes.POINTER(sz)]
     L.symgpu_ogg_page_end_trims.restype = ctypes.c_int
     L.symgpu_ogg_page_end_trims.argtypes = [vp, vp, vp, vp, sz, vp]
     L.symgpu_aac_fe_create.restype = ctypes.c_int

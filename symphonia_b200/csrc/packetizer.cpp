@@ -1,5 +1,6 @@
 // C entry points of the packetisers (include/symgpu.h "Packetisers"): thin adapters from the index builders of
 // include/symgpu/packetizer.hpp to flat, caller-owned tables.  Host only; no context, no device.
+#include <cstring>
 #include <vector>
 
 #include "../../include/symgpu.h"
@@ -139,6 +140,27 @@ extern "C" symgpu_status symgpu_vorbis_setup_parse(const uint8_t* packet, size_t
     return SYMGPU_OK;
 }
 static_assert(sizeof(symgpu_vorbis_setup_info) == 160, "record sizes are ABI");
+
+extern "C" symgpu_status symgpu_ogg_gather(const uint8_t* data, size_t n, const symgpu_ogg_packet* packets, size_t n_packets, const symgpu_piece* pieces,
+                                           size_t n_pieces, uint8_t* out, size_t cap, symgpu_piece* table, size_t* used) {
+    if ((!data && n) || (n_packets && (!packets || !pieces || !table)) || !used || (cap && !out)) return SYMGPU_ERR_ARG;
+    size_t at = 0;
+    for (size_t i = 0; i < n_packets; ++i) {
+        const symgpu_ogg_packet& pk = packets[i];
+        if (size_t(pk.first_piece) + pk.n_pieces > n_pieces) return SYMGPU_ERR_ARG;
+        const size_t start = at;
+        for (uint32_t k = 0; k < pk.n_pieces; ++k) {
+            const symgpu_piece& pc = pieces[pk.first_piece + k];
+            if (pc.offset > n || pc.len > n - pc.offset) return SYMGPU_ERR_ARG;
+            if (pc.len > cap - at) return SYMGPU_ERR_LIMIT;
+            std::memcpy(out + at, data + pc.offset, pc.len);
+            at += pc.len;
+        }
+        table[i] = symgpu_piece{start, uint32_t(at - start), 0};
+    }
+    *used = at;
+    return SYMGPU_OK;
+}
 
 extern "C" symgpu_status symgpu_ogg_page_end_trims(const uint32_t* page_sequence, const uint64_t* page_absgp, const uint32_t* dur,
                                                    const uint32_t* discard, size_t n, uint32_t* trim_end) {

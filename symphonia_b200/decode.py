@@ -59,43 +59,44 @@ def ogg_vorbis_plan(data, serial=None):
         raise ValueError("no Ogg packets")
     serial = int(packets["serial"][0]) if serial is None else serial
     mine = packets[packets["serial"] == serial]
-    blobs = [packetizer.gather(data, pk, pieces) for pk in mine]
-    ident_b = blobs[0]
+    blob, table = packetizer.ogg_gather(data, mine, pieces)       # the logical stream, packets back to back
+    off, ln = table["offset"].astype(np.int64), table["len"].astype(np.int64)
+    padded = np.concatenate([blob, np.zeros(8, dtype=np.uint8)])
+    b0, b1 = padded[off], padded[off + 1]                           # (bytes beyond a short packet are masked by `ln` below)
+    ident_b = blob[off[0]:off[0] + ln[0]].tobytes()
     ident = packetizer.vorbis_ident(ident_b)
-    at = 1
-    while at < len(blobs) and not (len(blobs[at]) >= 7 and blobs[at][0] == 5 and blobs[at][1:7] == b"vorbis"):
-        at += 1
-    if at == len(blobs):
+    is_setup = (ln >= 7) & (b0 == 5)
+    for k, c in enumerate(b"vorbis"):
+        is_setup &= padded[off + 1 + k] == c
+    is_setup[0] = False
+    if not is_setup.any():
         raise ValueError("no Vorbis setup header")
-    setup_b = blobs[at]
+    at = int(np.argmax(is_setup))
+    setup_b = blob[off[at]:off[at] + ln[at]].tobytes()
     n_modes, mask = packetizer.vorbis_setup_modes(setup_b, ident)
-    audio = [(pk, b) for pk, b in zip(mine[at + 1:], blobs[at + 1:]) if len(b) and (b[0] & 1) == 0]
-    dur, discard, _ = packetizer.vorbis_packet_durations(ident, n_modes, mask, [b for _, b in audio])
+    audio = np.nonzero((np.arange(len(mine)) > at) & (ln > 0) & ((b0 & 1) == 0))[0]
+    heads = b0[audio].astype(np.uint16) | (np.where(ln[audio] > 1, b1[audio], 0).astype(np.uint16) << 8)
+    dur, discard, _ = packetizer.vorbis_packet_durations(ident, n_modes, mask, None, heads=heads, lens=np.minimum(ln[audio], 2))
     dur, discard = dur.astype(np.int64), discard.astype(np.int64)
-    trim_end = packetizer.ogg_page_end_trims([int(pk["page_sequence"]) for pk, _ in audio], [int(pk["page_absgp"]) for pk, _ in audio],
-                                             dur, discard).astype(np.int64)
+    trim_end = packetizer.ogg_page_end_trims(mine["page_sequence"][audio], mine["page_absgp"][audio], dur, discard).astype(np.int64)
     fe = frontend.VorbisFrontend(ident_b, setup_b)
     slot = fe.slot
-    blob = b"".join(b for _, b in audio)
-    table = np.zeros(len(audio), dtype=nat.PIECE_DTYPE)
-    table["len"] = [len(b) for _, b in audio]
-    table["offset"] = np.concatenate([[0], np.cumsum(table["len"][:-1], dtype=np.uint64)]) if len(audio) else 0
-    units, fy, res, keep = fe.decode_packets(blob, table)
+    units, fy, res, keep = fe.decode_packets(blob, table[audio])
     n = len(units)
     stream, floors = np.array([fe.stream], dtype=nat.VORBIS_STREAM_DTYPE), fe.floors.copy()
     fe.close()
-    bs = {0: 1 << int(ident["bs0_exp"]), 1: 1 << int(ident["bs1_exp"])}
+    bs0, bs1 = 1 << int(ident["bs0_exp"]), 1 << int(ident["bs1_exp"])
+    frames = (np.where(units["prev_block_flag"] != 0, bs1, bs0) + np.where(units["block_flag"] != 0, bs1, bs0)).astype(np.int64) // 4
+    ts = np.minimum(discard[keep], frames)
+    te = np.minimum(trim_end[keep], frames - ts)
+    if n:
+        ts[0], te[0] = frames[0], 0   # the first packet after a reset is silenced in gapless mode (codec-vorbis lib.rs:318-322)
+    left = frames - ts - te
     spans = np.zeros(n, dtype=nat.PCM_SPAN_DTYPE)
-    total = 0
-    for o, k in enumerate(keep):
-        frames = (bs[int(units[o]["prev_block_flag"])] + bs[int(units[o]["block_flag"])]) // 4
-        if o == 0:
-            ts, te = frames, 0  # the first packet after a reset is silenced in gapless mode (codec-vorbis lib.rs:318-322)
-        else:
-            ts = min(int(discard[k]), frames)
-            te = min(int(trim_end[k]), frames - ts)
-        spans[o] = (o * 2 * slot, slot, frames, ts, te, total)
-        total += frames - ts - te
+    spans["src"] = np.arange(n, dtype=np.uint64) * (2 * slot)
+    spans["plane_stride"], spans["frames"], spans["trim_start"], spans["trim_end"] = slot, frames, ts, te
+    spans["dst_frame"] = np.concatenate([[0], np.cumsum(left)[:-1]]).astype(np.uint64) if n else 0
+    total = int(left.sum())
     runs = np.zeros(1, dtype=nat.VORBIS_RUN_DTYPE)
     runs["n_packets"] = n
     return dict(stream=stream, floors=floors, units=units, floor_y=fy, residue=res, runs=runs, slot=slot, spans=spans, channels=int(ident["channels"]), sample_rate=int(ident["sample_rate"]), total_frames=total)

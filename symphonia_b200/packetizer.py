@@ -87,10 +87,15 @@ def vorbis_setup_modes(packet, ident):
     return n.value, mask.value
 
 
-def vorbis_packet_durations(ident, n_modes, mask, packets, prev_exp=0):
-    """(dur, discard, prev_exp) for a run of audio packets given as bytes objects."""
-    heads = np.array([int.from_bytes(bytes(pk[:2]).ljust(2, b"\0"), "little") for pk in packets], dtype=np.uint16)
-    lens = np.array([min(len(pk), 2) for pk in packets], dtype=np.uint8)
+def vorbis_packet_durations(ident, n_modes, mask, packets, prev_exp=0, heads=None, lens=None):
+    """(dur, discard, prev_exp) for a run of audio packets given as bytes objects -- or as `heads` (first two bytes, little-endian) and
+    `lens` (min(length, 2)) arrays."""
+    if heads is None:
+        heads = np.array([int.from_bytes(bytes(pk[:2]).ljust(2, b"\0"), "little") for pk in packets], dtype=np.uint16)
+        lens = np.array([min(len(pk), 2) for pk in packets], dtype=np.uint8)
+    else:
+        heads, lens = np.ascontiguousarray(heads, dtype=np.uint16), np.ascontiguousarray(lens, dtype=np.uint8)
+        packets = heads
     dur, discard = np.zeros(len(packets), dtype=np.uint32), np.zeros(len(packets), dtype=np.uint32)
     idb = np.array([ident], dtype=nat.VORBIS_IDENT_DTYPE)
     prev = np.array([prev_exp], dtype=np.uint8)
@@ -133,3 +138,16 @@ def ogg_page_end_trims(page_sequence, page_absgp, dur, discard):
     _check(nat.lib().symgpu_ogg_page_end_trims(_vp(seq.ctypes.data), _vp(gp.ctypes.data), _vp(d.ctypes.data), _vp(c.ctypes.data), len(seq),
                                                _vp(out.ctypes.data)), "symgpu_ogg_page_end_trims")
     return out
+
+
+def ogg_gather(data, packets, pieces):
+    """(blob, table): the packets copied back to back, table[i] (PIECE_DTYPE) = where packet i lies in `blob`."""
+    a, p = _buf(data)
+    packets = np.ascontiguousarray(packets, dtype=nat.OGG_PACKET_DTYPE)
+    pieces = np.ascontiguousarray(pieces, dtype=nat.PIECE_DTYPE)
+    blob = np.zeros(int(packets["len"].sum()), dtype=np.uint8)
+    table = np.zeros(len(packets), dtype=nat.PIECE_DTYPE)
+    used = ctypes.c_size_t(0)
+    _check(nat.lib().symgpu_ogg_gather(p, a.size, _vp(packets.ctypes.data), len(packets), _vp(pieces.ctypes.data), len(pieces),
+                                       _vp(blob.ctypes.data) if blob.size else None, blob.size, _vp(table.ctypes.data), ctypes.byref(used)), "symgpu_ogg_gather")
+    return blob, table

@@ -53,6 +53,18 @@ static void run_all(const std::vector<uint8_t>& d) {
         size_t count = 0;
         symgpu_status stop;
         symgpu_adts_index(p, n, nullptr, 0, &count, &stop);
+        {   // C entry points: index, then the gathered copy of everything
+            size_t np_ = 0, nq = 0;
+            symgpu_ogg_index(p, n, nullptr, 0, &np_, nullptr, 0, &nq);
+            std::vector<symgpu_ogg_packet> pk(np_);
+            std::vector<symgpu_piece> pc(nq), tab(np_);
+            if (np_ && symgpu_ogg_index(p, n, pk.data(), np_, &np_, pc.data(), nq, &nq) == SYMGPU_OK) {
+                size_t total = 0, used = 0;
+                for (const auto& q : pk) total += q.len;
+                std::vector<uint8_t> out(total + 1);
+                symgpu_ogg_gather(p, n, pk.data(), np_, pc.data(), nq, out.data(), total, tab.data(), &used);
+            }
+        }
         OggIndex ix;
         OggIndex::build(p, n, ix, false);
         for (auto& kv : ix.streams) {
