@@ -19,3 +19,4 @@ SYMGPU_TEST_VORBIS_CHAIN=1 timeout 600 python -m pytest tests/test_zz_ogg_vorbis
 SYMGPU_TEST_AAC_CHAIN=1 timeout 600 python -m pytest tests/test_zz_adts_aac_to_pcm.py -m gpu -q > gpurun_out/aac_chain.log 2>&1; tail -3 gpurun_out/aac_chain.log
 # 7. many files of all three codecs at once: one synthesis launch per codec
 SYMGPU_TEST_MANY_FILES=1 timeout 600 python -m pytest tests/test_zz_many_files.py -m gpu -q > gpurun_out/many_files.log 2>&1; tail -3 gpurun_out/many_files.log
+timeout 900 python tools/files_e2e_bench.py > gpurun_out/files_e2e.json 2> gpurun_out/files_e2e.err; cat gpurun_out/files_e2e.json
