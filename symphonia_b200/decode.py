@@ -114,22 +114,28 @@ def decode_ogg_vorbis(engine, data, fmt=nat.FMT_S16, serial=None):
     return engine.pcm_pack_host(pcm, plan["spans"], plan["channels"], fmt, plan["total_frames"]), plan["sample_rate"]
 
 
-def adts_aac_plan(data):
-    """CPU half for an ADTS file: frames (symgpu_adts_index: header rules of adts.rs:130-309) -> raw_data_block payloads -> AAC-LC
-    entropy front-end (symgpu_aac_fe_*) -> the synthesis stage's batch.  The reader gives every frame 1024 samples and trims
-    nothing.  Returns dict(units [n,2], tns, coeffs [n,2,1024], runs, spans, channels, sample_rate, total_frames).  Packets the
-    front-end refuses are dropped, as a caller of the reference drops a DecodeError; the stream's parameters are the first
-    frame's (AdtsReader::try_new)."""
+def adts_aac_index(data):
+    """(packets, sample_rate, channels): the ADTS frame index and the stream's parameters (the first frame's, AdtsReader::try_new)."""
     packets, _ = packetizer.adts_index(data)
     if len(packets) == 0:
         raise ValueError("no ADTS frames")
     rate, channels = int(packets[0]["sample_rate"]), int(packets[0]["channels"])
     if channels not in (1, 2):
         raise ValueError("channel configuration outside AAC-LC mono / stereo")
+    return packets, rate, channels
+
+
+def adts_aac_plan(data, index=None, out=None):
+    """CPU half for an ADTS file: frames (symgpu_adts_index: header rules of adts.rs:130-309) -> raw_data_block payloads -> AAC-LC
+    entropy front-end (symgpu_aac_fe_*) -> the synthesis stage's batch.  The reader gives every frame 1024 samples and trims
+    nothing.  Returns dict(units [n,2], tns, coeffs [n,2,1024], runs, spans, channels, sample_rate, total_frames).  Packets the
+    front-end refuses are dropped, as a caller of the reference drops a DecodeError.  index: the result of adts_aac_index (else
+    computed here); out: (units, coeffs) staging slices with room for every packet."""
+    packets, rate, channels = adts_aac_index(data) if index is None else index
     fe = frontend.AacFrontend(rate, channels)
     table = np.zeros(len(packets), dtype=nat.PIECE_DTYPE)
     table["offset"], table["len"] = packets["offset"], packets["size"]
-    units, tns, coeffs, _ = fe.decode_packets(data, table)
+    units, tns, coeffs, _ = fe.decode_packets(data, table, out=out)
     fe.close()
     n = len(units)
     runs = np.zeros(1, dtype=nat.AAC_RUN_DTYPE)
@@ -140,6 +146,24 @@ def adts_aac_plan(data):
     spans["dst_frame"] = np.arange(n, dtype=np.uint64) * 1024
     return dict(units=units, tns=tns, coeffs=coeffs, runs=runs, spans=spans, channels=channels, sample_rate=rate,
                 total_frames=1024 * n)
+
+
+class Arena:
+    """Reusable staging memory for `plan_files`: take(name, shape, dtype) hands out a view of a buffer that persists across calls (and
+    grows when too small), so that a serving loop's front-ends write into pages that are already mapped instead of paying the first
+    touch of fresh allocations on every batch.  Contents are whatever the last user left."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def take(self, name, shape, dtype):
+        need = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        b = self._buf.get(name)
+        if b is None or b.size < need:
+            b = np.zeros(max(need + need // 4, 1), dtype=np.uint8)
+            b[::4096] = 0          # touch every page once, here
+            self._buf[name] = b
+        return b[:need].view(dtype).reshape(shape)
 
 
 def decode_adts_aac(engine, data, fmt=nat.FMT_S16, stream=0):
@@ -177,14 +201,33 @@ def plan_file(data):
     return dict(kind={1: "mpa1", 2: "mpa2", 3: "mp3"}[layer], payload=payload, runs=runs, spans=spans, sample_rate=rate, channels=channels, total_frames=total)
 
 
-def plan_files(files, threads=None):
+def plan_files(files, threads=None, arena=None):
     """Plans every file (front-ends on `threads` host threads: the native calls release the interpreter lock) and merges the plans
     into one batch per codec, every file a stream of its own.  Returns (plans, batches): batches[kind] = dict(members = indices into
-    `files`, first = each member's first unit in the batch, + the arrays of that codec's synthesis entry point)."""
+    `files`, first = each member's first unit in the batch, + the arrays of that codec's synthesis entry point).  AAC files are indexed
+    first and then decoded straight into their slices of the batch arrays (taken from `arena` when given: reusable staging memory);
+    a file whose front-end refuses packets leaves the tail of its slice unused -- runs name what is valid."""
     import concurrent.futures
     import os
+    kinds = [sniff(f) for f in files]
+    aac = [i for i, k in enumerate(kinds) if k == "aac"]
     with concurrent.futures.ThreadPoolExecutor(max_workers=threads or os.cpu_count()) as pool:
-        plans = list(pool.map(plan_file, files))
+        index = dict(zip(aac, pool.map(lambda i: adts_aac_index(files[i]), aac)))
+        starts, total = {}, 0
+        for i in aac:
+            starts[i] = total
+            total += len(index[i][0])
+        take = arena.take if arena is not None else (lambda name, shape, dtype: np.zeros(shape, dtype=dtype))
+        aac_units, aac_coeffs = take("aac_units", (total, 2), nat.AAC_UNIT_DTYPE), take("aac_coeffs", (total, 2, 1024), np.float32)
+
+        def plan(i):
+            if kinds[i] != "aac":
+                return plan_file(files[i])
+            a, n = starts[i], len(index[i][0])
+            p = adts_aac_plan(files[i], index[i], out=(aac_units[a:a + n], aac_coeffs[a:a + n]))
+            aac_units[a + len(p["units"]):a + n].view(np.uint8)[...] = 0   # refused packets: the unused tail holds valid (empty) records
+            return dict(p, kind="aac", slice_start=a)
+        plans = list(pool.map(plan, range(len(files))))
     batches = {}
     for kind in ("mp3", "mpa1", "mpa2", "aac", "vorbis"):
         members = [i for i, p in enumerate(plans) if p["kind"] == kind and len(p["spans"])]
@@ -203,13 +246,14 @@ def plan_files(files, threads=None):
             b["subbands"] = np.concatenate([plans[i]["payload"] for i in members])
             runs = np.concatenate([plans[i]["runs"] for i in members])
         elif kind == "aac":
-            units = [plans[i]["units"].copy() for i in members]
             base = 0
-            for u, i in zip(units, members):
+            for i in members:                                  # the units already lie in the batch array: re-base their TNS references
+                u = plans[i]["units"]
                 u["tns_first"] = np.where(u["n_tns"] > 0, u["tns_first"] + base, 0)
                 base += len(plans[i]["tns"])
-            b["units"], b["tns"] = np.concatenate(units), np.concatenate([plans[i]["tns"] for i in members])
-            b["coeffs"] = np.concatenate([plans[i]["coeffs"] for i in members])
+            b["first"] = first = [plans[i]["slice_start"] for i in members]
+            b["units"], b["coeffs"] = aac_units, aac_coeffs
+            b["tns"] = np.concatenate([plans[i]["tns"] for i in members])
             runs = np.concatenate([plans[i]["runs"] for i in members])
         else:
             slot = max(plans[i]["slot"] for i in members)

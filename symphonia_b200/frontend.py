@@ -296,15 +296,20 @@ class AacFrontend:
             raise SymgpuError(rc, "symgpu_aac_fe_decode")
         return units, tns[:n.value], coeffs
 
-    def decode_packets(self, data, packets, tns_base=0):
+    def decode_packets(self, data, packets, tns_base=0, out=None):
         """All packets of the stream in one call (PIECE_DTYPE table over `data`): (units [g,2], tns [t], coeffs [g,2,1024], frame_of [g]);
-        refused packets are left out."""
+        refused packets are left out.  out = (units [>= n, 2], coeffs [>= n, 2, 1024]): contiguous staging memory to decode into."""
         a = _u8(data)
         packets = np.ascontiguousarray(packets, dtype=nat.PIECE_DTYPE)
         n = len(packets)
-        units = np.zeros((n, 2), dtype=nat.AAC_UNIT_DTYPE)
         tns = np.zeros(16 * n, dtype=nat.AAC_TNS_DTYPE)
-        coeffs = np.zeros((n, 2, 1024), dtype=np.float32)
+        if out is None:
+            units = np.zeros((n, 2), dtype=nat.AAC_UNIT_DTYPE)
+            coeffs = np.zeros((n, 2, 1024), dtype=np.float32)
+        else:
+            units, coeffs = out
+            assert units.flags.c_contiguous and coeffs.flags.c_contiguous and len(units) >= n and len(coeffs) >= n
+            assert units.dtype == nat.AAC_UNIT_DTYPE and coeffs.dtype == np.float32
         frame_of = np.zeros(n, dtype=np.uint32)
         good, n_tns = ctypes.c_size_t(0), ctypes.c_size_t(0)
         rc = self._L.symgpu_aac_fe_decode_packets(self._h, _vp(a.ctypes.data) if a.size else None, a.size, _vp(packets.ctypes.data), n, int(tns_base),
