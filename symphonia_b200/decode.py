@@ -47,13 +47,11 @@ def decode_mpeg_audio(engine, data, fmt=nat.FMT_S16, stream=0):
     return engine.pcm_pack_host(pcm, spans, channels, fmt, total), rate
 
 
-def ogg_vorbis_plan(data, serial=None):
-    """CPU half for a Vorbis-in-Ogg file: pages -> packets (symgpu_ogg_index) -> identification / setup headers -> entropy front-end
-    (symgpu_vorbis_fe_*) -> the synthesis stage's batch, plus the reader's time line: per-packet duration and leading discard
-    (mappings/vorbis.rs:45-107) and the end trim against each page's granule position (symphonia-format-ogg/src/logical.rs:164-302;
-    a page whose predecessor completed no packet starts at end - total duration, a stream whose audio sits on one page starts at
-    -discard when that leaves padding).  Returns dict(stream, floors, units, floor_y, residue, runs, slot, spans, channels,
-    sample_rate, total_frames).  Packets the front-end refuses are dropped, as a caller of the reference drops a DecodeError."""
+def ogg_vorbis_index(data, serial=None):
+    """Everything about a Vorbis-in-Ogg file short of decoding its audio packets: pages -> packets (symgpu_ogg_index), the logical
+    stream gathered back to back, identification / setup headers, the front-end object (codebooks, floors, ...), per audio packet its
+    place, duration, leading discard (mappings/vorbis.rs:45-107) and end trim against the page granule positions
+    (symphonia-format-ogg/src/logical.rs:164-302)."""
     packets, pieces = packetizer.ogg_index(data)
     if len(packets) == 0:
         raise ValueError("no Ogg packets")
@@ -80,8 +78,19 @@ def ogg_vorbis_plan(data, serial=None):
     dur, discard = dur.astype(np.int64), discard.astype(np.int64)
     trim_end = packetizer.ogg_page_end_trims(mine["page_sequence"][audio], mine["page_absgp"][audio], dur, discard).astype(np.int64)
     fe = frontend.VorbisFrontend(ident_b, setup_b)
-    slot = fe.slot
-    units, fy, res, keep = fe.decode_packets(blob, table[audio])
+    return dict(blob=blob, table=table[audio], ident=ident, fe=fe, discard=discard, trim_end=trim_end)
+
+
+def ogg_vorbis_plan(data, serial=None, index=None, out=None, slot=None, floor_base=0):
+    """CPU half for a Vorbis-in-Ogg file: ogg_vorbis_index, then the entropy front-end (symgpu_vorbis_fe_*) over the audio packets
+    -> the synthesis stage's batch and the output spans with the reader's trims.  Returns dict(stream, floors, units, floor_y, residue,
+    runs, slot, spans, channels, sample_rate, total_frames).  Packets the front-end refuses are dropped, as a caller of the reference
+    drops a DecodeError.  index / out / slot / floor_base: for `plan_files` (decode into slices of a batch whose residue rows are
+    `slot` long and whose floor tables start at `floor_base`)."""
+    ix = ogg_vorbis_index(data, serial) if index is None else index
+    fe, ident, discard, trim_end = ix["fe"], ix["ident"], ix["discard"], ix["trim_end"]
+    slot = fe.slot if slot is None else slot
+    units, fy, res, keep = fe.decode_packets(ix["blob"], ix["table"], slot=slot, floor_base=floor_base, out=out)
     n = len(units)
     stream, floors = np.array([fe.stream], dtype=nat.VORBIS_STREAM_DTYPE), fe.floors.copy()
     fe.close()
@@ -99,7 +108,8 @@ def ogg_vorbis_plan(data, serial=None):
     total = int(left.sum())
     runs = np.zeros(1, dtype=nat.VORBIS_RUN_DTYPE)
     runs["n_packets"] = n
-    return dict(stream=stream, floors=floors, units=units, floor_y=fy, residue=res, runs=runs, slot=slot, spans=spans, channels=int(ident["channels"]), sample_rate=int(ident["sample_rate"]), total_frames=total)
+    return dict(stream=stream, floors=floors, units=units, floor_y=fy, residue=res, runs=runs, slot=slot, spans=spans,
+                channels=int(ident["channels"]), sample_rate=int(ident["sample_rate"]), total_frames=total)
 
 
 def decode_ogg_vorbis(engine, data, fmt=nat.FMT_S16, serial=None):
@@ -219,8 +229,24 @@ def plan_files(files, threads=None, arena=None):
             total += len(index[i][0])
         take = arena.take if arena is not None else (lambda name, shape, dtype: np.zeros(shape, dtype=dtype))
         aac_units, aac_coeffs = take("aac_units", (total, 2), nat.AAC_UNIT_DTYPE), take("aac_coeffs", (total, 2, 1024), np.float32)
+        vor = [i for i, k in enumerate(kinds) if k == "vorbis"]
+        vindex = dict(zip(vor, pool.map(lambda i: ogg_vorbis_index(files[i]), vor)))
+        vstarts, vfloor, vtotal, nfl = {}, {}, 0, 0
+        for i in vor:
+            vstarts[i], vfloor[i] = vtotal, nfl
+            vtotal += len(vindex[i]["table"])
+            nfl += len(vindex[i]["fe"].floors)
+        vslot = max([vindex[i]["fe"].slot for i in vor], default=0)
+        v_units, v_fy = take("vorbis_units", (vtotal,), nat.VORBIS_UNIT_DTYPE), take("vorbis_floor_y", (vtotal, 2, 65), np.uint16)
+        v_res = take("vorbis_residue", (vtotal, 2, vslot), np.float32)
 
         def plan(i):
+            if kinds[i] == "vorbis":
+                a, n = vstarts[i], len(vindex[i]["table"])
+                p = ogg_vorbis_plan(files[i], index=vindex[i], out=(v_units[a:a + n], v_fy[a:a + n], v_res[a:a + n]), slot=vslot, floor_base=vfloor[i])
+                tail = v_units[a + len(p["units"]):a + n].view(np.uint8)
+                tail[...] = 0
+                return dict(p, kind="vorbis", slice_start=a)
             if kinds[i] != "aac":
                 return plan_file(files[i])
             a, n = starts[i], len(index[i][0])
@@ -256,19 +282,10 @@ def plan_files(files, threads=None, arena=None):
             b["tns"] = np.concatenate([plans[i]["tns"] for i in members])
             runs = np.concatenate([plans[i]["runs"] for i in members])
         else:
-            slot = max(plans[i]["slot"] for i in members)
-            units, res, base = [], [], 0
-            for i in members:
-                u = plans[i]["units"].copy()
-                u["floor"] = np.where(u["floor"] == 0xFFFF, 0xFFFF, u["floor"] + base).astype(np.uint16)
-                base += len(plans[i]["floors"])
-                units.append(u)
-                r = np.zeros((len(u), 2, slot), dtype=np.float32)
-                r[:, :, :plans[i]["slot"]] = plans[i]["residue"]
-                res.append(r)
+            b["first"] = first = [plans[i]["slice_start"] for i in members]
             b["streams"] = np.concatenate([plans[i]["stream"] for i in members])
-            b["floors"] = np.concatenate([plans[i]["floors"] for i in members])
-            b["units"], b["floor_y"], b["residue"], b["slot"] = np.concatenate(units), np.concatenate([plans[i]["floor_y"] for i in members]), np.concatenate(res), slot
+            b["floors"] = np.concatenate([vindex[i]["fe"].floors for i in vor])      # every Vorbis file's tables, in file order (floor_base)
+            b["units"], b["floor_y"], b["residue"], b["slot"] = v_units, v_fy, v_res, vslot
             runs = np.concatenate([plans[i]["runs"] for i in members])
         runs = runs.copy()
         runs["stream"] = np.arange(len(members))

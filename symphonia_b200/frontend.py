@@ -229,16 +229,22 @@ class VorbisFrontend:
             raise SymgpuError(rc, "symgpu_vorbis_fe_decode")
         return unit[0], floor_y, residue
 
-    def decode_packets(self, data, packets, slot=None, floor_base=0):
+    def decode_packets(self, data, packets, slot=None, floor_base=0, out=None):
         """All audio packets of the stream in one call (PIECE_DTYPE table over `data`): (units [g], floor_y [g,2,65], residue [g,2,slot],
-        packet_of [g]); refused packets are left out."""
+        packet_of [g]); refused packets are left out.  out = (units [>= n], floor_y [>= n,2,65], residue [>= n,2,slot]): contiguous
+        staging memory to decode into."""
         slot = self.slot if slot is None else slot
         a = _u8(data)
         packets = np.ascontiguousarray(packets, dtype=nat.PIECE_DTYPE)
         n = len(packets)
-        units = np.zeros(n, dtype=nat.VORBIS_UNIT_DTYPE)
-        floor_y = np.zeros((n, 2, 65), dtype=np.uint16)
-        residue = np.zeros((n, 2, slot), dtype=np.float32)
+        if out is None:
+            units = np.zeros(n, dtype=nat.VORBIS_UNIT_DTYPE)
+            floor_y = np.zeros((n, 2, 65), dtype=np.uint16)
+            residue = np.zeros((n, 2, slot), dtype=np.float32)
+        else:
+            units, floor_y, residue = out
+            assert all(x.flags.c_contiguous and len(x) >= n for x in out) and residue.shape[1:] == (2, slot) and residue.dtype == np.float32
+            assert units.dtype == nat.VORBIS_UNIT_DTYPE and floor_y.dtype == np.uint16 and floor_y.shape[1:] == (2, 65)
         packet_of = np.zeros(n, dtype=np.uint32)
         good = ctypes.c_size_t(0)
         rc = self._L.symgpu_vorbis_fe_decode_packets(self._h, _vp(a.ctypes.data) if a.size else None, a.size, _vp(packets.ctypes.data), n, slot, floor_base,
