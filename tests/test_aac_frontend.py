@@ -524,3 +524,47 @@ def test_audio_specific_config_every_object_type_and_random_tails():
     # random bytes
     for _ in range(400):
         _asc_both(rng.integers(0, 256, int(rng.integers(0, 9)), dtype=np.uint8).tobytes())
+
+
+def test_audio_specific_config_extension_edges():
+    """Cases the randomised tails did not pin (found by mutating the parser, tools/mutate_frontend.py asc)."""
+    # ER AAC LD (23) with the extension flag: three resilience bits are skipped before extensionFlag3 (mod.rs:307-314)
+    st_, a = _asc_both(_asc_bits(23, 4, 2, tail=((0, 1), (0, 1), (1, 1), (7, 3), (0, 1), (0, 2))).bytes())
+    assert st_ == 0 and a["object_type"] == 23
+    # backward-compatible signalling behind an explicit SBR prefix: sync 0x2b7, SBR, sbr_present = 0 switches SBR OFF again (:390-404) ...
+    core = ((3, 4), (2, 5), (0, 3))                                   # extension rate 48 kHz, object type LC, GASpecificConfig
+    st_, a = _asc_both(_asc_bits(5, 6, 2, tail=core + ((0x2B7, 11), (5, 5), (0, 1))).bytes())
+    assert st_ == 0 and a["sbr_present"] == 0 and a["has_ext"] == 1 and ao.decoder_accepts(a) is None
+    st_, a = _asc_both(_asc_bits(5, 6, 2, tail=core + ((0x2B6, 11), (5, 5), (0, 1))).bytes())
+    assert st_ == 0 and a["sbr_present"] == 1
+    # ... and with sbr_present = 1 a second sync (0x548) carries the PS flag, if twelve bits are left for it (:396-402)
+    st_, a = _asc_both(_asc_bits(5, 6, 2, tail=core + ((0x2B7, 11), (5, 5), (1, 1), (3, 4), (0x548, 11), (1, 1))).bytes())
+    assert st_ == 0 and (a["sbr_present"], a["ps_present"]) == (1, 1)
+    st_, a = _asc_both(_asc_bits(5, 6, 2, tail=core + ((0x2B7, 11), (5, 5), (1, 1), (3, 4), (0x549, 11), (1, 1))).bytes())
+    assert st_ == 0 and a["ps_present"] == 0
+    # (exactly twelve bits left are enough for it: a configuration with the 14-bit core-coder delay ends on a byte boundary here)
+    w = _asc_bits(5, 6, 2, tail=((3, 4), (2, 5), (0, 1), (1, 1), (0, 14), (0, 1), (0x2B7, 11), (5, 5), (1, 1), (3, 4), (0x548, 11), (1, 1)))
+    assert len(w.bits) == 72
+    st_, a = _asc_both(w.bytes())
+    assert st_ == 0 and a["ps_present"] == 1
+    # exactly sixteen bits behind the configuration are enough to look for the sync -- and then the flag behind it is missing
+    found = 0
+    for inner in (2, 6, 17, 20):
+        for depends in (0, 1):
+            for ext in (0, 1):
+                tail = ((3, 4), (inner, 5), (0, 1), (depends, 1)) + (((0, 14),) if depends else ()) + ((ext, 1),)
+                if inner in (6, 20):
+                    tail += ((0, 3),)                                   # layer number
+                if ext:
+                    tail += (((0, 3),) if inner in (17, 20) else ()) + ((0, 1),)   # resilience flags, extensionFlag3
+                if inner in (17, 20):
+                    tail += ((0, 2),)                                   # epConfig
+                w = _asc_bits(5, 6, 2, tail=tail)
+                if len(w.bits) % 8:
+                    continue
+                found += 1
+                blob = _asc_bits(5, 6, 2, tail=tail + ((0x2B7, 11), (5, 5))).bytes()
+                assert len(blob) * 8 == len(w.bits) + 16
+                assert _asc_both(blob)[0] == 1
+                assert _asc_both(blob + b"\x00")[0] == 0
+    assert found

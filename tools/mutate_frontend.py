@@ -64,6 +64,34 @@ TARGETS = {
         ("CHECK(pairs[pair_no]->channel == channel);", ""),
         ("2.51984209978974632953f * scale", "2.5198421f * scale * 1.0000001f"),
     ]),
+    "asc": dict(src="aac_frontend.cpp", prefix="symgpu_aac_", tests=["tests/test_aac_frontend.py"], mutants=[
+        ("if (v == 31) v = bs.read(6) + 32;", "if (v == 31) v = bs.read(6) + 31;"),
+        ("if (idx <= 12) rate = kRates[idx];", "if (idx <= 11) rate = kRates[idx];"),
+        ("else if (idx == 15) rate = bs.read(24);", "else if (idx >= 14) rate = bs.read(24);"),
+        ("CHECK(out->sample_rate != 0);", ""),
+        ("CHECK(idx <= 7);", "CHECK(idx <= 8);"),
+        ("static const uint8_t kChannels[8] = {0, 1, 2, 3, 4, 5, 6, 8};", "static const uint8_t kChannels[8] = {0, 1, 2, 3, 4, 5, 6, 7};"),
+        ("if (aot == 5 || aot == 29) {  // SBR / PS", "if (aot == 5) {  // SBR / PS"),
+        ("out->ps_present = aot == 29,", "out->ps_present = 0,"),
+        ("if (aot == 22 && (st = channel_config(out->ext_channels)) != SYMGPU_OK) return st;", ""),
+        ("out->samples = short_frame ? 960 : 1024;", "out->samples = 1024;"),
+        ("if (depends_on_core) bs.read(14);", "if (depends_on_core) bs.read(13);"),
+        ("if (out->channels == 0) return SYMGPU_ERR_UNSUPPORTED;  // program config element", ""),
+        ("if (aot == 6 || aot == 20) bs.read(3);", "if (aot == 6) bs.read(3);"),
+        ("if (aot == 22) bs.read(5), bs.read(11);", ""),
+        ("if (aot == 17 || aot == 19 || aot == 20 || aot == 23) bs.read(3);", "if (aot == 17 || aot == 19 || aot == 20) bs.read(3);"),
+        ("if (extension_flag3) return SYMGPU_ERR_UNSUPPORTED;", ""),
+        ("if (ep_config >= 2) return SYMGPU_ERR_UNSUPPORTED;", "if (ep_config >= 3) return SYMGPU_ERR_UNSUPPORTED;"),
+        ("if (out->has_ext && bs.left() >= 16) {", "if (out->has_ext && bs.left() >= 17) {"),
+        ("if (out->has_ext && bs.left() >= 16) {", "if (bs.left() >= 16) {"),
+        ("if (sync == 0x2b7) {", "if (sync == 0x2b6) {"),
+        ("if (bs.left() >= 12) {", "if (bs.left() >= 13) {"),
+        ("if (bs.read(11) == 0x548) out->ps_present = bs.read_bool();", "if (bs.read(11) == 0x549) out->ps_present = bs.read_bool();"),
+        ("if (n < 2) return SYMGPU_ERR_DECODE;", "if (n < 1) return SYMGPU_ERR_DECODE;"),
+        ("if (asc.object_type != 2 || asc.sbr_present || asc.channels > 2 || asc.samples != 1024) return SYMGPU_ERR_UNSUPPORTED;", "if (asc.object_type != 2 || asc.channels > 2 || asc.samples != 1024) return SYMGPU_ERR_UNSUPPORTED;"),
+        ("if (asc.object_type != 2 || asc.sbr_present || asc.channels > 2 || asc.samples != 1024) return SYMGPU_ERR_UNSUPPORTED;", "if (asc.object_type != 2 || asc.sbr_present || asc.channels > 2) return SYMGPU_ERR_UNSUPPORTED;"),
+        ("case 35: case 36: case 37: case 38: case 39: case 40: case 41:", "case 35: case 36: case 37: case 38: case 39: case 40:"),
+    ]),
     "vorbis": dict(src="vorbis_frontend.cpp", prefix="symgpu_vorbis_fe_", tests=["tests/test_vorbis_frontend.py", "tests/test_zz_ogg_vorbis_to_pcm.py"], mutants=[
         ("size_t k = (64 - left) >> 3;", "size_t k = (63 - left) >> 3;"),
         ("            needed -= left;\n            if (!fetch()) return false;", "            if (!fetch()) return false;\n            needed -= left > needed ? needed : left;"),
