@@ -56,3 +56,49 @@ def test_two_rank_sharding_and_table_broadcast(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+FILES_WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    import torch, torch.distributed as dist
+    sys.path.insert(0, os.environ["SYMGPU_ROOT"])
+    from symphonia_b200 import decode, sharding
+    from tests.test_zz_many_files import _files
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    files = _files()                                  # the same corpus on every rank (seeded)
+    mine = sharding.shard_streams(len(files), rank, world)
+    plans, batches = decode.plan_files([files[i] for i in mine], threads=2)
+    # every file is planned by exactly one rank, and the ranks' audio adds up to the corpus planned in one piece on rank 0
+    owner = torch.zeros(len(files), dtype=torch.int32)
+    owner[torch.from_numpy(mine)] = 1
+    dist.all_reduce(owner)
+    assert (owner == 1).all()
+    frames = torch.tensor([sum(p["total_frames"] for p in plans)], dtype=torch.int64)
+    dist.all_reduce(frames)
+    if rank == 0:
+        whole, _ = decode.plan_files(files, threads=2)
+        assert frames.item() == sum(p["total_frames"] for p in whole)
+        # a file's plan does not depend on which batch it is planned in
+        for k, i in enumerate(mine):
+            a, b = plans[k], whole[i]
+            assert a["kind"] == b["kind"] and a["total_frames"] == b["total_frames"] and a["spans"].tobytes() == b["spans"].tobytes()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_two_rank_file_corpus(tmp_path):
+    """BASELINE config 4's shape on the host side: a mixed corpus of files sharded by stream over two ranks, no data-path collective."""
+    script = tmp_path / "files_worker.py"
+    script.write_text(FILES_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, SYMGPU_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2
