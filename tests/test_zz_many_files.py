@@ -36,6 +36,25 @@ def _files():
     pages = tv.st.ogg_paginate(5, [s.ident], rng, eos=False) + tv.st.ogg_paginate(5, [b"\x03vorbis" + bytes(9), s.setup], rng, first_sequence=1, bos=False, eos=False)
     pages += tv.st.ogg_paginate(5, pk, rng, first_sequence=len(pages), bos=False, granule_of=[10 ** 9] * len(pk))
     files.append(b"".join(pages))
+    # a Vorbis stream with three modes and, in the middle, an audio packet that names mode 3: valid pages, a packet the decoder refuses
+    seed = 0
+    while True:
+        rng = np.random.default_rng(4000 + seed)
+        s = tv.vb.Stream(rng, bs_exp=(8, 11), per_word=1)
+        if len(s.modes) == 3:
+            break
+        seed += 1
+    pk, gran, g = [], [], 0
+    for k in range(10):
+        b, t = s.packet()
+        if k:
+            g += ((1 << (11 if t["prev_block_flag"] else 8)) + (1 << (11 if t["block_flag"] else 8))) // 4
+        pk.append(b), gran.append(g)
+        if k == 4:
+            pk.append(bytes([3 << 1]) + bytes(12)), gran.append(g)
+    pages = tv.st.ogg_paginate(6, [s.ident], rng, eos=False) + tv.st.ogg_paginate(6, [b"\x03vorbis" + bytes(9), s.setup], rng, first_sequence=1, bos=False, eos=False)
+    pages += tv.st.ogg_paginate(6, pk, rng, max_segments=7, first_sequence=len(pages), bos=False, granule_of=gran)
+    files.append(b"".join(pages))
     order = np.random.default_rng(3).permutation(len(files))
     return [files[i] for i in order]
 
@@ -106,6 +125,7 @@ def test_arena_reuse_leaves_nothing_behind(oracle):
                 continue
             assert (np.asarray(v).tobytes() == np.asarray(w).tobytes()) if isinstance(v, np.ndarray) else v == w, (kind, key)
     assert holes > 0                                     # the damaged file lost frames: its slice has an unused tail
+    assert len(a["vorbis"]["units"]) > int(a["vorbis"]["runs"]["n_packets"].sum()) or not any(len(f) and f[:4] == b"OggS" for f in other)
     # and the host entry point's descriptor check accepts the whole extent, unused tails included
     import symphonia_b200 as sb
     u, t = a["aac"]["units"], a["aac"]["tns"]
