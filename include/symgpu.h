@@ -740,6 +740,14 @@ symgpu_status symgpu_aac_fe_decode(symgpu_aac_fe* fe, const uint8_t* packet, siz
 symgpu_status symgpu_aac_fe_decode_packets(symgpu_aac_fe* fe, const uint8_t* data, size_t n, const symgpu_piece* packets, size_t n_packets,
                                            uint32_t tns_base, symgpu_aac_unit* units, symgpu_aac_tns* tns, size_t tns_cap, float* coeffs,
                                            uint32_t* frame_of, size_t* n_good, size_t* n_tns);
+/* The blocks of ONE stream as independent jobs on n_threads host threads (the decomposition a device front-end would use):
+ * every block decoded from a fresh state, noise generators jumped ahead over the prefix sums of each block's draws, blocks that drew
+ * noise decoded again from the right state, window history chained afterwards.  units [2 n_packets], coeffs [2048 n_packets], tns
+ * compacted as in symgpu_aac_fe_decode_packets.  SYMGPU_OK: identical to the serial front-end.  SYMGPU_ERR_RESET: the stream needs the
+ * serial path (a block is refused, the element layout changes, or a pulse reads a scale left behind by an earlier block). */
+symgpu_status symgpu_aac_fe_decode_packets_jobs(uint32_t sample_rate, uint32_t channels, const uint8_t* data, size_t n, const symgpu_piece* packets,
+                                                size_t n_packets, uint32_t tns_base, symgpu_aac_unit* units, symgpu_aac_tns* tns, size_t tns_cap,
+                                                float* coeffs, size_t* n_tns, uint32_t n_threads);
 /* The dequantisation tables the front-end uses (for tests): x^(4/3) [8192], 2^((i-156)/4) [256], 0.5^((i-155)/4) [256]. */
 void symgpu_aac_fe_tables(float* pow43, float* normal_scf, float* intensity_scf);
 

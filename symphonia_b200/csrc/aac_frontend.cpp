@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/symgpu.h"
@@ -180,7 +181,17 @@ struct Bits {
 
 struct Lcg {  // common.rs:96-111
     uint32_t state = 0x1f2e3d4c;
-    int32_t next() { return int32_t(state = state * 1664525u + 1013904223u); }
+    uint64_t draws = 0;
+    int32_t next() { return ++draws, int32_t(state = state * 1664525u + 1013904223u); }
+    // The state after `n` more draws: the n-th power of the affine map x -> a x + c, by squaring (mod 2^32).
+    static uint32_t jump(uint32_t s, uint64_t n) {
+        uint32_t a = 1664525u, c = 1013904223u, ra = 1, rc = 0;
+        for (; n; n >>= 1) {
+            if (n & 1) ra *= a, rc = rc * a + c;
+            c = c * a + c, a *= a;
+        }
+        return ra * s + rc;
+    }
 };
 
 enum : uint8_t { ZERO_HCB = 0, RESERVED_HCB = 12, NOISE_HCB = 13, INTENSITY_HCB2 = 14, INTENSITY_HCB = 15 };
@@ -207,7 +218,7 @@ struct Ics {
     bool long_win = true;
     // Ics
     uint32_t global_gain = 0;
-    bool has_pulse = false, has_tns = false;
+    bool has_pulse = false, has_tns = false, stale_scale_read = false;
     uint32_t n_pulse = 0, pulse_start = 0;
     uint8_t pulse_off[4] = {}, pulse_amp[4] = {};
     uint32_t n_filt[8] = {};
@@ -502,6 +513,7 @@ struct Ics {
             k += pulse_off[i];
             if (k >= 1024) return;
             while (b.v[band + 1] <= k) ++band;
+            if (band >= max_sfb) stale_scale_read = true;  // a band no section coded: the scale is whatever an earlier block left
             const float scale = scales[0][band];
             float base = coeffs[k];
             if (base != 0.0f) {
@@ -605,10 +617,12 @@ struct symgpu_aac_fe {
     uint32_t channels, rate_idx;
     const SubbandInfo* sb;
     std::vector<std::unique_ptr<Pair>> pairs;
+    std::vector<uint32_t> lcg_start;  // job mode: the noise generator's state when pair k is first seen
 
     symgpu_status set_pair(size_t pair_no, uint32_t channel, bool pair) {  // mod.rs:114-126
         if (pairs.size() <= pair_no) {
             pairs.emplace_back(new Pair(pair, channel, sb));
+            if (pair_no < lcg_start.size()) pairs.back()->lcg.state = lcg_start[pair_no];
         } else {
             CHECK(pairs[pair_no]->channel == channel);
             CHECK(pairs[pair_no]->is_pair == pair);
@@ -869,6 +883,79 @@ symgpu_status symgpu_aac_fe_decode_packets(symgpu_aac_fe* fe, const uint8_t* dat
         frame_of[good++] = uint32_t(i);
     }
     *n_good = good, *n_tns = total;
+    return SYMGPU_OK;
+}
+
+// Blocks of ONE stream as independent jobs: between raw_data_blocks only the previous window shape, the element layout
+// and the noise generators carry over.  Pass A decodes every block with a fresh state on `n_threads` threads and counts each
+// pair's noise draws; the generators' states at every block follow by jumping ahead over the prefix sums; pass B decodes again the
+// blocks that drew noise, from the right states; window history is chained afterwards.  Exact for streams every block of which
+// decodes with one element layout; anything else (a refused block, a changed layout, a pulse reading a scale an earlier block left
+// behind) is SYMGPU_ERR_RESET: the caller takes the serial path, which keeps the reference's state across failures.
+symgpu_status symgpu_aac_fe_decode_packets_jobs(uint32_t sample_rate, uint32_t channels, const uint8_t* data, size_t n, const symgpu_piece* packets,
+                                                size_t n_packets, uint32_t tns_base, symgpu_aac_unit* units, symgpu_aac_tns* tns, size_t tns_cap,
+                                                float* coeffs, size_t* n_tns, uint32_t n_threads) {
+    if ((!data && n) || (n_packets && (!packets || !units || !coeffs)) || !n_tns || (tns_cap && !tns)) return SYMGPU_ERR_ARG;
+    if (channels < 1 || channels > 2) return SYMGPU_ERR_UNSUPPORTED;
+    if (n_threads == 0) n_threads = 1;
+    struct Job {
+        symgpu_status st = SYMGPU_OK;
+        uint32_t n_pairs = 0, n_tns = 0;
+        bool is_pair[2] = {false, false}, stale = false;
+        uint64_t draws[2] = {0, 0};
+        uint32_t start[2] = {0x1f2e3d4c, 0x1f2e3d4c};
+        symgpu_aac_tns tns[16];
+    };
+    std::vector<Job> jobs(n_packets);
+    auto run = [&](size_t i, bool with_start) {
+        Job& j = jobs[i];
+        symgpu_aac_fe* fe = nullptr;
+        if (symgpu_aac_fe_create(sample_rate, channels, &fe) != SYMGPU_OK) return void(j.st = SYMGPU_ERR_LIMIT);
+        if (with_start) fe->lcg_start.assign(j.start, j.start + 2);
+        if (packets[i].offset > n || packets[i].len > n - packets[i].offset) j.st = SYMGPU_ERR_DECODE;
+        else j.st = symgpu_aac_fe_decode(fe, data + packets[i].offset, packets[i].len, 0, units + 2 * i, j.tns, &j.n_tns, coeffs + 2048 * i);
+        j.n_pairs = uint32_t(fe->pairs.size() < 2 ? fe->pairs.size() : 2);
+        for (uint32_t k = 0; k < j.n_pairs; ++k) {
+            const Pair& p = *fe->pairs[k];
+            j.is_pair[k] = p.is_pair, j.draws[k] = p.lcg.draws;
+            j.stale = j.stale || p.ics[0].stale_scale_read || p.ics[1].stale_scale_read;
+        }
+        symgpu_aac_fe_destroy(fe);
+    };
+    auto parallel = [&](bool second) {
+        std::vector<std::thread> pool;
+        for (uint32_t t = 0; t < n_threads; ++t)
+            pool.emplace_back([&, t] {
+                for (size_t i = t; i < n_packets; i += n_threads)
+                    if (!second || jobs[i].draws[0] || jobs[i].draws[1]) run(i, second);
+            });
+        for (auto& th : pool) th.join();
+    };
+    parallel(false);
+    uint64_t total[2] = {0, 0};
+    for (size_t i = 0; i < n_packets; ++i) {
+        const Job& j = jobs[i];
+        if (j.st != SYMGPU_OK || j.stale || j.n_pairs != jobs[0].n_pairs || j.is_pair[0] != jobs[0].is_pair[0] || j.is_pair[1] != jobs[0].is_pair[1])
+            return SYMGPU_ERR_RESET;
+        for (int k = 0; k < 2; ++k) jobs[i].start[k] = Lcg::jump(0x1f2e3d4c, total[k]), total[k] += j.draws[k];
+    }
+    parallel(true);
+    size_t at = 0;
+    for (size_t i = 0; i < n_packets; ++i) {
+        Job& j = jobs[i];
+        if (j.st != SYMGPU_OK) return SYMGPU_ERR_RESET;
+        if (at + j.n_tns > tns_cap) return SYMGPU_ERR_LIMIT;
+        uint32_t local = 0;
+        for (uint32_t c = 0; c < 2; ++c) {
+            symgpu_aac_unit& u = units[2 * i + c];
+            u.prev_window_shape = i ? units[2 * (i - 1) + c].window_shape : 0;
+            u.tns_first = u.n_tns ? uint32_t(tns_base + at + local) : 0;
+            local += u.n_tns;
+        }
+        std::memcpy(tns + at, j.tns, j.n_tns * sizeof(symgpu_aac_tns));
+        at += j.n_tns;
+    }
+    *n_tns = at;
     return SYMGPU_OK;
 }
 

@@ -342,3 +342,23 @@ def aac_asc_parse(extra_data):
     if rc != 0:
         raise SymgpuError(rc, "symgpu_aac_asc_parse")
     return out[0]
+
+
+def aac_decode_packets_jobs(sample_rate, channels, data, packets, tns_base=0, threads=4):
+    """The blocks of one AAC-LC stream as independent jobs on host threads (symgpu_aac_fe_decode_packets_jobs): (units [n,2], tns,
+    coeffs [n,2,1024]) identical to AacFrontend.decode_packets, or None when the stream needs the serial path."""
+    a = _u8(data)
+    packets = np.ascontiguousarray(packets, dtype=nat.PIECE_DTYPE)
+    n = len(packets)
+    units = np.zeros((n, 2), dtype=nat.AAC_UNIT_DTYPE)
+    tns = np.zeros(16 * n, dtype=nat.AAC_TNS_DTYPE)
+    coeffs = np.zeros((n, 2, 1024), dtype=np.float32)
+    n_tns = ctypes.c_size_t(0)
+    rc = nat.lib().symgpu_aac_fe_decode_packets_jobs(int(sample_rate), int(channels), _vp(a.ctypes.data) if a.size else None, a.size, _vp(packets.ctypes.data), n,
+                                                     int(tns_base), _vp(units.ctypes.data), _vp(tns.ctypes.data), len(tns), _vp(coeffs.ctypes.data),
+                                                     ctypes.byref(n_tns), int(threads))
+    if rc == 4:
+        return None
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_aac_fe_decode_packets_jobs")
+    return units, tns[:n_tns.value], coeffs

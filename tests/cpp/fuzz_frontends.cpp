@@ -150,6 +150,22 @@ static void run_all(const std::vector<uint8_t>& d) {
             }
             symgpu_aac_fe_destroy(fe);
         }
+        {   // the same blocks as independent jobs
+            std::vector<symgpu_piece> tab;
+            size_t at = 6;
+            while (at + 2 <= n && tab.size() < 64) {
+                const size_t len = size_t(p[at]) | size_t(p[at + 1]) << 8;
+                at += 2;
+                const size_t take = len < n - at ? len : n - at;
+                tab.push_back(symgpu_piece{at, uint32_t(take), 0});
+                at += take;
+            }
+            std::vector<symgpu_aac_unit> u(2 * tab.size() + 2);
+            std::vector<symgpu_aac_tns> t(16 * tab.size() + 16);
+            std::vector<float> co(2048 * tab.size() + 2048);
+            size_t nt = 0;
+            symgpu_aac_fe_decode_packets_jobs(rates[p[4] & 7], 1 + (p[5] & 1), p, n, tab.data(), tab.size(), 0, u.data(), t.data(), t.size(), co.data(), &nt, 2);
+        }
     }
     {
         size_t count = 0;

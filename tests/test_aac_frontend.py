@@ -568,3 +568,75 @@ def test_audio_specific_config_extension_edges():
                 assert _asc_both(blob)[0] == 1
                 assert _asc_both(blob + b"\x00")[0] == 0
     assert found
+
+
+# ---- the blocks of a stream as independent jobs ---------------------------------------------------------------------------------
+
+def test_blocks_as_independent_jobs_equal_the_serial_front_end():
+    """symgpu_aac_fe_decode_packets_jobs: every block from a fresh state, noise generators jumped ahead over the prefix sums of the
+    draws, window history chained afterwards -- the same bits as the serial front-end, for any thread count."""
+    done = noisy = 0
+    for seed, s, _ in _streams(600, 20):
+        pk = [s.packet()[0] for _ in range(14)]
+        blob = b"".join(pk)
+        table = np.zeros(len(pk), dtype=nat.PIECE_DTYPE)
+        table["len"] = [len(p) for p in pk]
+        table["offset"] = np.concatenate([[0], np.cumsum(table["len"][:-1], dtype=np.uint64)])
+        fe = frontend.AacFrontend(s.rate, s.channels)
+        units, tns, coeffs, frame_of = fe.decode_packets(blob, table, tns_base=7)
+        fe.close()
+        assert len(units) == len(pk)
+        for threads in (1, 3, 8):
+            got = frontend.aac_decode_packets_jobs(s.rate, s.channels, blob, table, tns_base=7, threads=threads)
+            assert got is not None, seed                     # (the writer keeps pulses inside the coded bands: no stale scale is read)
+            assert got[0].tobytes() == units.tobytes() and got[1].tobytes() == tns.tobytes(), (seed, threads)
+            assert np.array_equal(u32(got[2]), u32(coeffs)), (seed, threads)
+        done += 1
+        o = ao.AacFrontend(s.rate, s.channels)
+        for p in pk[:-1]:
+            o.decode(p)
+        noisy += int(any(q.lcg.state != 0x1F2E3D4C for q in o.pairs))   # noise was drawn before the last block: its start state is a jump
+    assert done == 20 and noisy >= 15
+    # the generator's jump-ahead against stepping it
+    lcg = ao.Lcg()
+    states = [lcg.state]
+    for _ in range(3000):
+        lcg.next()
+        states.append(lcg.state)
+    a, c = 1664525, 1013904223
+
+    def jump(s0, n):
+        ra, rc, aa, cc = 1, 0, a, c
+        while n:
+            if n & 1:
+                ra, rc = (ra * aa) % (1 << 32), (rc * aa + cc) % (1 << 32)
+            cc, aa = (cc * aa + cc) % (1 << 32), (aa * aa) % (1 << 32)
+            n >>= 1
+        return (ra * s0 + rc) % (1 << 32)
+    assert all(jump(states[0], n) == states[n] for n in (0, 1, 2, 3, 17, 1000, 2999, 3000))
+
+
+def test_streams_that_need_the_serial_path_say_so():
+    rng = np.random.default_rng(5)
+    s = ab.Stream(rng, 44100, 2)
+    pk = [s.packet()[0] for _ in range(8)]
+    pk[3] = pk[3][:len(pk[3]) // 2]                       # a block that ends early: refused, and the reference's state carries on from its middle
+    blob = b"".join(pk)
+    table = np.zeros(len(pk), dtype=nat.PIECE_DTYPE)
+    table["len"] = [len(p) for p in pk]
+    table["offset"] = np.concatenate([[0], np.cumsum(table["len"][:-1], dtype=np.uint64)])
+    assert frontend.aac_decode_packets_jobs(44100, 2, blob, table) is None
+    # a layout that changes between blocks (two single-channel elements, then a pair)
+    two, pair = ab.Stream(rng, 44100, 2, layout=["sce", "sce"]), ab.Stream(rng, 44100, 2)
+    pk = [two.packet(extras=False)[0], pair.packet(extras=False)[0]]
+    blob = b"".join(pk)
+    table = np.zeros(2, dtype=nat.PIECE_DTYPE)
+    table["len"] = [len(p) for p in pk]
+    table["offset"] = [0, len(pk[0])]
+    assert frontend.aac_decode_packets_jobs(44100, 2, blob, table) is None
+    # a pulse that lands above the coded bands reads a scale an earlier block left behind
+    w = _sce(150, 2, [(1, 2)], scf=[("d", 0), ("d", 0)], pulse=(10, [(0, 5)]), spectral=[QUAD_ZERO, QUAD_ZERO])
+    table = np.zeros(1, dtype=nat.PIECE_DTYPE)
+    table["len"] = len(w)
+    assert frontend.aac_decode_packets_jobs(44100, 1, w, table) is None
+    assert frontend.aac_decode_packets_jobs(44100, 1, _sce(150, 2, [(1, 2)], scf=[("d", 0), ("d", 0)], pulse=(1, [(0, 5)]), spectral=[QUAD_ZERO, QUAD_ZERO]), table) is not None

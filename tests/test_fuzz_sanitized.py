@@ -61,7 +61,7 @@ def _seeds(rng):
 def test_parsers_under_address_and_ub_sanitizers(tmp_path):
     csrc = os.path.join(ROOT, "symphonia_b200", "csrc")
     exe = str(tmp_path / "fuzz_frontends")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-ffp-contract=off",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-ffp-contract=off",
                            "-I/usr/local/cuda/include", "-o", exe, os.path.join(ROOT, "tests", "cpp", "fuzz_frontends.cpp")] +
                           [os.path.join(csrc, f) for f in ("mp3_frontend.cpp", "mpa12_frontend.cpp", "flac_frontend.cpp", "vorbis_frontend.cpp", "aac_frontend.cpp", "packetizer.cpp", "tables.cpp")])
     paths = []
