@@ -692,6 +692,13 @@ symgpu_status symgpu_vorbis_fe_config(const symgpu_vorbis_fe* fe, symgpu_vorbis_
  * (not an audio packet, bad mode number); a packet that merely ends early is decoded as far as it goes, as in the reference. */
 symgpu_status symgpu_vorbis_fe_decode(symgpu_vorbis_fe* fe, const uint8_t* packet, size_t n, uint32_t slot, uint32_t floor_base,
                                       symgpu_vorbis_unit* unit, uint16_t* floor_y, float* residue);
+/* The same as independent jobs on n_threads host threads (every thread builds its own front-end from the headers): outputs stay at their
+ * packet's index (units[i], floor_y[130 i], residue[2 slot i]; a refused packet's unit is zeroed), accepted[0 .. *n_good) lists the
+ * decoded packets in order and the previous block flags are chained over those -- always identical to the serial form. */
+symgpu_status symgpu_vorbis_fe_decode_packets_jobs(const uint8_t* ident, size_t n_ident, const uint8_t* setup, size_t n_setup, const uint8_t* data, size_t n,
+                                                   const symgpu_piece* packets, size_t n_packets, uint32_t slot, uint32_t floor_base,
+                                                   symgpu_vorbis_unit* units, uint16_t* floor_y, float* residue, uint32_t* accepted, size_t* n_good,
+                                                   uint32_t n_threads);
 /* A stream's audio packets in one call (packet i = data[packets[i].offset .. + len)): units[k], floor_y[130k..], residue[2*slot*k..],
  * packet_of[k] = i for every packet the front-end accepts, in order; refused packets are left out. */
 symgpu_status symgpu_vorbis_fe_decode_packets(symgpu_vorbis_fe* fe, const uint8_t* data, size_t n, const symgpu_piece* packets, size_t n_packets,

@@ -267,6 +267,8 @@ def lib():
     L.symgpu_vorbis_fe_decode_packets.argtypes = [vp, vp, sz, vp, sz, u32, u32, vp, vp, vp, vp, ctypes.POINTER(sz)]
     L.symgpu_aac_fe_decode_packets_jobs.restype = ctypes.c_int
     L.symgpu_aac_fe_decode_packets_jobs.argtypes = [u32, u32, vp, sz, vp, sz, u32, vp, vp, sz, vp, ctypes.POINTER(sz), u32]
+    L.symgpu_vorbis_fe_decode_packets_jobs.restype = ctypes.c_int
+    L.symgpu_vorbis_fe_decode_packets_jobs.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, u32, u32, vp, vp, vp, vp, ctypes.POINTER(sz), u32]
     L.symgpu_aac_fe_tables.restype = None
     L.symgpu_aac_fe_tables.argtypes = [vp, vp, vp]
     _LIB = L

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/symgpu.h"
@@ -501,4 +502,49 @@ extern "C" symgpu_status symgpu_vorbis_fe_decode_packets(symgpu_vorbis_fe* fe, c
     }
     *n_good = good;
     return SYMGPU_OK;
+}
+
+// A stream's audio packets as independent jobs: a packet depends on its predecessors only through the previous block
+// flag, which is output, not input, of the entropy stage -- the partition-class vector's history never reaches an entry a packet reads
+// before writing it, and what a class word writes does not depend on the vector's length beyond the entries it has (the digits kept
+// when it is cut are the same most significant ones).  Every thread owns a front-end built from the headers; outputs stay at their
+// packet's index (units[i], floor_y[130 i], residue[2 slot i]); accepted[0 .. n_good) lists the packets the reference decodes, in
+// order, and the previous block flags are chained over exactly those.
+extern "C" symgpu_status symgpu_vorbis_fe_decode_packets_jobs(const uint8_t* ident, size_t n_ident, const uint8_t* setup, size_t n_setup, const uint8_t* data,
+                                                              size_t n, const symgpu_piece* packets, size_t n_packets, uint32_t slot, uint32_t floor_base,
+                                                              symgpu_vorbis_unit* units, uint16_t* floor_y, float* residue, uint32_t* accepted, size_t* n_good,
+                                                              uint32_t n_threads) {
+    if ((!data && n) || (n_packets && (!packets || !units || !floor_y || !residue || !accepted)) || !n_good) return SYMGPU_ERR_ARG;
+    if (n_threads == 0) n_threads = 1;
+    std::vector<symgpu_vorbis_fe*> fes(n_threads, nullptr);
+    symgpu_status st = SYMGPU_OK;
+    for (uint32_t t = 0; t < n_threads && st == SYMGPU_OK; ++t) st = symgpu_vorbis_fe_create(ident, n_ident, setup, n_setup, &fes[t]);
+    if (st == SYMGPU_OK && slot < ((1u << fes[0]->ident.bs1_exp) >> 1)) st = SYMGPU_ERR_ARG;
+    std::vector<uint8_t> ok(n_packets, 0);
+    if (st == SYMGPU_OK) {
+        std::vector<std::thread> pool;
+        for (uint32_t t = 0; t < n_threads; ++t)
+            pool.emplace_back([&, t] {
+                for (size_t i = t; i < n_packets; i += n_threads) {
+                    if (packets[i].offset > n || packets[i].len > n - packets[i].offset) continue;
+                    ok[i] = symgpu_vorbis_fe_decode(fes[t], data + packets[i].offset, packets[i].len, slot, floor_base, units + i, floor_y + 130 * i,
+                                                    residue + 2 * size_t(slot) * i) == SYMGPU_OK;
+                }
+            });
+        for (auto& th : pool) th.join();
+        size_t good = 0;
+        int prev = -1;
+        for (size_t i = 0; i < n_packets; ++i) {
+            if (!ok[i]) {
+                std::memset(units + i, 0, sizeof *units);
+                continue;
+            }
+            units[i].prev_block_flag = uint8_t(prev < 0 ? units[i].block_flag : prev);
+            prev = units[i].block_flag;
+            accepted[good++] = uint32_t(i);
+        }
+        *n_good = good;
+    }
+    for (symgpu_vorbis_fe* fe : fes) symgpu_vorbis_fe_destroy(fe);
+    return st;
 }

@@ -362,3 +362,22 @@ def aac_decode_packets_jobs(sample_rate, channels, data, packets, tns_base=0, th
     if rc != 0:
         raise SymgpuError(rc, "symgpu_aac_fe_decode_packets_jobs")
     return units, tns[:n_tns.value], coeffs
+
+
+def vorbis_decode_packets_jobs(ident_packet, setup_packet, data, packets, slot, floor_base=0, threads=4):
+    """One Vorbis stream's audio packets as independent jobs on host threads: (units [n], floor_y [n,2,65], residue [n,2,slot], accepted)
+    with outputs at their packet's index; units[accepted] etc. equal VorbisFrontend.decode_packets."""
+    a, i_, s_ = _u8(data), _u8(bytes(ident_packet)), _u8(bytes(setup_packet))
+    packets = np.ascontiguousarray(packets, dtype=nat.PIECE_DTYPE)
+    n = len(packets)
+    units = np.zeros(n, dtype=nat.VORBIS_UNIT_DTYPE)
+    floor_y = np.zeros((n, 2, 65), dtype=np.uint16)
+    residue = np.zeros((n, 2, slot), dtype=np.float32)
+    accepted = np.zeros(n, dtype=np.uint32)
+    good = ctypes.c_size_t(0)
+    rc = nat.lib().symgpu_vorbis_fe_decode_packets_jobs(_vp(i_.ctypes.data), i_.size, _vp(s_.ctypes.data), s_.size, _vp(a.ctypes.data) if a.size else None, a.size,
+                                                        _vp(packets.ctypes.data), n, int(slot), int(floor_base), _vp(units.ctypes.data), _vp(floor_y.ctypes.data),
+                                                        _vp(residue.ctypes.data), _vp(accepted.ctypes.data), ctypes.byref(good), int(threads))
+    if rc != 0:
+        raise SymgpuError(rc, "symgpu_vorbis_fe_decode_packets_jobs")
+    return units, floor_y, residue, accepted[:good.value]

@@ -212,6 +212,18 @@ static void run_all(const std::vector<uint8_t>& d) {
             }
             symgpu_vorbis_fe_destroy(fe);
         }
+        if (parts.size() >= 3 && parts.size() < 200) {  // the same packets as independent jobs
+            std::vector<symgpu_piece> tab;
+            for (size_t k = 2; k < parts.size(); ++k) tab.push_back(symgpu_piece{parts[k].offset, parts[k].len, 0});
+            const uint32_t slot = 4096;
+            std::vector<symgpu_vorbis_unit> u(tab.size());
+            std::vector<uint16_t> fy(130 * tab.size());
+            std::vector<float> res(2 * size_t(slot) * tab.size());
+            std::vector<uint32_t> acc(tab.size());
+            size_t good = 0;
+            symgpu_vorbis_fe_decode_packets_jobs(p + parts[0].offset, parts[0].len, p + parts[1].offset, parts[1].len, p, n, tab.data(), tab.size(), slot, 0,
+                                                 u.data(), fy.data(), res.data(), acc.data(), &good, 2);
+        }
     }
 }
 

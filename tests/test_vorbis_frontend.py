@@ -356,3 +356,41 @@ def test_over_and_under_specified_codebooks_are_refused():
         del w
         return
     raise AssertionError("no plain-coded first book among the seeds")
+
+
+def test_packets_as_independent_jobs_equal_the_serial_front_end():
+    """symgpu_vorbis_fe_decode_packets_jobs: every thread its own front-end, packets in any order, previous block flags chained over the
+    accepted packets afterwards -- the serial front-end's bits on clean, truncated and damaged packets alike."""
+    refused = 0
+    for seed in range(18):
+        rng = np.random.default_rng(9500 + seed)
+        s = vb.Stream(rng, channels=1 if seed % 6 == 5 else 2, residue_type=seed % 3)
+        pk = []
+        for k in range(16):
+            p, _ = s.packet()
+            if k % 4 == 1 and len(p) > 2:
+                p = p[:int(rng.integers(1, len(p)))]
+            elif k % 4 == 2:
+                b = bytearray(p)
+                b[int(rng.integers(len(b)))] ^= 1 << int(rng.integers(8))
+                p = bytes(b)
+            elif k == 7:
+                p = b"\x01" + p                               # not an audio packet: refused
+            pk.append(p)
+        blob = b"".join(pk)
+        table = np.zeros(len(pk), dtype=sb._native.PIECE_DTYPE)
+        table["len"] = [len(p) for p in pk]
+        table["offset"] = np.concatenate([[0], np.cumsum(table["len"][:-1], dtype=np.uint64)])
+        fe = frontend.VorbisFrontend(s.ident, s.setup)
+        units, fy, res, keep = fe.decode_packets(blob, table)
+        slot = fe.slot
+        fe.close()
+        refused += len(pk) - len(keep)
+        for threads in (1, 3, 8):
+            ju, jf, jr, acc = frontend.vorbis_decode_packets_jobs(s.ident, s.setup, blob, table, slot, threads=threads)
+            assert acc.tolist() == keep.tolist(), (seed, threads)
+            assert ju[acc].tobytes() == units.tobytes() and jf[acc].tobytes() == fy.tobytes(), (seed, threads)
+            assert np.array_equal(bits(jr[acc]), bits(res)), (seed, threads)
+            gone = np.setdiff1d(np.arange(len(pk)), acc)
+            assert not ju[gone].tobytes().strip(b"\0")
+    assert refused >= 18
