@@ -135,18 +135,23 @@ def adts_aac_index(data):
     return packets, rate, channels
 
 
-def adts_aac_plan(data, index=None, out=None):
+def adts_aac_plan(data, index=None, out=None, threads=1):
     """CPU half for an ADTS file: frames (symgpu_adts_index: header rules of adts.rs:130-309) -> raw_data_block payloads -> AAC-LC
     entropy front-end (symgpu_aac_fe_*) -> the synthesis stage's batch.  The reader gives every frame 1024 samples and trims
     nothing.  Returns dict(units [n,2], tns, coeffs [n,2,1024], runs, spans, channels, sample_rate, total_frames).  Packets the
     front-end refuses are dropped, as a caller of the reference drops a DecodeError.  index: the result of adts_aac_index (else
-    computed here); out: (units, coeffs) staging slices with room for every packet."""
+    computed here); out: (units, coeffs) staging slices with room for every packet; threads > 1: a stream of 32 blocks or more is
+    decoded as independent jobs when it allows that."""
     packets, rate, channels = adts_aac_index(data) if index is None else index
-    fe = frontend.AacFrontend(rate, channels)
     table = np.zeros(len(packets), dtype=nat.PIECE_DTYPE)
     table["offset"], table["len"] = packets["offset"], packets["size"]
-    units, tns, coeffs, _ = fe.decode_packets(data, table, out=out)
-    fe.close()
+    jobs = frontend.aac_decode_packets_jobs(rate, channels, data, table, threads=threads) if (threads > 1 and out is None and len(packets) >= 32) else None
+    if jobs is not None:            # one long stream: its blocks as independent jobs on host threads (identical output, DESIGN 10.9)
+        units, tns, coeffs = jobs
+    else:                           # (or the stream needs the serial path: a refused block, a changed layout, ...)
+        fe = frontend.AacFrontend(rate, channels)
+        units, tns, coeffs, _ = fe.decode_packets(data, table, out=out)
+        fe.close()
     n = len(units)
     runs = np.zeros(1, dtype=nat.AAC_RUN_DTYPE)
     runs[0]["n_frames"], runs[0]["channels"] = n, channels
@@ -176,9 +181,9 @@ class Arena:
         return b[:need].view(dtype).reshape(shape)
 
 
-def decode_adts_aac(engine, data, fmt=nat.FMT_S16, stream=0):
+def decode_adts_aac(engine, data, fmt=nat.FMT_S16, stream=0, threads=1):
     """(samples [frames, channels] of `fmt`, sample_rate) of an ADTS AAC-LC file; stream slot `stream` of `engine` is reset first."""
-    plan = adts_aac_plan(data)
+    plan = adts_aac_plan(data, threads=threads)
     if len(plan["units"]) == 0:
         return np.zeros((0, plan["channels"]), dtype=nat.FMT_NUMPY[fmt]), plan["sample_rate"]
     plan["runs"]["stream"] = stream

@@ -105,3 +105,16 @@ def test_cpp_aac_decoder_on_adts_files(tmp_path, oracle):
         assert res.returncode == 0, res.stdout + res.stderr
         got = np.frombuffer(outp.read_bytes(), dtype=np.float32).reshape(-1, channels, 1024).transpose(0, 2, 1).reshape(-1, channels)
         assert got.shape == want.shape and (got.view(np.uint32) == np.ascontiguousarray(want).view(np.uint32)).all()
+
+
+def test_one_long_stream_as_jobs_gives_the_same_plan():
+    data, _ = _file(520, 44100, 2, n=40)
+    a, b = decode.adts_aac_plan(data), decode.adts_aac_plan(data, threads=4)
+    for key in ("units", "tns", "coeffs", "runs", "spans"):
+        assert a[key].tobytes() == b[key].tobytes(), key
+    # a stream with a damaged block falls back to the serial path, with the same result as without threads
+    hurt = bytearray(data)
+    hurt[len(hurt) // 2] ^= 0x3C
+    a, b = decode.adts_aac_plan(bytes(hurt)), decode.adts_aac_plan(bytes(hurt), threads=4)
+    for key in ("units", "tns", "coeffs", "runs", "spans"):
+        assert a[key].tobytes() == b[key].tobytes(), key
