@@ -78,10 +78,10 @@ def ogg_vorbis_index(data, serial=None):
     dur, discard = dur.astype(np.int64), discard.astype(np.int64)
     trim_end = packetizer.ogg_page_end_trims(mine["page_sequence"][audio], mine["page_absgp"][audio], dur, discard).astype(np.int64)
     fe = frontend.VorbisFrontend(ident_b, setup_b)
-    return dict(blob=blob, table=table[audio], ident=ident, fe=fe, discard=discard, trim_end=trim_end)
+    return dict(blob=blob, table=table[audio], ident=ident, fe=fe, discard=discard, trim_end=trim_end, headers=(ident_b, setup_b))
 
 
-def ogg_vorbis_plan(data, serial=None, index=None, out=None, slot=None, floor_base=0):
+def ogg_vorbis_plan(data, serial=None, index=None, out=None, slot=None, floor_base=0, threads=1):
     """CPU half for a Vorbis-in-Ogg file: ogg_vorbis_index, then the entropy front-end (symgpu_vorbis_fe_*) over the audio packets
     -> the synthesis stage's batch and the output spans with the reader's trims.  Returns dict(stream, floors, units, floor_y, residue,
     runs, slot, spans, channels, sample_rate, total_frames).  Packets the front-end refuses are dropped, as a caller of the reference
@@ -90,7 +90,11 @@ def ogg_vorbis_plan(data, serial=None, index=None, out=None, slot=None, floor_ba
     ix = ogg_vorbis_index(data, serial) if index is None else index
     fe, ident, discard, trim_end = ix["fe"], ix["ident"], ix["discard"], ix["trim_end"]
     slot = fe.slot if slot is None else slot
-    units, fy, res, keep = fe.decode_packets(ix["blob"], ix["table"], slot=slot, floor_base=floor_base, out=out)
+    if threads > 1 and out is None and len(ix["table"]) >= 32:   # one long stream: its packets as independent jobs (identical output)
+        ju, jf, jr, keep = frontend.vorbis_decode_packets_jobs(ix["headers"][0], ix["headers"][1], ix["blob"], ix["table"], slot, floor_base, threads)
+        units, fy, res = ju[keep], jf[keep], jr[keep]
+    else:
+        units, fy, res, keep = fe.decode_packets(ix["blob"], ix["table"], slot=slot, floor_base=floor_base, out=out)
     n = len(units)
     stream, floors = np.array([fe.stream], dtype=nat.VORBIS_STREAM_DTYPE), fe.floors.copy()
     fe.close()
@@ -112,10 +116,10 @@ def ogg_vorbis_plan(data, serial=None, index=None, out=None, slot=None, floor_ba
                 channels=int(ident["channels"]), sample_rate=int(ident["sample_rate"]), total_frames=total)
 
 
-def decode_ogg_vorbis(engine, data, fmt=nat.FMT_S16, serial=None):
+def decode_ogg_vorbis(engine, data, fmt=nat.FMT_S16, serial=None, threads=1):
     """(samples [frames, channels] of `fmt`, sample_rate) of one Vorbis logical stream (mono / stereo, floor 1: what the synthesis
     kernel takes).  Registers the stream as slot 0 of `engine` with its floors from index 0."""
-    plan = ogg_vorbis_plan(data, serial)
+    plan = ogg_vorbis_plan(data, serial, threads=threads)
     if len(plan["units"]) == 0:
         return np.zeros((0, plan["channels"]), dtype=nat.FMT_NUMPY[fmt]), plan["sample_rate"]
     engine.vorbis_streams_set(plan["stream"])

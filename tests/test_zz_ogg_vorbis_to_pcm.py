@@ -139,3 +139,12 @@ def test_cpp_vorbis_decoder_on_ogg_files(tmp_path, oracle):
         assert at == flat.size
         got = np.concatenate(rows)
         assert got.shape == want.shape and (np.ascontiguousarray(got).view(np.uint32) == np.ascontiguousarray(want).view(np.uint32)).all()
+
+
+def test_one_long_stream_as_jobs_gives_the_same_plan():
+    data, _, _, _ = _file(330, n_packets=48, pad=11)
+    a, b = decode.ogg_vorbis_plan(data), decode.ogg_vorbis_plan(data, threads=4)
+    assert len(a["units"]) == 48
+    for key in ("units", "floor_y", "residue", "runs", "spans", "floors", "stream"):
+        assert a[key].tobytes() == b[key].tobytes(), key
+    assert a["total_frames"] == b["total_frames"]
