@@ -16,6 +16,7 @@ struct symgpu_ctx {
     cudaStream_t stream = nullptr;
     char cuda_err[256] = {0};
     uint64_t launches = 0;
+    bool mp3_v2 = true; // Layer III kernel generation (mp3_kernel_v2.cu unless SYMGPU_MP3_KERNEL=v1)
     // tables
     symgpu::Mp3Tables* d_mp3_tab = nullptr;
     // MP3 streams

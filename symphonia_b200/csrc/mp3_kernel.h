@@ -99,4 +99,33 @@ int mp3_cta_warps();           // warps per CTA = granule jobs per group
 // Persistent grid size of the kernel on the current device (SM count x resident CTAs), <= 0 on error.
 int mp3_grid_size(cudaError_t* err);
 
+// ---- second-generation Layer III kernel (mp3_kernel_v2.cu): warp-autonomous, channel-pair packed FP32 ----
+// A warp owns a SHARE of the batch's granules (a list of Mp3Tile segments, walked in order); share s runs on
+// warp s / grid of CTA s % grid.  Tile flags: kTileLoadState (the segment starts its run: state from HBM),
+// kTileStoreState (it ends its run: state to HBM), kTileCarryIn / kTileCarryOut (the segment continues / is
+// continued by the neighbouring segment of the same share: the state simply stays in the warp); a segment with
+// neither input flag recomputes a 2-granule halo.
+#ifndef SYMGPU_MP3_V2_NW
+#define SYMGPU_MP3_V2_NW 12
+#endif
+constexpr int kMp3V2Warps = SYMGPU_MP3_V2_NW;
+struct Mp3V2Args {
+    const symgpu_mp3_gc* units;
+    const float* spectra;
+    float* pcm;
+    const uint32_t* first; // [n_shares + 1]: share s walks tiles first[s] .. first[s + 1] - 1 in order
+    const Mp3Tile* tiles;
+    int n_tiles;
+    int n_shares;
+    Mp3StreamState* states; // [n_streams][2] double-buffered, see gen
+    uint32_t* gen;          // [n_streams] state generation; buffer (gen & 1) is current
+    unsigned* done;         // retired-CTA counter (self-resetting)
+    const Mp3Tables* tab;
+    float one, mone;        // 1.0f, -1.0f: multiplicands of the packed sums (opaque to ptxas, see mp3_kernel_v2.cu)
+};
+cudaError_t mp3v2_upload_const(const Mp3Tables& t, cudaStream_t stream);
+cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream);
+int mp3v2_cta_warps();
+int mp3v2_sm_count(cudaError_t* err); // SMs of the current device (= CTAs of a full launch), <= 0 on error
+
 } // namespace symgpu

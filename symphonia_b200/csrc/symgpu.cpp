@@ -154,13 +154,131 @@ symgpu_status build_plan_for(int grid, uint32_t T, uint32_t T_halo, bool group, 
     return SYMGPU_OK;
 }
 
+
+// ---- launch plan of the second-generation kernel (mp3_kernel_v2.cu) ------------------------------------
+// The batch's granules, in run order, are cut into at most `max_shares` SHARES, one per warp of the launch.
+// A cut prefers a run boundary (no halo) when one is within a quarter of a share of the ideal position, and
+// never leaves fewer than two granules of the run before it (a halo recomputes two earlier granules, which
+// must be in the batch).  Same container as the first-generation plan: a header of n_shares + 1 tile
+// offsets (padded to 16-byte entries) followed by the tiles; a tile is one run segment of one share.
+symgpu_status build_plan_v2_for(int max_shares, uint32_t n_streams, const symgpu_mp3_run* runs, uint32_t n_runs,
+                                uint32_t n_frames, Mp3Plan& plan, bool whole_batch) {
+    constexpr uint64_t kMinShare = 4;     // granules: below this a share is not worth its halo
+    constexpr uint32_t kMaxTile = 32768;  // Mp3Tile::n_granules is 16 bits
+    uint64_t covered = 0, total_gran = 0;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_mp3_run& run = runs[r];
+        const int gpf = run.granules_per_frame ? run.granules_per_frame : 2;
+        const int n_ch = run.channels ? run.channels : 2;
+        if (gpf < 1 || gpf > 2 || n_ch < 1 || n_ch > 2 || run.reserved != 0) return SYMGPU_ERR_ARG;
+        if (run.n_frames == 0) continue;
+        if ((uint64_t)run.first_frame + run.n_frames > n_frames) return SYMGPU_ERR_ARG;
+        if (run.stream >= n_streams) return SYMGPU_ERR_LIMIT;
+        covered += run.n_frames;
+        total_gran += (uint64_t)run.n_frames * (uint32_t)gpf;
+    }
+    if (whole_batch && covered != n_frames) return SYMGPU_ERR_ARG; // runs must tile the batch exactly
+    if (max_shares < 1) return SYMGPU_ERR_ARG;
+    const uint64_t n_shares = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)max_shares, total_gran / kMinShare));
+    plan.multi = false;
+    plan.n_ctas = (int)n_shares; // shares, for this plan
+    plan.hdr = (int)((n_shares + 1 + 3) / 4);
+    plan.buf.assign((size_t)plan.hdr, Mp3Tile{});
+    std::vector<uint32_t> first((size_t)n_shares + 1, 0);
+    const uint64_t tol = total_gran / n_shares / 4; // snap distance
+
+    uint64_t pos = 0;    // granules of earlier runs
+    uint64_t share = 0;  // share being filled
+    uint32_t n_tiles = 0;
+    auto ideal_end = [&](uint64_t c) { return total_gran * (c + 1) / n_shares; };
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_mp3_run& run = runs[r];
+        if (run.n_frames == 0) continue;
+        const uint32_t gpf = run.granules_per_frame ? run.granules_per_frame : 2;
+        const uint32_t n_ch = run.channels ? run.channels : 2;
+        const uint64_t n_gran = (uint64_t)run.n_frames * gpf;
+        uint64_t q0 = 0;
+        while (q0 < n_gran) {
+            // shares whose ideal end lies at or before this position are closed (possibly empty)
+            while (share + 1 < n_shares) {
+                const uint64_t cut = ideal_end(share);
+                bool close = cut <= pos + q0;
+                // a cut just behind this run's start snaps back to the start
+                if (!close && q0 == 0 && cut < pos + n_gran && (cut - pos <= tol || cut - pos < 2)) close = true;
+                if (!close) break;
+                first[(size_t)++share] = n_tiles;
+            }
+            uint64_t q1 = n_gran;
+            if (share + 1 < n_shares) {
+                const uint64_t cut = ideal_end(share);
+                if (cut < pos + n_gran) {
+                    q1 = cut - pos;            // > q0, and >= 2 or it would have snapped to the run start above
+                    if (q1 <= q0) q1 = q0 + 1;
+                    if (q1 < 2) q1 = 2;
+                    if (n_gran - q1 <= tol || q1 >= n_gran) q1 = n_gran; // a cut just before the run's end snaps to the end
+                }
+            }
+            bool first_piece = true;
+            for (uint64_t a0 = q0; a0 < q1;) { // pieces of at most kMaxTile granules, the state stays in the warp between them
+                const uint64_t a1 = std::min<uint64_t>(q1, a0 + kMaxTile);
+                Mp3Tile t{};
+                t.first_frame = run.first_frame + (uint32_t)(a0 / gpf);
+                t.first_gr = (uint16_t)(a0 % gpf);
+                t.stream = run.stream;
+                t.n_granules = (uint16_t)(a1 - a0);
+                t.gpf = (uint8_t)gpf;
+                t.n_ch = (uint8_t)n_ch;
+                uint8_t fl = 0;
+                if (!first_piece) fl |= kTileCarryIn;
+                else if (a0 == 0) fl |= kTileLoadState;
+                if (a1 < q1) fl |= kTileCarryOut;
+                else if (a1 == n_gran) fl |= kTileStoreState;
+                t.flags = fl;
+                plan.buf.push_back(t);
+                ++n_tiles;
+                first_piece = false;
+                a0 = a1;
+            }
+            q0 = q1;
+            if (q0 < n_gran && share + 1 < n_shares) first[(size_t)++share] = n_tiles; // the rest of the run goes to the next share
+        }
+        pos += n_gran;
+    }
+    while (share < n_shares) first[(size_t)++share] = n_tiles;
+    plan.n_tiles = (int)n_tiles;
+    std::memcpy(plan.buf.data(), first.data(), first.size() * sizeof(uint32_t));
+    return SYMGPU_OK;
+}
+
 symgpu_status build_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, Mp3Plan& plan,
                          bool whole_batch = true) {
     cudaError_t ce = cudaSuccess;
+    if (ctx->mp3_v2) {
+        const int n_sm = mp3v2_sm_count(&ce);
+        if (ce != cudaSuccess || n_sm <= 0) return cuda_fail(ctx, ce, "mp3v2_sm_count");
+        return build_plan_v2_for(n_sm * mp3v2_cta_warps(), ctx->n_mp3_streams, runs, n_runs, n_frames, plan, whole_batch);
+    }
     const int grid = mp3_grid_size(&ce);
     if (ce != cudaSuccess || grid <= 0) return cuda_fail(ctx, ce, "mp3_grid_size");
     return build_plan_for(grid, (uint32_t)mp3_tile_granules(), (uint32_t)mp3_halo_tile_granules(), true, ctx->n_mp3_streams, runs,
                           n_runs, n_frames, plan, whole_batch);
+}
+
+// Launches the Layer III kernel the context is configured for over a plan whose entries sit at `d_plan`.
+cudaError_t launch_plan(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_tiles, int n_ctas, bool multi, const symgpu_mp3_gc* units,
+                        const float* spectra, float* pcm, cudaStream_t stream) {
+    if (ctx->mp3_v2) {
+        cudaError_t ce = cudaSuccess;
+        const int n_sm = mp3v2_sm_count(&ce);
+        if (ce != cudaSuccess) return ce;
+        const int n_shares = n_ctas; // the v2 plan counts shares
+        const Mp3V2Args a{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_shares,
+                          ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab, 1.0f, -1.0f};
+        return mp3v2_launch(a, std::min(n_sm, n_shares), stream);
+    }
+    const Mp3Args a{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas, multi ? 1 : 0,
+                    ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
+    return mp3_launch(a, stream);
 }
 
 // Makes room for `entries` plan entries in the device / pinned host buffers.
@@ -177,13 +295,6 @@ symgpu_status reserve_plan(symgpu_ctx* ctx, size_t entries) {
     CU(ctx, cudaMallocHost(&ctx->h_tiles, cap * sizeof(Mp3Tile)));
     ctx->tiles_cap = cap;
     return SYMGPU_OK;
-}
-
-// Kernel arguments of a plan whose entries sit at `d_plan`.
-Mp3Args plan_args(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_tiles, int n_ctas, bool multi, const symgpu_mp3_gc* units,
-                  const float* spectra, float* pcm) {
-    return Mp3Args{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas, multi ? 1 : 0,
-                   ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
 }
 
 symgpu_status ensure_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames) {
@@ -229,6 +340,19 @@ size_t symgpu_debug_mp3_plan(int grid, uint32_t n_streams, const symgpu_mp3_run*
     return plan.buf.size();
 }
 
+// Same for the second-generation kernel: the plan for a launch of at most `max_shares` warps (n_sm * warps per CTA
+// on a device).  *n_shares / *n_tiles / *hdr describe the layout; 0 on an argument error.
+size_t symgpu_debug_mp3_plan_v2(int max_shares, uint32_t n_streams, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames,
+                                void* out, size_t cap, int* n_shares, int* n_tiles, int* hdr) {
+    Mp3Plan plan;
+    if (build_plan_v2_for(max_shares, n_streams, runs, n_runs, n_frames, plan, true) != SYMGPU_OK) return 0;
+    if (out) std::memcpy(out, plan.buf.data(), std::min(cap, plan.buf.size()) * sizeof(Mp3Tile));
+    if (n_shares) *n_shares = plan.n_ctas;
+    if (n_tiles) *n_tiles = plan.n_tiles;
+    if (hdr) *hdr = plan.hdr;
+    return plan.buf.size();
+}
+
 const char* symgpu_strerror(symgpu_status status) {
     switch (status) {
         case SYMGPU_OK: return "ok";
@@ -268,6 +392,7 @@ symgpu_status symgpu_tables_upload(symgpu_ctx* ctx, const void* blob, size_t byt
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaMemcpy(ctx->d_mp3_tab, blob, bytes, cudaMemcpyHostToDevice));
     CU(ctx, mp3_upload_const(*static_cast<const Mp3Tables*>(blob), ctx->stream));
+    CU(ctx, mp3v2_upload_const(*static_cast<const Mp3Tables*>(blob), ctx->stream));
     return SYMGPU_OK;
 }
 
@@ -293,6 +418,8 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
         const int v = std::atoi(env);
         if (v >= 1 && v <= symgpu_ctx::kMaxSlices) ctx->n_slices = v;
     }
+    // SYMGPU_MP3_KERNEL=v1 selects the first-generation Layer III kernel (mp3_kernel.cu), kept for comparison
+    if (const char* env = std::getenv("SYMGPU_MP3_KERNEL")) ctx->mp3_v2 = std::strcmp(env, "v1") != 0;
     DeviceGuard guard(device);
     auto fail = [&](cudaError_t err, const char* where) {
         std::fprintf(stderr, "symgpu: %s failed: %s\n", where, cudaGetErrorString(err));
@@ -304,6 +431,7 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
     const Mp3Tables& t = mp3_tables_host();
     if ((e = cudaMemcpy(ctx->d_mp3_tab, &t, sizeof t, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy(tables)");
     if ((e = mp3_upload_const(t, ctx->stream)) != cudaSuccess) return fail(e, "cudaMemcpyToSymbol(tables)");
+    if ((e = mp3v2_upload_const(t, ctx->stream)) != cudaSuccess) return fail(e, "cudaMemcpyToSymbol(tables v2)");
     *out = ctx;
     return SYMGPU_OK;
 }
@@ -385,8 +513,8 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
     symgpu_status s = ensure_plan(ctx, runs, n_runs, n_frames);
     if (s != SYMGPU_OK) return s;
     if (ctx->cached_tiles == 0) return SYMGPU_OK;
-    const Mp3Args a = plan_args(ctx, ctx->d_tiles, ctx->cached_hdr, ctx->cached_tiles, ctx->cached_ctas, ctx->cached_multi, units, spectra, pcm);
-    CU(ctx, mp3_launch(a, ctx->stream));
+    CU(ctx, launch_plan(ctx, ctx->d_tiles, ctx->cached_hdr, ctx->cached_tiles, ctx->cached_ctas, ctx->cached_multi, units, spectra, pcm,
+                        ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;
 }
@@ -525,8 +653,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         CU(ctx, copy_in(sl.f0, nf, ctx->copy_in));
         CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
-        const Mp3Args a = plan_args(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, sl.multi, d_units, d_spec, d_pcm);
-        CU(ctx, mp3_launch(a, ctx->stream));
+        CU(ctx, launch_plan(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, sl.multi, d_units, d_spec, d_pcm, ctx->stream));
         ctx->launches += 1;
         CU(ctx, pack(sl.f0, (uint32_t)nf));
         CU(ctx, cudaEventRecord(ctx->ev_k[i], ctx->stream));

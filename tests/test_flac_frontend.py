@@ -271,7 +271,6 @@ def test_one_call_flac_plan(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("SYMGPU_TEST_FLAC") != "1", reason="FLAC restoration kernel: one fix pending re-verification on a B200")
 def test_one_call_flac_on_the_device(oracle):
     import symphonia_b200 as sb
     from symphonia_b200 import decode

@@ -15,9 +15,7 @@ from symphonia_b200 import workloads
 from symphonia_b200._native import FLAC_LPC
 from tests import test_oracle_kat_flac as kat
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SYMGPU_TEST_FLAC") != "1",
-                                 reason="FLAC kernel re-run pending after the FIXED-order-1 fix (set SYMGPU_TEST_FLAC=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

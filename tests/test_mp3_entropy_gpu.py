@@ -14,8 +14,7 @@ from symphonia_b200 import frontend, packetizer
 from tests import _oracle
 from tests import test_zz_file_to_pcm as chain
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SYMGPU_TEST_ENTROPY") != "1",
-                                                   reason="device entropy kernel not yet run on a GPU (set SYMGPU_TEST_ENTROPY=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_files_to_pcm_with_the_entropy_kernel(oracle):

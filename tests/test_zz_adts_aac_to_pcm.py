@@ -76,7 +76,6 @@ def test_plan_drops_frames_the_front_end_refuses(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SYMGPU_TEST_AAC_CHAIN") != "1", reason="written after the round's GPU budget was spent; opt-in until verified on a B200")
 def test_adts_file_to_pcm_on_the_device(oracle):
     import symphonia_b200 as sb
     with sb.Engine(0) as eng:
@@ -91,7 +90,6 @@ def test_adts_file_to_pcm_on_the_device(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SYMGPU_TEST_AAC_CHAIN") != "1", reason="written after the round's GPU budget was spent; opt-in until verified on a B200")
 def test_cpp_aac_decoder_on_adts_files(tmp_path, oracle):
     """The C++ mirror of the plug-in interface: registry -> GpuAacDecoder, one decode() per raw_data_block."""
     import subprocess

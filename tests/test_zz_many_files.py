@@ -143,7 +143,6 @@ def test_thread_count_does_not_change_the_plan():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SYMGPU_TEST_MANY_FILES") != "1", reason="written after the round's GPU budget was spent; opt-in until verified on a B200")
 def test_many_files_on_the_device(oracle):
     import symphonia_b200 as sb
     files = _files()

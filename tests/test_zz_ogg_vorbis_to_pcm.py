@@ -101,7 +101,6 @@ def test_plan_drops_packets_the_front_end_refuses(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SYMGPU_TEST_VORBIS_CHAIN") != "1", reason="written after the round's GPU budget was spent; opt-in until verified on a B200")
 def test_ogg_vorbis_file_to_pcm_on_the_device(oracle):
     import symphonia_b200 as sb
     with sb.Engine(0) as eng:
@@ -115,7 +114,6 @@ def test_ogg_vorbis_file_to_pcm_on_the_device(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SYMGPU_TEST_VORBIS_CHAIN") != "1", reason="written after the round's GPU budget was spent; opt-in until verified on a B200")
 def test_cpp_vorbis_decoder_on_ogg_files(tmp_path, oracle):
     """The C++ mirror of the plug-in interface: pages -> packets -> mapping -> registry -> GpuVorbisDecoder, one decode() per packet
     with the reader's trims."""
