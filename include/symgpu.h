@@ -196,7 +196,9 @@ symgpu_status symgpu_aac_stream_reset(symgpu_ctx* ctx, uint32_t stream); /* Ics:
 /* Synthesises `n_frames` AAC-LC frames (Pulse::synth, <= 4 lines, stays with the parser):
  *   units  [n_frames][2], tns [n_tns], coeffs [n_frames][2][1024] -> pcm [n_frames][2][1024]
  * (plane(ch) of frame f at pcm[f][ch]).  Same host/dev split as the MP3 entry points; `runs` is
- * host memory in both. */
+ * host memory in both.  Runs must not overlap but may leave frames out (a stream that lost packets keeps an
+ * unused tail in its slice): such frames are not decoded; their PCM is zero in the host variant and left
+ * untouched in the device variant.  The same holds for the Vorbis entry points and their packets. */
 symgpu_status symgpu_aac_synth_host(symgpu_ctx* ctx, const symgpu_aac_unit* units, const symgpu_aac_tns* tns,
                                     uint32_t n_tns, const float* coeffs, const symgpu_aac_run* runs,
                                     uint32_t n_runs, uint32_t n_frames, float* pcm);

@@ -355,16 +355,31 @@ __device__ __forceinline__ size_t granule_slot(const Mp3Tile& t, int k) {
     return (size_t)((int)t.first_frame + t.first_gr + k) * 2;
 }
 
+template <int NW>
 struct Mp3V2Smem {
-    WarpSmem w[kMp3V2Warps];
+    WarpSmem w[NW];
+    int max_iters;
     bool is_last;
 };
 
+// Variant bits (experiments, SYMGPU_MP3_V2_VARIANT=<warps>:<mode>):
+//   1  LOCKSTEP: the CTA's warps meet at three named-barrier points per granule.  No data crosses them -- they only
+//      keep the warps in the same stretch of code, so that one instruction fetch serves all of them.
+//   2  WIN_SCALAR_ADD: the polyphase window accumulates with two scalar FADD per product pair instead of one FFMA2
+//      (FFMA2 issues once per 3 cycles, two FADD take 2 cycles of the same pipe but 2 issue slots).
+enum : int { kV2Lockstep = 1, kV2WinScalarAdd = 2 };
+
 } // namespace
 
-__global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
+template <int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Mp3V2Smem& sm = *reinterpret_cast<Mp3V2Smem*>(smem_raw);
+    using Smem = Mp3V2Smem<NW>;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    constexpr bool LOCK = (MODE & kV2Lockstep) != 0;
+    auto phase_sync = [&]() {
+        if (LOCK) asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    };
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpSmem& ws = sm.w[warp];
@@ -392,6 +407,18 @@ __global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2A
         tma_bulk_g2s(ws.spec, a.spectra + slot * 1152, 4608u, &ws.bar);
         tma_bulk_g2s(ws.units[ubuf], a.units + slot * 2, 128u, &ws.bar);
     };
+
+    int my_iters = 0;
+    if (LOCK) {
+        for (int i = t_begin; i < t_end; ++i) {
+            const Mp3Tile t = ld_tile(a.tiles + i);
+            my_iters += (int)t.n_granules - tile_first_k(t);
+        }
+        if (threadIdx.x == 0) sm.max_iters = 0;
+        __syncthreads();
+        if (lane == 0) atomicMax(&sm.max_iters, my_iters);
+        __syncthreads();
+    }
 
     if (t_begin < t_end) {
         int ti = t_begin, k;
@@ -431,6 +458,7 @@ __global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2A
                 }
             }
 
+            phase_sync();
             mbar_wait(&ws.bar, phase & 1u);
             const symgpu_mp3_gc& g0 = ws.units[ubuf][0];
             const symgpu_mp3_gc& g1 = ws.units[ubuf][1];
@@ -751,6 +779,7 @@ __global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2A
 #pragma unroll
             for (int t = 0; t < 18; ++t) sec[t] = nsec[t];
             __syncwarp();
+            phase_sync();
 
             if (k >= -1) {
                 // C: DCT-32 of the granule's 18 time slots, in place; lane = slot, both channels packed.  // PHASE: C glue
@@ -767,6 +796,7 @@ __global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2A
                 __syncwarp();
             }
 
+            phase_sync();
             if (k >= 0) {
                 // D: polyphase window (synthesis.rs:247-263, :309-327).  lane = PCM sample index i; a 16-deep  // PHASE: D window
                 // register window of (V_lo[i], V_hi[i]) for both channels walks the 18 slots:
@@ -808,8 +838,20 @@ __global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2A
                             f2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                acc = o.add(o.mul(wl[(u - 2 * j) & 15], dlo[j]), acc);
-                                acc = o.add(o.mul(wh[(u - 2 * j - 1) & 15], dhi[j]), acc);
+                                const f2 p0 = o.mul(wl[(u - 2 * j) & 15], dlo[j]);
+                                if (MODE & kV2WinScalarAdd) {
+                                    acc.x += p0.x;
+                                    acc.y += p0.y;
+                                } else {
+                                    acc = o.add(p0, acc);
+                                }
+                                const f2 p1 = o.mul(wh[(u - 2 * j - 1) & 15], dhi[j]);
+                                if (MODE & kV2WinScalarAdd) {
+                                    acc.x += p1.x;
+                                    acc.y += p1.y;
+                                } else {
+                                    acc = o.add(p1, acc);
+                                }
                             }
                             out[u * 32] = acc.x;
                             if (stereo) out[1152 + u * 32] = acc.y;
@@ -857,6 +899,14 @@ __global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2A
         }
     }
 
+    if (LOCK) {
+        for (int i = my_iters; i < sm.max_iters; ++i) {
+            phase_sync();
+            phase_sync();
+            phase_sync();
+        }
+    }
+
     // Launch epilogue: the last CTA to retire publishes the new state generation of every run.
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -865,23 +915,50 @@ __global__ void __launch_bounds__(kMp3V2Warps * 32, 1) mp3v2_synth_kernel(Mp3V2A
     }
     __syncthreads();
     if (sm.is_last) {
-        for (int i = threadIdx.x; i < a.n_tiles; i += kMp3V2Warps * 32)
+        for (int i = threadIdx.x; i < a.n_tiles; i += NW * 32)
             if (a.tiles[i].flags & kTileStoreState) a.gen[a.tiles[i].stream] += 1;
         if (threadIdx.x == 0) *a.done = 0;
     }
 }
 
-int mp3v2_cta_warps() { return kMp3V2Warps; }
+namespace {
+struct V2Variant {
+    int nw, mode;
+    void (*kernel)(Mp3V2Args);
+    size_t smem;
+};
+#define V2_VARIANT(NW, MODE) {NW, MODE, mp3v2_synth_kernel<NW, MODE>, sizeof(Mp3V2Smem<NW>)}
+const V2Variant kV2Variants[] = {V2_VARIANT(kMp3V2Warps, 0), V2_VARIANT(kMp3V2Warps, 1), V2_VARIANT(kMp3V2Warps, 2),
+                                 V2_VARIANT(kMp3V2Warps, 3), V2_VARIANT(8, 0), V2_VARIANT(8, 1), V2_VARIANT(8, 3)};
+int g_v2_variant = 0;
+} // namespace
+
+// Selects the kernel instantiation (process-wide; experiments): warps per CTA and variant bits.  False if not built.
+bool mp3v2_set_variant(int nw, int mode) {
+    for (size_t i = 0; i < sizeof kV2Variants / sizeof kV2Variants[0]; ++i)
+        if (kV2Variants[i].nw == nw && kV2Variants[i].mode == mode) {
+            g_v2_variant = (int)i;
+            return true;
+        }
+    return false;
+}
+
+int mp3v2_cta_warps() { return kV2Variants[g_v2_variant].nw; }
 
 int mp3v2_sm_count(cudaError_t* err) {
     static int sm_for_device[64] = {0};
+    static int configured_variant[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess && !sm_for_device[dev & 63]) {
+    if (e == cudaSuccess && (!sm_for_device[dev & 63] || configured_variant[dev & 63] != g_v2_variant)) {
         int n_sm = 0;
-        e = cudaFuncSetAttribute(mp3v2_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Mp3V2Smem));
+        const V2Variant& v = kV2Variants[g_v2_variant];
+        e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) sm_for_device[dev & 63] = n_sm;
+        if (e == cudaSuccess) {
+            sm_for_device[dev & 63] = n_sm;
+            configured_variant[dev & 63] = g_v2_variant;
+        }
     }
     if (err) *err = e;
     return e == cudaSuccess ? sm_for_device[dev & 63] : 0;
@@ -891,8 +968,9 @@ cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream) {
     cudaError_t e = cudaSuccess;
     const int n_sm = mp3v2_sm_count(&e);
     if (e != cudaSuccess) return e;
-    if (n_ctas <= 0 || n_ctas > n_sm || a.n_shares > n_ctas * kMp3V2Warps) return cudaErrorInvalidConfiguration;
-    mp3v2_synth_kernel<<<n_ctas, kMp3V2Warps * 32, sizeof(Mp3V2Smem), stream>>>(a);
+    const V2Variant& v = kV2Variants[g_v2_variant];
+    if (n_ctas <= 0 || n_ctas > n_sm || a.n_shares > n_ctas * v.nw) return cudaErrorInvalidConfiguration;
+    v.kernel<<<n_ctas, v.nw * 32, v.smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -353,6 +353,10 @@ size_t symgpu_debug_mp3_plan_v2(int max_shares, uint32_t n_streams, const symgpu
     return plan.buf.size();
 }
 
+// Experiments: selects the instantiation of the second-generation kernel (warps per CTA, variant bits) for contexts
+// created afterwards; 1 if that variant is built.
+int symgpu_debug_mp3_v2_variant(int nw, int mode) { return mp3v2_set_variant(nw, mode) ? 1 : 0; }
+
 const char* symgpu_strerror(symgpu_status status) {
     switch (status) {
         case SYMGPU_OK: return "ok";
@@ -420,6 +424,14 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
     }
     // SYMGPU_MP3_KERNEL=v1 selects the first-generation Layer III kernel (mp3_kernel.cu), kept for comparison
     if (const char* env = std::getenv("SYMGPU_MP3_KERNEL")) ctx->mp3_v2 = std::strcmp(env, "v1") != 0;
+    if (const char* env = std::getenv("SYMGPU_MP3_V2_VARIANT")) { // "<warps>:<mode>", experiments
+        int nw = 0, mode = 0;
+        if (std::sscanf(env, "%d:%d", &nw, &mode) != 2 || !mp3v2_set_variant(nw, mode)) {
+            std::fprintf(stderr, "symgpu: SYMGPU_MP3_V2_VARIANT=%s is not a built variant\n", env);
+            delete ctx;
+            return SYMGPU_ERR_ARG;
+        }
+    }
     DeviceGuard guard(device);
     auto fail = [&](cudaError_t err, const char* where) {
         std::fprintf(stderr, "symgpu: %s failed: %s\n", where, cudaGetErrorString(err));

@@ -131,7 +131,7 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
     }
     symgpu_status s = SYMGPU_OK;
     if (!reuse) {
-        if (covered != n_frames) return SYMGPU_ERR_ARG;
+        if (covered > n_frames) return SYMGPU_ERR_ARG; // runs may leave frames out (a stream that lost packets), never overlap
         ctx->chunk_key.clear();
         s = upload_chunks(ctx, chunks);
         if (s != SYMGPU_OK) return s;
@@ -199,9 +199,14 @@ symgpu_status symgpu_aac_synth_host(symgpu_ctx* ctx, const symgpu_aac_unit* unit
     CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (n_tns) CU(ctx, cudaMemcpyAsync(d_tns, tns, (size_t)n_tns * sizeof(symgpu_aac_tns), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(d_spec, coeffs, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // planes no run writes (channel 1 of a mono stream, frames no run names) are defined as zero
     bool mono = false;
-    for (uint32_t r = 0; r < n_runs; ++r) mono |= runs[r].channels == 1;
-    if (mono) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
+    uint64_t covered = 0;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        mono |= runs[r].channels == 1;
+        covered += runs[r].n_frames;
+    }
+    if (mono || covered != n_frames) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
     s = symgpu_aac_synth_dev(ctx, d_units, d_tns, n_tns, d_spec, runs, n_runs, n_frames, d_pcm);
     if (s != SYMGPU_OK) return s;
     CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -328,7 +333,7 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
         });
     }
     if (!reuse) {
-        if (covered != n_packets) return SYMGPU_ERR_ARG;
+        if (covered > n_packets) return SYMGPU_ERR_ARG; // runs may leave packets out, never overlap
         ctx->chunk_key.clear();
         symgpu_status s = upload_chunks(ctx, chunks);
         if (s != SYMGPU_OK) return s;

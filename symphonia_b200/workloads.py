@@ -142,7 +142,8 @@ def flac_batch(n_frames=64, block_size=4096, seed=SEED_BASE + 5, bps=16, channel
     t = np.arange(block_size)
     for f in range(n_frames):
         n = block_size if f % 7 else max(channels and 40, block_size // 3 + 1)  # some short blocks
-        amp = (1 << (bps - 2)) - 1
+        # 32-bit planes: mid + side = 2 * left must still fit the decoder's i32 arithmetic (decoder.rs:32-82 wraps), so one bit less
+        amp = (1 << (bps - (3 if bps == 32 else 2))) - 1
         # a smooth signal plus noise, per channel, in `bps` bits
         pcm = [np.round(amp * 0.6 * np.sin(2 * np.pi * (rng.uniform(20, 2000) / 44100.0) * t[:n] + rng.uniform(0, 6))
                         + rng.normal(0, amp * 0.02, n)).astype(np.int64) for _ in range(channels)]
