@@ -126,6 +126,7 @@ struct Mp3V2Args {
 cudaError_t mp3v2_upload_const(const Mp3Tables& t, cudaStream_t stream);
 cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream);
 int mp3v2_cta_warps();
+int mp3v2_ctas_per_sm();
 bool mp3v2_set_variant(int nw, int mode); // experiments: warps per CTA, variant bits (mp3_kernel_v2.cu)
 int mp3v2_sm_count(cudaError_t* err); // SMs of the current device (= CTAs of a full launch), <= 0 on error
 

@@ -367,18 +367,26 @@ struct Mp3V2Smem {
 //      keep the warps in the same stretch of code, so that one instruction fetch serves all of them.
 //   2  WIN_SCALAR_ADD: the polyphase window accumulates with two scalar FADD per product pair instead of one FFMA2
 //      (FFMA2 issues once per 3 cycles, two FADD take 2 cycles of the same pipe but 2 issue slots).
-enum : int { kV2Lockstep = 1, kV2WinScalarAdd = 2 };
+//   4 / 8  WIN_GROUP2 / WIN_GROUP3: the window accumulates 2 / 3 time slots side by side (independent dependency chains).
+//   16 / 32  (with LOCKSTEP) only the first / the first two of the three meeting points: the warps re-align once per granule
+//      and may drift by a phase in between.
+enum : int { kV2Lockstep = 1, kV2WinScalarAdd = 2, kV2WinGroup2 = 4, kV2WinGroup3 = 8, kV2SyncTopOnly = 16, kV2SyncTopHybrid = 32, kV2Compact = 64 };
+//   64  COMPACT: smaller instruction footprint (the channel loop of the load phase and the two halves of the window are
+//      rolled), a few register moves more: for warps that are NOT kept in lockstep and must share the instruction caches.
 
 } // namespace
 
 template <int NW, int MODE>
-__global__ void __launch_bounds__(NW * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
+__global__ void __launch_bounds__(NW * 32, (NW <= 6 ? 12 / NW : 1)) mp3v2_synth_kernel(Mp3V2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = Mp3V2Smem<NW>;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     constexpr bool LOCK = (MODE & kV2Lockstep) != 0;
-    auto phase_sync = [&]() {
-        if (LOCK) asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    auto phase_sync = [&](int point = 0) {
+        if (!LOCK) return;
+        if ((MODE & kV2SyncTopOnly) && point != 0) return;
+        if ((MODE & kV2SyncTopHybrid) && point == 2) return;
+        asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
     };
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -515,59 +523,121 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
             const int rz_joint = max(rz0, rz1);
             const int rze[2] = {(ms || is) ? rz_joint : rz0, (ms || is) ? rz_joint : rz1};
             int rzr[2] = {rze[0], rze[1]}; // rzero after the reorder step
+            if constexpr ((MODE & kV2Compact) != 0) {
+                // one copy of the load code: channel 1 first into .x, moved to .y when channel 0 follows
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int ch = 1 - pass;
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                if (ch >= n_ch) continue;
-                const int kind = ch ? kind1 : kind0;
-                const float* Sc = S + ch * 576;
-                if (kind == kKindLong) {
-                    const uint16_t* iv2 = reinterpret_cast<const uint16_t*>(tab->iv_of_line[sr][kind] + 18 * lane);
+                    for (int i = 0; i < 18; ++i) {
+                        x[i].y = x[i].x;
+                        x[i].x = 0.0f;
+                    }
+                    if (ch >= n_ch) continue;
+                    const int kind = ch ? kind1 : kind0;
+                    const float* Sc = S + ch * 576;
+                    const float* scl = ws.scale[ch];
+                    const bool track = is && ch == 1;
+                    if (kind == kKindLong) {
+                        const uint16_t* iv2 = reinterpret_cast<const uint16_t*>(tab->iv_of_line[sr][kind] + 18 * lane);
 #pragma unroll
-                    for (int i = 0; i < 18; i += 2) {
-                        const float2 v = *reinterpret_cast<const float2*>(Sc + 18 * lane + i);
-                        const unsigned ivp = __ldg(iv2 + (i >> 1));
-                        // lines at or beyond rzero are +0.0 by contract (requantize.rs:234): 0 * scale = 0
-                        const float xa = v.x * ws.scale[ch][ivp & 0xff];
-                        const float xb = v.y * ws.scale[ch][ivp >> 8];
-                        if (ch == 0) {
+                        for (int i = 0; i < 18; i += 2) {
+                            const float2 v = *reinterpret_cast<const float2*>(Sc + 18 * lane + i);
+                            const unsigned ivp = __ldg(iv2 + (i >> 1));
+                            const float xa = v.x * scl[ivp & 0xff];
+                            const float xb = v.y * scl[ivp >> 8];
                             x[i].x = xa;
                             x[i + 1].x = xb;
-                        } else {
-                            x[i].y = xa;
-                            x[i + 1].y = xb;
-                            ivq[i >> 2] |= ivp << (8 * (i & 3)); // i is even: the pair lands in one word
-                            if (is) {
+                            if (track) {
+                                ivq[i >> 2] |= ivp << (8 * (i & 3));
                                 if (xa != 0.0f) ws.nz[ivp & 0xff] = 1;
                                 if (xb != 0.0f) ws.nz[ivp >> 8] = 1;
                             }
                         }
-                    }
-                } else {
-                    const int m = (kind == kKindMixed) ? 1 : 0;
-                    const int sw = m ? c2.mixed_switch[sr] : 0;
-                    const uint16_t* e = tab->edges[sr][kind] + sw;
-                    const int n_quads = (c2.n_edges[sr][kind] - sw - 1) / 3;
-                    const int rz = rze[ch];
-                    const bool below = (lane < n_quads) && ((int)e[3 * lane] < rz);
-                    const int n_done = __popc(__ballot_sync(0xffffffffu, below)); // reordered quads form a prefix
-                    const int start = e[0], i_end = e[3 * n_done];
-                    rzr[ch] = max(rz, i_end); // hybrid_synthesis.rs:213
-                    const uint32_t* map = tab->short_map[sr][m] + 18 * lane;
+                    } else {
+                        const int m = (kind == kKindMixed) ? 1 : 0;
+                        const int sw = m ? c2.mixed_switch[sr] : 0;
+                        const uint16_t* e = tab->edges[sr][kind] + sw;
+                        const int n_quads = (c2.n_edges[sr][kind] - sw - 1) / 3;
+                        const int rz = ch ? rze[1] : rze[0];
+                        const bool below = (lane < n_quads) && ((int)e[3 * lane] < rz);
+                        const int n_done = __popc(__ballot_sync(0xffffffffu, below)); // reordered quads form a prefix
+                        const int start = e[0], i_end = e[3 * n_done];
+                        if (ch) rzr[1] = max(rz, i_end); // hybrid_synthesis.rs:213
+                        else rzr[0] = max(rz, i_end);
+                        const uint32_t* map = tab->short_map[sr][m] + 18 * lane;
 #pragma unroll
-                    for (int i = 0; i < 18; ++i) {
-                        if (i == 6 || i == 12) asm volatile("" ::: "memory"); // keep the 18 lookups from being hoisted together
-                        const int d = 18 * lane + i;
-                        const uint32_t e3 = __ldg(map + i);
-                        const bool moved = d >= start && d < i_end;
-                        const int s = moved ? (int)(e3 & 1023u) : d;
-                        const int iv = moved ? (int)((e3 >> 10) & 63u) : (int)((e3 >> 16) & 63u);
-                        const float xv = Sc[s] * ws.scale[ch][iv];
-                        if (ch == 0) {
+                        for (int i = 0; i < 18; ++i) {
+                            if (i == 6 || i == 12) asm volatile("" ::: "memory");
+                            const int d = 18 * lane + i;
+                            const uint32_t e3 = __ldg(map + i);
+                            const bool moved = d >= start && d < i_end;
+                            const int sl = moved ? (int)(e3 & 1023u) : d;
+                            const int iv = moved ? (int)((e3 >> 10) & 63u) : (int)((e3 >> 16) & 63u);
+                            const float xv = Sc[sl] * scl[iv];
                             x[i].x = xv;
-                        } else {
-                            x[i].y = xv;
-                            ivq[i >> 2] |= (uint32_t)iv << (8 * (i & 3));
-                            if (is && xv != 0.0f) ws.nz[iv] = 1;
+                            if (track) {
+                                ivq[i >> 2] |= (uint32_t)iv << (8 * (i & 3));
+                                if (xv != 0.0f) ws.nz[iv] = 1;
+                            }
+                        }
+                    }
+                }
+            } else {
+    #pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    if (ch >= n_ch) continue;
+                    const int kind = ch ? kind1 : kind0;
+                    const float* Sc = S + ch * 576;
+                    if (kind == kKindLong) {
+                        const uint16_t* iv2 = reinterpret_cast<const uint16_t*>(tab->iv_of_line[sr][kind] + 18 * lane);
+    #pragma unroll
+                        for (int i = 0; i < 18; i += 2) {
+                            const float2 v = *reinterpret_cast<const float2*>(Sc + 18 * lane + i);
+                            const unsigned ivp = __ldg(iv2 + (i >> 1));
+                            // lines at or beyond rzero are +0.0 by contract (requantize.rs:234): 0 * scale = 0
+                            const float xa = v.x * ws.scale[ch][ivp & 0xff];
+                            const float xb = v.y * ws.scale[ch][ivp >> 8];
+                            if (ch == 0) {
+                                x[i].x = xa;
+                                x[i + 1].x = xb;
+                            } else {
+                                x[i].y = xa;
+                                x[i + 1].y = xb;
+                                ivq[i >> 2] |= ivp << (8 * (i & 3)); // i is even: the pair lands in one word
+                                if (is) {
+                                    if (xa != 0.0f) ws.nz[ivp & 0xff] = 1;
+                                    if (xb != 0.0f) ws.nz[ivp >> 8] = 1;
+                                }
+                            }
+                        }
+                    } else {
+                        const int m = (kind == kKindMixed) ? 1 : 0;
+                        const int sw = m ? c2.mixed_switch[sr] : 0;
+                        const uint16_t* e = tab->edges[sr][kind] + sw;
+                        const int n_quads = (c2.n_edges[sr][kind] - sw - 1) / 3;
+                        const int rz = rze[ch];
+                        const bool below = (lane < n_quads) && ((int)e[3 * lane] < rz);
+                        const int n_done = __popc(__ballot_sync(0xffffffffu, below)); // reordered quads form a prefix
+                        const int start = e[0], i_end = e[3 * n_done];
+                        rzr[ch] = max(rz, i_end); // hybrid_synthesis.rs:213
+                        const uint32_t* map = tab->short_map[sr][m] + 18 * lane;
+    #pragma unroll
+                        for (int i = 0; i < 18; ++i) {
+                            if (i == 6 || i == 12) asm volatile("" ::: "memory"); // keep the 18 lookups from being hoisted together
+                            const int d = 18 * lane + i;
+                            const uint32_t e3 = __ldg(map + i);
+                            const bool moved = d >= start && d < i_end;
+                            const int s = moved ? (int)(e3 & 1023u) : d;
+                            const int iv = moved ? (int)((e3 >> 10) & 63u) : (int)((e3 >> 16) & 63u);
+                            const float xv = Sc[s] * ws.scale[ch][iv];
+                            if (ch == 0) {
+                                x[i].x = xv;
+                            } else {
+                                x[i].y = xv;
+                                ivq[i >> 2] |= (uint32_t)iv << (8 * (i & 3));
+                                if (is && xv != 0.0f) ws.nz[iv] = 1;
+                            }
                         }
                     }
                 }
@@ -779,7 +849,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
 #pragma unroll
             for (int t = 0; t < 18; ++t) sec[t] = nsec[t];
             __syncwarp();
-            phase_sync();
+            phase_sync(1);
 
             if (k >= -1) {
                 // C: DCT-32 of the granule's 18 time slots, in place; lane = slot, both channels packed.  // PHASE: C glue
@@ -796,7 +866,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
                 __syncwarp();
             }
 
-            phase_sync();
+            phase_sync(2);
             if (k >= 0) {
                 // D: polyphase window (synthesis.rs:247-263, :309-327).  lane = PCM sample index i; a 16-deep  // PHASE: D window
                 // register window of (V_lo[i], V_hi[i]) for both channels walks the 18 slots:
@@ -813,53 +883,113 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
                     dlo[j] = lane > 16 ? -a0 : a0;
                     dhi[j] = -__ldg(tab->synth_d + 64 * j + 32 + lane);
                 }
-                f2 wl[16], wh[16];
-                {
-                    const uint32_t h_lo = prev_rows + (uint32_t)(3 * kPitch + col_lo) * 8u;
-                    const uint32_t h_hi = prev_rows + (uint32_t)(3 * kPitch + col_hi) * 8u;
-#pragma unroll
-                    for (int m = 0; m < 15; ++m) { // the 15 slots before slot 0 -> window index (m+1)&15
-                        wl[(m + 1) & 15] = lds64(h_lo + m * kRowBytes);
-                        wh[(m + 1) & 15] = lds64(h_hi + m * kRowBytes);
-                    }
-                }
-                uint32_t a_lo = cur_rows + (uint32_t)col_lo * 8u;
-                uint32_t a_hi = cur_rows + (uint32_t)col_hi * 8u;
+                // V values of slots -15 .. 17 at index slot + 15: all indices are compile-time, a value lives in a register
+                // from its load to its last tap.  WG slots are accumulated side by side (independent chains): a single
+                // chain of 16 dependent sums leaves the FMA pipe idle for most of its latency.
+                constexpr int WG = (MODE & kV2WinGroup3) ? 3 : (MODE & kV2WinGroup2) ? 2 : 1;
                 const Mp3Tile tw = ld_tile(a.tiles + ti);
                 const int lin = (tw.gpf == 2) ? (int)tw.first_frame * 2 + tw.first_gr + k : ((int)tw.first_frame + tw.first_gr + k) * 2;
                 float* out = a.pcm + (size_t)(lin >> 1) * SYMGPU_MP3_FRAME_FLOATS + (lin & 1) * 576 + lane;
                 const bool stereo = tw.n_ch == 2;
-                for (int base = 0; base < 18; base += 16) {
+                if constexpr ((MODE & kV2Compact) != 0) {
+                    // two passes of 9 slots over one copy of the code; the 15 newest V values move down in between
+                    f2 wl[24], wh[24];
+                    {
+                        const uint32_t h_lo = prev_rows + (uint32_t)(3 * kPitch + col_lo) * 8u;
+                        const uint32_t h_hi = prev_rows + (uint32_t)(3 * kPitch + col_hi) * 8u;
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        if (base + u < 18) {
-                            wl[u] = lds64(a_lo + u * kRowBytes);
-                            wh[u] = lds64(a_hi + u * kRowBytes);
-                            f2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const f2 p0 = o.mul(wl[(u - 2 * j) & 15], dlo[j]);
-                                if (MODE & kV2WinScalarAdd) {
-                                    acc.x += p0.x;
-                                    acc.y += p0.y;
-                                } else {
-                                    acc = o.add(p0, acc);
-                                }
-                                const f2 p1 = o.mul(wh[(u - 2 * j - 1) & 15], dhi[j]);
-                                if (MODE & kV2WinScalarAdd) {
-                                    acc.x += p1.x;
-                                    acc.y += p1.y;
-                                } else {
-                                    acc = o.add(p1, acc);
-                                }
-                            }
-                            out[u * 32] = acc.x;
-                            if (stereo) out[1152 + u * 32] = acc.y;
+                        for (int m = 0; m < 15; ++m) {
+                            wl[m] = lds64(h_lo + m * kRowBytes);
+                            wh[m] = lds64(h_hi + m * kRowBytes);
                         }
                     }
-                    a_lo += 16 * kRowBytes;
-                    a_hi += 16 * kRowBytes;
-                    out += 16 * 32;
+                    uint32_t a_lo = cur_rows + (uint32_t)col_lo * 8u;
+                    uint32_t a_hi = cur_rows + (uint32_t)col_hi * 8u;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                        for (int g0 = 0; g0 < 9; g0 += 3) {
+                            f2 acc[3];
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                wl[15 + g0 + q] = lds64(a_lo + (g0 + q) * kRowBytes);
+                                wh[15 + g0 + q] = lds64(a_hi + (g0 + q) * kRowBytes);
+                                acc[q] = make_float2(0.0f, 0.0f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) acc[q] = o.add(o.mul(wl[15 + g0 + q - 2 * j], dlo[j]), acc[q]);
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) acc[q] = o.add(o.mul(wh[15 + g0 + q - 2 * j - 1], dhi[j]), acc[q]);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                out[(g0 + q) * 32] = acc[q].x;
+                                if (stereo) out[1152 + (g0 + q) * 32] = acc[q].y;
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 15; ++e) {
+                            wl[e] = wl[e + 9];
+                            wh[e] = wh[e + 9];
+                        }
+                        a_lo += 9 * kRowBytes;
+                        a_hi += 9 * kRowBytes;
+                        out += 9 * 32;
+                    }
+                } else {
+                    f2 wl[33], wh[33];
+                    {
+                        const uint32_t h_lo = prev_rows + (uint32_t)(3 * kPitch + col_lo) * 8u;
+                        const uint32_t h_hi = prev_rows + (uint32_t)(3 * kPitch + col_hi) * 8u;
+    #pragma unroll
+                        for (int m = 0; m < 15; ++m) { // the 15 slots before slot 0
+                            wl[m] = lds64(h_lo + m * kRowBytes);
+                            wh[m] = lds64(h_hi + m * kRowBytes);
+                        }
+                    }
+                    const uint32_t a_lo = cur_rows + (uint32_t)col_lo * 8u;
+                    const uint32_t a_hi = cur_rows + (uint32_t)col_hi * 8u;
+    #pragma unroll
+                    for (int g0 = 0; g0 < 18; g0 += WG) {
+                        f2 acc[WG];
+    #pragma unroll
+                        for (int q = 0; q < WG; ++q) {
+                            wl[15 + g0 + q] = lds64(a_lo + (g0 + q) * kRowBytes);
+                            wh[15 + g0 + q] = lds64(a_hi + (g0 + q) * kRowBytes);
+                            acc[q] = make_float2(0.0f, 0.0f);
+                        }
+    #pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+    #pragma unroll
+                            for (int q = 0; q < WG; ++q) {
+                                const f2 p0 = o.mul(wl[15 + g0 + q - 2 * j], dlo[j]);
+                                if (MODE & kV2WinScalarAdd) {
+                                    acc[q].x += p0.x;
+                                    acc[q].y += p0.y;
+                                } else {
+                                    acc[q] = o.add(p0, acc[q]);
+                                }
+                            }
+    #pragma unroll
+                            for (int q = 0; q < WG; ++q) {
+                                const f2 p1 = o.mul(wh[15 + g0 + q - 2 * j - 1], dhi[j]);
+                                if (MODE & kV2WinScalarAdd) {
+                                    acc[q].x += p1.x;
+                                    acc[q].y += p1.y;
+                                } else {
+                                    acc[q] = o.add(p1, acc[q]);
+                                }
+                            }
+                        }
+    #pragma unroll
+                        for (int q = 0; q < WG; ++q) {
+                            out[(g0 + q) * 32] = acc[q].x;
+                            if (stereo) out[1152 + (g0 + q) * 32] = acc[q].y;
+                        }
+                    }
+            
                 }
             }
 
@@ -901,9 +1031,9 @@ __global__ void __launch_bounds__(NW * 32, 1) mp3v2_synth_kernel(Mp3V2Args a) {
 
     if (LOCK) {
         for (int i = my_iters; i < sm.max_iters; ++i) {
-            phase_sync();
-            phase_sync();
-            phase_sync();
+            phase_sync(0);
+            phase_sync(1);
+            phase_sync(2);
         }
     }
 
@@ -928,8 +1058,10 @@ struct V2Variant {
     size_t smem;
 };
 #define V2_VARIANT(NW, MODE) {NW, MODE, mp3v2_synth_kernel<NW, MODE>, sizeof(Mp3V2Smem<NW>)}
-const V2Variant kV2Variants[] = {V2_VARIANT(kMp3V2Warps, 0), V2_VARIANT(kMp3V2Warps, 1), V2_VARIANT(kMp3V2Warps, 2),
-                                 V2_VARIANT(kMp3V2Warps, 3), V2_VARIANT(8, 0), V2_VARIANT(8, 1), V2_VARIANT(8, 3)};
+const V2Variant kV2Variants[] = {V2_VARIANT(kMp3V2Warps, 0), V2_VARIANT(kMp3V2Warps, 1), V2_VARIANT(kMp3V2Warps, 5),
+                                 V2_VARIANT(kMp3V2Warps, 17), V2_VARIANT(kMp3V2Warps, 33), V2_VARIANT(kMp3V2Warps, 21),
+                                 V2_VARIANT(kMp3V2Warps, 64), V2_VARIANT(kMp3V2Warps, 65), V2_VARIANT(kMp3V2Warps, 81),
+                                 V2_VARIANT(14, 33), V2_VARIANT(14, 97), V2_VARIANT(10, 33)};
 int g_v2_variant = 0;
 } // namespace
 
@@ -944,6 +1076,8 @@ bool mp3v2_set_variant(int nw, int mode) {
 }
 
 int mp3v2_cta_warps() { return kV2Variants[g_v2_variant].nw; }
+// Resident CTAs per SM: small CTAs are stacked so that an SM always runs 12 warps (168 registers each).
+int mp3v2_ctas_per_sm() { return kV2Variants[g_v2_variant].nw <= 6 ? 12 / kV2Variants[g_v2_variant].nw : 1; }
 
 int mp3v2_sm_count(cudaError_t* err) {
     static int sm_for_device[64] = {0};
@@ -969,7 +1103,7 @@ cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream) {
     const int n_sm = mp3v2_sm_count(&e);
     if (e != cudaSuccess) return e;
     const V2Variant& v = kV2Variants[g_v2_variant];
-    if (n_ctas <= 0 || n_ctas > n_sm || a.n_shares > n_ctas * v.nw) return cudaErrorInvalidConfiguration;
+    if (n_ctas <= 0 || n_ctas > n_sm * mp3v2_ctas_per_sm() || a.n_shares > n_ctas * v.nw) return cudaErrorInvalidConfiguration;
     v.kernel<<<n_ctas, v.nw * 32, v.smem, stream>>>(a);
     return cudaGetLastError();
 }

@@ -256,7 +256,7 @@ symgpu_status build_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n
     if (ctx->mp3_v2) {
         const int n_sm = mp3v2_sm_count(&ce);
         if (ce != cudaSuccess || n_sm <= 0) return cuda_fail(ctx, ce, "mp3v2_sm_count");
-        return build_plan_v2_for(n_sm * mp3v2_cta_warps(), ctx->n_mp3_streams, runs, n_runs, n_frames, plan, whole_batch);
+        return build_plan_v2_for(n_sm * mp3v2_ctas_per_sm() * mp3v2_cta_warps(), ctx->n_mp3_streams, runs, n_runs, n_frames, plan, whole_batch);
     }
     const int grid = mp3_grid_size(&ce);
     if (ce != cudaSuccess || grid <= 0) return cuda_fail(ctx, ce, "mp3_grid_size");
@@ -274,7 +274,7 @@ cudaError_t launch_plan(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_t
         const int n_shares = n_ctas; // the v2 plan counts shares
         const Mp3V2Args a{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_shares,
                           ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab, 1.0f, -1.0f};
-        return mp3v2_launch(a, std::min(n_sm, n_shares), stream);
+        return mp3v2_launch(a, std::min(n_sm * mp3v2_ctas_per_sm(), n_shares), stream);
     }
     const Mp3Args a{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas, multi ? 1 : 0,
                     ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
