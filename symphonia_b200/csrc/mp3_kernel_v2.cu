@@ -358,6 +358,7 @@ __device__ __forceinline__ size_t granule_slot(const Mp3Tile& t, int k) {
 template <int NW>
 struct Mp3V2Smem {
     WarpSmem w[NW];
+    alignas(8) uint64_t lag_bar[3];
     int max_iters;
     bool is_last;
 };
@@ -370,7 +371,11 @@ struct Mp3V2Smem {
 //   4 / 8  WIN_GROUP2 / WIN_GROUP3: the window accumulates 2 / 3 time slots side by side (independent dependency chains).
 //   16 / 32  (with LOCKSTEP) only the first / the first two of the three meeting points: the warps re-align once per granule
 //      and may drift by a phase in between.
-enum : int { kV2Lockstep = 1, kV2WinScalarAdd = 2, kV2WinGroup2 = 4, kV2WinGroup3 = 8, kV2SyncTopOnly = 16, kV2SyncTopHybrid = 32, kV2Compact = 64 };
+enum : int { kV2Lockstep = 1, kV2WinScalarAdd = 2, kV2WinGroup2 = 4, kV2WinGroup3 = 8, kV2SyncTopOnly = 16, kV2SyncTopHybrid = 32, kV2Compact = 64, kV2Lagged = 128 };
+//   128  LAGGED (with LOCKSTEP): a meeting point lets a warp through once every warp has passed the PREVIOUS point (mbarrier
+//      arrive here, wait for the one before): the warps stay within one phase of each other, so the instruction stream stays
+//      shared, but a warp delayed in one phase (a short-block or intensity-stereo granule) is waited for one phase later,
+//      when the delays of different warps have had a chance to even out.
 //   64  COMPACT: smaller instruction footprint (the channel loop of the load phase and the two halves of the window are
 //      rolled), a few register moves more: for warps that are NOT kept in lockstep and must share the instruction caches.
 
@@ -382,20 +387,34 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 6 ? 12 / NW : 1)) mp3v2_synth_
     using Smem = Mp3V2Smem<NW>;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     constexpr bool LOCK = (MODE & kV2Lockstep) != 0;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t lag_round = 0; // meeting points passed so far (LAGGED)
     auto phase_sync = [&](int point = 0) {
         if (!LOCK) return;
+        if constexpr ((MODE & kV2Lagged) != 0) {
+            // point p of round r: arrive on bar[p]; wait until bar[(p + 2) % 3] has completed the point before this one
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.lag_bar[point])) : "memory");
+            if (lag_round > 0) {
+                const int prev = (point + 2) % 3;
+                const uint32_t uses = (lag_round - 1) / 3; // completed phases of bar[prev] before the one awaited
+                mbar_wait(&sm.lag_bar[prev], uses & 1u);
+            }
+            ++lag_round;
+            return;
+        }
         if ((MODE & kV2SyncTopOnly) && point != 0) return;
         if ((MODE & kV2SyncTopHybrid) && point == 2) return;
         asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
     };
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     WarpSmem& ws = sm.w[warp];
     const Mp3Tables* __restrict__ tab = a.tab;
     const Ops o{a.one, a.mone};
 
     if (lane == 0) {
         mbar_init(&ws.bar, 1);
+        if (LOCK && (MODE & kV2Lagged) && warp == 0)
+            for (int i = 0; i < 3; ++i) mbar_init(&sm.lag_bar[i], NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -1058,10 +1077,11 @@ struct V2Variant {
     size_t smem;
 };
 #define V2_VARIANT(NW, MODE) {NW, MODE, mp3v2_synth_kernel<NW, MODE>, sizeof(Mp3V2Smem<NW>)}
-const V2Variant kV2Variants[] = {V2_VARIANT(kMp3V2Warps, 0), V2_VARIANT(kMp3V2Warps, 1), V2_VARIANT(kMp3V2Warps, 5),
-                                 V2_VARIANT(kMp3V2Warps, 17), V2_VARIANT(kMp3V2Warps, 33), V2_VARIANT(kMp3V2Warps, 21),
-                                 V2_VARIANT(kMp3V2Warps, 64), V2_VARIANT(kMp3V2Warps, 65), V2_VARIANT(kMp3V2Warps, 81),
-                                 V2_VARIANT(14, 33), V2_VARIANT(14, 97), V2_VARIANT(10, 33)};
+// The first entry is the default: 12 warps in lockstep at the top of a granule and after the hybrid phase.
+const V2Variant kV2Variants[] = {V2_VARIANT(kMp3V2Warps, 33), V2_VARIANT(kMp3V2Warps, 0),  V2_VARIANT(kMp3V2Warps, 1),
+                                 V2_VARIANT(kMp3V2Warps, 5),  V2_VARIANT(kMp3V2Warps, 17), V2_VARIANT(kMp3V2Warps, 81),
+                                 V2_VARIANT(kMp3V2Warps, 64), V2_VARIANT(14, 33),          V2_VARIANT(14, 97),
+                                 V2_VARIANT(10, 33),          V2_VARIANT(kMp3V2Warps, 129), V2_VARIANT(kMp3V2Warps, 193)};
 int g_v2_variant = 0;
 } // namespace
 
