@@ -263,6 +263,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpus_before = os.sched_getaffinity(0)  # symgpu_ctx_create binds this thread to the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -556,10 +557,13 @@ def run_ours(args):
                                "-1 = checker unavailable" if float(ok.cpu()[0]) < 0 else
                                "first two streams (256 frames) of every rank's batch through symgpu_mp3_synth_host, uint32 equality"},
             "clocks": dict(sampler.summary(), window=f"device-timed region + {tail_launches} untimed launches of the same step"),
+            "numa": {"node_rank0": eng.numa_node, "cpus_rank0": len(os.sched_getaffinity(0)), "cpus_before": len(cpus_before),
+                     "what": "symgpu_ctx_create binds the rank's thread (and its first-touched pinned buffers) to the GPU's NUMA node"},
             "wall_s": wall,
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, cpus_before)  # the CPU arm may use every core of the box
             orc, arch = _load_oracle_native()
             threads = min(os.cpu_count() or 1, N_STREAMS)
             p1, d1 = _cpu_mp3(orc, units, spectra, runs, 1, 3.0)

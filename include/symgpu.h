@@ -22,7 +22,9 @@
  *
  * Threading (AudioDecoder: Send + Sync, symphonia-core/src/codecs/audio.rs:251): a context owns
  * one CUDA stream; calls on one context must be serialised by the caller (the trait's &mut self
- * already guarantees that per decoder).  Different contexts may be used concurrently.
+ * already guarantees that per decoder).  Different contexts may be used concurrently.  The exception is
+ * symgpu_mp3_submit / symgpu_mp3_submit_quantized / symgpu_mp3_wait: any number of decoder threads may call
+ * them on ONE context at the same time, and the context gathers their frames into shared launches.
  */
 #ifndef SYMGPU_H
 #define SYMGPU_H
@@ -52,8 +54,17 @@ typedef struct symgpu_ctx symgpu_ctx; /* opaque */
 
 /* Creates a context on CUDA device `device` (cudaSetDevice ordinal), builds every lookup table
  * on the host with libm (see DESIGN.md "tables") and uploads them.  Fails with SYMGPU_ERR_CUDA
- * when no usable sm_100 device is present: there is NO CPU fallback behind this ABI. */
+ * when no usable sm_100 device is present: there is NO CPU fallback behind this ABI.
+ * The calling thread is bound to the CPUs of the device's NUMA node (sysfs numa_node of the PCI device, intersected
+ * with the thread's current affinity), so that pinned host buffers it allocates afterwards are node-local by first
+ * touch -- one rank per GPU on a two-socket B200 node otherwise pushes half of its PCIe traffic across the socket link.
+ * SYMGPU_NUMA_BIND=0 in the environment switches this off. */
 symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out);
+/* NUMA node of CUDA device `device` (-1 if the platform does not say); binds the calling thread to that node's CPUs and
+ * returns the node (-1 if nothing was changed); node a context bound its creating thread to (-1 none, -2 switched off). */
+int symgpu_numa_node_of_device(int device);
+int symgpu_bind_thread_to_device_numa(int device);
+int symgpu_ctx_numa_node(const symgpu_ctx* ctx);
 void symgpu_ctx_destroy(symgpu_ctx* ctx);
 
 /* Static description of `status`. */
@@ -154,6 +165,32 @@ symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
 symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
                                    const float* spectra, const symgpu_mp3_run* runs,
                                    uint32_t n_runs, uint32_t n_frames, float* pcm);
+
+/* ---- MP3: asynchronous, thread-safe submission (many single-stream decoders sharing one context) ------------------- *
+ * The reference creates one decoder per stream (registry.rs:260-269) and calls decode() once per packet
+ * (codecs/audio.rs:251-298); a server runs many of them on as many threads.  These three entry points may be called
+ * concurrently from any number of threads on ONE context (every other entry point of a context still wants one caller at
+ * a time, and must not run concurrently with these).  submit copies one frame into the context's pinned staging batch
+ * and returns a ticket; wait returns that frame's PCM.  The first thread that waits for a ticket of the oldest
+ * unfinished batch closes the batch and runs it -- one copy in, ONE launch, one copy out -- for every thread that has a
+ * frame in it; the others sleep until it is done, while new submissions gather in the next batch.  Frames of a stream
+ * are synthesised in submission order (a stream occurs once per batch; batches run in order).  A malformed frame is
+ * refused by submit (SYMGPU_ERR_DECODE) and never reaches a batch.  Every ticket must be redeemed exactly once. */
+typedef struct symgpu_ticket {
+    uint64_t batch;
+    uint32_t slot;
+    uint32_t reserved;
+} symgpu_ticket;
+/* units [2][2], spectra [2][2][576] (one frame, as symgpu_mp3_synth_host takes them); granules_per_frame 2 | 1, channels 2 | 1. */
+symgpu_status symgpu_mp3_submit(symgpu_ctx* ctx, uint32_t stream, const symgpu_mp3_gc* units, const float* spectra,
+                                uint8_t granules_per_frame, uint8_t channels, symgpu_ticket* ticket);
+/* Same with the Huffman stage's int16 values sign * x (|x| <= 8206); the POW43 lookup happens at submission. */
+symgpu_status symgpu_mp3_submit_quantized(symgpu_ctx* ctx, uint32_t stream, const symgpu_mp3_gc* units, const int16_t* quant,
+                                          uint8_t granules_per_frame, uint8_t channels, symgpu_ticket* ticket);
+/* pcm [2][1152] of the ticket's frame.  Blocks until the frame's batch has run (running it if nobody else does). */
+symgpu_status symgpu_mp3_wait(symgpu_ctx* ctx, symgpu_ticket ticket, float* pcm);
+/* Launch batches run so far through submit / wait and the frames they held (frames / batches = achieved batching). */
+void symgpu_mp3_async_stats(const symgpu_ctx* ctx, uint64_t* batches, uint64_t* frames);
 
 /* ---- AAC-LC filterbank --------------------------------------------------------------------- */
 

@@ -25,6 +25,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -120,8 +121,10 @@ class CodecRegistry {
     std::map<uint32_t, AudioDecoderFactory[3]> slots_;
 };
 
-// A context shared by the GPU decoders of one thread (one CUDA stream, codecs/audio.rs "Send + Sync":
-// one call at a time per context).  Stream-state slots are handed out from a free list.
+// A context shared by GPU decoders (one CUDA stream).  Stream-state slots are handed out from a free list under a mutex.
+// MPEG Layer III decoders of ANY number of threads may share one context: their decode() goes through the thread-safe
+// symgpu_mp3_submit / symgpu_mp3_wait pair, which gathers the packets of all threads into shared launches.  The other decoders
+// (Layer I / II, AAC, Vorbis) still want one calling thread per context (codecs/audio.rs "Send + Sync": one call at a time).
 class GpuContext {
   public:
     static Result<std::shared_ptr<GpuContext>> create(int device, uint32_t max_streams) {
@@ -138,12 +141,16 @@ class GpuContext {
     symgpu_ctx* raw() const { return ctx_; }
     int device() const { return device_; }
     int acquire_stream() {
+        std::lock_guard<std::mutex> g(m_);
         if (free_.empty()) return -1;
         const int s = free_.back();
         free_.pop_back();
         return s;
     }
-    void release_stream(int s) { free_.push_back(s); }
+    void release_stream(int s) {
+        std::lock_guard<std::mutex> g(m_);
+        free_.push_back(s);
+    }
 
   private:
     GpuContext(symgpu_ctx* c, uint32_t n, int device) : ctx_(c), device_(device) {
@@ -151,6 +158,7 @@ class GpuContext {
     }
     symgpu_ctx* ctx_;
     int device_;
+    std::mutex m_;
     std::vector<int> free_;
 };
 
@@ -206,7 +214,10 @@ class GpuMpaDecoder final : public AudioDecoder {
         run.n_frames = 1;
         run.granules_per_frame = mpeg1 ? 2 : 1;
         run.channels = mono ? 1 : 2;
-        const symgpu_status st = symgpu_mp3_synth_host(gpu_->raw(), units, spectra, &run, 1, 1, pcm_.data());
+        // thread-safe, batched with the packets other decoders of this context have in flight
+        symgpu_ticket ticket;
+        symgpu_status st = symgpu_mp3_submit(gpu_->raw(), stream_, units, spectra, run.granules_per_frame, run.channels, &ticket);
+        if (st == SYMGPU_OK) st = symgpu_mp3_wait(gpu_->raw(), ticket, pcm_.data());
         if (st != SYMGPU_OK) return {{}, map_status(st)};
         return finish(packet, mpeg1 ? 1152 : 576, mono ? 1 : 2);
     }
@@ -240,7 +251,9 @@ class GpuMpaDecoder final : public AudioDecoder {
                     return {{}, {ErrorKind::DecodeError, "mpa: stereo channel pair block_type mismatch"}};
             symgpu_mp3_run run{};
             run.stream = stream_, run.n_frames = 1, run.granules_per_frame = info.granules, run.channels = info.channels;
-            st = symgpu_mp3_synth_host_quantized(gpu_->raw(), units, quant_, &run, 1, 1, -1, pcm_.data());
+            symgpu_ticket ticket;
+            st = symgpu_mp3_submit_quantized(gpu_->raw(), stream_, units, quant_, run.granules_per_frame, run.channels, &ticket);
+            if (st == SYMGPU_OK) st = symgpu_mp3_wait(gpu_->raw(), ticket, pcm_.data());
             frames = info.granules == 2 ? 1152 : 576;
         } else {
             const int layer = params_.codec == CODEC_ID_MP1 ? 1 : 2, n_slots = layer == 1 ? 12 : 36;

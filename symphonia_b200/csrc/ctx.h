@@ -11,11 +11,16 @@
 #include "mp3_kernel.h"
 #include "tables.h"
 
+struct symgpu_async_mp3;                       // symgpu_async.cpp: batches gathered from many submitting threads
+void symgpu_async_mp3_destroy(symgpu_async_mp3*);
+
 struct symgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     char cuda_err[256] = {0};
     uint64_t launches = 0;
+    symgpu_async_mp3* async_mp3 = nullptr;
+    int numa_node = -1; // node the creating thread was bound to (-1: platform does not say, -2: binding switched off)
     bool mp3_v2 = true; // Layer III kernel generation (mp3_kernel_v2.cu unless SYMGPU_MP3_KERNEL=v1)
     // tables
     symgpu::Mp3Tables* d_mp3_tab = nullptr;

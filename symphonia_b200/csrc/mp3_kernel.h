@@ -124,7 +124,7 @@ struct Mp3V2Args {
     float one, mone;        // 1.0f, -1.0f: multiplicands of the packed sums (opaque to ptxas, see mp3_kernel_v2.cu)
 };
 cudaError_t mp3v2_upload_const(const Mp3Tables& t, cudaStream_t stream);
-cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream);
+cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream, bool short_runs);
 int mp3v2_cta_warps();
 int mp3v2_ctas_per_sm();
 bool mp3v2_set_variant(int nw, int mode); // experiments: warps per CTA, variant bits (mp3_kernel_v2.cu)

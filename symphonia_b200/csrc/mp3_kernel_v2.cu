@@ -1099,30 +1099,53 @@ int mp3v2_cta_warps() { return kV2Variants[g_v2_variant].nw; }
 // Resident CTAs per SM: small CTAs are stacked so that an SM always runs 12 warps (168 registers each).
 int mp3v2_ctas_per_sm() { return kV2Variants[g_v2_variant].nw <= 6 ? 12 / kV2Variants[g_v2_variant].nw : 1; }
 
+namespace {
+// Raises the dynamic shared-memory limit of variant `vi` on the current device once.
+cudaError_t configure_variant(int vi, int dev) {
+    static bool done[64][sizeof kV2Variants / sizeof kV2Variants[0]] = {};
+    if (done[dev & 63][vi]) return cudaSuccess;
+    const V2Variant& v = kV2Variants[vi];
+    cudaError_t e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
+    if (e == cudaSuccess) done[dev & 63][vi] = true;
+    return e;
+}
+int variant_index(int nw, int mode) {
+    for (size_t i = 0; i < sizeof kV2Variants / sizeof kV2Variants[0]; ++i)
+        if (kV2Variants[i].nw == nw && kV2Variants[i].mode == mode) return (int)i;
+    return -1;
+}
+} // namespace
+
 int mp3v2_sm_count(cudaError_t* err) {
     static int sm_for_device[64] = {0};
-    static int configured_variant[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess && (!sm_for_device[dev & 63] || configured_variant[dev & 63] != g_v2_variant)) {
+    if (e == cudaSuccess && !sm_for_device[dev & 63]) {
         int n_sm = 0;
-        const V2Variant& v = kV2Variants[g_v2_variant];
-        e = cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) {
-            sm_for_device[dev & 63] = n_sm;
-            configured_variant[dev & 63] = g_v2_variant;
-        }
+        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) sm_for_device[dev & 63] = n_sm;
     }
     if (err) *err = e;
     return e == cudaSuccess ? sm_for_device[dev & 63] : 0;
 }
 
-cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream) {
+// short_runs: the plan is made of many short runs (the serving shape: a frame or two per stream).  Unless an experiment
+// pinned a variant, such plans take the compact instantiation that re-aligns its warps once per granule only: with a state
+// load and store around almost every granule the phases of different warps differ too much for three meeting points.
+cudaError_t mp3v2_launch(const Mp3V2Args& a, int n_ctas, cudaStream_t stream, bool short_runs) {
     cudaError_t e = cudaSuccess;
     const int n_sm = mp3v2_sm_count(&e);
     if (e != cudaSuccess) return e;
-    const V2Variant& v = kV2Variants[g_v2_variant];
+    int vi = g_v2_variant;
+    if (vi == 0 && short_runs) {
+        const int alt = variant_index(kV2Variants[0].nw, kV2Lockstep | kV2SyncTopOnly | kV2Compact);
+        if (alt >= 0) vi = alt;
+    }
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = configure_variant(vi, dev);
+    if (e != cudaSuccess) return e;
+    const V2Variant& v = kV2Variants[vi];
     if (n_ctas <= 0 || n_ctas > n_sm * mp3v2_ctas_per_sm() || a.n_shares > n_ctas * v.nw) return cudaErrorInvalidConfiguration;
     v.kernel<<<n_ctas, v.nw * 32, v.smem, stream>>>(a);
     return cudaGetLastError();

@@ -4,8 +4,10 @@
 // point that produces PCM launches the CUDA kernels, and context creation fails loudly when no
 // CUDA device is usable.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -274,7 +276,9 @@ cudaError_t launch_plan(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_t
         const int n_shares = n_ctas; // the v2 plan counts shares
         const Mp3V2Args a{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_shares,
                           ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab, 1.0f, -1.0f};
-        return mp3v2_launch(a, std::min(n_sm * mp3v2_ctas_per_sm(), n_shares), stream);
+        // many short run segments per share = the serving shape (a frame or two per stream)
+        const bool short_runs = n_tiles >= 2 * n_shares;
+        return mp3v2_launch(a, std::min(n_sm * mp3v2_ctas_per_sm(), n_shares), stream, short_runs);
     }
     const Mp3Args a{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas, multi ? 1 : 0,
                     ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
@@ -318,6 +322,70 @@ symgpu_status ensure_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t 
 }
 
 } // namespace
+
+
+// ---- NUMA placement ------------------------------------------------------------------------------------------------
+// A B200 node has its GPUs behind two sockets; a rank whose thread (and therefore its first-touched pinned buffers)
+// sits on the far socket pays for every H2D / D2H byte twice on the inter-socket link, and eight ranks doing so at once
+// is what bent round 1's end-to-end scaling (0.62 at 8 GPUs).  Parses "0-3,8,10-11" style lists.
+static bool parse_cpulist(const char* text, cpu_set_t* set) {
+    CPU_ZERO(set);
+    int n = 0;
+    const char* p = text;
+    while (*p) {
+        char* end = nullptr;
+        const long a = std::strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        p = end;
+        if (*p == '-') {
+            b = std::strtol(p + 1, &end, 10);
+            if (end == p + 1) return false;
+            p = end;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+            CPU_SET((int)c, set);
+            ++n;
+        }
+        while (*p == ',' || *p == '\n' || *p == ' ') ++p;
+    }
+    return n > 0;
+}
+
+static bool read_small_file(const char* path, char* buf, size_t cap) {
+    std::FILE* f = std::fopen(path, "r");
+    if (!f) return false;
+    const size_t n = std::fread(buf, 1, cap - 1, f);
+    std::fclose(f);
+    buf[n] = 0;
+    return n > 0;
+}
+
+extern "C" int symgpu_numa_node_of_device(int device) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) return -1;
+    for (char* c = bdf; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    char path[128], buf[64];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    if (!read_small_file(path, buf, sizeof buf)) return -1;
+    return std::atoi(buf); // -1 when the platform does not say
+}
+
+extern "C" int symgpu_bind_thread_to_device_numa(int device) {
+    const int node = symgpu_numa_node_of_device(device);
+    if (node < 0) return -1;
+    char path[128], buf[4096];
+    std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    if (!read_small_file(path, buf, sizeof buf)) return -1;
+    cpu_set_t want, have, both;
+    if (!parse_cpulist(buf, &want)) return -1;
+    // stay inside the CPUs this process is allowed to use (containers, taskset)
+    if (sched_getaffinity(0, sizeof have, &have) != 0) return -1;
+    CPU_AND(&both, &want, &have);
+    if (CPU_COUNT(&both) == 0) return -1;
+    if (sched_setaffinity(0, sizeof both, &both) != 0) return -1;
+    return node;
+}
 
 extern "C" {
 
@@ -432,6 +500,12 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
             return SYMGPU_ERR_ARG;
         }
     }
+    // The calling thread moves to the CPUs of the GPU's NUMA node (pinned buffers it allocates from now on are local by
+    // first touch); SYMGPU_NUMA_BIND=0 leaves the affinity alone.
+    {
+        const char* env = std::getenv("SYMGPU_NUMA_BIND");
+        ctx->numa_node = (env && env[0] == '0') ? -2 : symgpu_bind_thread_to_device_numa(device);
+    }
     DeviceGuard guard(device);
     auto fail = [&](cudaError_t err, const char* where) {
         std::fprintf(stderr, "symgpu: %s failed: %s\n", where, cudaGetErrorString(err));
@@ -452,6 +526,7 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    symgpu_async_mp3_destroy(ctx->async_mp3);
     if (ctx->d_mp3_tab) cudaFree(ctx->d_mp3_tab);
     if (ctx->d_mp3_states) cudaFree(ctx->d_mp3_states);
     if (ctx->d_mp3_gen) cudaFree(ctx->d_mp3_gen);
@@ -488,6 +563,7 @@ symgpu_status symgpu_sync(symgpu_ctx* ctx) {
 }
 
 void* symgpu_cuda_stream(symgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int symgpu_ctx_numa_node(const symgpu_ctx* ctx) { return ctx ? ctx->numa_node : -1; }
 uint64_t symgpu_launch_count(const symgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 symgpu_status symgpu_mp3_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams) {

@@ -65,6 +65,13 @@ class Engine:
         return self._lib.symgpu_cuda_stream(self._ctx)
 
     @property
+    def numa_node(self):
+        """NUMA node the creating thread was bound to by symgpu_ctx_create (-1: unknown, -2: SYMGPU_NUMA_BIND=0)."""
+        self._lib.symgpu_ctx_numa_node.restype = ctypes.c_int
+        self._lib.symgpu_ctx_numa_node.argtypes = [ctypes.c_void_p]
+        return int(self._lib.symgpu_ctx_numa_node(self._ctx))
+
+    @property
     def launch_count(self):
         return int(self._lib.symgpu_launch_count(self._ctx))
 

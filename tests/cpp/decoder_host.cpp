@@ -2,14 +2,19 @@
 //   decoder_host registry            CPU tier: tier ordering / Unsupported / no-GPU error behaviour
 //   decoder_host decode IN OUT       GPU tier: decode a stream of parsed MP3 packets one decode() call at a
 //                                    time (BASELINE config 0 "plumbing") and write planar PCM
+//   decoder_host threads S IN OUT    GPU tier: S decoder threads, one stream each, sharing ONE context: every decode() is a
+//                                    symgpu_mp3_submit + symgpu_mp3_wait, the context batches the packets of all threads
 //   decoder_host file LAYER IN OUT   GPU tier: an MPEG audio FILE end to end in C++ -- packetiser (packetizer.hpp), registry,
 //                                    GpuMpaDecoder::decode on real frames with the packetiser's gapless trims -- planar PCM out
 //   decoder_host file aac IN OUT     GPU tier: an ADTS file: frame index, registry, GpuAacDecoder::decode per raw_data_block
 //   decoder_host file vorbis IN OUT  GPU tier: a Vorbis-in-Ogg file: pages -> packets -> mapping (durations, discards, end trims
 //                                    against the page granule positions), registry, GpuVorbisDecoder::decode per audio packet
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <thread>
 #include <vector>
 
 #include "../../include/symgpu/decoder.hpp"
@@ -97,6 +102,7 @@ static int run_decode(const char* in_path, const char* out_path) {
     auto dec = reg.make_audio_decoder(params, opts);
     if (!dec.ok()) return 3;
     std::ofstream out(out_path, std::ios::binary);
+    const auto t0 = std::chrono::steady_clock::now();
     for (size_t i = 0; i < n; ++i) {
         Packet p;
         p.data = bytes.data() + i * GpuMpaDecoder::kPacketBytes;
@@ -109,8 +115,65 @@ static int run_decode(const char* in_path, const char* out_path) {
         for (size_t ch = 0; ch < 2; ++ch)
             out.write(reinterpret_cast<const char*>(res.value.planes[ch]), (std::streamsize)(res.value.frames * sizeof(float)));
     }
-    std::printf("decoded %zu packets\n", n);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("decoded %zu packets us_per_packet %.2f (AudioDecoder::decode, one packet per call, file write included)\n", n, 1e6 * sec / (double)n);
     return 0;
+}
+
+
+// S decoders on S threads share one context (the server shape of SURVEY 8b): IN = S streams x F parsed packets, stream-major.
+static int run_threads(int n_streams, const char* in_path, const char* out_path) {
+    std::ifstream in(in_path, std::ios::binary);
+    std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    const size_t n = bytes.size() / GpuMpaDecoder::kPacketBytes;
+    if (n_streams <= 0 || n % (size_t)n_streams) return 6;
+    const size_t per = n / (size_t)n_streams;
+    auto gpu = GpuContext::create(0, (uint32_t)n_streams);
+    if (!gpu.ok()) {
+        std::fprintf(stderr, "%s\n", gpu.error.message);
+        return 2;
+    }
+    CodecRegistry reg;
+    register_gpu_decoders(reg, gpu.value);
+    std::vector<float> pcm(n * 2 * 1152, 0.0f);
+    std::atomic<int> failed{0};
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (int s = 0; s < n_streams; ++s)
+        threads.emplace_back([&, s] {
+            AudioCodecParameters params;
+            params.codec = CODEC_ID_MP3;
+            params.channels = 2;
+            AudioDecoderOptions opts;
+            opts.gapless = false;
+            auto dec = reg.make_audio_decoder(params, opts);
+            if (!dec.ok()) {
+                failed++;
+                return;
+            }
+            for (size_t i = 0; i < per; ++i) {
+                Packet p;
+                p.data = bytes.data() + ((size_t)s * per + i) * GpuMpaDecoder::kPacketBytes;
+                p.len = GpuMpaDecoder::kPacketBytes;
+                auto res = dec.value->decode(p);
+                if (!res.ok() || res.value.frames != 1152) {
+                    failed++;
+                    return;
+                }
+                for (size_t ch = 0; ch < 2; ++ch)
+                    std::memcpy(pcm.data() + (((size_t)s * per + i) * 2 + ch) * 1152, res.value.planes[ch], 1152 * sizeof(float));
+            }
+        });
+    for (auto& t : threads) t.join();
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t batches = 0, frames = 0;
+    symgpu_mp3_async_stats(gpu.value->raw(), &batches, &frames);
+    std::ofstream out(out_path, std::ios::binary);
+    out.write(reinterpret_cast<const char*>(pcm.data()), (std::streamsize)(pcm.size() * sizeof(float)));
+    std::printf("threads %d packets %zu batches %llu frames %llu frames_per_batch %.2f seconds %.4f packets_per_s %.0f failed %d\n", n_streams, n,
+                (unsigned long long)batches, (unsigned long long)frames, batches ? (double)frames / (double)batches : 0.0, sec, (double)n / sec,
+                failed.load());
+    return failed.load() ? 4 : 0;
 }
 
 static int run_file(int layer, const char* in_path, const char* out_path) {
@@ -246,6 +309,7 @@ static int run_ogg_vorbis(const char* in_path, const char* out_path) {
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "registry") return test_registry();
     if (argc >= 4 && std::string(argv[1]) == "decode") return run_decode(argv[2], argv[3]);
+    if (argc >= 5 && std::string(argv[1]) == "threads") return run_threads(std::atoi(argv[2]), argv[3], argv[4]);
     if (argc >= 5 && std::string(argv[1]) == "file" && std::string(argv[2]) == "aac") return run_adts(argv[3], argv[4]);
     if (argc >= 5 && std::string(argv[1]) == "file" && std::string(argv[2]) == "vorbis") return run_ogg_vorbis(argv[3], argv[4]);
     if (argc >= 5 && std::string(argv[1]) == "file") return run_file(std::atoi(argv[2]), argv[3], argv[4]);

@@ -18,7 +18,7 @@ def _build():
     hdr = os.path.join(ROOT, "include", "symgpu", "decoder.hpp")
     hdr2 = os.path.join(ROOT, "include", "symgpu", "packetizer.hpp")
     if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(lib), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", EXE, src, "-L" + os.path.dirname(lib), "-lsymgpu",
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-o", EXE, src, "-L" + os.path.dirname(lib), "-lsymgpu",
                                "-Wl,-rpath," + os.path.dirname(lib)])
     return EXE
 
@@ -43,3 +43,26 @@ def test_packet_by_packet_decode_matches_oracle(tmp_path, oracle):
     assert res.returncode == 0, res.stdout + res.stderr
     got = np.frombuffer(outp.read_bytes(), dtype=np.float32).reshape(F, 2, 1152)
     assert (got.view(np.uint32) == want.view(np.uint32)).all()
+
+
+@pytest.mark.gpu
+def test_sixty_four_decoder_threads_share_one_context(tmp_path, oracle):
+    """The server shape: 64 single-stream decoders on 64 threads, ONE context; every decode() is a submit + wait and
+    the context batches whatever the threads have in flight.  Bit-exact per stream, and the launches really are shared."""
+    import re
+    from symphonia_b200 import workloads
+    from tests import _oracle
+    S, F = 64, 12
+    units, spectra, runs = workloads.mp3_batch(S, F, seed=4242)
+    rc, want, _ = _oracle.mp3_batch(oracle, units, spectra, runs, S)
+    assert rc == 0
+    blob = b"".join(units[f].tobytes() + spectra[f].tobytes() for f in range(S * F))   # stream-major: frames of a run are consecutive
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    inp.write_bytes(blob)
+    res = subprocess.run([_build(), "threads", str(S), str(inp), str(outp)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    got = np.frombuffer(outp.read_bytes(), dtype=np.float32).reshape(S * F, 2, 1152)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    m = re.search(r"batches (\d+) frames (\d+)", res.stdout)
+    assert m and int(m.group(2)) == S * F
+    assert int(m.group(1)) < S * F, "some launches carried the packets of several decoders: " + res.stdout
