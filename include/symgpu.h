@@ -82,6 +82,12 @@ size_t symgpu_tables_host_blob(void* out, size_t cap);
 size_t symgpu_codec_tables_host_blob(void* out, size_t cap);
 /* Replace the device tables of `ctx` with a blob received from rank 0. */
 symgpu_status symgpu_tables_upload(symgpu_ctx* ctx, const void* blob, size_t bytes);
+/* The same exchange without leaving the library: broadcasts the table blobs (MP3 and AAC / Vorbis) from rank `root` of
+ * `nccl_comm` -- an ncclComm_t the host application created, passed as void* so that this header needs no nccl.h -- in
+ * place over NCCL on the context's stream, and refreshes the constant-memory copies.  NULL: single GPU, nothing to do.
+ * libnccl.so.2 is looked up with dlopen on first use (no link-time dependency); SYMGPU_ERR_UNSUPPORTED if it is absent.
+ * Collective: every rank of the communicator must call it. */
+symgpu_status symgpu_tables_broadcast(symgpu_ctx* ctx, void* nccl_comm, int root);
 
 /* Blocks until every kernel / copy enqueued on the context's stream has finished. */
 symgpu_status symgpu_sync(symgpu_ctx* ctx);
@@ -284,6 +290,9 @@ typedef struct symgpu_vorbis_run {
 /* Registers stream configurations (and zeroes their overlap state) / floor setups with a context. */
 symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_stream* streams, uint32_t n_streams);
 symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floor1* floors, uint32_t n_floors);
+/* The validation symgpu_vorbis_floors_set applies, without a context (host only): SYMGPU_OK or SYMGPU_ERR_ARG.  The Vorbis
+ * front-end runs it when a stream is opened, so that an unusable setup is refused per stream (SYMGPU_ERR_UNSUPPORTED). */
+symgpu_status symgpu_vorbis_floors_check(const symgpu_vorbis_floor1* floors, uint32_t n_floors);
 symgpu_status symgpu_vorbis_stream_reset(symgpu_ctx* ctx, uint32_t stream); /* dsp.rs:26-32, :128-131 */
 
 /* Synthesises `n_packets` packets.  Every per-packet array uses fixed slots of `slot` floats per

@@ -12,6 +12,7 @@
 // tables use the C library's powf, which is what f32::powf calls (tests/test_aac_frontend.py: the scale-factor tables are the
 // correctly rounded powers of two; x^(4/3) is within one unit in the last place, 10 of 8192 entries differ under glibc).
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -897,7 +898,9 @@ symgpu_status symgpu_aac_fe_decode_packets_jobs(uint32_t sample_rate, uint32_t c
                                                 float* coeffs, size_t* n_tns, uint32_t n_threads) {
     if ((!data && n) || (n_packets && (!packets || !units || !coeffs)) || !n_tns || (tns_cap && !tns)) return SYMGPU_ERR_ARG;
     if (channels < 1 || channels > 2) return SYMGPU_ERR_UNSUPPORTED;
-    if (n_threads == 0) n_threads = 1;
+    n_threads = std::max<uint32_t>(1, std::min<uint32_t>({n_threads, 64u, std::max(1u, std::thread::hardware_concurrency()),
+                                                           uint32_t(std::min<size_t>(std::max<size_t>(n_packets, 1), 64))}));
+    try { // no C++ exception crosses the ABI (vector / thread creation may throw)
     struct Job {
         symgpu_status st = SYMGPU_OK;
         uint32_t n_pairs = 0, n_tns = 0;
@@ -957,6 +960,9 @@ symgpu_status symgpu_aac_fe_decode_packets_jobs(uint32_t sample_rate, uint32_t c
     }
     *n_tns = at;
     return SYMGPU_OK;
+    } catch (...) {
+        return SYMGPU_ERR_LIMIT;
+    }
 }
 
 void symgpu_aac_fe_tables(float* pow43, float* normal_scf, float* intensity_scf) {

@@ -21,7 +21,9 @@ struct symgpu_ctx {
     uint64_t launches = 0;
     symgpu_async_mp3* async_mp3 = nullptr;
     int numa_node = -1; // node the creating thread was bound to (-1: platform does not say, -2: binding switched off)
-    bool mp3_v2 = true; // Layer III kernel generation (mp3_kernel_v2.cu unless SYMGPU_MP3_KERNEL=v1)
+    // Layer III kernel choice (SYMGPU_MP3_KERNEL): 0 auto (by plan shape: long runs -> first generation with the packed window,
+    // short runs -> second generation), 1 always the first generation, 2 always the second
+    int mp3_kernel_mode = 0;
     // tables
     symgpu::Mp3Tables* d_mp3_tab = nullptr;
     // MP3 streams
@@ -36,11 +38,13 @@ struct symgpu_ctx {
     uint32_t cached_frames = 0;
     int cached_tiles = 0, cached_hdr = 0, cached_ctas = 0;
     bool cached_multi = false;
+    bool cached_v2 = false;
     // staging for the host entry points
     void* d_stage = nullptr;
     size_t stage_cap = 0;
     // copy pipeline of the host entry points: H2D on copy_in, kernels on `stream`, D2H on copy_out
     static constexpr int kMaxSlices = 32;
+    int h2d_ahead = 2; // slices whose H2D copy is queued before the host's descriptor check and planning (SYMGPU_H2D_AHEAD)
     int n_slices = 8; // slices of a host batch in the copy pipeline (SYMGPU_SLICES overrides, for tuning)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};

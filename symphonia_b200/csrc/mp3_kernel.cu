@@ -257,6 +257,25 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
     return v;
 }
 
+
+// ---- packed f32x2 arithmetic for the (ch0, ch1) pairs of the window phase (round 2, see mp3_kernel_v2.cu for the rules:
+// a packed sum is fma(a, ONE, b) with ONE a kernel argument, because ptxas contracts mul.f32x2 + add.f32x2) ----------------
+__device__ __forceinline__ float2 pk_mul(float2 a, float s) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(s));
+    return r;
+}
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b, float one) { // a * 1 + b
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mov.b64 rc, {%5,%6}; fma.rn.f32x2 rd, ra, rb, rc; "
+        "mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(one), "f"(b.x), "f"(b.y));
+    return r;
+}
+
 // Polyphase window of `total` consecutive time slots whose DCT vectors sit in XT rows row0 ..  // PHASE: D window
 // (with the 15 rows before row0 holding the history).  lane = PCM sample index i; each warp walks a
 // contiguous range of slots with a 16-deep register window of (V_lo[i], V_hi[i]) for both channels:
@@ -267,10 +286,10 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
 // batch-wide sequence number of the first slot: slots of a frame are contiguous in a PCM plane
 // (plane[gr*576 + t*32 + i]) and frames are SYMGPU_MP3_FRAME_FLOATS apart.
 // TWO_JUMPS: a block of 16 slots may cross two frame boundaries (Layer I: 12 slots per frame).
-template <bool TWO_JUMPS = false>
+template <bool TWO_JUMPS = false, bool PACKED = false>
 __device__ __forceinline__ void window_phase(const float* xt, int row0, int begin, int end, int lane,
                                              const float* __restrict__ synth_d, float* __restrict__ pcm, int slot_seq0,
-                                             int slots_per_frame, bool stereo) {
+                                             int slots_per_frame, bool stereo, float one = 1.0f) {
     const int col_lo = lane < 16 ? 16 + lane : (lane == 16 ? 32 : 48 - lane);
     const int col_hi = lane <= 16 ? 16 - lane : lane - 16;
     float dlo[8], dhi[8];
@@ -307,14 +326,25 @@ __device__ __forceinline__ void window_phase(const float* xt, int row0, int begi
                 wl[u] = lds64(a_lo + u * kRowBytes);
                 wh[u] = lds64(a_hi + u * kRowBytes);
                 float o0 = 0.0f, o1 = 0.0f;
+                if constexpr (PACKED) {
+                    float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float2 v0 = wl[(u - 2 * j) & 15];
-                    const float2 v1 = wh[(u - 2 * j - 1) & 15];
-                    o0 += v0.x * dlo[j];
-                    o1 += v0.y * dlo[j];
-                    o0 += v1.x * dhi[j];
-                    o1 += v1.y * dhi[j];
+                    for (int j = 0; j < 8; ++j) {
+                        acc = pk_add(pk_mul(wl[(u - 2 * j) & 15], dlo[j]), acc, one);
+                        acc = pk_add(pk_mul(wh[(u - 2 * j - 1) & 15], dhi[j]), acc, one);
+                    }
+                    o0 = acc.x;
+                    o1 = acc.y;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 v0 = wl[(u - 2 * j) & 15];
+                        const float2 v1 = wh[(u - 2 * j - 1) & 15];
+                        o0 += v0.x * dlo[j];
+                        o1 += v0.y * dlo[j];
+                        o0 += v1.x * dhi[j];
+                        o1 += v1.y * dhi[j];
+                    }
                 }
                 float* o = (u < kj ? out0 : out1) + u * 32;
                 if (TWO_JUMPS && u >= kj + slots_per_frame) o += frame_jump;
@@ -346,7 +376,7 @@ struct Mp3Smem {
 
 // MULTI = false: every group of the plan is a single tile (the shape of large batches); the loops over the
 // pieces of a group then fold away at compile time.
-template <int T, int NW, bool MULTI>
+template <int T, int NW, bool MULTI, bool PK = false>
 __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) {
     static_assert(NW >= T, "one warp per granule job (a tile with a halo holds NW - 2 granules)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -834,7 +864,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) 
                 if (b < e) {
                     const int shift = t.gpf == 2 ? 1 : 0;
                     const int gseq = ((int)t.first_frame << shift) + t.first_gr;
-                    window_phase(xt, 18 * (regions + 1), b, e, lane, tab->synth_d, a.pcm, gseq * 18, 18 << shift, t.n_ch == 2);
+                    window_phase<false, PK>(xt, 18 * (regions + 1), b, e, lane, tab->synth_d, a.pcm, gseq * 18, 18 << shift, t.n_ch == 2, a.one);
                 }
                 first += cnt;
                 regions += t.n_granules + 1;
@@ -1047,13 +1077,29 @@ int mp3_grid_size(cudaError_t* err) {
     return e == cudaSuccess ? grid_for_device[dev & 63] : 0;
 }
 
+static bool g_v1_packed_window = false;
+void mp3_v1_set_packed_window(bool on) { g_v1_packed_window = on; }
+
 cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream) {
     constexpr size_t smem = sizeof(Mp3Smem<kMp3TileGranules, kMp3Warps>);
     cudaError_t e = cudaSuccess;
     const int max_grid = mp3_grid_size(&e);
     if (e != cudaSuccess) return e;
     if (a.n_ctas <= 0 || a.n_ctas > max_grid) return cudaErrorInvalidConfiguration;
-    if (a.multi_tile_groups)
+    if (g_v1_packed_window) {
+        static bool configured = false;
+        if (!configured) {
+            e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(mp3_synth_kernel<kMp3TileGranules, kMp3Warps, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        if (a.multi_tile_groups)
+            mp3_synth_kernel<kMp3TileGranules, kMp3Warps, true, true><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
+        else
+            mp3_synth_kernel<kMp3TileGranules, kMp3Warps, false, true><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
+    } else if (a.multi_tile_groups)
         mp3_synth_kernel<kMp3TileGranules, kMp3Warps, true><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);
     else
         mp3_synth_kernel<kMp3TileGranules, kMp3Warps, false><<<a.n_ctas, kMp3Warps * 32, smem, stream>>>(a);

@@ -71,6 +71,7 @@ struct Mp3Args {
     uint32_t* gen;          // [n_streams] state generation; buffer (gen & 1) is current
     unsigned* done;         // retired-CTA counter (self-resetting)
     const Mp3Tables* tab;
+    float one;              // 1.0f: multiplicand of the packed sums of the window phase (opaque to ptxas)
 };
 
 // MPEG Layer I / II polyphase synthesis (mpa12_synth_kernel): tiles are whole frames of one stream, `n_granules`
@@ -93,6 +94,7 @@ int mpa12_tile_frames(int n_slots); // frames per tile
 
 cudaError_t mp3_upload_const(const Mp3Tables& t, cudaStream_t stream);
 cudaError_t mp3_launch(const Mp3Args& a, cudaStream_t stream);
+void mp3_v1_set_packed_window(bool on); // experiment: channel-pair packed FMUL2 / FFMA2 in the window phase of the first-generation kernel
 int mp3_tile_granules();
 int mp3_halo_tile_granules(); // limit for a tile that recomputes its halo (two warps go to the halo granules)
 int mp3_cta_warps();           // warps per CTA = granule jobs per group

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "ctx.h"
@@ -32,6 +33,7 @@ struct Mp3Plan {
     int n_tiles = 0;
     int n_ctas = 0;
     bool multi = false;       // some group holds more than one tile
+    bool v2 = false;          // laid out for the second-generation kernel: n_ctas counts SHARES (one per warp)
 };
 
 // Cuts the caller's runs into CHAINS of tiles, one chain per CTA of the persistent grid: the batch's
@@ -255,7 +257,22 @@ symgpu_status build_plan_v2_for(int max_shares, uint32_t n_streams, const symgpu
 symgpu_status build_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames, Mp3Plan& plan,
                          bool whole_batch = true) {
     cudaError_t ce = cudaSuccess;
-    if (ctx->mp3_v2) {
+    // Which kernel: the second generation (one warp per share, state in registers) wins where runs are short -- the serving
+    // shape, a frame or two per stream: 164 us against 219 us for 8192 one-frame streams -- the first generation (CTA-wide
+    // tiles of 16 consecutive granules, one halo per CTA chain) with the packed window phase where runs are long: 128 us
+    // against 135 us for 64 streams x 128 frames (profiles/r02_mp3_variants_log.txt).
+    bool v2 = ctx->mp3_kernel_mode == 2;
+    if (ctx->mp3_kernel_mode == 0) {
+        uint64_t gran = 0, n = 0;
+        for (uint32_t r = 0; r < n_runs; ++r)
+            if (runs[r].n_frames) {
+                gran += (uint64_t)runs[r].n_frames * (runs[r].granules_per_frame == 1 ? 1u : 2u);
+                ++n;
+            }
+        v2 = n > 0 && gran < 16 * n; // fewer than 16 granules per run on average
+    }
+    plan.v2 = v2;
+    if (v2) {
         const int n_sm = mp3v2_sm_count(&ce);
         if (ce != cudaSuccess || n_sm <= 0) return cuda_fail(ctx, ce, "mp3v2_sm_count");
         return build_plan_v2_for(n_sm * mp3v2_ctas_per_sm() * mp3v2_cta_warps(), ctx->n_mp3_streams, runs, n_runs, n_frames, plan, whole_batch);
@@ -267,9 +284,9 @@ symgpu_status build_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n
 }
 
 // Launches the Layer III kernel the context is configured for over a plan whose entries sit at `d_plan`.
-cudaError_t launch_plan(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_tiles, int n_ctas, bool multi, const symgpu_mp3_gc* units,
-                        const float* spectra, float* pcm, cudaStream_t stream) {
-    if (ctx->mp3_v2) {
+cudaError_t launch_plan(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_tiles, int n_ctas, bool multi, bool v2,
+                        const symgpu_mp3_gc* units, const float* spectra, float* pcm, cudaStream_t stream) {
+    if (v2) {
         cudaError_t ce = cudaSuccess;
         const int n_sm = mp3v2_sm_count(&ce);
         if (ce != cudaSuccess) return ce;
@@ -281,7 +298,7 @@ cudaError_t launch_plan(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_t
         return mp3v2_launch(a, std::min(n_sm * mp3v2_ctas_per_sm(), n_shares), stream, short_runs);
     }
     const Mp3Args a{units, spectra, pcm, reinterpret_cast<const uint32_t*>(d_plan), d_plan + hdr, n_tiles, n_ctas, multi ? 1 : 0,
-                    ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab};
+                    ctx->d_mp3_states, ctx->d_mp3_gen, ctx->d_mp3_gen + ctx->n_mp3_streams, ctx->d_mp3_tab, 1.0f};
     return mp3_launch(a, stream);
 }
 
@@ -318,6 +335,7 @@ symgpu_status ensure_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t 
     ctx->cached_hdr = plan.hdr;
     ctx->cached_ctas = plan.n_ctas;
     ctx->cached_multi = plan.multi;
+    ctx->cached_v2 = plan.v2;
     return SYMGPU_OK;
 }
 
@@ -486,12 +504,21 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
     symgpu_ctx* ctx = new (std::nothrow) symgpu_ctx();
     if (!ctx) return SYMGPU_ERR_LIMIT;
     ctx->device = device;
+    if (const char* env = std::getenv("SYMGPU_H2D_AHEAD")) { // H2D copies queued before the host's check / planning (tuning)
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= symgpu_ctx::kMaxSlices) ctx->h2d_ahead = v;
+    }
     if (const char* env = std::getenv("SYMGPU_SLICES")) {
         const int v = std::atoi(env);
         if (v >= 1 && v <= symgpu_ctx::kMaxSlices) ctx->n_slices = v;
     }
     // SYMGPU_MP3_KERNEL=v1 selects the first-generation Layer III kernel (mp3_kernel.cu), kept for comparison
-    if (const char* env = std::getenv("SYMGPU_MP3_KERNEL")) ctx->mp3_v2 = std::strcmp(env, "v1") != 0;
+    // SYMGPU_MP3_KERNEL = auto (default) | v1 (first generation, scalar window) | v1p (first generation, packed window) | v2
+    mp3_v1_set_packed_window(true);
+    if (const char* env = std::getenv("SYMGPU_MP3_KERNEL")) {
+        ctx->mp3_kernel_mode = std::strncmp(env, "v1", 2) == 0 ? 1 : std::strcmp(env, "v2") == 0 ? 2 : 0;
+        mp3_v1_set_packed_window(std::strcmp(env, "v1") != 0);
+    }
     if (const char* env = std::getenv("SYMGPU_MP3_V2_VARIANT")) { // "<warps>:<mode>", experiments
         int nw = 0, mode = 0;
         if (std::sscanf(env, "%d:%d", &nw, &mode) != 2 || !mp3v2_set_variant(nw, mode)) {
@@ -601,7 +628,7 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
     symgpu_status s = ensure_plan(ctx, runs, n_runs, n_frames);
     if (s != SYMGPU_OK) return s;
     if (ctx->cached_tiles == 0) return SYMGPU_OK;
-    CU(ctx, launch_plan(ctx, ctx->d_tiles, ctx->cached_hdr, ctx->cached_tiles, ctx->cached_ctas, ctx->cached_multi, units, spectra, pcm,
+    CU(ctx, launch_plan(ctx, ctx->d_tiles, ctx->cached_hdr, ctx->cached_tiles, ctx->cached_ctas, ctx->cached_multi, ctx->cached_v2, units, spectra, pcm,
                         ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;
@@ -621,9 +648,13 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     const size_t sample_bytes = format < 0 ? sizeof(float) : symgpu_sample_bytes(format);
     if (sample_bytes == 0) return SYMGPU_ERR_ARG;
     if (n_frames == 0) return SYMGPU_OK;
-    {
-        const symgpu_status chk = symgpu_mp3_units_check(units, runs, n_runs, n_frames);
-        if (chk != SYMGPU_OK) return chk;
+    // The runs' geometry is checked now (cheap); the 64-byte descriptors of every granule-channel (~200 us of host time
+    // for 8192 frames) are checked while the first H2D copies are already on their way.
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const int gpf = runs[r].granules_per_frame ? runs[r].granules_per_frame : 2;
+        const int n_ch = runs[r].channels ? runs[r].channels : 2;
+        if (gpf < 1 || gpf > 2 || n_ch < 1 || n_ch > 2) return SYMGPU_ERR_ARG;
+        if ((uint64_t)runs[r].first_frame + runs[r].n_frames > n_frames) return SYMGPU_ERR_ARG;
     }
     DeviceGuard guard(ctx->device);
     const size_t unit_bytes = (size_t)n_frames * 4 * sizeof(symgpu_mp3_gc);
@@ -674,8 +705,12 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         // small or unsorted batch: one copy in, one launch, one copy out
         CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, copy_in(0, n_frames, ctx->stream));
-        s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
-        if (s != SYMGPU_OK) return s;
+        s = symgpu_mp3_units_check(units, runs, n_runs, n_frames); // overlaps the copies; nothing has been launched yet
+        if (s == SYMGPU_OK) s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
+        if (s != SYMGPU_OK) {
+            cudaStreamSynchronize(ctx->stream); // the copies read the caller's buffers
+            return s;
+        }
         CU(ctx, pack(0, n_frames));
         CU(ctx, cudaMemcpyAsync(out_bytes, d_result, (size_t)n_frames * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -694,10 +729,8 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         }
     }
     const int n_slices = (int)std::min<uint32_t>((uint32_t)ctx->n_slices, n_runs);
-    struct Slice { uint32_t r0, r1, f0, f1; int t0, hdr, n_tiles, n_ctas; bool multi; };
+    struct Slice { uint32_t r0, r1, f0, f1; int t0, hdr, n_tiles, n_ctas; bool multi, v2; };
     std::vector<Slice> slices;
-    std::vector<Mp3Tile> all_tiles;
-    Mp3Plan plan;
     uint32_t r = 0;
     // Both PCIe directions carry about the same bytes, so the run is as long as the D2H chain, which cannot start
     // before the first slice is in and cannot end before the last slice is out: the slices taper at both ends
@@ -711,43 +744,72 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     for (int i = 0; i < n_slices; ++i) {
         w_acc += weight(i);
         const uint32_t target = (uint32_t)((double)n_frames * (w_acc / w_total));
-        Slice sl{r, r, runs[r].first_frame, 0, (int)all_tiles.size(), 0, 0, 0, false};
+        Slice sl{r, r, runs[r].first_frame, 0, 0, 0, 0, 0, false, false};
         while (r < n_runs && (runs[r].first_frame + runs[r].n_frames <= target || sl.r1 == sl.r0)) {
             ++r;
             sl.r1 = r;
         }
         if (i + 1 == n_slices) { r = n_runs; sl.r1 = n_runs; }
         sl.f1 = sl.r1 < n_runs ? runs[sl.r1].first_frame : n_frames;
+        if (sl.r1 > sl.r0 && sl.f1 > sl.f0) slices.push_back(sl);
+        if (r >= n_runs) break;
+    }
+    // 1. the H2D copies of the first `ahead` slices are queued at once, so that the copy engine has work while the host checks
+    //    the descriptors and plans the launches.  The rest is queued slice by slice BEHIND the D2H copy of an earlier slice:
+    //    queueing every H2D copy up front was measured to serialise the two directions (2.9 ms instead of 2.2 ms per step).
+    const size_t ahead = std::min<size_t>(slices.size(), (size_t)std::max(1, ctx->h2d_ahead));
+    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->copy_in)); // 256 B per frame: one copy
+    for (size_t i = 0; i < ahead; ++i) {
+        CU(ctx, copy_in(slices[i].f0, slices[i].f1 - slices[i].f0, ctx->copy_in));
+        CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
+    }
+    // 2. host work under those copies: descriptor check (a helper thread) and the launch plans of the slices
+    symgpu_status chk = SYMGPU_OK;
+    std::thread checker([&] { chk = symgpu_mp3_units_check(units, runs, n_runs, n_frames); });
+    std::vector<Mp3Tile> all_tiles;
+    Mp3Plan plan;
+    s = SYMGPU_OK;
+    for (size_t i = 0; i < slices.size() && s == SYMGPU_OK; ++i) {
+        Slice& sl = slices[i];
         s = build_plan(ctx, runs + sl.r0, sl.r1 - sl.r0, n_frames, plan, false);
-        if (s != SYMGPU_OK) return s;
+        sl.t0 = (int)all_tiles.size();
         all_tiles.insert(all_tiles.end(), plan.buf.begin(), plan.buf.end());
         sl.hdr = plan.hdr;
         sl.n_tiles = plan.n_tiles;
         sl.n_ctas = plan.n_ctas;
         sl.multi = plan.multi;
-        if (sl.r1 > sl.r0 && sl.n_tiles > 0) slices.push_back(sl);
-        if (r >= n_runs) break;
+        sl.v2 = plan.v2;
     }
-    s = reserve_plan(ctx, all_tiles.size());
-    if (s != SYMGPU_OK) return s;
+    if (s == SYMGPU_OK) s = reserve_plan(ctx, all_tiles.size());
+    checker.join();
+    if (s == SYMGPU_OK) s = chk;
+    if (s != SYMGPU_OK) {
+        cudaStreamSynchronize(ctx->copy_in); // the copies read the caller's buffers; nothing has been launched
+        return s;
+    }
     ctx->cached_runs.clear(); // the cached plan of the device entry point is about to be replaced
     ctx->cached_frames = 0;
     std::memcpy(ctx->h_tiles, all_tiles.data(), all_tiles.size() * sizeof(Mp3Tile));
     CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, all_tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->copy_in)); // 256 B per frame: one copy
+    // 3. kernels as the slices land, D2H copies as the kernels finish, the next H2D copy behind each D2H copy
     for (size_t i = 0; i < slices.size(); ++i) {
         const Slice& sl = slices[i];
         const size_t nf = sl.f1 - sl.f0;
-        CU(ctx, copy_in(sl.f0, nf, ctx->copy_in));
-        CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
-        CU(ctx, launch_plan(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, sl.multi, d_units, d_spec, d_pcm, ctx->stream));
-        ctx->launches += 1;
+        if (sl.n_tiles > 0) {
+            CU(ctx, launch_plan(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, sl.multi, sl.v2, d_units, d_spec, d_pcm, ctx->stream));
+            ctx->launches += 1;
+        }
         CU(ctx, pack(sl.f0, (uint32_t)nf));
         CU(ctx, cudaEventRecord(ctx->ev_k[i], ctx->stream));
         CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
         CU(ctx, cudaMemcpyAsync(out_bytes + (size_t)sl.f0 * frame_out_bytes, d_result + (size_t)sl.f0 * frame_out_bytes,
                                 nf * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (i + ahead < slices.size()) {
+            const Slice& nx = slices[i + ahead];
+            CU(ctx, copy_in(nx.f0, nx.f1 - nx.f0, ctx->copy_in));
+            CU(ctx, cudaEventRecord(ctx->ev_in[i + ahead], ctx->copy_in));
+        }
     }
     CU(ctx, cudaStreamSynchronize(ctx->copy_out));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

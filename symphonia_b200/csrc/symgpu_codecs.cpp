@@ -1,6 +1,7 @@
 // AAC-LC and Vorbis entry points of the C ABI (include/symgpu.h).  Like the MP3 ones they only
 // stage buffers, cut runs into per-CTA chunks and launch CUDA kernels: there is no CPU path.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -214,6 +215,44 @@ symgpu_status symgpu_aac_synth_host(symgpu_ctx* ctx, const symgpu_aac_unit* unit
     return SYMGPU_OK;
 }
 
+// ---- table broadcast over a caller-supplied NCCL communicator (the one collective of this path) -----------
+// libnccl is not a link-time dependency: it is looked up in the process on first use (the host application, which made
+// the communicator, has it loaded already).
+symgpu_status symgpu_tables_broadcast(symgpu_ctx* ctx, void* nccl_comm, int root) {
+    if (!ctx) return SYMGPU_ERR_ARG;
+    if (!nccl_comm) return SYMGPU_OK; // single GPU: the locally built tables stand
+    using BroadcastFn = int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    static BroadcastFn bcast = nullptr;
+    if (!bcast) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) bcast = reinterpret_cast<BroadcastFn>(dlsym(h, "ncclBroadcast"));
+        if (!bcast) {
+            std::snprintf(ctx->cuda_err, sizeof ctx->cuda_err, "symgpu_tables_broadcast: libnccl.so.2 / ncclBroadcast not found");
+            return SYMGPU_ERR_UNSUPPORTED;
+        }
+    }
+    DeviceGuard guard(ctx->device);
+    symgpu_status s = ensure_codec_tables(ctx);
+    if (s != SYMGPU_OK) return s;
+    constexpr int kNcclUint8 = 1; // ncclDataType_t: ncclUint8
+    int rc = bcast(ctx->d_mp3_tab, ctx->d_mp3_tab, sizeof(Mp3Tables), kNcclUint8, root, nccl_comm, ctx->stream);
+    if (rc == 0) rc = bcast(ctx->d_codec_tab, ctx->d_codec_tab, sizeof(CodecTables), kNcclUint8, root, nccl_comm, ctx->stream);
+    if (rc != 0) {
+        std::snprintf(ctx->cuda_err, sizeof ctx->cuda_err, "ncclBroadcast failed with ncclResult_t %d", rc);
+        return SYMGPU_ERR_CUDA;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // the uniformly indexed tables also live in constant memory: refresh them from what arrived
+    std::vector<unsigned char> blob(sizeof(Mp3Tables));
+    CU(ctx, cudaMemcpy(blob.data(), ctx->d_mp3_tab, blob.size(), cudaMemcpyDeviceToHost));
+    alignas(16) static thread_local Mp3Tables host_copy;
+    std::memcpy(&host_copy, blob.data(), sizeof host_copy);
+    CU(ctx, mp3_upload_const(host_copy, ctx->stream));
+    CU(ctx, mp3v2_upload_const(host_copy, ctx->stream));
+    return SYMGPU_OK;
+}
+
 // ---- Vorbis ------------------------------------------------------------------------------------
 
 symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_stream* streams, uint32_t n_streams) {
@@ -249,24 +288,26 @@ symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_str
     return SYMGPU_OK;
 }
 
-symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
-    if (!ctx || !floors || n_floors == 0) return SYMGPU_ERR_ARG;
+// Host-only validation of floor-1 setups (no context needed): what the kernel's level sweep and divisions rely on.  levels (may be
+// null) receives each setup's dependency levels.
+static symgpu_status vorbis_floors_validate(const symgpu_vorbis_floor1* floors, uint32_t n_floors, FloorAux* levels) {
+    if (!floors || n_floors == 0) return SYMGPU_ERR_ARG;
     // A setup is what Floor1Setup holds after the reference's own checks (floor.rs:300-420): distinct x
     // positions, sort_order a permutation by ascending x that starts at x = 0, and for every post >= 2 the
     // nearest lower / higher neighbours among the EARLIER posts.  The kernel divides by x differences and
-    // sweeps the posts by dependency level, so none of this may be taken on trust.
-    std::vector<FloorAux> aux(n_floors);
+    // sweeps the posts by dependency level, so none of this may be taken on trust.  x <= 2^15: rangebits up to 15
+    // are legal (floor.rs:519-536); the seeded division stays exact (numerator < 2^23, divisor < 2^15).
     for (uint32_t i = 0; i < n_floors; ++i) {
         const symgpu_vorbis_floor1& f = floors[i];
         if (f.multiplier < 1 || f.multiplier > 4 || f.n_posts < 2 || f.n_posts > 65) return SYMGPU_ERR_ARG;
         bool seen[65] = {false};
         for (int k = 0; k < f.n_posts; ++k) {
-            if (f.sort_order[k] >= f.n_posts || seen[f.sort_order[k]] || f.x_list[k] > 4096) return SYMGPU_ERR_ARG;
+            if (f.sort_order[k] >= f.n_posts || seen[f.sort_order[k]] || f.x_list[k] > 32768) return SYMGPU_ERR_ARG;
             seen[f.sort_order[k]] = true;
             if (k && f.x_list[f.sort_order[k]] <= f.x_list[f.sort_order[k - 1]]) return SYMGPU_ERR_ARG;
         }
         if (f.x_list[f.sort_order[0]] != 0) return SYMGPU_ERR_ARG;
-        FloorAux& a = aux[i];
+        FloorAux a;
         std::memset(&a, 0, sizeof a);
         for (int k = 2; k < f.n_posts; ++k) {
             const int lo = f.low[k], hi = f.high[k];
@@ -274,6 +315,21 @@ symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floo
             a.level[k] = (uint8_t)(1 + std::max(a.level[lo], a.level[hi]));
             a.max_level = std::max(a.max_level, a.level[k]);
         }
+        if (levels) levels[i] = a;
+    }
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_floors_check(const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
+    return vorbis_floors_validate(floors, n_floors, nullptr);
+}
+
+symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
+    if (!ctx || !floors || n_floors == 0) return SYMGPU_ERR_ARG;
+    std::vector<FloorAux> aux(n_floors);
+    {
+        const symgpu_status chk = vorbis_floors_validate(floors, n_floors, aux.data());
+        if (chk != SYMGPU_OK) return chk;
     }
     DeviceGuard guard(ctx->device);
     CU(ctx, cudaStreamSynchronize(ctx->stream));

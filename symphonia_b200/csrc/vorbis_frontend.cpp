@@ -407,6 +407,19 @@ extern "C" symgpu_status symgpu_vorbis_fe_create(const uint8_t* ident, size_t n_
         if (m.couplings.size() > 1) return SYMGPU_ERR_UNSUPPORTED;
         if (m.couplings.size() == 1 && !(m.couplings[0].first == 0 && m.couplings[0].second == 1)) return SYMGPU_ERR_UNSUPPORTED;
     }
+    // what symgpu_vorbis_floors_set will insist on at launch time is refused here, per stream (a setup whose read X values
+    // repeat an implied end point passes the reference's parser but would divide by zero in its render_line)
+    {
+        std::vector<symgpu_vorbis_floor1> fl(fe->setup.floor1.size());
+        for (size_t i = 0; i < fl.size(); ++i) {
+            const VorbisFloor1Setup& f = fe->setup.floor1[i];
+            std::memset(&fl[i], 0, sizeof fl[i]);
+            fl[i].multiplier = f.multiplier, fl[i].n_posts = f.n_posts;
+            std::memcpy(fl[i].x_list, f.x_list, sizeof fl[i].x_list), std::memcpy(fl[i].low, f.low, 65), std::memcpy(fl[i].high, f.high, 65),
+                std::memcpy(fl[i].sort_order, f.sort_order, 65);
+        }
+        if (!fl.empty() && symgpu_vorbis_floors_check(fl.data(), uint32_t(fl.size())) != SYMGPU_OK) return SYMGPU_ERR_UNSUPPORTED;
+    }
     // one coupling flag per stream record: every mode's mapping must agree
     for (size_t k = 1; k < fe->setup.modes.size(); ++k)
         if (fe->setup.mappings[fe->setup.modes[k].second].couplings.size() != fe->setup.mappings[fe->setup.modes[0].second].couplings.size())
@@ -461,6 +474,7 @@ extern "C" symgpu_status symgpu_vorbis_fe_decode(symgpu_vorbis_fe* fe, const uin
     // behind it unread -- which the reader reports by failing every later read, exactly the reference's behaviour.
     for (int ch = 0; ch < n_ch; ++ch) {
         const uint8_t floor_idx = mapping.submap_floor[mapping.multiplex[ch]];
+        if (uint64_t(floor_base) + floor_idx >= 0xffffu) return SYMGPU_ERR_LIMIT; // unit->floor is 16 bits, 0xffff = unused
         const bool used = read_floor1(*fe, fe->setup.floor1[floor_idx], bs, floor_y + ch * 65);
         unit->do_not_decode[ch] = !used;
         unit->floor[ch] = used ? uint16_t(floor_base + floor_idx) : uint16_t(0xffff);
@@ -514,8 +528,11 @@ extern "C" symgpu_status symgpu_vorbis_fe_decode_packets_jobs(const uint8_t* ide
                                                               size_t n, const symgpu_piece* packets, size_t n_packets, uint32_t slot, uint32_t floor_base,
                                                               symgpu_vorbis_unit* units, uint16_t* floor_y, float* residue, uint32_t* accepted, size_t* n_good,
                                                               uint32_t n_threads) {
+    if (n_good) *n_good = 0;
     if ((!data && n) || (n_packets && (!packets || !units || !floor_y || !residue || !accepted)) || !n_good) return SYMGPU_ERR_ARG;
-    if (n_threads == 0) n_threads = 1;
+    n_threads = std::max<uint32_t>(1, std::min<uint32_t>({n_threads, 64u, std::max(1u, std::thread::hardware_concurrency()),
+                                                           uint32_t(std::min<size_t>(std::max<size_t>(n_packets, 1), 64))}));
+    try { // no C++ exception crosses the ABI (vector / thread creation may throw)
     std::vector<symgpu_vorbis_fe*> fes(n_threads, nullptr);
     symgpu_status st = SYMGPU_OK;
     for (uint32_t t = 0; t < n_threads && st == SYMGPU_OK; ++t) st = symgpu_vorbis_fe_create(ident, n_ident, setup, n_setup, &fes[t]);
@@ -547,4 +564,8 @@ extern "C" symgpu_status symgpu_vorbis_fe_decode_packets_jobs(const uint8_t* ide
     }
     for (symgpu_vorbis_fe* fe : fes) symgpu_vorbis_fe_destroy(fe);
     return st;
+    } catch (...) {
+        *n_good = 0;
+        return SYMGPU_ERR_LIMIT;
+    }
 }

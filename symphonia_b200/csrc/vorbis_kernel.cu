@@ -96,7 +96,9 @@ __device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, cons
         }
     }
     __syncwarp();
+    // step2 flags: posts 0..63 in a 64-bit mask, post 64 (a setup may hold 65 posts, floor.rs:455-560) on its own
     unsigned long long bits = 0ull;
+    bool bit64 = false;
     const int max_level = aux.max_level;
     for (int level = 1; level <= max_level; ++level) {
 #pragma unroll
@@ -108,7 +110,9 @@ __device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, cons
                 int fin = predicted;
                 if (val != 0) {
                     const int room = 2 * (highroom < lowroom ? highroom : lowroom);
-                    bits |= (1ull << plo[k]) | (1ull << phi[k]) | (1ull << (lane + 32 * k));
+                    bits |= (1ull << plo[k]) | (1ull << phi[k]); // neighbours are earlier posts: indices <= 63
+                    if (lane + 32 * k < 64) bits |= 1ull << (lane + 32 * k);
+                    else bit64 = true;
                     if (val >= room) fin = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
                     else fin = (val & 1) ? predicted - ((val + 1) / 2) : predicted + (val / 2);
                 }
@@ -120,6 +124,7 @@ __device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, cons
     const unsigned f_lo = __reduce_or_sync(0xffffffffu, (unsigned)bits) | 3u; // floor_step2_flag[0] = [1] = true
     const unsigned f_hi = __reduce_or_sync(0xffffffffu, (unsigned)(bits >> 32));
     const unsigned long long flag = ((unsigned long long)f_hi << 32) | f_lo;
+    const bool flag64 = __any_sync(0xffffffffu, bit64);
 
     // points in X order: the flagged posts, amplitudes scaled and clamped (floor.rs:631-648)
     int n = 0;
@@ -130,7 +135,7 @@ __device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, cons
         bool on = false;
         if (r < count) {
             i = s.sort_order[r];
-            on = (flag >> i) & 1ull;
+            on = i < 64 ? (bool)((flag >> i) & 1ull) : flag64;
         }
         const unsigned vote = __ballot_sync(0xffffffffu, on);
         if (on) {

@@ -356,7 +356,7 @@ def make_floor1_setup(x_list, multiplier):
 
 
 def vorbis_batch(n_streams=64, packets_per_stream=128, seed=SEED_BASE + 3, bs_exp=(8, 11), channels=2, coupled=True,
-                 unused_prob=0.05):
+                 unused_prob=0.05, posts=None):
     """Vorbis batch with a long/short block mix.
 
     Returns dict(streams, floors, units [P], floor_y [P,2,65], residue [P,2,slot], runs, slot, out_len [P])."""
@@ -372,6 +372,8 @@ def vorbis_batch(n_streams=64, packets_per_stream=128, seed=SEED_BASE + 3, bs_ex
     for flag, n2 in ((0, bs0 // 2), (1, bs1 // 2)):
         for _ in range(4):
             n_posts = int(min(rng.integers(20, 41), n2 // 2))
+            if posts is not None:  # e.g. 65: the largest setup floor.rs:455-560 admits (post 64 needs its own step-2 flag)
+                n_posts = int(min(posts, n2 // 2))
             inner = rng.choice(np.arange(1, n2), size=n_posts - 2, replace=False).tolist()
             rng.shuffle(inner)
             mult = int(rng.choice([1, 2, 2, 2, 3, 4]))

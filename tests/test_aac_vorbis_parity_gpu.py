@@ -124,6 +124,15 @@ def test_vorbis_mixed(engine, oracle):
     _vorbis_case(engine, oracle, 6, 40, seed=201)
 
 
+def test_vorbis_floor_with_65_posts(engine, oracle):
+    """The largest floor-1 setup (floor.rs:455-560): post 64 has a step-2 flag of its own in the kernel (a 64-bit mask cannot hold
+    it); most of its Y values are non-zero here so that the flag matters."""
+    wl, _ = _vorbis_case(engine, oracle, 4, 24, seed=207, posts=65, unused_prob=0.0)
+    assert wl["floors"]["n_posts"].max() == 65            # the long-block setups (a 256-sample block has room for 64 posts)
+    last = wl["floor_y"].reshape(-1, 65)[:, 64]
+    assert (last != 0).mean() > 0.25
+
+
 @pytest.mark.parametrize("bs", [(6, 6), (6, 9), (7, 10), (8, 11), (9, 12), (8, 13), (11, 11)])
 def test_vorbis_block_sizes(engine, oracle, bs):
     _vorbis_case(engine, oracle, 2, 12, seed=210 + bs[0] + 16 * bs[1], bs_exp=bs)

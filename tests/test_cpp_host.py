@@ -66,3 +66,31 @@ def test_sixty_four_decoder_threads_share_one_context(tmp_path, oracle):
     m = re.search(r"batches (\d+) frames (\d+)", res.stdout)
     assert m and int(m.group(2)) == S * F
     assert int(m.group(1)) < S * F, "some launches carried the packets of several decoders: " + res.stdout
+
+
+def _build_nccl():
+    src = os.path.join(ROOT, "tests", "cpp", "nccl_tables.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "nccl_tables")
+    lib = os.path.join(ROOT, "symphonia_b200", "libsymgpu.so")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(lib)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-I/usr/local/cuda/include", "-o", exe, src,
+                               "-L" + os.path.dirname(lib), "-lsymgpu", "-L/usr/local/cuda/lib64", "-lcudart", "-ldl",
+                               "-Wl,-rpath," + os.path.dirname(lib) + ":/usr/local/cuda/lib64"])
+    return exe
+
+
+@pytest.mark.gpu
+def test_native_table_broadcast_over_nccl(tmp_path, oracle):
+    """symgpu_tables_broadcast with a communicator made in C++ (ncclCommInitAll): two ranks when the box has two GPUs -- rank 1
+    starts from zeroed tables and must decode bit-exactly afterwards -- else a 1-rank communicator over the same code path."""
+    from symphonia_b200 import workloads
+    from tests import _oracle
+    F = 10
+    units, spectra, runs = workloads.mp3_batch(1, F, seed=777)
+    rc, want, _ = _oracle.mp3_batch(oracle, units, spectra, runs, 1)
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    inp.write_bytes(b"".join(units[f].tobytes() + spectra[f].tobytes() for f in range(F)))
+    res = subprocess.run([_build_nccl(), str(inp), str(outp)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    got = np.frombuffer(outp.read_bytes(), dtype=np.float32).reshape(F, 2, 1152)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all(), res.stdout
