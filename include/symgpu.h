@@ -308,6 +308,39 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
                                       const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
                                       uint32_t n_packets, uint32_t slot, float* pcm);
 
+/* ---- Vorbis with more than two channels / several coupling steps ------------------------------------------------------ *
+ * The reference maps up to 8 channels (codec-vorbis/src/lib.rs:771-788) and applies every coupling step of the packet's
+ * mapping in order (lib.rs:252-278).  Channels interact ONLY there: afterwards floor * residue, IMDCT and overlap-add are
+ * per channel.  So the multichannel entry points run the inverse coupling of all steps as an element-wise pass over the
+ * residue vectors (in place, on the device) and then synthesise the channel planes two at a time with the stereo kernel
+ * (coupling off).  All per-packet arrays carry `channels` planes: floor_y [n_packets][channels][65], residue / pcm
+ * [n_packets][channels][slot]; `channels` = the largest channel count among the streams of the call (planes a stream does
+ * not have are left alone).  Stream indices of runs refer to symgpu_vorbis_mc_streams_set; a context holds either
+ * classic or multichannel Vorbis streams, not both.  The device variant decouples `residue` in place. */
+#define SYMGPU_VORBIS_MAX_CHANNELS 8
+#define SYMGPU_VORBIS_MAX_COUPLINGS 16
+typedef struct symgpu_vorbis_stream_mc {
+    uint8_t bs0_exp, bs1_exp;  /* identification header                                          */
+    uint8_t channels;          /* 1..8                                                           */
+    uint8_t n_couplings;       /* mapping.couplings.len(), applied in this order                 */
+    uint8_t magnitude_ch[SYMGPU_VORBIS_MAX_COUPLINGS];
+    uint8_t angle_ch[SYMGPU_VORBIS_MAX_COUPLINGS];
+} symgpu_vorbis_stream_mc;
+typedef struct symgpu_vorbis_unit_mc {      /* 32 bytes */
+    uint8_t block_flag, prev_block_flag;
+    uint8_t do_not_decode[SYMGPU_VORBIS_MAX_CHANNELS];
+    uint16_t floor[SYMGPU_VORBIS_MAX_CHANNELS]; /* floor-1 setup per channel, 0xffff = unused */
+    uint8_t reserved[6];
+} symgpu_vorbis_unit_mc;
+symgpu_status symgpu_vorbis_mc_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_stream_mc* streams, uint32_t n_streams);
+symgpu_status symgpu_vorbis_mc_stream_reset(symgpu_ctx* ctx, uint32_t stream);
+symgpu_status symgpu_vorbis_mc_synth_host(symgpu_ctx* ctx, const symgpu_vorbis_unit_mc* units, const uint16_t* floor_y,
+                                          const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
+                                          uint32_t n_packets, uint32_t channels, uint32_t slot, float* pcm);
+symgpu_status symgpu_vorbis_mc_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit_mc* units, const uint16_t* floor_y,
+                                         float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
+                                         uint32_t n_packets, uint32_t channels, uint32_t slot, float* pcm);
+
 /* ===================================================================================================
  * Output stage: planar f32 PCM -> interleaved samples of the caller's format, with
  * the decoder's gapless trim, on the device -- so that the D2H copy carries i16 instead of f32.

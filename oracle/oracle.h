@@ -55,6 +55,13 @@ const float* oracle_aac_window(int kbd, int is_short);
 typedef struct oracle_vorbis_state {
     float overlap[2][4096]; // DspChannel.overlap, bs1/2 <= 4096
 } oracle_vorbis_state;
+typedef struct oracle_vorbis_mc_state {
+    float overlap[SYMGPU_VORBIS_MAX_CHANNELS][4096];
+} oracle_vorbis_mc_state;
+// Same contract as symgpu_vorbis_mc_synth_host: every coupling step of the mapping in order (lib.rs:252-278), up to 8 channels.
+int oracle_vorbis_mc_batch(oracle_vorbis_mc_state* states, const symgpu_vorbis_stream_mc* streams, const symgpu_vorbis_floor1* floors,
+                           const symgpu_vorbis_unit_mc* units, const uint16_t* floor_y, const float* residue, const symgpu_vorbis_run* runs,
+                           uint32_t n_runs, uint32_t channels, uint32_t slot, float* pcm);
 void oracle_vorbis_floor1(const symgpu_vorbis_floor1* setup, const uint16_t* floor_y, uint32_t n, float* floor);
 int oracle_vorbis_batch(oracle_vorbis_state* states, const symgpu_vorbis_stream* streams,
                         const symgpu_vorbis_floor1* floors, const symgpu_vorbis_unit* units, const uint16_t* floor_y,

@@ -254,4 +254,50 @@ int oracle_vorbis_batch(oracle_vorbis_state* states, const symgpu_vorbis_stream*
     for (auto& th : pool) th.join();
     return 0;
 }
+
+// VorbisDecoder::decode_inner from the coupling step on (lib.rs:250-315) for any channel count the reference maps (<= 8,
+// lib.rs:771-788) and any number of coupling steps, which it applies in the order of the mapping (lib.rs:252-278).
+int oracle_vorbis_mc_batch(oracle_vorbis_mc_state* states, const symgpu_vorbis_stream_mc* streams, const symgpu_vorbis_floor1* floors,
+                           const symgpu_vorbis_unit_mc* units, const uint16_t* floor_y, const float* residue, const symgpu_vorbis_run* runs,
+                           uint32_t n_runs, uint32_t channels, uint32_t slot, float* pcm) {
+    std::vector<float> fl[SYMGPU_VORBIS_MAX_CHANNELS], res[SYMGPU_VORBIS_MAX_CHANNELS];
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_vorbis_stream_mc& cfg = streams[runs[r].stream];
+        oracle_vorbis_mc_state& st = states[runs[r].stream];
+        const int bs0 = 1 << cfg.bs0_exp, bs1 = 1 << cfg.bs1_exp;
+        if (cfg.channels > channels || cfg.channels > SYMGPU_VORBIS_MAX_CHANNELS) return 1;
+        for (uint32_t p = runs[r].first_packet; p < runs[r].first_packet + runs[r].n_packets; ++p) {
+            const symgpu_vorbis_unit_mc& u = units[p];
+            const int n = u.block_flag ? bs1 : bs0, n2 = n >> 1;
+            for (int ch = 0; ch < cfg.channels; ++ch) {
+                const size_t plane = (size_t)p * channels + ch;
+                fl[ch].assign(n2, 0.0f);
+                res[ch].assign(residue + plane * slot, residue + plane * slot + n2);
+                if (u.floor[ch] != 0xffff) oracle_vorbis_floor1(&floors[u.floor[ch]], floor_y + plane * 65, (uint32_t)n2, fl[ch].data());
+            }
+            for (int c = 0; c < cfg.n_couplings; ++c) { // lib.rs:252-278
+                std::vector<float>& mag = res[cfg.magnitude_ch[c]];
+                std::vector<float>& ang = res[cfg.angle_ch[c]];
+                for (int i = 0; i < n2; ++i) {
+                    const float m = mag[i], a = ang[i];
+                    float nm, na;
+                    if (m > 0.0f) {
+                        if (a > 0.0f) { nm = m; na = m - a; } else { nm = m + a; na = m; }
+                    } else {
+                        if (a > 0.0f) { nm = m; na = m + a; } else { nm = m - a; na = m; }
+                    }
+                    mag[i] = nm;
+                    ang[i] = na;
+                }
+            }
+            for (int ch = 0; ch < cfg.channels; ++ch) { // lib.rs:282-292
+                if (u.do_not_decode[ch]) continue;
+                for (int i = 0; i < n2; ++i) fl[ch][i] *= res[ch][i];
+            }
+            for (int ch = 0; ch < cfg.channels; ++ch)
+                channel_synth(fl[ch].data(), st.overlap[ch], bs0, bs1, u.block_flag, u.prev_block_flag, pcm + ((size_t)p * channels + ch) * slot);
+        }
+    }
+    return 0;
+}
 }

@@ -58,6 +58,11 @@ VORBIS_UNIT_DTYPE = np.dtype([("block_flag", "u1"), ("prev_block_flag", "u1"), (
                               ("floor", "<u2", (2,)), ("reserved", "u1", (8,))])
 VORBIS_RUN_DTYPE = np.dtype([("stream", "<u4"), ("first_packet", "<u4"), ("n_packets", "<u4"), ("reserved", "<u4")])
 assert AAC_UNIT_DTYPE.itemsize == 16 and AAC_TNS_DTYPE.itemsize == 88 and AAC_RUN_DTYPE.itemsize == 16
+VORBIS_STREAM_MC_DTYPE = np.dtype([("bs0_exp", "u1"), ("bs1_exp", "u1"), ("channels", "u1"), ("n_couplings", "u1"),
+                                   ("magnitude_ch", "u1", (16,)), ("angle_ch", "u1", (16,))])
+VORBIS_UNIT_MC_DTYPE = np.dtype([("block_flag", "u1"), ("prev_block_flag", "u1"), ("do_not_decode", "u1", (8,)), ("floor", "<u2", (8,)),
+                                 ("reserved", "u1", (6,))])
+assert VORBIS_STREAM_MC_DTYPE.itemsize == 36 and VORBIS_UNIT_MC_DTYPE.itemsize == 32
 assert VORBIS_FLOOR1_DTYPE.itemsize == 332 and VORBIS_STREAM_DTYPE.itemsize == 4
 assert VORBIS_UNIT_DTYPE.itemsize == 16 and VORBIS_RUN_DTYPE.itemsize == 16
 # `symgpu_pcm_span`, 32 bytes; sample formats of the output stage
@@ -166,6 +171,12 @@ def lib():
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, vp]
+    L.symgpu_vorbis_mc_streams_set.restype = ctypes.c_int
+    L.symgpu_vorbis_mc_streams_set.argtypes = [vp, vp, u32]
+    for name in ("symgpu_vorbis_mc_synth_host", "symgpu_vorbis_mc_synth_dev"):
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, u32, vp]
     L.symgpu_sample_bytes.restype = sz
     L.symgpu_sample_bytes.argtypes = [ctypes.c_int]
     L.symgpu_pcm_pack_dev.restype = ctypes.c_int

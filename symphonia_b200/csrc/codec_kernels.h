@@ -64,6 +64,8 @@ struct VorbisArgs {
     const FloorAux* floor_aux;
     uint32_t n_floors;
     uint32_t slot;              // floats per channel slot in residue / pcm
+    uint32_t pkt_ch;            // channel planes per packet in floor_y / residue / pcm: 2, or C for the multichannel entry points
+    uint32_t ch_base;           // first of the (at most two) planes this launch works on
     float* states;              // [n_streams][2 generations][kVorbisStateFloats]
     uint32_t* gen;
     unsigned* done;
@@ -72,6 +74,12 @@ struct VorbisArgs {
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, cudaStream_t stream);
 cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream);
+// Multichannel helpers (symgpu_vorbis_mc_*): inverse coupling over every step of a mapping (lib.rs:252-278), in place on
+// residue [n_packets][channels][slot]; and the (block flags, floor, do-not-decode) records of channel pair `pair`.
+cudaError_t vorbis_mc_decouple_launch(const symgpu_vorbis_unit_mc* units, const uint32_t* stream_of_packet, const symgpu_vorbis_stream_mc* streams,
+                                      float* residue, uint32_t n_packets, uint32_t channels, uint32_t slot, cudaStream_t stream);
+cudaError_t vorbis_mc_split_units_launch(const symgpu_vorbis_unit_mc* units, uint32_t n_packets, uint32_t pair, symgpu_vorbis_unit* out,
+                                         cudaStream_t stream);
 // Packet slots per CTA (chunk packets + 1) for a batch whose largest blocksize_1 is 2^max_bs1_exp.
 int vorbis_slots_for(int max_bs1_exp);
 

@@ -44,6 +44,9 @@ struct symgpu_ctx {
     size_t stage_cap = 0;
     // copy pipeline of the host entry points: H2D on copy_in, kernels on `stream`, D2H on copy_out
     static constexpr int kMaxSlices = 32;
+    // pinned (device-mapped) host buffers go straight to the kernels: 0 never, 1 output only (PCM stores cross PCIe from the
+    // kernel, no D2H copy), 2 input too (TMA reads across PCIe; measured slower than staged H2D).  SYMGPU_ZERO_COPY
+    int zero_copy = 1;
     int h2d_ahead = 2; // slices whose H2D copy is queued before the host's descriptor check and planning (SYMGPU_H2D_AHEAD)
     int n_slices = 8; // slices of a host batch in the copy pipeline (SYMGPU_SLICES overrides, for tuning)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -71,6 +74,12 @@ struct symgpu_ctx {
     float* d_vorbis_states = nullptr; // [n][2 gen][kVorbisStateFloats]
     uint32_t* d_vorbis_gen = nullptr;
     uint32_t n_vorbis_streams = 0;
+    // multichannel Vorbis (symgpu_vorbis_mc_*): the caller's stream records; every one is registered as 4 stereo pseudo-streams
+    symgpu_vorbis_stream_mc* d_vorbis_mc_streams = nullptr;
+    std::vector<symgpu_vorbis_stream_mc> h_vorbis_mc_streams;
+    uint32_t n_vorbis_mc_streams = 0;
+    void* d_vorbis_mc_scratch = nullptr; // per-pair unit records + stream of every packet
+    size_t vorbis_mc_scratch_cap = 0;
     uint32_t vorbis_cfg_epoch = 0;   // bumped by streams_set: chunk sizes depend on the stream block sizes
 };
 

@@ -504,6 +504,8 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
     symgpu_ctx* ctx = new (std::nothrow) symgpu_ctx();
     if (!ctx) return SYMGPU_ERR_LIMIT;
     ctx->device = device;
+    // SYMGPU_ZERO_COPY = 0 never | 1 output only (default) | 2 input and output
+    if (const char* env = std::getenv("SYMGPU_ZERO_COPY")) ctx->zero_copy = env[0] == '0' ? 0 : env[0] == '2' ? 2 : 1;
     if (const char* env = std::getenv("SYMGPU_H2D_AHEAD")) { // H2D copies queued before the host's check / planning (tuning)
         const int v = std::atoi(env);
         if (v >= 1 && v <= symgpu_ctx::kMaxSlices) ctx->h2d_ahead = v;
@@ -572,6 +574,8 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (ctx->d_vorbis_floor_aux) cudaFree(ctx->d_vorbis_floor_aux);
     if (ctx->d_vorbis_states) cudaFree(ctx->d_vorbis_states);
     if (ctx->d_vorbis_gen) cudaFree(ctx->d_vorbis_gen);
+    if (ctx->d_vorbis_mc_streams) cudaFree(ctx->d_vorbis_mc_streams);
+    if (ctx->d_vorbis_mc_scratch) cudaFree(ctx->d_vorbis_mc_scratch);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     for (int i = 0; i < symgpu_ctx::kMaxSlices; ++i) {
@@ -659,6 +663,53 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     DeviceGuard guard(ctx->device);
     const size_t unit_bytes = (size_t)n_frames * 4 * sizeof(symgpu_mp3_gc);
     const size_t spec_bytes = (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sizeof(float);
+    // ---- zero-copy: pinned, device-mapped host buffers are read and written by the kernel itself --------------------------------
+    // When `units`, `spectra` and `out` are pinned host memory (cudaHostAlloc / cudaHostRegister: device-accessible under unified
+    // addressing), the synthesis kernel takes them as they are: its TMA bulk copies pull the next granule's spectra across PCIe
+    // one granule (or tile) ahead of the arithmetic and its coalesced 128-byte PCM stores go straight to host memory.  H2D
+    // traffic, arithmetic and D2H traffic overlap inside ONE launch -- no staging copy, no slice pipeline, no copy-engine
+    // scheduling between them -- and the step takes as long as the slower PCIe direction.  SYMGPU_ZERO_COPY=0 switches it off.
+    if (ctx->zero_copy == 2 && !quant && format < 0) {
+        bool whole = true;
+        for (uint32_t r = 0; r < n_runs; ++r) whole &= runs[r].granules_per_frame != 1 && runs[r].channels != 1;
+        auto mapped = [](const void* p) -> void* {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+                cudaGetLastError(); // pageable memory on older drivers: clear the error
+                return nullptr;
+            }
+            return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+        };
+        void* d_u = whole ? mapped(units) : nullptr;
+        void* d_s = d_u ? mapped(spectra) : nullptr;
+        void* d_o = d_s ? mapped(out) : nullptr;
+        if (d_o) {
+            // descriptors are checked before anything runs on them (four host threads: ~50 us for 8192 frames)
+            symgpu_status chk[4] = {SYMGPU_OK, SYMGPU_OK, SYMGPU_OK, SYMGPU_OK};
+            {
+                std::thread workers[3];
+                const uint32_t per = (n_runs + 3) / 4;
+                auto part = [&](int k) {
+                    const uint32_t r0 = std::min<uint32_t>(n_runs, per * (uint32_t)k), r1 = std::min<uint32_t>(n_runs, r0 + per);
+                    if (r1 > r0) chk[k] = symgpu_mp3_units_check(units, runs + r0, r1 - r0, n_frames);
+                };
+                const bool threaded = n_frames >= 1024;
+                for (int k = 1; k < 4; ++k)
+                    if (threaded) workers[k - 1] = std::thread(part, k);
+                    else part(k);
+                part(0);
+                for (auto& w : workers)
+                    if (w.joinable()) w.join();
+            }
+            for (symgpu_status c : chk)
+                if (c != SYMGPU_OK) return c;
+            symgpu_status zs = symgpu_mp3_synth_dev(ctx, static_cast<const symgpu_mp3_gc*>(d_u), static_cast<const float*>(d_s), runs, n_runs,
+                                                    n_frames, static_cast<float*>(d_o));
+            if (zs != SYMGPU_OK) return zs;
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            return SYMGPU_OK;
+        }
+    }
     const size_t packed_bytes = format < 0 ? 0 : (size_t)n_frames * SYMGPU_MP3_FRAME_FLOATS * sample_bytes;
     const size_t quant_bytes = quant ? spec_bytes / 2 : 0;
     symgpu_status s = ensure_stage(ctx, unit_bytes + 2 * spec_bytes + packed_bytes + quant_bytes);
@@ -700,6 +751,18 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     sorted &= next == n_frames;
     if (partial && format >= 0) return SYMGPU_ERR_UNSUPPORTED;
     if (partial) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
+    // Output zero-copy: a pinned (device-mapped) f32 output buffer is written by the kernels themselves -- coalesced 128-byte
+    // PCM stores that cross PCIe while the next slice is still coming in -- so the D2H copies and their scheduling disappear.
+    bool out_mapped = false;
+    if (ctx->zero_copy && format < 0 && !partial) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            d_pcm = static_cast<float*>(at.devicePointer);
+            out_mapped = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
 
     if (!sorted || n_frames < 512 || n_runs < 2) {
         // small or unsorted batch: one copy in, one launch, one copy out
@@ -712,7 +775,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
             return s;
         }
         CU(ctx, pack(0, n_frames));
-        CU(ctx, cudaMemcpyAsync(out_bytes, d_result, (size_t)n_frames * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!out_mapped) CU(ctx, cudaMemcpyAsync(out_bytes, d_result, (size_t)n_frames * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         return SYMGPU_OK;
     }
@@ -757,7 +820,8 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     // 1. the H2D copies of the first `ahead` slices are queued at once, so that the copy engine has work while the host checks
     //    the descriptors and plans the launches.  The rest is queued slice by slice BEHIND the D2H copy of an earlier slice:
     //    queueing every H2D copy up front was measured to serialise the two directions (2.9 ms instead of 2.2 ms per step).
-    const size_t ahead = std::min<size_t>(slices.size(), (size_t)std::max(1, ctx->h2d_ahead));
+    // (with the output written by the kernels there are no D2H copies to interleave with: everything is queued at once)
+    const size_t ahead = out_mapped ? slices.size() : std::min<size_t>(slices.size(), (size_t)std::max(1, ctx->h2d_ahead));
     CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->copy_in)); // 256 B per frame: one copy
     for (size_t i = 0; i < ahead; ++i) {
         CU(ctx, copy_in(slices[i].f0, slices[i].f1 - slices[i].f0, ctx->copy_in));
@@ -801,10 +865,12 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
             ctx->launches += 1;
         }
         CU(ctx, pack(sl.f0, (uint32_t)nf));
-        CU(ctx, cudaEventRecord(ctx->ev_k[i], ctx->stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
-        CU(ctx, cudaMemcpyAsync(out_bytes + (size_t)sl.f0 * frame_out_bytes, d_result + (size_t)sl.f0 * frame_out_bytes,
-                                nf * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (!out_mapped) {
+            CU(ctx, cudaEventRecord(ctx->ev_k[i], ctx->stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
+            CU(ctx, cudaMemcpyAsync(out_bytes + (size_t)sl.f0 * frame_out_bytes, d_result + (size_t)sl.f0 * frame_out_bytes,
+                                    nf * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
         if (i + ahead < slices.size()) {
             const Slice& nx = slices[i + ahead];
             CU(ctx, copy_in(nx.f0, nx.f1 - nx.f0, ctx->copy_in));

@@ -208,9 +208,19 @@ symgpu_status symgpu_aac_synth_host(symgpu_ctx* ctx, const symgpu_aac_unit* unit
         covered += runs[r].n_frames;
     }
     if (mono || covered != n_frames) CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream));
-    s = symgpu_aac_synth_dev(ctx, d_units, d_tns, n_tns, d_spec, runs, n_runs, n_frames, d_pcm);
+    // A pinned (device-mapped) output buffer is written by the kernel itself: its PCM stores cross PCIe while it is still
+    // computing, and the D2H copy disappears (every plane is written when no stream is mono and the runs cover the batch).
+    float* d_out = d_pcm;
+    if (ctx->zero_copy && !mono && covered == n_frames) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, pcm) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            d_out = static_cast<float*>(at.devicePointer);
+        else
+            cudaGetLastError();
+    }
+    s = symgpu_aac_synth_dev(ctx, d_units, d_tns, n_tns, d_spec, runs, n_runs, n_frames, d_out);
     if (s != SYMGPU_OK) return s;
-    CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_out == d_pcm) CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SYMGPU_OK;
 }
@@ -282,6 +292,7 @@ symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_str
     CU(ctx, cudaMalloc(&ctx->d_vorbis_gen, ((size_t)n_streams + 1) * sizeof(uint32_t)));
     CU(ctx, cudaMemset(ctx->d_vorbis_gen, 0, ((size_t)n_streams + 1) * sizeof(uint32_t)));
     ctx->h_vorbis_streams.assign(streams, streams + n_streams);
+    ctx->n_vorbis_mc_streams = 0; // (symgpu_vorbis_mc_streams_set sets it again after this call)
     ctx->vorbis_cfg_epoch = (ctx->vorbis_cfg_epoch + 1) & 0xffu;
     ctx->chunk_key.clear();
     ctx->n_vorbis_streams = n_streams;
@@ -355,9 +366,11 @@ symgpu_status symgpu_vorbis_stream_reset(symgpu_ctx* ctx, uint32_t stream) {
     return SYMGPU_OK;
 }
 
-symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit* units, const uint16_t* floor_y,
-                                      const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
-                                      uint32_t n_packets, uint32_t slot, float* pcm) {
+// The Vorbis launch behind the classic and the multichannel entry points: planes [p][pkt_ch][...] of which this launch works on
+// ch_base, ch_base + 1; run.stream s stands for registered stream s * stream_mul + stream_add.
+static symgpu_status vorbis_synth_dev_impl(symgpu_ctx* ctx, const symgpu_vorbis_unit* units, const uint16_t* floor_y, const float* residue,
+                                           const symgpu_vorbis_run* runs, uint32_t n_runs, uint32_t n_packets, uint32_t slot, float* pcm,
+                                           uint32_t pkt_ch, uint32_t ch_base, uint32_t stream_mul, uint32_t stream_add) {
     if (!ctx || !units || !floor_y || !residue || !runs || !pcm) return SYMGPU_ERR_ARG;
     if (n_packets == 0) return SYMGPU_OK;
     if (!ctx->d_vorbis_states || !ctx->d_vorbis_floors) return SYMGPU_ERR_LIMIT;
@@ -365,24 +378,26 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
     std::vector<CodecChunk> chunks;
     uint64_t covered = 0;
     int max_bs1 = 6;
+    auto reg = [&](uint32_t s) { return (uint64_t)s * stream_mul + stream_add; };
     for (uint32_t r = 0; r < n_runs; ++r)
-        if (runs[r].n_packets && runs[r].stream < ctx->n_vorbis_streams)
-            max_bs1 = std::max(max_bs1, (int)ctx->h_vorbis_streams[runs[r].stream].bs1_exp);
+        if (runs[r].n_packets && reg(runs[r].stream) < ctx->n_vorbis_streams)
+            max_bs1 = std::max(max_bs1, (int)ctx->h_vorbis_streams[reg(runs[r].stream)].bs1_exp);
     const uint32_t per_chunk = (uint32_t)vorbis_slots_for(max_bs1) - 1; // one slot is the packet before the chunk
-    const std::vector<unsigned char> key = chunk_key_of(0x564f5200u + ctx->vorbis_cfg_epoch, n_packets, slot, runs, (size_t)n_runs * sizeof *runs);
+    const std::vector<unsigned char> key = chunk_key_of(0x564f5200u + ctx->vorbis_cfg_epoch + (stream_add << 8) + (stream_mul << 12), n_packets, slot, runs,
+                                                        (size_t)n_runs * sizeof *runs);
     const bool reuse = key == ctx->chunk_key;
     for (uint32_t r = 0; r < n_runs && !reuse; ++r) {
         const symgpu_vorbis_run& run = runs[r];
         if (run.n_packets == 0) continue;
         if ((uint64_t)run.first_packet + run.n_packets > n_packets || run.reserved) return SYMGPU_ERR_ARG;
-        if (run.stream >= ctx->n_vorbis_streams) return SYMGPU_ERR_LIMIT;
-        const symgpu_vorbis_stream& cfg = ctx->h_vorbis_streams[run.stream];
+        if (reg(run.stream) >= ctx->n_vorbis_streams) return SYMGPU_ERR_LIMIT;
+        const symgpu_vorbis_stream& cfg = ctx->h_vorbis_streams[reg(run.stream)];
         if ((1u << (cfg.bs1_exp - 1)) > slot) return SYMGPU_ERR_ARG; // slot too small for this stream
         covered += run.n_packets;
         split_even(run.n_packets, per_chunk, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
             CodecChunk c{};
             c.first = run.first_packet + lo;
-            c.stream = run.stream;
+            c.stream = (uint32_t)reg(run.stream);
             c.count = (uint16_t)(hi - lo);
             c.flags = (uint8_t)((first ? kChunkLoadState : 0) | (last ? kChunkStoreState : 0));
             chunks.push_back(c);
@@ -396,11 +411,137 @@ symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit*
         ctx->chunk_key = key;
         ctx->cached_chunks = (int)chunks.size();
     }
+    if (ctx->cached_chunks == 0) return SYMGPU_OK;
     VorbisArgs a{units, floor_y, residue, pcm, ctx->d_chunks, ctx->d_vorbis_streams, ctx->d_vorbis_floors,
-                 ctx->d_vorbis_floor_aux, ctx->n_vorbis_floors, slot, ctx->d_vorbis_states, ctx->d_vorbis_gen,
+                 ctx->d_vorbis_floor_aux, ctx->n_vorbis_floors, slot, pkt_ch, ch_base, ctx->d_vorbis_states, ctx->d_vorbis_gen,
                  ctx->d_vorbis_gen + ctx->n_vorbis_streams, ctx->d_codec_tab};
     CU(ctx, vorbis_launch(a, ctx->cached_chunks, max_bs1, ctx->stream));
     ctx->launches += 1;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit* units, const uint16_t* floor_y,
+                                      const float* residue, const symgpu_vorbis_run* runs, uint32_t n_runs,
+                                      uint32_t n_packets, uint32_t slot, float* pcm) {
+    if (ctx && ctx->n_vorbis_mc_streams) return SYMGPU_ERR_ARG; // the context holds multichannel streams
+    return vorbis_synth_dev_impl(ctx, units, floor_y, residue, runs, n_runs, n_packets, slot, pcm, 2, 0, 1, 0);
+}
+
+// ---- multichannel (symgpu_vorbis_mc_*) ---------------------------------------------------------------------------------
+static constexpr uint32_t kMcPairs = SYMGPU_VORBIS_MAX_CHANNELS / 2; // registered pseudo-streams per multichannel stream
+
+symgpu_status symgpu_vorbis_mc_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_stream_mc* streams, uint32_t n_streams) {
+    if (!ctx || !streams || n_streams == 0) return SYMGPU_ERR_ARG;
+    std::vector<symgpu_vorbis_stream> pseudo((size_t)n_streams * kMcPairs);
+    for (uint32_t i = 0; i < n_streams; ++i) {
+        const symgpu_vorbis_stream_mc& m = streams[i];
+        if (m.channels < 1 || m.channels > SYMGPU_VORBIS_MAX_CHANNELS) return SYMGPU_ERR_UNSUPPORTED;
+        if (m.n_couplings > SYMGPU_VORBIS_MAX_COUPLINGS) return SYMGPU_ERR_UNSUPPORTED;
+        for (int c = 0; c < m.n_couplings; ++c) // lib.rs:741-752: distinct channels inside the stream
+            if (m.magnitude_ch[c] == m.angle_ch[c] || m.magnitude_ch[c] >= m.channels || m.angle_ch[c] >= m.channels) return SYMGPU_ERR_ARG;
+        for (uint32_t k = 0; k < kMcPairs; ++k) {
+            const int left = (int)m.channels - 2 * (int)k;
+            // pairs beyond the stream's channels are placeholders no run ever names
+            pseudo[(size_t)i * kMcPairs + k] = symgpu_vorbis_stream{m.bs0_exp, m.bs1_exp, (uint8_t)(left >= 2 ? 2 : 1), 0};
+        }
+    }
+    symgpu_status s = symgpu_vorbis_streams_set(ctx, pseudo.data(), (uint32_t)pseudo.size());
+    if (s != SYMGPU_OK) return s;
+    DeviceGuard guard(ctx->device);
+    if (ctx->d_vorbis_mc_streams) cudaFree(ctx->d_vorbis_mc_streams);
+    ctx->d_vorbis_mc_streams = nullptr;
+    CU(ctx, cudaMalloc(&ctx->d_vorbis_mc_streams, (size_t)n_streams * sizeof *streams));
+    CU(ctx, cudaMemcpy(ctx->d_vorbis_mc_streams, streams, (size_t)n_streams * sizeof *streams, cudaMemcpyHostToDevice));
+    ctx->h_vorbis_mc_streams.assign(streams, streams + n_streams);
+    ctx->n_vorbis_mc_streams = n_streams;
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_mc_stream_reset(symgpu_ctx* ctx, uint32_t stream) {
+    if (!ctx) return SYMGPU_ERR_ARG;
+    if (stream >= ctx->n_vorbis_mc_streams) return SYMGPU_ERR_LIMIT;
+    for (uint32_t k = 0; k < kMcPairs; ++k) {
+        const symgpu_status s = symgpu_vorbis_stream_reset(ctx, stream * kMcPairs + k);
+        if (s != SYMGPU_OK) return s;
+    }
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_mc_synth_dev(symgpu_ctx* ctx, const symgpu_vorbis_unit_mc* units, const uint16_t* floor_y, float* residue,
+                                         const symgpu_vorbis_run* runs, uint32_t n_runs, uint32_t n_packets, uint32_t channels, uint32_t slot,
+                                         float* pcm) {
+    if (!ctx || !units || !floor_y || !residue || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (channels < 1 || channels > SYMGPU_VORBIS_MAX_CHANNELS) return SYMGPU_ERR_ARG;
+    if (n_packets == 0) return SYMGPU_OK;
+    if (!ctx->n_vorbis_mc_streams) return SYMGPU_ERR_LIMIT;
+    DeviceGuard guard(ctx->device);
+    // which stream a packet belongs to (0xffffffff: no run names it), and the channel pairs in use
+    std::vector<uint32_t> stream_of((size_t)n_packets, 0xffffffffu);
+    uint32_t max_ch = 0;
+    for (uint32_t r = 0; r < n_runs; ++r) {
+        const symgpu_vorbis_run& run = runs[r];
+        if (run.n_packets == 0) continue;
+        if ((uint64_t)run.first_packet + run.n_packets > n_packets || run.reserved) return SYMGPU_ERR_ARG;
+        if (run.stream >= ctx->n_vorbis_mc_streams) return SYMGPU_ERR_LIMIT;
+        if (ctx->h_vorbis_mc_streams[run.stream].channels > channels) return SYMGPU_ERR_ARG;
+        max_ch = std::max<uint32_t>(max_ch, ctx->h_vorbis_mc_streams[run.stream].channels);
+        for (uint32_t p = run.first_packet; p < run.first_packet + run.n_packets; ++p) stream_of[p] = run.stream;
+    }
+    const size_t need = (size_t)n_packets * (sizeof(uint32_t) + sizeof(symgpu_vorbis_unit));
+    if (need > ctx->vorbis_mc_scratch_cap) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_vorbis_mc_scratch) cudaFree(ctx->d_vorbis_mc_scratch);
+        ctx->d_vorbis_mc_scratch = nullptr;
+        ctx->vorbis_mc_scratch_cap = 0;
+        CU(ctx, cudaMalloc(&ctx->d_vorbis_mc_scratch, need + need / 2));
+        ctx->vorbis_mc_scratch_cap = need + need / 2;
+    }
+    symgpu_vorbis_unit* d_pair_units = static_cast<symgpu_vorbis_unit*>(ctx->d_vorbis_mc_scratch);
+    uint32_t* d_stream_of = reinterpret_cast<uint32_t*>(d_pair_units + n_packets);
+    CU(ctx, cudaMemcpyAsync(d_stream_of, stream_of.data(), (size_t)n_packets * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // stream_of is a local vector
+    CU(ctx, vorbis_mc_decouple_launch(units, d_stream_of, ctx->d_vorbis_mc_streams, residue, n_packets, channels, slot, ctx->stream));
+    ctx->launches += 1;
+    for (uint32_t k = 0; 2 * k < max_ch; ++k) {
+        // the runs of this pair: streams that have the pair's first channel
+        std::vector<symgpu_vorbis_run> pr;
+        for (uint32_t r = 0; r < n_runs; ++r)
+            if (runs[r].n_packets && ctx->h_vorbis_mc_streams[runs[r].stream].channels > 2 * k) pr.push_back(runs[r]);
+        if (pr.empty()) continue;
+        CU(ctx, vorbis_mc_split_units_launch(units, n_packets, k, d_pair_units, ctx->stream));
+        ctx->launches += 1;
+        const symgpu_status s = vorbis_synth_dev_impl(ctx, d_pair_units, floor_y, residue, pr.data(), (uint32_t)pr.size(), n_packets, slot, pcm, channels,
+                                                      2 * k, kMcPairs, k);
+        if (s != SYMGPU_OK) return s;
+    }
+    return SYMGPU_OK;
+}
+
+symgpu_status symgpu_vorbis_mc_synth_host(symgpu_ctx* ctx, const symgpu_vorbis_unit_mc* units, const uint16_t* floor_y, const float* residue,
+                                          const symgpu_vorbis_run* runs, uint32_t n_runs, uint32_t n_packets, uint32_t channels, uint32_t slot,
+                                          float* pcm) {
+    if (!ctx || !units || !floor_y || !residue || !runs || !pcm) return SYMGPU_ERR_ARG;
+    if (channels < 1 || channels > SYMGPU_VORBIS_MAX_CHANNELS) return SYMGPU_ERR_ARG;
+    if (n_packets == 0) return SYMGPU_OK;
+    DeviceGuard guard(ctx->device);
+    const size_t unit_bytes = (size_t)n_packets * sizeof(symgpu_vorbis_unit_mc);
+    const size_t fy_bytes = ((size_t)n_packets * channels * 65 * sizeof(uint16_t) + 15) & ~(size_t)15;
+    const size_t spec_bytes = (size_t)n_packets * channels * slot * sizeof(float);
+    symgpu_status s = ensure_stage(ctx, 2 * spec_bytes + unit_bytes + fy_bytes);
+    if (s != SYMGPU_OK) return s;
+    char* base = static_cast<char*>(ctx->d_stage);
+    float* d_res = reinterpret_cast<float*>(base);
+    float* d_pcm = reinterpret_cast<float*>(base + spec_bytes);
+    symgpu_vorbis_unit_mc* d_units = reinterpret_cast<symgpu_vorbis_unit_mc*>(base + 2 * spec_bytes);
+    uint16_t* d_fy = reinterpret_cast<uint16_t*>(base + 2 * spec_bytes + unit_bytes);
+    CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_fy, floor_y, (size_t)n_packets * channels * 65 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_res, residue, spec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_pcm, 0, spec_bytes, ctx->stream)); // packets fill only (prev_n + n) / 4 of their slot
+    s = symgpu_vorbis_mc_synth_dev(ctx, d_units, d_fy, d_res, runs, n_runs, n_packets, channels, slot, d_pcm);
+    if (s != SYMGPU_OK) return s;
+    CU(ctx, cudaMemcpyAsync(pcm, d_pcm, spec_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SYMGPU_OK;
 }
 

@@ -176,26 +176,54 @@ __device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, cons
     __syncwarp();
 }
 
-// Renders the curve for lines x = lane, lane + 32, ... < n_half: each lane walks the segments in ascending x
-// (floor.rs:785-825 in closed form: after d steps of render_line's error accumulator,
-// y(d) = y0 + d*base + sign(dy) * floor(d*ady / adx)).
-__device__ __forceinline__ void floor1_render(const FloorPoints& p, int n_half, int lane, float* spec,
-                                              const float* __restrict__ inv_db) {
-    int seg = 0;
-    int x1 = p.seg[1].x0, x2 = p.seg[2].x0; // the boundary after next is fetched ahead of its use
-    for (int x = lane; x < n_half; x += 32) {
-        while (x >= x1) { // at most 66 advances per lane in total
+// Index of line x in a channel's curve buffer (one byte per line: the floor1_inverse_dB_table index): lane l of the rendering warp
+// owns the L = n_half / 32 consecutive lines [l * L, (l + 1) * L); four pad bytes per lane-run put the lanes on distinct banks.
+__device__ __forceinline__ int ybuf_index(int x, int log2_l) { return log2_l >= 2 ? x + ((x >> log2_l) << 2) : x; }
+
+// Renders the curve (floor.rs:785-825) as table indices: every lane walks ITS run of consecutive lines with render_line's own
+// error accumulator -- y += base; err += ady; on err >= adx: err -= adx, y += sign(dy) -- entered in the middle of a segment
+// through the closed form  y(d) = y0 + d * base + sign(dy) * floor(d * ady / adx),  err(d) = d * ady mod adx  (one exact
+// division per lane instead of one per line).
+__device__ __forceinline__ void floor1_render(const FloorPoints& p, int n_half, int lane, uint8_t* ybuf) {
+    const int log2_l = 31 - __clz(n_half >> 5);
+    const int len = 1 << log2_l;
+    int x = lane << log2_l;
+    // the segment that holds x: the last one whose x0 <= x (seg[0].x0 = 0; a sentinel ends the list)
+    int lo = 0, hi = p.n - 1; // p.n points: segments 0 .. n - 2, the sentinel behind them
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.seg[mid].x0 <= x) lo = mid;
+        else hi = mid - 1;
+    }
+    int seg = lo;
+    int4 w = *reinterpret_cast<const int4*>(&p.seg[seg]);
+    int x1 = p.seg[seg + 1].x0;
+    int base = w.y >> 16, ady = (int)(short)(w.z & 0xffff), adx_s = w.z >> 16;
+    int adx = abs(adx_s), sgn = adx_s < 0 ? -1 : 1;
+    const int d = x - w.x;
+    const int carries = ady ? div_seeded(d * ady, adx, __int_as_float(w.w)) : 0;
+    int err = d * ady - carries * adx;
+    int y = (int)(short)(w.y & 0xffff) + d * base + sgn * carries;
+    uint8_t* dst = ybuf + ybuf_index(x, log2_l);
+    for (int j = 0; j < len; ++j) {
+        dst[j] = (uint8_t)y;
+        ++x;
+        if (x == x1) { // the next segment starts exactly on its own first point
             ++seg;
-            x1 = x2;
-            x2 = p.seg[min(seg + 2, 67)].x0;
+            w = *reinterpret_cast<const int4*>(&p.seg[seg]);
+            x1 = p.seg[seg + 1].x0;
+            base = w.y >> 16, ady = (int)(short)(w.z & 0xffff), adx_s = w.z >> 16;
+            adx = abs(adx_s), sgn = adx_s < 0 ? -1 : 1;
+            y = (int)(short)(w.y & 0xffff);
+            err = 0;
+        } else {
+            y += base;
+            err += ady;
+            if (err >= adx) {
+                err -= adx;
+                y += sgn;
+            }
         }
-        const int4 w = *reinterpret_cast<const int4*>(&p.seg[seg]);
-        const int x0 = w.x, y0 = (int)(short)(w.y & 0xffff), base = w.y >> 16;
-        const int ady = (int)(short)(w.z & 0xffff), adx_s = w.z >> 16;
-        const int d = x - x0;
-        const int carries = div_seeded(d * ady, abs(adx_s), __int_as_float(w.w));
-        const int y = y0 + d * base + (adx_s < 0 ? -carries : carries);
-        spec[x] = __ldg(inv_db + y);
     }
 }
 
@@ -232,12 +260,15 @@ __host__ __device__ inline size_t vorbis_slot_bytes(int slot_smem) {
 __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slot_smem) {
     extern __shared__ __align__(16) unsigned char raw[];
     __shared__ bool is_last;
+    __shared__ float inv_db_s[256]; // floor1_inverse_dB_table (floor.rs:21-86): 2 K lookups per long packet
     const int tid = threadIdx.x, grp = tid >> 6, gt = tid & 63, warp_in_grp = gt >> 5, lane = tid & 31;
     const size_t slot_bytes = vorbis_slot_bytes(slot_smem);
     auto slot_out = [&](int k, int ch) { return reinterpret_cast<float*>(raw + k * slot_bytes) + (size_t)ch * 2 * slot_smem; };
     float2* z = reinterpret_cast<float2*>(reinterpret_cast<float*>(raw + grp * slot_bytes) + 4 * slot_smem);
     FloorPoints* pts = reinterpret_cast<FloorPoints*>(raw + (grp + 1) * slot_bytes - 2 * sizeof(FloorPoints));
 
+    if (threadIdx.x < 256) inv_db_s[threadIdx.x] = a.tab->vorbis_inverse_db[threadIdx.x];
+    __syncthreads();
     const CodecChunk ck = a.chunks[blockIdx.x];
     const symgpu_vorbis_stream cfg = a.streams[ck.stream];
     const CodecTables* __restrict__ tab = a.tab;
@@ -261,26 +292,27 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
         const int n2 = bs >> 1;
         NamedSync sync{1 + grp, kVorbisThreads};
         // pull this packet's residue (both channels) towards the SM while the floors are built
-        for (uint32_t i = 32u * gt; i < 2u * a.slot; i += 32u * kVorbisThreads)
-            if ((i % a.slot) < (uint32_t)n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residue + (size_t)p * 2 * a.slot + i));
-        // (1) floor curves: warp = channel, rendered into the channel's spectrum area
-        if (warp_in_grp < n_ch) {
+        for (uint32_t i = 32u * gt; i < (uint32_t)n_ch * a.slot; i += 32u * kVorbisThreads)
+            if ((i % a.slot) < (uint32_t)n2)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residue + ((size_t)p * a.pkt_ch + a.ch_base) * a.slot + i));
+        // (1) floor curves: warp = channel.  The curve is kept as one table index per line, in the upper half of the channel's
+        //     area (free until the IMDCT writes its output); the look-up happens where the value is used, in (2).
+        const int log2_l = 31 - __clz(n2 >> 5);
+        bool used[2] = {false, false};
+        for (int ch = 0; ch < n_ch; ++ch) used[ch] = u.floor[ch] != 0xffff && u.floor[ch] < a.n_floors;
+        if (warp_in_grp < n_ch && used[warp_in_grp]) {
             const int ch = warp_in_grp;
-            float* spec = slot_out(grp, ch);
-            const bool used = u.floor[ch] != 0xffff && u.floor[ch] < a.n_floors;
-            if (used) {
-                floor1_build(a.floors[u.floor[ch]], a.floor_aux[u.floor[ch]], a.floor_y + ((size_t)p * 2 + ch) * 65, n2, pts[ch], lane);
-                floor1_render(pts[ch], n2, lane, spec, tab->vorbis_inverse_db);
-            } else {
-                for (int x = lane; x < n2; x += 32) spec[x] = 0.0f; // ch.floor[..n2].fill(0.0)
-            }
+            floor1_build(a.floors[u.floor[ch]], a.floor_aux[u.floor[ch]], a.floor_y + ((size_t)p * a.pkt_ch + a.ch_base + ch) * 65, n2, pts[ch], lane);
+            floor1_render(pts[ch], n2, lane, reinterpret_cast<uint8_t*>(slot_out(grp, ch) + n2));
         }
         sync();
-        // (2) inverse coupling + dot product
-        const float* r0 = a.residue + ((size_t)p * 2 + 0) * a.slot;
-        const float* r1 = a.residue + ((size_t)p * 2 + 1) * a.slot;
+        // (2) inverse coupling + dot product (an unused floor is all zeros: ch.floor[..n2].fill(0.0))
+        const float* r0 = a.residue + ((size_t)p * a.pkt_ch + a.ch_base) * a.slot;
+        const float* r1 = r0 + a.slot;
         float* spec0 = slot_out(grp, 0);
         float* spec1 = slot_out(grp, 1);
+        const uint8_t* yb0 = reinterpret_cast<const uint8_t*>(spec0 + n2);
+        const uint8_t* yb1 = reinterpret_cast<const uint8_t*>(spec1 + n2);
         for (int i = gt; i < n2; i += kVorbisThreads) {
             float m = __ldg(r0 + i);
             float ang = n_ch == 2 ? __ldg(r1 + i) : 0.0f;
@@ -294,8 +326,13 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
                 m = nm;
                 ang = na;
             }
-            if (!u.do_not_decode[0]) spec0[i] = spec0[i] * m;
-            if (n_ch == 2 && !u.do_not_decode[1]) spec1[i] = spec1[i] * ang;
+            const int yi = ybuf_index(i, log2_l);
+            const float f0 = used[0] ? inv_db_s[yb0[yi]] : 0.0f;
+            spec0[i] = u.do_not_decode[0] ? f0 : f0 * m;
+            if (n_ch == 2) {
+                const float f1 = used[1] ? inv_db_s[yb1[yi]] : 0.0f;
+                spec1[i] = u.do_not_decode[1] ? f1 : f1 * ang;
+            }
         }
         sync();
         // (3) IMDCT per channel, in place over the channel's area (the spectrum is dead after the pre-twiddle)
@@ -316,7 +353,7 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
         for (int ch = 0; ch < n_ch; ++ch) {
             const float* out = slot_out(grp, ch);
             const float* ov = slot_out(grp - 1, ch) + pbs / 2; // overlap[..] = imdct[bs/2..bs] of the previous packet
-            float* dst = a.pcm + ((size_t)p * 2 + ch) * a.slot;
+            float* dst = a.pcm + ((size_t)p * a.pkt_ch + a.ch_base + ch) * a.slot;
             if (prev_flag == block_flag) {
                 const int len = bs / 2;
                 for (int k = gt; k < len; k += kVorbisThreads)
@@ -356,6 +393,70 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
 }
 
 } // namespace
+
+
+// ---- multichannel helpers --------------------------------------------------------------------------------------------
+namespace {
+// Inverse coupling of every step of the packet's mapping, in the reference's order (lib.rs:252-278: `for coupling in
+// mapping.couplings.iter()`), one thread per spectral line: the steps of a line only touch that line.
+__global__ void __launch_bounds__(256) vorbis_mc_decouple_kernel(const symgpu_vorbis_unit_mc* __restrict__ units, const uint32_t* __restrict__ stream_of_packet,
+                                                                 const symgpu_vorbis_stream_mc* __restrict__ streams, float* residue,
+                                                                 uint32_t n_packets, uint32_t channels, uint32_t slot) {
+    const uint32_t p = blockIdx.y;
+    if (p >= n_packets) return;
+    const uint32_t sidx = stream_of_packet[p];
+    if (sidx == 0xffffffffu) return; // a packet no run names
+    const symgpu_vorbis_stream_mc& cfg = streams[sidx];
+    const int n2 = (units[p].block_flag ? (1 << cfg.bs1_exp) : (1 << cfg.bs0_exp)) >> 1;
+    float* base = residue + (size_t)p * channels * slot;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        for (int c = 0; c < cfg.n_couplings; ++c) {
+            float* pm = base + (size_t)cfg.magnitude_ch[c] * slot + i;
+            float* pa = base + (size_t)cfg.angle_ch[c] * slot + i;
+            const float m = *pm, ang = *pa;
+            float nm, na;
+            if (m > 0.0f) {
+                if (ang > 0.0f) { nm = m; na = m - ang; } else { nm = m + ang; na = m; }
+            } else {
+                if (ang > 0.0f) { nm = m; na = m + ang; } else { nm = m - ang; na = m; }
+            }
+            *pm = nm;
+            *pa = na;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vorbis_mc_split_units_kernel(const symgpu_vorbis_unit_mc* __restrict__ units, uint32_t n_packets, uint32_t pair,
+                                                                    symgpu_vorbis_unit* __restrict__ out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_packets) return;
+    const symgpu_vorbis_unit_mc u = units[p];
+    symgpu_vorbis_unit o{};
+    o.block_flag = u.block_flag;
+    o.prev_block_flag = u.prev_block_flag;
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t ch = 2 * pair + c;
+        o.do_not_decode[c] = ch < SYMGPU_VORBIS_MAX_CHANNELS ? u.do_not_decode[ch] : 1;
+        o.floor[c] = ch < SYMGPU_VORBIS_MAX_CHANNELS ? u.floor[ch] : 0xffff;
+    }
+    out[p] = o;
+}
+} // namespace
+
+cudaError_t vorbis_mc_decouple_launch(const symgpu_vorbis_unit_mc* units, const uint32_t* stream_of_packet, const symgpu_vorbis_stream_mc* streams,
+                                      float* residue, uint32_t n_packets, uint32_t channels, uint32_t slot, cudaStream_t stream) {
+    if (n_packets == 0) return cudaSuccess;
+    const dim3 grid((slot + 255) / 256 < 16 ? (slot + 255) / 256 : 16, n_packets);
+    vorbis_mc_decouple_kernel<<<grid, 256, 0, stream>>>(units, stream_of_packet, streams, residue, n_packets, channels, slot);
+    return cudaGetLastError();
+}
+
+cudaError_t vorbis_mc_split_units_launch(const symgpu_vorbis_unit_mc* units, uint32_t n_packets, uint32_t pair, symgpu_vorbis_unit* out,
+                                         cudaStream_t stream) {
+    if (n_packets == 0) return cudaSuccess;
+    vorbis_mc_split_units_kernel<<<(n_packets + 255) / 256, 256, 0, stream>>>(units, n_packets, pair, out);
+    return cudaGetLastError();
+}
 
 int vorbis_slots_for(int max_bs1_exp) {
     const size_t per = vorbis_slot_bytes(1 << (max_bs1_exp - 1));

@@ -9,7 +9,8 @@ import numpy as np
 
 from . import _native
 from ._native import (AAC_RUN_DTYPE, AAC_TNS_DTYPE, AAC_UNIT_DTYPE, FMT_NUMPY, MP3_GC_DTYPE, MP3_RUN_DTYPE, MPA12_RUN_DTYPE,
-                      PCM_SPAN_DTYPE, VORBIS_FLOOR1_DTYPE, VORBIS_RUN_DTYPE, VORBIS_STREAM_DTYPE, VORBIS_UNIT_DTYPE)
+                      PCM_SPAN_DTYPE, VORBIS_FLOOR1_DTYPE, VORBIS_RUN_DTYPE, VORBIS_STREAM_DTYPE, VORBIS_STREAM_MC_DTYPE, VORBIS_UNIT_DTYPE,
+                      VORBIS_UNIT_MC_DTYPE)
 
 
 class SymgpuError(RuntimeError):
@@ -282,6 +283,26 @@ class Engine:
             out = np.empty((n, 2, slot), dtype=np.float32)
         self._check(self._lib.symgpu_vorbis_synth_host(self._ctx, _np_ptr(units), _np_ptr(floor_y), _np_ptr(residue),
                                                        _np_ptr(runs), len(runs), n, int(slot), _np_ptr(out)))
+        return out
+
+    def vorbis_mc_streams_set(self, streams):
+        """Multichannel Vorbis streams (up to 8 channels, every coupling step of the mapping): VORBIS_STREAM_MC_DTYPE records."""
+        streams = np.ascontiguousarray(streams, dtype=VORBIS_STREAM_MC_DTYPE)
+        self._check(self._lib.symgpu_vorbis_mc_streams_set(self._ctx, _np_ptr(streams), len(streams)))
+
+    def vorbis_mc_synth_host(self, units, floor_y, residue, runs, channels, slot, out=None):
+        """units [P] VORBIS_UNIT_MC_DTYPE, floor_y [P,C,65] u16, residue [P,C,slot] f32 -> pcm [P,C,slot]."""
+        units = np.ascontiguousarray(units, dtype=VORBIS_UNIT_MC_DTYPE)
+        floor_y = np.ascontiguousarray(floor_y, dtype=np.uint16)
+        residue = np.ascontiguousarray(residue, dtype=np.float32)
+        runs = np.ascontiguousarray(runs, dtype=VORBIS_RUN_DTYPE)
+        n, C = len(units), int(channels)
+        if residue.size != n * C * slot or floor_y.size != n * C * 65:
+            raise ValueError("residue must be [n, channels, slot] and floor_y [n, channels, 65]")
+        if out is None:
+            out = np.empty((n, C, slot), dtype=np.float32)
+        self._check(self._lib.symgpu_vorbis_mc_synth_host(self._ctx, _np_ptr(units), _np_ptr(floor_y), _np_ptr(residue), _np_ptr(runs), len(runs), n,
+                                                          C, int(slot), _np_ptr(out)))
         return out
 
     def vorbis_synth_dev(self, units_t, floor_y_t, residue_t, runs, slot, pcm_t):

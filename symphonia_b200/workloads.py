@@ -425,3 +425,74 @@ def vorbis_batch(n_streams=64, packets_per_stream=128, seed=SEED_BASE + 3, bs_ex
     runs["n_packets"] = F
     return dict(streams=streams, floors=floors, units=units.reshape(P), floor_y=floor_y.reshape(P, 2, 65),
                 residue=residue.reshape(P, 2, slot), runs=runs, slot=slot, out_len=out_len.reshape(P))
+
+
+def vorbis_mc_batch(n_streams=4, packets_per_stream=24, seed=SEED_BASE + 9, bs_exp=(8, 11), channels=6,
+                    couplings=((0, 2), (3, 4), (1, 0)), unused_prob=0.05):
+    """Multichannel Vorbis batch (symgpu_vorbis_mc_*): `channels` planes per packet and a list of coupling steps
+    (magnitude channel, angle channel) applied in order -- the default is a 5.1 layout in which channel 0 takes part in two steps,
+    so the order of the steps matters.  Same floors / residues / block mix as vorbis_batch.
+
+    Returns dict(streams, floors, units [P], floor_y [P,C,65], residue [P,C,slot], runs, slot, out_len [P], channels)."""
+    from ._native import VORBIS_STREAM_MC_DTYPE, VORBIS_UNIT_MC_DTYPE
+    rng = np.random.Generator(np.random.PCG64(seed))
+    S, F, C = int(n_streams), int(packets_per_stream), int(channels)
+    bs0, bs1 = 1 << bs_exp[0], 1 << bs_exp[1]
+    slot = bs1 // 2
+    streams = np.zeros(S, dtype=VORBIS_STREAM_MC_DTYPE)
+    streams["bs0_exp"], streams["bs1_exp"], streams["channels"], streams["n_couplings"] = bs_exp[0], bs_exp[1], C, len(couplings)
+    for k, (m, a) in enumerate(couplings):
+        streams["magnitude_ch"][:, k], streams["angle_ch"][:, k] = m, a
+    floors, by_size = [], {0: [], 1: []}
+    for flag, n2 in ((0, bs0 // 2), (1, bs1 // 2)):
+        for _ in range(4):
+            n_posts = int(min(rng.integers(20, 41), n2 // 2))
+            inner = rng.choice(np.arange(1, n2), size=n_posts - 2, replace=False).tolist()
+            rng.shuffle(inner)
+            by_size[flag].append(len(floors))
+            floors.append(make_floor1_setup([0, n2] + inner, int(rng.choice([1, 2, 2, 2, 3, 4]))))
+    floors = np.array(floors, dtype=VORBIS_FLOOR1_DTYPE)
+    P = S * F
+    units = np.zeros((S, F), dtype=VORBIS_UNIT_MC_DTYPE)
+    units["floor"] = 0xFFFF
+    units["do_not_decode"] = 1
+    floor_y = np.zeros((S, F, C, 65), dtype=np.uint16)
+    residue = np.zeros((S, F, C, slot), dtype=np.float32)
+    out_len = np.zeros((S, F), dtype=np.int32)
+    flag = (rng.random(S) < 0.8).astype(np.uint8)
+    for f in range(F):
+        if f:
+            u = rng.random(S)
+            flag = np.where(flag == 1, (u < 0.9).astype(np.uint8), (u >= 0.7).astype(np.uint8))
+        prev = units["block_flag"][:, f - 1] if f else flag
+        units["block_flag"][:, f] = flag
+        units["prev_block_flag"][:, f] = prev
+        out_len[:, f] = (np.where(prev == 1, bs1, bs0) + np.where(flag == 1, bs1, bs0)) // 4
+        for s in range(S):
+            n2 = (bs1 if flag[s] else bs0) // 2
+            dnd = []
+            for ch in range(C):
+                fi = by_size[int(flag[s])][int(rng.integers(0, 4))]
+                setup = floors[fi]
+                npost = int(setup["n_posts"])
+                rng_ = {1: 256, 2: 128, 3: 86, 4: 64}[int(setup["multiplier"])]
+                y = rng.integers(0, 24, size=npost)
+                y[rng.random(npost) < 0.3] = 0
+                y[0], y[1] = rng.integers(0, rng_, size=2)
+                floor_y[s, f, ch, :npost] = y
+                unused = rng.random() < unused_prob
+                units[s, f]["floor"][ch] = 0xFFFF if unused else fi
+                dnd.append(bool(unused))
+                r = rng.standard_normal(n2).astype(np.float32) * 4.0
+                r[int(0.8 * n2):] = 0.0
+                residue[s, f, ch, :n2] = r
+            for m, a in couplings:  # non-zero vector propagate (lib.rs:215-225), in mapping order
+                if dnd[m] != dnd[a]:
+                    dnd[m] = dnd[a] = False
+            units[s, f]["do_not_decode"][:C] = [int(d) for d in dnd]
+    runs = np.zeros(S, dtype=VORBIS_RUN_DTYPE)
+    runs["stream"] = np.arange(S)
+    runs["first_packet"] = np.arange(S) * F
+    runs["n_packets"] = F
+    return dict(streams=streams, floors=floors, units=units.reshape(P), floor_y=floor_y.reshape(P, C, 65),
+                residue=residue.reshape(P, C, slot), runs=runs, slot=slot, out_len=out_len.reshape(P), channels=C)

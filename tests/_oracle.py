@@ -29,6 +29,10 @@ class VorbisState(ctypes.Structure):
     _fields_ = [("overlap", ctypes.c_float * (2 * 4096))]
 
 
+class VorbisMcState(ctypes.Structure):
+    _fields_ = [("overlap", ctypes.c_float * (8 * 4096))]
+
+
 def build(arch=None, out=None):
     cmd = ["make", "-C", ODIR, "-s"]
     if arch:
@@ -143,4 +147,16 @@ def vorbis_batch(lib, wl, n_threads=1):
     rc = lib.oracle_vorbis_batch(ctypes.byref(states), ptr(arrs["streams"]), ptr(arrs["floors"]), ptr(arrs["units"]),
                                  ptr(arrs["floor_y"]), ptr(arrs["residue"]), ptr(arrs["runs"]),
                                  ctypes.c_uint32(len(arrs["runs"])), ctypes.c_uint32(wl["slot"]), ptr(pcm), n_threads)
+    return rc, pcm
+
+
+def vorbis_mc_batch(lib, wl):
+    """wl: the dict returned by symphonia_b200.workloads.vorbis_mc_batch."""
+    states = (VorbisMcState * len(wl["streams"]))()
+    C = int(wl["channels"])
+    pcm = np.zeros((len(wl["units"]), C, wl["slot"]), dtype=np.float32)
+    arrs = {k: np.ascontiguousarray(wl[k]) for k in ("streams", "floors", "units", "floor_y", "residue", "runs")}
+    lib.oracle_vorbis_mc_batch.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_uint32] * 3 + [ctypes.c_void_p]
+    rc = lib.oracle_vorbis_mc_batch(ctypes.byref(states), ptr(arrs["streams"]), ptr(arrs["floors"]), ptr(arrs["units"]), ptr(arrs["floor_y"]),
+                                    ptr(arrs["residue"]), ptr(arrs["runs"]), len(arrs["runs"]), C, int(wl["slot"]), ptr(pcm))
     return rc, pcm

@@ -178,3 +178,56 @@ def test_vorbis_state_carry(engine, oracle):
     mask = np.arange(slot)[None, None, :] < wl["out_len"][:, None, None]
     got = got.reshape(S * F, 2, slot)
     _cmp(np.where(mask, got, 0), np.where(mask, want, 0), "vorbis state carry")
+
+
+# ---- BASELINE sizes: every frame / packet of the 8192-unit batches against the (multi-threaded) oracle --------------------
+
+def test_aac_full_size_matches_oracle(engine, oracle):
+    import os
+    from symphonia_b200 import workloads
+    S, F = 64, 128
+    units, tns, coeffs, runs = workloads.aac_batch(S, F, seed=workloads.SEED_BASE + 2)
+    rc, want = _oracle.aac_batch(oracle, units, tns, coeffs, runs, S, n_threads=min(os.cpu_count() or 1, S))
+    assert rc == 0
+    engine.aac_streams_alloc(S)
+    got = engine.aac_synth_host(units, tns, coeffs, runs)
+    _cmp(got, want, "aac 8192 frames")
+
+
+def test_vorbis_full_size_matches_oracle(engine, oracle):
+    import os
+    from symphonia_b200 import workloads
+    S, F = 64, 128
+    wl = workloads.vorbis_batch(S, F, seed=workloads.SEED_BASE + 3)
+    rc, want = _oracle.vorbis_batch(oracle, wl, n_threads=min(os.cpu_count() or 1, S))
+    assert rc == 0
+    engine.vorbis_streams_set(wl["streams"])
+    engine.vorbis_floors_set(wl["floors"])
+    got = engine.vorbis_synth_host(wl["units"], wl["floor_y"], wl["residue"], wl["runs"], wl["slot"])
+    mask = np.broadcast_to(np.arange(wl["slot"])[None, None, :] < wl["out_len"][:, None, None], got.shape)
+    _cmp(np.where(mask, got, 0), np.where(mask, want, 0), "vorbis 8192 packets")
+
+
+# ---- Vorbis with more than two channels and several coupling steps (symgpu_vorbis_mc_*) ---------------------------------
+
+def _vorbis_mc_case(engine, oracle, **kw):
+    from symphonia_b200 import workloads
+    wl = workloads.vorbis_mc_batch(**kw)
+    rc, want = _oracle.vorbis_mc_batch(oracle, wl)
+    assert rc == 0
+    engine.vorbis_mc_streams_set(wl["streams"])
+    engine.vorbis_floors_set(wl["floors"])
+    got = engine.vorbis_mc_synth_host(wl["units"], wl["floor_y"], wl["residue"], wl["runs"], wl["channels"], wl["slot"])
+    mask = np.broadcast_to(np.arange(wl["slot"])[None, None, :] < wl["out_len"][:, None, None], got.shape)
+    _cmp(np.where(mask, got, 0), np.where(mask, want, 0), f"vorbis multichannel {kw}")
+
+
+def test_vorbis_5_1_with_three_coupling_steps(engine, oracle):
+    """Six channels, three coupling steps in which channel 0 takes part twice (the order of the steps matters: the reference walks
+    the mapping's list front to back, lib.rs:252-278), four streams with long / short block switching."""
+    _vorbis_mc_case(engine, oracle, n_streams=4, packets_per_stream=24, seed=301)
+
+
+@pytest.mark.parametrize("channels,couplings", [(1, ()), (2, ((0, 1),)), (3, ((0, 1), (2, 0))), (5, ((0, 1), (2, 3))), (8, ((0, 1), (2, 3), (4, 5), (7, 6), (0, 7)))])
+def test_vorbis_channel_counts(engine, oracle, channels, couplings):
+    _vorbis_mc_case(engine, oracle, n_streams=3, packets_per_stream=10, seed=310 + channels, channels=channels, couplings=couplings)

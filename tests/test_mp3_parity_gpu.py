@@ -135,7 +135,7 @@ def test_device_resident_entry_point(engine, oracle):
 def test_full_size_properties(engine, oracle):
     """BASELINE config 2 size (8192 frames): linearity-free size-independent checks.
     (a) batch-split invariance: one launch == the same streams cut into two launches, bit for bit;
-    (b) a 64-frame sample of streams matches the oracle."""
+    (b) EVERY stream of the batch matches the oracle (multi-threaded oracle pass)."""
     from symphonia_b200 import workloads
     S, F = 64, 128
     units, spectra, runs = workloads.mp3_batch(S, F, seed=workloads.SEED_BASE + 1)
@@ -154,10 +154,31 @@ def test_full_size_properties(engine, oracle):
         halves.append(out.reshape(S, hi - lo, 2, 1152))
     split = np.concatenate(halves, axis=1).reshape(S * F, 2, 1152)
     _compare(split, whole, "batch-split invariance")
-    pick = [0, 17, 63]
-    for s in pick:
-        r = runs[s:s + 1].copy()
-        r["first_frame"] = 0
-        r["stream"] = 0
-        rc, want, _ = _oracle.mp3_batch(oracle, u4[s].reshape(-1, 2, 2), s4[s].reshape(-1, 2, 2, 576), r, 1)
-        _compare(whole.reshape(S, F, 2, 1152)[s], want, f"stream {s} of the full batch")
+    import ctypes
+    import os
+    states = (_oracle.Mp3State * S)()
+    want = np.zeros((S * F, 2, 1152), dtype=np.float32)
+    rc = oracle.oracle_mp3_batch_mt(ctypes.byref(states), _oracle.ptr(units), _oracle.ptr(spectra), _oracle.ptr(runs),
+                                    ctypes.c_uint32(len(runs)), _oracle.ptr(want), ctypes.c_int(min(os.cpu_count() or 1, S)))
+    assert rc == 0
+    _compare(whole, want, "all 64 streams of the full batch")
+
+
+def test_pinned_host_buffers_take_the_zero_copy_path(engine, oracle):
+    """Pinned (device-mapped) host buffers go to the kernel as they are: its TMA copies read the spectra across PCIe, its PCM
+    stores land in host memory.  Same bits as the staged path and as the oracle; long runs and the serving shape."""
+    import torch
+    import symphonia_b200 as sb
+    from symphonia_b200 import workloads
+    for S, F, seed in ((6, 40, 31), (96, 1, 32)):
+        units, spectra, runs = workloads.mp3_batch(S, F, seed=seed)
+        rc, want, _ = _oracle.mp3_batch(oracle, units, spectra, runs, S)
+        assert rc == 0
+        u_pin = torch.from_numpy(units.view(np.uint8).reshape(-1).copy()).pin_memory()
+        s_pin = torch.from_numpy(spectra.copy()).pin_memory()
+        p_pin = torch.zeros((S * F, 2, 1152), dtype=torch.float32).pin_memory()
+        engine.mp3_streams_alloc(S)
+        launches = engine.launch_count
+        got = engine.mp3_synth_host(u_pin.numpy().view(sb._native.MP3_GC_DTYPE).reshape(S * F, 2, 2), s_pin.numpy(), runs, out=p_pin.numpy())
+        assert engine.launch_count == launches + 1, "one launch, no staging kernels"
+        _compare(got, want, f"zero-copy host entry point S={S} F={F}")
