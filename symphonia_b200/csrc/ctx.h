@@ -44,9 +44,11 @@ struct symgpu_ctx {
     size_t stage_cap = 0;
     // copy pipeline of the host entry points: H2D on copy_in, kernels on `stream`, D2H on copy_out
     static constexpr int kMaxSlices = 32;
-    // pinned (device-mapped) host buffers go straight to the kernels: 0 never, 1 output only (PCM stores cross PCIe from the
-    // kernel, no D2H copy), 2 input too (TMA reads across PCIe; measured slower than staged H2D).  SYMGPU_ZERO_COPY
-    int zero_copy = 1;
+    // pinned (device-mapped) host buffers handed straight to the kernels: 0 never (default), 1 output only (PCM stores cross
+    // PCIe from the kernel, no D2H copy), 2 input too (TMA reads across PCIe).  Measured on a B200 (profiles/r02l): 8192 MP3 frames
+    // take 2.20 ms staged through the copy pipeline, 2.36 ms with both directions zero-copy, 3.2 ms with output only -- SM stores to
+    // host memory reach ~25 GB/s against the copy engines' ~50 -- so the staged pipeline stays the default.  SYMGPU_ZERO_COPY
+    int zero_copy = 0;
     int h2d_ahead = 2; // slices whose H2D copy is queued before the host's descriptor check and planning (SYMGPU_H2D_AHEAD)
     int n_slices = 8; // slices of a host batch in the copy pipeline (SYMGPU_SLICES overrides, for tuning)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;

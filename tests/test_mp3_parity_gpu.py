@@ -164,12 +164,16 @@ def test_full_size_properties(engine, oracle):
     _compare(whole, want, "all 64 streams of the full batch")
 
 
-def test_pinned_host_buffers_take_the_zero_copy_path(engine, oracle):
-    """Pinned (device-mapped) host buffers go to the kernel as they are: its TMA copies read the spectra across PCIe, its PCM
-    stores land in host memory.  Same bits as the staged path and as the oracle; long runs and the serving shape."""
+@pytest.mark.parametrize("mode", ["2", "1", "0"])
+def test_pinned_host_buffers_and_the_zero_copy_paths(oracle, mode, monkeypatch):
+    """SYMGPU_ZERO_COPY=2: pinned (device-mapped) host buffers go to the kernel as they are -- its TMA copies read the spectra
+    across PCIe, its PCM stores land in host memory; =1: only the output; =0: staged copies (the default).  Same bits as the
+    oracle in every mode; long runs and the serving shape."""
     import torch
     import symphonia_b200 as sb
     from symphonia_b200 import workloads
+    monkeypatch.setenv("SYMGPU_ZERO_COPY", mode)
+    engine = sb.Engine(0)
     for S, F, seed in ((6, 40, 31), (96, 1, 32)):
         units, spectra, runs = workloads.mp3_batch(S, F, seed=seed)
         rc, want, _ = _oracle.mp3_batch(oracle, units, spectra, runs, S)
@@ -181,4 +185,5 @@ def test_pinned_host_buffers_take_the_zero_copy_path(engine, oracle):
         launches = engine.launch_count
         got = engine.mp3_synth_host(u_pin.numpy().view(sb._native.MP3_GC_DTYPE).reshape(S * F, 2, 2), s_pin.numpy(), runs, out=p_pin.numpy())
         assert engine.launch_count == launches + 1, "one launch, no staging kernels"
-        _compare(got, want, f"zero-copy host entry point S={S} F={F}")
+        _compare(got, want, f"zero-copy mode {mode}, host entry point S={S} F={F}")
+    engine.close()
