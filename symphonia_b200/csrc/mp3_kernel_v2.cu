@@ -475,8 +475,18 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 6 ? 12 / NW : 1)) mp3v2_synth_
             if (k == 0 && (tile.flags & kTileLoadState)) {
                 const uint32_t gen = __ldg(a.gen + tile.stream); // bumped only by the launch epilogue
                 const Mp3StreamState* st = a.states + (size_t)tile.stream * 2 + (gen & 1);
+                // overlap[ch][sub-band][18]: fetched with coalesced 16-byte loads into the (still unused) region of the granule in
+                // flight, then read per lane -- a lane's own 18 values lie 72 bytes apart from its neighbour's
+                {
+                    float* scr = reinterpret_cast<float*>(ws.xt) + (size_t)(18 * region) * kPitch * 2;
+                    const float4* src = reinterpret_cast<const float4*>(&st->overlap[0][0][0]);
 #pragma unroll
-                for (int t = 0; t < 18; ++t) sec[t] = make_float2(st->overlap[0][lane][t], st->overlap[1][lane][t]);
+                    for (int i = 0; i < 9; ++i) reinterpret_cast<float4*>(scr)[lane + 32 * i] = __ldg(src + lane + 32 * i);
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 18; ++t) sec[t] = make_float2(scr[18 * lane + t], scr[576 + 18 * lane + t]);
+                    __syncwarp();
+                }
                 for (int idx = lane; idx < 15 * kPitch; idx += 32) {
                     const int srow = idx / kPitch, col = idx - srow * kPitch;
                     f2 v = make_float2(0.0f, 0.0f);
@@ -1019,14 +1029,24 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 6 ? 12 / NW : 1)) mp3v2_synth_
                 if (last && (te.flags & kTileStoreState)) {
                     const uint32_t gen = __ldg(a.gen + te.stream);
                     Mp3StreamState* st = a.states + (size_t)te.stream * 2 + ((gen + 1) & 1);
-#pragma unroll
-                    for (int t = 0; t < 18; ++t) {
-                        st->overlap[0][lane][t] = sec[t].x;
-                        st->overlap[1][lane][t] = te.n_ch == 2 ? sec[t].y : 0.0f;
-                    }
                     for (int idx = lane; idx < 15 * 32; idx += 32) {
                         const int srow = idx >> 5, col = idx & 31;
                         st->dhist[srow][col] = lds64(cur_rows + (uint32_t)((3 + srow) * kPitch + col) * 8u);
+                    }
+                    // overlap: through the region of the granule before (its last reader, the window phase, is done), so that
+                    // the stores to HBM are coalesced 16-byte ones
+                    {
+                        __syncwarp();
+                        float* scr = reinterpret_cast<float*>(ws.xt) + (size_t)(18 * (region ^ 1)) * kPitch * 2;
+#pragma unroll
+                        for (int t = 0; t < 18; ++t) {
+                            scr[18 * lane + t] = sec[t].x;
+                            scr[576 + 18 * lane + t] = te.n_ch == 2 ? sec[t].y : 0.0f;
+                        }
+                        __syncwarp();
+                        float4* dst = reinterpret_cast<float4*>(&st->overlap[0][0][0]);
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) dst[lane + 32 * i] = reinterpret_cast<const float4*>(scr)[lane + 32 * i];
                     }
                 }
                 if (last && ti + 1 >= (int)__ldg(a.first + share + 1)) break;

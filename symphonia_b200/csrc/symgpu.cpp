@@ -258,7 +258,7 @@ symgpu_status build_plan(symgpu_ctx* ctx, const symgpu_mp3_run* runs, uint32_t n
                          bool whole_batch = true) {
     cudaError_t ce = cudaSuccess;
     // Which kernel: the second generation (one warp per share, state in registers) wins where runs are short -- the serving
-    // shape, a frame or two per stream: 164 us against 219 us for 8192 one-frame streams -- the first generation (CTA-wide
+    // shape, a frame or two per stream: 143 us against 219 us for 8192 one-frame streams -- the first generation (CTA-wide
     // tiles of 16 consecutive granules, one halo per CTA chain) with the packed window phase where runs are long: 128 us
     // against 135 us for 64 streams x 128 frames (profiles/r02_mp3_variants_log.txt).
     bool v2 = ctx->mp3_kernel_mode == 2;
