@@ -39,6 +39,14 @@ struct symgpu_ctx {
     int cached_tiles = 0, cached_hdr = 0, cached_ctas = 0;
     bool cached_multi = false;
     bool cached_v2 = false;
+    // launch plans of the host entry point's copy pipeline (one per slice), kept while the caller repeats the same runs: a
+    // server that decodes the same streams step after step plans once.  Invalidated by anything that rewrites d_tiles.
+    struct SlicePlan { uint32_t r0, r1, f0, f1; int t0, hdr, n_tiles, n_ctas; bool multi, v2; };
+    std::vector<SlicePlan> slice_plans;
+    std::vector<symgpu_mp3_run> slice_runs;
+    uint32_t slice_frames = 0;
+    int slice_key_slices = 0, slice_key_mode = -1;
+    bool slice_plans_valid = false;
     // staging for the host entry points
     void* d_stage = nullptr;
     size_t stage_cap = 0;

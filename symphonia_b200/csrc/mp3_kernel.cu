@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/symgpu.h"
 #include "mp3_kernel.h"
@@ -1054,9 +1055,21 @@ cudaError_t mpa12_launch(const Mpa12Args& a, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-int mp3_tile_granules() { return kMp3TileGranules; }
+// Granules per tile of the launch plan (<= kMp3TileGranules).  SYMGPU_MP3_T overrides it (tuning): with 14 granules a tile's
+// 504 DCT vectors fit the 512 threads in one round and its 252 time slots are 16 per warp, one window block each.
+int mp3_tile_granules() {
+    static int t = 0;
+    if (!t) {
+        t = kMp3TileGranules;
+        if (const char* env = getenv("SYMGPU_MP3_T")) {
+            const int v = atoi(env);
+            if (v >= 4 && v <= kMp3TileGranules) t = v;
+        }
+    }
+    return t;
+}
 int mp3_cta_warps() { return kMp3Warps; }
-int mp3_halo_tile_granules() { return kMp3Warps - 2 < kMp3TileGranules ? kMp3Warps - 2 : kMp3TileGranules; }
+int mp3_halo_tile_granules() { return kMp3Warps - 2 < mp3_tile_granules() ? kMp3Warps - 2 : mp3_tile_granules(); }
 
 int mp3_grid_size(cudaError_t* err) {
     constexpr size_t smem = sizeof(Mp3Smem<kMp3TileGranules, kMp3Warps>);

@@ -304,6 +304,7 @@ cudaError_t launch_plan(symgpu_ctx* ctx, const Mp3Tile* d_plan, int hdr, int n_t
 
 // Makes room for `entries` plan entries in the device / pinned host buffers.
 symgpu_status reserve_plan(symgpu_ctx* ctx, size_t entries) {
+    ctx->slice_plans_valid = false; // whoever asks for room is about to rewrite d_tiles
     CU(ctx, cudaStreamSynchronize(ctx->stream)); // the previous launch may still read d_tiles; h_tiles is rewritten
     if (entries <= ctx->tiles_cap) return SYMGPU_OK;
     if (ctx->d_tiles) cudaFree(ctx->d_tiles);
@@ -608,6 +609,7 @@ symgpu_status symgpu_mp3_streams_alloc(symgpu_ctx* ctx, uint32_t n_streams) {
     ctx->n_mp3_streams = 0;
     ctx->cached_runs.clear();
     ctx->cached_frames = 0;
+    ctx->slice_plans_valid = false;
     CU(ctx, cudaMalloc(&ctx->d_mp3_states, (size_t)n_streams * 2 * sizeof(Mp3StreamState)));
     CU(ctx, cudaMemset(ctx->d_mp3_states, 0, (size_t)n_streams * 2 * sizeof(Mp3StreamState)));
     CU(ctx, cudaMalloc(&ctx->d_mp3_gen, ((size_t)n_streams + 1) * sizeof(uint32_t)));
@@ -641,6 +643,26 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
 } // extern "C"
 
 static inline float* d_spec_base(char* stage_base) { return reinterpret_cast<float*>(stage_base); }
+
+
+// symgpu_mp3_units_check over the runs in four parts on as many threads (the 64-byte descriptors of 8192 frames take ~190 us on
+// one thread, which is 9 % of an end-to-end step).
+static symgpu_status units_check_mt(const symgpu_mp3_gc* units, const symgpu_mp3_run* runs, uint32_t n_runs, uint32_t n_frames) {
+    if (n_frames < 1024 || n_runs < 4) return symgpu_mp3_units_check(units, runs, n_runs, n_frames);
+    symgpu_status chk[4] = {SYMGPU_OK, SYMGPU_OK, SYMGPU_OK, SYMGPU_OK};
+    std::thread workers[3];
+    const uint32_t per = (n_runs + 3) / 4;
+    auto part = [&](int k) {
+        const uint32_t r0 = std::min<uint32_t>(n_runs, per * (uint32_t)k), r1 = std::min<uint32_t>(n_runs, r0 + per);
+        if (r1 > r0) chk[k] = symgpu_mp3_units_check(units, runs + r0, r1 - r0, n_frames);
+    };
+    for (int k = 1; k < 4; ++k) workers[k - 1] = std::thread(part, k);
+    part(0);
+    for (auto& w : workers) w.join();
+    for (symgpu_status c : chk)
+        if (c != SYMGPU_OK) return c;
+    return SYMGPU_OK;
+}
 
 // Host-buffer MP3 synthesis.  format < 0: planar f32 into `out` (the AudioBuffer layout); otherwise the
 // output stage runs on the device after each slice's kernel and `out` receives interleaved samples.
@@ -686,24 +708,10 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         void* d_o = d_s ? mapped(out) : nullptr;
         if (d_o) {
             // descriptors are checked before anything runs on them (four host threads: ~50 us for 8192 frames)
-            symgpu_status chk[4] = {SYMGPU_OK, SYMGPU_OK, SYMGPU_OK, SYMGPU_OK};
             {
-                std::thread workers[3];
-                const uint32_t per = (n_runs + 3) / 4;
-                auto part = [&](int k) {
-                    const uint32_t r0 = std::min<uint32_t>(n_runs, per * (uint32_t)k), r1 = std::min<uint32_t>(n_runs, r0 + per);
-                    if (r1 > r0) chk[k] = symgpu_mp3_units_check(units, runs + r0, r1 - r0, n_frames);
-                };
-                const bool threaded = n_frames >= 1024;
-                for (int k = 1; k < 4; ++k)
-                    if (threaded) workers[k - 1] = std::thread(part, k);
-                    else part(k);
-                part(0);
-                for (auto& w : workers)
-                    if (w.joinable()) w.join();
-            }
-            for (symgpu_status c : chk)
+                const symgpu_status c = units_check_mt(units, runs, n_runs, n_frames);
                 if (c != SYMGPU_OK) return c;
+            }
             symgpu_status zs = symgpu_mp3_synth_dev(ctx, static_cast<const symgpu_mp3_gc*>(d_u), static_cast<const float*>(d_s), runs, n_runs,
                                                     n_frames, static_cast<float*>(d_o));
             if (zs != SYMGPU_OK) return zs;
@@ -769,7 +777,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         // small or unsorted batch: one copy in, one launch, one copy out
         CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, copy_in(0, n_frames, ctx->stream));
-        s = symgpu_mp3_units_check(units, runs, n_runs, n_frames); // overlaps the copies; nothing has been launched yet
+        s = units_check_mt(units, runs, n_runs, n_frames); // overlaps the copies; nothing has been launched yet
         if (s == SYMGPU_OK) s = symgpu_mp3_synth_dev(ctx, d_units, d_spec, runs, n_runs, n_frames, d_pcm);
         if (s != SYMGPU_OK) {
             cudaStreamSynchronize(ctx->stream); // the copies read the caller's buffers
@@ -828,34 +836,60 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         CU(ctx, copy_in(slices[i].f0, slices[i].f1 - slices[i].f0, ctx->copy_in));
         CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
     }
-    // 2. host work under those copies: descriptor check (a helper thread) and the launch plans of the slices
+    // 2. host work under those copies: descriptor check (helper threads) and the launch plans of the slices -- which are kept
+    //    (and stay on the device) while the caller repeats the same runs
     symgpu_status chk = SYMGPU_OK;
-    std::thread checker([&] { chk = symgpu_mp3_units_check(units, runs, n_runs, n_frames); });
-    std::vector<Mp3Tile> all_tiles;
-    Mp3Plan plan;
+    std::thread checker([&] { chk = units_check_mt(units, runs, n_runs, n_frames); });
+    const bool plans_cached = ctx->slice_plans_valid && ctx->slice_frames == n_frames && ctx->slice_key_slices == n_slices &&
+                              ctx->slice_key_mode == ctx->mp3_kernel_mode && ctx->slice_runs.size() == n_runs &&
+                              std::memcmp(ctx->slice_runs.data(), runs, n_runs * sizeof *runs) == 0 && ctx->slice_plans.size() == slices.size();
     s = SYMGPU_OK;
-    for (size_t i = 0; i < slices.size() && s == SYMGPU_OK; ++i) {
-        Slice& sl = slices[i];
-        s = build_plan(ctx, runs + sl.r0, sl.r1 - sl.r0, n_frames, plan, false);
-        sl.t0 = (int)all_tiles.size();
-        all_tiles.insert(all_tiles.end(), plan.buf.begin(), plan.buf.end());
-        sl.hdr = plan.hdr;
-        sl.n_tiles = plan.n_tiles;
-        sl.n_ctas = plan.n_ctas;
-        sl.multi = plan.multi;
-        sl.v2 = plan.v2;
+    if (plans_cached) {
+        for (size_t i = 0; i < slices.size(); ++i) {
+            const symgpu_ctx::SlicePlan& c = ctx->slice_plans[i];
+            slices[i].t0 = c.t0, slices[i].hdr = c.hdr, slices[i].n_tiles = c.n_tiles, slices[i].n_ctas = c.n_ctas;
+            slices[i].multi = c.multi, slices[i].v2 = c.v2;
+        }
+        checker.join();
+        s = chk;
+    } else {
+        std::vector<Mp3Tile> all_tiles;
+        Mp3Plan plan;
+        for (size_t i = 0; i < slices.size() && s == SYMGPU_OK; ++i) {
+            Slice& sl = slices[i];
+            s = build_plan(ctx, runs + sl.r0, sl.r1 - sl.r0, n_frames, plan, false);
+            sl.t0 = (int)all_tiles.size();
+            all_tiles.insert(all_tiles.end(), plan.buf.begin(), plan.buf.end());
+            sl.hdr = plan.hdr;
+            sl.n_tiles = plan.n_tiles;
+            sl.n_ctas = plan.n_ctas;
+            sl.multi = plan.multi;
+            sl.v2 = plan.v2;
+        }
+        if (s == SYMGPU_OK) s = reserve_plan(ctx, all_tiles.size());
+        checker.join();
+        if (s == SYMGPU_OK) s = chk;
+        if (s == SYMGPU_OK) {
+            ctx->cached_runs.clear(); // the cached plan of the device entry point is replaced
+            ctx->cached_frames = 0;
+            std::memcpy(ctx->h_tiles, all_tiles.data(), all_tiles.size() * sizeof(Mp3Tile));
+            cudaError_t ce = cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, all_tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream);
+            if (ce != cudaSuccess) s = cuda_fail(ctx, ce, "cudaMemcpyAsync(slice plans)");
+        }
+        if (s == SYMGPU_OK) {
+            ctx->slice_plans.clear();
+            for (const Slice& sl : slices) ctx->slice_plans.push_back({sl.r0, sl.r1, sl.f0, sl.f1, sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, sl.multi, sl.v2});
+            ctx->slice_runs.assign(runs, runs + n_runs);
+            ctx->slice_frames = n_frames;
+            ctx->slice_key_slices = n_slices;
+            ctx->slice_key_mode = ctx->mp3_kernel_mode;
+            ctx->slice_plans_valid = true;
+        }
     }
-    if (s == SYMGPU_OK) s = reserve_plan(ctx, all_tiles.size());
-    checker.join();
-    if (s == SYMGPU_OK) s = chk;
     if (s != SYMGPU_OK) {
         cudaStreamSynchronize(ctx->copy_in); // the copies read the caller's buffers; nothing has been launched
         return s;
     }
-    ctx->cached_runs.clear(); // the cached plan of the device entry point is about to be replaced
-    ctx->cached_frames = 0;
-    std::memcpy(ctx->h_tiles, all_tiles.data(), all_tiles.size() * sizeof(Mp3Tile));
-    CU(ctx, cudaMemcpyAsync(ctx->d_tiles, ctx->h_tiles, all_tiles.size() * sizeof(Mp3Tile), cudaMemcpyHostToDevice, ctx->stream));
     // 3. kernels as the slices land, D2H copies as the kernels finish, the next H2D copy behind each D2H copy
     for (size_t i = 0; i < slices.size(); ++i) {
         const Slice& sl = slices[i];
