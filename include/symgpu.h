@@ -293,6 +293,8 @@ symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floo
 /* The validation symgpu_vorbis_floors_set applies, without a context (host only): SYMGPU_OK or SYMGPU_ERR_ARG.  The Vorbis
  * front-end runs it when a stream is opened, so that an unusable setup is refused per stream (SYMGPU_ERR_UNSUPPORTED). */
 symgpu_status symgpu_vorbis_floors_check(const symgpu_vorbis_floor1* floors, uint32_t n_floors);
+/* The same, also writing each setup's dependency levels (72 bytes per setup: level[65], the largest level, 6 zero bytes). */
+symgpu_status symgpu_vorbis_floors_levels(const symgpu_vorbis_floor1* floors, uint32_t n_floors, uint8_t* levels);
 symgpu_status symgpu_vorbis_stream_reset(symgpu_ctx* ctx, uint32_t stream); /* dsp.rs:26-32, :128-131 */
 
 /* Synthesises `n_packets` packets.  Every per-packet array uses fixed slots of `slot` floats per

@@ -223,3 +223,39 @@ extern "C" symgpu_status symgpu_flac_index(const uint8_t* data, size_t n, symgpu
 static_assert(sizeof(symgpu_flac_stream_info) == 56 && sizeof(symgpu_flac_packet) == 24, "record sizes are ABI");
 static_assert(sizeof(symgpu_mpa_track) == 48 && sizeof(symgpu_mpa_packet) == 48 && sizeof(symgpu_adts_packet) == 32, "record sizes are ABI");
 static_assert(sizeof(symgpu_piece) == 16 && sizeof(symgpu_ogg_packet) == 40 && sizeof(symgpu_vorbis_ident) == 8, "record sizes are ABI");
+
+// ---- floor-1 setups: what the synthesis kernel relies on (host only; used by symgpu_vorbis_floors_set and by the Vorbis
+// front-end when a stream is opened) ---------------------------------------------------------------------------------------
+// A setup is what Floor1Setup holds after the reference's own checks (floor.rs:300-420): distinct x positions, sort_order a
+// permutation by ascending x that starts at x = 0, and for every post >= 2 the nearest lower / higher neighbours among the
+// EARLIER posts.  The kernel divides by x differences and sweeps the posts by dependency level, so none of this may be taken
+// on trust.  x <= 2^15: rangebits up to 15 are legal (floor.rs:519-536); the kernel's seeded division stays exact (numerator
+// < 2^23, divisor < 2^15).  levels (may be null): per setup 72 bytes = level[65] (level[i] = 1 + max(level[low[i]], level[high[i]]),
+// level[0] = level[1] = 0), the largest level, 6 zero bytes -- struct FloorAux of codec_kernels.h.
+extern "C" symgpu_status symgpu_vorbis_floors_levels(const symgpu_vorbis_floor1* floors, uint32_t n_floors, uint8_t* levels) {
+    if (!floors || n_floors == 0) return SYMGPU_ERR_ARG;
+    for (uint32_t i = 0; i < n_floors; ++i) {
+        const symgpu_vorbis_floor1& f = floors[i];
+        if (f.multiplier < 1 || f.multiplier > 4 || f.n_posts < 2 || f.n_posts > 65) return SYMGPU_ERR_ARG;
+        bool seen[65] = {false};
+        for (int k = 0; k < f.n_posts; ++k) {
+            if (f.sort_order[k] >= f.n_posts || seen[f.sort_order[k]] || f.x_list[k] > 32768) return SYMGPU_ERR_ARG;
+            seen[f.sort_order[k]] = true;
+            if (k && f.x_list[f.sort_order[k]] <= f.x_list[f.sort_order[k - 1]]) return SYMGPU_ERR_ARG;
+        }
+        if (f.x_list[f.sort_order[0]] != 0) return SYMGPU_ERR_ARG;
+        uint8_t level[72] = {0};
+        for (int k = 2; k < f.n_posts; ++k) {
+            const int lo = f.low[k], hi = f.high[k];
+            if (lo >= k || hi >= k || !(f.x_list[lo] < f.x_list[k] && f.x_list[k] < f.x_list[hi])) return SYMGPU_ERR_ARG;
+            level[k] = (uint8_t)(1 + (level[lo] > level[hi] ? level[lo] : level[hi]));
+            if (level[k] > level[65]) level[65] = level[k];
+        }
+        if (levels) std::memcpy(levels + (size_t)i * 72, level, 72);
+    }
+    return SYMGPU_OK;
+}
+
+extern "C" symgpu_status symgpu_vorbis_floors_check(const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
+    return symgpu_vorbis_floors_levels(floors, n_floors, nullptr);
+}

@@ -299,47 +299,12 @@ symgpu_status symgpu_vorbis_streams_set(symgpu_ctx* ctx, const symgpu_vorbis_str
     return SYMGPU_OK;
 }
 
-// Host-only validation of floor-1 setups (no context needed): what the kernel's level sweep and divisions rely on.  levels (may be
-// null) receives each setup's dependency levels.
-static symgpu_status vorbis_floors_validate(const symgpu_vorbis_floor1* floors, uint32_t n_floors, FloorAux* levels) {
-    if (!floors || n_floors == 0) return SYMGPU_ERR_ARG;
-    // A setup is what Floor1Setup holds after the reference's own checks (floor.rs:300-420): distinct x
-    // positions, sort_order a permutation by ascending x that starts at x = 0, and for every post >= 2 the
-    // nearest lower / higher neighbours among the EARLIER posts.  The kernel divides by x differences and
-    // sweeps the posts by dependency level, so none of this may be taken on trust.  x <= 2^15: rangebits up to 15
-    // are legal (floor.rs:519-536); the seeded division stays exact (numerator < 2^23, divisor < 2^15).
-    for (uint32_t i = 0; i < n_floors; ++i) {
-        const symgpu_vorbis_floor1& f = floors[i];
-        if (f.multiplier < 1 || f.multiplier > 4 || f.n_posts < 2 || f.n_posts > 65) return SYMGPU_ERR_ARG;
-        bool seen[65] = {false};
-        for (int k = 0; k < f.n_posts; ++k) {
-            if (f.sort_order[k] >= f.n_posts || seen[f.sort_order[k]] || f.x_list[k] > 32768) return SYMGPU_ERR_ARG;
-            seen[f.sort_order[k]] = true;
-            if (k && f.x_list[f.sort_order[k]] <= f.x_list[f.sort_order[k - 1]]) return SYMGPU_ERR_ARG;
-        }
-        if (f.x_list[f.sort_order[0]] != 0) return SYMGPU_ERR_ARG;
-        FloorAux a;
-        std::memset(&a, 0, sizeof a);
-        for (int k = 2; k < f.n_posts; ++k) {
-            const int lo = f.low[k], hi = f.high[k];
-            if (lo >= k || hi >= k || !(f.x_list[lo] < f.x_list[k] && f.x_list[k] < f.x_list[hi])) return SYMGPU_ERR_ARG;
-            a.level[k] = (uint8_t)(1 + std::max(a.level[lo], a.level[hi]));
-            a.max_level = std::max(a.max_level, a.level[k]);
-        }
-        if (levels) levels[i] = a;
-    }
-    return SYMGPU_OK;
-}
-
-symgpu_status symgpu_vorbis_floors_check(const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
-    return vorbis_floors_validate(floors, n_floors, nullptr);
-}
-
 symgpu_status symgpu_vorbis_floors_set(symgpu_ctx* ctx, const symgpu_vorbis_floor1* floors, uint32_t n_floors) {
     if (!ctx || !floors || n_floors == 0) return SYMGPU_ERR_ARG;
     std::vector<FloorAux> aux(n_floors);
     {
-        const symgpu_status chk = vorbis_floors_validate(floors, n_floors, aux.data());
+        static_assert(sizeof(FloorAux) == 72, "symgpu_vorbis_floors_levels writes 65 levels + the maximum + 6 pad bytes per setup");
+        const symgpu_status chk = symgpu_vorbis_floors_levels(floors, n_floors, reinterpret_cast<uint8_t*>(aux.data()));
         if (chk != SYMGPU_OK) return chk;
     }
     DeviceGuard guard(ctx->device);
