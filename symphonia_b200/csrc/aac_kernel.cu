@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/symgpu.h"
 #include "codec_kernels.h"
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(kTnsWarps * 32) aac_tns_apply(const symgpu_aac
 // the chunk (its delay line).  Each frame has its own group of 64 threads and its own named barrier,
 // so the K+1 IMDCTs proceed independently; the window / overlap step then reads the IMDCT output of
 // frame f and of frame f-1 (the `delay` of the reference is a pure function of frame f-1's output).
-constexpr int kAacK = kAacChunkFrames;
+constexpr int kAacK = kAacChunkFrames;     // frames per chunk, two warps per frame (named barriers)
+constexpr int kAacKWarp = kAacChunkFramesWarp; // frames per chunk, ONE warp per frame (__syncwarp only)
 struct alignas(16) AacFrameSmem {
     float out[2048];          // spectrum (first 1024 floats) until the pre-twiddle has consumed it, then pcm_long
     float2 z[zpad_len(512)];
@@ -268,13 +270,17 @@ __device__ __forceinline__ float aac_new_delay(int seq, const float* out, const 
 
 // Persistent: gridDim.x CTAs (two per SM) walk the chunks blockIdx.x, blockIdx.x + gridDim.x, ...; the twiddle
 // and window tables are staged in shared memory once per CTA.
-__global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs a) {
+// GW = threads per frame: 64 (two warps, named barrier; K = 6 frames per chunk, two CTAs per SM) or 32 (one warp, __syncwarp
+// only; K = 13 frames per chunk, one CTA per SM: half the warps, no hardware barrier inside the IMDCT, one halo frame in 14
+// instead of one in 7).
+template <int GW, int K>
+__global__ void __launch_bounds__((K + 1) * GW, GW == 64 ? 2 : 1) aac_synth_kernel(AacArgs a) {
     extern __shared__ __align__(16) unsigned char aac_raw[];
     AacFrameSmem* fs = reinterpret_cast<AacFrameSmem*>(aac_raw);
-    AacTabSmem& ts = *reinterpret_cast<AacTabSmem*>(aac_raw + (kAacK + 1) * sizeof(AacFrameSmem));
+    AacTabSmem& ts = *reinterpret_cast<AacTabSmem*>(aac_raw + (K + 1) * sizeof(AacFrameSmem));
     __shared__ bool is_last;
     const int tid = threadIdx.x;
-    const int grp = tid >> 6, gt = tid & 63; // frame slot of this thread, thread within the slot's group
+    const int grp = tid / GW, gt = tid % GW; // frame slot of this thread, thread within the slot's group
     const CodecTables* __restrict__ tab = a.tab;
     {
         const float2* g_fft = reinterpret_cast<const float2*>(tab->fft_lit16);
@@ -313,17 +319,26 @@ __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs 
             u = a.units[unit_idx];
             AacFrameSmem& me = fs[grp];
             const float* src = (u.n_tns ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
-            for (int i = gt; i < 256; i += 64) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-            NamedSync sync{1 + grp, 64};
-            sync();
+            for (int i = gt; i < 256; i += GW) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
             // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
-            if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-                imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
-            else
-                imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 64, sync);
+            if constexpr (GW == 64) {
+                NamedSync sync{1 + grp, 64};
+                sync();
+                if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
+                    imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
+                else
+                    imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 64, sync);
+            } else {
+                WarpSync sync;
+                sync();
+                if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
+                    imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 32, sync);
+                else
+                    imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 32, sync);
+            }
         } else if (grp == 0) {
             // run start: slot 0 holds the delay line itself (stored in out[1024..2048))
-            for (int i = gt; i < 1024; i += 64) fs[0].out[1024 + i] = st_in[i];
+            for (int i = gt; i < 1024; i += GW) fs[0].out[1024 + i] = st_in[i];
         }
         __syncthreads();
 
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs 
             const float* q_psw = ts.win_short[pu.prev_window_shape ? 1 : 0];
             float* dst = a.pcm + (2 * (size_t)f + ch) * 1024;
 #pragma unroll 4
-            for (int i = gt; i < 1024; i += 64) {
+            for (int i = gt; i < 1024; i += GW) {
                 const float d = prev_is_state ? pout[1024 + i] : aac_new_delay(pseq, pout, q_lw, q_sw, q_psw, i);
                 float y;
                 switch (seq) {
@@ -367,7 +382,7 @@ __global__ void __launch_bounds__((kAacK + 1) * 64, 2) aac_synth_kernel(AacArgs 
             }
             if (grp == count && (ck.flags & kChunkStoreState)) { // the run's last frame leaves its delay line in the state
                 const float* lw = ts.win_long[u.window_shape ? 1 : 0];
-                for (int i = gt; i < 1024; i += 64) st_out[i] = aac_new_delay(seq, out, lw, sw, psw, i);
+                for (int i = gt; i < 1024; i += GW) st_out[i] = aac_new_delay(seq, out, lw, sw, psw, i);
             }
         }
         __syncthreads(); // the frame slots are reused by the next chunk
@@ -399,21 +414,45 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
+    AacArgs b = a;
+    b.n_chunks = n_chunks;
+    cudaError_t e = cudaSuccess;
+    if (aac_warp_per_frame()) {
+        constexpr size_t smem = (kAacKWarp + 1) * sizeof(AacFrameSmem) + sizeof(AacTabSmem);
+        static int max_grid = 0;
+        if (!max_grid) {
+            if ((e = cudaFuncSetAttribute(aac_synth_kernel<32, kAacKWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            int dev = 0, n_sm = 0;
+            if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+            if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+            max_grid = n_sm;
+        }
+        aac_synth_kernel<32, kAacKWarp><<<n_chunks < max_grid ? n_chunks : max_grid, (kAacKWarp + 1) * 32, smem, stream>>>(b);
+        return cudaGetLastError();
+    }
     constexpr size_t smem = (kAacK + 1) * sizeof(AacFrameSmem) + sizeof(AacTabSmem);
     static int max_grid = 0;
     if (!max_grid) {
-        cudaError_t e = cudaFuncSetAttribute(aac_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(aac_synth_kernel<64, kAacK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         int dev = 0, n_sm = 0, per_sm = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aac_synth_kernel, (kAacK + 1) * 64, smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aac_synth_kernel<64, kAacK>, (kAacK + 1) * 64, smem)) != cudaSuccess) return e;
         max_grid = n_sm * (per_sm > 0 ? per_sm : 1);
     }
-    AacArgs b = a;
-    b.n_chunks = n_chunks;
-    aac_synth_kernel<<<n_chunks < max_grid ? n_chunks : max_grid, (kAacK + 1) * 64, smem, stream>>>(b);
+    aac_synth_kernel<64, kAacK><<<n_chunks < max_grid ? n_chunks : max_grid, (kAacK + 1) * 64, smem, stream>>>(b);
     return cudaGetLastError();
 }
+
+// One warp per frame (SYMGPU_AAC_KERNEL=warp) or two (default).
+bool aac_warp_per_frame() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* env = getenv("SYMGPU_AAC_KERNEL");
+        mode = (env && env[0] == 'w') ? 1 : 0;
+    }
+    return mode == 1;
+}
+int aac_chunk_frames() { return aac_warp_per_frame() ? kAacKWarp : kAacK; }
 
 } // namespace symgpu

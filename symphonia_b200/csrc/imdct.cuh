@@ -118,6 +118,9 @@ __device__ __forceinline__ void fft_pass(float2* z, int n_pts, int tid, int n_th
 struct CtaSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
+struct WarpSync { // a block owned by ONE warp: no hardware barrier at all
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
 struct NamedSync {
     int id, n;
     __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }

@@ -120,7 +120,7 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
         if (run.stream >= ctx->n_aac_streams) return SYMGPU_ERR_LIMIT;
         covered += run.n_frames;
         for (int ch = 0; ch < n_ch; ++ch)
-            split_even(run.n_frames, kAacChunkFrames, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
+            split_even(run.n_frames, (uint32_t)aac_chunk_frames(), [&](uint32_t lo, uint32_t hi, bool first, bool last) {
                 CodecChunk c{};
                 c.first = run.first_frame + lo;
                 c.stream = run.stream;
