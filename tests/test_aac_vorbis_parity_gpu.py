@@ -231,3 +231,18 @@ def test_vorbis_5_1_with_three_coupling_steps(engine, oracle):
 @pytest.mark.parametrize("channels,couplings", [(1, ()), (2, ((0, 1),)), (3, ((0, 1), (2, 0))), (5, ((0, 1), (2, 3))), (8, ((0, 1), (2, 3), (4, 5), (7, 6), (0, 7)))])
 def test_vorbis_channel_counts(engine, oracle, channels, couplings):
     _vorbis_mc_case(engine, oracle, n_streams=3, packets_per_stream=10, seed=310 + channels, channels=channels, couplings=couplings)
+
+
+def test_aac_one_warp_per_frame_variant_matches_too():
+    """`SYMGPU_AAC_KERNEL=warp` (13 frames per chunk, __syncwarp only; measured slower, kept selectable - DESIGN 4) is read once
+    per process, so the AAC cases above are re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SYMGPU_AAC_KERNEL="warp")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "test_aac_mixed or test_aac_chunk_boundaries or test_aac_state_carry or test_aac_heavy_tns or test_aac_mono"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
