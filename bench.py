@@ -533,7 +533,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "frames_per_gpu": N_FRAMES, "parallelism": f"streams sharded over {world} GPU(s)",
                        "l2": f"rotating {N_BUFFER_SETS} input/output buffer sets ({N_BUFFER_SETS * 151} MB) > 126 MB L2",
                        "fma": "disabled (bit-exact parity with the reference)",
-                       "kernel": os.environ.get("SYMGPU_MP3_KERNEL", "v2") + ":" + os.environ.get("SYMGPU_MP3_V2_VARIANT", "default")},
+                       "kernel": os.environ.get("SYMGPU_MP3_KERNEL", "auto (per launch plan; this batch of 256-granule runs: mp3_synth_kernel<16,16,0,1>, "
+                                                                     "the first-generation kernel with the packed window phase)")},
             "roofline": dict(roofline(algo_bytes, avg_kernel_ms, "mp3"),
                              note="FMA is off for parity, so the kernel is FP32-pipe bound, not HBM bound: the no-FMA floor for this "
                                   "batch is ~31 us (1.1e9 f32 lane-ops at the measured 35.9e12/s) vs 23 us at the HBM peak; traffic "

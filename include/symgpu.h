@@ -161,7 +161,11 @@ symgpu_status symgpu_mp3_stream_reset(symgpu_ctx* ctx, uint32_t stream);
  *                                 must tile [0, n_frames) without overlap and no stream may
  *                                 appear in two runs of the same call
  *   pcm     [n_frames][2][1152]   f32 planar per frame: plane(ch)[gr*576 .. gr*576+576]
- * Host variant: copies in, launches, copies out, and returns after the PCM is in `pcm`. */
+ * Host variant: copies in, launches, copies out, and returns after the PCM is in `pcm`.  Batches of 512 frames or more are cut
+ * into slices whose H2D copy, kernel and D2H copy overlap.  Smaller batches (one packet per call is the extreme) whose three
+ * buffers are pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister) are handed to the kernel as they are -- one
+ * launch, one synchronisation, no staging copy; pageable buffers are staged.  SYMGPU_ZERO_COPY=s forces staging, =2 hands
+ * batches of any size to the kernel. */
 symgpu_status symgpu_mp3_synth_host(symgpu_ctx* ctx, const symgpu_mp3_gc* units,
                                     const float* spectra, const symgpu_mp3_run* runs,
                                     uint32_t n_runs, uint32_t n_frames, float* pcm);

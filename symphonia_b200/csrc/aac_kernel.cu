@@ -12,6 +12,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 #include "../../include/symgpu.h"
 #include "codec_kernels.h"
@@ -240,31 +241,47 @@ struct alignas(16) AacTabSmem {
     float win_short[2][128];
 };
 
-// delay[i] after a frame with IMDCT output `out` (aac/dsp.rs:131-157) -- what the NEXT frame overlaps with.
-__device__ __forceinline__ float aac_new_delay(int seq, const float* out, const float* __restrict__ lw,
-                                               const float* __restrict__ sw, const float* __restrict__ psw, int i);
+// Two layouts of a frame slot.  Array: the 2048 IMDCT outputs as the reference stores them (12.8 KB with the FFT scratch).
+// Z: only the 512 post-twiddled complex values (imdct_to_z, 4.6 KB); an output sample is looked up through imdct_out.
+struct alignas(8) AacFrameZ {
+    float2 z[zpad_len(512)];
+};
+struct OutArray {
+    const float* p;
+    __device__ __forceinline__ float lng(int j) const { return p[j]; }
+    __device__ __forceinline__ float sht(int j) const { return p[j]; }     // eight short blocks: block j / 256, sample j % 256
+    __device__ __forceinline__ float state(int i) const { return p[1024 + i]; } // slot 0 of a run start holds the delay line
+};
+struct OutZ {
+    const float2* z;
+    __device__ __forceinline__ float lng(int j) const { return imdct_out<9>(z, 0, j); }
+    __device__ __forceinline__ float sht(int j) const { return imdct_out<6>(z, j >> 8, j & 255); }
+    __device__ __forceinline__ float state(int i) const { return reinterpret_cast<const float*>(z)[i]; }
+};
 
 // pcm_short[x] of aac/dsp.rs:86-101, rebuilt per sample with the reference's operation order: the
 // second half of window w-1 is written first (assignment for w-1 = 0, "0.0 +=" otherwise), then the
 // first half of window w is added.
-__device__ __forceinline__ float aac_pcm_short(const float* out, const float* __restrict__ sw,
-                                               const float* __restrict__ psw, int x) {
+template <typename Out>
+__device__ __forceinline__ float aac_pcm_short(const Out out, const float* __restrict__ sw, const float* __restrict__ psw, int x) {
     const int w = x >> 7, i = x & 127;
-    if (w == 0) return out[i] * psw[i];
-    const float t2 = out[256 * (w - 1) + 128 + i] * sw[127 - i];
+    if (w == 0) return out.sht(i) * psw[i];
+    const float t2 = out.sht(256 * (w - 1) + 128 + i) * sw[127 - i];
     const float prev = (w == 1) ? t2 : 0.0f + t2;
     if (w == 8) return prev;
-    return prev + out[256 * w + i] * sw[i];
+    return prev + out.sht(256 * w + i) * sw[i];
 }
 
-__device__ __forceinline__ float aac_new_delay(int seq, const float* out, const float* __restrict__ lw,
-                                               const float* __restrict__ sw, const float* __restrict__ psw, int i) {
+// delay[i] after a frame with IMDCT output `out` (aac/dsp.rs:131-157) -- what the NEXT frame overlaps with.
+template <typename Out>
+__device__ __forceinline__ float aac_new_delay(int seq, const Out out, const float* __restrict__ lw, const float* __restrict__ sw,
+                                               const float* __restrict__ psw, int i) {
     switch (seq) {
         case SYMGPU_AAC_ONLY_LONG:
-        case SYMGPU_AAC_LONG_STOP: return out[i + 1024] * lw[1023 - i];
+        case SYMGPU_AAC_LONG_STOP: return out.lng(i + 1024) * lw[1023 - i];
         case SYMGPU_AAC_EIGHT_SHORT: return i < P1 ? aac_pcm_short(out, sw, psw, i + 512 + 64) : 0.0f;
         default: // LONG_START
-            return i < P0 ? out[i + 1024] : i < P1 ? out[i + 1024] * sw[127 - (i - P0)] : 0.0f;
+            return i < P0 ? out.lng(i + 1024) : i < P1 ? out.lng(i + 1024) * sw[127 - (i - P0)] : 0.0f;
     }
 }
 
@@ -273,11 +290,22 @@ __device__ __forceinline__ float aac_new_delay(int seq, const float* out, const 
 // GW = threads per frame: 64 (two warps, named barrier; K = 6 frames per chunk, two CTAs per SM) or 32 (one warp, __syncwarp
 // only; K = 13 frames per chunk, one CTA per SM: half the warps, no hardware barrier inside the IMDCT, one halo frame in 14
 // instead of one in 7).
-template <int GW, int K>
-__global__ void __launch_bounds__((K + 1) * GW, GW == 64 ? 2 : 1) aac_synth_kernel(AacArgs a) {
+//
+// ZL (GW = 32 only): frame slots in the Z layout -- 14 slots are 65 KB instead of 180 KB, so two CTAs share an SM: 28 frames in
+// flight per SM, one warp each, no hardware barrier inside an IMDCT.
+template <int GW, int K, bool ZL>
+__global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_synth_kernel(AacArgs a) {
+    static_assert(!ZL || GW == 32, "the Z layout is written for one warp per frame");
     extern __shared__ __align__(16) unsigned char aac_raw[];
-    AacFrameSmem* fs = reinterpret_cast<AacFrameSmem*>(aac_raw);
-    AacTabSmem& ts = *reinterpret_cast<AacTabSmem*>(aac_raw + (K + 1) * sizeof(AacFrameSmem));
+    using Slot = typename std::conditional<ZL, AacFrameZ, AacFrameSmem>::type;
+    using Out = typename std::conditional<ZL, OutZ, OutArray>::type;
+    Slot* fs = reinterpret_cast<Slot*>(aac_raw);
+    // the tables follow the slots at a 16-byte boundary
+    AacTabSmem& ts = *reinterpret_cast<AacTabSmem*>(aac_raw + (((K + 1) * sizeof(Slot) + 15) & ~size_t(15)));
+    auto out_of = [&](int slot) -> Out {
+        if constexpr (ZL) return Out{fs[slot].z};
+        else return Out{fs[slot].out};
+    };
     __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int grp = tid / GW, gt = tid % GW; // frame slot of this thread, thread within the slot's group
@@ -317,28 +345,40 @@ __global__ void __launch_bounds__((K + 1) * GW, GW == 64 ? 2 : 1) aac_synth_kern
         if (have_frame) {
             const size_t unit_idx = 2 * (size_t)f + ch;
             u = a.units[unit_idx];
-            AacFrameSmem& me = fs[grp];
             const float* src = (u.n_tns ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
-            for (int i = gt; i < 256; i += GW) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-            // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
-            if constexpr (GW == 64) {
-                NamedSync sync{1 + grp, 64};
-                sync();
-                if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-                    imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
-                else
-                    imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 64, sync);
-            } else {
+            if constexpr (ZL) {
                 WarpSync sync;
-                sync();
                 if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-                    imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 32, sync);
+                    imdct_to_z<9>(src, fs[grp].z, 1, ts.tw_long, ft, gt, 32, sync);
                 else
-                    imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 32, sync);
+                    imdct_to_z<6>(src, fs[grp].z, 8, ts.tw_short, ft, gt, 32, sync);
+            } else {
+                auto& me = fs[grp];
+                for (int i = gt; i < 256; i += GW) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+                // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
+                if constexpr (GW == 64) {
+                    NamedSync sync{1 + grp, 64};
+                    sync();
+                    if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
+                        imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
+                    else
+                        imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 64, sync);
+                } else {
+                    WarpSync sync;
+                    sync();
+                    if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
+                        imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 32, sync);
+                    else
+                        imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 32, sync);
+                }
             }
         } else if (grp == 0) {
-            // run start: slot 0 holds the delay line itself (stored in out[1024..2048))
-            for (int i = gt; i < 1024; i += GW) fs[0].out[1024 + i] = st_in[i];
+            // run start: slot 0 holds the delay line itself (Array layout: in out[1024..2048); Z layout: the first 1024 floats)
+            if constexpr (ZL) {
+                for (int i = gt; i < 1024; i += GW) reinterpret_cast<float*>(fs[0].z)[i] = st_in[i];
+            } else {
+                for (int i = gt; i < 1024; i += GW) fs[0].out[1024 + i] = st_in[i];
+            }
         }
         __syncthreads();
 
@@ -355,8 +395,8 @@ __global__ void __launch_bounds__((K + 1) * GW, GW == 64 ? 2 : 1) aac_synth_kern
 
         // window + overlap-add (aac/dsp.rs:103-129): thread = (frame slot, sample)
         if (grp >= 1 && grp <= count) {
-            const float* out = fs[grp].out;
-            const float* pout = fs[grp - 1].out;
+            const Out out = out_of(grp);
+            const Out pout = out_of(grp - 1);
             const symgpu_aac_unit pu = (grp > 1 || !load_state) ? a.units[2 * (size_t)(f - 1) + ch] : symgpu_aac_unit{};
             const bool prev_is_state = grp == 1 && load_state;
             const int seq = u.window_sequence, pseq = pu.window_sequence;
@@ -370,13 +410,13 @@ __global__ void __launch_bounds__((K + 1) * GW, GW == 64 ? 2 : 1) aac_synth_kern
             float* dst = a.pcm + (2 * (size_t)f + ch) * 1024;
 #pragma unroll 4
             for (int i = gt; i < 1024; i += GW) {
-                const float d = prev_is_state ? pout[1024 + i] : aac_new_delay(pseq, pout, q_lw, q_sw, q_psw, i);
+                const float d = prev_is_state ? pout.state(i) : aac_new_delay(pseq, pout, q_lw, q_sw, q_psw, i);
                 float y;
                 switch (seq) {
                     case SYMGPU_AAC_ONLY_LONG:
-                    case SYMGPU_AAC_LONG_START: y = d + (out[i] * plw[i]); break;
+                    case SYMGPU_AAC_LONG_START: y = d + (out.lng(i) * plw[i]); break;
                     case SYMGPU_AAC_EIGHT_SHORT: y = i < P0 ? d : d + aac_pcm_short(out, sw, psw, i - P0); break;
-                    default: y = i < P0 ? d : i < P1 ? d + out[i] * psw[i - P0] : d + out[i]; break; // LONG_STOP
+                    default: y = i < P0 ? d : i < P1 ? d + out.lng(i) * psw[i - P0] : d + out.lng(i); break; // LONG_STOP
                 }
                 dst[i] = y;
             }
@@ -403,6 +443,24 @@ __global__ void __launch_bounds__((K + 1) * GW, GW == 64 ? 2 : 1) aac_synth_kern
 
 } // namespace
 
+template <int GW, int K, bool ZL>
+static cudaError_t launch_variant(const AacArgs& b, cudaStream_t stream) {
+    constexpr size_t slot = ZL ? sizeof(AacFrameZ) : sizeof(AacFrameSmem);
+    constexpr size_t smem = (((K + 1) * slot + 15) & ~size_t(15)) + sizeof(AacTabSmem);
+    static int max_grid = 0;
+    cudaError_t e;
+    if (!max_grid) {
+        if ((e = cudaFuncSetAttribute(aac_synth_kernel<GW, K, ZL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int dev = 0, n_sm = 0, per_sm = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aac_synth_kernel<GW, K, ZL>, (K + 1) * GW, smem)) != cudaSuccess) return e;
+        max_grid = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    aac_synth_kernel<GW, K, ZL><<<b.n_chunks < max_grid ? b.n_chunks : max_grid, (K + 1) * GW, smem, stream>>>(b);
+    return cudaGetLastError();
+}
+
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, cudaStream_t stream) {
     if (any_tns) {
         // owner[] starts at "no owner" so that filters outside every channel-frame's range are skipped
@@ -416,43 +474,23 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
     }
     AacArgs b = a;
     b.n_chunks = n_chunks;
-    cudaError_t e = cudaSuccess;
-    if (aac_warp_per_frame()) {
-        constexpr size_t smem = (kAacKWarp + 1) * sizeof(AacFrameSmem) + sizeof(AacTabSmem);
-        static int max_grid = 0;
-        if (!max_grid) {
-            if ((e = cudaFuncSetAttribute(aac_synth_kernel<32, kAacKWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-            int dev = 0, n_sm = 0;
-            if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-            if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-            max_grid = n_sm;
-        }
-        aac_synth_kernel<32, kAacKWarp><<<n_chunks < max_grid ? n_chunks : max_grid, (kAacKWarp + 1) * 32, smem, stream>>>(b);
-        return cudaGetLastError();
+    switch (aac_kernel_variant()) {
+        case 1: return launch_variant<32, kAacKWarp, false>(b, stream);
+        case 2: return launch_variant<32, kAacKWarp, true>(b, stream);
+        default: return launch_variant<64, kAacK, false>(b, stream);
     }
-    constexpr size_t smem = (kAacK + 1) * sizeof(AacFrameSmem) + sizeof(AacTabSmem);
-    static int max_grid = 0;
-    if (!max_grid) {
-        if ((e = cudaFuncSetAttribute(aac_synth_kernel<64, kAacK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        int dev = 0, n_sm = 0, per_sm = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aac_synth_kernel<64, kAacK>, (kAacK + 1) * 64, smem)) != cudaSuccess) return e;
-        max_grid = n_sm * (per_sm > 0 ? per_sm : 1);
-    }
-    aac_synth_kernel<64, kAacK><<<n_chunks < max_grid ? n_chunks : max_grid, (kAacK + 1) * 64, smem, stream>>>(b);
-    return cudaGetLastError();
 }
 
-// One warp per frame (SYMGPU_AAC_KERNEL=warp) or two (default).
-bool aac_warp_per_frame() {
+// SYMGPU_AAC_KERNEL = pair (two warps per frame, named barriers) | warp (one warp per frame) | z (one warp per frame, Z layout).
+int aac_kernel_variant() {
     static int mode = -1;
     if (mode < 0) {
         const char* env = getenv("SYMGPU_AAC_KERNEL");
-        mode = (env && env[0] == 'w') ? 1 : 0;
+        mode = !env ? kAacDefaultVariant : env[0] == 'w' ? 1 : env[0] == 'z' ? 2 : env[0] == 'p' ? 0 : kAacDefaultVariant;
     }
-    return mode == 1;
+    return mode;
 }
+bool aac_warp_per_frame() { return aac_kernel_variant() != 0; }
 int aac_chunk_frames() { return aac_warp_per_frame() ? kAacKWarp : kAacK; }
 
 } // namespace symgpu

@@ -24,7 +24,9 @@ static_assert(sizeof(CodecChunk) == 16, "CodecChunk is 16 bytes");
 
 constexpr int kAacChunkFrames = 6;      // two warps per frame
 constexpr int kAacChunkFramesWarp = 13; // one warp per frame
-bool aac_warp_per_frame();              // SYMGPU_AAC_KERNEL=warp
+constexpr int kAacDefaultVariant = 0;    // 0 pair | 1 warp | 2 z (SYMGPU_AAC_KERNEL overrides)
+int aac_kernel_variant();
+bool aac_warp_per_frame();
 int aac_chunk_frames();                 // frames per chunk of the variant in use
 
 constexpr int kVorbisStateFloats = 2 * 4096; // overlap of both channels, blocksize_1 <= 8192

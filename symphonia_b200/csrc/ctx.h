@@ -57,6 +57,7 @@ struct symgpu_ctx {
     // take 2.20 ms staged through the copy pipeline, 2.36 ms with both directions zero-copy, 3.2 ms with output only -- SM stores to
     // host memory reach ~25 GB/s against the copy engines' ~50 -- so the staged pipeline stays the default.  SYMGPU_ZERO_COPY
     int zero_copy = 0;
+    bool zero_copy_small = true; // host batches below the pipeline threshold with mapped buffers: one launch on the caller's memory
     int h2d_ahead = 2; // slices whose H2D copy is queued before the host's descriptor check and planning (SYMGPU_H2D_AHEAD)
     int n_slices = 8; // slices of a host batch in the copy pipeline (SYMGPU_SLICES overrides, for tuning)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;

@@ -506,7 +506,11 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
     if (!ctx) return SYMGPU_ERR_LIMIT;
     ctx->device = device;
     // SYMGPU_ZERO_COPY = 0 never (default) | 1 output only | 2 input and output
-    if (const char* env = std::getenv("SYMGPU_ZERO_COPY")) ctx->zero_copy = env[0] == '0' ? 0 : env[0] == '2' ? 2 : 1;
+    if (const char* env = std::getenv("SYMGPU_ZERO_COPY")) {
+        ctx->zero_copy = env[0] == '0' ? 0 : env[0] == '2' ? 2 : 1;
+        ctx->zero_copy_small = env[0] != '0' && env[0] != 's'; // "0": never; "s": staged copies for small batches too
+        if (env[0] == 's') ctx->zero_copy = 0;
+    }
     if (const char* env = std::getenv("SYMGPU_H2D_AHEAD")) { // H2D copies queued before the host's check / planning (tuning)
         const int v = std::atoi(env);
         if (v >= 1 && v <= symgpu_ctx::kMaxSlices) ctx->h2d_ahead = v;
@@ -642,6 +646,7 @@ symgpu_status symgpu_mp3_synth_dev(symgpu_ctx* ctx, const symgpu_mp3_gc* units, 
 
 } // extern "C"
 
+constexpr uint32_t kPipelineMinFrames = 512; // smaller host batches: no slice pipeline (and zero-copy when the buffers are mapped)
 static inline float* d_spec_base(char* stage_base) { return reinterpret_cast<float*>(stage_base); }
 
 
@@ -692,7 +697,10 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     // traffic, arithmetic and D2H traffic overlap inside ONE launch -- no staging copy, no slice pipeline, no copy-engine
     // scheduling between them.  Opt-in (SYMGPU_ZERO_COPY=2): measured 2.36 ms per 8192-frame step against 2.20 ms for the
     // staged pipeline below (profiles/r02l_*), bit-identical output (tests/test_mp3_parity_gpu.py).
-    if (ctx->zero_copy == 2 && !quant && format < 0) {
+    // Small batches (a single packet is the extreme: config 1) take this path by default when the buffers allow it: one launch and
+    // one synchronisation instead of two or three copy set-ups around them (SYMGPU_ZERO_COPY=0 switches it off).
+    const bool small_auto = ctx->zero_copy_small && n_frames < kPipelineMinFrames;
+    if ((ctx->zero_copy == 2 || small_auto) && !quant && format < 0) {
         bool whole = true;
         for (uint32_t r = 0; r < n_runs; ++r) whole &= runs[r].granules_per_frame != 1 && runs[r].channels != 1;
         auto mapped = [](const void* p) -> void* {
@@ -773,7 +781,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         }
     }
 
-    if (!sorted || n_frames < 512 || n_runs < 2) {
+    if (!sorted || n_frames < kPipelineMinFrames || n_runs < 2) {
         // small or unsorted batch: one copy in, one launch, one copy out
         CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, copy_in(0, n_frames, ctx->stream));

@@ -41,6 +41,7 @@ def test_packet_by_packet_decode_matches_oracle(tmp_path, oracle):
     inp.write_bytes(blob)
     res = subprocess.run([_build(), "decode", str(inp), str(outp)], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
+    print(res.stdout.strip())
     got = np.frombuffer(outp.read_bytes(), dtype=np.float32).reshape(F, 2, 1152)
     assert (got.view(np.uint32) == want.view(np.uint32)).all()
 

@@ -164,7 +164,7 @@ def test_full_size_properties(engine, oracle):
     _compare(whole, want, "all 64 streams of the full batch")
 
 
-@pytest.mark.parametrize("mode", ["2", "1", "0"])
+@pytest.mark.parametrize("mode", ["2", "1", "0", "s"])
 def test_pinned_host_buffers_and_the_zero_copy_paths(oracle, mode, monkeypatch):
     """SYMGPU_ZERO_COPY=2: pinned (device-mapped) host buffers go to the kernel as they are -- its TMA copies read the spectra
     across PCIe, its PCM stores land in host memory; =1: only the output; =0: staged copies (the default).  Same bits as the
@@ -186,4 +186,38 @@ def test_pinned_host_buffers_and_the_zero_copy_paths(oracle, mode, monkeypatch):
         got = engine.mp3_synth_host(u_pin.numpy().view(sb._native.MP3_GC_DTYPE).reshape(S * F, 2, 2), s_pin.numpy(), runs, out=p_pin.numpy())
         assert engine.launch_count == launches + 1, "one launch, no staging kernels"
         _compare(got, want, f"zero-copy mode {mode}, host entry point S={S} F={F}")
+    engine.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_one_packet_per_call_with_and_without_pinned_buffers(oracle, pinned, monkeypatch):
+    """Config 1's call pattern: one host call per packet, the stream state carried between the calls.  With pinned (device-mapped)
+    buffers a batch below the pipeline threshold is one launch on the caller's memory (the default); with pageable buffers it is
+    staged through device memory.  Same bits either way."""
+    import torch
+    import symphonia_b200 as sb
+    from symphonia_b200 import workloads
+    monkeypatch.delenv("SYMGPU_ZERO_COPY", raising=False)
+    engine = sb.Engine(0)
+    F = 24
+    units, spectra, runs = workloads.mp3_batch(1, F, seed=77, joint=False)
+    rc, want, _ = _oracle.mp3_batch(oracle, units, spectra, runs, 1)
+    assert rc == 0
+    if pinned:
+        u_buf = torch.from_numpy(units.view(np.uint8).reshape(-1).copy()).pin_memory().numpy().view(sb._native.MP3_GC_DTYPE).reshape(F, 2, 2)
+        s_buf = torch.from_numpy(spectra.copy()).pin_memory().numpy()
+        p_keep = torch.zeros((1, 2, 1152), dtype=torch.float32).pin_memory()
+        p_buf = p_keep.numpy()
+    else:
+        u_buf, s_buf, p_buf = units, spectra, np.zeros((1, 2, 1152), dtype=np.float32)
+    one = runs.copy()
+    one["n_frames"] = 1
+    engine.mp3_streams_alloc(1)
+    got = np.zeros((F, 2, 1152), dtype=np.float32)
+    for f in range(F):
+        launches = engine.launch_count
+        engine.mp3_synth_host(u_buf[f:f + 1], s_buf[f:f + 1], one, out=p_buf)
+        assert engine.launch_count == launches + 1
+        got[f] = p_buf[0]
+    _compare(got, want, f"one packet per call, pinned={pinned}")
     engine.close()
