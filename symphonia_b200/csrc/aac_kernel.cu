@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kTnsWarps * 32) aac_tns_apply(const symgpu_aac
 // frame f and of frame f-1 (the `delay` of the reference is a pure function of frame f-1's output).
 constexpr int kAacK = kAacChunkFrames;     // frames per chunk, two warps per frame (named barriers)
 constexpr int kAacKWarp = kAacChunkFramesWarp; // frames per chunk, ONE warp per frame (__syncwarp only)
+constexpr int kAacKZ = kAacChunkFramesZ;       // the same with frame slots in the Z layout
 struct alignas(16) AacFrameSmem {
     float out[2048];          // spectrum (first 1024 floats) until the pre-twiddle has consumed it, then pcm_long
     float2 z[zpad_len(512)];
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
     };
     __shared__ bool is_last;
     const int tid = threadIdx.x;
-    const int grp = tid / GW, gt = tid % GW; // frame slot of this thread, thread within the slot's group
+    const int slot = tid / GW, gt = tid % GW; // frame slot of this thread's group in the CTA, thread within the group
     const CodecTables* __restrict__ tab = a.tab;
     {
         const float2* g_fft = reinterpret_cast<const float2*>(tab->fft_lit16);
@@ -329,18 +330,43 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
     __syncthreads();
     const FftTables* ft = reinterpret_cast<const FftTables*>(ts.fft);
 
-    for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
-        const CodecChunk ck = a.chunks[c];
+    const uint32_t* __restrict__ group_first = reinterpret_cast<const uint32_t*>(a.chunks + a.n_chunks);
+    const int lane = tid & 31;
+    // My chunk of group g and my slot inside it: the chunks of a group take count + 1 consecutive frame slots each.
+    auto locate = [&](int g, int& grp) -> int {
+        const uint32_t c0 = group_first[g], nc = group_first[g + 1] - c0;
+        const int cnt = (uint32_t)lane < nc ? (int)a.chunks[c0 + lane].count + 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const unsigned mine = __ballot_sync(0xffffffffu, cnt > 0 && incl - cnt <= slot && slot < incl);
+        if (!mine) {
+            grp = 0;
+            return -1;
+        }
+        const int j = __ffs(mine) - 1;
+        grp = slot - __shfl_sync(0xffffffffu, incl - cnt, j);
+        return (int)c0 + j;
+    };
+
+    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        int grp;
+        const int cidx = locate(g, grp);
+        const bool active = cidx >= 0;
+        const CodecChunk ck = active ? a.chunks[cidx] : CodecChunk{};
         const int ch = ck.channel;
-        const uint32_t gen = a.gen[ck.stream];
+        const uint32_t gen = active ? a.gen[ck.stream] : 0u;
         const float* st_in = a.states + (((size_t)ck.stream * 2 + (gen & 1)) * 2 + ch) * 1024;
         float* st_out = a.states + (((size_t)ck.stream * 2 + ((gen + 1) & 1)) * 2 + ch) * 1024;
         const bool load_state = ck.flags & kChunkLoadState;
-        const int count = ck.count;
+        const int count = active ? (int)ck.count : -1;
 
-        // slot 0 = the frame before the chunk (or the stream state), slot k = chunk frame k-1
+        // slot 0 of a chunk = the frame before it (or the stream state), slot k = chunk frame k-1
         const int f = (int)ck.first - 1 + grp;
-        const bool have_frame = grp <= count && (grp > 0 || !load_state);
+        const bool have_frame = active && grp <= count && (grp > 0 || !load_state);
         symgpu_aac_unit u = {};
         if (have_frame) {
             const size_t unit_idx = 2 * (size_t)f + ch;
@@ -349,15 +375,15 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
             if constexpr (ZL) {
                 WarpSync sync;
                 if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-                    imdct_to_z<9>(src, fs[grp].z, 1, ts.tw_long, ft, gt, 32, sync);
+                    imdct_to_z<9>(src, fs[slot].z, 1, ts.tw_long, ft, gt, 32, sync);
                 else
-                    imdct_to_z<6>(src, fs[grp].z, 8, ts.tw_short, ft, gt, 32, sync);
+                    imdct_to_z<6>(src, fs[slot].z, 8, ts.tw_short, ft, gt, 32, sync);
             } else {
-                auto& me = fs[grp];
+                auto& me = fs[slot];
                 for (int i = gt; i < 256; i += GW) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
                 // the spectrum sits in out[0..1024); the pre-twiddle reads all of it before anything is written back
                 if constexpr (GW == 64) {
-                    NamedSync sync{1 + grp, 64};
+                    NamedSync sync{1 + slot, 64};
                     sync();
                     if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
                         imdct_blocks<9>(me.out, me.out, me.z, 1, ts.tw_long, ft, gt, 64, sync);
@@ -372,31 +398,35 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
                         imdct_blocks<6>(me.out, me.out, me.z, 8, ts.tw_short, ft, gt, 32, sync);
                 }
             }
-        } else if (grp == 0) {
+        } else if (active && grp == 0) {
             // run start: slot 0 holds the delay line itself (Array layout: in out[1024..2048); Z layout: the first 1024 floats)
             if constexpr (ZL) {
-                for (int i = gt; i < 1024; i += GW) reinterpret_cast<float*>(fs[0].z)[i] = st_in[i];
+                for (int i = gt; i < 1024; i += GW) reinterpret_cast<float*>(fs[slot].z)[i] = st_in[i];
             } else {
-                for (int i = gt; i < 1024; i += GW) fs[0].out[1024 + i] = st_in[i];
+                for (int i = gt; i < 1024; i += GW) fs[slot].out[1024 + i] = st_in[i];
             }
         }
         __syncthreads();
 
-        // Pull the next chunk's spectra towards the SM (HBM -> L2) while this chunk is windowed.
-        if (c + (int)gridDim.x < a.n_chunks && gt < 32) {
-            const CodecChunk nk = a.chunks[c + gridDim.x];
-            const int nf = (int)nk.first - 1 + grp;
-            if (grp <= nk.count && (grp > 0 || !(nk.flags & kChunkLoadState))) {
-                const size_t nidx = 2 * (size_t)nf + nk.channel;
-                const float* nsrc = (a.units[nidx].n_tns ? a.tns_scratch : a.coeffs) + nidx * 1024;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 32 * gt));
+        // Pull the next group's spectra towards the SM (HBM -> L2) while this one is windowed.
+        if (g + (int)gridDim.x < a.n_groups && gt < 32) {
+            int ngrp;
+            const int nidx_c = locate(g + gridDim.x, ngrp);
+            if (nidx_c >= 0) {
+                const CodecChunk nk = a.chunks[nidx_c];
+                const int nf = (int)nk.first - 1 + ngrp;
+                if (ngrp > 0 || !(nk.flags & kChunkLoadState)) {
+                    const size_t nidx = 2 * (size_t)nf + nk.channel;
+                    const float* nsrc = (a.units[nidx].n_tns ? a.tns_scratch : a.coeffs) + nidx * 1024;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 32 * gt));
+                }
             }
         }
 
         // window + overlap-add (aac/dsp.rs:103-129): thread = (frame slot, sample)
-        if (grp >= 1 && grp <= count) {
-            const Out out = out_of(grp);
-            const Out pout = out_of(grp - 1);
+        if (active && grp >= 1 && grp <= count) {
+            const Out out = out_of(slot);
+            const Out pout = out_of(slot - 1);
             const symgpu_aac_unit pu = (grp > 1 || !load_state) ? a.units[2 * (size_t)(f - 1) + ch] : symgpu_aac_unit{};
             const bool prev_is_state = grp == 1 && load_state;
             const int seq = u.window_sequence, pseq = pu.window_sequence;
@@ -425,7 +455,7 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
                 for (int i = gt; i < 1024; i += GW) st_out[i] = aac_new_delay(seq, out, lw, sw, psw, i);
             }
         }
-        __syncthreads(); // the frame slots are reused by the next chunk
+        __syncthreads(); // the frame slots are reused by the next group
     }
 
     // launch epilogue: the last CTA publishes the new state generation (see mp3_kernel.cu)
@@ -457,11 +487,11 @@ static cudaError_t launch_variant(const AacArgs& b, cudaStream_t stream) {
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aac_synth_kernel<GW, K, ZL>, (K + 1) * GW, smem)) != cudaSuccess) return e;
         max_grid = n_sm * (per_sm > 0 ? per_sm : 1);
     }
-    aac_synth_kernel<GW, K, ZL><<<b.n_chunks < max_grid ? b.n_chunks : max_grid, (K + 1) * GW, smem, stream>>>(b);
+    aac_synth_kernel<GW, K, ZL><<<b.n_groups < max_grid ? b.n_groups : max_grid, (K + 1) * GW, smem, stream>>>(b);
     return cudaGetLastError();
 }
 
-cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, cudaStream_t stream) {
+cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream) {
     if (any_tns) {
         // owner[] starts at "no owner" so that filters outside every channel-frame's range are skipped
         cudaError_t e = cudaMemsetAsync(a.tns_owner, 0xff, (size_t)a.n_tns * sizeof(uint32_t), stream);
@@ -474,9 +504,10 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
     }
     AacArgs b = a;
     b.n_chunks = n_chunks;
+    b.n_groups = n_groups;
     switch (aac_kernel_variant()) {
         case 1: return launch_variant<32, kAacKWarp, false>(b, stream);
-        case 2: return launch_variant<32, kAacKWarp, true>(b, stream);
+        case 2: return launch_variant<32, kAacKZ, true>(b, stream);
         default: return launch_variant<64, kAacK, false>(b, stream);
     }
 }
@@ -491,6 +522,6 @@ int aac_kernel_variant() {
     return mode;
 }
 bool aac_warp_per_frame() { return aac_kernel_variant() != 0; }
-int aac_chunk_frames() { return aac_warp_per_frame() ? kAacKWarp : kAacK; }
+int aac_chunk_frames() { return aac_kernel_variant() == 2 ? kAacKZ : aac_kernel_variant() == 1 ? kAacKWarp : kAacK; }
 
 } // namespace symgpu

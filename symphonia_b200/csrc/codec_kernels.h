@@ -24,6 +24,7 @@ static_assert(sizeof(CodecChunk) == 16, "CodecChunk is 16 bytes");
 
 constexpr int kAacChunkFrames = 6;      // two warps per frame
 constexpr int kAacChunkFramesWarp = 13; // one warp per frame
+constexpr int kAacChunkFramesZ = 15;    // one warp per frame, Z layout (16 warps, two CTAs per SM)
 constexpr int kAacDefaultVariant = 0;    // 0 pair | 1 warp | 2 z (SYMGPU_AAC_KERNEL overrides)
 int aac_kernel_variant();
 bool aac_warp_per_frame();
@@ -41,6 +42,7 @@ struct AacArgs {
     uint32_t* tns_owner;        // [n_tns] channel-frame of each filter
     uint32_t n_tns;
     int n_chunks;               // filled in by aac_launch
+    int n_groups;               // filled in by aac_launch: group_first = (const uint32_t*)(chunks + n_chunks), n_groups + 1 entries
     float* pcm;
     const CodecChunk* chunks;
     float* states;              // [n_streams][2 generations][2 channels][1024]
@@ -77,7 +79,7 @@ struct VorbisArgs {
     const CodecTables* tab;
 };
 
-cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, cudaStream_t stream);
+cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream);
 cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream);
 // Multichannel helpers (symgpu_vorbis_mc_*): inverse coupling over every step of a mapping (lib.rs:252-278), in place on
 // residue [n_packets][channels][slot]; and the (block flags, floor, do-not-decode) records of channel pair `pair`.

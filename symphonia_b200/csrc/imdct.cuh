@@ -212,17 +212,18 @@ __device__ __forceinline__ void imdct_blocks(const float* spec, float* out, floa
 // memory per 1024-line block instead of 12.8 KB, a quarter of the shared-memory stores, and no staging of the spectrum: the
 // pre-twiddle reads it from where it lies (global memory), two mirrored float2 per pair of FFT inputs, every float used.
 //
-// spec: [batch][N] floats (8-byte aligned), N = 2^(LOG2+1); z: zpad_len(batch * 2^LOG2) float2 of shared memory.
-template <int LOG2, typename Sync>
-__device__ __forceinline__ void imdct_to_z(const float* __restrict__ spec, float2* z, int batch, const float2* __restrict__ tw,
-                                           const FftTables* __restrict__ ft, int tid, int n_threads, Sync sync) {
+// `pair(b, l)` returns the spectral lines (l, l + 1) of block b (l even): a plain load, or whatever produces the spectrum
+// (the Vorbis kernel multiplies floor and residue right here).  z: zpad_len(batch * 2^LOG2) float2 of shared memory.
+template <int LOG2, typename Pair, typename Sync>
+__device__ __forceinline__ void imdct_to_z_from(Pair pair, float2* z, int batch, const float2* __restrict__ tw,
+                                                const FftTables* __restrict__ ft, int tid, int n_threads, Sync sync) {
     constexpr int n2 = 1 << LOG2, n = 2 * n2, n4 = n2 / 2;
-    // FFT input i needs spec[2i] and spec[n-1-2i]; input n2-1-i needs spec[n-2-2i] and spec[2i+1]: the same two float2.
+    // FFT input i needs spec[2i] and spec[n-1-2i]; input n2-1-i needs spec[n-2-2i] and spec[2i+1]: the same two pairs.
+#pragma unroll 2
     for (int e = tid; e < batch * n4; e += n_threads) {
         const int b = e >> (LOG2 - 1), i = e & (n4 - 1), i2 = n2 - 1 - i;
-        const float* s = spec + b * n;
-        const float2 lo = __ldg(reinterpret_cast<const float2*>(s + 2 * i));
-        const float2 hi = __ldg(reinterpret_cast<const float2*>(s + n - 2 - 2 * i));
+        const float2 lo = pair(b, 2 * i);
+        const float2 hi = pair(b, n - 2 - 2 * i);
         {
             const float even = lo.x, odd = -hi.y;
             const float2 w = tw[i];
@@ -245,6 +246,14 @@ __device__ __forceinline__ void imdct_to_z(const float* __restrict__ spec, float
     sync();
 }
 
+// spec: [batch][N] floats in global memory (8-byte aligned), N = 2^(LOG2+1).
+template <int LOG2, typename Sync>
+__device__ __forceinline__ void imdct_to_z(const float* __restrict__ spec, float2* z, int batch, const float2* __restrict__ tw,
+                                           const FftTables* __restrict__ ft, int tid, int n_threads, Sync sync) {
+    auto pair = [spec](int b, int l) { return __ldg(reinterpret_cast<const float2*>(spec + (b << (LOG2 + 1)) + l)); };
+    imdct_to_z_from<LOG2>(pair, z, batch, tw, ft, tid, n_threads, sync);
+}
+
 // out[j] (0 <= j < 4 * n2) of block `b` after imdct_to_z, bit for bit what imdct_blocks stores.
 template <int LOG2>
 __device__ __forceinline__ float imdct_out(const float2* z, int b, int j) {
@@ -257,6 +266,18 @@ __device__ __forceinline__ float imdct_out(const float2* z, int b, int j) {
     const int k = low ? half : n4 + half;
     const float2 v = z[zpad((b << LOG2) + k)];
     // low: quarters 0, 1 -> im, quarters 2, 3 -> re; high: quarters 0, 1 -> re, quarters 2, 3 -> im
+    const float val = ((q >> 1) ^ (low ? 0 : 1)) ? v.x : v.y;
+    return q == 0 ? -val : val;
+}
+
+// The same for a block size known only at run time (one block: b = 0).
+__device__ __forceinline__ float imdct_out_rt(const float2* z, int log2, int j) {
+    const int n2 = 1 << log2, n4 = n2 >> 1;
+    const int q = j >> log2, r = j & (n2 - 1);
+    const bool odd = r & 1;
+    const bool low = (q & 1) ? !odd : odd;
+    const int half = odd ? (n2 - 1 - r) >> 1 : r >> 1;
+    const float2 v = z[zpad(low ? half : n4 + half)];
     const float val = ((q >> 1) ^ (low ? 0 : 1)) ? v.x : v.y;
     return q == 0 ? -val : val;
 }

@@ -134,10 +134,30 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
     if (!reuse) {
         if (covered > n_frames) return SYMGPU_ERR_ARG; // runs may leave frames out (a stream that lost packets), never overlap
         ctx->chunk_key.clear();
+        // A CTA pass takes a GROUP of consecutive chunks whose frame slots (count + 1 each: the state or the frame before the
+        // chunk rides along) fit its warps, so short runs (a stream that submits a few frames per call) still fill the CTA.
+        // group_first[g] .. group_first[g + 1] are the chunks of group g; the array travels behind the chunk list.
+        const size_t n_chunks = chunks.size();
+        std::vector<uint32_t> group_first;
+        const uint32_t cap_slots = (uint32_t)aac_chunk_frames() + 1;
+        uint32_t used = cap_slots + 1; // forces the first chunk to open a group
+        for (size_t i = 0; i < n_chunks; ++i) {
+            const uint32_t need = (uint32_t)chunks[i].count + 1;
+            if (used + need > cap_slots) {
+                group_first.push_back((uint32_t)i);
+                used = 0;
+            }
+            used += need;
+        }
+        const size_t n_groups = group_first.size();
+        group_first.push_back((uint32_t)n_chunks);
+        chunks.resize(n_chunks + (group_first.size() * sizeof(uint32_t) + sizeof(CodecChunk) - 1) / sizeof(CodecChunk));
+        std::memcpy(static_cast<void*>(chunks.data() + n_chunks), group_first.data(), group_first.size() * sizeof(uint32_t));
         s = upload_chunks(ctx, chunks);
         if (s != SYMGPU_OK) return s;
         ctx->chunk_key = key;
-        ctx->cached_chunks = (int)chunks.size();
+        ctx->cached_chunks = (int)n_chunks;
+        ctx->cached_groups = (int)n_groups;
     }
     const size_t spec_bytes = (size_t)n_frames * 2 * 1024 * sizeof(float);
     if (n_tns && spec_bytes > ctx->aac_scratch_cap) {
@@ -158,9 +178,9 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
         ctx->aac_tns_idx_cap = cap;
     }
     AacArgs a{units, tns, coeffs, ctx->d_aac_scratch, ctx->d_aac_scratch,
-              ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0,
+              ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0, 0,
               pcm, ctx->d_chunks, ctx->d_aac_states, ctx->d_aac_gen, ctx->d_aac_gen + ctx->n_aac_streams, ctx->d_codec_tab};
-    CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, ctx->cached_chunks, ctx->stream));
+    CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, ctx->cached_chunks, ctx->cached_groups, ctx->stream));
     ctx->launches += n_tns ? 4 : 1;
     return SYMGPU_OK;
 }

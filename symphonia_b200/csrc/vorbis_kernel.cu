@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/symgpu.h"
 #include "codec_kernels.h"
@@ -405,6 +406,170 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
     }
 }
 
+
+// =========================================================================================================================
+// Z layout (the default): one WARP per (packet, channel).  The IMDCT output is kept as its post-twiddled complex values
+// (imdct.cuh: imdct_to_z / imdct_out), floor x residue is formed inside the pre-twiddle straight from global memory, and the
+// floor points share the bytes of z (they are dead once the curve is rendered).  A unit then takes 5.8 KB of shared memory at
+// blocksize_1 = 2048 instead of 10.5 KB, the kernel runs at 64 registers, and two CTAs of 8 packet slots share an SM: 32 warps
+// per SM instead of 16, and no named barrier anywhere -- channels only meet in the inverse coupling, which both warps of a
+// packet evaluate from the two residues.
+// =========================================================================================================================
+__host__ __device__ inline size_t vorbis_unit_z_bytes(int slot_smem) {  // z | floor points | the state tail of slot 0
+    size_t b = sizeof(float2) * zpad_len(slot_smem / 2);
+    if (b < sizeof(FloorPoints)) b = sizeof(FloorPoints);
+    return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t vorbis_unit_bytes(int slot_smem) { // + one table index per line (ybuf_index pads)
+    return vorbis_unit_z_bytes(slot_smem) + (((size_t)slot_smem + 128 + 15) & ~(size_t)15);
+}
+
+template <int LOG2, typename Pair>
+__device__ __forceinline__ void imdct_z_one(Pair pair, float2* z, const CodecTables* tab, int lane) {
+    const FftTables* ft = reinterpret_cast<const FftTables*>(tab->fft_lit16);
+    const float2* tw = reinterpret_cast<const float2*>(tab->vorbis_tw) + ((1 << LOG2) - 16);
+    imdct_to_z_from<LOG2>(pair, z, 1, tw, ft, lane, 32, WarpSync{});
+}
+
+__global__ void __launch_bounds__(512, 2) vorbis_synth_kernel_z(VorbisArgs a, int slot_smem) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    __shared__ bool is_last;
+    __shared__ float inv_db_s[256]; // floor1_inverse_dB_table (floor.rs:21-86)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp >> 1, ch = warp & 1; // packet slot, channel
+    const size_t unit_bytes = vorbis_unit_bytes(slot_smem), z_bytes = vorbis_unit_z_bytes(slot_smem);
+    auto unit_z = [&](int k, int c) { return reinterpret_cast<float2*>(raw + (size_t)(2 * k + c) * unit_bytes); };
+    auto unit_y = [&](int k, int c) { return raw + (size_t)(2 * k + c) * unit_bytes + z_bytes; };
+
+    if (threadIdx.x < 256) inv_db_s[threadIdx.x] = a.tab->vorbis_inverse_db[threadIdx.x];
+    __syncthreads();
+    const CodecChunk ck = a.chunks[blockIdx.x];
+    const symgpu_vorbis_stream cfg = a.streams[ck.stream];
+    const CodecTables* __restrict__ tab = a.tab;
+    const int bs0 = 1 << cfg.bs0_exp, bs1 = 1 << cfg.bs1_exp;
+    const int n_ch = cfg.channels;
+    const uint32_t gen = a.gen[ck.stream];
+    const float* st_in = a.states + ((size_t)ck.stream * 2 + (gen & 1)) * kVorbisStateFloats;
+    float* st_out = a.states + ((size_t)ck.stream * 2 + ((gen + 1) & 1)) * kVorbisStateFloats;
+    const bool load_state = ck.flags & kChunkLoadState;
+    const int count = ck.count;
+    const int half1 = bs1 >> 1;
+
+    // slot 0 = the packet before the chunk (or the stream state), slot k = chunk packet k-1
+    const int p = (int)ck.first - 1 + grp;
+    const bool have_packet = grp <= count && (grp > 0 || !load_state);
+    symgpu_vorbis_unit u = {};
+    int bs = bs0;
+    if (have_packet && ch < n_ch) {
+        u = a.units[p];
+        bs = u.block_flag ? bs1 : bs0;
+        const int n2 = bs >> 1;
+        const float* r0 = a.residue + ((size_t)p * a.pkt_ch + a.ch_base) * a.slot;
+        const float* r1 = r0 + a.slot;
+        // pull this channel's residue towards the SM while the floor is built (the other channel's warp pulls the other one)
+        for (int i = 32 * lane; i < n2; i += 32 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"((ch ? r1 : r0) + i));
+        // (1) floor curve as one table index per line
+        const int log2_l = 31 - __clz(n2 >> 5);
+        const bool used = u.floor[ch] != 0xffff && u.floor[ch] < a.n_floors;
+        const uint8_t* yb = unit_y(grp, ch);
+        if (used) {
+            FloorPoints& pts = *reinterpret_cast<FloorPoints*>(unit_z(grp, ch));
+            floor1_build(a.floors[u.floor[ch]], a.floor_aux[u.floor[ch]], a.floor_y + ((size_t)p * a.pkt_ch + a.ch_base + ch) * 65, n2, pts, lane);
+            floor1_render(pts, n2, lane, unit_y(grp, ch));
+        }
+        __syncwarp();
+        // (2) + (3) inverse coupling (lib.rs:267-277: the comparisons are "> 0.0"), floor x residue (an unused floor is all
+        //     zeros) and the IMDCT's pre-twiddle in one pass over the lines; then the FFT and the post-twiddle in place
+        const bool couple = cfg.coupled && n_ch == 2;
+        const bool dnd = u.do_not_decode[ch] != 0;
+        auto line = [&](float m, float ang, int i) -> float {
+            if (couple) {
+                float nm, na;
+                if (m > 0.0f) {
+                    if (ang > 0.0f) { nm = m; na = m - ang; } else { nm = m + ang; na = m; }
+                } else {
+                    if (ang > 0.0f) { nm = m; na = m + ang; } else { nm = m - ang; na = m; }
+                }
+                m = nm;
+                ang = na;
+            }
+            const float f = used ? inv_db_s[yb[ybuf_index(i, log2_l)]] : 0.0f;
+            return dnd ? f : f * (ch ? ang : m);
+        };
+        auto pair = [&](int, int l) -> float2 {
+            const float2 m = __ldg(reinterpret_cast<const float2*>(r0 + l));
+            const float2 g = n_ch == 2 ? __ldg(reinterpret_cast<const float2*>(r1 + l)) : make_float2(0.0f, 0.0f);
+            return make_float2(line(m.x, g.x, l), line(m.y, g.y, l + 1));
+        };
+        float2* z = unit_z(grp, ch);
+        switch (31 - __clz(bs >> 2)) { // FFT size = blocksize / 4
+            case 4: imdct_z_one<4>(pair, z, tab, lane); break;
+            case 5: imdct_z_one<5>(pair, z, tab, lane); break;
+            case 6: imdct_z_one<6>(pair, z, tab, lane); break;
+            case 7: imdct_z_one<7>(pair, z, tab, lane); break;
+            case 8: imdct_z_one<8>(pair, z, tab, lane); break;
+            case 9: imdct_z_one<9>(pair, z, tab, lane); break;
+            case 10: imdct_z_one<10>(pair, z, tab, lane); break;
+            default: imdct_z_one<11>(pair, z, tab, lane); break;
+        }
+    } else if (grp == 0 && ch < n_ch) {
+        // run start: slot 0 holds the overlap line itself (plain floats where a packet would keep z)
+        float* zf = reinterpret_cast<float*>(unit_z(0, ch));
+        for (int i = lane; i < half1; i += 32) zf[i] = st_in[ch * half1 + i];
+    }
+    __syncthreads();
+
+    // (4) window + overlap-add against the previous packet's tail (dsp.rs:83-122)
+    if (grp >= 1 && grp <= count && ch < n_ch) {
+        const bool block_flag = u.block_flag != 0, prev_flag = u.prev_block_flag != 0;
+        const bool prev_is_state = grp == 1 && load_state;
+        const int pbs = prev_is_state ? bs1 : (a.units[p - 1].block_flag ? bs1 : bs0); // geometry of slot grp-1's tail
+        const int out_len = ((prev_flag ? bs1 : bs0) + bs) >> 2;
+        const float* win = tab->vorbis_win + (((block_flag && prev_flag) ? bs1 : bs0) / 2 - 32);
+        const float2* zc = unit_z(grp, ch);
+        const float2* zp = unit_z(grp - 1, ch);
+        const int lg = 31 - __clz(bs >> 2), plg = 31 - __clz(pbs >> 2);
+        auto out = [&](int j) { return imdct_out_rt(zc, lg, j); };
+        // overlap[k] = imdct[pbs/2 + k] of the previous packet, or the state line
+        auto ov = [&](int k) { return prev_is_state ? reinterpret_cast<const float*>(zp)[k] : imdct_out_rt(zp, plg, (pbs >> 1) + k); };
+        float* dst = a.pcm + ((size_t)p * a.pkt_ch + a.ch_base + ch) * a.slot;
+        if (prev_flag == block_flag) {
+            const int len = bs / 2;
+#pragma unroll 4
+            for (int k = lane; k < len; k += 32) dst[k] = ov(k) * __ldg(win + len - 1 - k) + out(k) * __ldg(win + k);
+        } else if (prev_flag && !block_flag) {
+            const int start = (bs1 - bs0) / 4, len = bs0 / 2;
+            for (int k = lane; k < out_len; k += 32) {
+                if (k < start) dst[k] = ov(k);
+                else {
+                    const int j = k - start;
+                    dst[k] = ov(k) * __ldg(win + len - 1 - j) + out(j) * __ldg(win + j);
+                }
+            }
+        } else {
+            const int start = (bs1 - bs0) / 4, len = bs0 / 2, end = start + len;
+            for (int k = lane; k < out_len; k += 32) {
+                if (k < len) dst[k] = ov(k) * __ldg(win + len - 1 - k) + out(start + k) * __ldg(win + k);
+                else dst[k] = out(end + (k - len));
+            }
+        }
+        if (grp == count && (ck.flags & kChunkStoreState)) // the run's last packet leaves its tail in the state
+            for (int k = lane; k < bs / 2; k += 32) st_out[ch * half1 + k] = out(bs / 2 + k);
+    }
+
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        for (unsigned i = tid; i < gridDim.x; i += blockDim.x)
+            if (a.chunks[i].flags & kChunkStoreState) a.gen[a.chunks[i].stream] += 1;
+        if (tid == 0) *a.done = 0;
+    }
+}
+
 } // namespace
 
 
@@ -471,7 +636,23 @@ cudaError_t vorbis_mc_split_units_launch(const symgpu_vorbis_unit_mc* units, uin
     return cudaGetLastError();
 }
 
+// SYMGPU_VORBIS_KERNEL = z (one warp per packet-channel, Z layout: the default) | pair (64 threads per packet, array layout)
+bool vorbis_kernel_z() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* env = getenv("SYMGPU_VORBIS_KERNEL");
+        mode = (env && env[0] == 'p') ? 0 : 1;
+    }
+    return mode == 1;
+}
+
 int vorbis_slots_for(int max_bs1_exp) {
+    if (vorbis_kernel_z()) {
+        // eight slots when two CTAs of them share an SM or when they fit at all; fewer for the largest blocks
+        const size_t per = 2 * vorbis_unit_bytes(1 << (max_bs1_exp - 1));
+        const int n = (int)((216u * 1024u) / per);
+        return n < 2 ? 2 : (n > 8 ? 8 : n);
+    }
     const size_t per = vorbis_slot_bytes(1 << (max_bs1_exp - 1));
     const int n = (int)((200u * 1024u) / per);
     return n < 2 ? 2 : (n > 8 ? 8 : n);
@@ -480,6 +661,17 @@ int vorbis_slots_for(int max_bs1_exp) {
 cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream) {
     const int slot_smem = 1 << (max_bs1_exp - 1);
     const int n_slots = vorbis_slots_for(max_bs1_exp);
+    if (vorbis_kernel_z()) {
+        const size_t smem = 2 * vorbis_unit_bytes(slot_smem) * n_slots;
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(vorbis_synth_kernel_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        vorbis_synth_kernel_z<<<n_chunks, n_slots * 64, smem, stream>>>(a, slot_smem);
+        return cudaGetLastError();
+    }
     const size_t smem = vorbis_slot_bytes(slot_smem) * n_slots;
     static size_t configured = 0;
     if (smem > configured) {

@@ -7,4 +7,5 @@ for k in ${AAC_VARIANTS:-pair warp z}; do
   SYMGPU_AAC_KERNEL=$k timeout 600 python -m pytest tests/test_aac_vorbis_parity_gpu.py -m gpu -x -q -k "aac or Aac or AAC" 2>&1 | tail -3
   SYMGPU_AAC_KERNEL=$k timeout 300 python bench_codecs.py --codec aac --steps 30 --warmup 5 2>&1 | tail -2
   SYMGPU_AAC_KERNEL=$k timeout 300 python bench_codecs.py --codec aac --steps 30 --warmup 5 --tns 0 2>&1 | tail -1
+  SYMGPU_AAC_KERNEL=$k timeout 300 python bench_codecs.py --codec mixed --steps 20 --warmup 5 2>&1 | tail -1 | cut -c1-600
 done
