@@ -438,8 +438,18 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
             const float* q_sw = ts.win_short[pu.window_shape ? 1 : 0];
             const float* q_psw = ts.win_short[pu.prev_window_shape ? 1 : 0];
             float* dst = a.pcm + (2 * (size_t)f + ch) * 1024;
+            bool done = false;
+            if constexpr (ZL) {
+                // long block after long block (the common case): straight from the two z arrays, two adjacent samples at a time
+                if (!prev_is_state && (seq == SYMGPU_AAC_ONLY_LONG || seq == SYMGPU_AAC_LONG_START) &&
+                    (pseq == SYMGPU_AAC_ONLY_LONG || pseq == SYMGPU_AAC_LONG_STOP)) {
+                    auto win2 = [plw, q_lw](bool fall, int idx) { return *reinterpret_cast<const float2*>((fall ? q_lw : plw) + idx); };
+                    overlap_add_equal(fs[slot].z, fs[slot - 1].z, 9, win2, dst, gt, 32);
+                    done = true;
+                }
+            }
 #pragma unroll 4
-            for (int i = gt; i < 1024; i += GW) {
+            for (int i = gt; i < 1024 && !done; i += GW) {
                 const float d = prev_is_state ? pout.state(i) : aac_new_delay(pseq, pout, q_lw, q_sw, q_psw, i);
                 float y;
                 switch (seq) {

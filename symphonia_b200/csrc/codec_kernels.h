@@ -77,6 +77,7 @@ struct VorbisArgs {
     uint32_t* gen;
     unsigned* done;
     const CodecTables* tab;
+    void* floor_pts;            // scratch of the floor pre-pass (Z kernel): vorbis_floor_pts_bytes(n_packets) bytes
 };
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream);
@@ -89,5 +90,7 @@ cudaError_t vorbis_mc_split_units_launch(const symgpu_vorbis_unit_mc* units, uin
                                          cudaStream_t stream);
 // Packet slots per CTA (chunk packets + 1) for a batch whose largest blocksize_1 is 2^max_bs1_exp.
 int vorbis_slots_for(int max_bs1_exp);
+bool vorbis_kernel_z();
+size_t vorbis_floor_pts_bytes(uint32_t n_packets);
 
 } // namespace symgpu

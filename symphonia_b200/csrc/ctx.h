@@ -70,6 +70,8 @@ struct symgpu_ctx {
     // the chunk list on the device is reused while the caller repeats the same runs (tag + raw run bytes)
     std::vector<unsigned char> chunk_key;
     int cached_chunks = 0;
+    void* d_vorbis_floor_pts = nullptr; // scratch of the Vorbis floor pre-pass
+    size_t vorbis_floor_pts_cap = 0;
     int cached_groups = 0; // AAC: CTA passes (groups of chunks) of the cached list
     float* d_aac_states = nullptr;   // [n][2 gen][2 ch][1024]
     uint32_t* d_aac_gen = nullptr;   // [n] + retired-CTA counter

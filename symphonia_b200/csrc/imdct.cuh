@@ -270,6 +270,40 @@ __device__ __forceinline__ float imdct_out(const float2* z, int b, int j) {
     return q == 0 ? -val : val;
 }
 
+// Window + overlap-add of two equally sized blocks straight from their z arrays:
+//   dst[j] = prev_out[2*n2 + j] * fall[len - 1 - j] + cur_out[j] * rise[j],   0 <= j < len = 2 * n2
+// (the reference's `overlap * win[len-1-j] + imdct[j] * win[j]`, dsp.rs:96-101; aac/dsp.rs:104-108 is the same expression).
+// Iteration i (0 <= i < n2 / 2) produces the adjacent outputs (2i, 2i+1) and (n2+2i, n2+2i+1): by the post-twiddle's scatter
+// (see imdct_out) they are, for the current block, (-z[n4+i].re, -z[n4-1-i].im) and (z[i].im, z[n2-1-i].re), and for the second
+// half of the previous block (z[n4+i].im, z[n4-1-i].re) and (z[i].re, z[n2-1-i].im) -- four 8-byte loads per block for four
+// outputs, no index arithmetic per sample, 8-byte stores.  fall / rise: `len` floats each, 8-byte aligned.
+template <typename WinLoad>
+__device__ __forceinline__ void overlap_add_equal(const float2* zc, const float2* zp, int log2, WinLoad win2, float* dst, int tid,
+                                                  int n_threads) {
+    const int n2 = 1 << log2, n4 = n2 >> 1, len = 2 * n2;
+#pragma unroll 2
+    for (int i = tid; i < n4; i += n_threads) {
+        const float2 ca = zc[zpad(n4 + i)], cb = zc[zpad(n4 - 1 - i)], cc = zc[zpad(i)], cd = zc[zpad(n2 - 1 - i)];
+        const float2 pa = zp[zpad(n4 + i)], pb = zp[zpad(n4 - 1 - i)], pc = zp[zpad(i)], pd = zp[zpad(n2 - 1 - i)];
+        {
+            const int j = 2 * i;
+            const float2 r = win2(false, j), f = win2(true, len - 2 - j); // f = (fall for j + 1, fall for j)
+            float2 y;
+            y.x = pa.y * f.y + (-ca.x) * r.x;
+            y.y = pb.x * f.x + (-cb.y) * r.y;
+            *reinterpret_cast<float2*>(dst + j) = y;
+        }
+        {
+            const int j = n2 + 2 * i;
+            const float2 r = win2(false, j), f = win2(true, len - 2 - j);
+            float2 y;
+            y.x = pc.x * f.y + cc.y * r.x;
+            y.y = pd.y * f.x + cd.x * r.y;
+            *reinterpret_cast<float2*>(dst + j) = y;
+        }
+    }
+}
+
 // The same for a block size known only at run time (one block: b = 0).
 __device__ __forceinline__ float imdct_out_rt(const float2* z, int log2, int j) {
     const int n2 = 1 << log2, n4 = n2 >> 1;

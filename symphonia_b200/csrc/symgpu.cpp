@@ -577,6 +577,7 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (ctx->d_vorbis_streams) cudaFree(ctx->d_vorbis_streams);
     if (ctx->d_vorbis_floors) cudaFree(ctx->d_vorbis_floors);
     if (ctx->d_vorbis_floor_aux) cudaFree(ctx->d_vorbis_floor_aux);
+    if (ctx->d_vorbis_floor_pts) cudaFree(ctx->d_vorbis_floor_pts);
     if (ctx->d_vorbis_states) cudaFree(ctx->d_vorbis_states);
     if (ctx->d_vorbis_gen) cudaFree(ctx->d_vorbis_gen);
     if (ctx->d_vorbis_mc_streams) cudaFree(ctx->d_vorbis_mc_streams);
