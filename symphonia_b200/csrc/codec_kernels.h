@@ -25,7 +25,7 @@ static_assert(sizeof(CodecChunk) == 16, "CodecChunk is 16 bytes");
 constexpr int kAacChunkFrames = 6;      // two warps per frame
 constexpr int kAacChunkFramesWarp = 13; // one warp per frame
 constexpr int kAacChunkFramesZ = 15;    // one warp per frame, Z layout (16 warps, two CTAs per SM)
-constexpr int kAacDefaultVariant = 0;    // 0 pair | 1 warp | 2 z (SYMGPU_AAC_KERNEL overrides)
+constexpr int kAacDefaultVariant = 2;    // 0 pair | 1 warp | 2 z (SYMGPU_AAC_KERNEL overrides)
 int aac_kernel_variant();
 bool aac_warp_per_frame();
 int aac_chunk_frames();                 // frames per chunk of the variant in use
@@ -77,7 +77,6 @@ struct VorbisArgs {
     uint32_t* gen;
     unsigned* done;
     const CodecTables* tab;
-    void* floor_pts;            // scratch of the floor pre-pass (Z kernel): vorbis_floor_pts_bytes(n_packets) bytes
 };
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream);
@@ -91,6 +90,5 @@ cudaError_t vorbis_mc_split_units_launch(const symgpu_vorbis_unit_mc* units, uin
 // Packet slots per CTA (chunk packets + 1) for a batch whose largest blocksize_1 is 2^max_bs1_exp.
 int vorbis_slots_for(int max_bs1_exp);
 bool vorbis_kernel_z();
-size_t vorbis_floor_pts_bytes(uint32_t n_packets);
 
 } // namespace symgpu

@@ -61,7 +61,11 @@ struct symgpu_ctx {
     int h2d_ahead = 2; // slices whose H2D copy is queued before the host's descriptor check and planning (SYMGPU_H2D_AHEAD)
     int n_slices = 8; // slices of a host batch in the copy pipeline (SYMGPU_SLICES overrides, for tuning)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t copy_in2 = nullptr, copy_out2 = nullptr; // odd slices (SYMGPU_COPY_STREAMS=2): the next copy is already queued on
+                                                          // another engine when one ends, so the link does not idle between slices
+    int copy_streams = 1; // 2 was measured slower (2.6 ms against 2.27 ms per step): copies of one direction on two streams delay each other
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
+    cudaEvent_t ev_units = nullptr;
     // ---- AAC / Vorbis ----
     symgpu::CodecTables* d_codec_tab = nullptr;
     symgpu::CodecChunk* d_chunks = nullptr;
@@ -70,8 +74,6 @@ struct symgpu_ctx {
     // the chunk list on the device is reused while the caller repeats the same runs (tag + raw run bytes)
     std::vector<unsigned char> chunk_key;
     int cached_chunks = 0;
-    void* d_vorbis_floor_pts = nullptr; // scratch of the Vorbis floor pre-pass
-    size_t vorbis_floor_pts_cap = 0;
     int cached_groups = 0; // AAC: CTA passes (groups of chunks) of the cached list
     float* d_aac_states = nullptr;   // [n][2 gen][2 ch][1024]
     uint32_t* d_aac_gen = nullptr;   // [n] + retired-CTA counter

@@ -506,6 +506,7 @@ symgpu_status symgpu_ctx_create(int device, symgpu_ctx** out) {
     if (!ctx) return SYMGPU_ERR_LIMIT;
     ctx->device = device;
     // SYMGPU_ZERO_COPY = 0 never (default) | 1 output only | 2 input and output
+    if (const char* env = std::getenv("SYMGPU_COPY_STREAMS")) ctx->copy_streams = std::atoi(env) >= 2 ? 2 : 1;
     if (const char* env = std::getenv("SYMGPU_ZERO_COPY")) {
         ctx->zero_copy = env[0] == '0' ? 0 : env[0] == '2' ? 2 : 1;
         ctx->zero_copy_small = env[0] != '0' && env[0] != 's'; // "0": never; "s": staged copies for small batches too
@@ -577,13 +578,15 @@ void symgpu_ctx_destroy(symgpu_ctx* ctx) {
     if (ctx->d_vorbis_streams) cudaFree(ctx->d_vorbis_streams);
     if (ctx->d_vorbis_floors) cudaFree(ctx->d_vorbis_floors);
     if (ctx->d_vorbis_floor_aux) cudaFree(ctx->d_vorbis_floor_aux);
-    if (ctx->d_vorbis_floor_pts) cudaFree(ctx->d_vorbis_floor_pts);
     if (ctx->d_vorbis_states) cudaFree(ctx->d_vorbis_states);
     if (ctx->d_vorbis_gen) cudaFree(ctx->d_vorbis_gen);
     if (ctx->d_vorbis_mc_streams) cudaFree(ctx->d_vorbis_mc_streams);
     if (ctx->d_vorbis_mc_scratch) cudaFree(ctx->d_vorbis_mc_scratch);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    if (ctx->copy_in2) cudaStreamDestroy(ctx->copy_in2);
+    if (ctx->ev_units) cudaEventDestroy(ctx->ev_units);
+    if (ctx->copy_out2) cudaStreamDestroy(ctx->copy_out2);
     for (int i = 0; i < symgpu_ctx::kMaxSlices; ++i) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
@@ -804,6 +807,9 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     if (!ctx->copy_in) {
         CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_in2, cudaStreamNonBlocking));
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_out2, cudaStreamNonBlocking));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_units, cudaEventDisableTiming));
         for (int i = 0; i < symgpu_ctx::kMaxSlices; ++i) {
             CU(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
             CU(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
@@ -840,10 +846,31 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     //    queueing every H2D copy up front was measured to serialise the two directions (2.9 ms instead of 2.2 ms per step).
     // (with the output written by the kernels there are no D2H copies to interleave with: everything is queued at once)
     const size_t ahead = out_mapped ? slices.size() : std::min<size_t>(slices.size(), (size_t)std::max(1, ctx->h2d_ahead));
+    // SYMGPU_E2E_TRACE=1: timing events around every copy and launch of the pipeline, printed after the call (diagnostics only)
+    static const bool trace = [] { const char* e = std::getenv("SYMGPU_E2E_TRACE"); return e && e[0] == '1'; }();
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    const bool two = ctx->copy_streams >= 2;
+    auto cin = [&](size_t i) { return (two && (i & 1)) ? ctx->copy_in2 : ctx->copy_in; };
+    auto cout_ = [&](size_t i) { return (two && (i & 1)) ? ctx->copy_out2 : ctx->copy_out; };
+    mark(ctx->copy_in); // t0
     CU(ctx, cudaMemcpyAsync(d_units, units, unit_bytes, cudaMemcpyHostToDevice, ctx->copy_in)); // 256 B per frame: one copy
+    // the descriptors travel on the first copy stream; the second one must not overtake them
+    if (two) {
+        CU(ctx, cudaEventRecord(ctx->ev_units, ctx->copy_in));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_units, 0));
+    }
     for (size_t i = 0; i < ahead; ++i) {
-        CU(ctx, copy_in(slices[i].f0, slices[i].f1 - slices[i].f0, ctx->copy_in));
-        CU(ctx, cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
+        mark(cin(i));
+        CU(ctx, copy_in(slices[i].f0, slices[i].f1 - slices[i].f0, cin(i)));
+        mark(cin(i));
+        CU(ctx, cudaEventRecord(ctx->ev_in[i], cin(i)));
     }
     // 2. host work under those copies: descriptor check (helper threads) and the launch plans of the slices -- which are kept
     //    (and stay on the device) while the caller repeats the same runs
@@ -897,6 +924,7 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
     }
     if (s != SYMGPU_OK) {
         cudaStreamSynchronize(ctx->copy_in); // the copies read the caller's buffers; nothing has been launched
+        if (two) cudaStreamSynchronize(ctx->copy_in2);
         return s;
     }
     // 3. kernels as the slices land, D2H copies as the kernels finish, the next H2D copy behind each D2H copy
@@ -904,25 +932,43 @@ static symgpu_status mp3_synth_host_impl(symgpu_ctx* ctx, const symgpu_mp3_gc* u
         const Slice& sl = slices[i];
         const size_t nf = sl.f1 - sl.f0;
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+        mark(ctx->stream);
         if (sl.n_tiles > 0) {
             CU(ctx, launch_plan(ctx, ctx->d_tiles + sl.t0, sl.hdr, sl.n_tiles, sl.n_ctas, sl.multi, sl.v2, d_units, d_spec, d_pcm, ctx->stream));
             ctx->launches += 1;
         }
         CU(ctx, pack(sl.f0, (uint32_t)nf));
+        mark(ctx->stream);
         if (!out_mapped) {
             CU(ctx, cudaEventRecord(ctx->ev_k[i], ctx->stream));
-            CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[i], 0));
+            CU(ctx, cudaStreamWaitEvent(cout_(i), ctx->ev_k[i], 0));
+            mark(cout_(i));
             CU(ctx, cudaMemcpyAsync(out_bytes + (size_t)sl.f0 * frame_out_bytes, d_result + (size_t)sl.f0 * frame_out_bytes,
-                                    nf * frame_out_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+                                    nf * frame_out_bytes, cudaMemcpyDeviceToHost, cout_(i)));
+            mark(cout_(i));
         }
         if (i + ahead < slices.size()) {
             const Slice& nx = slices[i + ahead];
-            CU(ctx, copy_in(nx.f0, nx.f1 - nx.f0, ctx->copy_in));
-            CU(ctx, cudaEventRecord(ctx->ev_in[i + ahead], ctx->copy_in));
+            mark(cin(i + ahead));
+            CU(ctx, copy_in(nx.f0, nx.f1 - nx.f0, cin(i + ahead)));
+            mark(cin(i + ahead));
+            CU(ctx, cudaEventRecord(ctx->ev_in[i + ahead], cin(i + ahead)));
         }
     }
     CU(ctx, cudaStreamSynchronize(ctx->copy_out));
+    if (two) CU(ctx, cudaStreamSynchronize(ctx->copy_out2));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (trace && !tev.empty()) {
+        // marks in issue order: t0 | (h2d start, end) x ahead | per slice: k start, k end, [d2h start, end], [h2d start, end]
+        std::fprintf(stderr, "symgpu e2e trace (ms from the first copy; %zu slices, %zu H2D ahead):", slices.size(), ahead);
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            std::fprintf(stderr, "%s%.3f", (i % 2) ? "  " : "-", ms);
+        }
+        std::fprintf(stderr, "\n");
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return SYMGPU_OK;
 }
 

@@ -397,20 +397,11 @@ static symgpu_status vorbis_synth_dev_impl(symgpu_ctx* ctx, const symgpu_vorbis_
         ctx->cached_chunks = (int)chunks.size();
     }
     if (ctx->cached_chunks == 0) return SYMGPU_OK;
-    const size_t pts_bytes = vorbis_floor_pts_bytes(n_packets);
-    if (pts_bytes > ctx->vorbis_floor_pts_cap) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_vorbis_floor_pts) cudaFree(ctx->d_vorbis_floor_pts);
-        ctx->d_vorbis_floor_pts = nullptr;
-        ctx->vorbis_floor_pts_cap = 0;
-        CU(ctx, cudaMalloc(&ctx->d_vorbis_floor_pts, pts_bytes + pts_bytes / 4));
-        ctx->vorbis_floor_pts_cap = pts_bytes + pts_bytes / 4;
-    }
     VorbisArgs a{units, floor_y, residue, pcm, ctx->d_chunks, ctx->d_vorbis_streams, ctx->d_vorbis_floors,
                  ctx->d_vorbis_floor_aux, ctx->n_vorbis_floors, slot, pkt_ch, ch_base, ctx->d_vorbis_states, ctx->d_vorbis_gen,
-                 ctx->d_vorbis_gen + ctx->n_vorbis_streams, ctx->d_codec_tab, ctx->d_vorbis_floor_pts};
+                 ctx->d_vorbis_gen + ctx->n_vorbis_streams, ctx->d_codec_tab};
     CU(ctx, vorbis_launch(a, ctx->cached_chunks, max_bs1, ctx->stream));
-    ctx->launches += vorbis_kernel_z() ? 2 : 1;
+    ctx->launches += 1;
     return SYMGPU_OK;
 }
 

@@ -411,93 +411,6 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
 }
 
 
-// ---- floor points, one THREAD per (packet, channel) ------------------------------------------------------------------------
-// Step 1 of the floor synthesis is a recurrence over <= 65 posts: a warp sweeping it level by level (floor1_build) spends ~1100
-// warp-instructions on it, a fifth of the synthesis kernel.  Run the way the reference runs it (floor.rs:568-653: posts in
-// order, then the sort-order walk) it is ~65 short iterations of ONE thread, so a pre-pass gives every packet-channel a thread
-// and leaves the segment list of the curve (FloorSeg[kFloorSegSlots], the count in the last slot) in a scratch buffer; the
-// synthesis kernel copies it to shared memory and renders it.  A chunk's warp handles the chunk's own packets; the packet
-// before the chunk belongs to the previous chunk of the run.
-constexpr int kFloorSegSlots = 68; // 65 posts + flat tail + sentinel; slot 67 holds the point count
-constexpr int kFloorPreThreads = 128;
-
-__global__ void __launch_bounds__(kFloorPreThreads) vorbis_floor_points_kernel(VorbisArgs a, int n_chunks, FloorSeg* __restrict__ out) {
-    __shared__ int16_t fin_s[65 * kFloorPreThreads]; // final_y[i] of thread t at [i * kFloorPreThreads + t]
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int c = blockIdx.x * (kFloorPreThreads / 32) + (tid >> 5);
-    if (c >= n_chunks) return;
-    const CodecChunk ck = a.chunks[c];
-    const int k = lane >> 1, ch = lane & 1;
-    const symgpu_vorbis_stream cfg = a.streams[ck.stream];
-    if (k >= ck.count || ch >= cfg.channels) return;
-    const int p = (int)ck.first + k;
-    const symgpu_vorbis_unit u = a.units[p];
-    FloorSeg* seg = out + ((size_t)p * 2 + ch) * kFloorSegSlots;
-    if (u.floor[ch] == 0xffff || u.floor[ch] >= a.n_floors) return; // unused floor: the synthesis kernel never looks
-    const symgpu_vorbis_floor1& s = a.floors[u.floor[ch]];
-    const uint16_t* __restrict__ fy = a.floor_y + ((size_t)p * a.pkt_ch + a.ch_base + ch) * 65;
-    const int n_half = (u.block_flag ? (1 << cfg.bs1_exp) : (1 << cfg.bs0_exp)) >> 1;
-    const int count = s.n_posts, mult = s.multiplier;
-    const int range = mult == 1 ? 256 : mult == 2 ? 128 : mult == 3 ? 86 : 64;
-    int16_t* fin = fin_s + tid;
-    // step 1 (floor.rs:568-625)
-    unsigned long long flag = 3ull; // floor_step2_flag[0] = [1] = true
-    bool flag64 = false;
-    fin[0] = (int16_t)fy[0];
-    fin[kFloorPreThreads] = (int16_t)fy[1];
-    for (int i = 2; i < count; ++i) {
-        const int lo = s.low[i], hi = s.high[i];
-        const int predicted = render_point(s.x_list[lo], fin[lo * kFloorPreThreads], s.x_list[hi], fin[hi * kFloorPreThreads], s.x_list[i]);
-        const int val = fy[i];
-        const int highroom = range - predicted, lowroom = predicted;
-        int f = predicted;
-        if (val != 0) {
-            const int room = 2 * (highroom < lowroom ? highroom : lowroom);
-            flag |= (1ull << lo) | (1ull << hi); // neighbours are earlier posts: indices <= 63
-            if (i < 64) flag |= 1ull << i;
-            else flag64 = true;
-            if (val >= room) f = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
-            else f = (val & 1) ? predicted - ((val + 1) / 2) : predicted + (val / 2);
-        }
-        fin[i * kFloorPreThreads] = (int16_t)f;
-    }
-    // the flagged posts in X order (floor.rs:627-653), every segment with render_line's constants (floor.rs:785-800)
-    int n = 0, px = 0, py = 0;
-    auto emit = [&](int x, int y) {
-        if (n > 0) {
-            const int dy = y - py, adx = x - px;
-            const int base = dy / adx;
-            FloorSeg g;
-            g.x0 = px;
-            g.y0 = (int16_t)py;
-            g.base = (int16_t)base;
-            g.ady = (int16_t)(abs(dy) - abs(base) * adx);
-            g.adx_s = (int16_t)(dy < 0 ? -adx : adx);
-            g.inv = __fdividef(1.0f, (float)adx);
-            seg[n - 1] = g;
-        }
-        px = x;
-        py = y;
-        ++n;
-    };
-    for (int r = 0; r < count; ++r) {
-        const int i = s.sort_order[r];
-        const bool on = i < 64 ? (bool)((flag >> i) & 1ull) : flag64;
-        if (on) emit(s.x_list[i], min(max((int)fin[i * kFloorPreThreads] * mult, 0), 255));
-    }
-    if (px < n_half) emit(n_half, py); // render_line(hx, hy, n, hy): a flat tail (floor.rs:650-652)
-    FloorSeg last{};
-    last.x0 = px; // the last point only ends the previous segment; behind it the sentinel of the segment walk
-    last.y0 = (int16_t)py;
-    seg[n - 1] = last;
-    FloorSeg sentinel{};
-    sentinel.x0 = 0x7fffffff;
-    seg[n] = sentinel;
-    FloorSeg cnt{};
-    cnt.x0 = n;
-    seg[kFloorSegSlots - 1] = cnt;
-}
-
 // =========================================================================================================================
 // Z layout (the default): one WARP per (packet, channel).  The IMDCT output is kept as its post-twiddled complex values
 // (imdct.cuh: imdct_to_z / imdct_out), floor x residue is formed inside the pre-twiddle straight from global memory, and the
@@ -508,7 +421,7 @@ __global__ void __launch_bounds__(kFloorPreThreads) vorbis_floor_points_kernel(V
 // =========================================================================================================================
 __host__ __device__ inline size_t vorbis_unit_z_bytes(int slot_smem) {  // z | floor points | the state tail of slot 0
     size_t b = sizeof(float2) * zpad_len(slot_smem / 2);
-    if (b < sizeof(FloorSeg) * kFloorSegSlots) b = sizeof(FloorSeg) * kFloorSegSlots;
+    if (b < sizeof(FloorPoints)) b = sizeof(FloorPoints);
     return (b + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t vorbis_unit_bytes(int slot_smem) { // + one table index per line (ybuf_index pads)
@@ -522,7 +435,7 @@ __device__ __forceinline__ void imdct_z_one(Pair pair, float2* z, const CodecTab
     imdct_to_z_from<LOG2>(pair, z, 1, tw, ft, lane, 32, WarpSync{});
 }
 
-__global__ void __launch_bounds__(512, 2) vorbis_synth_kernel_z(VorbisArgs a, const FloorSeg* __restrict__ pts_in, int slot_smem) {
+__global__ void __launch_bounds__(512, 2) vorbis_synth_kernel_z(VorbisArgs a, int slot_smem) {
     extern __shared__ __align__(16) unsigned char raw[];
     __shared__ bool is_last;
     __shared__ float inv_db_s[256]; // floor1_inverse_dB_table (floor.rs:21-86)
@@ -564,13 +477,10 @@ __global__ void __launch_bounds__(512, 2) vorbis_synth_kernel_z(VorbisArgs a, co
         const bool used = u.floor[ch] != 0xffff && u.floor[ch] < a.n_floors;
         const uint8_t* yb = unit_y(grp, ch);
         if (used) {
-            // the segment list of the pre-pass, into the bytes that will hold z, then the curve
-            const int4* src = reinterpret_cast<const int4*>(pts_in + ((size_t)p * 2 + ch) * kFloorSegSlots);
-            int4* segs = reinterpret_cast<int4*>(unit_z(grp, ch));
-            const int n_pts = __ldg(&src[kFloorSegSlots - 1]).x;
-            for (int i = lane; i <= n_pts; i += 32) segs[i] = __ldg(src + i);
-            __syncwarp();
-            floor1_render(SegList{reinterpret_cast<const FloorSeg*>(segs), n_pts}, n2, lane, unit_y(grp, ch));
+            // the floor points share the bytes that will hold z
+            FloorPoints& pts = *reinterpret_cast<FloorPoints*>(unit_z(grp, ch));
+            floor1_build(a.floors[u.floor[ch]], a.floor_aux[u.floor[ch]], a.floor_y + ((size_t)p * a.pkt_ch + a.ch_base + ch) * 65, n2, pts, lane);
+            floor1_render(SegList{pts.seg, pts.n}, n2, lane, unit_y(grp, ch));
         }
         __syncwarp();
         // (2) + (3) inverse coupling (lib.rs:267-277: the comparisons are "> 0.0"), floor x residue (an unused floor is all
@@ -745,8 +655,6 @@ bool vorbis_kernel_z() {
     return mode == 1;
 }
 
-size_t vorbis_floor_pts_bytes(uint32_t n_packets) { return vorbis_kernel_z() ? (size_t)n_packets * 2 * kFloorSegSlots * sizeof(FloorSeg) : 0; }
-
 int vorbis_slots_for(int max_bs1_exp) {
     if (vorbis_kernel_z()) {
         // eight slots when two CTAs of them share an SM or when they fit at all; fewer for the largest blocks
@@ -770,9 +678,7 @@ cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cu
             if (e != cudaSuccess) return e;
             configured = smem;
         }
-        FloorSeg* pts = static_cast<FloorSeg*>(a.floor_pts);
-        vorbis_floor_points_kernel<<<(n_chunks + kFloorPreThreads / 32 - 1) / (kFloorPreThreads / 32), kFloorPreThreads, 0, stream>>>(a, n_chunks, pts);
-        vorbis_synth_kernel_z<<<n_chunks, n_slots * 64, smem, stream>>>(a, pts, slot_smem);
+        vorbis_synth_kernel_z<<<n_chunks, n_slots * 64, smem, stream>>>(a, slot_smem);
         return cudaGetLastError();
     }
     const size_t smem = vorbis_slot_bytes(slot_smem) * n_slots;
