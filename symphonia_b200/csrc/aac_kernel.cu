@@ -50,19 +50,46 @@ __device__ __forceinline__ float tns_line(float v, int m, float (&h)[20], const 
 
 // `cnt` consecutive lines of one filter, held in a column of the warp's tile (row stride 33 floats).
 template <int ORDER>
-__device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h)[20], const float (&lpc)[20]) {
+__device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h)[20], const float (&lpc)[20], int stride = 33) {
     int k = 0;
-    for (; k < cnt && m0 + k < ORDER; ++k) col[33 * k] = tns_line<ORDER, true>(col[33 * k], m0 + k, h, lpc);
+    for (; k < cnt && m0 + k < ORDER; ++k) col[stride * k] = tns_line<ORDER, true>(col[stride * k], m0 + k, h, lpc);
     for (; k + 4 <= cnt; k += 4) { // four lines per trip: the loads are issued together
         float x[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = col[33 * (k + u)];
+        for (int u = 0; u < 4; ++u) x[u] = col[stride * (k + u)];
 #pragma unroll
         for (int u = 0; u < 4; ++u) x[u] = tns_line<ORDER, false>(x[u], 0, h, lpc);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) col[33 * (k + u)] = x[u];
+        for (int u = 0; u < 4; ++u) col[stride * (k + u)] = x[u];
     }
-    for (; k < cnt; ++k) col[33 * k] = tns_line<ORDER, false>(col[33 * k], 0, h, lpc);
+    for (; k < cnt; ++k) col[stride * k] = tns_line<ORDER, false>(col[stride * k], 0, h, lpc);
+}
+
+// One whole filter by one thread, in place on a channel-frame's 1024 lines in shared memory (the Z kernel runs the filters of a
+// frame on the lanes of the frame's own warp, one filter per lane, before its IMDCT).  Out of line: its twenty instantiations
+// and their registers stay out of the filterbank's code.
+__device__ __noinline__ void tns_filter_in_place(float* lines, const symgpu_aac_tns* __restrict__ t) {
+    int start = t->start, end = t->end;
+    if (end > 1024) end = 1024; // a malformed filter must not leave its channel-frame
+    const int order = t->order;
+    if (!(start < end) || order < 1 || order > 20) return;
+    const bool down = t->direction != 0;
+    float lpc[20], h[20];
+#pragma unroll
+    for (int j = 0; j < 20; ++j) {
+        h[j] = 0.0f;
+        lpc[j] = j < order ? __ldg(t->lpc + j) : 0.0f;
+    }
+    float* first = lines + (down ? end - 1 : start);
+    const int stride = down ? -1 : 1, len = end - start;
+    switch (order) {
+#define TNS_CASE(N) case N: tns_lines<N>(first, len, 0, h, lpc, stride); break;
+        TNS_CASE(1) TNS_CASE(2) TNS_CASE(3) TNS_CASE(4) TNS_CASE(5) TNS_CASE(6) TNS_CASE(7) TNS_CASE(8) TNS_CASE(9)
+        TNS_CASE(10) TNS_CASE(11) TNS_CASE(12) TNS_CASE(13) TNS_CASE(14) TNS_CASE(15) TNS_CASE(16) TNS_CASE(17)
+        TNS_CASE(18) TNS_CASE(19) TNS_CASE(20)
+#undef TNS_CASE
+        default: break;
+    }
 }
 
 // One warp per channel-frame: copy the spectra that carry filters, note the owner of each filter.
@@ -244,7 +271,7 @@ struct alignas(16) AacTabSmem {
 
 // Two layouts of a frame slot.  Array: the 2048 IMDCT outputs as the reference stores them (12.8 KB with the FFT scratch).
 // Z: only the 512 post-twiddled complex values (imdct_to_z, 4.6 KB); an output sample is looked up through imdct_out.
-struct alignas(8) AacFrameZ {
+struct alignas(16) AacFrameZ { // 16: the in-kernel TNS moves a frame through these bytes as float4
     float2 z[zpad_len(512)];
 };
 struct OutArray {
@@ -371,13 +398,42 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
         if (have_frame) {
             const size_t unit_idx = 2 * (size_t)f + ch;
             u = a.units[unit_idx];
-            const float* src = (u.n_tns ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
+            const float* src = ((u.n_tns && !(ZL && a.tns_inline)) ? a.tns_scratch : a.coeffs) + unit_idx * 1024;
             if constexpr (ZL) {
                 WarpSync sync;
+                bool filtered = false;
+                if (a.tns_inline && u.n_tns) {
+                    // TNS here instead of in a pre-pass: the frame's lines into shared memory (the bytes z will take), one
+                    // filter per lane in place (filters of a frame never read outside their own range, tns.rs:163-196), and
+                    // out to the scratch buffer, where the pre-twiddle picks them up (through L2: they were written by this
+                    // kernel).  The longest recurrence of a CTA pass delays its window phase; the SM's other CTA fills in.
+                    float* lines = reinterpret_cast<float*>(fs[slot].z);
+                    float* back = a.tns_scratch_rw + unit_idx * 1024;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        reinterpret_cast<float4*>(lines)[gt + 32 * i] = __ldg(reinterpret_cast<const float4*>(a.coeffs + unit_idx * 1024) + gt + 32 * i);
+                    __syncwarp();
+                    if ((uint32_t)gt < u.n_tns && u.tns_first + gt < a.n_tns) tns_filter_in_place(lines, a.tns + u.tns_first + gt);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(back)[gt + 32 * i] = reinterpret_cast<const float4*>(lines)[gt + 32 * i];
+                    __threadfence_block();
+                    __syncwarp();
+                    src = back;
+                    filtered = true;
+                }
+                auto pair_long = [src, filtered](int, int l) {
+                    const float2* q = reinterpret_cast<const float2*>(src + l);
+                    return filtered ? __ldcg(q) : __ldg(q);
+                };
+                auto pair_short = [src, filtered](int b, int l) {
+                    const float2* q = reinterpret_cast<const float2*>(src + (b << 7) + l);
+                    return filtered ? __ldcg(q) : __ldg(q);
+                };
                 if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-                    imdct_to_z<9>(src, fs[slot].z, 1, ts.tw_long, ft, gt, 32, sync);
+                    imdct_to_z_from<9>(pair_long, fs[slot].z, 1, ts.tw_long, ft, gt, 32, sync);
                 else
-                    imdct_to_z<6>(src, fs[slot].z, 8, ts.tw_short, ft, gt, 32, sync);
+                    imdct_to_z_from<6>(pair_short, fs[slot].z, 8, ts.tw_short, ft, gt, 32, sync);
             } else {
                 auto& me = fs[slot];
                 for (int i = gt; i < 256; i += GW) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
@@ -417,7 +473,7 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
                 const int nf = (int)nk.first - 1 + ngrp;
                 if (ngrp > 0 || !(nk.flags & kChunkLoadState)) {
                     const size_t nidx = 2 * (size_t)nf + nk.channel;
-                    const float* nsrc = (a.units[nidx].n_tns ? a.tns_scratch : a.coeffs) + nidx * 1024;
+                    const float* nsrc = ((a.units[nidx].n_tns && !(ZL && a.tns_inline)) ? a.tns_scratch : a.coeffs) + nidx * 1024;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 32 * gt));
                 }
             }
@@ -501,8 +557,22 @@ static cudaError_t launch_variant(const AacArgs& b, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// SYMGPU_AAC_TNS = prepass (sort / prepare / apply, the default) | inline (Z kernel only: the filters of a frame run on the lanes
+// of the frame's own warp before its IMDCT, no pre-pass and no scratch copy).  Measured on 8192 frames: with filters in 20 % of
+// the channel-frames inline is slower (172 us against 160 us: a CTA pass waits at its barrier for the longest recurrence among
+// its 16 frames), with 5 % it is faster (143 us against 149 us).
+static bool aac_tns_inline() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* env = getenv("SYMGPU_AAC_TNS");
+        mode = (env && env[0] == 'i') ? 1 : 0;
+    }
+    return mode == 1 && aac_kernel_variant() == 2;
+}
+int aac_launch_count(bool any_tns) { return (any_tns && !aac_tns_inline()) ? 4 : 1; }
+
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream) {
-    if (any_tns) {
+    if (any_tns && !aac_tns_inline()) {
         // owner[] starts at "no owner" so that filters outside every channel-frame's range are skipped
         cudaError_t e = cudaMemsetAsync(a.tns_owner, 0xff, (size_t)a.n_tns * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return e;
@@ -515,6 +585,7 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
     AacArgs b = a;
     b.n_chunks = n_chunks;
     b.n_groups = n_groups;
+    b.tns_inline = (any_tns && aac_tns_inline()) ? 1 : 0;
     switch (aac_kernel_variant()) {
         case 1: return launch_variant<32, kAacKWarp, false>(b, stream);
         case 2: return launch_variant<32, kAacKZ, true>(b, stream);

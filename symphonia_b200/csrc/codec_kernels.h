@@ -27,6 +27,7 @@ constexpr int kAacChunkFramesWarp = 13; // one warp per frame
 constexpr int kAacChunkFramesZ = 15;    // one warp per frame, Z layout (16 warps, two CTAs per SM)
 constexpr int kAacDefaultVariant = 2;    // 0 pair | 1 warp | 2 z (SYMGPU_AAC_KERNEL overrides)
 int aac_kernel_variant();
+int aac_launch_count(bool any_tns);        // kernels one aac_launch starts
 bool aac_warp_per_frame();
 int aac_chunk_frames();                 // frames per chunk of the variant in use
 
@@ -42,6 +43,7 @@ struct AacArgs {
     uint32_t* tns_owner;        // [n_tns] channel-frame of each filter
     uint32_t n_tns;
     int n_chunks;               // filled in by aac_launch
+    int tns_inline;             // filled in by aac_launch: the Z kernel applies the filters itself (no pre-pass)
     int n_groups;               // filled in by aac_launch: group_first = (const uint32_t*)(chunks + n_chunks), n_groups + 1 entries
     float* pcm;
     const CodecChunk* chunks;

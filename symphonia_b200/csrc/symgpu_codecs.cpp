@@ -178,10 +178,10 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
         ctx->aac_tns_idx_cap = cap;
     }
     AacArgs a{units, tns, coeffs, ctx->d_aac_scratch, ctx->d_aac_scratch,
-              ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0, 0,
+              ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0, 0, 0,
               pcm, ctx->d_chunks, ctx->d_aac_states, ctx->d_aac_gen, ctx->d_aac_gen + ctx->n_aac_streams, ctx->d_codec_tab};
     CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, ctx->cached_chunks, ctx->cached_groups, ctx->stream));
-    ctx->launches += n_tns ? 4 : 1;
+    ctx->launches += aac_launch_count(n_tns != 0);
     return SYMGPU_OK;
 }
 

@@ -233,16 +233,48 @@ def test_vorbis_channel_counts(engine, oracle, channels, couplings):
     _vorbis_mc_case(engine, oracle, n_streams=3, packets_per_stream=10, seed=310 + channels, channels=channels, couplings=couplings)
 
 
-def test_aac_one_warp_per_frame_variant_matches_too():
-    """`SYMGPU_AAC_KERNEL=warp` (13 frames per chunk, __syncwarp only; measured slower, kept selectable - DESIGN 4) is read once
-    per process, so the AAC cases above are re-run in a child process with it set."""
+@pytest.mark.parametrize("variant", ["pair", "warp"])
+def test_aac_older_kernel_shapes_match_too(variant):
+    """`SYMGPU_AAC_KERNEL=pair` (two warps per frame, named barriers: round 1's shape) and `=warp` (one warp per frame, array
+    layout; measured slower) stay selectable next to the default Z layout.  The variable is read once per process, so
+    the AAC cases above are re-run in a child process with it set."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, SYMGPU_AAC_KERNEL="warp")
+    env = dict(os.environ, SYMGPU_AAC_KERNEL=variant)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
                         "test_aac_mixed or test_aac_chunk_boundaries or test_aac_state_carry or test_aac_heavy_tns or test_aac_mono"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+def test_aac_tns_on_the_frames_own_warp_matches_too():
+    """`SYMGPU_AAC_TNS=inline`: the Z kernel runs a frame's TNS filters on the lanes of the frame's warp instead of the pre-pass
+    (faster when few frames carry filters); read once per process, so the TNS cases are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SYMGPU_AAC_TNS="inline")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "test_aac_mixed or test_aac_heavy_tns or test_aac_chunk_boundaries or test_aac_device_entry_point"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+def test_vorbis_array_layout_kernel_matches_too():
+    """`SYMGPU_VORBIS_KERNEL=pair`: round 1's kernel (64 threads per packet, array layout) stays selectable next to the default Z
+    layout; the Vorbis cases above are re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SYMGPU_VORBIS_KERNEL="pair")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "test_vorbis_mixed or test_vorbis_block_sizes or test_vorbis_state_carry or test_vorbis_5_1 or test_vorbis_floor_with_65"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
