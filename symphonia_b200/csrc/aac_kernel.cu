@@ -92,6 +92,35 @@ __device__ __noinline__ void tns_filter_in_place(float* lines, const symgpu_aac_
     }
 }
 
+// The pre-pass in ONE kernel (the default): a warp per channel-frame that carries filters moves the frame's 1024 lines into
+// shared memory (coalesced), runs its filters there, one per lane -- a long frame has at most 3, eight short windows at most 8,
+// and together they cover at most the frame's TNS band range, so a warp's serial work is bounded by ~670 lines -- and writes the
+// lines to the scratch buffer (coalesced).  No sort, no owner table, no 32-line transposition rounds: the three-kernel pre-pass
+// below spent three quarters of its apply kernel moving lines in and out of its tiles.
+constexpr int kTnsFrameWarps = 8;
+__global__ void __launch_bounds__(kTnsFrameWarps * 32) aac_tns_frames(const symgpu_aac_unit* __restrict__ units, const symgpu_aac_tns* __restrict__ tns,
+                                                                     uint32_t n_tns, const float* __restrict__ coeffs, float* __restrict__ scratch,
+                                                                     uint32_t n_units) {
+    __shared__ __align__(16) float lines_s[kTnsFrameWarps][1024];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t u = blockIdx.x * kTnsFrameWarps + warp;
+    if (u >= n_units) return;
+    const symgpu_aac_unit unit = units[u];
+    if (unit.n_tns == 0) return;
+    float* lines = lines_s[warp];
+    const float4* src = reinterpret_cast<const float4*>(coeffs + (size_t)u * 1024);
+    float4* dst = reinterpret_cast<float4*>(scratch + (size_t)u * 1024);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(lines)[lane + 32 * i] = __ldg(src + lane + 32 * i);
+    __syncwarp();
+    for (uint32_t f = lane; f < unit.n_tns; f += 32)
+        if (unit.tns_first + f < n_tns) tns_filter_in_place(lines, tns + unit.tns_first + f);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[lane + 32 * i] = reinterpret_cast<const float4*>(lines)[lane + 32 * i];
+}
+
+// ---- the three-kernel pre-pass of round 1 (SYMGPU_AAC_TNS=sorted) ----
 // One warp per channel-frame: copy the spectra that carry filters, note the owner of each filter.
 __global__ void __launch_bounds__(256) aac_tns_prepare(const symgpu_aac_unit* __restrict__ units, const float* __restrict__ coeffs,
                                                        float* __restrict__ scratch, uint32_t* __restrict__ owner, uint32_t n_units,
@@ -413,7 +442,8 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
                     for (int i = 0; i < 8; ++i)
                         reinterpret_cast<float4*>(lines)[gt + 32 * i] = __ldg(reinterpret_cast<const float4*>(a.coeffs + unit_idx * 1024) + gt + 32 * i);
                     __syncwarp();
-                    if ((uint32_t)gt < u.n_tns && u.tns_first + gt < a.n_tns) tns_filter_in_place(lines, a.tns + u.tns_first + gt);
+                    for (uint32_t f = gt; f < u.n_tns; f += 32)
+                        if (u.tns_first + f < a.n_tns) tns_filter_in_place(lines, a.tns + u.tns_first + f);
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(back)[gt + 32 * i] = reinterpret_cast<const float4*>(lines)[gt + 32 * i];
@@ -557,22 +587,28 @@ static cudaError_t launch_variant(const AacArgs& b, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-// SYMGPU_AAC_TNS = prepass (sort / prepare / apply, the default) | inline (Z kernel only: the filters of a frame run on the lanes
-// of the frame's own warp before its IMDCT, no pre-pass and no scratch copy).  Measured on 8192 frames: with filters in 20 % of
-// the channel-frames inline is slower (172 us against 160 us: a CTA pass waits at its barrier for the longest recurrence among
-// its 16 frames), with 5 % it is faster (143 us against 149 us).
-static bool aac_tns_inline() {
+// SYMGPU_AAC_TNS = frames (the default: one pre-pass kernel, a warp per filtered channel-frame) | sorted (round 1's three kernels:
+// sort by order / prepare / apply, one filter per lane) | inline (Z kernel only: the filters of a frame run on the lanes of the
+// frame's own warp before its IMDCT, no pre-pass and no scratch copy; slower at 20 % TNS -- a CTA pass waits at its barrier for
+// the longest recurrence among its 16 frames -- faster at 5 %).
+static int aac_tns_mode() { // 0 frames | 1 sorted | 2 inline
     static int mode = -1;
     if (mode < 0) {
         const char* env = getenv("SYMGPU_AAC_TNS");
-        mode = (env && env[0] == 'i') ? 1 : 0;
+        mode = !env ? 0 : env[0] == 's' ? 1 : env[0] == 'i' ? 2 : 0;
+        if (mode == 2 && aac_kernel_variant() != 2) mode = 0;
     }
-    return mode == 1 && aac_kernel_variant() == 2;
+    return mode;
 }
-int aac_launch_count(bool any_tns) { return (any_tns && !aac_tns_inline()) ? 4 : 1; }
+static bool aac_tns_inline() { return aac_tns_mode() == 2; }
+int aac_launch_count(bool any_tns) { return !any_tns ? 1 : aac_tns_mode() == 0 ? 2 : aac_tns_mode() == 1 ? 4 : 1; }
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream) {
-    if (any_tns && !aac_tns_inline()) {
+    if (any_tns && aac_tns_mode() == 0) {
+        aac_tns_frames<<<(n_units + kTnsFrameWarps - 1) / kTnsFrameWarps, kTnsFrameWarps * 32, 0, stream>>>(a.units, a.tns, a.n_tns, a.coeffs, a.tns_scratch_rw, n_units);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    } else if (any_tns && !aac_tns_inline()) {
         // owner[] starts at "no owner" so that filters outside every channel-frame's range are skipped
         cudaError_t e = cudaMemsetAsync(a.tns_owner, 0xff, (size_t)a.n_tns * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return e;

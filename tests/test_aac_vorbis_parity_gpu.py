@@ -250,13 +250,15 @@ def test_aac_older_kernel_shapes_match_too(variant):
     assert " passed" in r.stdout
 
 
-def test_aac_tns_on_the_frames_own_warp_matches_too():
-    """`SYMGPU_AAC_TNS=inline`: the Z kernel runs a frame's TNS filters on the lanes of the frame's warp instead of the pre-pass
-    (faster when few frames carry filters); read once per process, so the TNS cases are re-run in a child process."""
+@pytest.mark.parametrize("mode", ["inline", "sorted"])
+def test_aac_other_tns_arrangements_match_too(mode):
+    """`SYMGPU_AAC_TNS=inline`: the Z kernel runs a frame's TNS filters on the lanes of the frame's warp instead of a pre-pass
+    (faster when few frames carry filters); `=sorted`: round 1's three-kernel pre-pass.  The default is the one-kernel
+    pre-pass (a warp per filtered channel-frame).  Read once per process, so the TNS cases are re-run in a child process."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, SYMGPU_AAC_TNS="inline")
+    env = dict(os.environ, SYMGPU_AAC_TNS=mode)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
                         "test_aac_mixed or test_aac_heavy_tns or test_aac_chunk_boundaries or test_aac_device_entry_point"],
