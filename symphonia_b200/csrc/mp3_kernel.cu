@@ -378,7 +378,7 @@ struct Mp3Smem {
 // MULTI = false: every group of the plan is a single tile (the shape of large batches); the loops over the
 // pieces of a group then fold away at compile time.
 template <int T, int NW, bool MULTI, bool PK = false>
-__global__ void __launch_bounds__(NW * 32, 16 / NW) mp3_synth_kernel(Mp3Args a) {
+__global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) mp3_synth_kernel(Mp3Args a) {
     static_assert(NW >= T, "one warp per granule job (a tile with a halo holds NW - 2 granules)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = Mp3Smem<T, NW>;
