@@ -23,7 +23,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
 # full captures of the dominant kernels
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mp3_synth -c 1 -s 4 -o $out/${tag}_prof_mp3 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs > $out/${tag}_prof_mp3.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mp3v2_synth -c 1 -s 4 -o $out/${tag}_prof_mp3_serving -f python bench_codecs.py --codec mp3-short --steps 3 --warmup 3 > $out/${tag}_prof_mp3_serving.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"aac_synth|aac_tns_apply" -c 2 -s 6 -o $out/${tag}_prof_aac -f python bench_codecs.py --codec aac --steps 3 --warmup 3 > $out/${tag}_prof_aac.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"aac_synth|aac_tns_frames" -c 2 -s 6 -o $out/${tag}_prof_aac -f python bench_codecs.py --codec aac --steps 3 --warmup 3 > $out/${tag}_prof_aac.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:vorbis_synth -c 1 -s 3 -o $out/${tag}_prof_vorbis -f python bench_codecs.py --codec vorbis --steps 3 --warmup 3 > $out/${tag}_prof_vorbis.log 2>&1
 tail -1 $out/${tag}_prof_mp3.log; tail -1 $out/${tag}_prof_mp3_serving.log; tail -1 $out/${tag}_prof_aac.log; tail -1 $out/${tag}_prof_vorbis.log
 ls -la $out | grep ${tag}
