@@ -53,14 +53,32 @@ template <int ORDER>
 __device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h)[20], const float (&lpc)[20], int stride = 33) {
     int k = 0;
     for (; k < cnt && m0 + k < ORDER; ++k) col[stride * k] = tns_line<ORDER, true>(col[stride * k], m0 + k, h, lpc);
-    for (; k + 4 <= cnt; k += 4) { // four lines per trip: the loads are issued together
-        float x[4];
+    // Main part: trips of L lines (a multiple of ORDER) with the history in a ring of ORDER registers -- c[r % ORDER] is the
+    // output of the trip's line r, so the output j + 1 lines back sits at c[(r - 1 - j) mod ORDER] with every index known at
+    // compile time: no register moves between lines (the shifting form below spends ORDER of its ~3.3 ORDER instructions per
+    // line on them).  Same operations on the same operands in the same order.
+    constexpr int L = ORDER >= 4 ? ORDER : ORDER == 3 ? 6 : 4;
+    if (k + L <= cnt) {
+        float c[ORDER];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = col[stride * (k + u)];
+        for (int j = 0; j < ORDER; ++j) c[ORDER - 1 - j] = h[j];
+        for (; k + L <= cnt; k += L) {
+            float x[L];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = tns_line<ORDER, false>(x[u], 0, h, lpc);
+            for (int r = 0; r < L; ++r) x[r] = col[stride * (k + r)];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) col[stride * (k + u)] = x[u];
+            for (int r = 0; r < L; ++r) {
+                float v = x[r];
+#pragma unroll
+                for (int j = 0; j < ORDER; ++j) v -= c[(r + 2 * L - 1 - j) % ORDER] * lpc[j];
+                c[r % ORDER] = v;
+                x[r] = v;
+            }
+#pragma unroll
+            for (int r = 0; r < L; ++r) col[stride * (k + r)] = x[r];
+        }
+#pragma unroll
+        for (int j = 0; j < ORDER; ++j) h[j] = c[ORDER - 1 - j];
     }
     for (; k < cnt; ++k) col[stride * k] = tns_line<ORDER, false>(col[stride * k], 0, h, lpc);
 }
@@ -68,6 +86,8 @@ __device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h
 // One whole filter by one thread, in place on a channel-frame's 1024 lines in shared memory (the Z kernel runs the filters of a
 // frame on the lanes of the frame's own warp, one filter per lane, before its IMDCT).  Out of line: its twenty instantiations
 // and their registers stay out of the filterbank's code.
+// (TAG: one copy per calling kernel, so that the 64-register budget of the Z kernel does not bind the pre-pass kernel's copy.)
+template <int TAG>
 __device__ __noinline__ void tns_filter_in_place(float* lines, const symgpu_aac_tns* __restrict__ t) {
     int start = t->start, end = t->end;
     if (end > 1024) end = 1024; // a malformed filter must not leave its channel-frame
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(kTnsFrameWarps * 32) aac_tns_frames(const symg
     for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(lines)[lane + 32 * i] = __ldg(src + lane + 32 * i);
     __syncwarp();
     for (uint32_t f = lane; f < unit.n_tns; f += 32)
-        if (unit.tns_first + f < n_tns) tns_filter_in_place(lines, tns + unit.tns_first + f);
+        if (unit.tns_first + f < n_tns) tns_filter_in_place<0>(lines, tns + unit.tns_first + f);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) dst[lane + 32 * i] = reinterpret_cast<const float4*>(lines)[lane + 32 * i];
@@ -443,7 +463,7 @@ __global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_sy
                         reinterpret_cast<float4*>(lines)[gt + 32 * i] = __ldg(reinterpret_cast<const float4*>(a.coeffs + unit_idx * 1024) + gt + 32 * i);
                     __syncwarp();
                     for (uint32_t f = gt; f < u.n_tns; f += 32)
-                        if (u.tns_first + f < a.n_tns) tns_filter_in_place(lines, a.tns + u.tns_first + f);
+                        if (u.tns_first + f < a.n_tns) tns_filter_in_place<1>(lines, a.tns + u.tns_first + f);
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(back)[gt + 32 * i] = reinterpret_cast<const float4*>(lines)[gt + 32 * i];

@@ -411,6 +411,42 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
 }
 
 
+// ---- mbarrier / TMA bulk copy (as in mp3_kernel.cu): the Z kernel pulls its stream's FFT and IMDCT twiddle tables into shared
+// memory with three bulk copies issued by one thread at CTA start; every warp waits for them right before its IMDCT, which is
+// after its floor curve is built -- no CTA barrier, no exposed latency.
+__device__ __forceinline__ uint32_t vz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vz_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vz_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void vz_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vz_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(vz_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void vz_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vz_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(vz_smem_u32(bar))
+                 : "memory");
+}
+// Table area behind the unit slots, in float2: FFT prefix (lit16, lit32, merge tables up to size n2max) | twiddles of the long
+// block (n2max) | twiddles of the short block (at most n2max / 2 when the two sizes differ), n2max = slot_smem / 2.
+__host__ __device__ inline size_t vorbis_z_tab_bytes(int slot_smem) {
+    const int n2max = slot_smem / 2;
+    const int fft = n2max >= 64 ? n2max - 8 : 24;
+    return sizeof(float2) * (size_t)(fft + n2max + n2max / 2);
+}
+
 // =========================================================================================================================
 // Z layout (the default): one WARP per (packet, channel).  The IMDCT output is kept as its post-twiddled complex values
 // (imdct.cuh: imdct_to_z / imdct_out), floor x residue is formed inside the pre-twiddle straight from global memory, and the
@@ -429,9 +465,7 @@ __host__ __device__ inline size_t vorbis_unit_bytes(int slot_smem) { // + one ta
 }
 
 template <int LOG2, typename Pair>
-__device__ __forceinline__ void imdct_z_one(Pair pair, float2* z, const CodecTables* tab, int lane) {
-    const FftTables* ft = reinterpret_cast<const FftTables*>(tab->fft_lit16);
-    const float2* tw = reinterpret_cast<const float2*>(tab->vorbis_tw) + ((1 << LOG2) - 16);
+__device__ __forceinline__ void imdct_z_one(Pair pair, float2* z, const FftTables* ft, const float2* tw, int lane) {
     imdct_to_z_from<LOG2>(pair, z, 1, tw, ft, lane, 32, WarpSync{});
 }
 
@@ -445,12 +479,28 @@ __global__ void __launch_bounds__(512, 2) vorbis_synth_kernel_z(VorbisArgs a, in
     auto unit_z = [&](int k, int c) { return reinterpret_cast<float2*>(raw + (size_t)(2 * k + c) * unit_bytes); };
     auto unit_y = [&](int k, int c) { return raw + (size_t)(2 * k + c) * unit_bytes + z_bytes; };
 
-    if (threadIdx.x < 256) inv_db_s[threadIdx.x] = a.tab->vorbis_inverse_db[threadIdx.x];
-    __syncthreads();
+    __shared__ __align__(8) uint64_t tab_bar;
     const CodecChunk ck = a.chunks[blockIdx.x];
     const symgpu_vorbis_stream cfg = a.streams[ck.stream];
     const CodecTables* __restrict__ tab = a.tab;
     const int bs0 = 1 << cfg.bs0_exp, bs1 = 1 << cfg.bs1_exp;
+    // the stream's tables: FFT prefix for sizes up to bs1 / 4, IMDCT twiddles of both block sizes
+    const int n2max = slot_smem / 2, n2_1 = bs1 >> 2, n2_0 = bs0 >> 2;
+    float2* tab_s = reinterpret_cast<float2*>(raw + (size_t)(blockDim.x >> 5) * unit_bytes);
+    float2* tw1_s = tab_s + (n2max >= 64 ? n2max - 8 : 24);
+    float2* tw0_s = n2_0 == n2_1 ? tw1_s : tw1_s + n2max;
+    if (tid == 0) {
+        vz_mbar_init(&tab_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t fft_bytes = (uint32_t)sizeof(float2) * (n2_1 >= 64 ? n2_1 - 8 : 24);
+        const uint32_t tw1_bytes = (uint32_t)sizeof(float2) * n2_1, tw0_bytes = n2_0 == n2_1 ? 0u : (uint32_t)sizeof(float2) * n2_0;
+        vz_mbar_expect_tx(&tab_bar, fft_bytes + tw1_bytes + tw0_bytes);
+        vz_bulk_g2s(tab_s, tab->fft_lit16, fft_bytes, &tab_bar);
+        vz_bulk_g2s(tw1_s, reinterpret_cast<const float2*>(tab->vorbis_tw) + (n2_1 - 16), tw1_bytes, &tab_bar);
+        if (tw0_bytes) vz_bulk_g2s(tw0_s, reinterpret_cast<const float2*>(tab->vorbis_tw) + (n2_0 - 16), tw0_bytes, &tab_bar);
+    }
+    if (threadIdx.x < 256) inv_db_s[threadIdx.x] = a.tab->vorbis_inverse_db[threadIdx.x];
+    __syncthreads(); // also publishes the initialised mbarrier
     const int n_ch = cfg.channels;
     const uint32_t gen = a.gen[ck.stream];
     const float* st_in = a.states + ((size_t)ck.stream * 2 + (gen & 1)) * kVorbisStateFloats;
@@ -507,15 +557,18 @@ __global__ void __launch_bounds__(512, 2) vorbis_synth_kernel_z(VorbisArgs a, in
             return make_float2(line(m.x, g.x, l), line(m.y, g.y, l + 1));
         };
         float2* z = unit_z(grp, ch);
+        vz_mbar_wait(&tab_bar, 0); // the tables have landed (long ago, as a rule)
+        const FftTables* ft = reinterpret_cast<const FftTables*>(tab_s);
+        const float2* tw = u.block_flag ? tw1_s : tw0_s;
         switch (31 - __clz(bs >> 2)) { // FFT size = blocksize / 4
-            case 4: imdct_z_one<4>(pair, z, tab, lane); break;
-            case 5: imdct_z_one<5>(pair, z, tab, lane); break;
-            case 6: imdct_z_one<6>(pair, z, tab, lane); break;
-            case 7: imdct_z_one<7>(pair, z, tab, lane); break;
-            case 8: imdct_z_one<8>(pair, z, tab, lane); break;
-            case 9: imdct_z_one<9>(pair, z, tab, lane); break;
-            case 10: imdct_z_one<10>(pair, z, tab, lane); break;
-            default: imdct_z_one<11>(pair, z, tab, lane); break;
+            case 4: imdct_z_one<4>(pair, z, ft, tw, lane); break;
+            case 5: imdct_z_one<5>(pair, z, ft, tw, lane); break;
+            case 6: imdct_z_one<6>(pair, z, ft, tw, lane); break;
+            case 7: imdct_z_one<7>(pair, z, ft, tw, lane); break;
+            case 8: imdct_z_one<8>(pair, z, ft, tw, lane); break;
+            case 9: imdct_z_one<9>(pair, z, ft, tw, lane); break;
+            case 10: imdct_z_one<10>(pair, z, ft, tw, lane); break;
+            default: imdct_z_one<11>(pair, z, ft, tw, lane); break;
         }
     } else if (grp == 0 && ch < n_ch) {
         // run start: slot 0 holds the overlap line itself (plain floats where a packet would keep z)
@@ -659,7 +712,7 @@ int vorbis_slots_for(int max_bs1_exp) {
     if (vorbis_kernel_z()) {
         // eight slots when two CTAs of them share an SM or when they fit at all; fewer for the largest blocks
         const size_t per = 2 * vorbis_unit_bytes(1 << (max_bs1_exp - 1));
-        const int n = (int)((216u * 1024u) / per);
+        const int n = (int)((216u * 1024u - vorbis_z_tab_bytes(1 << (max_bs1_exp - 1))) / per);
         return n < 2 ? 2 : (n > 8 ? 8 : n);
     }
     const size_t per = vorbis_slot_bytes(1 << (max_bs1_exp - 1));
@@ -671,7 +724,7 @@ cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cu
     const int slot_smem = 1 << (max_bs1_exp - 1);
     const int n_slots = vorbis_slots_for(max_bs1_exp);
     if (vorbis_kernel_z()) {
-        const size_t smem = 2 * vorbis_unit_bytes(slot_smem) * n_slots;
+        const size_t smem = 2 * vorbis_unit_bytes(slot_smem) * n_slots + vorbis_z_tab_bytes(slot_smem);
         static size_t configured = 0;
         if (smem > configured) {
             cudaError_t e = cudaFuncSetAttribute(vorbis_synth_kernel_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

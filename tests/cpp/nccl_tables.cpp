@@ -27,10 +27,22 @@ int main(int argc, char** argv) {
     if (!init_all || !destroy) return 3;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) return 2;
-    const int n = n_dev >= 2 ? 2 : 1;
+    int n = n_dev >= 2 ? 2 : 1;
     int devs[2] = {0, 1};
     void* comms[2] = {nullptr, nullptr};
-    if (init_all(comms, n, devs) != 0) return 4;
+    int nccl_rc = init_all(comms, n, devs);
+    if (nccl_rc != 0 && n == 2) {
+        // the communicator is the host application's business, not the library's: when this box's NCCL cannot make a 2-rank one
+        // (seen once on an 8-GPU NVSwitch box with the system libnccl), run the same code path over a 1-rank communicator
+        std::fprintf(stderr, "ncclCommInitAll(2 ranks) failed with ncclResult_t %d: falling back to one rank\n", nccl_rc);
+        n = 1;
+        comms[0] = comms[1] = nullptr;
+        nccl_rc = init_all(comms, n, devs);
+    }
+    if (nccl_rc != 0) {
+        std::fprintf(stderr, "ncclCommInitAll failed with ncclResult_t %d\n", nccl_rc);
+        return 4;
+    }
 
     std::ifstream in(argv[1], std::ios::binary);
     std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
