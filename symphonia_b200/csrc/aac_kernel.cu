@@ -58,6 +58,7 @@ __device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h
     // compile time: no register moves between lines (the shifting form below spends ORDER of its ~3.3 ORDER instructions per
     // line on them).  Same operations on the same operands in the same order.
     constexpr int L = ORDER >= 4 ? ORDER : ORDER == 3 ? 6 : 4;
+#ifndef SYMGPU_TNS_NO_RING // (A/B switch of tools/r02_gpu_ab.sh)
     if (k + L <= cnt) {
         float c[ORDER];
 #pragma unroll
@@ -80,6 +81,7 @@ __device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h
 #pragma unroll
         for (int j = 0; j < ORDER; ++j) h[j] = c[ORDER - 1 - j];
     }
+#endif
     for (; k < cnt; ++k) col[stride * k] = tns_line<ORDER, false>(col[stride * k], 0, h, lpc);
 }
 

@@ -75,7 +75,8 @@ __device__ __forceinline__ void floor1_build(const symgpu_vorbis_floor1& s, cons
     const int mult = s.multiplier;
     const int range = mult == 1 ? 256 : mult == 2 ? 128 : mult == 3 ? 86 : 64;
     int16_t* final_y = out.final_y;
-    // my posts: i = lane, lane + 32, lane + 64
+    // my posts: i = lane, lane + 32, lane + 64  (ordering the posts by level on the host, so that a level touches fewer of the
+    // three slots, was measured: 139.5 -> 138.9 us, not worth the table)
     int px[3], plo[3], phi[3], pxlo[3], pxhi[3], pval[3], plvl[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
