@@ -373,7 +373,7 @@ __device__ __forceinline__ float aac_new_delay(int seq, const Out out, const flo
 // ZL (GW = 32 only): frame slots in the Z layout -- 14 slots are 65 KB instead of 180 KB, so two CTAs share an SM: 28 frames in
 // flight per SM, one warp each, no hardware barrier inside an IMDCT.
 template <int GW, int K, bool ZL>
-__global__ void __launch_bounds__((K + 1) * GW, (GW == 64 || ZL) ? 2 : 1) aac_synth_kernel(AacArgs a) {
+__global__ void __launch_bounds__((K + 1) * GW, ZL ? (K >= 15 ? 2 : K >= 9 ? 3 : 4) : GW == 64 ? 2 : 1) aac_synth_kernel(AacArgs a) {
     static_assert(!ZL || GW == 32, "the Z layout is written for one warp per frame");
     extern __shared__ __align__(16) unsigned char aac_raw[];
     using Slot = typename std::conditional<ZL, AacFrameZ, AacFrameSmem>::type;
@@ -623,6 +623,7 @@ static int aac_tns_mode() { // 0 frames | 1 sorted | 2 inline
     return mode;
 }
 static bool aac_tns_inline() { return aac_tns_mode() == 2; }
+int aac_z_frames();
 int aac_launch_count(bool any_tns) { return !any_tns ? 1 : aac_tns_mode() == 0 ? 2 : aac_tns_mode() == 1 ? 4 : 1; }
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream) {
@@ -646,7 +647,12 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
     b.tns_inline = (any_tns && aac_tns_inline()) ? 1 : 0;
     switch (aac_kernel_variant()) {
         case 1: return launch_variant<32, kAacKWarp, false>(b, stream);
-        case 2: return launch_variant<32, kAacKZ, true>(b, stream);
+        case 2:
+            switch (aac_z_frames()) { // frames per chunk of the Z kernel: 16 warps x 2 CTAs per SM (default), 10 x 3, 8 x 4
+                case 9: return launch_variant<32, 9, true>(b, stream);
+                case 7: return launch_variant<32, 7, true>(b, stream);
+                default: return launch_variant<32, kAacKZ, true>(b, stream);
+            }
         default: return launch_variant<64, kAacK, false>(b, stream);
     }
 }
@@ -661,6 +667,16 @@ int aac_kernel_variant() {
     return mode;
 }
 bool aac_warp_per_frame() { return aac_kernel_variant() != 0; }
-int aac_chunk_frames() { return aac_kernel_variant() == 2 ? kAacKZ : aac_kernel_variant() == 1 ? kAacKWarp : kAacK; }
+// SYMGPU_AAC_Z_FRAMES = 15 (default) | 9 | 7: frames per chunk of the Z kernel, i.e. 16, 10 or 8 warps per CTA at 2, 3 or 4 CTAs per SM
+int aac_z_frames() {
+    static int k = -1;
+    if (k < 0) {
+        const char* env = getenv("SYMGPU_AAC_Z_FRAMES");
+        const int v = env ? atoi(env) : kAacKZ;
+        k = (v == 9 || v == 7) ? v : kAacKZ;
+    }
+    return k;
+}
+int aac_chunk_frames() { return aac_kernel_variant() == 2 ? aac_z_frames() : aac_kernel_variant() == 1 ? kAacKWarp : kAacK; }
 
 } // namespace symgpu

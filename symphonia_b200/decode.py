@@ -199,11 +199,13 @@ def decode_adts_aac(engine, data, fmt=nat.FMT_S16, stream=0, threads=1):
 # ---- many files at once: one synthesis launch per codec --------------------------------------------------------------------
 
 def sniff(data):
-    """'vorbis' (Ogg capture pattern), 'aac' (ADTS: 12 sync bits, layer field 00) or 'mpa' (anything else: the MPEG audio indexer looks
-    for a frame, skipping tags and junk)."""
+    """'vorbis' (Ogg capture pattern), 'flac' (native FLAC marker), 'aac' (ADTS: 12 sync bits, layer field 00) or 'mpa' (anything else:
+    the MPEG audio indexer looks for a frame, skipping tags and junk)."""
     head = bytes(data[:4])
     if head == b"OggS":
         return "vorbis"
+    if head == b"fLaC":
+        return "flac"  # the integer path has its own entry point (decode_flac); plan_files reports it as an error for that file
     if len(head) >= 2 and head[0] == 0xFF and (head[1] & 0xF6) == 0xF0:
         return "aac"
     return "mpa"
@@ -216,6 +218,8 @@ def plan_file(data):
         return dict(ogg_vorbis_plan(data), kind="vorbis")
     if kind == "aac":
         return dict(adts_aac_plan(data), kind="aac")
+    if kind == "flac":
+        raise ValueError("native FLAC goes through decode_flac (integer samples), not through the f32 synthesis batches")
     layer, payload, runs, spans, rate, channels, total = mpeg_audio_plan(data)
     return dict(kind={1: "mpa1", 2: "mpa2", 3: "mp3"}[layer], payload=payload, runs=runs, spans=spans, sample_rate=rate, channels=channels, total_frames=total)
 
@@ -225,13 +229,30 @@ def plan_files(files, threads=None, arena=None):
     into one batch per codec, every file a stream of its own.  Returns (plans, batches): batches[kind] = dict(members = indices into
     `files`, first = each member's first unit in the batch, + the arrays of that codec's synthesis entry point).  AAC files are indexed
     first and then decoded straight into their slices of the batch arrays (taken from `arena` when given: reusable staging memory);
-    a file whose front-end refuses packets leaves the tail of its slice unused -- runs name what is valid."""
+    a file whose front-end refuses packets leaves the tail of its slice unused -- runs name what is valid.
+    A file that cannot be indexed or planned at all (an Ogg stream that is not Vorbis, more than two channels, floor 0, an ADTS channel
+    configuration outside 1 / 2, a native FLAC file, ...) does not take the others down: its plan is dict(kind="error", error=<message>)
+    with no spans, it is in no batch, and pack_files returns an empty result for it."""
     import concurrent.futures
     import os
     kinds = [sniff(f) for f in files]
+    errors = {}
+
+    def guarded(fn):
+        def run(i):
+            try:
+                return fn(i)
+            except Exception as e:  # noqa: BLE001 -- one bad file must not abort the batch; the message is kept in its plan
+                errors[i] = f"{type(e).__name__}: {e}"
+                return None
+        return run
+
+    def error_plan(i):
+        return dict(kind="error", error=errors[i], spans=np.zeros(0, dtype=nat.PCM_SPAN_DTYPE), channels=0, sample_rate=0, total_frames=0)
     aac = [i for i, k in enumerate(kinds) if k == "aac"]
     with concurrent.futures.ThreadPoolExecutor(max_workers=threads or os.cpu_count()) as pool:
-        index = dict(zip(aac, pool.map(lambda i: adts_aac_index(files[i]), aac)))
+        index = dict(zip(aac, pool.map(guarded(lambda i: adts_aac_index(files[i])), aac)))
+        aac = [i for i in aac if i not in errors]
         starts, total = {}, 0
         for i in aac:
             starts[i] = total
@@ -239,7 +260,8 @@ def plan_files(files, threads=None, arena=None):
         take = arena.take if arena is not None else (lambda name, shape, dtype: np.zeros(shape, dtype=dtype))
         aac_units, aac_coeffs = take("aac_units", (total, 2), nat.AAC_UNIT_DTYPE), take("aac_coeffs", (total, 2, 1024), np.float32)
         vor = [i for i, k in enumerate(kinds) if k == "vorbis"]
-        vindex = dict(zip(vor, pool.map(lambda i: ogg_vorbis_index(files[i]), vor)))
+        vindex = dict(zip(vor, pool.map(guarded(lambda i: ogg_vorbis_index(files[i])), vor)))
+        vor = [i for i in vor if i not in errors]
         vstarts, vfloor, vtotal, nfl = {}, {}, 0, 0
         for i in vor:
             vstarts[i], vfloor[i] = vtotal, nfl
@@ -250,6 +272,8 @@ def plan_files(files, threads=None, arena=None):
         v_res = take("vorbis_residue", (vtotal, 2, vslot), np.float32)
 
         def plan(i):
+            if i in errors:
+                return error_plan(i)
             if kinds[i] == "vorbis":
                 a, n = vstarts[i], len(vindex[i]["table"])
                 p = ogg_vorbis_plan(files[i], index=vindex[i], out=(v_units[a:a + n], v_fy[a:a + n], v_res[a:a + n]), slot=vslot, floor_base=vfloor[i])
@@ -262,7 +286,18 @@ def plan_files(files, threads=None, arena=None):
             p = adts_aac_plan(files[i], index[i], out=(aac_units[a:a + n], aac_coeffs[a:a + n]))
             aac_units[a + len(p["units"]):a + n].view(np.uint8)[...] = 0   # refused packets: the unused tail holds valid (empty) records
             return dict(p, kind="aac", slice_start=a)
-        plans = list(pool.map(plan, range(len(files))))
+        plans = list(pool.map(guarded(plan), range(len(files))))
+    for i, p in enumerate(plans):
+        if p is None:  # failed in the plan stage: its slice of the batch arrays stays empty records, its front-end is released now
+            plans[i] = error_plan(i)
+            if kinds[i] == "vorbis" and i in vindex and vindex[i] is not None and hasattr(vindex[i].get("fe"), "close"):
+                vindex[i]["fe"].close()
+            if kinds[i] == "vorbis" and i in vstarts:
+                a, n = vstarts[i], len(vindex[i]["table"])
+                v_units[a:a + n].view(np.uint8)[...] = 0
+            if kinds[i] == "aac" and i in starts:
+                a, n = starts[i], len(index[i][0])
+                aac_units[a:a + n].view(np.uint8)[...] = 0
     batches = {}
     for kind in ("mp3", "mpa1", "mpa2", "aac", "vorbis"):
         members = [i for i, p in enumerate(plans) if p["kind"] == kind and len(p["spans"])]

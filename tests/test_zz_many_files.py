@@ -152,3 +152,31 @@ def test_many_files_on_the_device(oracle):
             for i, data in enumerate(files):
                 want = _alone(oracle, data, fmt)
                 assert got[i][0].shape == want.shape and (got[i][0].view(np.uint8) == want.view(np.uint8)).all(), i
+
+
+def test_one_bad_file_does_not_take_the_batch_down(oracle):
+    """Files that cannot be indexed or planned at all -- an Ogg stream that is not Vorbis, a native FLAC file, an ADTS stream with a
+    channel configuration the front-end does not take -- become error plans; every other file of the request renders as it does alone."""
+    good = _files()
+    rng = np.random.default_rng(99)
+    not_vorbis = b"".join(tv.st.ogg_paginate(9, [b"\x7fOpusHead" + bytes(11)], rng, eos=True))
+    flac = b"fLaC" + bytes(200)
+    aac6 = bytearray(ta._file(510, 44100, 2, n=3)[0])
+    for at in range(0, len(aac6) - 7):                      # every ADTS header: channel_configuration 2 -> 6
+        if aac6[at] == 0xFF and (aac6[at + 1] & 0xF6) == 0xF0 and ((aac6[at + 2] & 1) << 2 | aac6[at + 3] >> 6) == 2:
+            aac6[at + 2] = (aac6[at + 2] & 0xFE) | 1
+            aac6[at + 3] = (aac6[at + 3] & 0x3F) | (2 << 6)
+    files = [not_vorbis] + good[:5] + [flac] + good[5:] + [bytes(aac6)]
+    bad = {0, 6, len(files) - 1}
+    plans, batches = decode.plan_files(files, threads=4)
+    for i in bad:
+        assert plans[i]["kind"] == "error" and plans[i]["error"], i
+    assert sorted(i for b in batches.values() for i in b["members"]) == [i for i in range(len(files)) if i not in bad]
+    pcm = _render_batches(oracle, batches)
+    got = decode.pack_files(plans, batches, pcm, lambda p, sp, ch, f, total: _oracle.pcm_pack(oracle, p, sp, ch, f, total), nat.FMT_S16)
+    for i, data in enumerate(files):
+        if i in bad:
+            assert got[i][0].shape[0] == 0
+            continue
+        want = _alone(oracle, data, nat.FMT_S16)
+        assert got[i][0].shape == want.shape and (got[i][0].view(np.uint8) == want.view(np.uint8)).all(), (i, plans[i]["kind"])
