@@ -623,7 +623,6 @@ static int aac_tns_mode() { // 0 frames | 1 sorted | 2 inline
     return mode;
 }
 static bool aac_tns_inline() { return aac_tns_mode() == 2; }
-int aac_z_frames();
 int aac_launch_count(bool any_tns) { return !any_tns ? 1 : aac_tns_mode() == 0 ? 2 : aac_tns_mode() == 1 ? 4 : 1; }
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream) {
@@ -648,7 +647,7 @@ cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_c
     switch (aac_kernel_variant()) {
         case 1: return launch_variant<32, kAacKWarp, false>(b, stream);
         case 2:
-            switch (aac_z_frames()) { // frames per chunk of the Z kernel: 16 warps x 2 CTAs per SM (default), 10 x 3, 8 x 4
+            switch (b.z_frames) { // frames per chunk of the Z kernel: 16 warps x 2 CTAs per SM, 10 x 3, 8 x 4 (aac_chunk_frames_for)
                 case 9: return launch_variant<32, 9, true>(b, stream);
                 case 7: return launch_variant<32, 7, true>(b, stream);
                 default: return launch_variant<32, kAacKZ, true>(b, stream);
@@ -667,16 +666,23 @@ int aac_kernel_variant() {
     return mode;
 }
 bool aac_warp_per_frame() { return aac_kernel_variant() != 0; }
-// SYMGPU_AAC_Z_FRAMES = 15 (default) | 9 | 7: frames per chunk of the Z kernel, i.e. 16, 10 or 8 warps per CTA at 2, 3 or 4 CTAs per SM
-int aac_z_frames() {
-    static int k = -1;
-    if (k < 0) {
+// Frames per chunk of the Z kernel, i.e. 16, 10 or 8 warps per CTA at 2, 3 or 4 CTAs per SM.  Measured on one box: long runs
+// (8192 frames = 128 stream-channels x 128) 106 / 114 / 116 us with 15 / 9 / 7; short runs (the mixed corpus: 8-16 frames per
+// stream and call, a chunk plus its state slot fills 9 of the 16 warps) 1.166 / 1.115 / 1.130 ms per step.  So the plan takes 9
+// when the runs are short and 15 otherwise; SYMGPU_AAC_Z_FRAMES = 15 | 9 | 7 pins it.
+int aac_z_frames(uint32_t mean_run_frames) {
+    static int pinned = -1;
+    if (pinned < 0) {
         const char* env = getenv("SYMGPU_AAC_Z_FRAMES");
-        const int v = env ? atoi(env) : kAacKZ;
-        k = (v == 9 || v == 7) ? v : kAacKZ;
+        const int v = env ? atoi(env) : 0;
+        pinned = (v == 15 || v == 9 || v == 7) ? v : 0;
     }
-    return k;
+    if (pinned) return pinned;
+    return mean_run_frames <= 24 ? 9 : kAacKZ;
 }
-int aac_chunk_frames() { return aac_kernel_variant() == 2 ? aac_z_frames() : aac_kernel_variant() == 1 ? kAacKWarp : kAacK; }
+int aac_chunk_frames_for(uint32_t mean_run_frames) {
+    return aac_kernel_variant() == 2 ? aac_z_frames(mean_run_frames) : aac_kernel_variant() == 1 ? kAacKWarp : kAacK;
+}
+int aac_chunk_frames() { return aac_chunk_frames_for(1u << 20); }
 
 } // namespace symgpu

@@ -29,7 +29,8 @@ constexpr int kAacDefaultVariant = 2;    // 0 pair | 1 warp | 2 z (SYMGPU_AAC_KE
 int aac_kernel_variant();
 int aac_launch_count(bool any_tns);        // kernels one aac_launch starts
 bool aac_warp_per_frame();
-int aac_chunk_frames();                 // frames per chunk of the variant in use
+int aac_chunk_frames();                 // frames per chunk of the variant in use (long runs)
+int aac_chunk_frames_for(uint32_t mean_run_frames); // ... for a batch whose runs hold that many frames on average
 
 constexpr int kVorbisStateFloats = 2 * 4096; // overlap of both channels, blocksize_1 <= 8192
 
@@ -43,6 +44,7 @@ struct AacArgs {
     uint32_t* tns_owner;        // [n_tns] channel-frame of each filter
     uint32_t n_tns;
     int n_chunks;               // filled in by aac_launch
+    int z_frames;               // frames per chunk the plan was made for (Z kernel: 15 | 9 | 7)
     int tns_inline;             // filled in by aac_launch: the Z kernel applies the filters itself (no pre-pass)
     int n_groups;               // filled in by aac_launch: group_first = (const uint32_t*)(chunks + n_chunks), n_groups + 1 entries
     float* pcm;

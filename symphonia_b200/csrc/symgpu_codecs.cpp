@@ -111,6 +111,11 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
     uint64_t covered = 0;
     const std::vector<unsigned char> key = chunk_key_of(0x41414300u, n_frames, ctx->n_aac_streams, runs, (size_t)n_runs * sizeof *runs);
     const bool reuse = key == ctx->chunk_key;
+    // frames per chunk: a function of the runs alone (so a cached plan stays valid), shorter chunks for short runs
+    uint64_t run_frames = 0, run_count = 0;
+    for (uint32_t r = 0; r < n_runs; ++r)
+        if (runs[r].n_frames) run_frames += runs[r].n_frames, ++run_count;
+    const int chunk_frames = aac_chunk_frames_for(run_count ? (uint32_t)(run_frames / run_count) : 1u);
     for (uint32_t r = 0; r < n_runs && !reuse; ++r) {
         const symgpu_aac_run& run = runs[r];
         const int n_ch = run.channels ? run.channels : 2;
@@ -120,7 +125,7 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
         if (run.stream >= ctx->n_aac_streams) return SYMGPU_ERR_LIMIT;
         covered += run.n_frames;
         for (int ch = 0; ch < n_ch; ++ch)
-            split_even(run.n_frames, (uint32_t)aac_chunk_frames(), [&](uint32_t lo, uint32_t hi, bool first, bool last) {
+            split_even(run.n_frames, (uint32_t)chunk_frames, [&](uint32_t lo, uint32_t hi, bool first, bool last) {
                 CodecChunk c{};
                 c.first = run.first_frame + lo;
                 c.stream = run.stream;
@@ -139,7 +144,7 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
         // group_first[g] .. group_first[g + 1] are the chunks of group g; the array travels behind the chunk list.
         const size_t n_chunks = chunks.size();
         std::vector<uint32_t> group_first;
-        const uint32_t cap_slots = (uint32_t)aac_chunk_frames() + 1;
+        const uint32_t cap_slots = (uint32_t)chunk_frames + 1;
         uint32_t used = cap_slots + 1; // forces the first chunk to open a group
         for (size_t i = 0; i < n_chunks; ++i) {
             const uint32_t need = (uint32_t)chunks[i].count + 1;
@@ -178,7 +183,7 @@ symgpu_status symgpu_aac_synth_dev(symgpu_ctx* ctx, const symgpu_aac_unit* units
         ctx->aac_tns_idx_cap = cap;
     }
     AacArgs a{units, tns, coeffs, ctx->d_aac_scratch, ctx->d_aac_scratch,
-              ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0, 0, 0,
+              ctx->d_aac_tns_idx, ctx->d_aac_tns_idx ? ctx->d_aac_tns_idx + ctx->aac_tns_idx_cap : nullptr, n_tns, 0, chunk_frames, 0, 0,
               pcm, ctx->d_chunks, ctx->d_aac_states, ctx->d_aac_gen, ctx->d_aac_gen + ctx->n_aac_streams, ctx->d_codec_tab};
     CU(ctx, aac_launch(a, n_frames * 2, n_tns != 0, ctx->cached_chunks, ctx->cached_groups, ctx->stream));
     ctx->launches += aac_launch_count(n_tns != 0);
