@@ -84,7 +84,7 @@ struct VorbisArgs {
 };
 
 cudaError_t aac_launch(const AacArgs& a, uint32_t n_units, bool any_tns, int n_chunks, int n_groups, cudaStream_t stream);
-cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream);
+cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, int n_slots, cudaStream_t stream);
 // Multichannel helpers (symgpu_vorbis_mc_*): inverse coupling over every step of a mapping (lib.rs:252-278), in place on
 // residue [n_packets][channels][slot]; and the (block flags, floor, do-not-decode) records of channel pair `pair`.
 cudaError_t vorbis_mc_decouple_launch(const symgpu_vorbis_unit_mc* units, const uint32_t* stream_of_packet, const symgpu_vorbis_stream_mc* streams,

@@ -372,7 +372,21 @@ static symgpu_status vorbis_synth_dev_impl(symgpu_ctx* ctx, const symgpu_vorbis_
     for (uint32_t r = 0; r < n_runs; ++r)
         if (runs[r].n_packets && reg(runs[r].stream) < ctx->n_vorbis_streams)
             max_bs1 = std::max(max_bs1, (int)ctx->h_vorbis_streams[reg(runs[r].stream)].bs1_exp);
-    const uint32_t per_chunk = (uint32_t)vorbis_slots_for(max_bs1) - 1; // one slot is the packet before the chunk
+    uint32_t per_chunk = (uint32_t)vorbis_slots_for(max_bs1) - 1; // one slot is the packet before the chunk
+    {
+        // Short runs (a stream that submits a few packets per call): cut every run into equal chunks and size the CTA for them --
+        // a run of 8 packets is two chunks of 4 in CTAs of 5 slots, not two chunks of 4 in CTAs of 8.  A function of the runs
+        // alone, so a cached plan stays valid.
+        uint64_t run_packets = 0, run_count = 0;
+        for (uint32_t r = 0; r < n_runs; ++r)
+            if (runs[r].n_packets) run_packets += runs[r].n_packets, ++run_count;
+        const uint32_t mean = run_count ? (uint32_t)(run_packets / run_count) : 0;
+        if (mean && mean <= 4 * per_chunk) {
+            const uint32_t pieces = (mean + per_chunk - 1) / per_chunk;
+            const uint32_t fit = (mean + pieces - 1) / pieces;
+            if (fit >= 1 && fit < per_chunk) per_chunk = fit;
+        }
+    }
     const std::vector<unsigned char> key = chunk_key_of(0x564f5200u + ctx->vorbis_cfg_epoch + (stream_add << 8) + (stream_mul << 12), n_packets, slot, runs,
                                                         (size_t)n_runs * sizeof *runs);
     const bool reuse = key == ctx->chunk_key;
@@ -405,7 +419,7 @@ static symgpu_status vorbis_synth_dev_impl(symgpu_ctx* ctx, const symgpu_vorbis_
     VorbisArgs a{units, floor_y, residue, pcm, ctx->d_chunks, ctx->d_vorbis_streams, ctx->d_vorbis_floors,
                  ctx->d_vorbis_floor_aux, ctx->n_vorbis_floors, slot, pkt_ch, ch_base, ctx->d_vorbis_states, ctx->d_vorbis_gen,
                  ctx->d_vorbis_gen + ctx->n_vorbis_streams, ctx->d_codec_tab};
-    CU(ctx, vorbis_launch(a, ctx->cached_chunks, max_bs1, ctx->stream));
+    CU(ctx, vorbis_launch(a, ctx->cached_chunks, max_bs1, (int)per_chunk + 1, ctx->stream));
     ctx->launches += 1;
     return SYMGPU_OK;
 }

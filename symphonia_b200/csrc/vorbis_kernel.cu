@@ -721,9 +721,11 @@ int vorbis_slots_for(int max_bs1_exp) {
     return n < 2 ? 2 : (n > 8 ? 8 : n);
 }
 
-cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, cudaStream_t stream) {
+// n_slots: packet slots per CTA the chunks were cut for (chunk packets + 1), at most vorbis_slots_for(max_bs1_exp); batches of
+// short runs use fewer, so that more (smaller) CTAs share an SM instead of leaving warps of a big one idle.
+cudaError_t vorbis_launch(const VorbisArgs& a, int n_chunks, int max_bs1_exp, int n_slots, cudaStream_t stream) {
     const int slot_smem = 1 << (max_bs1_exp - 1);
-    const int n_slots = vorbis_slots_for(max_bs1_exp);
+    if (n_slots < 2 || n_slots > vorbis_slots_for(max_bs1_exp)) n_slots = vorbis_slots_for(max_bs1_exp);
     if (vorbis_kernel_z()) {
         const size_t smem = 2 * vorbis_unit_bytes(slot_smem) * n_slots + vorbis_z_tab_bytes(slot_smem);
         static size_t configured = 0;
