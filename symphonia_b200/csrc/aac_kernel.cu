@@ -304,6 +304,10 @@ __global__ void __launch_bounds__(kTnsWarps * 32) aac_tns_apply(const symgpu_aac
 // frame f and of frame f-1 (the `delay` of the reference is a pure function of frame f-1's output).
 constexpr int kAacK = kAacChunkFrames;     // frames per chunk, two warps per frame (named barriers)
 constexpr int kAacKWarp = kAacChunkFramesWarp; // frames per chunk, ONE warp per frame (__syncwarp only)
+#ifndef SYMGPU_AAC_PRE_UNROLL
+#define SYMGPU_AAC_PRE_UNROLL 2
+#endif
+constexpr int kAacPreUnroll = SYMGPU_AAC_PRE_UNROLL; // pre-twiddle iterations (4 spectrum loads each) in flight per lane
 constexpr int kAacKZ = kAacChunkFramesZ;       // the same with frame slots in the Z layout
 struct alignas(16) AacFrameSmem {
     float out[2048];          // spectrum (first 1024 floats) until the pre-twiddle has consumed it, then pcm_long
@@ -483,9 +487,9 @@ __global__ void __launch_bounds__((K + 1) * GW, ZL ? (K >= 15 ? 2 : K >= 9 ? 3 :
                     return filtered ? __ldcg(q) : __ldg(q);
                 };
                 if (u.window_sequence != SYMGPU_AAC_EIGHT_SHORT)
-                    imdct_to_z_from<9>(pair_long, fs[slot].z, 1, ts.tw_long, ft, gt, 32, sync);
+                    imdct_to_z_from<9, kAacPreUnroll>(pair_long, fs[slot].z, 1, ts.tw_long, ft, gt, 32, sync);
                 else
-                    imdct_to_z_from<6>(pair_short, fs[slot].z, 8, ts.tw_short, ft, gt, 32, sync);
+                    imdct_to_z_from<6, kAacPreUnroll>(pair_short, fs[slot].z, 8, ts.tw_short, ft, gt, 32, sync);
             } else {
                 auto& me = fs[slot];
                 for (int i = gt; i < 256; i += GW) reinterpret_cast<float4*>(me.out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);

@@ -214,12 +214,13 @@ __device__ __forceinline__ void imdct_blocks(const float* spec, float* out, floa
 //
 // `pair(b, l)` returns the spectral lines (l, l + 1) of block b (l even): a plain load, or whatever produces the spectrum
 // (the Vorbis kernel multiplies floor and residue right here).  z: zpad_len(batch * 2^LOG2) float2 of shared memory.
-template <int LOG2, typename Pair, typename Sync>
+// UNROLL: pre-twiddle iterations whose loads are in flight together (2 when the pair functor is heavy, more for a plain load).
+template <int LOG2, int UNROLL = 2, typename Pair, typename Sync>
 __device__ __forceinline__ void imdct_to_z_from(Pair pair, float2* z, int batch, const float2* __restrict__ tw,
                                                 const FftTables* __restrict__ ft, int tid, int n_threads, Sync sync) {
     constexpr int n2 = 1 << LOG2, n = 2 * n2, n4 = n2 / 2;
     // FFT input i needs spec[2i] and spec[n-1-2i]; input n2-1-i needs spec[n-2-2i] and spec[2i+1]: the same two pairs.
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int e = tid; e < batch * n4; e += n_threads) {
         const int b = e >> (LOG2 - 1), i = e & (n4 - 1), i2 = n2 - 1 - i;
         const float2 lo = pair(b, 2 * i);

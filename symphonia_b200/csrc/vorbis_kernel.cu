@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(512) vorbis_synth_kernel(VorbisArgs a, int slo
     float2* z = reinterpret_cast<float2*>(reinterpret_cast<float*>(raw + grp * slot_bytes) + 4 * slot_smem);
     FloorPoints* pts = reinterpret_cast<FloorPoints*>(raw + (grp + 1) * slot_bytes - 2 * sizeof(FloorPoints));
 
-    if (threadIdx.x < 256) inv_db_s[threadIdx.x] = a.tab->vorbis_inverse_db[threadIdx.x];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) inv_db_s[i] = a.tab->vorbis_inverse_db[i]; // (a CTA may have fewer than 256 threads)
     __syncthreads();
     const CodecChunk ck = a.chunks[blockIdx.x];
     const symgpu_vorbis_stream cfg = a.streams[ck.stream];
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(512, 2) vorbis_synth_kernel_z(VorbisArgs a, in
         vz_bulk_g2s(tw1_s, reinterpret_cast<const float2*>(tab->vorbis_tw) + (n2_1 - 16), tw1_bytes, &tab_bar);
         if (tw0_bytes) vz_bulk_g2s(tw0_s, reinterpret_cast<const float2*>(tab->vorbis_tw) + (n2_0 - 16), tw0_bytes, &tab_bar);
     }
-    if (threadIdx.x < 256) inv_db_s[threadIdx.x] = a.tab->vorbis_inverse_db[threadIdx.x];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) inv_db_s[i] = a.tab->vorbis_inverse_db[i]; // (a CTA may have fewer than 256 threads)
     __syncthreads(); // also publishes the initialised mbarrier
     const int n_ch = cfg.channels;
     const uint32_t gen = a.gen[ck.stream];

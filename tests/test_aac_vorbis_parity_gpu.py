@@ -280,3 +280,17 @@ def test_vorbis_array_layout_kernel_matches_too():
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+def test_vorbis_small_ctas_in_a_fresh_process():
+    """Batches of very short runs get small CTAs (two packet slots = 128 threads for one-packet runs).  Shared memory keeps what an
+    earlier, larger launch of the same process left there, so a table that a small CTA fails to fill completely goes unnoticed
+    unless the small launch comes first: the one-packet cases run here in a process of their own."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", "test_vorbis_chunk_boundaries"],
+                       cwd=root, env=dict(os.environ), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
