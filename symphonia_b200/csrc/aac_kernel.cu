@@ -307,7 +307,8 @@ constexpr int kAacKWarp = kAacChunkFramesWarp; // frames per chunk, ONE warp per
 #ifndef SYMGPU_AAC_PRE_UNROLL
 #define SYMGPU_AAC_PRE_UNROLL 2
 #endif
-constexpr int kAacPreUnroll = SYMGPU_AAC_PRE_UNROLL; // pre-twiddle iterations (4 spectrum loads each) in flight per lane
+constexpr int kAacPreUnroll = SYMGPU_AAC_PRE_UNROLL; // pre-twiddle iterations (4 spectrum loads each) in flight per lane; 2 / 4 / 8
+                                                     // measured on one box: 105.9-106.2 us each (tools/r02_gpu_ab.sh) -- no effect
 constexpr int kAacKZ = kAacChunkFramesZ;       // the same with frame slots in the Z layout
 struct alignas(16) AacFrameSmem {
     float out[2048];          // spectrum (first 1024 floats) until the pre-twiddle has consumed it, then pcm_long
