@@ -58,7 +58,7 @@ __device__ __forceinline__ void tns_lines(float* col, int cnt, int m0, float (&h
     // compile time: no register moves between lines (the shifting form below spends ORDER of its ~3.3 ORDER instructions per
     // line on them).  Same operations on the same operands in the same order.
     constexpr int L = ORDER >= 4 ? ORDER : ORDER == 3 ? 6 : 4;
-#ifndef SYMGPU_TNS_NO_RING // (A/B switch of tools/r02_gpu_ab.sh)
+#ifndef SYMGPU_TNS_NO_RING // (A/B switch of tools/gpu_calls/r02_gpu_ab.sh)
     if (k + L <= cnt) {
         float c[ORDER];
 #pragma unroll
@@ -308,7 +308,7 @@ constexpr int kAacKWarp = kAacChunkFramesWarp; // frames per chunk, ONE warp per
 #define SYMGPU_AAC_PRE_UNROLL 2
 #endif
 constexpr int kAacPreUnroll = SYMGPU_AAC_PRE_UNROLL; // pre-twiddle iterations (4 spectrum loads each) in flight per lane; 2 / 4 / 8
-                                                     // measured on one box: 105.9-106.2 us each (tools/r02_gpu_ab.sh) -- no effect
+                                                     // measured on one box: 105.9-106.2 us each (tools/gpu_calls/r02_gpu_ab.sh) -- no effect
 constexpr int kAacKZ = kAacChunkFramesZ;       // the same with frame slots in the Z layout
 struct alignas(16) AacFrameSmem {
     float out[2048];          // spectrum (first 1024 floats) until the pre-twiddle has consumed it, then pcm_long

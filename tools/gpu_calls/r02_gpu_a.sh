@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call A: parity of the v2 MP3 kernel + every previously gated test, A/B bench v2 vs v1, ncu of v2.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02a}
 out=gpurun_out
 mkdir -p $out

@@ -1,6 +1,6 @@
 #!/bin/bash
 # same-box A/B: AAC pre-twiddle iterations in flight (2 / 4 / 8), then the Vorbis + many-files GPU tests
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 for v in 2 8 4 2; do
   make -C symphonia_b200/csrc -B EXTRA="-DSYMGPU_AAC_PRE_UNROLL=$v" > gpurun_out/r02ab_build.log 2>&1 || { tail -5 gpurun_out/r02ab_build.log; exit 1; }
   echo "== SYMGPU_AAC_PRE_UNROLL=$v"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call B: A/B of the v2 kernel variants; re-run of the two tests that failed in call A.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02b}
 out=gpurun_out
 mkdir -p $out

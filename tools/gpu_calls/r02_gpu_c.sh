@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call C: window-chain interleave variants + ncu of one of them
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02c}
 prof=${2:-12:9}
 out=gpurun_out

@@ -1,6 +1,6 @@
 #!/bin/bash
 # AAC kernel: one warp per frame (SYMGPU_AAC_KERNEL=warp) against two warps per frame.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02r_build.log 2>&1 || { tail -20 gpurun_out/r02r_build.log; exit 1; }
 for k in ${AAC_VARIANTS:-pair warp z}; do
   echo "== SYMGPU_AAC_KERNEL=$k"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # small host batches on the caller's pinned memory (one launch) against staged copies: parity + per-packet time
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02s_build.log 2>&1 || { tail -20 gpurun_out/r02s_build.log; exit 1; }
 timeout 600 python -m pytest tests/test_mp3_parity_gpu.py tests/test_cpp_host.py tests/test_abi_errors_gpu.py -m gpu -x -q 2>&1 | tail -3
 for z in default s; do

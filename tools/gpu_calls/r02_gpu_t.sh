@@ -1,6 +1,6 @@
 #!/bin/bash
 # Vorbis kernel: Z layout (one warp per packet-channel) against the 64-thread array layout
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02t_build.log 2>&1 || { tail -20 gpurun_out/r02t_build.log; exit 1; }
 for k in ${VORBIS_VARIANTS:-z pair}; do
   echo "== SYMGPU_VORBIS_KERNEL=$k"

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02v_build.log 2>&1 || { tail -20 gpurun_out/r02v_build.log; exit 1; }
 for cs in 2 1; do
   echo "== SYMGPU_COPY_STREAMS=$cs"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # AAC Z kernel: TNS on the frame's own warp against the three-kernel pre-pass
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02x_build.log 2>&1 || { tail -20 gpurun_out/r02x_build.log; exit 1; }
 for t in ${TNS_MODES:-frames sorted}; do
   echo "== SYMGPU_AAC_TNS=$t"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # AAC Z kernel: 16 warps x 2 CTAs per SM against 10 x 3 and 8 x 4 (same box)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02zk_build.log 2>&1 || { tail -20 gpurun_out/r02zk_build.log; exit 1; }
 for k in 15 9 7 15; do
   echo "== SYMGPU_AAC_Z_FRAMES=$k"
